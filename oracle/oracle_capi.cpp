@@ -1,0 +1,391 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+#include "oracle_capi.h"
+#include "vina_oracle.hpp"
+#include <cstring>
+
+using namespace vo;
+
+static Mat3 m3(const double* a)
+{
+  Mat3 m;
+  memcpy(m.d, a, sizeof(m.d));
+  return m;
+}
+static Vec3 v3(const double* a) { return V3(a[0], a[1], a[2]); }
+
+static void to_imust(const vo_state* s, IMUST& x)
+{
+  x.t = s->t;
+  x.R = m3(s->R);
+  x.p = v3(s->p);
+  x.v = v3(s->v);
+  x.bg = v3(s->bg);
+  x.ba = v3(s->ba);
+  x.g = v3(s->g);
+  memcpy(x.cov.d, s->cov, sizeof(x.cov.d));
+}
+static void from_imust(const IMUST& x, vo_state* s)
+{
+  s->t = x.t;
+  memcpy(s->R, x.R.d, sizeof(s->R));
+  memcpy(s->p, x.p.d, 24);
+  memcpy(s->v, x.v.d, 24);
+  memcpy(s->bg, x.bg.d, 24);
+  memcpy(s->ba, x.ba.d, 24);
+  memcpy(s->g, x.g.d, 24);
+  memcpy(s->cov, x.cov.d, sizeof(s->cov));
+}
+static Cloud to_cloud(const float* xyz4, int n)
+{
+  Cloud c(n);
+  for (int i = 0; i < n; i++)
+  {
+    c[i].x = xyz4[4 * i + 0];
+    c[i].y = xyz4[4 * i + 1];
+    c[i].z = xyz4[4 * i + 2];
+    c[i].curvature = xyz4[4 * i + 3];
+  }
+  return c;
+}
+static void from_cloud(const Cloud& c, float* xyz4)
+{
+  for (size_t i = 0; i < c.size(); i++)
+  {
+    xyz4[4 * i + 0] = c[i].x;
+    xyz4[4 * i + 1] = c[i].y;
+    xyz4[4 * i + 2] = c[i].z;
+    xyz4[4 * i + 3] = c[i].curvature;
+  }
+}
+static std::deque<ImuSample> to_imus(const double* imu7, int m)
+{
+  std::deque<ImuSample> d;
+  for (int i = 0; i < m; i++)
+  {
+    ImuSample s;
+    s.t = imu7[7 * i];
+    for (int k = 0; k < 3; k++)
+    {
+      s.gyr[k] = imu7[7 * i + 1 + k];
+      s.acc[k] = imu7[7 * i + 4 + k];
+    }
+    d.push_back(s);
+  }
+  return d;
+}
+
+extern "C" {
+
+void vo_eig3(const double A[9], double vals[3], double vecs[9])
+{
+  SelfAdjointEigen3 s(m3(A));
+  memcpy(vals, s.values.d, 24);
+  memcpy(vecs, s.vectors.d, 72);
+}
+void vo_inverse15(const double A[225], double out[225])
+{
+  Mat15 m;
+  memcpy(m.d, A, sizeof(m.d));
+  Mat15 r = inverse(m);
+  memcpy(out, r.d, sizeof(r.d));
+}
+void vo_exp(const double w[3], double R[9])
+{
+  Mat3 r = Exp(v3(w));
+  memcpy(R, r.d, 72);
+}
+void vo_exp_dt(const double w[3], double dt, double R[9])
+{
+  Mat3 r = Exp(v3(w), dt);
+  memcpy(R, r.d, 72);
+}
+void vo_log(const double R[9], double w[3])
+{
+  Vec3 r = Log(m3(R));
+  memcpy(w, r.d, 24);
+}
+void vo_var_init(int n, const float* xyz4, const double ext_R[9], const double ext_t[3], double dept_err,
+                 double beam_err, double* pnt, double* var)
+{
+  IMUST ext;
+  ext.R = m3(ext_R);
+  ext.p = v3(ext_t);
+  Cloud c = to_cloud(xyz4, n);
+  PVecPtr pptr(new PVec);
+  var_init(ext, c, pptr, dept_err, beam_err);
+  for (int i = 0; i < n; i++)
+  {
+    memcpy(pnt + 3 * (size_t)i, (*pptr)[i].pnt.d, 24);
+    memcpy(var + 9 * (size_t)i, (*pptr)[i].var.d, 72);
+  }
+}
+void vo_pvec_update(int n, const double* pnt, double* var, const double R[9], const double p[3],
+                    const double cov[225], double* pwld)
+{
+  IMUST x;
+  x.R = m3(R);
+  x.p = v3(p);
+  memcpy(x.cov.d, cov, sizeof(x.cov.d));
+  PVecPtr pptr(new PVec(n));
+  for (int i = 0; i < n; i++)
+  {
+    (*pptr)[i].pnt = v3(pnt + 3 * (size_t)i);
+    (*pptr)[i].var = m3(var + 9 * (size_t)i);
+  }
+  std::vector<Vec3> pw;
+  pvec_update(pptr, x, pw);
+  for (int i = 0; i < n; i++)
+  {
+    memcpy(var + 9 * (size_t)i, (*pptr)[i].var.d, 72);
+    memcpy(pwld + 3 * (size_t)i, pw[i].d, 24);
+  }
+}
+void vo_voxel_keys(int n, const double* pw, double voxel_size, int64_t* keys)
+{
+  for (int i = 0; i < n; i++)
+  {
+    VOXEL_LOC k = voxel_key(v3(pw + 3 * (size_t)i), voxel_size);
+    keys[3 * (size_t)i + 0] = k.x;
+    keys[3 * (size_t)i + 1] = k.y;
+    keys[3 * (size_t)i + 2] = k.z;
+  }
+}
+int vo_down_sampling_voxel(int n, const float* xyz4_in, double voxel_size, float* xyz4_out)
+{
+  Cloud c = to_cloud(xyz4_in, n);
+  down_sampling_voxel(c, voxel_size);
+  from_cloud(c, xyz4_out);
+  return (int)c.size();
+}
+
+void* vo_odom_create(const vo_config* cfg)
+{
+  Globals g;
+  g.voxel_size = cfg->voxel_size;
+  g.min_eigen_value = cfg->min_eigen_value;
+  for (int i = 0; i < 4; i++)
+  {
+    g.plane_eigen_value_thre[i] = 1.0 / cfg->plane_eigen_value_thre[i];  // node.cpp:256-259
+    g.min_point[i] = cfg->min_point[i];
+  }
+  g.max_layer = cfg->max_layer;
+  g.max_points = cfg->max_points;
+  g.win_size = cfg->win_size;
+  g.thread_num = cfg->thread_num;
+  g.dept_err = cfg->dept_err;
+  g.beam_err = cfg->beam_err;
+  g.down_size = cfg->down_size;
+  Odom* o = new Odom(g);
+  o->extrin_para.R = m3(cfg->ext_R);
+  o->extrin_para.p = v3(cfg->ext_t);
+  o->odom_ekf.Lid_rot_to_IMU = m3(cfg->ext_R);
+  o->odom_ekf.Lid_offset_to_IMU = v3(cfg->ext_t);
+  o->odom_ekf.cov_gyr = V3(cfg->cov_gyr, cfg->cov_gyr, cfg->cov_gyr);
+  o->odom_ekf.cov_acc = V3(cfg->cov_acc, cfg->cov_acc, cfg->cov_acc);
+  o->odom_ekf.cov_bias_gyr = V3(cfg->rdw_gyr, cfg->rdw_gyr, cfg->rdw_gyr);
+  o->odom_ekf.cov_bias_acc = V3(cfg->rdw_acc, cfg->rdw_acc, cfg->rdw_acc);
+  return o;
+}
+void vo_odom_destroy(void* h) { delete (Odom*)h; }
+void vo_odom_set_state(void* h, const vo_state* s) { to_imust(s, ((Odom*)h)->x_curr); }
+void vo_odom_get_state(void* h, vo_state* s) { from_imust(((Odom*)h)->x_curr, s); }
+void vo_odom_set_imu_anchor(void* h, double last_pcl_end_time, const double last_imu7[7], double scale_gravity)
+{
+  Odom* o = (Odom*)h;
+  o->odom_ekf.last_pcl_end_time = last_pcl_end_time;
+  o->odom_ekf.last_imu.t = last_imu7[0];
+  for (int k = 0; k < 3; k++)
+  {
+    o->odom_ekf.last_imu.gyr[k] = last_imu7[1 + k];
+    o->odom_ekf.last_imu.acc[k] = last_imu7[4 + k];
+  }
+  o->odom_ekf.scale_gravity = scale_gravity;
+}
+void vo_odom_bootstrap(void* h, const float* xyz4, int n, const vo_state* x_known)
+{
+  Odom* o = (Odom*)h;
+  Cloud c = to_cloud(xyz4, n);
+  IMUST x;
+  to_imust(x_known, x);
+  o->bootstrap(c, x);
+}
+int vo_odom_step(void* h, float* xyz4, int n, double pcl_beg_time, const double* imu7, int m, int iekf_on_full,
+                 int max_iter)
+{
+  Odom* o = (Odom*)h;
+  Cloud c = to_cloud(xyz4, n);
+  std::deque<ImuSample> imus = to_imus(imu7, m);
+  int r = o->step(c, pcl_beg_time, imus, iekf_on_full != 0, max_iter);
+  from_cloud(c, xyz4);
+  return r;
+}
+void vo_odom_stage_times(void* h, double t[4])
+{
+  Odom* o = (Odom*)h;
+  t[0] = o->t_odom;
+  t[1] = o->t_insert;
+  t[2] = o->t_recut;
+  t[3] = o->t_margi;
+}
+int vo_odom_last_iters(void* h) { return ((Odom*)h)->last_iters; }
+int vo_odom_last_down(void* h, float* xyz4, int cap)
+{
+  Odom* o = (Odom*)h;
+  int n = (int)o->last_down.size();
+  if (xyz4 && cap >= n) from_cloud(o->last_down, xyz4);
+  return n;
+}
+
+int vo_odom_propagate(void* h, double pcl_beg_time, double pcl_end_time, const double* imu7, int m)
+{
+  Odom* o = (Odom*)h;
+  o->odom_ekf.pcl_beg_time = pcl_beg_time;
+  o->odom_ekf.pcl_end_time = pcl_end_time;
+  std::deque<ImuSample> imus = to_imus(imu7, m);
+  return o->odom_ekf.propagate(o->x_curr, imus);
+}
+int vo_odom_imu_poses(void* h, double* poses22, int cap)
+{
+  Odom* o = (Odom*)h;
+  int n = (int)o->odom_ekf.imu_poses.size();
+  if (!poses22 || cap < n) return n;
+  for (int i = 0; i < n; i++)
+  {
+    IMUST& s = o->odom_ekf.imu_poses[i];
+    double* q = poses22 + 22 * (size_t)i;
+    q[0] = s.t;
+    memcpy(q + 1, s.R.d, 72);
+    memcpy(q + 10, s.p.d, 24);
+    memcpy(q + 13, s.v.d, 24);
+    memcpy(q + 16, s.bg.d, 24);  // angvel_avr
+    memcpy(q + 19, s.ba.d, 24);  // acc_imu
+  }
+  return n;
+}
+void vo_odom_deskew(void* h, float* xyz4, int n)
+{
+  Odom* o = (Odom*)h;
+  Cloud c = to_cloud(xyz4, n);
+  o->odom_ekf.deskew(o->x_curr, c);
+  from_cloud(c, xyz4);
+}
+void vo_odom_set_dump(void* h, int on) { ((Odom*)h)->dump_iters = on != 0; }
+int vo_odom_iekf(void* h, int n, const double* pnt, const double* var, int max_iter)
+{
+  Odom* o = (Odom*)h;
+  PVecPtr pptr(new PVec(n));
+  for (int i = 0; i < n; i++)
+  {
+    (*pptr)[i].pnt = v3(pnt + 3 * (size_t)i);
+    (*pptr)[i].var = m3(var + 9 * (size_t)i);
+  }
+  return o->LioStateEstimation(pptr, max_iter) ? 1 : 0;
+}
+int vo_odom_iter_dump(void* h, int it, double HTH[36], double HTz[6], double nnt[9], int32_t* match_num,
+                      int64_t* keys, int32_t* codes, uint8_t* flags, double* sigma, double R[9], double p[3])
+{
+  Odom* o = (Odom*)h;
+  if (it < 0 || it >= (int)o->iter_dumps.size()) return -1;
+  IekfIterDump& d = o->iter_dumps[it];
+  memcpy(HTH, d.HTH, sizeof(d.HTH));
+  memcpy(HTz, d.HTz, sizeof(d.HTz));
+  memcpy(nnt, d.nnt, sizeof(d.nnt));
+  *match_num = d.match_num;
+  if (keys) memcpy(keys, d.keys.data(), d.keys.size() * sizeof(int64_t));
+  if (codes) memcpy(codes, d.codes.data(), d.codes.size() * sizeof(int32_t));
+  if (flags) memcpy(flags, d.flags.data(), d.flags.size());
+  if (sigma) memcpy(sigma, d.sigma.data(), d.sigma.size() * sizeof(double));
+  memcpy(R, d.R, sizeof(d.R));
+  memcpy(p, d.p, sizeof(d.p));
+  return (int)d.flags.size();
+}
+void vo_odom_map_update(void* h, int n, const double* pnt, const double* var)
+{
+  Odom* o = (Odom*)h;
+  PVecPtr pptr(new PVec(n));
+  for (int i = 0; i < n; i++)
+  {
+    (*pptr)[i].pnt = v3(pnt + 3 * (size_t)i);
+    (*pptr)[i].var = m3(var + 9 * (size_t)i);
+  }
+  o->pwld.clear();
+  pvec_update(pptr, o->x_curr, o->pwld);
+  o->map_update(pptr);
+}
+
+static void count_nodes(OctoTree* n, int64_t& c)
+{
+  c++;
+  for (int i = 0; i < 8; i++)
+    if (n->leaves[i]) count_nodes(n->leaves[i], c);
+}
+int64_t vo_odom_map_count(void* h, int64_t* n_roots, int64_t* n_slide)
+{
+  Odom* o = (Odom*)h;
+  int64_t c = 0;
+  for (auto& kv : o->surf_map) count_nodes(kv.second, c);
+  if (n_roots) *n_roots = (int64_t)o->surf_map.size();
+  if (n_slide) *n_slide = (int64_t)o->surf_map_slide.size();
+  return c;
+}
+static void export_node(Odom* o, OctoTree* n, vo_node_record* out, int64_t cap, int64_t& c)
+{
+  if (c < cap)
+  {
+    vo_node_record& r = out[c];
+    memset(&r, 0, sizeof(r));
+    r.key[0] = n->root_key.x;
+    r.key[1] = n->root_key.y;
+    r.key[2] = n->root_key.z;
+    r.code = n->code();
+    r.layer = n->layer;
+    r.octo_state = n->octo_state;
+    r.isexist = n->isexist;
+    r.has_sw = n->sw != nullptr;
+    r.is_plane = n->plane.is_plane;
+    r.last_num = n->last_num;
+    r.opt_state = n->opt_state >= 0 ? 1 : 0;
+    r.N_add = n->pcr_add.N;
+    r.N_fix = n->pcr_fix.N;
+    r.n_point_fix = (int)n->point_fix.size();
+    if (n->sw)
+    {
+      for (int i = 0; i < o->G.win_size && i < 16; i++)
+      {
+        r.N_local[i] = n->sw->pcrs_local[o->G.mp[i]].N;
+        r.n_win_points += (int)n->sw->points[o->G.mp[i]].size();
+      }
+    }
+    memcpy(r.P_add, n->pcr_add.P.d, 72);
+    memcpy(r.v_add, n->pcr_add.v.d, 24);
+    memcpy(r.P_fix, n->pcr_fix.P.d, 72);
+    memcpy(r.v_fix, n->pcr_fix.v.d, 24);
+    memcpy(r.eig_value, n->eig_value.d, 24);
+    memcpy(r.eig_vector, n->eig_vector.d, 72);
+    memcpy(r.center, n->plane.center.d, 24);
+    memcpy(r.normal, n->plane.normal.d, 24);
+    memcpy(r.plane_var, n->plane.plane_var.d, 288);
+    r.radius = n->plane.radius;
+    memcpy(r.cov_add, n->cov_add.d, 648);
+    memcpy(r.voxel_center, n->voxel_center, 24);
+    r.quater_length = n->quater_length;
+  }
+  c++;
+  for (int i = 0; i < 8; i++)
+    if (n->leaves[i]) export_node(o, n->leaves[i], out, cap, c);
+}
+int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap)
+{
+  Odom* o = (Odom*)h;
+  int64_t c = 0;
+  for (auto& kv : o->surf_map) export_node(o, kv.second, out, cap, c);
+  return c;
+}
+int vo_odom_window(void* h, int* win_count, int* mp, int cap)
+{
+  Odom* o = (Odom*)h;
+  *win_count = o->win_count;
+  for (int i = 0; i < o->G.win_size && i < cap; i++) mp[i] = o->G.mp[i];
+  return o->G.win_size;
+}
+}

@@ -1,0 +1,97 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+ * Plain-C view of the CPU restatement so tests/ and bench.py's cpu_baseline
+ * leg can drive it through ctypes. Matrices are column-major (Eigen default).
+ */
+#ifndef VINA_ORACLE_CAPI_H
+#define VINA_ORACLE_CAPI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vo_config
+{
+  double voxel_size;
+  double min_eigen_value;
+  double plane_eigen_value_thre[4]; /* as in the yaml (NOT inverted); inverted on load like node.cpp:256-259 */
+  double min_point[4];
+  double dept_err, beam_err;
+  double down_size;
+  double ext_R[9]; /* Lid_rot_to_IMU, column-major */
+  double ext_t[3];
+  double cov_gyr, cov_acc, rdw_gyr, rdw_acc; /* Odometry.* (node.cpp:211-214) */
+  int32_t max_layer;
+  int32_t max_points;
+  int32_t win_size;
+  int32_t thread_num;
+} vo_config;
+
+typedef struct vo_state
+{
+  double t;
+  double R[9];
+  double p[3], v[3], bg[3], ba[3], g[3];
+  double cov[225];
+} vo_state;
+
+/* one octree node as exported for parity (interior nodes included) */
+typedef struct vo_node_record
+{
+  int64_t key[3];
+  int32_t code; /* layer | path<<2, path = child index per level, 3 bits each */
+  int32_t layer, octo_state, isexist, has_sw, is_plane, last_num, opt_state;
+  int32_t N_add, N_fix, n_point_fix, n_win_points;
+  int32_t N_local[16]; /* pcrs_local[mp[i]].N for frame ordinal i */
+  double P_add[9], v_add[3], P_fix[9], v_fix[3];
+  double eig_value[3], eig_vector[9];
+  double center[3], normal[3], plane_var[36], radius;
+  double cov_add[81];
+  double voxel_center[3], quater_length;
+} vo_node_record;
+
+/* ---- stateless pieces ---- */
+void vo_eig3(const double A[9], double vals[3], double vecs[9]);
+void vo_inverse15(const double A[225], double out[225]);
+void vo_exp(const double w[3], double R[9]);
+void vo_exp_dt(const double w[3], double dt, double R[9]);
+void vo_log(const double R[9], double w[3]);
+void vo_var_init(int n, const float* xyz4, const double ext_R[9], const double ext_t[3], double dept_err,
+                 double beam_err, double* pnt, double* var);
+void vo_pvec_update(int n, const double* pnt, double* var, const double R[9], const double p[3],
+                    const double cov[225], double* pwld);
+void vo_voxel_keys(int n, const double* pw, double voxel_size, int64_t* keys);
+int vo_down_sampling_voxel(int n, const float* xyz4_in, double voxel_size, float* xyz4_out);
+
+/* ---- per-sequence odometry (VINA_SLAM members of the per-scan loop) ---- */
+void* vo_odom_create(const vo_config* cfg);
+void vo_odom_destroy(void* h);
+void vo_odom_set_state(void* h, const vo_state* s);
+void vo_odom_get_state(void* h, vo_state* s);
+void vo_odom_set_imu_anchor(void* h, double last_pcl_end_time, const double last_imu7[7], double scale_gravity);
+void vo_odom_bootstrap(void* h, const float* xyz4, int n, const vo_state* x_known);
+/* full scan: xyz4 = (x,y,z,curvature) in/out (deskewed on return); imu7 = m x (t,gx,gy,gz,ax,ay,az) */
+int vo_odom_step(void* h, float* xyz4, int n, double pcl_beg_time, const double* imu7, int m, int iekf_on_full,
+                 int max_iter);
+void vo_odom_stage_times(void* h, double t[4]); /* odom(deskew+var+iekf+pvec_update), insert, recut, margi */
+int vo_odom_last_iters(void* h);
+int vo_odom_last_down(void* h, float* xyz4, int cap); /* the down-sampled cloud of the last step */
+
+/* stage-wise entries */
+int vo_odom_propagate(void* h, double pcl_beg_time, double pcl_end_time, const double* imu7, int m);
+int vo_odom_imu_poses(void* h, double* poses22, int cap); /* t,R(9),p,v,w,a per pose */
+void vo_odom_deskew(void* h, float* xyz4, int n);
+void vo_odom_set_dump(void* h, int on);
+/* IEKF on caller-provided pointVar arrays (pnt n x 3, var n x 9 column-major); returns "not degenerate" */
+int vo_odom_iekf(void* h, int n, const double* pnt, const double* var, int max_iter);
+int vo_odom_iter_dump(void* h, int it, double HTH[36], double HTz[6], double nnt[9], int32_t* match_num,
+                      int64_t* keys, int32_t* codes, uint8_t* flags, double* sigma, double R[9], double p[3]);
+/* map update on caller-provided world-var pointVar + pose already in x_curr */
+void vo_odom_map_update(void* h, int n, const double* pnt, const double* var);
+int64_t vo_odom_map_count(void* h, int64_t* n_roots, int64_t* n_slide);
+int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap);
+int vo_odom_window(void* h, int* win_count, int* mp, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

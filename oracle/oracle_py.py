@@ -1,0 +1,327 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+
+ctypes view of oracle/liboracle.so (strict IEEE build, the parity checker) and
+oracle/liboracle_fast.so (-O3 -ffast-math, the timed CPU baseline).  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class VoConfig(C.Structure):
+    _fields_ = [
+        ("voxel_size", C.c_double), ("min_eigen_value", C.c_double), ("plane_eigen_value_thre", C.c_double * 4),
+        ("min_point", C.c_double * 4), ("dept_err", C.c_double), ("beam_err", C.c_double), ("down_size", C.c_double),
+        ("ext_R", C.c_double * 9), ("ext_t", C.c_double * 3), ("cov_gyr", C.c_double), ("cov_acc", C.c_double),
+        ("rdw_gyr", C.c_double), ("rdw_acc", C.c_double), ("max_layer", C.c_int32), ("max_points", C.c_int32),
+        ("win_size", C.c_int32), ("thread_num", C.c_int32),
+    ]
+
+
+class VoState(C.Structure):
+    _fields_ = [
+        ("t", C.c_double), ("R", C.c_double * 9), ("p", C.c_double * 3), ("v", C.c_double * 3),
+        ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("g", C.c_double * 3), ("cov", C.c_double * 225),
+    ]
+
+
+NODE_DTYPE = np.dtype([
+    ("key", "<i8", 3), ("code", "<i4"), ("layer", "<i4"), ("octo_state", "<i4"), ("isexist", "<i4"),
+    ("has_sw", "<i4"), ("is_plane", "<i4"), ("last_num", "<i4"), ("opt_state", "<i4"), ("N_add", "<i4"),
+    ("N_fix", "<i4"), ("n_point_fix", "<i4"), ("n_win_points", "<i4"), ("N_local", "<i4", 16),
+    ("P_add", "<f8", 9), ("v_add", "<f8", 3), ("P_fix", "<f8", 9), ("v_fix", "<f8", 3), ("eig_value", "<f8", 3),
+    ("eig_vector", "<f8", 9), ("center", "<f8", 3), ("normal", "<f8", 3), ("plane_var", "<f8", 36),
+    ("radius", "<f8"), ("cov_add", "<f8", 81), ("voxel_center", "<f8", 3), ("quater_length", "<f8"),
+], align=True)
+
+
+def build(force: bool = False) -> None:
+    need = force or not all(os.path.exists(os.path.join(_HERE, f)) for f in ("liboracle.so", "liboracle_fast.so"))
+    if not need:
+        srcs = ["vina_oracle.cpp", "oracle_capi.cpp", "omat.hpp", "vina_oracle.hpp", "oracle_capi.h", "Makefile"]
+        so_t = min(os.path.getmtime(os.path.join(_HERE, f)) for f in ("liboracle.so", "liboracle_fast.so"))
+        need = any(os.path.getmtime(os.path.join(_HERE, s)) > so_t for s in srcs)
+    if need:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _dp(a):
+    return _ptr(a, C.c_double)
+
+
+def _fp(a):
+    return _ptr(a, C.c_float)
+
+
+_LIBS = {}
+
+
+def load(fast: bool = False):
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name in _LIBS:
+        return _LIBS[name]
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    lib.vo_odom_create.restype = C.c_void_p
+    lib.vo_odom_create.argtypes = [C.POINTER(VoConfig)]
+    for fn in ("vo_odom_destroy", "vo_odom_set_state", "vo_odom_get_state", "vo_odom_set_imu_anchor",
+               "vo_odom_bootstrap", "vo_odom_stage_times", "vo_odom_deskew", "vo_odom_set_dump",
+               "vo_odom_map_update"):
+        getattr(lib, fn).restype = None
+    lib.vo_odom_map_count.restype = C.c_int64
+    lib.vo_odom_map_export.restype = C.c_int64
+    _LIBS[name] = lib
+    return lib
+
+
+def make_config(cfg) -> VoConfig:
+    """cfg: vina_slam_b200.synth.SensorConfig (duck-typed)."""
+    c = VoConfig()
+    c.voxel_size = cfg.voxel_size
+    c.min_eigen_value = cfg.min_eigen_value
+    for i in range(4):
+        c.plane_eigen_value_thre[i] = cfg.plane_thre[i]
+        c.min_point[i] = (20, 20, 15, 10)[i]  # node.cpp:219
+    c.dept_err, c.beam_err, c.down_size = cfg.dept_err, cfg.beam_err, cfg.down_size
+    R = cfg.ext_R_colmajor()
+    for i in range(9):
+        c.ext_R[i] = R[i]
+    for i in range(3):
+        c.ext_t[i] = cfg.ext_t[i]
+    c.cov_gyr, c.cov_acc, c.rdw_gyr, c.rdw_acc = cfg.cov_gyr, cfg.cov_acc, cfg.rdw_gyr, cfg.rdw_acc
+    c.max_layer, c.max_points, c.win_size, c.thread_num = cfg.max_layer, cfg.max_points, cfg.win_size, cfg.thread_num
+    return c
+
+
+def make_state(R_rowmajor=None, p=None, v=None, t=0.0, cov=None, g=(0.0, 0.0, -9.8)) -> VoState:
+    s = VoState()
+    s.t = t
+    R = np.eye(3) if R_rowmajor is None else np.asarray(R_rowmajor, dtype=np.float64).reshape(3, 3)
+    Rc = R.T.reshape(-1)  # column-major
+    for i in range(9):
+        s.R[i] = Rc[i]
+    for i in range(3):
+        s.p[i] = 0.0 if p is None else float(p[i])
+        s.v[i] = 0.0 if v is None else float(v[i])
+        s.g[i] = g[i]
+    if cov is None:  # IMUST::setZero, types.hpp:101-112
+        cov = np.eye(15) * 1e-4
+        cov[9:, 9:] = np.eye(6) * 1e-5
+    cc = np.asarray(cov, dtype=np.float64).T.reshape(-1)
+    for i in range(225):
+        s.cov[i] = cc[i]
+    return s
+
+
+def state_arrays(s: VoState):
+    R = np.array(s.R[:]).reshape(3, 3).T  # back to row-major numpy
+    cov = np.array(s.cov[:]).reshape(15, 15).T
+    return dict(t=s.t, R=R, p=np.array(s.p[:]), v=np.array(s.v[:]), bg=np.array(s.bg[:]), ba=np.array(s.ba[:]),
+                g=np.array(s.g[:]), cov=cov)
+
+
+class Odom:
+    """One sequence's oracle context (vo::Odom)."""
+
+    def __init__(self, cfg, fast: bool = False):
+        self.lib = load(fast)
+        self.cfg = cfg
+        self._c = make_config(cfg)
+        self.h = C.c_void_p(self.lib.vo_odom_create(C.byref(self._c)))
+
+    def close(self):
+        if self.h:
+            self.lib.vo_odom_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, s: VoState):
+        self.lib.vo_odom_set_state(self.h, C.byref(s))
+
+    def get_state(self) -> VoState:
+        s = VoState()
+        self.lib.vo_odom_get_state(self.h, C.byref(s))
+        return s
+
+    def set_imu_anchor(self, last_end: float, last_imu7, scale_gravity: float = 1.0):
+        a = np.ascontiguousarray(last_imu7, dtype=np.float64)
+        self.lib.vo_odom_set_imu_anchor(self.h, C.c_double(last_end), _dp(a), C.c_double(scale_gravity))
+
+    def bootstrap(self, xyz4: np.ndarray, state: VoState):
+        a = np.ascontiguousarray(xyz4, dtype=np.float32)
+        self.lib.vo_odom_bootstrap(self.h, _fp(a), C.c_int(a.shape[0]), C.byref(state))
+
+    def step(self, xyz4: np.ndarray, beg_time: float, imu7: np.ndarray, iekf_on_full: bool = True, max_iter: int = 4):
+        a = np.ascontiguousarray(xyz4, dtype=np.float32).copy()
+        im = np.ascontiguousarray(imu7, dtype=np.float64)
+        r = self.lib.vo_odom_step(self.h, _fp(a), C.c_int(a.shape[0]), C.c_double(beg_time), _dp(im),
+                                  C.c_int(im.shape[0]), C.c_int(1 if iekf_on_full else 0), C.c_int(max_iter))
+        return r, a
+
+    def stage_times(self):
+        t = np.zeros(4)
+        self.lib.vo_odom_stage_times(self.h, _dp(t))
+        return t
+
+    def last_iters(self) -> int:
+        return self.lib.vo_odom_last_iters(self.h)
+
+    def last_down(self) -> np.ndarray:
+        n = self.lib.vo_odom_last_down(self.h, None, C.c_int(0))
+        a = np.zeros((n, 4), dtype=np.float32)
+        self.lib.vo_odom_last_down(self.h, _fp(a), C.c_int(n))
+        return a
+
+    def propagate(self, beg: float, end: float, imu7: np.ndarray) -> int:
+        im = np.ascontiguousarray(imu7, dtype=np.float64)
+        return self.lib.vo_odom_propagate(self.h, C.c_double(beg), C.c_double(end), _dp(im), C.c_int(im.shape[0]))
+
+    def imu_poses(self) -> np.ndarray:
+        n = self.lib.vo_odom_imu_poses(self.h, None, C.c_int(0))
+        a = np.zeros((n, 22))
+        self.lib.vo_odom_imu_poses(self.h, _dp(a), C.c_int(n))
+        return a
+
+    def deskew(self, xyz4: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(xyz4, dtype=np.float32).copy()
+        self.lib.vo_odom_deskew(self.h, _fp(a), C.c_int(a.shape[0]))
+        return a
+
+    def set_dump(self, on: bool):
+        self.lib.vo_odom_set_dump(self.h, C.c_int(1 if on else 0))
+
+    def iekf(self, pnt: np.ndarray, var: np.ndarray, max_iter: int = 4) -> int:
+        p = np.ascontiguousarray(pnt, dtype=np.float64)
+        v = np.ascontiguousarray(var, dtype=np.float64)
+        return self.lib.vo_odom_iekf(self.h, C.c_int(p.shape[0]), _dp(p), _dp(v), C.c_int(max_iter))
+
+    def iter_dump(self, it: int, n: int):
+        HTH, HTz, nnt = np.zeros(36), np.zeros(6), np.zeros(9)
+        mn = C.c_int32(0)
+        keys = np.zeros((n, 3), dtype=np.int64)
+        codes = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.uint8)
+        sigma = np.zeros(n)
+        R, p = np.zeros(9), np.zeros(3)
+        r = self.lib.vo_odom_iter_dump(self.h, C.c_int(it), _dp(HTH), _dp(HTz), _dp(nnt), C.byref(mn),
+                                       _ptr(keys, C.c_int64), _ptr(codes, C.c_int32), _ptr(flags, C.c_uint8),
+                                       _dp(sigma), _dp(R), _dp(p))
+        if r < 0:
+            return None
+        return dict(HTH=HTH.reshape(6, 6).T, HTz=HTz, nnt=nnt.reshape(3, 3).T, match_num=mn.value, keys=keys,
+                    codes=codes, flags=flags, sigma=sigma, R_col=R, p=p)
+
+    def map_update(self, pnt: np.ndarray, var: np.ndarray):
+        p = np.ascontiguousarray(pnt, dtype=np.float64)
+        v = np.ascontiguousarray(var, dtype=np.float64)
+        self.lib.vo_odom_map_update(self.h, C.c_int(p.shape[0]), _dp(p), _dp(v))
+
+    def map_count(self):
+        nr, ns = C.c_int64(0), C.c_int64(0)
+        n = self.lib.vo_odom_map_count(self.h, C.byref(nr), C.byref(ns))
+        return n, nr.value, ns.value
+
+    def map_export(self) -> np.ndarray:
+        n, _, _ = self.map_count()
+        out = np.zeros(n, dtype=NODE_DTYPE)
+        self.lib.vo_odom_map_export(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(n))
+        return out
+
+    def window(self):
+        wc = C.c_int(0)
+        mp = np.zeros(16, dtype=np.int32)
+        ws = self.lib.vo_odom_window(self.h, C.byref(wc), _ptr(mp, C.c_int), C.c_int(16))
+        return wc.value, mp[:ws].copy()
+
+
+# ---- stateless helpers -----------------------------------------------------
+def eig3(A: np.ndarray):
+    lib = load()
+    a = np.ascontiguousarray(np.asarray(A, dtype=np.float64).T.reshape(-1))
+    vals, vecs = np.zeros(3), np.zeros(9)
+    lib.vo_eig3(_dp(a), _dp(vals), _dp(vecs))
+    return vals, vecs.reshape(3, 3).T
+
+
+def inverse15(A: np.ndarray) -> np.ndarray:
+    lib = load()
+    a = np.ascontiguousarray(np.asarray(A, dtype=np.float64).T.reshape(-1))
+    out = np.zeros(225)
+    lib.vo_inverse15(_dp(a), _dp(out))
+    return out.reshape(15, 15).T
+
+
+def var_init(xyz4: np.ndarray, cfg):
+    lib = load()
+    a = np.ascontiguousarray(xyz4, dtype=np.float32)
+    n = a.shape[0]
+    pnt, var = np.zeros((n, 3)), np.zeros((n, 9))
+    R = cfg.ext_R_colmajor()
+    t = np.asarray(cfg.ext_t, dtype=np.float64)
+    lib.vo_var_init(C.c_int(n), _fp(a), _dp(R), _dp(t), C.c_double(cfg.dept_err), C.c_double(cfg.beam_err),
+                    _dp(pnt), _dp(var))
+    return pnt, var
+
+
+def pvec_update(pnt, var, R_col, p, cov_col):
+    lib = load()
+    pn = np.ascontiguousarray(pnt, dtype=np.float64)
+    vr = np.ascontiguousarray(var, dtype=np.float64).copy()
+    pw = np.zeros_like(pn)
+    lib.vo_pvec_update(C.c_int(pn.shape[0]), _dp(pn), _dp(vr), _dp(np.ascontiguousarray(R_col)),
+                       _dp(np.ascontiguousarray(p)), _dp(np.ascontiguousarray(cov_col)), _dp(pw))
+    return vr, pw
+
+
+def voxel_keys(pw: np.ndarray, voxel_size: float) -> np.ndarray:
+    lib = load()
+    a = np.ascontiguousarray(pw, dtype=np.float64)
+    k = np.zeros((a.shape[0], 3), dtype=np.int64)
+    lib.vo_voxel_keys(C.c_int(a.shape[0]), _dp(a), C.c_double(voxel_size), _ptr(k, C.c_int64))
+    return k
+
+
+def down_sampling_voxel(xyz4: np.ndarray, voxel_size: float) -> np.ndarray:
+    lib = load()
+    a = np.ascontiguousarray(xyz4, dtype=np.float32)
+    out = np.zeros_like(a)
+    n = lib.vo_down_sampling_voxel(C.c_int(a.shape[0]), _fp(a), C.c_double(voxel_size), _fp(out))
+    return out[:n].copy()
+
+
+def exp_so3(w, dt=None):
+    lib = load()
+    R = np.zeros(9)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    if dt is None:
+        lib.vo_exp(_dp(w), _dp(R))
+    else:
+        lib.vo_exp_dt(_dp(w), C.c_double(dt), _dp(R))
+    return R.reshape(3, 3).T
+
+
+def log_so3(R):
+    lib = load()
+    a = np.ascontiguousarray(np.asarray(R, dtype=np.float64).T.reshape(-1))
+    w = np.zeros(3)
+    lib.vo_log(_dp(a), _dp(w))
+    return w
