@@ -1,0 +1,217 @@
+/* vina_b200.h — C ABI of the B200-native per-scan hot path of VINA-SLAM.
+ *
+ * This is the drop-in boundary. The reference has no FFI
+ * layer: its "interface" is a handful of C++ functions with Eigen/PCL/STL
+ * arguments called from the single odometry thread. Each entry point below
+ * names the reference function it replaces (file:line under the reference
+ * tree); INTEGRATION.md shows the thin C++ adapters a maintainer adds on the
+ * reference side. POD only: no Eigen/STL/torch types cross the boundary.
+ * All 3x3 matrices are COLUMN-MAJOR (Eigen's default storage), so
+ * `Eigen::Matrix3d::data()` can be passed as is.
+ *
+ * Conventions
+ *  - every call returns an int: 0 = ok, negative = error (VINA_E_*); nothing
+ *    here ever calls exit() (the reference does, imu_ekf.cpp:19-24);
+ *    vina_last_error(ctx) gives the text.
+ *  - a ctx belongs to ONE caller thread (the odometry thread, node.cpp:437);
+ *    calls are ordered on the ctx's CUDA stream. Different ctxs are
+ *    independent (replicas / other GPUs).
+ *  - there is NO CPU fallback: without a CUDA device vina_ctx_create fails
+ *    with VINA_E_CUDA.
+ */
+#ifndef VINA_B200_H
+#define VINA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VINA_OK 0
+#define VINA_E_ARG -1      /* bad argument */
+#define VINA_E_CUDA -2     /* CUDA runtime error / no device */
+#define VINA_E_CAPACITY -3 /* a device pool (points, voxels, nodes, hash) is full */
+#define VINA_E_ORDER -4    /* scan not time-sorted (lidar_decoder.cpp:30 contract) */
+#define VINA_E_TIME -5     /* "LiDAR time regress" (imu_ekf.cpp:19-24) */
+#define VINA_E_STATE -6    /* call sequence error (e.g. accumulate before begin) */
+
+#define VINA_MAX_WIN 10   /* LocalBA.win_size of every reference yaml */
+#define VINA_MAX_POSES 96 /* IMU poses per scan (reference: ~20 @200 Hz, ~40 @400 Hz) */
+
+typedef struct vina_ctx vina_ctx;
+
+/* The reference's mutable globals (src/mapping/octree.cpp:67-75, node.cpp:38,
+ * 210-219, 256-259) plus device capacities. */
+typedef struct vina_config
+{
+  double voxel_size;                /* Odometry.voxel_size */
+  double min_eigen_value;           /* Odometry.min_eigen_value */
+  double plane_eigen_value_thre[4]; /* LocalBA.plane_eigen_value_thre AS IN THE YAML; inverted on load like node.cpp:256-259 */
+  double min_point[4];              /* {20,20,15,10}, node.cpp:219 */
+  double dept_err, beam_err;        /* Odometry.dept_err / beam_err (deg) */
+  double down_size;                 /* Odometry.down_size */
+  double ext_R[9];                  /* Lid_rot_to_IMU (column-major), ekf_imu.hpp:24 */
+  double ext_t[3];                  /* Lid_offset_to_IMU, ekf_imu.hpp:25 */
+  double cov_gyr, cov_acc, rdw_gyr, rdw_acc; /* Odometry.* noise, node.cpp:211-214 */
+  int32_t max_layer;                /* LocalBA.max_layer (<= 3) */
+  int32_t max_points;               /* 100, octree.cpp:70 */
+  int32_t win_size;                 /* LocalBA.win_size (<= VINA_MAX_WIN) */
+  int32_t thread_num;               /* LocalBA.thread_num: only the "fewer roots than threads" early-outs
+                                       (voxel_map.cpp:96-97, local_mapping.cpp:26-28,150-154) depend on it */
+  /* device capacities (0 = default) */
+  int32_t max_scan_points;          /* points per scan */
+  int32_t max_nodes;                /* octree nodes (roots + children) */
+  int32_t hash_capacity_log2;       /* open-addressing table slots = 2^this (>= 2x root voxels) */
+  int32_t device;                   /* CUDA device ordinal */
+  int64_t fix_pool_points;          /* capacity of the fixed-point pool (point_fix lists) */
+  int64_t win_pool_points;          /* capacity of EACH per-frame window arena (SlideWindow::points) */
+} vina_config;
+
+void vina_config_default(vina_config* cfg);
+
+/* IMUST as POD (include/vina_slam/core/types.hpp:43-54); R and cov column-major. */
+typedef struct vina_state
+{
+  double t;
+  double R[9];
+  double p[3], v[3], bg[3], ba[3], g[3];
+  double cov[225];
+} vina_state;
+
+/* one entry of IMUEKF::imu_poses (imu_ekf.cpp:62-63): offset time, pose,
+ * velocity, mean angular velocity and world acceleration of the interval. */
+typedef struct vina_imu_pose
+{
+  double t;
+  double R[9];
+  double p[3], v[3], w[3], a[3];
+} vina_imu_pose;
+
+typedef struct vina_pose
+{
+  double R[9];
+  double p[3];
+} vina_pose;
+
+/* one sensor_msgs::Imu: stamp (s), gyro, accel */
+typedef struct vina_imu
+{
+  double t;
+  double gyr[3];
+  double acc[3];
+} vina_imu;
+
+/* one octree node as exported for parity checks (same layout as the oracle's vo_node_record) */
+typedef struct vina_node_record
+{
+  int64_t key[3];
+  int32_t code; /* layer | path<<2, path = child index per level, 3 bits each */
+  int32_t layer, octo_state, isexist, has_sw, is_plane, last_num, opt_state;
+  int32_t N_add, N_fix, n_point_fix, n_win_points;
+  int32_t N_local[16];
+  double P_add[9], v_add[3], P_fix[9], v_fix[3];
+  double eig_value[3], eig_vector[9];
+  double center[3], normal[3], plane_var[36], radius;
+  double cov_add[81];
+  double voxel_center[3], quater_length;
+} vina_node_record;
+
+/* per-stage device time of the last vina_odom_step / vina_map_update (ms, CUDA events) */
+typedef struct vina_timings
+{
+  float deskew_ms, downsample_ms, var_init_ms, iekf_ms, insert_ms, recut_ms, margi_ms, total_ms;
+  float iekf_kernel_ms; /* sum over iterations of the accumulate kernel alone */
+  int32_t iekf_iters;
+  int32_t kernel_launches;
+} vina_timings;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int vina_ctx_create(const vina_config* cfg, vina_ctx** out);
+void vina_ctx_destroy(vina_ctx* ctx);
+const char* vina_last_error(vina_ctx* ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the ctx's own */
+int vina_ctx_set_stream(vina_ctx* ctx, void* cuda_stream);
+int vina_ctx_sync(vina_ctx* ctx);
+
+/* ---- a2: deskew — replaces the per-point loop of IMUEKF::motion_blur
+ * (src/estimation/imu_ekf.cpp:114-144). xyzt = n x (x,y,z,curvature) float32,
+ * time-sorted (lidar_decoder.cpp:30). The scan stays resident on the device. */
+int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n);
+int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
+int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap); /* returns n or <0 */
+
+/* ---- f1: down_sampling_voxel (include/vina_slam/core/point_utils.hpp:7-44) on
+ * the device-resident scan, incl. the "<2000 points -> down_size/2" retry of
+ * local_mapping.cpp:396-403. vina_down_upload instead installs a caller-made
+ * down-sampled cloud (used by stage-wise parity tests). */
+int vina_downsample(vina_ctx* ctx);
+int vina_down_upload(vina_ctx* ctx, const float* xyzt, int n);
+int vina_down_download(vina_ctx* ctx, float* xyzt, int cap); /* returns n_d or <0 */
+
+/* ---- a3: var_init (src/core/point_utils.cpp:36-52). which: 0 = full scan, 1 = down-sampled */
+int vina_var_init(vina_ctx* ctx, int which);
+/* caller-provided pointVar arrays instead (pnt n x 3; var n x 9 column-major) */
+int vina_pvec_upload(vina_ctx* ctx, int which, const double* pnt, const double* var, int n);
+/* pnt n x 3, var n x 9 (symmetric storage expanded) */
+int vina_pvec_download(vina_ctx* ctx, int which, double* pnt, double* var, int cap);
+
+/* ---- a4-a6: one IEKF iteration of VINA_SLAM::LioStateEstimation's point loop
+ * (src/pipeline/odometry.cpp:98-148) incl. match() (src/mapping/voxel_map.cpp:241-266),
+ * OctoTree::match/inside (src/mapping/octree.cpp:551-595, 732-737).
+ * begin: fixes the prior covariance blocks (odometry.cpp:105-106) and resets the
+ * per-point leaf cache (odometry.cpp:79). accumulate: sums for state (R,p);
+ * HTH 6x6 column-major, HTz 6, nnt 3x3 column-major. */
+int vina_iekf_begin(vina_ctx* ctx, int which, const double rot_var[9], const double tsl_var[9]);
+int vina_iekf_accumulate(vina_ctx* ctx, const double R[9], const double p[3], double HTH[36], double HTz[6],
+                         double nnt[9], int32_t* match_num);
+/* same sums, and additionally records the per-point association for vina_iekf_debug_assoc */
+int vina_iekf_accumulate_debug(vina_ctx* ctx, const double R[9], const double p[3], double HTH[36], double HTz[6],
+                               double nnt[9], int32_t* match_num);
+/* association of the last accumulate_debug: keys n x 3, leaf code (-1 = none), flag, sigma_d */
+int vina_iekf_debug_assoc(vina_ctx* ctx, int64_t* keys, int32_t* codes, uint8_t* flags, double* sigma, int cap);
+
+/* ---- a8-a12: pvec_update + cut_voxel_multi + multi_recut + multi_margi
+ * (src/core/point_utils.cpp:54-65; src/mapping/voxel_map.cpp:47-135;
+ * src/mapping/octree.cpp:151-177, 203-228, 335-495; src/pipeline/local_mapping.cpp:17-84, 144-201).
+ * insert works on the down-sampled device pointVar set; win_ord = win_count-1 is the frame ordinal. */
+int vina_map_insert(vina_ctx* ctx, int win_ord, const double R[9], const double p[3], const double cov_rot[9],
+                    const double cov_tsl[9]);
+int vina_map_recut(vina_ctx* ctx, int win_count, const vina_pose* x_buf);
+int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_buf);
+/* rotate the ring map mp[] after a marginalisation (local_mapping.cpp:521-526) */
+int vina_map_shift_window(vina_ctx* ctx);
+int64_t vina_map_count(vina_ctx* ctx, int64_t* n_roots, int64_t* n_slide);
+int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t cap);
+
+/* ---- the per-scan loop body (src/pipeline/local_mapping.cpp:389-546), host
+ * orchestration in C++ inside the library: a1 IMU propagation on the host
+ * (imu_ekf.cpp:33-94), kernels for a2-a6/a8-a12, a7 solve on the host
+ * (odometry.cpp:192-230). */
+int vina_odom_set_state(vina_ctx* ctx, const vina_state* s);
+int vina_odom_get_state(vina_ctx* ctx, vina_state* s);
+int vina_odom_set_imu_anchor(vina_ctx* ctx, double last_pcl_end_time, const vina_imu* last_imu, double scale_gravity);
+/* harness bootstrap (replaces initialization()): an already
+ * deskewed scan at a known state -> downsample, var_init, map update */
+int vina_odom_bootstrap(vina_ctx* ctx, const float* xyzt, int n, const vina_state* x_known);
+/* one scan from HOST buffers. iekf_on_full: IEKF on the un-downsampled scan
+ * (production, local_mapping.cpp:413) or the down-sampled one (:412).
+ * max_iter <= 0: the reference's 20 (plain variant); 4 = the VNC_lio budget. */
+int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time, const vina_imu* imus, int m,
+                   int iekf_on_full, int max_iter, vina_state* x_out);
+/* same scan, but the raw points are already on the device (installed by
+ * vina_scan_upload): the timed "inputs resident in HBM" leg of bench.py */
+int vina_odom_step_resident(vina_ctx* ctx, double pcl_beg_time, const vina_imu* imus, int m, int iekf_on_full,
+                            int max_iter, vina_state* x_out);
+/* stage-wise pieces of the step, for parity tests */
+int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
+                        vina_imu_pose* poses_out, int cap); /* returns #poses */
+int vina_odom_iekf(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate);
+int vina_odom_map_update(vina_ctx* ctx); /* pvec_update + insert + recut + (margi + shift) with x_curr */
+int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap);
+int vina_get_timings(vina_ctx* ctx, vina_timings* t);
+/* record per-stage CUDA-event timings (adds event records + one sync per step) */
+int vina_set_profiling(vina_ctx* ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

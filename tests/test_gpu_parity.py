@@ -1,0 +1,275 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): voxel keys and point-to-voxel associations bit-exact; H/b within 1e-4
+relative; trajectory within 1 mm / 0.01 deg. Tighter bars are asserted where the design guarantees them
+(bit-exact body points, cluster sums, eigen-decompositions and plane decisions).
+"""
+import numpy as np
+import pytest
+
+from helpers import SMALL_CAPS, bootstrap_pair, col, cov_blocks, rel_err, small_cfg, sort_nodes, ulp_diff_f32
+from vina_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ctx_create_and_empty_map(gpu_lib):
+    cfg = small_cfg()
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    n, nr, ns = gx.map_count()
+    assert (n, nr, ns) == (0, 0, 0)
+    gx.close()
+
+
+def test_var_init_bit_exact(oracle_lib, gpu_lib):
+    """a3: body point and the upper triangle of the body covariance, bit for bit (incl. the z == 0 mutation)."""
+    for base in ("robosense128", "velodyne32", "mid360"):
+        cfg = small_cfg(base, 16, 500) if base != "mid360" else synth.small_sensor(base, 1, 8000)
+        seq = synth.Sequence(cfg)
+        sc = seq.next_scan(deskewed=True)
+        xyzt = sc.xyzt.copy()
+        xyzt[5, 2] = 0.0  # calcBodyVar's pb[2] == 0 branch (point_utils.cpp:5-8)
+        pnt_o, var_o = oracle_lib.var_init(xyzt, cfg)
+        gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+        gx.down_upload(xyzt)
+        gx.var_init(1)
+        pnt_g, var_g = gx.pvec_download(1, xyzt.shape[0])
+        assert np.array_equal(pnt_g, pnt_o)
+        for (i, j) in ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)):
+            assert np.array_equal(var_g[:, i + 3 * j], var_o[:, i + 3 * j]), (base, i, j)
+        gx.close()
+
+
+def test_imu_propagation_and_deskew(oracle_lib, gpu_lib):
+    """a1 (host) within 1e-12; a2 deskewed float32 xyz within 1 ulp and >= 99.99 % bit-equal
+    (device sin/cos vs glibc differ in the last ulp of a double now and then)."""
+    cfg = small_cfg()
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, n_boot=2)
+    sc = seq.next_scan()
+    end = sc.beg_time + float(sc.xyzt[-1, 3])
+    st = oracle_lib.make_state(last.gt_R, last.gt_p, last.gt_v, t=last.end_time)
+    od.set_state(st)
+    gx.set_state(gpu_lib.make_state(last.gt_R, last.gt_p, last.gt_v, t=last.end_time))
+    assert od.propagate(sc.beg_time, end, sc.imu) == 0
+    poses_o = od.imu_poses()
+    poses_g = gx.propagate(sc.beg_time, end, sc.imu)
+    assert poses_g.shape[0] == poses_o.shape[0] and poses_o.shape[0] >= 15
+    flat_g = np.concatenate([poses_g[k].reshape(len(poses_g), -1) for k in ("t", "R", "p", "v", "w", "a")], axis=1)
+    assert np.max(np.abs(flat_g - poses_o)) < 1e-12
+    so = oracle_lib.state_arrays(od.get_state())
+    sg = gpu_lib.state_arrays(gx.get_state())
+    assert np.max(np.abs(so["R"] - sg["R"])) < 1e-13 and np.max(np.abs(so["p"] - sg["p"])) < 1e-12
+    assert rel_err(sg["cov"], so["cov"]) < 1e-12
+    # deskew with the ORACLE's pose table on both sides
+    desk_o = od.deskew(sc.xyzt)
+    ps = np.zeros(poses_o.shape[0], dtype=gpu_lib.IMU_POSE_DTYPE)
+    ps["t"], ps["R"], ps["p"], ps["v"], ps["w"], ps["a"] = (poses_o[:, 0], poses_o[:, 1:10], poses_o[:, 10:13],
+                                                           poses_o[:, 13:16], poses_o[:, 16:19], poses_o[:, 19:22])
+    gx.scan_upload(sc.xyzt)
+    gx.deskew(ps, col(so["R"]), so["p"])
+    desk_g = gx.scan_download(sc.xyzt.shape[0])
+    assert np.array_equal(desk_g[:, 3], sc.xyzt[:, 3])
+    ulps = ulp_diff_f32(desk_g[:, :3], desk_o[:, :3])
+    assert ulps.max() <= 1
+    assert (ulps > 0).mean() < 1e-4
+    # points at or before the first pose stay untouched (imu_ekf.cpp:124)
+    head = sc.xyzt[:, 3] <= poses_o[0, 0]
+    assert np.array_equal(desk_g[head, :3], sc.xyzt[head, :3])
+    moved = np.abs(desk_o[:, :3] - sc.xyzt[:, :3]).max()
+    assert moved > 1e-3  # the scan really was distorted
+    gx.close()
+
+
+def test_deskew_rejects_unsorted_scan(oracle_lib, gpu_lib):
+    cfg = small_cfg()
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, n_boot=1)
+    sc = seq.next_scan()
+    bad = sc.xyzt.copy()
+    bad[[10, 2000]] = bad[[2000, 10]]
+    poses = gx.propagate(sc.beg_time, sc.end_time, sc.imu)
+    gx.scan_upload(bad)
+    s = gpu_lib.state_arrays(gx.get_state())
+    gx.deskew(poses, col(s["R"]), s["p"])
+    with pytest.raises(gpu_lib.VinaError) as ei:
+        gx.scan_download(bad.shape[0])
+    assert ei.value.code == -4
+    gx.close()
+
+
+def _iekf_compare(oracle_lib, gpu_lib, cfg, n_iter=4, world=None):
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, world=world)
+    sc = seq.next_scan(deskewed=True)
+    pnt, var = oracle_lib.var_init(sc.xyzt, cfg)
+    n = pnt.shape[0]
+    # start from a perturbed state so that several iterations and re-associations happen
+    R0 = sc.gt_R @ oracle_lib.exp_so3(np.array([0.004, -0.003, 0.005]))
+    p0 = sc.gt_p + np.array([0.03, -0.02, 0.015])
+    od.set_state(oracle_lib.make_state(R0, p0, sc.gt_v, t=sc.end_time))
+    od.set_dump(True)
+    od.iekf(pnt, var, n_iter)
+    iters = od.last_iters()
+    assert iters >= 2
+    cov = oracle_lib.state_arrays(oracle_lib.make_state())["cov"]
+    rot_var, tsl_var = cov_blocks(cov)
+    gx.pvec_upload(0, pnt, var)
+    gx.iekf_begin(0, rot_var, tsl_var)
+    total = 0
+    for it in range(iters):
+        d = od.iter_dump(it, n)
+        g = gx.iekf_accumulate(d["R_col"], d["p"], debug=True)
+        a = gx.iekf_debug_assoc(n)
+        assert np.array_equal(a["keys"], d["keys"]), f"voxel keys differ at iteration {it}"
+        assert np.array_equal(a["flags"], d["flags"]), f"match flags differ at iteration {it}"
+        assert np.array_equal(a["codes"], d["codes"]), f"associated leaves differ at iteration {it}"
+        assert g["match_num"] == d["match_num"] and d["match_num"] > 0.3 * n
+        m = d["flags"] > 0
+        assert rel_err(a["sigma"][m], d["sigma"][m]) < 1e-9
+        assert rel_err(g["HTH"], d["HTH"]) < 1e-4 and rel_err(g["HTz"], d["HTz"]) < 1e-4
+        assert rel_err(g["nnt"], d["nnt"]) < 1e-4
+        # the design is far tighter than the contract
+        assert rel_err(g["HTH"], d["HTH"]) < 1e-10 and rel_err(g["HTz"], d["HTz"]) < 1e-9
+        # same sums from the non-debug kernel
+        g2 = gx.iekf_accumulate(d["R_col"], d["p"], debug=False)
+        assert np.array_equal(g2["HTH"], g["HTH"]) and g2["match_num"] == g["match_num"]
+        total += d["match_num"]
+    gx.close()
+    return total
+
+
+def test_iekf_association_and_sums_robosense(oracle_lib, gpu_lib):
+    _iekf_compare(oracle_lib, gpu_lib, small_cfg("robosense128", 32, 600))
+
+
+def test_iekf_association_and_sums_velodyne_layer3(oracle_lib, gpu_lib):
+    _iekf_compare(oracle_lib, gpu_lib, small_cfg("velodyne32", 32, 500))
+
+
+def test_iekf_association_and_sums_mid360_negative_keys(oracle_lib, gpu_lib):
+    """voxel_size 0.5, non-repetitive pattern, world shifted so that keys are negative on all three axes."""
+    cfg = synth.small_sensor("mid360", 1, 12000)
+    total = _iekf_compare(oracle_lib, gpu_lib, cfg, world=synth.World(offset=(-70.0, -40.0, -9.5)))
+    assert total > 0
+
+
+def _compare_maps(mo, mg, exact_cov=False):
+    mo, mg = sort_nodes(mo), sort_nodes(mg)
+    assert mo.shape[0] == mg.shape[0], "different number of octree nodes"
+    for f in ("key", "code", "layer", "octo_state", "isexist", "has_sw", "is_plane", "last_num", "opt_state",
+              "N_add", "N_fix", "n_point_fix", "n_win_points", "N_local"):
+        assert np.array_equal(mo[f], mg[f]), f"map field {f} differs"
+    assert np.array_equal(mo["voxel_center"], mg["voxel_center"])
+    assert np.array_equal(mo["quater_length"], mg["quater_length"])
+    leaf = mo["octo_state"] == 0
+    # cluster sums: lower triangle + v, bit for bit (same summation order as the reference)
+    low = [0, 1, 2, 4, 5, 8]
+    for f in ("P_add", "P_fix"):
+        assert np.array_equal(mo[f][leaf][:, low], mg[f][leaf][:, low]), f"{f} differs"
+    assert np.array_equal(mo["v_add"][leaf], mg["v_add"][leaf])
+    assert np.array_equal(mo["v_fix"][leaf], mg["v_fix"][leaf])
+    # eigen-decomposition and plane parameters derived from them: bit for bit
+    assert np.array_equal(mo["eig_value"][leaf], mg["eig_value"][leaf])
+    assert np.array_equal(mo["eig_vector"][leaf], mg["eig_vector"][leaf])
+    assert np.array_equal(mo["center"], mg["center"]) and np.array_equal(mo["normal"], mg["normal"])
+    assert np.array_equal(mo["radius"], mg["radius"])
+    # covariance-derived quantities: the device stores point covariances symmetric -> tolerance
+    for f in ("cov_add", "plane_var"):
+        den = np.maximum(np.abs(mo[f]).max(axis=1, keepdims=True), 1e-300)
+        assert np.max(np.abs(mo[f] - mg[f]) / den) < 1e-9, f"{f} differs"
+    return mo, mg
+
+
+@pytest.mark.parametrize("base,beams,steps", [("robosense128", 32, 600), ("velodyne32", 32, 500)])
+def test_map_insert_recut_margi_parity(oracle_lib, gpu_lib, base, beams, steps):
+    """a8-a12 over bootstrap + sliding steps with identical inputs: the whole map state is compared."""
+    cfg = small_cfg(base, beams, steps)
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg)
+    mo, mg = _compare_maps(od.map_export(), gx.map_export())
+    assert mo.shape[0] > 2000 and (mo["is_plane"] > 0).sum() > 300 and (mo["octo_state"] == 1).sum() > 100
+    assert od.map_count()[2] == gx.map_count()[2]  # surf_map_slide size
+    # more scans with the window sliding (marginalisation each scan), same poses on both sides
+    for k in range(6):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.set_state(gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.down_upload(od.last_down())
+        gx.var_init(1)
+        gx.odom_map_update()
+    _compare_maps(od.map_export(), gx.map_export())
+    assert od.window()[0] == gx.window()[0] and np.array_equal(od.window()[1], gx.window()[1])
+    assert od.map_count()[2] == gx.map_count()[2]
+    gx.close()
+
+
+def test_insert_dropped_when_fewer_roots_than_threads(oracle_lib, gpu_lib):
+    """voxel_map.cpp:96-97: a scan touching fewer root voxels than thread_num is not inserted at all."""
+    cfg = small_cfg()
+    od = oracle_lib.Odom(cfg)
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    rng = np.random.default_rng(5)
+    pts = np.zeros((300, 4), dtype=np.float32)
+    pts[:, :3] = rng.uniform(0.1, 0.9, (300, 3)) + np.array([3.0, 3.0, 0.0])  # a single 1 m voxel ... plus 2 more
+    pts[100:200, 0] += 1.0
+    pts[200:, 1] += 1.0
+    st_o = oracle_lib.make_state(np.eye(3), np.zeros(3), np.zeros(3))
+    od.bootstrap(pts, st_o)
+    gx.set_state(gpu_lib.make_state(np.eye(3), np.zeros(3), np.zeros(3)))
+    gx.down_upload(od.last_down())
+    gx.var_init(1)
+    gx.odom_map_update()
+    mo, mg = sort_nodes(od.map_export()), sort_nodes(gx.map_export())
+    assert mo.shape[0] == mg.shape[0] == 3
+    assert (mo["N_add"] == 0).all() and (mg["N_add"] == 0).all()
+    assert np.array_equal(mo["isexist"], mg["isexist"]) and np.array_equal(mo["key"], mg["key"])
+    gx.close()
+
+
+def test_downsample_matches_reference_voxel_set(oracle_lib, gpu_lib):
+    """f1: same voxels and counts as the reference; means agree to fp32 rounding (order-dependent running
+    mean in the reference vs exact sum here)."""
+    cfg = small_cfg()
+    seq = synth.Sequence(cfg)
+    sc = seq.next_scan(deskewed=True)
+    ref = oracle_lib.down_sampling_voxel(sc.xyzt, cfg.down_size)
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    gx.scan_upload(sc.xyzt)
+    gx.downsample()
+    got = gx.down_download(sc.xyzt.shape[0])
+    assert got.shape[0] == ref.shape[0]
+
+    def keyed(a):
+        k = np.floor(a[:, :3].astype(np.float64) / cfg.down_size).astype(np.int64)
+        o = np.lexsort((k[:, 2], k[:, 1], k[:, 0]))
+        return k[o], a[o]
+
+    kr, r = keyed(ref)
+    kg, g = keyed(got)
+    assert np.array_equal(kr, kg)
+    assert np.array_equal(r[:, 3], g[:, 3])  # per-voxel point counts
+    assert np.max(np.abs(r[:, :3] - g[:, :3])) < 2e-5
+    # deterministic: voxels come out in order of their first point
+    gx.scan_upload(sc.xyzt)
+    gx.downsample()
+    again = gx.down_download(sc.xyzt.shape[0])
+    assert np.array_equal(again, got)
+    gx.close()
+
+
+def test_end_to_end_trajectory(oracle_lib, gpu_lib):
+    """Full path through vina_odom_step from host buffers vs the oracle's step: 1 mm / 0.01 deg."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, gpu_own_downsample=True)
+    worst_p, worst_r = 0.0, 0.0
+    for k in range(12):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        worst_p = max(worst_p, float(np.linalg.norm(sg["p"] - so["p"])))
+        worst_r = max(worst_r, synth.rot_err_deg(sg["R"], so["R"]))
+        # and both track the ground truth of the synthetic trajectory
+        assert np.linalg.norm(sg["p"] - sc.gt_p) < 0.02
+    gx.sync()
+    assert worst_p < 1e-3, worst_p
+    assert worst_r < 0.01, worst_r
+    gx.close()

@@ -1,0 +1,350 @@
+"""ctypes binding of libvina_b200.so (include/vina_b200.h) — the call a Python user makes.
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be
+checked on a CPU box), but creating a context without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvina_b200.so")
+
+VINA_MAX_WIN = 10
+
+
+class VinaConfig(C.Structure):
+    _fields_ = [
+        ("voxel_size", C.c_double), ("min_eigen_value", C.c_double), ("plane_eigen_value_thre", C.c_double * 4),
+        ("min_point", C.c_double * 4), ("dept_err", C.c_double), ("beam_err", C.c_double), ("down_size", C.c_double),
+        ("ext_R", C.c_double * 9), ("ext_t", C.c_double * 3), ("cov_gyr", C.c_double), ("cov_acc", C.c_double),
+        ("rdw_gyr", C.c_double), ("rdw_acc", C.c_double), ("max_layer", C.c_int32), ("max_points", C.c_int32),
+        ("win_size", C.c_int32), ("thread_num", C.c_int32), ("max_scan_points", C.c_int32), ("max_nodes", C.c_int32),
+        ("hash_capacity_log2", C.c_int32), ("device", C.c_int32), ("fix_pool_points", C.c_int64),
+        ("win_pool_points", C.c_int64),
+    ]
+
+
+class VinaState(C.Structure):
+    _fields_ = [
+        ("t", C.c_double), ("R", C.c_double * 9), ("p", C.c_double * 3), ("v", C.c_double * 3),
+        ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("g", C.c_double * 3), ("cov", C.c_double * 225),
+    ]
+
+
+class VinaTimings(C.Structure):
+    _fields_ = [
+        ("deskew_ms", C.c_float), ("downsample_ms", C.c_float), ("var_init_ms", C.c_float), ("iekf_ms", C.c_float),
+        ("insert_ms", C.c_float), ("recut_ms", C.c_float), ("margi_ms", C.c_float), ("total_ms", C.c_float),
+        ("iekf_kernel_ms", C.c_float), ("iekf_iters", C.c_int32), ("kernel_launches", C.c_int32),
+    ]
+
+
+IMU_DTYPE = np.dtype([("t", "<f8"), ("gyr", "<f8", 3), ("acc", "<f8", 3)])
+IMU_POSE_DTYPE = np.dtype([("t", "<f8"), ("R", "<f8", 9), ("p", "<f8", 3), ("v", "<f8", 3), ("w", "<f8", 3),
+                           ("a", "<f8", 3)])
+POSE_DTYPE = np.dtype([("R", "<f8", 9), ("p", "<f8", 3)])
+NODE_DTYPE = np.dtype([
+    ("key", "<i8", 3), ("code", "<i4"), ("layer", "<i4"), ("octo_state", "<i4"), ("isexist", "<i4"),
+    ("has_sw", "<i4"), ("is_plane", "<i4"), ("last_num", "<i4"), ("opt_state", "<i4"), ("N_add", "<i4"),
+    ("N_fix", "<i4"), ("n_point_fix", "<i4"), ("n_win_points", "<i4"), ("N_local", "<i4", 16),
+    ("P_add", "<f8", 9), ("v_add", "<f8", 3), ("P_fix", "<f8", 9), ("v_fix", "<f8", 3), ("eig_value", "<f8", 3),
+    ("eig_vector", "<f8", 9), ("center", "<f8", 3), ("normal", "<f8", 3), ("plane_var", "<f8", 36),
+    ("radius", "<f8"), ("cov_add", "<f8", 81), ("voxel_center", "<f8", 3), ("quater_length", "<f8"),
+], align=True)
+
+# every symbol include/vina_b200.h declares
+EXPORTS = [
+    "vina_config_default", "vina_ctx_create", "vina_ctx_destroy", "vina_last_error", "vina_ctx_set_stream",
+    "vina_ctx_sync", "vina_scan_upload", "vina_deskew", "vina_scan_download", "vina_downsample", "vina_down_upload",
+    "vina_down_download", "vina_var_init", "vina_pvec_upload", "vina_pvec_download", "vina_iekf_begin",
+    "vina_iekf_accumulate", "vina_iekf_accumulate_debug", "vina_iekf_debug_assoc", "vina_map_insert",
+    "vina_map_recut", "vina_map_margi", "vina_map_shift_window", "vina_map_count", "vina_map_export",
+    "vina_odom_set_state", "vina_odom_get_state", "vina_odom_set_imu_anchor", "vina_odom_bootstrap",
+    "vina_odom_step", "vina_odom_step_resident", "vina_odom_propagate", "vina_odom_iekf", "vina_odom_map_update",
+    "vina_odom_window", "vina_get_timings", "vina_set_profiling",
+]
+
+
+class VinaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vina_b200 error {code}: {msg}")
+        self.code = code
+
+
+_LIB = None
+
+
+def load():
+    """dlopen the in-tree library; fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m vina_slam_b200.build` (nvcc, sm_100a). "
+                          "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.vina_last_error.restype = C.c_char_p
+    lib.vina_ctx_destroy.restype = None
+    lib.vina_config_default.restype = None
+    lib.vina_map_count.restype = C.c_int64
+    lib.vina_map_export.restype = C.c_int64
+    _LIB = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def make_config(cfg, **caps) -> VinaConfig:
+    """cfg: synth.SensorConfig (duck-typed). caps override the device capacities."""
+    lib = load()
+    c = VinaConfig()
+    lib.vina_config_default(C.byref(c))
+    c.voxel_size = cfg.voxel_size
+    c.min_eigen_value = cfg.min_eigen_value
+    for i in range(4):
+        c.plane_eigen_value_thre[i] = cfg.plane_thre[i]
+        c.min_point[i] = (20, 20, 15, 10)[i]
+    c.dept_err, c.beam_err, c.down_size = cfg.dept_err, cfg.beam_err, cfg.down_size
+    R = cfg.ext_R_colmajor()
+    for i in range(9):
+        c.ext_R[i] = R[i]
+    for i in range(3):
+        c.ext_t[i] = cfg.ext_t[i]
+    c.cov_gyr, c.cov_acc, c.rdw_gyr, c.rdw_acc = cfg.cov_gyr, cfg.cov_acc, cfg.rdw_gyr, cfg.rdw_acc
+    c.max_layer, c.max_points, c.win_size, c.thread_num = cfg.max_layer, cfg.max_points, cfg.win_size, cfg.thread_num
+    for k, v in caps.items():
+        setattr(c, k, v)
+    return c
+
+
+def make_state(R_rowmajor=None, p=None, v=None, t=0.0, cov=None, g=(0.0, 0.0, -9.8)) -> VinaState:
+    s = VinaState()
+    s.t = t
+    R = np.eye(3) if R_rowmajor is None else np.asarray(R_rowmajor, dtype=np.float64).reshape(3, 3)
+    Rc = R.T.reshape(-1)
+    for i in range(9):
+        s.R[i] = Rc[i]
+    for i in range(3):
+        s.p[i] = 0.0 if p is None else float(p[i])
+        s.v[i] = 0.0 if v is None else float(v[i])
+        s.g[i] = g[i]
+    if cov is None:  # IMUST::setZero, types.hpp:101-112
+        cov = np.eye(15) * 1e-4
+        cov[9:, 9:] = np.eye(6) * 1e-5
+    cc = np.asarray(cov, dtype=np.float64).T.reshape(-1)
+    for i in range(225):
+        s.cov[i] = cc[i]
+    return s
+
+
+def state_arrays(s: VinaState):
+    return dict(t=s.t, R=np.array(s.R[:]).reshape(3, 3).T, p=np.array(s.p[:]), v=np.array(s.v[:]),
+                bg=np.array(s.bg[:]), ba=np.array(s.ba[:]), g=np.array(s.g[:]),
+                cov=np.array(s.cov[:]).reshape(15, 15).T)
+
+
+def imu_array(imu7: np.ndarray) -> np.ndarray:
+    a = np.zeros(imu7.shape[0], dtype=IMU_DTYPE)
+    a["t"] = imu7[:, 0]
+    a["gyr"] = imu7[:, 1:4]
+    a["acc"] = imu7[:, 4:7]
+    return a
+
+
+class Ctx:
+    """One sequence on one GPU (vina_ctx)."""
+
+    def __init__(self, cfg, **caps):
+        self.lib = load()
+        self.cfg = cfg
+        self._c = make_config(cfg, **caps)
+        h = C.c_void_p()
+        r = self.lib.vina_ctx_create(C.byref(self._c), C.byref(h))
+        self.h = h
+        if r != 0:
+            msg = self.lib.vina_last_error(h).decode() if h else "no CUDA device (there is no CPU fallback)"
+            if h:
+                self.lib.vina_ctx_destroy(h)
+            self.h = None
+            raise VinaError(r, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vina_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r):
+        if r < 0:
+            raise VinaError(int(r), self.lib.vina_last_error(self.h).decode())
+        return r
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self.lib.vina_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._ck(self.lib.vina_ctx_sync(self.h))
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.vina_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def timings(self) -> VinaTimings:
+        t = VinaTimings()
+        self._ck(self.lib.vina_get_timings(self.h, C.byref(t)))
+        return t
+
+    # ---- scan stages
+    def scan_upload(self, xyzt: np.ndarray):
+        a = np.ascontiguousarray(xyzt, dtype=np.float32)
+        self._keep = a
+        self._ck(self.lib.vina_scan_upload(self.h, _fp(a), C.c_int(a.shape[0])))
+        self.sync()
+
+    def deskew(self, poses: np.ndarray, R_end_col, p_end):
+        ps = np.ascontiguousarray(poses, dtype=IMU_POSE_DTYPE)
+        R = np.ascontiguousarray(R_end_col, dtype=np.float64)
+        p = np.ascontiguousarray(p_end, dtype=np.float64)
+        self._ck(self.lib.vina_deskew(self.h, ps.ctypes.data_as(C.c_void_p), C.c_int(ps.shape[0]), _dp(R), _dp(p)))
+
+    def scan_download(self, n: int) -> np.ndarray:
+        a = np.zeros((n, 4), dtype=np.float32)
+        k = self._ck(self.lib.vina_scan_download(self.h, _fp(a), C.c_int(n)))
+        return a[:k]
+
+    def downsample(self):
+        self._ck(self.lib.vina_downsample(self.h))
+
+    def down_upload(self, xyzt: np.ndarray):
+        a = np.ascontiguousarray(xyzt, dtype=np.float32)
+        self._ck(self.lib.vina_down_upload(self.h, _fp(a), C.c_int(a.shape[0])))
+        self.sync()
+
+    def down_download(self, cap: int) -> np.ndarray:
+        a = np.zeros((cap, 4), dtype=np.float32)
+        k = self._ck(self.lib.vina_down_download(self.h, _fp(a), C.c_int(cap)))
+        return a[:k]
+
+    def var_init(self, which: int):
+        self._ck(self.lib.vina_var_init(self.h, C.c_int(which)))
+
+    def pvec_upload(self, which: int, pnt: np.ndarray, var: np.ndarray):
+        p = np.ascontiguousarray(pnt, dtype=np.float64)
+        v = np.ascontiguousarray(var, dtype=np.float64)
+        self._ck(self.lib.vina_pvec_upload(self.h, C.c_int(which), _dp(p), _dp(v), C.c_int(p.shape[0])))
+
+    def pvec_download(self, which: int, cap: int):
+        p = np.zeros((cap, 3))
+        v = np.zeros((cap, 9))
+        k = self._ck(self.lib.vina_pvec_download(self.h, C.c_int(which), _dp(p), _dp(v), C.c_int(cap)))
+        return p[:k], v[:k]
+
+    # ---- IEKF
+    def iekf_begin(self, which: int, rot_var_col, tsl_var_col):
+        a = np.ascontiguousarray(rot_var_col, dtype=np.float64)
+        b = np.ascontiguousarray(tsl_var_col, dtype=np.float64)
+        self._ck(self.lib.vina_iekf_begin(self.h, C.c_int(which), _dp(a), _dp(b)))
+
+    def iekf_accumulate(self, R_col, p, debug: bool = False):
+        R = np.ascontiguousarray(R_col, dtype=np.float64)
+        pp = np.ascontiguousarray(p, dtype=np.float64)
+        HTH, HTz, nnt = np.zeros(36), np.zeros(6), np.zeros(9)
+        mn = C.c_int32(0)
+        fn = self.lib.vina_iekf_accumulate_debug if debug else self.lib.vina_iekf_accumulate
+        self._ck(fn(self.h, _dp(R), _dp(pp), _dp(HTH), _dp(HTz), _dp(nnt), C.byref(mn)))
+        return dict(HTH=HTH.reshape(6, 6).T, HTz=HTz, nnt=nnt.reshape(3, 3).T, match_num=mn.value)
+
+    def iekf_debug_assoc(self, n: int):
+        keys = np.zeros((n, 3), dtype=np.int64)
+        codes = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.uint8)
+        sigma = np.zeros(n)
+        self._ck(self.lib.vina_iekf_debug_assoc(self.h, keys.ctypes.data_as(C.c_void_p),
+                                                codes.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p),
+                                                _dp(sigma), C.c_int(n)))
+        return dict(keys=keys, codes=codes, flags=flags, sigma=sigma)
+
+    # ---- map
+    def map_count(self):
+        nr, ns = C.c_int64(0), C.c_int64(0)
+        n = self._ck(self.lib.vina_map_count(self.h, C.byref(nr), C.byref(ns)))
+        return int(n), nr.value, ns.value
+
+    def map_export(self) -> np.ndarray:
+        n, _, _ = self.map_count()
+        out = np.zeros(max(n, 1), dtype=NODE_DTYPE)
+        k = self._ck(self.lib.vina_map_export(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(out.shape[0])))
+        return out[:k]
+
+    # ---- odometry (host pipeline inside the library)
+    def set_state(self, s: VinaState):
+        self._ck(self.lib.vina_odom_set_state(self.h, C.byref(s)))
+
+    def get_state(self) -> VinaState:
+        s = VinaState()
+        self._ck(self.lib.vina_odom_get_state(self.h, C.byref(s)))
+        return s
+
+    def set_imu_anchor(self, last_end: float, last_imu7, scale_gravity: float = 1.0):
+        a = imu_array(np.asarray(last_imu7, dtype=np.float64).reshape(1, 7))
+        self._ck(self.lib.vina_odom_set_imu_anchor(self.h, C.c_double(last_end), a.ctypes.data_as(C.c_void_p),
+                                                   C.c_double(scale_gravity)))
+
+    def bootstrap(self, xyzt: np.ndarray, state: VinaState):
+        a = np.ascontiguousarray(xyzt, dtype=np.float32)
+        self._ck(self.lib.vina_odom_bootstrap(self.h, _fp(a), C.c_int(a.shape[0]), C.byref(state)))
+        self.sync()
+
+    def step(self, xyzt: np.ndarray, beg_time: float, imu7: np.ndarray, iekf_on_full: bool = True, max_iter: int = 4):
+        a = np.ascontiguousarray(xyzt, dtype=np.float32)
+        im = imu_array(np.asarray(imu7, dtype=np.float64))
+        out = VinaState()
+        self._ck(self.lib.vina_odom_step(self.h, _fp(a), C.c_int(a.shape[0]), C.c_double(beg_time),
+                                         im.ctypes.data_as(C.c_void_p), C.c_int(im.shape[0]),
+                                         C.c_int(1 if iekf_on_full else 0), C.c_int(max_iter), C.byref(out)))
+        return out
+
+    def step_resident(self, beg_time: float, imu7: np.ndarray, iekf_on_full: bool = True, max_iter: int = 4):
+        im = imu_array(np.asarray(imu7, dtype=np.float64))
+        out = VinaState()
+        self._ck(self.lib.vina_odom_step_resident(self.h, C.c_double(beg_time), im.ctypes.data_as(C.c_void_p),
+                                                  C.c_int(im.shape[0]), C.c_int(1 if iekf_on_full else 0),
+                                                  C.c_int(max_iter), C.byref(out)))
+        return out
+
+    def propagate(self, beg: float, end: float, imu7: np.ndarray) -> np.ndarray:
+        im = imu_array(np.asarray(imu7, dtype=np.float64))
+        poses = np.zeros(96, dtype=IMU_POSE_DTYPE)
+        k = self._ck(self.lib.vina_odom_propagate(self.h, C.c_double(beg), C.c_double(end),
+                                                  im.ctypes.data_as(C.c_void_p), C.c_int(im.shape[0]),
+                                                  poses.ctypes.data_as(C.c_void_p), C.c_int(96)))
+        return poses[:k]
+
+    def odom_iekf(self, which: int, max_iter: int):
+        it, ok = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.vina_odom_iekf(self.h, C.c_int(which), C.c_int(max_iter), C.byref(it), C.byref(ok)))
+        return it.value, ok.value
+
+    def odom_map_update(self):
+        self._ck(self.lib.vina_odom_map_update(self.h))
+
+    def window(self):
+        wc = C.c_int(0)
+        mp = np.zeros(16, dtype=np.int32)
+        ws = self._ck(self.lib.vina_odom_window(self.h, C.byref(wc), mp.ctypes.data_as(C.c_void_p), C.c_int(16)))
+        return wc.value, mp[:ws].copy()

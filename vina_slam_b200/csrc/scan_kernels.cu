@@ -1,0 +1,361 @@
+// Per-point scan kernels: deskew (a2), var_init (a3), down_sampling_voxel (f1).
+// This translation unit is compiled with -fmad=false: every expression keeps
+// the reference's operation order with one rounding per operation, so the
+// results can be compared bit-for-bit with the strict CPU restatement.
+#include "vn_kernels.cuh"
+
+// ---------------------------------------------------------------------------
+// a2 deskew: src/estimation/imu_ekf.cpp:114-144. The reference walks the
+// time-sorted scan backwards together with the IMU pose table; for sorted
+// input that is "pose k(i) = last k with t_k < curvature_i", found here by
+// binary search. Points with curvature <= t_0 are left untouched (:124).
+// Point 0 is re-compensated by every earlier pose as well, because the
+// reference's inner loop breaks at begin() without leaving the outer loop
+// (:139-142).
+__device__ __forceinline__ void exp_so3_dt(const double* w, double dt, double* E)
+{
+  double nrm = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  for (int i = 0; i < 9; i++) E[i] = 0.0;
+  E[0] = E[4] = E[8] = 1.0;
+  if (nrm > 1e-7)  // math.hpp:29
+  {
+    double ax[3] = { w[0] / nrm, w[1] / nrm, w[2] / nrm };
+    double K[9], KK[9], sK[9];
+    hat3(ax, K);
+    double r_ang = nrm * dt;
+    double s = sin(r_ang), c1 = 1.0 - cos(r_ang);
+    for (int i = 0; i < 9; i++) sK[i] = c1 * K[i];
+    // ((1-cos) K) K, coefficient sums left to right
+    for (int j = 0; j < 3; j++)
+      for (int i = 0; i < 3; i++)
+        KK[i + 3 * j] = sK[i] * K[3 * j] + sK[i + 3] * K[3 * j + 1] + sK[i + 6] * K[3 * j + 2];
+    for (int i = 0; i < 9; i++) E[i] = (E[i] + s * K[i]) + KK[i];
+  }
+}
+
+__device__ __forceinline__ void compensate(const DeskewPoses& P, int k, float curv, float* xyz)
+{
+  const vina_imu_pose& h = P.pose[k];
+  double dt = (double)curv - h.t;
+  double E[9], Ri[9];
+  exp_so3_dt(h.w, dt, E);
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++)
+      Ri[i + 3 * j] = h.R[i] * E[3 * j] + h.R[i + 3] * E[3 * j + 1] + h.R[i + 6] * E[3 * j + 2];
+  double T[3];
+  for (int i = 0; i < 3; i++) T[i] = ((h.p[i] + h.v[i] * dt) + ((0.5 * h.a[i]) * dt) * dt) - P.p_end[i];
+  double Pi[3] = { (double)xyz[0], (double)xyz[1], (double)xyz[2] };
+  double a[3], b[3], c[3], d[3];
+  for (int i = 0; i < 3; i++)
+    a[i] = ((P.ext_R[i] * Pi[0] + P.ext_R[i + 3] * Pi[1]) + P.ext_R[i + 6] * Pi[2]) + P.ext_t[i];
+  for (int i = 0; i < 3; i++) b[i] = ((Ri[i] * a[0] + Ri[i + 3] * a[1]) + Ri[i + 6] * a[2]) + T[i];
+  for (int i = 0; i < 3; i++)
+    c[i] = ((P.R_end[3 * i] * b[0] + P.R_end[3 * i + 1] * b[1]) + P.R_end[3 * i + 2] * b[2]) - P.ext_t[i];
+  for (int i = 0; i < 3; i++) d[i] = (P.ext_R[3 * i] * c[0] + P.ext_R[3 * i + 1] * c[1]) + P.ext_R[3 * i + 2] * c[2];
+  xyz[0] = (float)d[0];
+  xyz[1] = (float)d[1];
+  xyz[2] = (float)d[2];
+}
+
+__global__ void __launch_bounds__(256) k_deskew(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg,
+                                                int* __restrict__ status)
+{
+  __shared__ DeskewPoses P;
+  {
+    const int words = sizeof(DeskewPoses) / 4;
+    const int* src = reinterpret_cast<const int*>(Pg);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = pts[i];
+  // the contract of lidar_decoder.cpp:30: sorted by curvature
+  if (i + 1 < n && pts[i + 1].w < q.w) atomicOr(status, VN_ST_UNSORTED);
+  // k = last pose with t_k < curvature
+  int lo = 0, hi = P.m;  // first index with t >= curv
+  double cv = (double)q.w;
+  while (lo < hi)
+  {
+    int mid = (lo + hi) >> 1;
+    if (P.pose[mid].t < cv)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  int k = lo - 1;
+  if (k < 0) return;
+  float xyz[3] = { q.x, q.y, q.z };
+  compensate(P, k, q.w, xyz);
+  if (i == 0)
+    for (int kk = k - 1; kk >= 0; kk--) compensate(P, kk, q.w, xyz);
+  pts[i] = make_float4(xyz[0], xyz[1], xyz[2], q.w);
+}
+
+// ---------------------------------------------------------------------------
+// a3 var_init: src/core/point_utils.cpp:3-52 (calcBodyVar + extrinsic).
+__global__ void __launch_bounds__(256)
+    k_var_init(const float4* __restrict__ pts, const int* __restrict__ n_ptr, int n_host, ScanView out, VarInitParams prm)
+{
+  int n = n_ptr ? *n_ptr : n_host;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = pts[i];
+  double pb[3] = { (double)q.x, (double)q.y, (double)q.z };
+  if (pb[2] == 0) pb[2] = 0.0001;
+  float range = (float)sqrt(pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2]);
+  double rv = (double)prm.range_var;
+  double dv = prm.dir_var;
+  double d[3] = { pb[0], pb[1], pb[2] };
+  {
+    double z = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+    if (z > 0)
+    {
+      double s = sqrt(z);
+      d[0] = d[0] / s;
+      d[1] = d[1] / s;
+      d[2] = d[2] / s;
+    }
+  }
+  double dh[9];
+  hat3(d, dh);
+  double b1[3] = { 1.0, 1.0, -(d[0] + d[1]) / d[2] };
+  {
+    double z = (b1[0] * b1[0] + b1[1] * b1[1]) + b1[2] * b1[2];
+    if (z > 0)
+    {
+      double s = sqrt(z);
+      b1[0] = b1[0] / s;
+      b1[1] = b1[1] / s;
+      b1[2] = b1[2] / s;
+    }
+  }
+  double b2[3] = { b1[1] * d[2] - b1[2] * d[1], b1[2] * d[0] - b1[0] * d[2], b1[0] * d[1] - b1[1] * d[0] };
+  {
+    double z = (b2[0] * b2[0] + b2[1] * b2[1]) + b2[2] * b2[2];
+    if (z > 0)
+    {
+      double s = sqrt(z);
+      b2[0] = b2[0] / s;
+      b2[1] = b2[1] / s;
+      b2[2] = b2[2] / s;
+    }
+  }
+  // A = (range * direction_hat) * N, N = [b1 b2]
+  double rh[9];
+  for (int k = 0; k < 9; k++) rh[k] = (double)range * dh[k];
+  double A[6];  // column-major 3x2
+  for (int r = 0; r < 3; r++)
+  {
+    A[r] = (rh[r] * b1[0] + rh[r + 3] * b1[1]) + rh[r + 6] * b1[2];
+    A[r + 3] = (rh[r] * b2[0] + rh[r + 3] * b2[1]) + rh[r + 6] * b2[2];
+  }
+  // var = (d*rv)*d^T + (A*diag(dv,dv))*A^T
+  double AD[6];
+  for (int r = 0; r < 3; r++)
+  {
+    AD[r] = A[r] * dv + A[r + 3] * 0.0;
+    AD[r + 3] = A[r] * 0.0 + A[r + 3] * dv;
+  }
+  double var[9];
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++) var[r + 3 * c] = (d[r] * rv) * d[c] + (AD[r] * A[c] + AD[r + 3] * A[c + 3]);
+  // extrinsic: pnt = R_L pnt + t_L ; var = R_L var R_L^T
+  double pn[3];
+  for (int r = 0; r < 3; r++)
+    pn[r] = ((prm.ext_R[r] * pb[0] + prm.ext_R[r + 3] * pb[1]) + prm.ext_R[r + 6] * pb[2]) + prm.ext_t[r];
+  double T[9];
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++)
+      T[r + 3 * c] = (prm.ext_R[r] * var[3 * c] + prm.ext_R[r + 3] * var[3 * c + 1]) + prm.ext_R[r + 6] * var[3 * c + 2];
+  const int ui[6] = { 0, 0, 0, 1, 1, 2 }, uj[6] = { 0, 1, 2, 1, 2, 2 };
+  out.p[0][i] = pn[0];
+  out.p[1][i] = pn[1];
+  out.p[2][i] = pn[2];
+  for (int k = 0; k < 6; k++)
+  {
+    int r = ui[k], c = uj[k];
+    out.v[k][i] = (T[r] * prm.ext_R[c] + T[r + 3] * prm.ext_R[c + 3]) + T[r + 6] * prm.ext_R[c + 6];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// f1 down_sampling_voxel: include/vina_slam/core/point_utils.hpp:7-44.
+// The reference keeps an order-dependent fp32 running mean per voxel and emits
+// voxels in unordered_map order; here each voxel's mean is the fp64 sum of its
+// points (exact for float inputs, hence order-independent) divided by the count
+// and rounded to float, and voxels are emitted in order of their first point.
+// Same voxel set and counts as the reference; coordinates agree to fp32
+// rounding ("tolerance parity only").
+__global__ void __launch_bounds__(256)
+    k_down_accum(const float4* __restrict__ pts, int n, double voxel_size, DownSlot* __restrict__ tab, unsigned int mask,
+                 int* __restrict__ slot_of, int* __restrict__ status)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = pts[i];
+  const float data[3] = { q.x, q.y, q.z };
+  long long kc[3];
+  for (int j = 0; j < 3; j++)
+  {
+    float loc = (float)((double)data[j] / voxel_size);
+    if (loc < 0) loc = loc - 1.0f;
+    kc[j] = (long long)loc;
+  }
+  unsigned long long key;
+  if (!pack_key(kc[0], kc[1], kc[2], &key))
+  {
+    atomicOr(status, VN_ST_KEY_RANGE);
+    slot_of[i] = -1;
+    return;
+  }
+  unsigned int h = hash_key(key) & mask;
+  for (unsigned int probe = 0; probe <= mask; probe++)
+  {
+    unsigned long long old = tab[h].key;
+    if (old == VN_EMPTY_KEY) old = atomicCAS(&tab[h].key, VN_EMPTY_KEY, key);
+    if (old == VN_EMPTY_KEY || old == key)
+    {
+      atomicAdd(&tab[h].sum[0], (double)q.x);
+      atomicAdd(&tab[h].sum[1], (double)q.y);
+      atomicAdd(&tab[h].sum[2], (double)q.z);
+      atomicAdd(&tab[h].cnt, 1);
+      atomicMin(&tab[h].first, i);
+      slot_of[i] = (int)h;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+  atomicOr(status, VN_ST_DOWN_FULL);
+  slot_of[i] = -1;
+}
+
+// flag[i] = 1 when point i is the first point of its voxel
+__global__ void __launch_bounds__(256)
+    k_down_flag(int n, const DownSlot* __restrict__ tab, const int* __restrict__ slot_of, int* __restrict__ flag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = slot_of[i];
+  flag[i] = (s >= 0 && tab[s].first == i) ? 1 : 0;
+}
+
+// three-kernel exclusive scan over int flags (n <= 1024*1024)
+__global__ void __launch_bounds__(1024) k_scan_block(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                     int* __restrict__ block_sums)
+{
+  __shared__ int warp_sums[32];
+  int i = blockIdx.x * 1024 + threadIdx.x;
+  int v = (i < n) ? in[i] : 0;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[w] = x;
+  __syncthreads();
+  if (w == 0)
+  {
+    int s = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  int incl = x + (w > 0 ? warp_sums[w - 1] : 0);
+  if (i < n) out[i] = incl - v;
+  if (threadIdx.x == 1023) block_sums[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ block_sums, int nb, int* __restrict__ total)
+{
+  __shared__ int warp_sums[32];
+  int v = (threadIdx.x < nb) ? block_sums[threadIdx.x] : 0;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[w] = x;
+  __syncthreads();
+  if (w == 0)
+  {
+    int s = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  int incl = x + (w > 0 ? warp_sums[w - 1] : 0);
+  if (threadIdx.x < nb) block_sums[threadIdx.x] = incl - v;
+  if (threadIdx.x == 1023) *total = incl;
+}
+
+// emit voxel means in first-point order and clean the table slot for the next scan
+__global__ void __launch_bounds__(256)
+    k_down_emit(int n, DownSlot* __restrict__ tab, const int* __restrict__ slot_of, const int* __restrict__ flag,
+                const int* __restrict__ scan, const int* __restrict__ block_sums, float4* __restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!flag[i]) return;
+  int ord = scan[i] + block_sums[i >> 10];
+  DownSlot& s = tab[slot_of[i]];
+  double c = (double)s.cnt;
+  out[ord] = make_float4((float)(s.sum[0] / c), (float)(s.sum[1] / c), (float)(s.sum[2] / c), (float)s.cnt);
+  s.key = VN_EMPTY_KEY;
+  s.sum[0] = s.sum[1] = s.sum[2] = 0.0;
+  s.cnt = 0;
+  s.first = 0x7fffffff;
+}
+
+__global__ void k_down_init(DownSlot* tab, unsigned int nslots)
+{
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  tab[i].key = VN_EMPTY_KEY;
+  tab[i].sum[0] = tab[i].sum[1] = tab[i].sum[2] = 0.0;
+  tab[i].cnt = 0;
+  tab[i].first = 0x7fffffff;
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status)
+{
+  if (n <= 0) return;
+  k_deskew<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status);
+}
+void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n_host, ScanView out,
+                     const VarInitParams& prm)
+{
+  if (n_host <= 0) return;
+  k_var_init<<<(n_host + 255) / 256, 256, 0, st>>>(pts, n_dev, n_host, out, prm);
+}
+void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots)
+{
+  k_down_init<<<(nslots + 255) / 256, 256, 0, st>>>(tab, nslots);
+}
+int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
+                      int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status)
+{
+  if (n <= 0) return 0;
+  int nb = (n + 1023) / 1024;
+  if (nb > 1024) return -1;
+  k_down_accum<<<(n + 255) / 256, 256, 0, st>>>(pts, n, voxel_size, tab, mask, slot_of, status);
+  k_down_flag<<<(n + 255) / 256, 256, 0, st>>>(n, tab, slot_of, flag);
+  k_scan_block<<<nb, 1024, 0, st>>>(flag, scan, n, block_sums);
+  k_scan_sums<<<1, 1024, 0, st>>>(block_sums, nb, n_out_dev);
+  k_down_emit<<<(n + 255) / 256, 256, 0, st>>>(n, tab, slot_of, flag, scan, block_sums, out);
+  return 5;
+}

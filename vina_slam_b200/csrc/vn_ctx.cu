@@ -1,0 +1,681 @@
+// Context management and the low-level entry points of the C ABI
+// (include/vina_b200.h): memory pools in HBM, per-stage kernel launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "vn_ctx.h"
+
+#define CU(call)                                               \
+  do                                                           \
+  {                                                            \
+    int _r = vn_check_cuda(ctx, (call), #call);                \
+    if (_r) return _r;                                         \
+  } while (0)
+
+int vn_fail(vina_ctx* c, int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+int vn_check_cuda(vina_ctx* c, cudaError_t e, const char* what)
+{
+  if (e == cudaSuccess) return VINA_OK;
+  return vn_fail(c, VINA_E_CUDA, "CUDA error %s (%d) at %s", cudaGetErrorString(e), (int)e, what);
+}
+
+static int status_to_code(vina_ctx* ctx, int st)
+{
+  if (st == 0) return VINA_OK;
+  if (st & VN_ST_UNSORTED) return vn_fail(ctx, VINA_E_ORDER, "scan is not sorted by time offset (status 0x%x)", st);
+  if (st & VN_ST_SPIN) return vn_fail(ctx, VINA_E_CUDA, "device spin-wait limit hit (status 0x%x)", st);
+  return vn_fail(ctx, VINA_E_CAPACITY,
+                 "device pool exhausted or key out of range (status 0x%x: 1=hash 2=nodes 4=window arena 8=fixed pool "
+                 "16=key range 128=downsample table)",
+                 st);
+}
+
+int vn_check_status(vina_ctx* ctx)
+{
+  CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return status_to_code(ctx, *ctx->h_status);
+}
+
+extern "C" void vina_config_default(vina_config* c)
+{
+  memset(c, 0, sizeof(*c));
+  c->voxel_size = 1.0;
+  c->min_eigen_value = 0.0025;
+  for (int i = 0; i < 4; i++) c->plane_eigen_value_thre[i] = 1.0;
+  c->min_point[0] = 20;
+  c->min_point[1] = 20;
+  c->min_point[2] = 15;
+  c->min_point[3] = 10;
+  c->dept_err = 0.02;
+  c->beam_err = 0.05;
+  c->down_size = 0.1;
+  c->ext_R[0] = c->ext_R[4] = c->ext_R[8] = 1.0;
+  c->cov_gyr = 0.01;
+  c->cov_acc = 1.0;
+  c->rdw_gyr = 1e-4;
+  c->rdw_acc = 1e-4;
+  c->max_layer = 2;
+  c->max_points = 100;
+  c->win_size = 10;
+  c->thread_num = 5;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count, bool zero = true)
+{
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (zero) e = cudaMemset(*p, 0, count * sizeof(T));
+  return e;
+}
+
+extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
+{
+  if (!cfg_in || !out) return VINA_E_ARG;
+  *out = nullptr;
+  vina_ctx* ctx = new vina_ctx();
+  ctx->cfg = *cfg_in;
+  vina_config& cfg = ctx->cfg;
+  memset(&ctx->tm, 0, sizeof(ctx->tm));
+  memset(&ctx->map, 0, sizeof(ctx->map));
+  memset(&ctx->ins, 0, sizeof(ctx->ins));
+  memset(ctx->pv, 0, sizeof(ctx->pv));
+  if (cfg.win_size < 1 || cfg.win_size > VINA_MAX_WIN || cfg.max_layer < 0 || cfg.max_layer > 3 ||
+      cfg.voxel_size <= 0 || cfg.thread_num < 1)
+  {
+    delete ctx;
+    return VINA_E_ARG;
+  }
+  if (cfg.max_scan_points <= 0) cfg.max_scan_points = 300000;
+  if (cfg.max_nodes <= 0) cfg.max_nodes = 1 << 20;
+  if (cfg.hash_capacity_log2 <= 0) cfg.hash_capacity_log2 = 21;
+  if (cfg.fix_pool_points <= 0) cfg.fix_pool_points = 16ll << 20;
+  if (cfg.win_pool_points <= 0) cfg.win_pool_points = 4ll * cfg.max_scan_points;
+  if (cfg.max_points <= 0) cfg.max_points = 100;
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+  {
+    // no CPU fallback: the product path needs a CUDA device
+    fprintf(stderr, "vina_b200: no CUDA device (%s); there is no CPU fallback\n", cudaGetErrorString(e));
+    delete ctx;
+    return VINA_E_CUDA;
+  }
+  ctx->device = cfg.device;
+  *out = ctx;  // from here on errors keep the ctx so that vina_last_error works
+  CU(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  for (int i = 0; i < 16; i++) CU(cudaEventCreate(&ctx->ev[i]));
+
+  const int cap = cfg.max_scan_points;
+  ctx->cap_points = cap;
+  CU(dalloc(&ctx->d_scan, cap));
+  CU(dalloc(&ctx->d_down, cap));
+  CU(dalloc(&ctx->d_n_down, 1));
+  CU(cudaHostAlloc((void**)&ctx->h_n_down, sizeof(int), cudaHostAllocDefault));
+  for (int w = 0; w < 2; w++)
+  {
+    for (int k = 0; k < 3; k++) CU(dalloc(&ctx->pv[w].p[k], cap));
+    for (int k = 0; k < 6; k++) CU(dalloc(&ctx->pv[w].v[k], cap));
+  }
+  CU(dalloc(&ctx->d_cache, cap));
+  CU(dalloc(&ctx->d_poses, 1));
+  CU(cudaHostAlloc((void**)&ctx->h_poses, sizeof(DeskewPoses), cudaHostAllocDefault));
+  // down-sampling table: >= 2x points
+  unsigned int dslots = 1;
+  while (dslots < 2u * (unsigned)cap) dslots <<= 1;
+  ctx->dmask = dslots - 1;
+  CU(dalloc(&ctx->d_dtab, dslots, false));
+  CU(dalloc(&ctx->d_slot_of, cap));
+  CU(dalloc(&ctx->d_flag, cap));
+  CU(dalloc(&ctx->d_scanbuf, cap));
+  CU(dalloc(&ctx->d_block_sums, 1024));
+  launch_down_init(ctx->stream, ctx->d_dtab, dslots);
+  // IEKF
+  CU(dalloc(&ctx->d_partials, (size_t)ctx->sm_count * 8 * VN_IEKF_NACC));
+  CU(dalloc(&ctx->d_ticket, 1));
+  CU(cudaHostAlloc((void**)&ctx->h_result, 64 * sizeof(double), cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_result, ctx->h_result, 0));
+  memset(ctx->h_result, 0, 64 * sizeof(double));
+  CU(dalloc(&ctx->d_status, 1));
+  CU(cudaHostAlloc((void**)&ctx->h_status, sizeof(int), cudaHostAllocDefault));
+
+  // map
+  MapView& M = ctx->map;
+  ctx->hash_slots = 1u << cfg.hash_capacity_log2;
+  M.hmask = ctx->hash_slots - 1;
+  CU(dalloc(&M.slots, ctx->hash_slots, false));
+  M.max_nodes = cfg.max_nodes;
+  CU(dalloc(&M.hot, (size_t)cfg.max_nodes));
+  CU(dalloc(&M.cold, (size_t)cfg.max_nodes));
+  CU(dalloc(&M.node_count, 1));
+  CU(dalloc(&M.root_count, 1));
+  M.win_cap = cfg.win_pool_points;
+  for (int s = 0; s < cfg.win_size; s++) CU(dalloc(&M.win_pool[s], (size_t)cfg.win_pool_points, false));
+  CU(dalloc(&M.win_cursor, VINA_MAX_WIN));
+  M.fix_cap = cfg.fix_pool_points;
+  CU(dalloc(&M.fix_pool, (size_t)cfg.fix_pool_points, false));
+  M.fixseg_cap = (int)(cfg.fix_pool_points / 4 > (1 << 30) ? (1 << 30) : cfg.fix_pool_points / 4);
+  if (M.fixseg_cap < 1024) M.fixseg_cap = 1024;
+  CU(dalloc(&M.fix_segs, (size_t)M.fixseg_cap, false));
+  CU(dalloc(&M.fix_cursor, 1));
+  CU(dalloc(&M.fixseg_cursor, 1));
+  CU(dalloc(&M.slide_list[0], (size_t)cfg.max_nodes));
+  CU(dalloc(&M.slide_list[1], (size_t)cfg.max_nodes));
+  CU(dalloc(&M.slide_count, 2));
+  M.slide_cur = 0;
+  M.status = ctx->d_status;
+  M.voxel_size = cfg.voxel_size;
+  M.min_eigen_value = cfg.min_eigen_value;
+  for (int i = 0; i < 4; i++)
+  {
+    M.thre[i] = 1.0 / cfg.plane_eigen_value_thre[i];  // node.cpp:256-259
+    M.min_point[i] = cfg.min_point[i];
+  }
+  M.max_layer = cfg.max_layer;
+  M.max_points = cfg.max_points;
+  M.win_size = cfg.win_size;
+  M.thread_num = cfg.thread_num;
+  for (int i = 0; i < VINA_MAX_WIN; i++) M.mp[i] = i;  // node.cpp:431-435
+  launch_map_init(ctx->stream, M, ctx->hash_slots);
+
+  InsertScratch& S = ctx->ins;
+  for (int k = 0; k < 3; k++) CU(dalloc(&S.pw[k], cap));
+  for (int k = 0; k < 6; k++) CU(dalloc(&S.vw[k], cap));
+  CU(dalloc(&S.root_of, cap));
+  CU(dalloc(&S.leaf_of, cap));
+  CU(dalloc(&S.rank_of, cap));
+  CU(dalloc(&S.touched, cap));
+  CU(dalloc(&S.counters, 4));
+  CU(dalloc(&S.idx, cap));
+  S.stamp = 0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  return VINA_OK;
+}
+
+extern "C" void vina_ctx_destroy(vina_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->odom) odom_host_destroy(ctx->odom);
+  cudaFree(ctx->d_scan);
+  cudaFree(ctx->d_down);
+  cudaFree(ctx->d_n_down);
+  cudaFreeHost(ctx->h_n_down);
+  for (int w = 0; w < 2; w++)
+  {
+    for (int k = 0; k < 3; k++) cudaFree(ctx->pv[w].p[k]);
+    for (int k = 0; k < 6; k++) cudaFree(ctx->pv[w].v[k]);
+  }
+  cudaFree(ctx->d_cache);
+  cudaFree(ctx->d_poses);
+  cudaFreeHost(ctx->h_poses);
+  cudaFree(ctx->d_dtab);
+  cudaFree(ctx->d_slot_of);
+  cudaFree(ctx->d_flag);
+  cudaFree(ctx->d_scanbuf);
+  cudaFree(ctx->d_block_sums);
+  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_ticket);
+  cudaFreeHost(ctx->h_result);
+  cudaFree(ctx->d_status);
+  cudaFreeHost(ctx->h_status);
+  cudaFree(ctx->dbg.keys);
+  cudaFree(ctx->dbg.codes);
+  cudaFree(ctx->dbg.flags);
+  cudaFree(ctx->dbg.sigma);
+  MapView& M = ctx->map;
+  cudaFree(M.slots);
+  cudaFree(M.hot);
+  cudaFree(M.cold);
+  cudaFree(M.node_count);
+  cudaFree(M.root_count);
+  for (int s = 0; s < VINA_MAX_WIN; s++) cudaFree(M.win_pool[s]);
+  cudaFree(M.win_cursor);
+  cudaFree(M.fix_pool);
+  cudaFree(M.fix_segs);
+  cudaFree(M.fix_cursor);
+  cudaFree(M.fixseg_cursor);
+  cudaFree(M.slide_list[0]);
+  cudaFree(M.slide_list[1]);
+  cudaFree(M.slide_count);
+  InsertScratch& S = ctx->ins;
+  for (int k = 0; k < 3; k++) cudaFree(S.pw[k]);
+  for (int k = 0; k < 6; k++) cudaFree(S.vw[k]);
+  cudaFree(S.root_of);
+  cudaFree(S.leaf_of);
+  cudaFree(S.rank_of);
+  cudaFree(S.touched);
+  cudaFree(S.counters);
+  cudaFree(S.idx);
+  for (int i = 0; i < 16; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* vina_last_error(vina_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int vina_ctx_set_stream(vina_ctx* ctx, void* cuda_stream)
+{
+  if (!ctx) return VINA_E_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return VINA_OK;
+}
+
+extern "C" int vina_ctx_sync(vina_ctx* ctx)
+{
+  if (!ctx) return VINA_E_ARG;
+  return vn_check_status(ctx);
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n)
+{
+  if (!ctx || !xyzt || n < 0) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points %d", n, ctx->cap_points);
+  CU(cudaMemcpyAsync(ctx->d_scan, xyzt, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->n_scan = n;
+  return VINA_OK;
+}
+
+extern "C" int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9],
+                           const double p_end[3])
+{
+  if (!ctx || !poses || m < 0 || !R_end || !p_end) return VINA_E_ARG;
+  if (m > VINA_MAX_POSES) return vn_fail(ctx, VINA_E_CAPACITY, "%d IMU poses > VINA_MAX_POSES", m);
+  // the pinned staging buffer may still be in flight from the previous scan
+  CU(cudaStreamSynchronize(ctx->stream));
+  DeskewPoses* P = ctx->h_poses;
+  P->m = m;
+  memcpy(P->pose, poses, (size_t)m * sizeof(vina_imu_pose));
+  memcpy(P->R_end, R_end, 72);
+  memcpy(P->p_end, p_end, 24);
+  memcpy(P->ext_R, ctx->cfg.ext_R, 72);
+  memcpy(P->ext_t, ctx->cfg.ext_t, 24);
+  CU(cudaMemcpyAsync(ctx->d_poses, P, sizeof(DeskewPoses), cudaMemcpyHostToDevice, ctx->stream));
+  launch_deskew(ctx->stream, ctx->d_scan, ctx->n_scan, ctx->d_poses, ctx->d_status);
+  ctx->launches += 1;
+  return VINA_OK;
+}
+
+extern "C" int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap)
+{
+  if (!ctx || !xyzt) return VINA_E_ARG;
+  if (cap < ctx->n_scan) return VINA_E_ARG;
+  CU(cudaMemcpyAsync(xyzt, ctx->d_scan, (size_t)ctx->n_scan * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  int r = vn_check_status(ctx);
+  if (r) return r;
+  return ctx->n_scan;
+}
+
+static int run_downsample(vina_ctx* ctx, double size)
+{
+  int k = launch_downsample(ctx->stream, ctx->d_scan, ctx->n_scan, size, ctx->d_dtab, ctx->dmask, ctx->d_slot_of,
+                            ctx->d_flag, ctx->d_scanbuf, ctx->d_block_sums, ctx->d_n_down, ctx->d_down, ctx->d_status);
+  if (k < 0) return vn_fail(ctx, VINA_E_CAPACITY, "scan too large for the down-sampling scan kernels");
+  ctx->launches += k;
+  CU(cudaMemcpyAsync(ctx->h_n_down, ctx->d_n_down, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->n_down_pending = true;
+  return VINA_OK;
+}
+
+// resolve the pending down-sampled count (one stream sync) and apply the
+// "< 2000 points -> down_size / 2" retry of local_mapping.cpp:399-403
+static int resolve_n_down(vina_ctx* ctx)
+{
+  if (!ctx->n_down_pending) return VINA_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->n_down = *ctx->h_n_down;
+  ctx->n_down_pending = false;
+  return VINA_OK;
+}
+
+extern "C" int vina_downsample(vina_ctx* ctx)
+{
+  if (!ctx) return VINA_E_ARG;
+  if (ctx->cfg.down_size < 0.001)
+  {
+    CU(cudaMemcpyAsync(ctx->d_down, ctx->d_scan, (size_t)ctx->n_scan * sizeof(float4), cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+    ctx->n_down = ctx->n_scan;
+    ctx->n_down_pending = false;
+    return VINA_OK;
+  }
+  return run_downsample(ctx, ctx->cfg.down_size);
+}
+
+// called by the pipeline once the count is needed on the host
+int vn_finish_downsample(vina_ctx* ctx)
+{
+  int r = resolve_n_down(ctx);
+  if (r) return r;
+  if (ctx->n_down < 2000 && ctx->cfg.down_size >= 0.001 && ctx->n_scan > 0)
+  {
+    // retry with half the voxel size (local_mapping.cpp:399-403)
+    r = run_downsample(ctx, ctx->cfg.down_size / 2);
+    if (r) return r;
+    r = resolve_n_down(ctx);
+    if (r) return r;
+  }
+  return VINA_OK;
+}
+
+extern "C" int vina_down_upload(vina_ctx* ctx, const float* xyzt, int n)
+{
+  if (!ctx || !xyzt || n < 0) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "cloud of %d points > max_scan_points", n);
+  CU(cudaMemcpyAsync(ctx->d_down, xyzt, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->n_down = n;
+  ctx->n_down_pending = false;
+  return VINA_OK;
+}
+
+extern "C" int vina_down_download(vina_ctx* ctx, float* xyzt, int cap)
+{
+  if (!ctx || !xyzt) return VINA_E_ARG;
+  int r = resolve_n_down(ctx);
+  if (r) return r;
+  if (cap < ctx->n_down) return VINA_E_ARG;
+  CU(cudaMemcpyAsync(xyzt, ctx->d_down, (size_t)ctx->n_down * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  r = vn_check_status(ctx);
+  if (r) return r;
+  return ctx->n_down;
+}
+
+extern "C" int vina_var_init(vina_ctx* ctx, int which)
+{
+  if (!ctx || which < 0 || which > 1) return VINA_E_ARG;
+  VarInitParams prm;
+  const float range_inc = (float)ctx->cfg.dept_err, degree_inc = (float)ctx->cfg.beam_err;  // point_utils.cpp:3
+  prm.range_var = range_inc * range_inc;
+  double s = sin((degree_inc)*M_PI / 180.0);
+  prm.dir_var = s * s;
+  memcpy(prm.ext_R, ctx->cfg.ext_R, 72);
+  memcpy(prm.ext_t, ctx->cfg.ext_t, 24);
+  if (which == 1)
+  {
+    int r = resolve_n_down(ctx);
+    if (r) return r;
+  }
+  const int n = which == 0 ? ctx->n_scan : ctx->n_down;
+  launch_var_init(ctx->stream, which == 0 ? ctx->d_scan : ctx->d_down, nullptr, n, ctx->pv[which], prm);
+  ctx->n_pv[which] = n;
+  ctx->launches += 1;
+  return VINA_OK;
+}
+
+extern "C" int vina_pvec_upload(vina_ctx* ctx, int which, const double* pnt, const double* var, int n)
+{
+  if (!ctx || which < 0 || which > 1 || !pnt || !var || n < 0) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "%d points > max_scan_points", n);
+  std::vector<double> tmp((size_t)n);
+  for (int k = 0; k < 3; k++)
+  {
+    for (int i = 0; i < n; i++) tmp[i] = pnt[3 * (size_t)i + k];
+    CU(cudaMemcpy(ctx->pv[which].p[k], tmp.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  }
+  const int ui[6] = { 0, 0, 0, 1, 1, 2 }, uj[6] = { 0, 1, 2, 1, 2, 2 };
+  for (int k = 0; k < 6; k++)
+  {
+    for (int i = 0; i < n; i++) tmp[i] = var[9 * (size_t)i + ui[k] + 3 * uj[k]];
+    CU(cudaMemcpy(ctx->pv[which].v[k], tmp.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  }
+  ctx->n_pv[which] = n;
+  if (which == 1)
+  {
+    ctx->n_down = n;
+    ctx->n_down_pending = false;
+  }
+  else
+    ctx->n_scan = n;
+  return VINA_OK;
+}
+
+extern "C" int vina_pvec_download(vina_ctx* ctx, int which, double* pnt, double* var, int cap)
+{
+  if (!ctx || which < 0 || which > 1 || !pnt || !var) return VINA_E_ARG;
+  const int n = ctx->n_pv[which];
+  if (cap < n) return VINA_E_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<double> tmp((size_t)n);
+  for (int k = 0; k < 3; k++)
+  {
+    CU(cudaMemcpy(tmp.data(), ctx->pv[which].p[k], (size_t)n * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) pnt[3 * (size_t)i + k] = tmp[i];
+  }
+  const int ui[6] = { 0, 0, 0, 1, 1, 2 }, uj[6] = { 0, 1, 2, 1, 2, 2 };
+  for (int k = 0; k < 6; k++)
+  {
+    CU(cudaMemcpy(tmp.data(), ctx->pv[which].v[k], (size_t)n * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++)
+    {
+      var[9 * (size_t)i + ui[k] + 3 * uj[k]] = tmp[i];
+      var[9 * (size_t)i + uj[k] + 3 * ui[k]] = tmp[i];
+    }
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int vina_iekf_begin(vina_ctx* ctx, int which, const double rot_var[9], const double tsl_var[9])
+{
+  if (!ctx || which < 0 || which > 1 || !rot_var || !tsl_var) return VINA_E_ARG;
+  memcpy(ctx->rot_var, rot_var, 72);
+  memcpy(ctx->tsl_var, tsl_var, 72);
+  ctx->iekf_which = which;
+  const int n = ctx->n_pv[which];
+  launch_fill_int(ctx->stream, ctx->d_cache, -1, n);  // vector<OctoTree*> octos(psize, nullptr), odometry.cpp:79
+  ctx->iekf_blocks = iekf_grid_blocks(n, ctx->sm_count);
+  ctx->launches += 1;
+  return VINA_OK;
+}
+
+static int ensure_debug(vina_ctx* ctx)
+{
+  if (ctx->dbg.keys) return VINA_OK;
+  const size_t cap = ctx->cap_points;
+  CU(dalloc(&ctx->dbg.keys, 3 * cap));
+  CU(dalloc(&ctx->dbg.codes, cap));
+  CU(dalloc(&ctx->dbg.flags, cap));
+  CU(dalloc(&ctx->dbg.sigma, cap));
+  return VINA_OK;
+}
+
+int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool debug)
+{
+  if (ctx->iekf_which < 0) return vn_fail(ctx, VINA_E_STATE, "vina_iekf_accumulate before vina_iekf_begin");
+  IekfParams prm;
+  memcpy(prm.R, R, 72);
+  memcpy(prm.p, p, 24);
+  memcpy(prm.rot_var, ctx->rot_var, 72);
+  memcpy(prm.tsl_var, ctx->tsl_var, 72);
+  prm.voxel_size = ctx->cfg.voxel_size;
+  const int w = ctx->iekf_which;
+  if (debug)
+  {
+    int r = ensure_debug(ctx);
+    if (r) return r;
+  }
+  launch_iekf(ctx->stream, ctx->pv[w], nullptr, ctx->n_pv[w], ctx->d_cache, ctx->map, prm, ctx->d_partials,
+              ctx->d_ticket, ctx->d_result, ctx->iekf_blocks, debug ? &ctx->dbg : nullptr);
+  ctx->dbg_valid = debug;
+  ctx->launches += 1;
+  return VINA_OK;
+}
+
+// expand the 34 packed sums
+void vn_iekf_unpack(const double* r, double HTH[36], double HTz[6], double nnt[9], int32_t* match_num)
+{
+  int t = 0;
+  for (int a = 0; a < 6; a++)
+    for (int b = a; b < 6; b++, t++)
+    {
+      HTH[a + 6 * b] = r[t];
+      HTH[b + 6 * a] = r[t];
+    }
+  for (int a = 0; a < 6; a++) HTz[a] = r[21 + a];
+  const int ui[6] = { 0, 0, 0, 1, 1, 2 }, uj[6] = { 0, 1, 2, 1, 2, 2 };
+  for (int k = 0; k < 6; k++)
+  {
+    nnt[ui[k] + 3 * uj[k]] = r[27 + k];
+    nnt[uj[k] + 3 * ui[k]] = r[27 + k];
+  }
+  *match_num = (int32_t)(r[33] + 0.5);
+}
+
+extern "C" int vina_iekf_accumulate(vina_ctx* ctx, const double R[9], const double p[3], double HTH[36],
+                                    double HTz[6], double nnt[9], int32_t* match_num)
+{
+  if (!ctx || !R || !p || !HTH || !HTz || !nnt || !match_num) return VINA_E_ARG;
+  int r = vn_iekf_launch(ctx, R, p, false);
+  if (r) return r;
+  CU(cudaStreamSynchronize(ctx->stream));
+  vn_iekf_unpack(ctx->h_result, HTH, HTz, nnt, match_num);
+  return VINA_OK;
+}
+
+extern "C" int vina_iekf_debug_assoc(vina_ctx* ctx, int64_t* keys, int32_t* codes, uint8_t* flags, double* sigma,
+                                     int cap)
+{
+  if (!ctx || ctx->iekf_which < 0) return VINA_E_ARG;
+  const int n = ctx->n_pv[ctx->iekf_which];
+  if (cap < n) return VINA_E_ARG;
+  if (!ctx->dbg_valid) return vn_fail(ctx, VINA_E_STATE, "no debug association recorded (use vina_iekf_accumulate_debug)");
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (keys) CU(cudaMemcpy(keys, ctx->dbg.keys, (size_t)n * 24, cudaMemcpyDeviceToHost));
+  if (codes) CU(cudaMemcpy(codes, ctx->dbg.codes, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (flags) CU(cudaMemcpy(flags, ctx->dbg.flags, (size_t)n, cudaMemcpyDeviceToHost));
+  if (sigma) CU(cudaMemcpy(sigma, ctx->dbg.sigma, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+// same as vina_iekf_accumulate but also records the per-point association for vina_iekf_debug_assoc
+extern "C" int vina_iekf_accumulate_debug(vina_ctx* ctx, const double R[9], const double p[3], double HTH[36],
+                                          double HTz[6], double nnt[9], int32_t* match_num)
+{
+  if (!ctx || !R || !p || !HTH || !HTz || !nnt || !match_num) return VINA_E_ARG;
+  int r = vn_iekf_launch(ctx, R, p, true);
+  if (r) return r;
+  CU(cudaStreamSynchronize(ctx->stream));
+  vn_iekf_unpack(ctx->h_result, HTH, HTz, nnt, match_num);
+  return VINA_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int vina_map_insert(vina_ctx* ctx, int win_ord, const double R[9], const double p[3],
+                               const double cov_rot[9], const double cov_tsl[9])
+{
+  if (!ctx || win_ord < 0 || win_ord >= ctx->cfg.win_size || !R || !p || !cov_rot || !cov_tsl) return VINA_E_ARG;
+  PoseD x;
+  memcpy(x.R, R, 72);
+  memcpy(x.p, p, 24);
+  ctx->ins.stamp++;
+  const int n = ctx->n_pv[1];
+  ctx->launches += launch_map_insert(ctx->stream, ctx->map, ctx->pv[1], nullptr, n, ctx->ins, win_ord, x, cov_rot, cov_tsl);
+  return VINA_OK;
+}
+
+extern "C" int vina_map_recut(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
+{
+  if (!ctx || win_count < 1 || win_count > ctx->cfg.win_size || !x_buf) return VINA_E_ARG;
+  ctx->launches += launch_map_recut(ctx->stream, ctx->map, win_count, reinterpret_cast<const PoseD*>(x_buf));
+  return VINA_OK;
+}
+
+extern "C" int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
+{
+  if (!ctx || win_count < 1 || win_count > ctx->cfg.win_size || !x_buf) return VINA_E_ARG;
+  ctx->launches += launch_map_margi(ctx->stream, ctx->map, win_count, reinterpret_cast<const PoseD*>(x_buf));
+  ctx->map.slide_cur = 1 - ctx->map.slide_cur;
+  return VINA_OK;
+}
+
+extern "C" int vina_map_shift_window(vina_ctx* ctx)
+{
+  if (!ctx) return VINA_E_ARG;
+  // the slot of the marginalised frame is free again: reset its arena
+  const int freed = ctx->map.mp[0];
+  CU(cudaMemsetAsync(ctx->map.win_cursor + freed, 0, sizeof(int), ctx->stream));
+  for (int i = 0; i < ctx->cfg.win_size; i++)  // local_mapping.cpp:521-526, mgsize = 1
+  {
+    ctx->map.mp[i] += 1;
+    if (ctx->map.mp[i] >= ctx->cfg.win_size) ctx->map.mp[i] -= ctx->cfg.win_size;
+  }
+  return VINA_OK;
+}
+
+extern "C" int64_t vina_map_count(vina_ctx* ctx, int64_t* n_roots, int64_t* n_slide)
+{
+  if (!ctx) return VINA_E_ARG;
+  int r = vn_check_status(ctx);
+  if (r) return r;
+  int nn = 0, sc[2] = { 0, 0 };
+  CU(cudaMemcpy(&nn, ctx->map.node_count, 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(sc, ctx->map.slide_count, 8, cudaMemcpyDeviceToHost));
+  if (n_slide) *n_slide = sc[ctx->map.slide_cur];
+  if (n_roots)
+  {
+    int nr = 0;
+    CU(cudaMemcpy(&nr, ctx->map.root_count, 4, cudaMemcpyDeviceToHost));
+    *n_roots = nr;
+  }
+  return nn;
+}
+
+extern "C" int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t cap)
+{
+  if (!ctx || !out) return VINA_E_ARG;
+  int r = vn_check_status(ctx);
+  if (r) return r;
+  int nn = 0;
+  CU(cudaMemcpy(&nn, ctx->map.node_count, 4, cudaMemcpyDeviceToHost));
+  if (nn > ctx->map.max_nodes) nn = ctx->map.max_nodes;
+  if (cap < nn) return VINA_E_ARG;
+  if (nn == 0) return 0;
+  vina_node_record* d_out = nullptr;
+  long long* d_cnt = nullptr;
+  CU(cudaMalloc((void**)&d_out, (size_t)nn * sizeof(vina_node_record)));
+  CU(cudaMalloc((void**)&d_cnt, 8));
+  launch_map_export(ctx->stream, ctx->map, d_out, nn, d_cnt);
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(out, d_out, (size_t)nn * sizeof(vina_node_record), cudaMemcpyDeviceToHost));
+  cudaFree(d_out);
+  cudaFree(d_cnt);
+  return nn;
+}
+
+extern "C" int vina_set_profiling(vina_ctx* ctx, int on)
+{
+  if (!ctx) return VINA_E_ARG;
+  ctx->profiling = on != 0;
+  return VINA_OK;
+}
+
+extern "C" int vina_get_timings(vina_ctx* ctx, vina_timings* t)
+{
+  if (!ctx || !t) return VINA_E_ARG;
+  *t = ctx->tm;
+  return VINA_OK;
+}

@@ -1,0 +1,69 @@
+// The opaque context behind the C ABI (include/vina_b200.h): device pools,
+// per-scan buffers, the CUDA stream and the host-side odometry state.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "vn_kernels.cuh"
+
+struct OdomHost;  // host/vina_pipeline.cpp
+
+struct vina_ctx
+{
+  vina_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+
+  // scan buffers
+  int cap_points = 0;
+  float4* d_scan = nullptr;  // raw -> deskewed in place (x,y,z,curvature)
+  float4* d_down = nullptr;  // down-sampled cloud
+  int n_scan = 0;
+  int n_down = 0;            // host copy (valid after a sync)
+  bool n_down_pending = false;
+  int* d_n_down = nullptr;
+  int* h_n_down = nullptr;   // pinned
+  ScanView pv[2];            // [0] full scan, [1] down-sampled
+  int n_pv[2] = { 0, 0 };
+  int* d_cache = nullptr;
+  DeskewPoses* d_poses = nullptr;
+  DeskewPoses* h_poses = nullptr;  // pinned
+  // down-sampling scratch
+  DownSlot* d_dtab = nullptr;
+  unsigned int dmask = 0;
+  int *d_slot_of = nullptr, *d_flag = nullptr, *d_scanbuf = nullptr, *d_block_sums = nullptr;
+  // IEKF
+  int iekf_which = -1;
+  int iekf_blocks = 0;
+  double rot_var[9], tsl_var[9];
+  double* d_partials = nullptr;
+  unsigned int* d_ticket = nullptr;
+  double* h_result = nullptr;  // pinned + mapped; the kernel's last block writes it
+  double* d_result = nullptr;  // device alias of h_result
+  IekfDebug dbg = { nullptr, nullptr, nullptr, nullptr };
+  bool dbg_valid = false;
+  // map
+  MapView map;
+  InsertScratch ins;
+  unsigned int hash_slots = 0;
+  int* d_status = nullptr;
+  int* h_status = nullptr;  // pinned
+  int win_count_last = 0;
+
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[16];
+  vina_timings tm;
+  int launches = 0;
+
+  OdomHost* odom = nullptr;
+};
+
+int vn_fail(vina_ctx* c, int code, const char* fmt, ...);
+int vn_check_cuda(vina_ctx* c, cudaError_t e, const char* what);
+// copy the device status word back (synchronises) and translate it
+int vn_check_status(vina_ctx* c);
+void odom_host_destroy(OdomHost* o);

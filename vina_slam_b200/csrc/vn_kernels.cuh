@@ -1,0 +1,75 @@
+// Launcher prototypes and small parameter blocks shared by the kernel TUs and the context.
+#pragma once
+#include <cuda_runtime.h>
+#include "vn_math.cuh"
+#include "vn_types.cuh"
+
+struct VarInitParams
+{
+  float range_var;  // (float)dept_err * (float)dept_err   (point_utils.cpp:11)
+  double dir_var;   // sin(deg2rad((float)beam_err))^2      (point_utils.cpp:14)
+  double ext_R[9], ext_t[3];
+};
+
+struct DownSlot
+{
+  unsigned long long key;
+  double sum[3];
+  int cnt;
+  int first;
+};
+
+// per-iteration constants of the IEKF accumulate kernel
+struct IekfParams
+{
+  double R[9], p[3];       // x_curr.R / x_curr.p of this iteration
+  double rot_var[9], tsl_var[9];  // prior covariance blocks (odometry.cpp:105-106)
+  double voxel_size;
+};
+
+#define VN_IEKF_NACC 34  // 21 (HTH upper) + 6 (HTz) + 6 (nnt upper) + 1 (count)
+
+struct IekfDebug
+{
+  long long* keys;  // n x 3
+  int* codes;
+  unsigned char* flags;
+  double* sigma;
+};
+
+// scan_kernels.cu
+void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status);
+void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n_host, ScanView out,
+                     const VarInitParams& prm);
+void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots);
+int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
+                      int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status);
+
+// iekf_kernel.cu
+int iekf_grid_blocks(int n, int sm_count);
+void launch_iekf(cudaStream_t st, const ScanView& scan, const int* n_dev, int n_host, int* cache, const MapView& map,
+                 const IekfParams& prm, double* partials, unsigned int* ticket, double* result, int blocks,
+                 const IekfDebug* dbg);
+void launch_fill_int(cudaStream_t st, int* p, int v, int n);
+
+// map_kernels.cu
+struct InsertScratch
+{
+  double* pw[3];   // world points of the down-sampled scan
+  double* vw[6];   // world covariance (symmetric)
+  int* root_of;    // per point
+  int* leaf_of;    // per point
+  int* rank_of;    // per point: arrival rank within its leaf
+  int* touched;    // leaves touched by this scan
+  int* counters;   // [0]=g_size (distinct roots) [1]=n_touched [2]=idx cursor
+  int* idx;        // point indices grouped by leaf
+  int stamp;       // scan stamp for distinct-root counting
+};
+int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
+                      const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
+                      const double* tsl_var);
+int launch_map_recut(cudaStream_t st, const MapView& map, int win_count, const PoseD* h_xbuf);
+// margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
+int launch_map_margi(cudaStream_t st, const MapView& map, int win_count, const PoseD* h_xbuf);
+int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count);
+void launch_map_init(cudaStream_t st, const MapView& map, unsigned int nslots);

@@ -1,0 +1,141 @@
+// Device data model of the voxel map and scan buffers (DESIGN.md "Data layout in HBM").
+// Mirrors what the hot path needs from the reference's structures:
+//   unordered_map<VOXEL_LOC,OctoTree*>  -> open-addressing table of 16-B slots (packed key -> root id)
+//   OctoTree (octree.hpp:24-45)          -> NodeHot (256 B, what match() reads) + NodeCold (accumulators)
+//   SlideWindow::points[slot]            -> one bump arena per window slot, (offset,count) per leaf
+//   OctoTree::point_fix                  -> chained segments in a fixed-point pool
+#pragma once
+#include <cstdint>
+#include "../../include/vina_b200.h"
+
+#define VN_FLAG_PLANE 1     // Plane::is_plane
+#define VN_FLAG_INTERIOR 2  // octo_state == 1
+#define VN_KEY_BIAS (1 << 20)
+#define VN_KEY_MASK ((1u << 21) - 1)
+#define VN_EMPTY_KEY 0ull
+
+// status bits written by kernels into Ctx::d_status
+#define VN_ST_HASH_FULL 1
+#define VN_ST_NODES_FULL 2
+#define VN_ST_WIN_FULL 4
+#define VN_ST_FIX_FULL 8
+#define VN_ST_KEY_RANGE 16
+#define VN_ST_SPIN 32
+#define VN_ST_UNSORTED 64
+#define VN_ST_DOWN_FULL 128
+
+struct __align__(16) HashSlot
+{
+  unsigned long long key;  // packed voxel key, 0 = empty
+  int root;                // node id, -2 while the creator is still initialising it
+  int pad;
+};
+
+// what OctoTree::match / inside read (octree.cpp:551-595, 732-737); one 256-B record = two 128-B lines
+struct __align__(128) NodeHot
+{
+  double center[3];   // plane.center
+  double normal[3];   // plane.normal
+  double pvar[21];    // plane.plane_var, upper triangle packed by rows
+  float radius;       // plane.radius
+  int flags;          // VN_FLAG_*
+  double vcenter[3];  // voxel_center
+  float ql;           // quater_length
+  int layer;
+};
+
+// PointCluster (types.hpp:115-175); P is symmetric by construction of every
+// cluster the scope builds, stored as (0,0),(1,0),(2,0),(1,1),(2,1),(2,2)
+struct Cluster
+{
+  double P[6];
+  double v[3];
+  int N;
+  int pad;
+};
+
+// pointVar (types.hpp:177-182) with the covariance stored symmetric:
+// (0,0),(0,1),(0,2),(1,1),(1,2),(2,2) = the upper triangle of the reference's matrix
+struct PointRec
+{
+  double p[3];
+  double v[6];
+};
+
+struct FixSeg
+{
+  int off, cnt, next, pad;
+};
+
+struct NodeCold
+{
+  Cluster pcr_add, pcr_fix;
+  Cluster pcrs_local[VINA_MAX_WIN];
+  double cov_add[45];  // 9x9 symmetric, upper triangle packed by rows
+  double eig_value[3];
+  double eig_vector[9];  // column-major
+  int win_off[VINA_MAX_WIN];
+  int win_cnt[VINA_MAX_WIN];
+  int fix_head, fix_tail, fix_count;  // chain of FixSeg
+  int last_num, opt_state, isexist, has_sw;
+  int path;
+  unsigned long long rootkey;
+  int pend_cnt, pend_off;  // per-insert scratch: points of this scan landing in the leaf
+  int touch_stamp, in_slide;
+  int children[8];
+};
+
+struct PoseD
+{
+  double R[9];  // column-major
+  double p[3];
+};
+
+struct DeskewPoses
+{
+  int m;
+  int pad;
+  vina_imu_pose pose[VINA_MAX_POSES];
+  double R_end[9], p_end[3];
+  double ext_R[9], ext_t[3];
+};
+
+// everything the map kernels need, passed by value
+struct MapView
+{
+  HashSlot* slots;
+  unsigned int hmask;
+  NodeHot* hot;
+  NodeCold* cold;
+  int max_nodes;
+  int* node_count;
+  int* root_count;
+  PointRec* win_pool[VINA_MAX_WIN];
+  int* win_cursor;  // [VINA_MAX_WIN]
+  long long win_cap;
+  PointRec* fix_pool;
+  FixSeg* fix_segs;
+  int* fix_cursor;      // points
+  int* fixseg_cursor;   // segments
+  long long fix_cap;
+  int fixseg_cap;
+  int* slide_list[2];
+  int* slide_count;  // [2]
+  int slide_cur;     // which of the two lists is surf_map_slide right now
+  int* status;
+  // config
+  double voxel_size;
+  double min_eigen_value;
+  double thre[4];  // already inverted
+  double min_point[4];
+  int max_layer, max_points, win_size, thread_num;
+  int mp[VINA_MAX_WIN];
+};
+
+struct ScanView
+{
+  // pointVar SoA (body frame): p[3][cap], v[6][cap]
+  double* p[3];
+  double* v[6];
+  int n;
+};

@@ -1,0 +1,559 @@
+// Host orchestration of the per-scan loop — the C++ that stays on the CPU
+// (north_star: "host code stays C++ in src/pipeline"). It mirrors
+//   IMUEKF::motion_blur, IMU part        src/estimation/imu_ekf.cpp:13-104   (a1, sequential, ~20-40 steps)
+//   VINA_SLAM::LioStateEstimation        src/pipeline/odometry.cpp:64-255   (iteration loop + a7 15x15 solve)
+//   thd_odometry_localmapping, scan body src/pipeline/local_mapping.cpp:389-546
+// and drives the CUDA kernels only through the low-level C ABI of
+// include/vina_b200.h — the same calls a reference-side adapter would make
+// (INTEGRATION.md). No point-level work happens here.
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <vector>
+#include "../csrc/vn_ctx.h"
+
+int vn_finish_downsample(vina_ctx* ctx);
+int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool debug);
+void vn_iekf_unpack(const double* r, double HTH[36], double HTz[6], double nnt[9], int32_t* match_num);
+
+namespace
+{
+// column-major helpers -------------------------------------------------------
+inline void m3_mul(const double* A, const double* B, double* C) { mat3_mul(A, B, C); }
+inline void m3_T(const double* A, double* T)
+{
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T[j + 3 * i] = A[i + 3 * j];
+}
+inline double norm3(const double* a) { return std::sqrt(dot3(a, a)); }
+
+// Exp(ang_vel, dt) — include/vina_slam/core/math.hpp:26-41
+void Exp_dt(const double* w, double dt, double* E)
+{
+  for (int i = 0; i < 9; i++) E[i] = 0;
+  E[0] = E[4] = E[8] = 1;
+  double nrm = norm3(w);
+  if (nrm > 1e-7)
+  {
+    double ax[3] = { w[0] / nrm, w[1] / nrm, w[2] / nrm };
+    double K[9], sK[9], KK[9];
+    hat3(ax, K);
+    double r = nrm * dt;
+    double s = std::sin(r), c1 = 1.0 - std::cos(r);
+    for (int i = 0; i < 9; i++) sK[i] = c1 * K[i];
+    m3_mul(sK, K, KK);
+    for (int i = 0; i < 9; i++) E[i] = (E[i] + s * K[i]) + KK[i];
+  }
+}
+// Exp(ang) — math.hpp:12-24
+void Exp_v(const double* a, double* E)
+{
+  for (int i = 0; i < 9; i++) E[i] = 0;
+  E[0] = E[4] = E[8] = 1;
+  double nrm = norm3(a);
+  if (nrm >= 1e-9)
+  {
+    double ax[3] = { a[0] / nrm, a[1] / nrm, a[2] / nrm };
+    double K[9], sK[9], KK[9];
+    hat3(ax, K);
+    double s = std::sin(nrm), c1 = 1.0 - std::cos(nrm);
+    for (int i = 0; i < 9; i++) sK[i] = c1 * K[i];
+    m3_mul(sK, K, KK);
+    for (int i = 0; i < 9; i++) E[i] = (E[i] + s * K[i]) + KK[i];
+  }
+}
+// Log(R) — math.hpp:43-48
+void Log_R(const double* R, double* w)
+{
+  double tr = (R[0] + R[4]) + R[8];
+  double theta = (tr > 3.0 - 1e-6) ? 0.0 : std::acos(0.5 * (tr - 1));
+  double K[3] = { R[5] - R[7], R[6] - R[2], R[1] - R[3] };
+  double f = (std::fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / std::sin(theta));
+  for (int i = 0; i < 3; i++) w[i] = f * K[i];
+}
+
+// dense column-major n x n helpers for the 15-dim state
+void mat_mul(int n, int k, int m, const double* A, const double* B, double* C)  // (n x k)(k x m)
+{
+  for (int j = 0; j < m; j++)
+    for (int i = 0; i < n; i++)
+    {
+      double s = A[i] * B[k * j];
+      for (int t = 1; t < k; t++) s = s + A[i + n * t] * B[t + k * j];
+      C[i + n * j] = s;
+    }
+}
+}  // namespace
+
+struct OdomHost
+{
+  vina_state x_curr;
+  // IMUEKF members (include/vina_slam/ekf_imu.hpp:12-42)
+  double pcl_beg_time = 0, pcl_end_time = 0, last_pcl_end_time = 0;
+  vina_imu last_imu;
+  double scale_gravity = 1.0;
+  std::vector<vina_imu_pose> imu_poses;
+  // sliding window (node.hpp: x_buf, win_count, win_base)
+  std::vector<vina_pose> x_buf;
+  int win_count = 0, win_base = 0;
+  int degrade_cnt = 0;
+  int last_iters = 0;
+  OdomHost()
+  {
+    memset(&x_curr, 0, sizeof(x_curr));
+    x_curr.R[0] = x_curr.R[4] = x_curr.R[8] = 1;
+    x_curr.g[2] = -9.8;
+    for (int i = 0; i < 15; i++) x_curr.cov[i + 15 * i] = i < 9 ? 1e-4 : 1e-5;  // IMUST::setZero, types.hpp:101-112
+    memset(&last_imu, 0, sizeof(last_imu));
+  }
+};
+
+void odom_host_destroy(OdomHost* o) { delete o; }
+
+static OdomHost* odom(vina_ctx* ctx)
+{
+  if (!ctx->odom) ctx->odom = new OdomHost();
+  return ctx->odom;
+}
+
+// a1 — IMUEKF::motion_blur, IMU forward propagation (imu_ekf.cpp:17-104)
+static int imu_propagate(vina_ctx* ctx, OdomHost* o, const vina_imu* imus_in, int m)
+{
+  std::deque<vina_imu> imus(imus_in, imus_in + m);
+  imus.push_front(o->last_imu);
+  if (o->last_pcl_end_time - o->pcl_beg_time > 0.01)
+    return vn_fail(ctx, VINA_E_TIME, "LiDAR time regress: beg %.6f < last end %.6f", o->pcl_beg_time,
+                   o->last_pcl_end_time);
+  vina_state& xc = o->x_curr;
+  const vina_config& cfg = ctx->cfg;
+  o->imu_poses.clear();
+  double acc_imu[3] = { 0, 0, 0 }, angvel_avr[3] = { 0, 0, 0 }, acc_avr[3];
+  double vel_imu[3], pos_imu[3], R_imu[9];
+  memcpy(vel_imu, xc.v, 24);
+  memcpy(pos_imu, xc.p, 24);
+  memcpy(R_imu, xc.R, 72);
+  std::vector<double> F(225), W(225), T1(225), T2(225), Ft(225);
+  double dt = 0;
+  for (size_t it = 0; it + 1 < imus.size(); it++)
+  {
+    const vina_imu& head = imus[it];
+    const vina_imu& tail = imus[it + 1];
+    if (head.t < o->last_pcl_end_time) continue;
+    for (int k = 0; k < 3; k++)
+    {
+      angvel_avr[k] = 0.5 * (head.gyr[k] + tail.gyr[k]);
+      acc_avr[k] = 0.5 * (head.acc[k] + tail.acc[k]);
+    }
+    for (int k = 0; k < 3; k++)
+    {
+      angvel_avr[k] = angvel_avr[k] - xc.bg[k];
+      acc_avr[k] = acc_avr[k] * o->scale_gravity - xc.ba[k];
+    }
+    rot_trans(R_imu, xc.g, acc_avr, acc_imu);
+    double cur_time = head.t;
+    if (cur_time < o->last_pcl_end_time) cur_time = o->last_pcl_end_time;
+    dt = tail.t - cur_time;
+    double offt = cur_time - o->pcl_beg_time;
+
+    vina_imu_pose ps;
+    ps.t = offt;
+    memcpy(ps.R, R_imu, 72);
+    memcpy(ps.p, pos_imu, 24);
+    memcpy(ps.v, vel_imu, 24);
+    memcpy(ps.w, angvel_avr, 24);
+    memcpy(ps.a, acc_imu, 24);
+    o->imu_poses.push_back(ps);
+
+    double acc_skew[9], Exp_f[9], Exp_b[9];
+    hat3(acc_avr, acc_skew);
+    Exp_dt(angvel_avr, dt, Exp_f);
+    Exp_dt(angvel_avr, -dt, Exp_b);
+    std::fill(F.begin(), F.end(), 0.0);
+    std::fill(W.begin(), W.end(), 0.0);
+    for (int i = 0; i < 15; i++) F[i + 15 * i] = 1.0;
+    auto setblk = [&](std::vector<double>& M, int r0, int c0, const double* B) {
+      for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) M[(r0 + i) + 15 * (c0 + j)] = B[i + 3 * j];
+    };
+    double B[9], nR[9], RA[9];
+    setblk(F, 0, 0, Exp_b);
+    for (int i = 0; i < 9; i++) B[i] = 0;
+    B[0] = B[4] = B[8] = -1.0 * dt;
+    setblk(F, 0, 9, B);
+    B[0] = B[4] = B[8] = 1.0 * dt;
+    setblk(F, 3, 6, B);
+    for (int i = 0; i < 9; i++) nR[i] = -1.0 * R_imu[i];
+    m3_mul(nR, acc_skew, RA);
+    for (int i = 0; i < 9; i++) B[i] = RA[i] * dt;
+    setblk(F, 6, 0, B);
+    for (int i = 0; i < 9; i++) B[i] = nR[i] * dt;
+    setblk(F, 6, 12, B);
+    for (int k = 0; k < 3; k++) W[k + 15 * k] = cfg.cov_gyr * dt * dt;
+    {
+      double D[9] = { cfg.cov_acc, 0, 0, 0, cfg.cov_acc, 0, 0, 0, cfg.cov_acc }, RD[9], RDRt[9];
+      m3_mul(R_imu, D, RD);
+      mat3_mulT(RD, R_imu, RDRt);
+      for (int i = 0; i < 9; i++) B[i] = RDRt[i] * dt * dt;
+      setblk(W, 6, 6, B);
+    }
+    for (int k = 0; k < 3; k++) W[(9 + k) + 15 * (9 + k)] = cfg.rdw_gyr * dt * dt;
+    for (int k = 0; k < 3; k++) W[(12 + k) + 15 * (12 + k)] = cfg.rdw_acc * dt * dt;
+    // cov = F cov F^T + W
+    mat_mul(15, 15, 15, F.data(), xc.cov, T1.data());
+    for (int i = 0; i < 15; i++)
+      for (int j = 0; j < 15; j++) Ft[j + 15 * i] = F[i + 15 * j];
+    mat_mul(15, 15, 15, T1.data(), Ft.data(), T2.data());
+    for (int i = 0; i < 225; i++) xc.cov[i] = T2[i] + W[i];
+
+    for (int k = 0; k < 3; k++) pos_imu[k] = (pos_imu[k] + vel_imu[k] * dt) + ((0.5 * acc_imu[k]) * dt) * dt;
+    for (int k = 0; k < 3; k++) vel_imu[k] = vel_imu[k] + acc_imu[k] * dt;
+    double Rn[9];
+    m3_mul(R_imu, Exp_f, Rn);
+    memcpy(R_imu, Rn, 72);
+  }
+  double imu_end_time = imus.back().t;
+  double note = o->pcl_end_time > imu_end_time ? 1.0 : -1.0;
+  dt = note * (o->pcl_end_time - imu_end_time);
+  double nw[3] = { note * angvel_avr[0], note * angvel_avr[1], note * angvel_avr[2] }, E[9], Rn[9];
+  for (int k = 0; k < 3; k++) xc.v[k] = vel_imu[k] + (note * acc_imu[k]) * dt;
+  Exp_dt(nw, dt, E);
+  m3_mul(R_imu, E, Rn);
+  memcpy(xc.R, Rn, 72);
+  for (int k = 0; k < 3; k++)
+    xc.p[k] = (pos_imu[k] + (note * vel_imu[k]) * dt) + (((note * 0.5) * acc_imu[k]) * dt) * dt;
+  xc.t = o->pcl_end_time;
+  o->last_imu = imus.back();
+  o->last_pcl_end_time = o->pcl_end_time;
+  return VINA_OK;
+}
+
+// x (+)= delta — IMUST::operator+= (types.hpp:67-75)
+static void state_boxplus(vina_state& x, const double* d)
+{
+  double E[9], Rn[9];
+  Exp_v(d, E);
+  m3_mul(x.R, E, Rn);
+  memcpy(x.R, Rn, 72);
+  for (int k = 0; k < 3; k++)
+  {
+    x.p[k] += d[3 + k];
+    x.v[k] += d[6 + k];
+    x.bg[k] += d[9 + k];
+    x.ba[k] += d[12 + k];
+  }
+}
+// a (-) b — IMUST::operator- (types.hpp:77-86)
+static void state_boxminus(const vina_state& a, const vina_state& b, double* out)
+{
+  double bt[9], M[9];
+  m3_T(b.R, bt);
+  m3_mul(bt, a.R, M);
+  Log_R(M, out);
+  for (int k = 0; k < 3; k++)
+  {
+    out[3 + k] = a.p[k] - b.p[k];
+    out[6 + k] = a.v[k] - b.v[k];
+    out[9 + k] = a.bg[k] - b.bg[k];
+    out[12 + k] = a.ba[k] - b.ba[k];
+  }
+}
+
+// VINA_SLAM::LioStateEstimation (odometry.cpp:64-255), use_vnc == false terms;
+// the per-point loop of each iteration runs on the GPU (vina_iekf_accumulate).
+static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_iter_override, int* not_degenerate)
+{
+  vina_state& x_curr = o->x_curr;
+  const vina_state x_prop = x_curr;
+  const int num_max_iter = max_iter_override > 0 ? max_iter_override : 20;
+  double G[225], HTH15[225], cov_inv[225], K1[225], tmp[225];
+  memset(G, 0, sizeof(G));
+  memset(HTH15, 0, sizeof(HTH15));
+  int rematch_num = 0;
+  double nnt[9] = { 0 };
+  inverse_lu<15>(x_curr.cov, cov_inv);
+  double rot_var[9], tsl_var[9];
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++)
+    {
+      rot_var[i + 3 * j] = x_curr.cov[i + 15 * j];
+      tsl_var[i + 3 * j] = x_curr.cov[(3 + i) + 15 * (3 + j)];
+    }
+  int r = vina_iekf_begin(ctx, which, rot_var, tsl_var);
+  if (r) return r;
+  o->last_iters = 0;
+  cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9];
+  float kernel_ms = 0;
+
+  for (int iterCount = 0; iterCount < num_max_iter; iterCount++)
+  {
+    double HTH[36], HTz[6];
+    int32_t match_num = 0;
+    if (ctx->profiling) cudaEventRecord(e0, ctx->stream);
+    r = vn_iekf_launch(ctx, x_curr.R, x_curr.p, false);
+    if (r) return r;
+    if (ctx->profiling) cudaEventRecord(e1, ctx->stream);
+    r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "iekf sync");
+    if (r) return r;
+    if (ctx->profiling)
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      kernel_ms += ms;
+    }
+    vn_iekf_unpack(ctx->h_result, HTH, HTz, nnt, &match_num);
+    o->last_iters = iterCount + 1;
+
+    for (int j = 0; j < 6; j++)
+      for (int i = 0; i < 6; i++) HTH15[i + 15 * j] = HTH[i + 6 * j];
+    for (int i = 0; i < 225; i++) tmp[i] = HTH15[i] + cov_inv[i];
+    inverse_lu<15>(tmp, K1);
+    // G(:,0:6) = K1(:,0:6) * HTH
+    double G6[90];
+    mat_mul(15, 6, 6, K1, HTH, G6);  // first 6 columns of K1 are the first 90 entries
+    memcpy(G, G6, sizeof(G6));
+    double vec[15], sol[15], a[15], b[15];
+    state_boxminus(x_prop, x_curr, vec);
+    mat_mul(15, 6, 1, K1, HTz, a);
+    mat_mul(15, 6, 1, G6, vec, b);
+    for (int i = 0; i < 15; i++) sol[i] = (a[i] + vec[i]) - b[i];
+    state_boxplus(x_curr, sol);
+
+    bool conv = (norm3(sol) * 57.3 < 0.01) && (norm3(sol + 3) * 100 < 0.015);
+    if (conv || ((rematch_num == 0) && (iterCount == num_max_iter - 2))) rematch_num++;
+    if (rematch_num >= 2 || (iterCount == num_max_iter - 1))
+    {
+      // cov = (I - G) cov
+      double IG[225], nc[225];
+      for (int i = 0; i < 225; i++) IG[i] = -G[i];
+      for (int i = 0; i < 15; i++) IG[i + 15 * i] = 1.0 - G[i + 15 * i];
+      mat_mul(15, 15, 15, IG, x_curr.cov, nc);
+      memcpy(x_curr.cov, nc, sizeof(nc));
+      break;
+    }
+  }
+  ctx->tm.iekf_kernel_ms = kernel_ms;
+  ctx->tm.iekf_iters = o->last_iters;
+  // degeneracy test on the last iteration's nnt (odometry.cpp:244-254)
+  double L[6] = { nnt[0], nnt[1], nnt[2], nnt[4], nnt[5], nnt[8] }, ev[3], Q[9];
+  eig3_sym(L, ev, Q);
+  *not_degenerate = !(ev[0] < 14);
+  return VINA_OK;
+}
+
+// local_mapping.cpp:425-451 and 489-546 with if_BA == 0
+static int map_update(vina_ctx* ctx, OdomHost* o)
+{
+  vina_state& x = o->x_curr;
+  double rot_var[9], tsl_var[9];
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++)
+    {
+      rot_var[i + 3 * j] = x.cov[i + 15 * j];
+      tsl_var[i + 3 * j] = x.cov[(3 + i) + 15 * (3 + j)];
+    }
+  o->win_count++;
+  vina_pose ps;
+  memcpy(ps.R, x.R, 72);
+  memcpy(ps.p, x.p, 24);
+  o->x_buf.push_back(ps);
+  cudaEvent_t* ev = ctx->ev;
+  if (ctx->profiling) cudaEventRecord(ev[4], ctx->stream);
+  int r = vina_map_insert(ctx, o->win_count - 1, x.R, x.p, rot_var, tsl_var);  // pvec_update + cut_voxel_multi
+  if (r) return r;
+  if (ctx->profiling) cudaEventRecord(ev[5], ctx->stream);
+  r = vina_map_recut(ctx, o->win_count, o->x_buf.data());
+  if (r) return r;
+  if (ctx->profiling) cudaEventRecord(ev[6], ctx->stream);
+  if (o->win_count >= ctx->cfg.win_size)
+  {
+    // x_curr.R/p = x_buf.back() is the identity without BA (local_mapping.cpp:501-502)
+    r = vina_map_margi(ctx, o->win_count, o->x_buf.data());
+    if (r) return r;
+    r = vina_map_shift_window(ctx);
+    if (r) return r;
+    o->x_buf.erase(o->x_buf.begin());
+    o->win_base += 1;
+    o->win_count -= 1;
+  }
+  if (ctx->profiling) cudaEventRecord(ev[7], ctx->stream);
+  return VINA_OK;
+}
+
+static void collect_timings(vina_ctx* ctx)
+{
+  if (!ctx->profiling) return;
+  cudaEventSynchronize(ctx->ev[7]);
+  cudaEvent_t* ev = ctx->ev;
+  cudaEventElapsedTime(&ctx->tm.deskew_ms, ev[0], ev[1]);
+  cudaEventElapsedTime(&ctx->tm.downsample_ms, ev[1], ev[2]);
+  cudaEventElapsedTime(&ctx->tm.var_init_ms, ev[2], ev[3]);
+  cudaEventElapsedTime(&ctx->tm.iekf_ms, ev[3], ev[4]);
+  cudaEventElapsedTime(&ctx->tm.insert_ms, ev[4], ev[5]);
+  cudaEventElapsedTime(&ctx->tm.recut_ms, ev[5], ev[6]);
+  cudaEventElapsedTime(&ctx->tm.margi_ms, ev[6], ev[7]);
+  cudaEventElapsedTime(&ctx->tm.total_ms, ev[0], ev[7]);
+}
+
+// the scan body of thd_odometry_localmapping (local_mapping.cpp:389-546); the raw scan is on the device
+static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, float last_curvature,
+                              const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
+{
+  const int l0 = ctx->launches;
+  o->pcl_beg_time = pcl_beg_time;
+  o->pcl_end_time = pcl_beg_time + (double)last_curvature;  // sync.cpp:40
+  int r = imu_propagate(ctx, o, imus, m);
+  if (r) return r;
+  cudaEvent_t* ev = ctx->ev;
+  if (ctx->profiling) cudaEventRecord(ev[0], ctx->stream);
+  r = vina_deskew(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+  if (r) return r;
+  if (ctx->profiling) cudaEventRecord(ev[1], ctx->stream);
+  r = vina_downsample(ctx);
+  if (r) return r;
+  if (ctx->profiling) cudaEventRecord(ev[2], ctx->stream);
+  int which = 1;
+  if (iekf_on_full)
+  {
+    r = vina_var_init(ctx, 0);
+    if (r) return r;
+    which = 0;
+  }
+  else
+  {
+    r = vn_finish_downsample(ctx);
+    if (r) return r;
+    r = vina_var_init(ctx, 1);
+    if (r) return r;
+  }
+  if (ctx->profiling) cudaEventRecord(ev[3], ctx->stream);
+  int ok = 0;
+  r = lio_state_estimation(ctx, o, which, max_iter, &ok);
+  if (r) return r;
+  if (ok)
+  {
+    if (o->degrade_cnt > 0) o->degrade_cnt--;
+  }
+  else
+    o->degrade_cnt++;
+  if (iekf_on_full)
+  {
+    // the down-sampled count arrived with the IEKF readbacks: no extra sync in the common case
+    r = vn_finish_downsample(ctx);
+    if (r) return r;
+    r = vina_var_init(ctx, 1);
+    if (r) return r;
+  }
+  r = map_update(ctx, o);
+  if (r) return r;
+  if (x_out) *x_out = o->x_curr;
+  collect_timings(ctx);
+  ctx->tm.kernel_launches = ctx->launches - l0;
+  return VINA_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int vina_odom_set_state(vina_ctx* ctx, const vina_state* s)
+{
+  if (!ctx || !s) return VINA_E_ARG;
+  odom(ctx)->x_curr = *s;
+  return VINA_OK;
+}
+int vina_odom_get_state(vina_ctx* ctx, vina_state* s)
+{
+  if (!ctx || !s) return VINA_E_ARG;
+  *s = odom(ctx)->x_curr;
+  return VINA_OK;
+}
+int vina_odom_set_imu_anchor(vina_ctx* ctx, double last_pcl_end_time, const vina_imu* last_imu, double scale_gravity)
+{
+  if (!ctx || !last_imu) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  o->last_pcl_end_time = last_pcl_end_time;
+  o->last_imu = *last_imu;
+  o->scale_gravity = scale_gravity;
+  return VINA_OK;
+}
+
+int vina_odom_bootstrap(vina_ctx* ctx, const float* xyzt, int n, const vina_state* x_known)
+{
+  if (!ctx || !xyzt || !x_known || n <= 0) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  o->x_curr = *x_known;
+  int r = vina_scan_upload(ctx, xyzt, n);
+  if (r) return r;
+  r = vina_downsample(ctx);
+  if (r) return r;
+  r = vn_finish_downsample(ctx);
+  if (r) return r;
+  r = vina_var_init(ctx, 1);
+  if (r) return r;
+  return map_update(ctx, o);
+}
+
+int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time, const vina_imu* imus, int m,
+                   int iekf_on_full, int max_iter, vina_state* x_out)
+{
+  if (!ctx || !xyzt || !imus || n <= 0 || m <= 0) return VINA_E_ARG;
+  int r = vina_scan_upload(ctx, xyzt, n);
+  if (r) return r;
+  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, xyzt[4 * (size_t)(n - 1) + 3], imus, m, iekf_on_full,
+                            max_iter, x_out);
+}
+
+int vina_odom_step_resident(vina_ctx* ctx, double pcl_beg_time, const vina_imu* imus, int m, int iekf_on_full,
+                            int max_iter, vina_state* x_out)
+{
+  if (!ctx || !imus || m <= 0 || ctx->n_scan <= 0) return VINA_E_ARG;
+  float last[4];
+  int r = vn_check_cuda(ctx,
+                        cudaMemcpyAsync(last, ctx->d_scan + (ctx->n_scan - 1), sizeof(float4), cudaMemcpyDeviceToHost,
+                                        ctx->stream),
+                        "read last curvature");
+  if (r) return r;
+  r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync");
+  if (r) return r;
+  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, last[3], imus, m, iekf_on_full, max_iter, x_out);
+}
+
+int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
+                        vina_imu_pose* poses_out, int cap)
+{
+  if (!ctx || !imus || m <= 0) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  o->pcl_beg_time = pcl_beg_time;
+  o->pcl_end_time = pcl_end_time;
+  int r = imu_propagate(ctx, o, imus, m);
+  if (r) return r;
+  int np = (int)o->imu_poses.size();
+  if (poses_out && cap >= np) memcpy(poses_out, o->imu_poses.data(), (size_t)np * sizeof(vina_imu_pose));
+  return np;
+}
+
+int vina_odom_iekf(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate)
+{
+  if (!ctx || which < 0 || which > 1) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  int ok = 0;
+  int r = lio_state_estimation(ctx, o, which, max_iter, &ok);
+  if (r) return r;
+  if (iters_out) *iters_out = o->last_iters;
+  if (not_degenerate) *not_degenerate = ok;
+  return VINA_OK;
+}
+
+int vina_odom_map_update(vina_ctx* ctx)
+{
+  if (!ctx) return VINA_E_ARG;
+  return map_update(ctx, odom(ctx));
+}
+
+int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap)
+{
+  if (!ctx || !win_count) return VINA_E_ARG;
+  *win_count = odom(ctx)->win_count;
+  for (int i = 0; i < ctx->cfg.win_size && i < cap; i++) mp[i] = ctx->map.mp[i];
+  return ctx->cfg.win_size;
+}
+}

@@ -106,9 +106,10 @@ def small_sensor(base: str, n_beams: int, n_steps: int, seed: int | None = None)
 class World:
     """Axis-aligned rectangles: (axis, offset, lo0, hi0, lo1, hi1) over the two other axes."""
 
-    def __init__(self, size=(60.0, 30.0, 8.0), pitch=6.0, tiles=(1, 1)):
+    def __init__(self, size=(60.0, 30.0, 8.0), pitch=6.0, tiles=(1, 1), offset=(0.0, 0.0, 0.0)):
         rects = []
         sx, sy, sz = size
+        self.offset = np.asarray(offset, dtype=np.float64)
         for tx in range(tiles[0]):
             for ty in range(tiles[1]):
                 ox, oy = tx * sx, ty * sy
@@ -137,6 +138,16 @@ class World:
                             rects.append((1, y - h, xc - h, xc + h, 0.0, sz))
                             rects.append((1, y + h, xc - h, xc + h, 0.0, sz))
         self.rects = np.asarray(rects, dtype=np.float64)
+        # shift the whole world (negative offsets exercise the "-1 if negative" key rule)
+        other = {0: (1, 2), 1: (0, 2), 2: (0, 1)}
+        for r in self.rects:
+            a = int(r[0])
+            b0, b1 = other[a]
+            r[1] += self.offset[a]
+            r[2] += self.offset[b0]
+            r[3] += self.offset[b0]
+            r[4] += self.offset[b1]
+            r[5] += self.offset[b1]
         self.size = size
         self.tiles = tiles
 
@@ -165,7 +176,7 @@ class Trajectory:
     def __init__(self, world: World, handheld: bool = False, seed: int = 0):
         rng = np.random.default_rng(seed + 7919)
         sx, sy, sz = world.size
-        self.c = np.array([sx / 2, sy / 2, 1.6])
+        self.c = np.array([sx / 2, sy / 2, 1.6]) + world.offset
         self.A = np.array([sx * 0.30, sy * 0.12, 0.25])
         self.w = np.array([0.045, 0.09, 0.31]) * (2.0 if handheld else 1.0)
         self.ph = rng.uniform(0, 2 * np.pi, 3)
