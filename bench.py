@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — pts/s of the per-scan hot path (deskew -> down-sample -> var_init -> IEKF association /
+H-b reduction -> pvec_update -> voxel insert -> recut -> margi) on synthetic scans.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one scan of the named sensor shape through the whole path. The default workload is
+BASELINE.json configs[2] (RoboSense-128-shaped, 240 k pts/scan), the configuration the north_star's
+">= 20x on a 128-beam-shaped scan" target is quoted on; it fits one GPU. N > 1 = N independent
+sequences (replicas, one per rank, no data-path collective): "scaling": "weak".
+
+  value  whole-job pts/s with each raw scan already resident in HBM (vina_odom_step_resident)
+  e2e    the same metric through vina_odom_step from pinned HOST buffers (H2D of the scan and the
+         34-double readback of every IEKF iteration inside the timed region)
+  roofline  dominant kernel (k_iekf): algorithmic bytes per launch / CUDA-event launch duration
+  cpu_baseline  the oracle's -O3 -ffast-math build on this box's host cores (bounded sample)
+
+--impl reference times the reference's own CPU implementation of the path; the reference cannot be
+built in this image (ROS 2 / PCL / Eigen absent), so it is the oracle port (cpu_baseline.kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from vina_slam_b200 import synth  # noqa: E402
+
+METRIC = "pts/s IEKF point-to-plane update + voxel insert (deskew -> IEKF -> map insert/recut/margi, per scan)"
+UNIT = "pts/s"
+MAX_ITER = 4  # the VNC_lio budget, odometry.cpp:68 / local_mapping.cpp:413
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for nm, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def gen_sequence(cfg, seed, n_boot, n_steps):
+    seq = synth.Sequence(cfg, seed=seed)
+    boots = [seq.next_scan(deskewed=True) for _ in range(n_boot)]
+    scans = [seq.next_scan() for _ in range(n_steps)]
+    return boots, scans
+
+
+# --------------------------------------------------------------------------- reference arm / cpu baseline
+def run_cpu(cfg, boots, scans, warmup, steps):
+    """The oracle's -O3 -ffast-math build (the reference's flags, CMakeLists.txt:92-96): IEKF single-threaded,
+    insert/recut/margi on thread_num = 5 std::threads, exactly as the reference does."""
+    from oracle import oracle_py as op
+
+    op.build()
+    od = op.Odom(cfg, fast=True)
+    for sc in boots:
+        od.bootstrap(sc.xyzt, op.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    od.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+    times, stages, pts = [], np.zeros(4), 0
+    for k, sc in enumerate(scans[: warmup + steps]):
+        t0 = time.perf_counter()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=MAX_ITER)
+        dt = time.perf_counter() - t0
+        assert r == 0
+        if k >= warmup:
+            times.append(dt)
+            stages += od.stage_times()
+            pts += sc.xyzt.shape[0]
+    total = float(np.sum(times))
+    return dict(value=pts / total, ms_per_step=1e3 * total / len(times), stage_ms=(1e3 * stages / len(times)).tolist(),
+                steps=len(times), cores=max(1, cfg.thread_num))
+
+
+def main_reference(args, cfg):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    boots, scans = gen_sequence(cfg, cfg.seed, cfg.win_size, args.warmup + args.steps)
+    r = run_cpu(cfg, boots, scans, args.warmup, args.steps)
+    sample = (f"{r['steps']} full scans of {cfg.n_points} pts after {args.warmup} warm-up scans; IEKF 1 thread, "
+              f"map ops {cfg.thread_num} threads (reference threading)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "max_iter": MAX_ITER, "iekf_on": "full scan", "vnc_terms": False,
+                   "if_BA": 0},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "stage_ms": dict(zip(["odom", "insert", "recut", "margi"], r["stage_ms"]))},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    return (f"{cfg.name}: {cfg.n_beams} beams x {cfg.n_steps} az steps = {cfg.n_points} pts/scan, 10 Hz, "
+            f"{int(cfg.imu_rate)} Hz IMU, voxel {cfg.voxel_size} m, max_layer {cfg.max_layer}")
+
+
+# --------------------------------------------------------------------------- our arm
+def main_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from vina_slam_b200 import capi
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    W, K = args.warmup, args.steps
+    boots, scans = gen_sequence(cfg, cfg.seed + rank, cfg.win_size, W + K)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=1 << 20, hash_capacity_log2=21,
+                device=local)
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def new_ctx():
+        gx = capi.Ctx(cfg, **caps)
+        gx.set_stream(stream.cuda_stream)
+        for sc in boots:
+            gx.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+        return gx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- leg 1: inputs resident in HBM -------------------------------------------------------------
+    gx = new_ctx()
+    d_scans = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
+    gx.set_profiling(True)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    tm_rows, traj_err = [], 0.0
+    sampler = None
+    barrier()
+    for k, sc in enumerate(scans):
+        if k == W:
+            barrier()
+            sampler = ClockSampler(local)
+            sampler.start()
+            l_start = None
+        flush.fill_(k & 0xFF)  # evict L2 between timed iterations (outside the timed segments)
+        ev0[k].record(stream)
+        st = gx.step_resident(d_scans[k].data_ptr(), sc.xyzt.shape[0], sc.beg_time, sc.end_time, sc.imu, True,
+                              MAX_ITER)
+        ev1[k].record(stream)
+        if k >= W:
+            tm_rows.append(gx.timings())
+            traj_err = max(traj_err, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
+    barrier()
+    clocks = sampler.stop() if sampler else {}
+    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(W, W + K)])
+    pts = sum(sc.xyzt.shape[0] for sc in scans[W:])
+    t_res = float(step_ms.sum()) * 1e-3
+    launches = int(sum(t.kernel_launches for t in tm_rows))
+    iters = int(sum(t.iekf_iters for t in tm_rows))
+    iekf_kernel_ms = float(sum(t.iekf_kernel_ms for t in tm_rows))
+    stage = {f: float(np.mean([getattr(t, f) for t in tm_rows])) for f in
+             ("deskew_ms", "downsample_ms", "var_init_ms", "iekf_ms", "insert_ms", "recut_ms", "margi_ms", "total_ms")}
+
+    # algorithmic bytes of one k_iekf launch (DESIGN.md "Kernels"): 80 B/pt streamed + one 256-B leaf record
+    # per distinct associated leaf + one 16-B hash slot per point that misses its cached leaf
+    sc = scans[-1]
+    n_last = sc.xyzt.shape[0]
+    s = gx.get_state()
+    gx.iekf_begin(0, np.zeros(9), np.zeros(9))
+    gx.iekf_accumulate(np.array(s.R[:]), np.array(s.p[:]), debug=True)
+    a = gx.iekf_debug_assoc(n_last)
+    m = a["flags"] > 0
+    leaf_id = a["keys"][m] @ np.array([1 << 42, 1 << 21, 1], dtype=np.int64) * 4096 + a["codes"][m]
+    U = int(np.unique(leaf_id).shape[0])
+    match_frac = float(m.mean())
+    n_mean = pts / K
+    iters_per_step = iters / K
+    # iteration 0 misses everywhere; later iterations miss only where no leaf is cached yet
+    miss = (n_mean + (iters_per_step - 1) * n_mean * (1 - match_frac)) / max(iters_per_step, 1)
+    bytes_per_launch = 80.0 * n_mean + 256.0 * U + 16.0 * miss + 34 * 8
+    launch_ms = iekf_kernel_ms / max(iters, 1)
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    gx.close()
+    del d_scans
+
+    # ---- leg 2: end to end from pinned host buffers ---------------------------------------------------
+    gx = new_ctx()
+    pinned = [torch.from_numpy(sc.xyzt).pin_memory() for sc in scans]
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+    iters_e2e = 0
+    barrier()
+    for k, sc in enumerate(scans):
+        if k == W:
+            barrier()
+        flush.fill_(k & 0xFF)
+        e0[k].record(stream)
+        gx.step(pinned[k].numpy(), sc.beg_time, sc.imu, True, MAX_ITER)
+        e1[k].record(stream)
+        if k >= W:
+            iters_e2e += gx.timings().iekf_iters
+    barrier()
+    e2e_ms = np.array([e0[k].elapsed_time(e1[k]) for k in range(W, W + K)])
+    t_e2e = float(e2e_ms.sum()) * 1e-3
+    gx.close()
+
+    # ---- max over ranks, aggregate --------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        p = torch.tensor([float(pts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(p, op=dist.ReduceOp.SUM)
+        t_res, t_e2e, pts_all = float(t[0]), float(t[1]), float(p[0])
+    else:
+        pts_all = float(pts)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n_cpu = min(K, 8)
+            r = run_cpu(cfg, boots, scans, min(W, 2), n_cpu)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                   "sample": f"{r['steps']} full scans of the same workload ({cfg.n_points} pts each); IEKF 1 thread, "
+                             f"map ops {cfg.thread_num} threads",
+                   "ms_per_step": r["ms_per_step"],
+                   "stage_ms": dict(zip(["odom", "insert", "recut", "margi"], r["stage_ms"]))}
+        line = {
+            "metric": METRIC, "value": pts_all / t_res, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "max_iter": MAX_ITER, "iekf_on": "full scan",
+                       "vnc_terms": False, "if_BA": 0, "parallelism": f"replicas x{world}",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); steps timed individually "
+                             "with CUDA events on the launching stream and summed",
+                       "iekf_iters_per_step": iters_per_step, "gt_traj_err_m": traj_err},
+            "e2e": {"value": pts_all / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K,
+                    "h2d_bytes_per_step": int(16 * n_mean + 17096),
+                    "d2h_bytes_per_step": int(iters_e2e / K * 34 * 8 + 4)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_iekf", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_us": 1e3 * launch_ms,
+                         "launches_timed": iters, "unique_leaves": U, "match_frac": match_frac},
+            "stage_ms": stage,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="robosense128", choices=sorted(synth.SENSORS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    cfg = synth.SENSORS[args.workload]
+    if args.impl == "reference":
+        main_reference(args, cfg)
+    else:
+        main_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -197,10 +197,12 @@ int vina_odom_bootstrap(vina_ctx* ctx, const float* xyzt, int n, const vina_stat
  * max_iter <= 0: the reference's 20 (plain variant); 4 = the VNC_lio budget. */
 int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time, const vina_imu* imus, int m,
                    int iekf_on_full, int max_iter, vina_state* x_out);
-/* same scan, but the raw points are already on the device (installed by
- * vina_scan_upload): the timed "inputs resident in HBM" leg of bench.py */
-int vina_odom_step_resident(vina_ctx* ctx, double pcl_beg_time, const vina_imu* imus, int m, int iekf_on_full,
-                            int max_iter, vina_state* x_out);
+/* same scan, but the raw points are already in HBM: d_xyzt is a DEVICE pointer
+ * (n x 4 float32) that is copied device-to-device into the ctx's scan buffer;
+ * pcl_end_time = pcl_beg_time + curvature of the last point (sync.cpp:40),
+ * which the caller knows. The timed "inputs resident" leg of bench.py. */
+int vina_odom_step_resident(vina_ctx* ctx, const void* d_xyzt, int n, double pcl_beg_time, double pcl_end_time,
+                            const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out);
 /* stage-wise pieces of the step, for parity tests */
 int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
                         vina_imu_pose* poses_out, int cap); /* returns #poses */

@@ -123,11 +123,14 @@ def _iekf_compare(oracle_lib, gpu_lib, cfg, n_iter=4, world=None):
         assert np.array_equal(a["codes"], d["codes"]), f"associated leaves differ at iteration {it}"
         assert g["match_num"] == d["match_num"] and d["match_num"] > 0.3 * n
         m = d["flags"] > 0
-        assert rel_err(a["sigma"][m], d["sigma"][m]) < 1e-9
+        # sigma_l = J plane_var J^T + n^T var n cancels ~7 digits (plane_var carries the lever arm of a
+        # centre tens of metres from the origin), so rounding-level differences show up at ~1e-9
+        assert np.max(np.abs(a["sigma"][m] - d["sigma"][m]) / d["sigma"][m]) < 1e-6
         assert rel_err(g["HTH"], d["HTH"]) < 1e-4 and rel_err(g["HTz"], d["HTz"]) < 1e-4
         assert rel_err(g["nnt"], d["nnt"]) < 1e-4
         # the design is far tighter than the contract
-        assert rel_err(g["HTH"], d["HTH"]) < 1e-10 and rel_err(g["HTz"], d["HTz"]) < 1e-9
+        assert rel_err(g["HTH"], d["HTH"]) < 1e-7 and rel_err(g["HTz"], d["HTz"]) < 1e-7
+        assert rel_err(g["nnt"], d["nnt"]) < 1e-12
         # same sums from the non-debug kernel
         g2 = gx.iekf_accumulate(d["R_col"], d["p"], debug=False)
         assert np.array_equal(g2["HTH"], g["HTH"]) and g2["match_num"] == g["match_num"]
@@ -172,9 +175,10 @@ def _compare_maps(mo, mg, exact_cov=False):
     assert np.array_equal(mo["center"], mg["center"]) and np.array_equal(mo["normal"], mg["normal"])
     assert np.array_equal(mo["radius"], mg["radius"])
     # covariance-derived quantities: the device stores point covariances symmetric -> tolerance
-    for f in ("cov_add", "plane_var"):
+    # (plane_var = u_c cov_add u_c^T cancels several digits, like sigma_l)
+    for f, tol in (("cov_add", 1e-12), ("plane_var", 1e-7)):
         den = np.maximum(np.abs(mo[f]).max(axis=1, keepdims=True), 1e-300)
-        assert np.max(np.abs(mo[f] - mg[f]) / den) < 1e-9, f"{f} differs"
+        assert np.max(np.abs(mo[f] - mg[f]) / den) < tol, f"{f} differs"
     return mo, mg
 
 

@@ -319,10 +319,13 @@ class Ctx:
                                          C.c_int(1 if iekf_on_full else 0), C.c_int(max_iter), C.byref(out)))
         return out
 
-    def step_resident(self, beg_time: float, imu7: np.ndarray, iekf_on_full: bool = True, max_iter: int = 4):
+    def step_resident(self, d_ptr: int, n: int, beg_time: float, end_time: float, imu7: np.ndarray,
+                      iekf_on_full: bool = True, max_iter: int = 4):
+        """d_ptr: device pointer to n x 4 float32 raw points already in HBM."""
         im = imu_array(np.asarray(imu7, dtype=np.float64))
         out = VinaState()
-        self._ck(self.lib.vina_odom_step_resident(self.h, C.c_double(beg_time), im.ctypes.data_as(C.c_void_p),
+        self._ck(self.lib.vina_odom_step_resident(self.h, C.c_void_p(d_ptr), C.c_int(n), C.c_double(beg_time),
+                                                  C.c_double(end_time), im.ctypes.data_as(C.c_void_p),
                                                   C.c_int(im.shape[0]), C.c_int(1 if iekf_on_full else 0),
                                                   C.c_int(max_iter), C.byref(out)))
         return out

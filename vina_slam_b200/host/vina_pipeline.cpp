@@ -395,12 +395,12 @@ static void collect_timings(vina_ctx* ctx)
 }
 
 // the scan body of thd_odometry_localmapping (local_mapping.cpp:389-546); the raw scan is on the device
-static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, float last_curvature,
+static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
                               const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
 {
   const int l0 = ctx->launches;
   o->pcl_beg_time = pcl_beg_time;
-  o->pcl_end_time = pcl_beg_time + (double)last_curvature;  // sync.cpp:40
+  o->pcl_end_time = pcl_end_time;
   int r = imu_propagate(ctx, o, imus, m);
   if (r) return r;
   cudaEvent_t* ev = ctx->ev;
@@ -498,23 +498,23 @@ int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time,
   if (!ctx || !xyzt || !imus || n <= 0 || m <= 0) return VINA_E_ARG;
   int r = vina_scan_upload(ctx, xyzt, n);
   if (r) return r;
-  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, xyzt[4 * (size_t)(n - 1) + 3], imus, m, iekf_on_full,
-                            max_iter, x_out);
+  // pcl_end_time = pcl_beg_time + back().curvature (sync.cpp:40)
+  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, pcl_beg_time + (double)xyzt[4 * (size_t)(n - 1) + 3], imus, m,
+                            iekf_on_full, max_iter, x_out);
 }
 
-int vina_odom_step_resident(vina_ctx* ctx, double pcl_beg_time, const vina_imu* imus, int m, int iekf_on_full,
-                            int max_iter, vina_state* x_out)
+int vina_odom_step_resident(vina_ctx* ctx, const void* d_xyzt, int n, double pcl_beg_time, double pcl_end_time,
+                            const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
 {
-  if (!ctx || !imus || m <= 0 || ctx->n_scan <= 0) return VINA_E_ARG;
-  float last[4];
+  if (!ctx || !d_xyzt || !imus || m <= 0 || n <= 0) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points", n);
   int r = vn_check_cuda(ctx,
-                        cudaMemcpyAsync(last, ctx->d_scan + (ctx->n_scan - 1), sizeof(float4), cudaMemcpyDeviceToHost,
+                        cudaMemcpyAsync(ctx->d_scan, d_xyzt, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice,
                                         ctx->stream),
-                        "read last curvature");
+                        "device-to-device scan copy");
   if (r) return r;
-  r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync");
-  if (r) return r;
-  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, last[3], imus, m, iekf_on_full, max_iter, x_out);
+  ctx->n_scan = n;
+  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, pcl_end_time, imus, m, iekf_on_full, max_iter, x_out);
 }
 
 int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,

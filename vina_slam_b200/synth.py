@@ -324,12 +324,10 @@ class Sequence:
         toff32 = self.toff.astype(np.float32)
         # pcl_end_time = beg + last curvature (sync.cpp:40), curvature is float32
         t_abs = beg + toff32.astype(np.float64)
-        # decide the kept set first so "end" is the last kept point's time
-        pts, keep = self._measure(t_abs, None, rng)
         if deskewed:
-            end_time = beg + float(toff32[keep][-1])
-            pts, keep2 = self._measure(t_abs, end_time, np.random.default_rng([self.seed, 2, k]))
-            keep = keep & keep2
+            pts, keep = self._measure(t_abs, beg + float(toff32[-1]), rng)
+        else:
+            pts, keep = self._measure(t_abs, None, rng)
         xyzt = np.concatenate([pts[keep], toff32[keep, None].astype(np.float64)], axis=1).astype(np.float32)
         end_time = beg + float(xyzt[-1, 3])
         # IMU samples with stamp <= end_time not yet handed out (sync.cpp:63-72)
