@@ -1,12 +1,16 @@
 // Voxel-map kernels: pvec_update + cut_voxel_multi (a8-a10), multi_recut (a11),
 // multi_margi (a12), export. Compiled with -fmad=false (see scan_kernels.cu).
 //
-// Parallel decomposition mirrors the reference's own task parallelism
-// (fork-join over ROOT voxels, voxel_map.cpp:94-134, local_mapping.cpp:17-84,
-// 144-201) scaled from 5 host threads to one GPU thread per root/leaf: the
-// work inside one root keeps the reference's sequential order, so every
-// cluster sum (P, v, N) and therefore every plane decision is reproduced
-// bit-for-bit; only the order in which independent roots are visited differs.
+// Parallel decomposition. The reference forks 5 host threads over ROOT voxels
+// (voxel_map.cpp:94-134, local_mapping.cpp:17-84, 144-201). Here every octree
+// NODE is one unit of work: recut / margi walk the trees of surf_map_slide
+// layer by layer (one launch per layer, one thread per node, the next layer's
+// node list is built with an atomic append), and the per-leaf accumulation of
+// an insert is done by one warp per touched leaf. Inside a leaf the reference's
+// sequential order is kept for the cluster sums (P, v, N: one lane per scalar,
+// points in ascending index order), so those sums - and through them every
+// eigen-decomposition and plane decision - are reproduced bit for bit; only
+// the order in which independent nodes are visited differs.
 #include "vn_kernels.cuh"
 
 #define SPIN_LIMIT 4000000
@@ -47,6 +51,7 @@ __device__ int make_child(const MapView& M, int parent, int ci)
   h.flags = 0;
   NodeCold& c = M.cold[id];
   c.rootkey = M.cold[parent].rootkey;
+  c.root = M.cold[parent].root;
   c.path = M.cold[parent].path | (ci << (3 * ph.layer));
   c.fix_head = c.fix_tail = -1;
   for (int k = 0; k < 8; k++) c.children[k] = -1;
@@ -106,6 +111,7 @@ __global__ void __launch_bounds__(256)
         nh.flags = 0;
         NodeCold& nc = M.cold[id];
         nc.rootkey = key;
+        nc.root = id;
         nc.path = 0;
         nc.fix_head = nc.fix_tail = -1;
         for (int k = 0; k < 8; k++) nc.children[k] = -1;
@@ -223,73 +229,270 @@ __global__ void __launch_bounds__(256)
   sc.idx[M.cold[leaf].pend_off + sc.rank_of[i]] = i;
 }
 
-// insert, phase 3: OctoTree::push for every point of the leaf in ascending point
-// order (octree.cpp:151-177; order = voxel_map.cpp:86 push_back(i))
-__global__ void __launch_bounds__(64) k_insert_accum(MapView M, ScanView scan, InsertScratch sc, int win_ord)
+// ---------------------------------------------------------------------------
+// Warp-cooperative leaf accumulation (used by the insert and by the subdivision).
+// One warp owns one leaf; points are consumed strictly in the reference's order.
+//   lanes  0.. 8 own cluster A (P[6] lower triangle, v[3])    exact single-rounding ops
+//   lanes  9..17 own cluster B, lanes 18..26 own cluster C
+//   every lane   owns cov_add entries `lane` and `lane + 32` of the 45 packed ones:
+//                entry(r,c) += W_r V W_c^T with W = [Bi; I3] (Bf_var, octree.cpp:83-92)
+// Points are staged 32 at a time in shared memory (one parallel gather), then applied one by one.
+struct LaneRole
 {
-  int nt = sc.counters[1];
-  const int mord = M.mp[win_ord];
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nt; j += gridDim.x * blockDim.x)
+  int er[2], ec[2];       // cov entries (row, col), -1 = none
+  float coefR[2][3], coefC[2][3];
+  int compR[2][3], compC[2][3];
+  int ck, ci, cj;         // cluster scalar: P[ck] = sum s[ci]*s[cj] (ck<6) or v[ck-6] = sum s[ci]
+};
+
+__device__ __forceinline__ double sel4(const double* v, int comp)
+{
+  return comp == 0 ? v[0] : (comp == 1 ? v[1] : (comp == 2 ? v[2] : 1.0));
+}
+
+__device__ void role_init(int lane, LaneRole& L)
+{
+  // W[r][j] = coef * vec[comp] (comp 3 = the constant 1): Bi rows [2x 0 0; y x 0; z 0 x; 0 2y 0; 0 z y; 0 0 2z], then I3
+  const float A[9][3] = { { 2, 0, 0 }, { 1, 1, 0 }, { 1, 0, 1 }, { 0, 2, 0 }, { 0, 1, 1 }, { 0, 0, 2 },
+                          { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } };
+  const int Cc[9][3] = { { 0, 0, 0 }, { 1, 0, 0 }, { 2, 0, 0 }, { 0, 1, 0 }, { 0, 2, 1 }, { 0, 0, 2 },
+                         { 3, 3, 3 }, { 3, 3, 3 }, { 3, 3, 3 } };
+  for (int q = 0; q < 2; q++)
   {
-    int leaf = sc.touched[j];
+    int e = lane + 32 * q, r = 0;
+    L.er[q] = L.ec[q] = -1;
+    if (e < 45)
+    {
+      while (e >= 9 - r)
+      {
+        e -= 9 - r;
+        r++;
+      }
+      L.er[q] = r;
+      L.ec[q] = r + e;
+    }
+    const int rr = L.er[q] < 0 ? 0 : L.er[q], cc = L.ec[q] < 0 ? 0 : L.ec[q];
+    for (int j = 0; j < 3; j++)
+    {
+      L.coefR[q][j] = A[rr][j];
+      L.compR[q][j] = Cc[rr][j];
+      L.coefC[q][j] = A[cc][j];
+      L.compC[q][j] = Cc[cc][j];
+    }
+  }
+  const int li[6] = { 0, 1, 2, 1, 2, 2 }, lj[6] = { 0, 0, 0, 1, 1, 2 };
+  L.ck = lane % 9;
+  L.ci = L.ck < 6 ? li[L.ck] : L.ck - 6;
+  L.cj = L.ck < 6 ? lj[L.ck] : 0;
+}
+
+__device__ __forceinline__ double cov_term(const LaneRole& L, int q, const double* V, const double* vec)
+{
+  double wr[3], wc[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+  {
+    wr[j] = (double)L.coefR[q][j] * sel4(vec, L.compR[q][j]);
+    wc[j] = (double)L.coefC[q][j] * sel4(vec, L.compC[q][j]);
+  }
+  const double t0 = V[0] * wc[0] + V[3] * wc[1] + V[6] * wc[2];
+  const double t1 = V[1] * wc[0] + V[4] * wc[1] + V[7] * wc[2];
+  const double t2 = V[2] * wc[0] + V[5] * wc[1] + V[8] * wc[2];
+  return wr[0] * t0 + wr[1] * t1 + wr[2] * t2;
+}
+
+// PointCluster::push for the scalar this lane owns (types.hpp:137-142)
+__device__ __forceinline__ double cluster_term(const LaneRole& L, double cl, const double* s)
+{
+  const double a_i = L.ci == 0 ? s[0] : (L.ci == 1 ? s[1] : s[2]);
+  const double a_j = L.cj == 0 ? s[0] : (L.cj == 1 ? s[1] : s[2]);
+  return L.ck < 6 ? da(cl, dm(a_i, a_j)) : da(cl, a_i);
+}
+__device__ __forceinline__ double cluster_get(const Cluster& c, int ck) { return ck < 6 ? c.P[ck] : c.v[ck - 6]; }
+__device__ __forceinline__ void cluster_set(Cluster& c, int ck, double v)
+{
+  if (ck < 6)
+    c.P[ck] = v;
+  else
+    c.v[ck - 6] = v;
+}
+
+#define PT_STRIDE 13   // staged point: p[3] (cluster B/C input), v[6], pw[3] (cluster A input and Bf_var vector)
+#define RED_STRIDE 47  // staged Bf_var contribution of one point: 45 packed entries
+
+// The 45 packed upper-triangle entries of Bf_var(pv, vec) (octree.cpp:83-92) for one point:
+// [[Bi V Bi^T, Bi V], [., V]], Bi = d(xx,xy,xz,yy,yz,zz)/dp. Fully unrolled, Bi's sparsity used.
+__device__ __forceinline__ void bf_var_terms(const double* v, const double* p, double* o)
+{
+  const double x = p[0], y = p[1], z = p[2];
+  const double r0[3] = { v[0], v[1], v[2] }, r1[3] = { v[1], v[3], v[4] }, r2[3] = { v[2], v[4], v[5] };
+  double U[6][3];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+  {
+    U[0][j] = 2.0 * x * r0[j];
+    U[1][j] = y * r0[j] + x * r1[j];
+    U[2][j] = z * r0[j] + x * r2[j];
+    U[3][j] = 2.0 * y * r1[j];
+    U[4][j] = z * r1[j] + y * r2[j];
+    U[5][j] = 2.0 * z * r2[j];
+  }
+  int t = 0;
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+  {
+    const double c6[6] = { 2.0 * x * U[r][0],           y * U[r][0] + x * U[r][1], z * U[r][0] + x * U[r][2],
+                           2.0 * y * U[r][1],           z * U[r][1] + y * U[r][2], 2.0 * z * U[r][2] };
+#pragma unroll
+    for (int c = r; c < 6; c++) o[t++] = c6[c];
+#pragma unroll
+    for (int c = 0; c < 3; c++) o[t++] = U[r][c];
+  }
+  o[t++] = v[0];
+  o[t++] = v[1];
+  o[t++] = v[2];
+  o[t++] = v[3];
+  o[t++] = v[4];
+  o[t++] = v[5];
+}
+
+// insert, phase 3: OctoTree::push for every point of a leaf (octree.cpp:151-177), one warp per touched
+// leaf, points in ascending index order (= voxel_map.cpp:86 push_back(i)).
+// cluster A = pcr_add (world point, lanes 0..8), cluster B = pcrs_local[slot] (body point, lanes 9..17):
+// sequential exact sums. cov_add: every lane computes the 45 Bf_var terms of one staged point, the warp
+// then sums the columns (lane owns packed entries `lane` and `lane + 32`).
+#define ACC_WARPS 3
+__global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, ScanView scan, InsertScratch sc, int win_ord)
+{
+  __shared__ double pt_s[ACC_WARPS][32][PT_STRIDE];
+  __shared__ double red_s[ACC_WARPS][32][RED_STRIDE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nt = sc.counters[1];
+  const int mord = M.mp[win_ord];
+  LaneRole L;
+  role_init(lane, L);
+  double(*pt)[PT_STRIDE] = pt_s[warp];
+  double(*red)[RED_STRIDE] = red_s[warp];
+  const bool has2 = lane + 32 < 45;
+
+  for (int j = blockIdx.x * ACC_WARPS + warp; j < nt; j += gridDim.x * ACC_WARPS)
+  {
+    const int leaf = sc.touched[j];
     NodeCold& c = M.cold[leaf];
     const int cnt = c.pend_cnt;
     int* idx = sc.idx + c.pend_off;
-    for (int a = 1; a < cnt; a++)  // arrival order is nearly sorted already
+    // ascending point order
+    if (cnt <= 32)
     {
-      int v = idx[a], b = a - 1;
-      while (b >= 0 && idx[b] > v)
+      const int v = lane < cnt ? idx[lane] : 0x7fffffff;
+      int rank = 0;
+      for (int o = 0; o < 32; o++)
       {
-        idx[b + 1] = idx[b];
-        b--;
+        int u = __shfl_sync(0xffffffffu, v, o);
+        rank += (u < v) ? 1 : 0;
       }
-      idx[b + 1] = v;
+      __syncwarp();
+      if (lane < cnt) idx[rank] = v;
     }
+    else if (lane == 0)
+    {
+      for (int a = 1; a < cnt; a++)  // arrival order is nearly sorted already
+      {
+        int v = idx[a], b = a - 1;
+        while (b >= 0 && idx[b] > v)
+        {
+          idx[b + 1] = idx[b];
+          b--;
+        }
+        idx[b + 1] = v;
+      }
+    }
+    __syncwarp();
     const bool store = M.hot[leaf].layer < M.max_layer;
-    int woff = 0;
     const int old_cnt = c.win_cnt[mord];
+    int woff = 0;
     if (store)
     {
-      woff = atomicAdd(&M.win_cursor[mord], cnt + old_cnt);
+      if (lane == 0) woff = atomicAdd(&M.win_cursor[mord], cnt + old_cnt);
+      woff = __shfl_sync(0xffffffffu, woff, 0);
       if ((long long)woff + cnt + old_cnt > M.win_cap)
       {
-        atomicOr(M.status, VN_ST_WIN_FULL);
-        c.pend_cnt = 0;
+        if (lane == 0)
+        {
+          atomicOr(M.status, VN_ST_WIN_FULL);
+          c.pend_cnt = 0;
+        }
         continue;
       }
       PointRec* pool = M.win_pool[mord];
-      for (int a = 0; a < old_cnt; a++) pool[woff + a] = pool[c.win_off[mord] + a];
+      for (int a = lane; a < old_cnt; a += 32) pool[woff + a] = pool[c.win_off[mord] + a];
     }
-    c.has_sw = 1;   // sw acquired (octree.cpp:154-164); recycled windows are empty
-    c.isexist = 1;  // octree.cpp:165-166
-    Cluster add = c.pcr_add, loc = c.pcrs_local[mord];
-    double cov[45];
-    for (int k = 0; k < 45; k++) cov[k] = c.cov_add[k];
-    for (int a = 0; a < cnt; a++)
+    double cl = 0.0;
+    if (lane < 9)
+      cl = cluster_get(c.pcr_add, L.ck);
+    else if (lane < 18)
+      cl = cluster_get(c.pcrs_local[mord], L.ck);
+    double cv0 = c.cov_add[lane];
+    double cv1 = has2 ? c.cov_add[lane + 32] : 0.0;
+    for (int base = 0; base < cnt; base += 32)
     {
-      int i = idx[a];
-      PointRec pr;
-      for (int k = 0; k < 3; k++) pr.p[k] = scan.p[k][i];
-      for (int k = 0; k < 6; k++) pr.v[k] = sc.vw[k][i];
-      double pw[3] = { sc.pw[0][i], sc.pw[1][i], sc.pw[2][i] };
-      if (store) M.win_pool[mord][woff + old_cnt + a] = pr;
-      cluster_push(loc, pr.p);
-      cluster_push(add, pw);
-      bf_var_add(cov, pr.v, pw);
+      const int a = base + lane;
+      if (a < cnt)
+      {
+        const int i = idx[a];
+        PointRec pr;
+        double pw[3];
+        for (int k = 0; k < 3; k++) pr.p[k] = scan.p[k][i];
+        for (int k = 0; k < 6; k++) pr.v[k] = sc.vw[k][i];
+        for (int k = 0; k < 3; k++) pw[k] = sc.pw[k][i];
+        for (int k = 0; k < 3; k++) pt[lane][k] = pr.p[k];
+        for (int k = 0; k < 3; k++) pt[lane][9 + k] = pw[k];
+        if (store) M.win_pool[mord][woff + old_cnt + a] = pr;
+        double o[45];
+        bf_var_terms(pr.v, pw, o);
+#pragma unroll
+        for (int e = 0; e < 45; e++) red[lane][e] = o[e];
+      }
+      __syncwarp();
+      const int m = min(32, cnt - base);
+      if (lane < 9)
+        for (int r = 0; r < m; r++) cl = cluster_term(L, cl, pt[r] + 9);
+      else if (lane < 18)
+        for (int r = 0; r < m; r++) cl = cluster_term(L, cl, pt[r]);
+      double s0 = 0.0, s1 = 0.0;
+      for (int r = 0; r < m; r++)
+      {
+        s0 += red[r][lane];
+        if (has2) s1 += red[r][lane + 32];
+      }
+      cv0 += s0;
+      cv1 += s1;
+      __syncwarp();
     }
-    c.pcr_add = add;
-    c.pcrs_local[mord] = loc;
-    for (int k = 0; k < 45; k++) c.cov_add[k] = cov[k];
-    if (store)
+    if (lane < 9)
+      cluster_set(c.pcr_add, L.ck, cl);
+    else if (lane < 18)
+      cluster_set(c.pcrs_local[mord], L.ck, cl);
+    c.cov_add[lane] = cv0;
+    if (has2) c.cov_add[lane + 32] = cv1;
+    if (lane == 0)
     {
-      c.win_off[mord] = woff;
-      c.win_cnt[mord] = cnt + old_cnt;
+      c.pcr_add.N += cnt;
+      c.pcrs_local[mord].N += cnt;
+      c.has_sw = 1;   // sw acquired (octree.cpp:154-164); recycled windows are empty
+      c.isexist = 1;  // octree.cpp:165-166
+      if (store)
+      {
+        c.win_off[mord] = woff;
+        c.win_cnt[mord] = cnt + old_cnt;
+      }
+      c.pend_cnt = 0;
     }
-    c.pend_cnt = 0;
+    __syncwarp();
   }
 }
 
-// ---------------------------------------------------------------------------
+
 // push_fix into a child (octree.cpp:179-188)
 __device__ __forceinline__ void child_push_fix(NodeCold& k, const PointRec& pr)
 {
@@ -321,171 +524,355 @@ __device__ int fix_append(const MapView& M, NodeCold& c, int cnt)
   return off;
 }
 
-// the subdivision branch of OctoTree::recut (octree.cpp:375-387): fix_divide (:257-277),
-// subdivide per window frame (:279-300), release of the parent's SlideWindow
-__device__ void split_leaf(const MapView& M, int n, int win_count, const PoseBuf& xb)
+__device__ __forceinline__ const int* layer_nodes(const MapView& M, const LayerLists& LL, int layer, int* count)
 {
-  NodeCold& c = M.cold[n];
-  NodeHot& h = M.hot[n];
-  const int child_layer = h.layer + 1;
-  const bool store = child_layer < M.max_layer;
-  int cnt8[8], off8[8], fill8[8];
-
-  if (c.pcr_fix.N != 0)
+  if (layer == 0)
   {
-    for (int k = 0; k < 8; k++) cnt8[k] = 0, fill8[k] = 0, off8[k] = -1;
-    for (int s = c.fix_head; s >= 0; s = M.fix_segs[s].next)
-    {
-      const FixSeg seg = M.fix_segs[s];
-      for (int a = 0; a < seg.cnt; a++) cnt8[child_index(M.fix_pool[seg.off + a].p, h.vcenter)]++;
-    }
-    for (int k = 0; k < 8; k++)
-      if (cnt8[k] > 0)
-      {
-        if (c.children[k] < 0) c.children[k] = make_child(M, n, k);
-        if (c.children[k] >= 0 && store) off8[k] = fix_append(M, M.cold[c.children[k]], cnt8[k]);
-      }
-    for (int s = c.fix_head; s >= 0; s = M.fix_segs[s].next)
-    {
-      const FixSeg seg = M.fix_segs[s];
-      for (int a = 0; a < seg.cnt; a++)
-      {
-        PointRec pr = M.fix_pool[seg.off + a];
-        int k = child_index(pr.p, h.vcenter);
-        int kid = c.children[k];
-        if (kid < 0) continue;
-        if (store && off8[k] >= 0) M.fix_pool[off8[k] + fill8[k]++] = pr;
-        child_push_fix(M.cold[kid], pr);
-      }
-    }
-    c.fix_head = c.fix_tail = -1;  // PVec().swap(point_fix)
-    c.fix_count = 0;
+    *count = M.slide_count[M.slide_cur];
+    return M.slide_list[M.slide_cur];
   }
-
-  for (int si = 0; si < win_count; si++)
-  {
-    const int slot = M.mp[si];
-    const int np = c.win_cnt[slot];
-    if (np == 0) continue;
-    const PointRec* src = M.win_pool[slot] + c.win_off[slot];
-    const PoseD& x = xb.x[si];
-    for (int k = 0; k < 8; k++) cnt8[k] = 0, fill8[k] = 0, off8[k] = -1;
-    for (int a = 0; a < np; a++)
-    {
-      double pw[3];
-      rot_trans(x.R, x.p, src[a].p, pw);
-      cnt8[child_index(pw, h.vcenter)]++;
-    }
-    for (int k = 0; k < 8; k++)
-      if (cnt8[k] > 0)
-      {
-        if (c.children[k] < 0) c.children[k] = make_child(M, n, k);
-        int kid = c.children[k];
-        if (kid < 0) continue;
-        NodeCold& kc = M.cold[kid];
-        kc.has_sw = 1;
-        kc.isexist = 1;
-        if (store)
-        {
-          int woff = atomicAdd(&M.win_cursor[slot], cnt8[k]);
-          if ((long long)woff + cnt8[k] > M.win_cap)
-          {
-            atomicOr(M.status, VN_ST_WIN_FULL);
-            continue;
-          }
-          off8[k] = woff;
-          kc.win_off[slot] = woff;
-          kc.win_cnt[slot] = cnt8[k];
-        }
-      }
-    for (int a = 0; a < np; a++)
-    {
-      PointRec pr = src[a];
-      double pw[3];
-      rot_trans(x.R, x.p, pr.p, pw);
-      int k = child_index(pw, h.vcenter);
-      int kid = c.children[k];
-      if (kid < 0) continue;
-      NodeCold& kc = M.cold[kid];
-      if (store && off8[k] >= 0) M.win_pool[slot][off8[k] + fill8[k]++] = pr;
-      cluster_push(kc.pcrs_local[slot], pr.p);
-      cluster_push(kc.pcr_add, pw);
-      bf_var_add(kc.cov_add, pr.v, pw);
-    }
-  }
-  // sw->clear(); sws.push_back(sw); sw = nullptr; octo_state = 1 (octree.cpp:384-387)
-  for (int s = 0; s < M.win_size; s++)
-  {
-    c.win_cnt[s] = 0;
-    cluster_clear(c.pcrs_local[s]);
-  }
-  c.has_sw = 0;
-  h.flags |= VN_FLAG_INTERIOR;
+  *count = LL.count[layer];
+  return LL.list[layer];
 }
 
-// OctoTree::recut over one root (octree.cpp:335-393) followed by tras_opt's
-// BA-factor marking (octree.cpp:498-521, local_mapping.cpp:196-200)
-__global__ void __launch_bounds__(64) k_recut(MapView M, int cur, int win_count, PoseBuf xb)
+// OctoTree::recut (octree.cpp:335-393) for the nodes of one layer, then tras_opt's BA-factor
+// marking of the same node (octree.cpp:498-521, local_mapping.cpp:196-200). Leaves that must be
+// subdivided go to the layer's split list (k_split); children of interior nodes are appended to the
+// next layer's node list.
+__global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, int layer)
 {
-  const int nroots = M.slide_count[cur];
-  if (nroots < M.thread_num) return;  // local_mapping.cpp:150-154
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
+  if (M.slide_count[M.slide_cur] < M.thread_num) return;  // local_mapping.cpp:150-154
+  int nn;
+  const int* nodes = layer_nodes(M, LL, layer, &nn);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
   {
-    int stack[40];
-    int sp = 0;
-    const int root = M.slide_list[cur][j];
-    stack[sp++] = root;
-    while (sp > 0)
+    const int n = nodes[j];
+    NodeHot& h = M.hot[n];
+    NodeCold& c = M.cold[n];
+    if (!(h.flags & VN_FLAG_INTERIOR))
     {
-      int n = stack[--sp];
-      NodeHot& h = M.hot[n];
-      NodeCold& c = M.cold[n];
-      if (!(h.flags & VN_FLAG_INTERIOR))
+      c.opt_state = -1;
+      if ((double)c.pcr_add.N <= M.min_point[h.layer])
       {
-        c.opt_state = -1;
-        if ((double)c.pcr_add.N <= M.min_point[h.layer])
-        {
-          h.flags &= ~VN_FLAG_PLANE;
-          continue;
-        }
-        if (!c.isexist || !c.has_sw) continue;
-        double L[6], ev[3], Q[9];
-        cluster_cov(c.pcr_add, L);
-        eig3_sym(L, ev, Q);
-        for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
-        for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
-        bool is_plane = (ev[0] < M.min_eigen_value) && ((ev[0] / ev[2]) < M.thre[h.layer]);  // octree.cpp:198-201
-        if (is_plane)
-          h.flags |= VN_FLAG_PLANE;
-        else
-          h.flags &= ~VN_FLAG_PLANE;
-        if (is_plane || h.layer >= M.max_layer) continue;
-        split_leaf(M, n, win_count, xb);
+        h.flags &= ~VN_FLAG_PLANE;
+        continue;
       }
-      for (int k = 7; k >= 0; k--)
-        if (c.children[k] >= 0) stack[sp++] = c.children[k];
-    }
-    // tras_opt: which leaves are BA factors
-    sp = 0;
-    stack[sp++] = root;
-    while (sp > 0)
-    {
-      int n = stack[--sp];
-      NodeHot& h = M.hot[n];
-      NodeCold& c = M.cold[n];
-      if (!(h.flags & VN_FLAG_INTERIOR))
+      if (!c.isexist || !c.has_sw) continue;
+      double L[6], ev[3], Q[9];
+      cluster_cov(c.pcr_add, L);
+      eig3_sym(L, ev, Q);
+      for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
+      for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
+      const bool is_plane = (ev[0] < M.min_eigen_value) && ((ev[0] / ev[2]) < M.thre[h.layer]);  // octree.cpp:198-201
+      if (is_plane)
       {
-        if (c.isexist && (h.flags & VN_FLAG_PLANE) && c.has_sw)
-          if (!(c.eig_value[0] / c.eig_value[1] > 0.12)) c.opt_state = 1;
+        h.flags |= VN_FLAG_PLANE;
+        if (!(ev[0] / ev[1] > 0.12)) c.opt_state = 1;  // tras_opt: this leaf is a BA factor
+        continue;
+      }
+      h.flags &= ~VN_FLAG_PLANE;
+      if (h.layer >= M.max_layer) continue;
+      int pos = atomicAdd(&LL.count[4 + layer], 1);
+      LL.split[pos] = n;  // k_split subdivides it and queues its children
+      continue;
+    }
+    if (layer < 3)
+      for (int k = 0; k < 8; k++)
+        if (c.children[k] >= 0)
+        {
+          int pos = atomicAdd(&LL.count[layer + 1], 1);
+          LL.list[layer + 1][pos] = c.children[k];
+        }
+  }
+}
+
+// The subdivision branch of OctoTree::recut (octree.cpp:375-387): fix_divide (:257-277), subdivide per
+// window frame (:279-300), release of the parent's SlideWindow (:384-387). One warp per splitting leaf.
+// Source classes in the reference's order: class 0 = point_fix, class 1+si = sw->points[mp[si]].
+// The parent's points are streamed once, 32 at a time; every lane keeps the running sums of its scalar
+// (cluster role / two cov_add entries) for all 8 children, and rows are applied in list order, so each
+// child's cluster sums are those of the reference's sequential loop.
+#define SPLIT_WARPS 2
+__global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
+{
+  __shared__ double pt_s[SPLIT_WARPS][32][PT_STRIDE];
+  __shared__ double red_s[SPLIT_WARPS][32][RED_STRIDE];
+  __shared__ int cnt_s[SPLIT_WARPS][11][8];
+  __shared__ int off_s[SPLIT_WARPS][11][8];
+  __shared__ int kid_s[SPLIT_WARPS][8];
+  __shared__ int kk_s[SPLIT_WARPS][32];
+  if (M.slide_count[M.slide_cur] < M.thread_num) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  LaneRole L;
+  role_init(lane, L);
+  double(*pt)[PT_STRIDE] = pt_s[warp];
+  double(*red)[RED_STRIDE] = red_s[warp];
+  int(*cnt)[8] = cnt_s[warp];
+  int(*off)[8] = off_s[warp];
+  int* kid = kid_s[warp];
+  int* kks = kk_s[warp];
+  const bool has2 = lane + 32 < 45;
+  const int nsplit = LL.count[4 + layer];
+  for (int j = blockIdx.x * SPLIT_WARPS + warp; j < nsplit; j += gridDim.x * SPLIT_WARPS)
+  {
+    const int n = LL.split[j];
+    NodeCold& c = M.cold[n];
+    NodeHot& h = M.hot[n];
+    const bool store = (h.layer + 1) < M.max_layer;
+    const double vc[3] = { h.vcenter[0], h.vcenter[1], h.vcenter[2] };
+    const bool has_fix = c.pcr_fix.N != 0;
+    for (int t = lane; t < 88; t += 32)
+    {
+      (&cnt[0][0])[t] = 0;
+      (&off[0][0])[t] = -1;
+    }
+    __syncwarp();
+    // pass 1: how many points of every class go to every child
+    if (has_fix)
+      for (int s = c.fix_head; s >= 0; s = M.fix_segs[s].next)
+      {
+        const FixSeg seg = M.fix_segs[s];
+        for (int a = lane; a < seg.cnt; a += 32) atomicAdd(&cnt[0][child_index(M.fix_pool[seg.off + a].p, vc)], 1);
+      }
+    for (int si = 0; si < win_count; si++)
+    {
+      const int slot = M.mp[si];
+      const int np = c.win_cnt[slot];
+      const PointRec* src = M.win_pool[slot] + c.win_off[slot];
+      for (int a = lane; a < np; a += 32)
+      {
+        double pw[3];
+        rot_trans(xb.x[si].R, xb.x[si].p, src[a].p, pw);
+        atomicAdd(&cnt[1 + si][child_index(pw, vc)], 1);
+      }
+    }
+    __syncwarp();
+    // children and their storage (lane k owns child k)
+    if (lane < 8)
+    {
+      const int k = lane;
+      int tot = 0;
+      for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][k];
+      int id = -1;
+      if (tot > 0)
+      {
+        id = c.children[k] >= 0 ? c.children[k] : make_child(M, n, k);
+        c.children[k] = id;
+        if (id >= 0)
+        {
+          NodeCold& kc = M.cold[id];
+          if (cnt[0][k] > 0 && store) off[0][k] = fix_append(M, kc, cnt[0][k]);
+          for (int si = 0; si < win_count; si++)
+            if (cnt[1 + si][k] > 0)
+            {
+              const int slot = M.mp[si];
+              kc.has_sw = 1;
+              kc.isexist = 1;
+              if (store)
+              {
+                int woff = atomicAdd(&M.win_cursor[slot], cnt[1 + si][k]);
+                if ((long long)woff + cnt[1 + si][k] > M.win_cap)
+                  atomicOr(M.status, VN_ST_WIN_FULL);
+                else
+                {
+                  off[1 + si][k] = woff;
+                  kc.win_off[slot] = woff;
+                  kc.win_cnt[slot] = cnt[1 + si][k];
+                }
+              }
+            }
+        }
+      }
+      kid[k] = id;
+    }
+    __syncwarp();
+
+    // running sums of this lane's scalars for the 8 children (children are new: they start from zero)
+    double clA[8], clB[8], cv0[8], cv1[8];  // clA: pcr_add (lanes 0..8); clB: pcr_fix (9..17) / pcrs_local (18..26)
+#pragma unroll
+    for (int k = 0; k < 8; k++) clA[k] = clB[k] = cv0[k] = cv1[k] = 0.0;
+    int fill[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) fill[k] = 0;
+
+    // pass 2: stream the classes in order
+    for (int cls = 0; cls <= win_count; cls++)
+    {
+      const bool is_fix = cls == 0;
+      if (is_fix && !has_fix) continue;
+      const int si = cls - 1;
+      const int slot = is_fix ? 0 : M.mp[si];
+      int seg_id = is_fix ? c.fix_head : 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) fill[k] = 0;
+      if (!is_fix)
+      {
+#pragma unroll
+        for (int k = 0; k < 8; k++) clB[k] = 0.0;
+      }
+      while (seg_id >= 0)
+      {
+        int np, next_seg;
+        const PointRec* src;
+        if (is_fix)
+        {
+          const FixSeg seg = M.fix_segs[seg_id];
+          np = seg.cnt;
+          src = M.fix_pool + seg.off;
+          next_seg = seg.next;
+        }
+        else
+        {
+          np = c.win_cnt[slot];
+          src = M.win_pool[slot] + c.win_off[slot];
+          next_seg = -1;
+        }
+        for (int base = 0; base < np; base += 32)
+        {
+          const int a = base + lane;
+          int kk = -1;
+          PointRec pr;
+          double pw[3];
+          if (a < np)
+          {
+            pr = src[a];
+            if (is_fix)
+            {
+              pw[0] = pr.p[0];
+              pw[1] = pr.p[1];
+              pw[2] = pr.p[2];
+            }
+            else
+              rot_trans(xb.x[si].R, xb.x[si].p, pr.p, pw);
+            kk = child_index(pw, vc);
+            for (int t = 0; t < 3; t++) pt[lane][t] = pr.p[t];
+            for (int t = 0; t < 3; t++) pt[lane][9 + t] = pw[t];
+            double o[45];
+            bf_var_terms(pr.v, pw, o);
+#pragma unroll
+            for (int e = 0; e < 45; e++) red[lane][e] = o[e];
+          }
+          kks[lane] = kk;
+          // copy the point into its child's list, keeping the order (stable rank within the batch)
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+          {
+            const unsigned mask = __ballot_sync(0xffffffffu, kk == k);
+            if (kk == k && off[cls][k] >= 0)
+            {
+              const int dst = off[cls][k] + fill[k] + __popc(mask & lt_mask);
+              if (is_fix)
+                M.fix_pool[dst] = pr;
+              else
+                M.win_pool[slot][dst] = pr;
+            }
+            fill[k] += __popc(mask);
+          }
+          __syncwarp();
+          const int m = min(32, np - base);
+          for (int r = 0; r < m; r++)
+          {
+            const int rk = kks[r];
+            const double e0 = red[r][lane];
+            const double e1 = has2 ? red[r][lane + 32] : 0.0;
+            // push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of row r into child rk
+            double ta = 0.0, tb = 0.0;
+            const bool roleA = lane < 9;
+            const bool roleB = is_fix ? (lane >= 9 && lane < 18) : (lane >= 18 && lane < 27);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              if (rk == k)
+              {
+                if (roleA) clA[k] = cluster_term(L, clA[k], pt[r] + 9);
+                if (roleB) clB[k] = cluster_term(L, clB[k], pt[r]);
+                cv0[k] += e0;
+                cv1[k] += e1;
+              }
+            (void)ta;
+            (void)tb;
+          }
+          __syncwarp();
+        }
+        seg_id = next_seg;
+      }
+      // end of class: the per-frame local cluster of every child is complete
+      if (is_fix)
+      {
+        if (lane >= 9 && lane < 18)
+        {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (kid[k] >= 0 && cnt[0][k] > 0) cluster_set(M.cold[kid[k]].pcr_fix, L.ck, clB[k]);
+        }
+        if (lane == 9)
+        {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (kid[k] >= 0) M.cold[kid[k]].pcr_fix.N += cnt[0][k];
+        }
       }
       else
-        for (int k = 7; k >= 0; k--)
-          if (c.children[k] >= 0) stack[sp++] = c.children[k];
+      {
+        if (lane >= 18 && lane < 27)
+        {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (kid[k] >= 0 && cnt[cls][k] > 0) cluster_set(M.cold[kid[k]].pcrs_local[slot], L.ck, clB[k]);
+        }
+        if (lane == 18)
+        {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (kid[k] >= 0) M.cold[kid[k]].pcrs_local[slot].N += cnt[cls][k];
+        }
+      }
     }
+    // children's pcr_add / cov_add
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+    {
+      if (kid[k] < 0) continue;
+      NodeCold& kc = M.cold[kid[k]];
+      if (lane < 9) cluster_set(kc.pcr_add, L.ck, clA[k]);
+      kc.cov_add[lane] = cv0[k];
+      if (has2) kc.cov_add[lane + 32] = cv1[k];
+      if (lane == 0)
+      {
+        int tot = 0;
+        for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][k];
+        kc.pcr_add.N += tot;
+      }
+    }
+    __syncwarp();
+    // PVec().swap(point_fix); sw->clear(); sws.push_back(sw); sw = nullptr; octo_state = 1
+    if (lane == 0)
+    {
+      if (has_fix)
+      {
+        c.fix_head = c.fix_tail = -1;
+        c.fix_count = 0;
+      }
+      for (int s = 0; s < M.win_size; s++)
+      {
+        c.win_cnt[s] = 0;
+        cluster_clear(c.pcrs_local[s]);
+      }
+      c.has_sw = 0;
+      h.flags |= VN_FLAG_INTERIOR;
+    }
+    if (lane < 8 && kid[lane] >= 0 && layer < 3)
+    {
+      int pos = atomicAdd(&LL.count[layer + 1], 1);
+      LL.list[layer + 1][pos] = kid[lane];
+    }
+    __syncwarp();
   }
 }
 
+
 // ---------------------------------------------------------------------------
+
 // OctoTree::plane_update (octree.cpp:302-333)
 __device__ void plane_update(NodeHot& h, NodeCold& c)
 {
@@ -635,89 +1022,73 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
   c.isexist = (c.pcr_fix.N >= c.pcr_add.N) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(64) k_margi(MapView M, int cur, int win_count, PoseBuf xb)
+// OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
+__global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb)
 {
-  const int nroots = M.slide_count[cur];
-  if (nroots < M.thread_num) return;  // local_mapping.cpp:26-28
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
+  if (M.slide_count[M.slide_cur] < M.thread_num) return;  // local_mapping.cpp:26-28
+  int nn;
+  const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
   {
-    int stack[40];
-    int sp = 0;
-    stack[sp++] = M.slide_list[cur][j] << 1;
-    while (sp > 0)
-    {
-      int e = stack[sp - 1];
-      int n = e >> 1;
-      NodeHot& h = M.hot[n];
-      NodeCold& c = M.cold[n];
-      if (!(h.flags & VN_FLAG_INTERIOR))
-      {
-        margi_leaf(M, n, win_count, xb);
-        sp--;
-      }
-      else if (!(e & 1))
-      {
-        stack[sp - 1] = e | 1;
-        for (int k = 7; k >= 0; k--)
-          if (c.children[k] >= 0) stack[sp++] = c.children[k] << 1;
-      }
-      else
-      {
-        int ex = 0;
-        for (int k = 0; k < 8; k++)
-          if (c.children[k] >= 0) ex |= M.cold[c.children[k]].isexist;
-        c.isexist = ex;
-        sp--;
-      }
-    }
+    const int n = nodes[j];
+    if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb);
   }
 }
 
-// erase loop of multi_margi (local_mapping.cpp:67-78): roots without live window data
-// leave surf_map_slide and give their SlideWindows back (OctoTree::clear_slwd, octree.cpp:739-756)
-__global__ void __launch_bounds__(64) k_slide_compact(MapView M, int cur)
+// OctoTree::margi, interior branch (octree.cpp:485-494): isexist = OR over the children, bottom-up
+__global__ void __launch_bounds__(128) k_margi_up(MapView M, LayerLists LL, int layer)
 {
-  const int nroots = M.slide_count[cur];
-  if (nroots < M.thread_num)
+  if (M.slide_count[M.slide_cur] < M.thread_num) return;
+  int nn;
+  const int* nodes = layer_nodes(M, LL, layer, &nn);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
   {
-    // early-out of multi_margi: the slide map is left as is -> copy the list over
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
-    {
-      int pos = atomicAdd(&M.slide_count[1 - cur], 1);
-      M.slide_list[1 - cur][pos] = M.slide_list[cur][j];
-    }
-    return;
+    const int n = nodes[j];
+    if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) continue;
+    NodeCold& c = M.cold[n];
+    int ex = 0;
+    for (int k = 0; k < 8; k++)
+      if (c.children[k] >= 0) ex |= M.cold[c.children[k]].isexist;
+    c.isexist = ex;
   }
+}
+
+// erase loop of multi_margi (local_mapping.cpp:67-78): every node whose root left surf_map_slide gives
+// its SlideWindow back (OctoTree::clear_slwd, octree.cpp:739-756). blockIdx.y = layer.
+__global__ void __launch_bounds__(128) k_margi_clear(MapView M, LayerLists LL)
+{
+  if (M.slide_count[M.slide_cur] < M.thread_num) return;
+  int nn;
+  const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
+  {
+    NodeCold& c = M.cold[nodes[j]];
+    if (M.cold[c.root].isexist || !c.has_sw) continue;
+    for (int s = 0; s < M.win_size; s++)
+    {
+      c.win_cnt[s] = 0;
+      cluster_clear(c.pcrs_local[s]);
+    }
+    c.has_sw = 0;
+  }
+}
+
+// surviving roots go to the other slide list (the caller flips slide_cur)
+__global__ void __launch_bounds__(128) k_slide_compact(MapView M)
+{
+  const int cur = M.slide_cur;
+  const int nroots = M.slide_count[cur];
+  const bool early_out = nroots < M.thread_num;  // multi_margi returned before its erase loop
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
   {
     const int root = M.slide_list[cur][j];
-    if (M.cold[root].isexist)
+    if (early_out || M.cold[root].isexist)
     {
       int pos = atomicAdd(&M.slide_count[1 - cur], 1);
       M.slide_list[1 - cur][pos] = root;
-      continue;
     }
-    M.cold[root].in_slide = 0;
-    int stack[40];
-    int sp = 0;
-    stack[sp++] = root;
-    while (sp > 0)
-    {
-      int n = stack[--sp];
-      NodeCold& c = M.cold[n];
-      if (M.hot[n].flags & VN_FLAG_INTERIOR)
-        for (int k = 0; k < 8; k++)
-          if (c.children[k] >= 0) stack[sp++] = c.children[k];
-      if (c.has_sw)
-      {
-        for (int s = 0; s < M.win_size; s++)
-        {
-          c.win_cnt[s] = 0;
-          cluster_clear(c.pcrs_local[s]);
-        }
-        c.has_sw = 0;
-      }
-    }
+    else
+      M.cold[root].in_slide = 0;
   }
 }
 
@@ -812,7 +1183,9 @@ int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan,
   if (tg > 1184) tg = 1184;
   k_insert_alloc<<<tg, 128, 0, st>>>(map, sc);
   k_insert_scatter<<<grid_for(n_host, 256), 256, 0, st>>>(map, n_dev, n_host, sc);
-  k_insert_accum<<<1184, 64, 0, st>>>(map, scan, sc, win_ord);
+  int ag = grid_for(n_host, ACC_WARPS);  // at most one warp per point's leaf
+  if (ag > 148 * 16) ag = 148 * 16;
+  k_insert_accum<<<ag, 32 * ACC_WARPS, 0, st>>>(map, scan, sc, win_ord);
   return 6;
 }
 
@@ -824,21 +1197,35 @@ static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)
   return b;
 }
 
-int launch_map_recut(cudaStream_t st, const MapView& map, int win_count, const PoseD* h_xbuf)
+int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf)
 {
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  k_recut<<<1184, 64, 0, st>>>(map, map.slide_cur, win_count, b);
-  return 1;
+  k_zero_ints<<<1, 32, 0, st>>>(LL.count, 8);
+  int launches = 1;
+  for (int layer = 0; layer <= map.max_layer; layer++)
+  {
+    k_recut_layer<<<592, 128, 0, st>>>(map, LL, layer);
+    launches++;
+    if (layer < map.max_layer)
+    {
+      k_split<<<592, 32 * SPLIT_WARPS, 0, st>>>(map, LL, layer, win_count, b);
+      launches++;
+    }
+  }
+  return launches;
 }
 
-int launch_map_margi(cudaStream_t st, const MapView& map, int win_count, const PoseD* h_xbuf)
+int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf)
 {
-  const int cur_list = map.slide_cur;
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  k_margi<<<1184, 64, 0, st>>>(map, cur_list, win_count, b);
-  k_zero_ints<<<1, 32, 0, st>>>(map.slide_count + (1 - cur_list), 1);
-  k_slide_compact<<<1184, 64, 0, st>>>(map, cur_list);
-  return 3;
+  int launches = 0;
+  k_margi_leaves<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b);
+  launches++;
+  for (int layer = map.max_layer - 1; layer >= 0; layer--, launches++) k_margi_up<<<296, 128, 0, st>>>(map, LL, layer);
+  k_margi_clear<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL);
+  k_zero_ints<<<1, 32, 0, st>>>(map.slide_count + (1 - map.slide_cur), 1);
+  k_slide_compact<<<296, 128, 0, st>>>(map);
+  return launches + 3;
 }
 
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count)

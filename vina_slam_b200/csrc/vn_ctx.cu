@@ -90,6 +90,7 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   memset(&ctx->tm, 0, sizeof(ctx->tm));
   memset(&ctx->map, 0, sizeof(ctx->map));
   memset(&ctx->ins, 0, sizeof(ctx->ins));
+  memset(&ctx->layers, 0, sizeof(ctx->layers));
   memset(ctx->pv, 0, sizeof(ctx->pv));
   if (cfg.win_size < 1 || cfg.win_size > VINA_MAX_WIN || cfg.max_layer < 0 || cfg.max_layer > 3 ||
       cfg.voxel_size <= 0 || cfg.thread_num < 1)
@@ -205,6 +206,9 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&S.counters, 4));
   CU(dalloc(&S.idx, cap));
   S.stamp = 0;
+  for (int l = 0; l < 4; l++) CU(dalloc(&ctx->layers.list[l], (size_t)cfg.max_nodes));
+  CU(dalloc(&ctx->layers.split, (size_t)cfg.max_nodes));
+  CU(dalloc(&ctx->layers.count, 8));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   return VINA_OK;
@@ -266,6 +270,9 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(S.touched);
   cudaFree(S.counters);
   cudaFree(S.idx);
+  for (int l = 0; l < 4; l++) cudaFree(ctx->layers.list[l]);
+  cudaFree(ctx->layers.split);
+  cudaFree(ctx->layers.count);
   for (int i = 0; i < 16; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -600,14 +607,14 @@ extern "C" int vina_map_insert(vina_ctx* ctx, int win_ord, const double R[9], co
 extern "C" int vina_map_recut(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
 {
   if (!ctx || win_count < 1 || win_count > ctx->cfg.win_size || !x_buf) return VINA_E_ARG;
-  ctx->launches += launch_map_recut(ctx->stream, ctx->map, win_count, reinterpret_cast<const PoseD*>(x_buf));
+  ctx->launches += launch_map_recut(ctx->stream, ctx->map, ctx->layers, win_count, reinterpret_cast<const PoseD*>(x_buf));
   return VINA_OK;
 }
 
 extern "C" int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
 {
   if (!ctx || win_count < 1 || win_count > ctx->cfg.win_size || !x_buf) return VINA_E_ARG;
-  ctx->launches += launch_map_margi(ctx->stream, ctx->map, win_count, reinterpret_cast<const PoseD*>(x_buf));
+  ctx->launches += launch_map_margi(ctx->stream, ctx->map, ctx->layers, win_count, reinterpret_cast<const PoseD*>(x_buf));
   ctx->map.slide_cur = 1 - ctx->map.slide_cur;
   return VINA_OK;
 }

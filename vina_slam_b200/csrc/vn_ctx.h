@@ -48,6 +48,7 @@ struct vina_ctx
   // map
   MapView map;
   InsertScratch ins;
+  LayerLists layers;
   unsigned int hash_slots = 0;
   int* d_status = nullptr;
   int* h_status = nullptr;  // pinned

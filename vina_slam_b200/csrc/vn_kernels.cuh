@@ -53,6 +53,7 @@ void launch_iekf(cudaStream_t st, const ScanView& scan, const int* n_dev, int n_
 void launch_fill_int(cudaStream_t st, int* p, int v, int n);
 
 // map_kernels.cu
+struct LayerLists;
 struct InsertScratch
 {
   double* pw[3];   // world points of the down-sampled scan
@@ -68,8 +69,17 @@ struct InsertScratch
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                       const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
                       const double* tsl_var);
-int launch_map_recut(cudaStream_t st, const MapView& map, int win_count, const PoseD* h_xbuf);
+int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
-int launch_map_margi(cudaStream_t st, const MapView& map, int win_count, const PoseD* h_xbuf);
+int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count);
 void launch_map_init(cudaStream_t st, const MapView& map, unsigned int nslots);
+
+// per-layer node lists of the roots in surf_map_slide, rebuilt by every multi_recut and reused by the
+// multi_margi of the same scan (layer 0 is the slide list itself)
+struct LayerLists
+{
+  int* list[4];
+  int* split;  // leaves to subdivide in the current layer
+  int* count;  // [0..3] nodes per layer, [4..7] splits per layer
+};

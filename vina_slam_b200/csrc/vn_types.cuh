@@ -79,6 +79,7 @@ struct NodeCold
   int fix_head, fix_tail, fix_count;  // chain of FixSeg
   int last_num, opt_state, isexist, has_sw;
   int path;
+  int root;  // node id of the root voxel this node belongs to
   unsigned long long rootkey;
   int pend_cnt, pend_off;  // per-insert scratch: points of this scan landing in the leaf
   int touch_stamp, in_slide;
