@@ -394,9 +394,23 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
       __syncwarp();
       if (lane < cnt) idx[rank] = v;
     }
+    else if (cnt <= 32 * RED_STRIDE * 2)
+    {
+      // rank sort through shared memory (indices are distinct): rank = number of smaller ones
+      int* sidx = reinterpret_cast<int*>(&red[0][0]);
+      for (int a = lane; a < cnt; a += 32) sidx[a] = idx[a];
+      __syncwarp();
+      for (int a = lane; a < cnt; a += 32)
+      {
+        const int v = sidx[a];
+        int rank = 0;
+        for (int b = 0; b < cnt; b++) rank += (sidx[b] < v) ? 1 : 0;
+        idx[rank] = v;
+      }
+    }
     else if (lane == 0)
     {
-      for (int a = 1; a < cnt; a++)  // arrival order is nearly sorted already
+      for (int a = 1; a < cnt; a++)
       {
         int v = idx[a], b = a - 1;
         while (b >= 0 && idx[b] > v)
@@ -587,34 +601,33 @@ __global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, i
 }
 
 // The subdivision branch of OctoTree::recut (octree.cpp:375-387): fix_divide (:257-277), subdivide per
-// window frame (:279-300), release of the parent's SlideWindow (:384-387). One warp per splitting leaf.
-// Source classes in the reference's order: class 0 = point_fix, class 1+si = sw->points[mp[si]].
-// The parent's points are streamed once, 32 at a time; every lane keeps the running sums of its scalar
-// (cluster role / two cov_add entries) for all 8 children, and rows are applied in list order, so each
-// child's cluster sums are those of the reference's sequential loop.
-#define SPLIT_WARPS 2
-__global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
+// window frame (:279-300), release of the parent's SlideWindow (:384-387). One 128-thread block per
+// splitting leaf. Source classes in the reference's order: class 0 = point_fix, class 1+si =
+// sw->points[mp[si]]. The parent's points are streamed once, 64 at a time; inside a batch the rows of
+// each child are listed in order (stable compaction) and
+//   thread t < 72  owns the cluster scalar s = t % 9 of child k = t / 9 (pcr_add and pcr_fix /
+//                  pcrs_local[slot]) and applies that child's rows sequentially (exact sums, reference order),
+//   every thread   owns up to three (child, cov_add entry) pairs and sums that child's staged Bf_var terms.
+#define SPLIT_THREADS 128
+#define SPLIT_BATCH 64
+__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
 {
-  __shared__ double pt_s[SPLIT_WARPS][32][PT_STRIDE];
-  __shared__ double red_s[SPLIT_WARPS][32][RED_STRIDE];
-  __shared__ int cnt_s[SPLIT_WARPS][11][8];
-  __shared__ int off_s[SPLIT_WARPS][11][8];
-  __shared__ int kid_s[SPLIT_WARPS][8];
-  __shared__ int kk_s[SPLIT_WARPS][32];
+  __shared__ double pt[SPLIT_BATCH][PT_STRIDE];
+  __shared__ double red[SPLIT_BATCH][RED_STRIDE];
+  __shared__ int cnt[11][8];
+  __shared__ int off[11][8];
+  __shared__ int kid[8];
+  __shared__ int fill[8];
+  __shared__ int wcount[2][8];
+  __shared__ unsigned char rows[8][SPLIT_BATCH];
   if (M.slide_count[M.slide_cur] < M.thread_num) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   LaneRole L;
-  role_init(lane, L);
-  double(*pt)[PT_STRIDE] = pt_s[warp];
-  double(*red)[RED_STRIDE] = red_s[warp];
-  int(*cnt)[8] = cnt_s[warp];
-  int(*off)[8] = off_s[warp];
-  int* kid = kid_s[warp];
-  int* kks = kk_s[warp];
-  const bool has2 = lane + 32 < 45;
+  role_init(t, L);  // L.ck = t % 9
+  const int my_k = t / 9;  // cluster chain of this thread (t < 72)
   const int nsplit = LL.count[4 + layer];
-  for (int j = blockIdx.x * SPLIT_WARPS + warp; j < nsplit; j += gridDim.x * SPLIT_WARPS)
+  for (int j = blockIdx.x; j < nsplit; j += gridDim.x)
   {
     const int n = LL.split[j];
     NodeCold& c = M.cold[n];
@@ -622,36 +635,38 @@ __global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerList
     const bool store = (h.layer + 1) < M.max_layer;
     const double vc[3] = { h.vcenter[0], h.vcenter[1], h.vcenter[2] };
     const bool has_fix = c.pcr_fix.N != 0;
-    for (int t = lane; t < 88; t += 32)
+    __syncthreads();
+    if (t < 88)
     {
       (&cnt[0][0])[t] = 0;
       (&off[0][0])[t] = -1;
     }
-    __syncwarp();
+    __syncthreads();
     // pass 1: how many points of every class go to every child
     if (has_fix)
       for (int s = c.fix_head; s >= 0; s = M.fix_segs[s].next)
       {
         const FixSeg seg = M.fix_segs[s];
-        for (int a = lane; a < seg.cnt; a += 32) atomicAdd(&cnt[0][child_index(M.fix_pool[seg.off + a].p, vc)], 1);
+        for (int a = t; a < seg.cnt; a += SPLIT_THREADS)
+          atomicAdd(&cnt[0][child_index(M.fix_pool[seg.off + a].p, vc)], 1);
       }
     for (int si = 0; si < win_count; si++)
     {
       const int slot = M.mp[si];
       const int np = c.win_cnt[slot];
       const PointRec* src = M.win_pool[slot] + c.win_off[slot];
-      for (int a = lane; a < np; a += 32)
+      for (int a = t; a < np; a += SPLIT_THREADS)
       {
         double pw[3];
         rot_trans(xb.x[si].R, xb.x[si].p, src[a].p, pw);
         atomicAdd(&cnt[1 + si][child_index(pw, vc)], 1);
       }
     }
-    __syncwarp();
-    // children and their storage (lane k owns child k)
-    if (lane < 8)
+    __syncthreads();
+    // children and their storage (thread k owns child k)
+    if (t < 8)
     {
-      const int k = lane;
+      const int k = t;
       int tot = 0;
       for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][k];
       int id = -1;
@@ -686,15 +701,11 @@ __global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerList
       }
       kid[k] = id;
     }
-    __syncwarp();
+    __syncthreads();
 
-    // running sums of this lane's scalars for the 8 children (children are new: they start from zero)
-    double clA[8], clB[8], cv0[8], cv1[8];  // clA: pcr_add (lanes 0..8); clB: pcr_fix (9..17) / pcrs_local (18..26)
-#pragma unroll
-    for (int k = 0; k < 8; k++) clA[k] = clB[k] = cv0[k] = cv1[k] = 0.0;
-    int fill[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) fill[k] = 0;
+    // running sums (children are new: they start from zero)
+    double clA = 0.0, clB = 0.0;  // thread t < 72: scalar L.ck of child my_k
+    double cv[3] = { 0.0, 0.0, 0.0 };  // pairs p = t + 128 q < 360: child p / 45, entry p % 45
 
     // pass 2: stream the classes in order
     for (int cls = 0; cls <= win_count; cls++)
@@ -704,13 +715,9 @@ __global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerList
       const int si = cls - 1;
       const int slot = is_fix ? 0 : M.mp[si];
       int seg_id = is_fix ? c.fix_head : 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) fill[k] = 0;
-      if (!is_fix)
-      {
-#pragma unroll
-        for (int k = 0; k < 8; k++) clB[k] = 0.0;
-      }
+      clB = 0.0;
+      if (t < 8) fill[t] = 0;
+      __syncthreads();
       while (seg_id >= 0)
       {
         int np, next_seg;
@@ -728,125 +735,121 @@ __global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerList
           src = M.win_pool[slot] + c.win_off[slot];
           next_seg = -1;
         }
-        for (int base = 0; base < np; base += 32)
+        for (int base = 0; base < np; base += SPLIT_BATCH)
         {
-          const int a = base + lane;
+          const int m = min(SPLIT_BATCH, np - base);
           int kk = -1;
           PointRec pr;
-          double pw[3];
-          if (a < np)
+          if (t < SPLIT_BATCH)
           {
-            pr = src[a];
-            if (is_fix)
+            const int a = base + t;
+            if (a < np)
             {
-              pw[0] = pr.p[0];
-              pw[1] = pr.p[1];
-              pw[2] = pr.p[2];
+              double pw[3];
+              pr = src[a];
+              if (is_fix)
+              {
+                pw[0] = pr.p[0];
+                pw[1] = pr.p[1];
+                pw[2] = pr.p[2];
+              }
+              else
+                rot_trans(xb.x[si].R, xb.x[si].p, pr.p, pw);
+              kk = child_index(pw, vc);
+              for (int q = 0; q < 3; q++) pt[t][q] = pr.p[q];
+              for (int q = 0; q < 3; q++) pt[t][9 + q] = pw[q];
+              double o[45];
+              bf_var_terms(pr.v, pw, o);
+#pragma unroll
+              for (int e = 0; e < 45; e++) red[t][e] = o[e];
             }
-            else
-              rot_trans(xb.x[si].R, xb.x[si].p, pr.p, pw);
-            kk = child_index(pw, vc);
-            for (int t = 0; t < 3; t++) pt[lane][t] = pr.p[t];
-            for (int t = 0; t < 3; t++) pt[lane][9 + t] = pw[t];
-            double o[45];
-            bf_var_terms(pr.v, pw, o);
+            // stable rank of the row inside its child, first within the warp ...
+            int myrank = 0;
 #pragma unroll
-            for (int e = 0; e < 45; e++) red[lane][e] = o[e];
-          }
-          kks[lane] = kk;
-          // copy the point into its child's list, keeping the order (stable rank within the batch)
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-          {
-            const unsigned mask = __ballot_sync(0xffffffffu, kk == k);
-            if (kk == k && off[cls][k] >= 0)
+            for (int k = 0; k < 8; k++)
             {
-              const int dst = off[cls][k] + fill[k] + __popc(mask & lt_mask);
+              const unsigned mask = __ballot_sync(0xffffffffu, kk == k);
+              if (kk == k) myrank = __popc(mask & lt_mask);
+              if (lane == 0) wcount[warp][k] = __popc(mask);
+            }
+            // (the two staging warps meet at the block barrier below)
+            pt[t][12] = (double)myrank;
+          }
+          __syncthreads();
+          if (t < SPLIT_BATCH && kk >= 0)
+          {
+            // ... then across the two staging warps (rows 0..31 precede rows 32..63)
+            const int rank = (int)pt[t][12] + (warp == 1 ? wcount[0][kk] : 0);
+            rows[kk][rank] = (unsigned char)t;
+            if (off[cls][kk] >= 0)
+            {
+              const int dst = off[cls][kk] + fill[kk] + rank;
               if (is_fix)
                 M.fix_pool[dst] = pr;
               else
                 M.win_pool[slot][dst] = pr;
             }
-            fill[k] += __popc(mask);
           }
-          __syncwarp();
-          const int m = min(32, np - base);
-          for (int r = 0; r < m; r++)
+          __syncthreads();
+          // push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows
+          if (t < 72)
           {
-            const int rk = kks[r];
-            const double e0 = red[r][lane];
-            const double e1 = has2 ? red[r][lane + 32] : 0.0;
-            // push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of row r into child rk
-            double ta = 0.0, tb = 0.0;
-            const bool roleA = lane < 9;
-            const bool roleB = is_fix ? (lane >= 9 && lane < 18) : (lane >= 18 && lane < 27);
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-              if (rk == k)
-              {
-                if (roleA) clA[k] = cluster_term(L, clA[k], pt[r] + 9);
-                if (roleB) clB[k] = cluster_term(L, clB[k], pt[r]);
-                cv0[k] += e0;
-                cv1[k] += e1;
-              }
-            (void)ta;
-            (void)tb;
+            const int mk = wcount[0][my_k] + (m > 32 ? wcount[1][my_k] : 0);
+            for (int i = 0; i < mk; i++)
+            {
+              const double* q = pt[rows[my_k][i]];
+              clA = cluster_term(L, clA, q + 9);
+              clB = cluster_term(L, clB, q);
+            }
           }
-          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 3; q++)
+          {
+            const int p = t + SPLIT_THREADS * q;
+            if (p < 360)
+            {
+              const int k = p / 45, e = p % 45;
+              const int mk = wcount[0][k] + (m > 32 ? wcount[1][k] : 0);
+              double s = 0.0;
+              for (int i = 0; i < mk; i++) s += red[rows[k][i]][e];
+              cv[q] += s;
+            }
+          }
+          __syncthreads();
+          if (t < 8) fill[t] += wcount[0][t] + (m > 32 ? wcount[1][t] : 0);
         }
         seg_id = next_seg;
       }
-      // end of class: the per-frame local cluster of every child is complete
-      if (is_fix)
+      // end of class: pcr_fix (class 0) or the per-frame local cluster of every child is complete
+      if (t < 72 && kid[my_k] >= 0 && cnt[cls][my_k] > 0)
       {
-        if (lane >= 9 && lane < 18)
-        {
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            if (kid[k] >= 0 && cnt[0][k] > 0) cluster_set(M.cold[kid[k]].pcr_fix, L.ck, clB[k]);
-        }
-        if (lane == 9)
-        {
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            if (kid[k] >= 0) M.cold[kid[k]].pcr_fix.N += cnt[0][k];
-        }
+        NodeCold& kc = M.cold[kid[my_k]];
+        Cluster& dst = is_fix ? kc.pcr_fix : kc.pcrs_local[slot];
+        cluster_set(dst, L.ck, clB);
+        if (L.ck == 0) dst.N += cnt[cls][my_k];
       }
-      else
-      {
-        if (lane >= 18 && lane < 27)
-        {
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            if (kid[k] >= 0 && cnt[cls][k] > 0) cluster_set(M.cold[kid[k]].pcrs_local[slot], L.ck, clB[k]);
-        }
-        if (lane == 18)
-        {
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            if (kid[k] >= 0) M.cold[kid[k]].pcrs_local[slot].N += cnt[cls][k];
-        }
-      }
+      __syncthreads();
     }
     // children's pcr_add / cov_add
-#pragma unroll
-    for (int k = 0; k < 8; k++)
+    if (t < 72 && kid[my_k] >= 0)
     {
-      if (kid[k] < 0) continue;
-      NodeCold& kc = M.cold[kid[k]];
-      if (lane < 9) cluster_set(kc.pcr_add, L.ck, clA[k]);
-      kc.cov_add[lane] = cv0[k];
-      if (has2) kc.cov_add[lane + 32] = cv1[k];
-      if (lane == 0)
+      NodeCold& kc = M.cold[kid[my_k]];
+      cluster_set(kc.pcr_add, L.ck, clA);
+      if (L.ck == 0)
       {
         int tot = 0;
-        for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][k];
+        for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][my_k];
         kc.pcr_add.N += tot;
       }
     }
-    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+    {
+      const int p = t + SPLIT_THREADS * q;
+      if (p < 360 && kid[p / 45] >= 0) M.cold[kid[p / 45]].cov_add[p % 45] = cv[q];
+    }
     // PVec().swap(point_fix); sw->clear(); sws.push_back(sw); sw = nullptr; octo_state = 1
-    if (lane == 0)
+    if (t == 0)
     {
       if (has_fix)
       {
@@ -861,17 +864,15 @@ __global__ void __launch_bounds__(32 * SPLIT_WARPS) k_split(MapView M, LayerList
       c.has_sw = 0;
       h.flags |= VN_FLAG_INTERIOR;
     }
-    if (lane < 8 && kid[lane] >= 0 && layer < 3)
+    if (t < 8 && kid[t] >= 0 && layer < 3)
     {
       int pos = atomicAdd(&LL.count[layer + 1], 1);
-      LL.list[layer + 1][pos] = kid[lane];
+      LL.list[layer + 1][pos] = kid[t];
     }
-    __syncwarp();
   }
 }
 
 
-// ---------------------------------------------------------------------------
 
 // OctoTree::plane_update (octree.cpp:302-333)
 __device__ void plane_update(NodeHot& h, NodeCold& c)
@@ -1208,7 +1209,7 @@ int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, 
     launches++;
     if (layer < map.max_layer)
     {
-      k_split<<<592, 32 * SPLIT_WARPS, 0, st>>>(map, LL, layer, win_count, b);
+      k_split<<<592, SPLIT_THREADS, 0, st>>>(map, LL, layer, win_count, b);
       launches++;
     }
   }
