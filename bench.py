@@ -160,7 +160,9 @@ def main_ours(args, cfg):
     dev = torch.device("cuda", local)
 
     W, K = args.warmup, args.steps
-    boots, scans = gen_sequence(cfg, cfg.seed + rank, cfg.win_size, W + K)
+    from vina_slam_b200 import replicas as _rep
+
+    boots, scans = gen_sequence(cfg, _rep.sequence_seed(cfg.seed, rank), cfg.win_size, W + K)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -265,14 +267,9 @@ def main_ours(args, cfg):
     gx.close()
 
     # ---- max over ranks, aggregate --------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        p = torch.tensor([float(pts)], dtype=torch.float64, device=dev)
-        dist.all_reduce(p, op=dist.ReduceOp.SUM)
-        t_res, t_e2e, pts_all = float(t[0]), float(t[1]), float(p[0])
-    else:
-        pts_all = float(pts)
+    from vina_slam_b200 import replicas
+
+    pts_all, (t_res, t_e2e) = replicas.reduce_throughput(pts, [t_res, t_e2e], device=dev)
 
     if rank == 0:
         cpu = None

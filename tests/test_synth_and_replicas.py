@@ -1,0 +1,87 @@
+"""Synthetic generator contract and the multi-GPU (replica) host logic on world_size-2 gloo."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vina_slam_b200 import replicas, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_scan_contract():
+    for name in ("mid360", "velodyne32", "robosense128", "hilti_xt32"):
+        cfg = synth.small_sensor(name, min(synth.SENSORS[name].n_beams, 8), 300)
+        a, b = synth.Sequence(cfg), synth.Sequence(cfg)
+        s1, s2 = a.next_scan(), b.next_scan()
+        assert np.array_equal(s1.xyzt, s2.xyzt) and np.array_equal(s1.imu, s2.imu)  # seeded
+        x = s1.xyzt
+        assert x.dtype == np.float32 and x.shape[1] == 4
+        assert np.all(np.diff(x[:, 3]) >= 0) and x[-1, 3] < 0.11  # sorted by time, <= 0.11 s (lidar_decoder.cpp:30-35)
+        assert np.all(np.einsum("ij,ij->i", x[:, :3], x[:, :3]) > cfg.blind ** 2)
+        n_imu = s1.imu.shape[0]
+        assert n_imu > 4 and np.all(np.diff(s1.imu[:, 0]) > 0) and s1.imu[-1, 0] <= s1.end_time + 1e-9
+        s3 = a.next_scan()
+        assert s3.imu[0, 0] > s1.imu[-1, 0]  # IMU samples are handed out once (sync.cpp:63-72)
+        assert abs(np.linalg.norm(s1.imu[:, 4:7], axis=1).mean() - 9.8) < 0.5  # specific force ~ g
+    assert synth.SENSORS["robosense128"].n_points == 240000 and synth.SENSORS["velodyne32"].n_points == 57600
+
+
+def test_full_size_shapes():
+    assert synth.SENSORS["mid360"].n_points == 20000 and synth.SENSORS["hilti_xt32"].n_points == 64000
+    assert synth.SENSORS["hilti_xt32"].imu_rate == 400.0
+    assert synth.SENSORS["mid360"].voxel_size == 0.5 and synth.SENSORS["velodyne32"].max_layer == 3
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle import oracle_py as op
+
+    cfg = synth.small_sensor("robosense128", 8, 200)
+    seed = replicas.sequence_seed(cfg.seed, rank)
+    seq = synth.Sequence(cfg, seed=seed)
+    od = op.Odom(cfg)
+    sc = None
+    for _ in range(3):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, op.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    pts = float(sc.xyzt.shape[0])
+    t_local = 0.1 * (rank + 1)
+    tot, (tmax,) = replicas.reduce_throughput(pts, [t_local])
+    digest = float(np.abs(sc.xyzt).sum())
+    lst = [None] * world
+    dist.all_gather_object(lst, (seed, digest, pts))
+    q.put((rank, tot, tmax, lst))
+    dist.destroy_process_group()
+
+
+def test_replicas_world_size_2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, tot, tmax, lst in res:
+        assert tmax == pytest.approx(0.2)  # max over ranks
+        assert tot == pytest.approx(sum(x[2] for x in lst))  # points summed over ranks
+        seeds = [x[0] for x in lst]
+        assert seeds[1] == seeds[0] + 1  # rank r replays sequence base + r
+        assert lst[0][1] != lst[1][1]  # ... which are different sequences
+
+
+def test_single_process_reduce_is_identity():
+    tot, ts = replicas.reduce_throughput(10.0, [1.0, 2.0])
+    assert tot == 10.0 and ts == [1.0, 2.0]
