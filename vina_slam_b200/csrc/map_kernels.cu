@@ -49,6 +49,7 @@ __device__ int make_child(const MapView& M, int parent, int ci)
   h.ql = ph.ql / 2;
   h.layer = ph.layer + 1;
   h.flags = 0;
+  for (int k = 0; k < 8; k++) h.children[k] = -1;
   NodeCold& c = M.cold[id];
   c.rootkey = M.cold[parent].rootkey;
   c.root = M.cold[parent].root;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256)
         nh.ql = (float)(M.voxel_size / 4.0);
         nh.layer = 0;
         nh.flags = 0;
+        for (int k = 0; k < 8; k++) nh.children[k] = -1;
         NodeCold& nc = M.cold[id];
         nc.rootkey = key;
         nc.root = id;
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(256)
       if (old == -1)
       {
         int id = make_child(M, node, ci);
+        if (id >= 0) M.hot[node].children[ci] = id;  // mirror read by k_iekf
         __threadfence();
         atomicExch(slot, id < 0 ? -3 : id);
         ch = id < 0 ? -3 : id;
@@ -862,6 +865,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         cluster_clear(c.pcrs_local[s]);
       }
       c.has_sw = 0;
+      for (int k = 0; k < 8; k++) h.children[k] = c.children[k];  // mirror read by k_iekf
       h.flags |= VN_FLAG_INTERIOR;
     }
     if (t < 8 && kid[t] >= 0 && layer < 3)
@@ -923,18 +927,29 @@ __device__ void plane_update(NodeHot& h, NodeCold& c)
     {
       double s = 0.0;
       for (int t = 0; t < 9; t++) s += Jc[a][t] * uc[b][t];
-      h.pvar[sN(6, a, b)] = s;
+      c.plane_var[sN(6, a, b)] = s;
     }
   for (int a = 0; a < 3; a++)
-    for (int b = 0; b < 3; b++) h.pvar[sN(6, a, 3 + b)] = nv * Jc[a][6 + b];
+    for (int b = 0; b < 3; b++) c.plane_var[sN(6, a, 3 + b)] = nv * Jc[a][6 + b];
   for (int a = 0; a < 3; a++)
-    for (int b = a; b < 3; b++) h.pvar[sN(6, 3 + a, 3 + b)] = (nv * nv) * c.cov_add[sN(9, 6 + a, 6 + b)];
+    for (int b = a; b < 3; b++) c.plane_var[sN(6, 3 + a, 3 + b)] = (nv * nv) * c.cov_add[sN(9, 6 + a, 6 + b)];
   for (int a = 0; a < 3; a++)
   {
     h.center[a] = center[a];
     h.normal[a] = u[0][a];
   }
   h.radius = (float)c.eig_value[2];
+  // per-plane part of sigma_l (see NodeHot): A, B n, n^T C n
+  const double* pv = c.plane_var;
+  const double* nrm = u[0];
+  for (int a = 0, q = 0; a < 3; a++)
+    for (int b = a; b < 3; b++, q++) h.qA[q] = pv[sN(6, a, b)];
+  for (int a = 0; a < 3; a++)
+    h.qb[a] = pv[sN(6, a, 3)] * nrm[0] + pv[sN(6, a, 4)] * nrm[1] + pv[sN(6, a, 5)] * nrm[2];
+  double qk = 0.0;
+  for (int a = 0; a < 3; a++)
+    qk += nrm[a] * (pv[sN(6, 3 + a, 3)] * nrm[0] + pv[sN(6, 3 + a, 4)] * nrm[1] + pv[sN(6, 3 + a, 5)] * nrm[2]);
+  h.qk = qk;
 }
 
 // leaf branch of OctoTree::margi (octree.cpp:397-484), mgsize = 1
@@ -1148,7 +1163,8 @@ __global__ void __launch_bounds__(128) k_export(MapView M, vina_node_record* out
     }
     for (int i = 0; i < 9; i++) r.eig_vector[i] = c.eig_vector[i];
     for (int i = 0; i < 6; i++)
-      for (int j = 0; j < 6; j++) r.plane_var[i + 6 * j] = h.pvar[sN(6, i, j)];
+      for (int j = 0; j < 6; j++)
+        r.plane_var[i + 6 * j] = c.plane_var[sN(6, i, j)];
     r.radius = (double)h.radius;
     for (int i = 0; i < 9; i++)
       for (int j = 0; j < 9; j++) r.cov_add[i + 9 * j] = c.cov_add[sN(9, i, j)];

@@ -149,7 +149,7 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&ctx->d_block_sums, 1024));
   launch_down_init(ctx->stream, ctx->d_dtab, dslots);
   // IEKF
-  CU(dalloc(&ctx->d_partials, (size_t)ctx->sm_count * 8 * VN_IEKF_NACC));
+  CU(dalloc(&ctx->d_partials, ((size_t)cap / 128 + 64) * VN_IEKF_NACC));
   CU(dalloc(&ctx->d_ticket, 1));
   CU(cudaHostAlloc((void**)&ctx->h_result, 64 * sizeof(double), cudaHostAllocMapped));
   CU(cudaHostGetDevicePointer((void**)&ctx->d_result, ctx->h_result, 0));
@@ -519,6 +519,7 @@ int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool deb
   memcpy(prm.rot_var, ctx->rot_var, 72);
   memcpy(prm.tsl_var, ctx->tsl_var, 72);
   prm.voxel_size = ctx->cfg.voxel_size;
+  prm.variant = ctx->iekf_variant;
   const int w = ctx->iekf_which;
   if (debug)
   {
@@ -684,5 +685,32 @@ extern "C" int vina_get_timings(vina_ctx* ctx, vina_timings* t)
 {
   if (!ctx || !t) return VINA_E_ARG;
   *t = ctx->tm;
+  return VINA_OK;
+}
+
+// experiment hook: `reps` back-to-back launches of the accumulate kernel between two CUDA events
+// (no host sync in between); variant bits switch parts of the kernel off (0 = product path).
+extern "C" int vina_iekf_time_kernel(vina_ctx* ctx, const double R[9], const double p[3], int reps, int variant,
+                                     int reset_cache, float* ms_per_launch)
+{
+  if (!ctx || !R || !p || reps < 1 || !ms_per_launch) return VINA_E_ARG;
+  ctx->iekf_variant = variant;
+  cudaEventRecord(ctx->ev[10], ctx->stream);
+  for (int r = 0; r < reps; r++)
+  {
+    if (reset_cache) launch_fill_int(ctx->stream, ctx->d_cache, -1, ctx->n_pv[ctx->iekf_which]);
+    int rc = vn_iekf_launch(ctx, R, p, false);
+    if (rc)
+    {
+      ctx->iekf_variant = 0;
+      return rc;
+    }
+  }
+  cudaEventRecord(ctx->ev[11], ctx->stream);
+  ctx->iekf_variant = 0;
+  CU(cudaEventSynchronize(ctx->ev[11]));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]);
+  *ms_per_launch = ms / reps;
   return VINA_OK;
 }

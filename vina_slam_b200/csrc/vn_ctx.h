@@ -38,6 +38,7 @@ struct vina_ctx
   // IEKF
   int iekf_which = -1;
   int iekf_blocks = 0;
+  int iekf_variant = 0;
   double rot_var[9], tsl_var[9];
   double* d_partials = nullptr;
   unsigned int* d_ticket = nullptr;

@@ -25,6 +25,7 @@ struct IekfParams
   double R[9], p[3];       // x_curr.R / x_curr.p of this iteration
   double rot_var[9], tsl_var[9];  // prior covariance blocks (odometry.cpp:105-106)
   double voxel_size;
+  int variant;  // experiment switches (0 = product path), see vina_iekf_time_kernel
 };
 
 #define VN_IEKF_NACC 34  // 21 (HTH upper) + 6 (HTz) + 6 (nnt upper) + 1 (count)

@@ -31,17 +31,26 @@ struct __align__(16) HashSlot
   int pad;
 };
 
-// what OctoTree::match / inside read (octree.cpp:551-595, 732-737); one 256-B record = two 128-B lines
+// what OctoTree::match / inside read (octree.cpp:551-595, 732-737); one 256-B record = two 128-B lines.
+// Line 0 is everything the gate needs from the plane. sigma_l = J plane_var J^T with J = [w - c, -n]
+// (octree.cpp:564-567) is hoisted per plane: with plane_var = [[A, B], [B^T, C]],
+//   J plane_var J^T = d^T A d - 2 d.(B n) + n^T C n,  d = w - c,
+// so the leaf stores A (6), B n (3) and n^T C n (1) instead of the 21 entries; the full plane_var lives in
+// NodeCold (export / parity only). Line 1 is what the descent needs (flags, voxel_center, children).
 struct __align__(128) NodeHot
 {
   double center[3];   // plane.center
   double normal[3];   // plane.normal
-  double pvar[21];    // plane.plane_var, upper triangle packed by rows
+  double qA[6];       // upper triangle of plane_var(0:3, 0:3)
+  double qb[3];       // plane_var(0:3, 3:6) * normal
+  double qk;          // normal^T plane_var(3:6, 3:6) normal
   float radius;       // plane.radius
   int flags;          // VN_FLAG_*
   double vcenter[3];  // voxel_center
   float ql;           // quater_length
   int layer;
+  int children[8];    // mirror of NodeCold::children for the IEKF descent (-1 = none)
+  int pad[14];
 };
 
 // PointCluster (types.hpp:115-175); P is symmetric by construction of every
@@ -72,6 +81,7 @@ struct NodeCold
   Cluster pcr_add, pcr_fix;
   Cluster pcrs_local[VINA_MAX_WIN];
   double cov_add[45];  // 9x9 symmetric, upper triangle packed by rows
+  double plane_var[21];  // Plane::plane_var, upper triangle packed by rows (the IEKF reads NodeHot::qA/qb/qk)
   double eig_value[3];
   double eig_vector[9];  // column-major
   int win_off[VINA_MAX_WIN];
