@@ -278,3 +278,78 @@ def test_end_to_end_trajectory(oracle_lib, gpu_lib):
     assert worst_p < 1e-3, worst_p
     assert worst_r < 0.01, worst_r
     gx.close()
+
+
+def test_error_codes_and_edge_cases(oracle_lib, gpu_lib):
+    """Error behaviour of the boundary: codes instead of exit() / exceptions across the ABI."""
+    import ctypes as C
+
+    cfg = small_cfg()
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    lib = gx.lib
+    # accumulate before begin
+    z9, z3 = np.zeros(9), np.zeros(3)
+    with pytest.raises(gpu_lib.VinaError) as ei:
+        gx.iekf_accumulate(np.eye(3).reshape(-1), z3)
+    assert ei.value.code == -6
+    # scan larger than max_scan_points
+    big = np.zeros((SMALL_CAPS["max_scan_points"] + 1, 4), dtype=np.float32)
+    assert lib.vina_scan_upload(gx.h, big.ctypes.data_as(C.c_void_p), C.c_int(big.shape[0])) == -3
+    assert b"max_scan_points" in lib.vina_last_error(gx.h)
+    # bad arguments
+    assert lib.vina_scan_upload(gx.h, None, C.c_int(5)) == -1
+    assert lib.vina_var_init(gx.h, C.c_int(7)) == -1
+    assert lib.vina_map_recut(gx.h, C.c_int(0), None) == -1
+    # empty clouds are fine for the per-stage entries
+    gx.down_upload(np.zeros((0, 4), dtype=np.float32))
+    gx.var_init(1)
+    assert gx.pvec_download(1, 1)[0].shape[0] == 0
+    # IEKF on an empty map: zero matches, zero sums
+    seq = synth.Sequence(cfg)
+    sc = seq.next_scan(deskewed=True)
+    gx.scan_upload(sc.xyzt)
+    gx.var_init(0)
+    gx.iekf_begin(0, np.eye(3).reshape(-1) * 1e-4, np.eye(3).reshape(-1) * 1e-4)
+    r = gx.iekf_accumulate(col(sc.gt_R), sc.gt_p)
+    assert r["match_num"] == 0 and not r["HTH"].any() and not r["HTz"].any()
+    # LiDAR time regress (imu_ekf.cpp:19-24 exit(0)s) -> VINA_E_TIME
+    gx.set_imu_anchor(sc.beg_time + 0.05, sc.imu[0])
+    with pytest.raises(gpu_lib.VinaError) as ei:
+        gx.step(sc.xyzt, sc.beg_time, sc.imu)
+    assert ei.value.code == -5
+    gx.close()
+    # node pool exhaustion is reported as VINA_E_CAPACITY at the next sync, never a crash
+    tiny = dict(SMALL_CAPS)
+    tiny["max_nodes"] = 64
+    gy = gpu_lib.Ctx(cfg, **tiny)
+    with pytest.raises(gpu_lib.VinaError) as ei:
+        gy.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    assert ei.value.code == -3
+    gy.close()
+    # voxel keys outside the 21-bit range
+    gz = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    far = sc.xyzt.copy()
+    far[:, 0] += 3.0e6
+    with pytest.raises(gpu_lib.VinaError) as ei:
+        gz.bootstrap(far, gpu_lib.make_state(np.eye(3), np.zeros(3), np.zeros(3)))
+    assert ei.value.code == -3
+    gz.close()
+
+
+def test_iekf_is_deterministic(oracle_lib, gpu_lib):
+    """Same inputs -> bit-identical sums (fixed reduction order, no floating-point atomics)."""
+    cfg = small_cfg()
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg)
+    sc = seq.next_scan(deskewed=True)
+    gx.scan_upload(sc.xyzt)
+    gx.var_init(0)
+    rv = np.eye(3).reshape(-1) * 1e-4
+    outs = []
+    for _ in range(3):
+        gx.iekf_begin(0, rv, rv)
+        outs.append(gx.iekf_accumulate(col(sc.gt_R), sc.gt_p))
+    for o in outs[1:]:
+        assert np.array_equal(o["HTH"], outs[0]["HTH"]) and np.array_equal(o["HTz"], outs[0]["HTz"])
+        assert np.array_equal(o["nnt"], outs[0]["nnt"]) and o["match_num"] == outs[0]["match_num"]
+    assert outs[0]["match_num"] > 0.5 * sc.xyzt.shape[0]
+    gx.close()

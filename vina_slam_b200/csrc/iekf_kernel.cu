@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
   // last block: one warp per column (34 columns over 32 warps), lanes stride over the <= 148 x IEKF_MIN_BLOCKS
   // per-block partials with independent loads, then a fixed shuffle tree -> deterministic
   __threadfence();
+  __shared__ double fin[VN_IEKF_NACC];
   for (int k = warp; k < VN_IEKF_NACC; k += IEKF_WARPS)
   {
     const double* col = partials + (size_t)k * nblk;
@@ -310,9 +311,23 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
     double v = ((v0 + v1) + (v2 + v3)) + v4;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) ((prm.variant & 2) ? partials : result)[k] = v;
+    if (lane == 0) fin[k] = v;
   }
-  if (threadIdx.x == 0) *ticket = 0u;
+  __syncthreads();
+  // the sums go straight to mapped pinned host memory; the sequence number is written last so that the
+  // host can poll for completion instead of paying a stream synchronisation per IEKF iteration
+  double* out = (prm.variant & 2) ? partials : result;
+  if (threadIdx.x < VN_IEKF_NACC)
+  {
+    out[threadIdx.x] = fin[threadIdx.x];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    *ticket = 0u;
+    reinterpret_cast<volatile unsigned long long*>(out)[40] = prm.seq;
+  }
 }
 
 __global__ void k_fill_int(int* p, int v, int n)

@@ -520,6 +520,7 @@ int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool deb
   memcpy(prm.tsl_var, ctx->tsl_var, 72);
   prm.voxel_size = ctx->cfg.voxel_size;
   prm.variant = ctx->iekf_variant;
+  prm.seq = ++ctx->iekf_seq;
   const int w = ctx->iekf_which;
   if (debug)
   {
@@ -530,6 +531,28 @@ int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool deb
               ctx->d_ticket, ctx->d_result, ctx->iekf_blocks, debug ? &ctx->dbg : nullptr);
   ctx->dbg_valid = debug;
   ctx->launches += 1;
+  return VINA_OK;
+}
+
+int vn_iekf_wait(vina_ctx* ctx)
+{
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(ctx->h_result) + 40;
+  const unsigned long long want = ctx->iekf_seq;
+  for (long spins = 0; *flag != want; spins++)
+  {
+    if ((spins & 0xfff) == 0xfff)
+    {
+      // the kernel may have failed: fall back to the stream state
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaSuccess)
+      {
+        if (*flag == want) break;
+        return vn_fail(ctx, VINA_E_CUDA, "k_iekf finished without publishing its result");
+      }
+      if (e != cudaErrorNotReady) return vn_check_cuda(ctx, e, "k_iekf");
+    }
+  }
+  __sync_synchronize();
   return VINA_OK;
 }
 
@@ -559,7 +582,8 @@ extern "C" int vina_iekf_accumulate(vina_ctx* ctx, const double R[9], const doub
   if (!ctx || !R || !p || !HTH || !HTz || !nnt || !match_num) return VINA_E_ARG;
   int r = vn_iekf_launch(ctx, R, p, false);
   if (r) return r;
-  CU(cudaStreamSynchronize(ctx->stream));
+  r = vn_iekf_wait(ctx);
+  if (r) return r;
   vn_iekf_unpack(ctx->h_result, HTH, HTz, nnt, match_num);
   return VINA_OK;
 }
@@ -585,6 +609,8 @@ extern "C" int vina_iekf_accumulate_debug(vina_ctx* ctx, const double R[9], cons
 {
   if (!ctx || !R || !p || !HTH || !HTz || !nnt || !match_num) return VINA_E_ARG;
   int r = vn_iekf_launch(ctx, R, p, true);
+  if (r) return r;
+  r = vn_iekf_wait(ctx);
   if (r) return r;
   CU(cudaStreamSynchronize(ctx->stream));
   vn_iekf_unpack(ctx->h_result, HTH, HTz, nnt, match_num);

@@ -39,6 +39,7 @@ struct vina_ctx
   int iekf_which = -1;
   int iekf_blocks = 0;
   int iekf_variant = 0;
+  unsigned long long iekf_seq = 0;
   double rot_var[9], tsl_var[9];
   double* d_partials = nullptr;
   unsigned int* d_ticket = nullptr;
@@ -68,4 +69,6 @@ int vn_fail(vina_ctx* c, int code, const char* fmt, ...);
 int vn_check_cuda(vina_ctx* c, cudaError_t e, const char* what);
 // copy the device status word back (synchronises) and translate it
 int vn_check_status(vina_ctx* c);
+// wait for the sums of the last k_iekf launch (polls the sequence number in mapped memory)
+int vn_iekf_wait(vina_ctx* c);
 void odom_host_destroy(OdomHost* o);

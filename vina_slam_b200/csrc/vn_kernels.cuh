@@ -26,6 +26,7 @@ struct IekfParams
   double rot_var[9], tsl_var[9];  // prior covariance blocks (odometry.cpp:105-106)
   double voxel_size;
   int variant;  // experiment switches (0 = product path), see vina_iekf_time_kernel
+  unsigned long long seq;  // launch sequence number, written after the sums so that the host can poll for them
 };
 
 #define VN_IEKF_NACC 34  // 21 (HTH upper) + 6 (HTz) + 6 (nnt upper) + 1 (count)

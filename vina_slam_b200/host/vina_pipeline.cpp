@@ -292,11 +292,12 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
     r = vn_iekf_launch(ctx, x_curr.R, x_curr.p, false);
     if (r) return r;
     if (ctx->profiling) cudaEventRecord(e1, ctx->stream);
-    r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "iekf sync");
+    r = vn_iekf_wait(ctx);
     if (r) return r;
     if (ctx->profiling)
     {
       float ms = 0;
+      cudaEventSynchronize(e1);
       cudaEventElapsedTime(&ms, e0, e1);
       kernel_ms += ms;
     }
