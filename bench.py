@@ -152,6 +152,8 @@ def main_ours(args, cfg):
     from vina_slam_b200 import capi
 
     rank, world, local = dist_env()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -241,6 +243,12 @@ def main_ours(args, cfg):
     miss = (n_mean + (iters_per_step - 1) * n_mean * (1 - match_frac)) / max(iters_per_step, 1)
     bytes_per_launch = 80.0 * n_mean + 256.0 * U + 16.0 * miss + 34 * 8
     launch_ms = iekf_kernel_ms / max(iters, 1)
+    traffic = None
+    try:  # dram__bytes_read + write per launch from the committed `ncu --set full` capture of this kernel
+        with open(os.path.join(ROOT, "profiles", "r01_iekf_ncu_full_summary.json")) as f:
+            traffic = json.load(f)["dram_traffic_bytes_per_launch"] if cfg.name == "robosense128" else None
+    except Exception:
+        pass
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     gx.close()
     del d_scans
@@ -266,10 +274,51 @@ def main_ours(args, cfg):
     t_e2e = float(e2e_ms.sum()) * 1e-3
     gx.close()
 
+    # ---- leg 3: B independent contexts driven concurrently on this GPU (config 5, batch replay) ---------
+    batch = None
+    if args.batch > 1:
+        import threading as _th
+
+        B = args.batch
+        ctxs = []
+        for b in range(B):
+            g = capi.Ctx(cfg, **caps)  # own CUDA stream each
+            for sc in boots:
+                g.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+            g.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+            ctxs.append(g)
+        d_sc = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
+
+        def run(g, lo, hi):
+            for k in range(lo, hi):
+                sc = scans[k]
+                g.step_resident(d_sc[k].data_ptr(), sc.xyzt.shape[0], sc.beg_time, sc.end_time, sc.imu, True, MAX_ITER)
+            g.sync()
+
+        for lo, hi in ((0, W), (W, W + K)):
+            barrier()
+            t0 = time.perf_counter()
+            th = [_th.Thread(target=run, args=(g, lo, hi)) for g in ctxs]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize(dev)
+            t_batch = time.perf_counter() - t0
+        for g in ctxs:
+            g.close()
+        batch = {"sequences_per_gpu": B, "seconds": t_batch, "points": float(B * pts)}
+
     # ---- max over ranks, aggregate --------------------------------------------------------------------
     from vina_slam_b200 import replicas
 
     pts_all, (t_res, t_e2e) = replicas.reduce_throughput(pts, [t_res, t_e2e], device=dev)
+    if batch:
+        bp, (bt,) = replicas.reduce_throughput(batch["points"], [batch["seconds"]], device=dev)
+        batch = {"sequences_per_gpu": batch["sequences_per_gpu"], "value": bp / bt, "unit": UNIT,
+                 "ms_per_scan_amortised": 1e3 * bt / (K * batch["sequences_per_gpu"]),
+                 "note": "B contexts (own streams, own host threads) replaying the same seeded sequence "
+                         "concurrently on one GPU; wall clock, no L2 flush"}
 
     if rank == 0:
         cpu = None
@@ -295,7 +344,7 @@ def main_ours(args, cfg):
                     "d2h_bytes_per_step": int(iters_e2e / K * 34 * 8 + 4)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_iekf", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": None,
+                         "frac": achieved / hbm_peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
                          "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_us": 1e3 * launch_ms,
                          "launches_timed": iters, "unique_leaves": U, "match_frac": match_frac},
             "stage_ms": stage,
@@ -303,6 +352,8 @@ def main_ours(args, cfg):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if batch:
+            line["batch"] = batch
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -316,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="robosense128", choices=sorted(synth.SENSORS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--batch", type=int, default=8, help="concurrent sequences per GPU in the batch-replay leg (0/1 = off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
