@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (parity unpinned: see oracle/README.md).
+// ORACLE — TEST INFRASTRUCTURE ONLY (pinned against the reference build oracle/_ref: see oracle/README.md).
 // Minimal fixed-size dense linear algebra used by the CPU restatement of the
 // VINA-SLAM hot path. It stands in for the Eigen3 expressions the reference
 // uses (Eigen is absent from this image). Storage is

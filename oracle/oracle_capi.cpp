@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+// ORACLE — TEST INFRASTRUCTURE ONLY (pinned against oracle/_ref, see vina_oracle.hpp).
 #include "oracle_capi.h"
 #include "vina_oracle.hpp"
 #include <cstring>
@@ -268,6 +268,36 @@ void vo_odom_deskew(void* h, float* xyz4, int n)
   Cloud c = to_cloud(xyz4, n);
   o->odom_ekf.deskew(o->x_curr, c);
   from_cloud(c, xyz4);
+}
+int vo_odom_motion_blur(void* h, float* xyz4, int n, double beg, double end, const double* imu7, int m)
+{
+  Odom* o = (Odom*)h;
+  Cloud c = to_cloud(xyz4, n);
+  std::deque<ImuSample> imus = to_imus(imu7, m);
+  o->odom_ekf.pcl_beg_time = beg;
+  o->odom_ekf.pcl_end_time = end;
+  int r = o->odom_ekf.motion_blur(o->x_curr, c, imus);
+  from_cloud(c, xyz4);
+  return r;
+}
+int vo_odom_match(void* h, int n, const double* wld, const double* var, uint8_t* flags, double* sigma, double* centers)
+{
+  Odom* o = (Odom*)h;
+  int cnt = 0;
+  for (int i = 0; i < n; i++)
+  {
+    Vec3 w = v3(wld + 3 * (size_t)i);
+    Mat3 v = m3(var + 9 * (size_t)i);
+    Plane* pla = nullptr;
+    double sd = 0;
+    OctoTree* oc = nullptr;
+    int f = match(&o->G, o->surf_map, w, pla, v, sd, oc);
+    flags[i] = f ? 1 : 0;
+    sigma[i] = f ? sd : 0.0;
+    for (int k = 0; k < 3; k++) centers[3 * (size_t)i + k] = f ? pla->center[k] : 0.0;
+    cnt += f ? 1 : 0;
+  }
+  return cnt;
 }
 void vo_odom_set_dump(void* h, int on) { ((Odom*)h)->dump_iters = on != 0; }
 int vo_odom_iekf(void* h, int n, const double* pnt, const double* var, int max_iter)

@@ -1,4 +1,4 @@
-/* ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+/* ORACLE — TEST INFRASTRUCTURE ONLY (pinned against oracle/_ref, see vina_oracle.hpp).
  * Plain-C view of the CPU restatement so tests/ and bench.py's cpu_baseline
  * leg can drive it through ctypes. Matrices are column-major (Eigen default).
  */
@@ -77,6 +77,10 @@ int vo_odom_last_iters(void* h);
 int vo_odom_last_down(void* h, float* xyz4, int cap); /* the down-sampled cloud of the last step */
 
 /* stage-wise entries */
+/* IMUEKF::motion_blur in one piece: propagation + deskew (xyz4 in/out) */
+int vo_odom_motion_blur(void* h, float* xyz4, int n, double pcl_beg_time, double pcl_end_time, const double* imu7, int m);
+/* match() (voxel_map.cpp:241-266) for n world points with their world covariances (n x 9 column-major) */
+int vo_odom_match(void* h, int n, const double* wld, const double* var, uint8_t* flags, double* sigma, double* centers);
 int vo_odom_propagate(void* h, double pcl_beg_time, double pcl_end_time, const double* imu7, int m);
 int vo_odom_imu_poses(void* h, double* poses22, int cap); /* t,R(9),p,v,w,a per pose */
 void vo_odom_deskew(void* h, float* xyz4, int n);

@@ -1,4 +1,4 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+"""ORACLE — TEST INFRASTRUCTURE ONLY (pinned against oracle/_ref, see vina_oracle.hpp).
 
 ctypes view of oracle/liboracle.so (strict IEEE build, the parity checker) and
 oracle/liboracle_fast.so (-O3 -ffast-math, the timed CPU baseline).  Only
@@ -68,12 +68,30 @@ def _fp(a):
 _LIBS = {}
 
 
-def load(fast: bool = False):
-    name = "liboracle_fast.so" if fast else "liboracle.so"
+def have_ref() -> bool:
+    """oracle/_ref/libvina_ref.so = the reference's own sources compiled against oracle/ref_shim (see Makefile)."""
+    return os.path.exists(os.path.join(_HERE, "_ref", "libvina_ref.so"))
+
+
+def build_ref(reference="/root/reference") -> bool:
+    """Only possible where the reference tree is mounted (this container); the GPU box gets the prebuilt files."""
+    if not os.path.isdir(os.path.join(reference, "src")):
+        return have_ref()
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={reference}"])
+    return have_ref()
+
+
+def load(fast: bool = False, ref: bool = False):
+    if ref:
+        name = os.path.join("_ref", "libvina_ref_fast.so" if fast else "libvina_ref.so")
+    else:
+        name = "liboracle_fast.so" if fast else "liboracle.so"
     if name in _LIBS:
         return _LIBS[name]
     path = os.path.join(_HERE, name)
     if not os.path.exists(path):
+        if ref:
+            raise FileNotFoundError(path)
         build()
     lib = C.CDLL(path)
     lib.vo_odom_create.restype = C.c_void_p
@@ -81,7 +99,8 @@ def load(fast: bool = False):
     for fn in ("vo_odom_destroy", "vo_odom_set_state", "vo_odom_get_state", "vo_odom_set_imu_anchor",
                "vo_odom_bootstrap", "vo_odom_stage_times", "vo_odom_deskew", "vo_odom_set_dump",
                "vo_odom_map_update"):
-        getattr(lib, fn).restype = None
+        if hasattr(lib, fn):
+            getattr(lib, fn).restype = None
     lib.vo_odom_map_count.restype = C.c_int64
     lib.vo_odom_map_export.restype = C.c_int64
     _LIBS[name] = lib
@@ -137,11 +156,14 @@ def state_arrays(s: VoState):
 class Odom:
     """One sequence's oracle context (vo::Odom)."""
 
-    def __init__(self, cfg, fast: bool = False):
-        self.lib = load(fast)
+    def __init__(self, cfg, fast: bool = False, ref: bool = False):
+        self.lib = load(fast, ref)
+        self.is_ref = ref
         self.cfg = cfg
         self._c = make_config(cfg)
         self.h = C.c_void_p(self.lib.vo_odom_create(C.byref(self._c)))
+        if not self.h:
+            raise RuntimeError("the reference build keeps its configuration in globals: one instance per process")
 
     def close(self):
         if self.h:
@@ -205,6 +227,23 @@ class Odom:
         a = np.ascontiguousarray(xyz4, dtype=np.float32).copy()
         self.lib.vo_odom_deskew(self.h, _fp(a), C.c_int(a.shape[0]))
         return a
+
+    def motion_blur(self, xyz4: np.ndarray, beg: float, end: float, imu7: np.ndarray):
+        a = np.ascontiguousarray(xyz4, dtype=np.float32).copy()
+        im = np.ascontiguousarray(imu7, dtype=np.float64)
+        r = self.lib.vo_odom_motion_blur(self.h, _fp(a), C.c_int(a.shape[0]), C.c_double(beg), C.c_double(end), _dp(im),
+                                         C.c_int(im.shape[0]))
+        return r, a
+
+    def match(self, wld: np.ndarray, var: np.ndarray):
+        w = np.ascontiguousarray(wld, dtype=np.float64)
+        v = np.ascontiguousarray(var, dtype=np.float64)
+        n = w.shape[0]
+        flags = np.zeros(n, dtype=np.uint8)
+        sigma = np.zeros(n)
+        centers = np.zeros((n, 3))
+        self.lib.vo_odom_match(self.h, C.c_int(n), _dp(w), _dp(v), _ptr(flags, C.c_uint8), _dp(sigma), _dp(centers))
+        return flags, sigma, centers
 
     def set_dump(self, on: bool):
         self.lib.vo_odom_set_dump(self.h, C.c_int(1 if on else 0))
@@ -270,8 +309,8 @@ def inverse15(A: np.ndarray) -> np.ndarray:
     return out.reshape(15, 15).T
 
 
-def var_init(xyz4: np.ndarray, cfg):
-    lib = load()
+def var_init(xyz4: np.ndarray, cfg, ref: bool = False):
+    lib = load(ref=ref)
     a = np.ascontiguousarray(xyz4, dtype=np.float32)
     n = a.shape[0]
     pnt, var = np.zeros((n, 3)), np.zeros((n, 9))
@@ -282,8 +321,8 @@ def var_init(xyz4: np.ndarray, cfg):
     return pnt, var
 
 
-def pvec_update(pnt, var, R_col, p, cov_col):
-    lib = load()
+def pvec_update(pnt, var, R_col, p, cov_col, ref: bool = False):
+    lib = load(ref=ref)
     pn = np.ascontiguousarray(pnt, dtype=np.float64)
     vr = np.ascontiguousarray(var, dtype=np.float64).copy()
     pw = np.zeros_like(pn)
@@ -300,16 +339,16 @@ def voxel_keys(pw: np.ndarray, voxel_size: float) -> np.ndarray:
     return k
 
 
-def down_sampling_voxel(xyz4: np.ndarray, voxel_size: float) -> np.ndarray:
-    lib = load()
+def down_sampling_voxel(xyz4: np.ndarray, voxel_size: float, ref: bool = False) -> np.ndarray:
+    lib = load(ref=ref)
     a = np.ascontiguousarray(xyz4, dtype=np.float32)
     out = np.zeros_like(a)
     n = lib.vo_down_sampling_voxel(C.c_int(a.shape[0]), _fp(a), C.c_double(voxel_size), _fp(out))
     return out[:n].copy()
 
 
-def exp_so3(w, dt=None):
-    lib = load()
+def exp_so3(w, dt=None, ref: bool = False):
+    lib = load(ref=ref)
     R = np.zeros(9)
     w = np.ascontiguousarray(w, dtype=np.float64)
     if dt is None:
@@ -319,8 +358,8 @@ def exp_so3(w, dt=None):
     return R.reshape(3, 3).T
 
 
-def log_so3(R):
-    lib = load()
+def log_so3(R, ref: bool = False):
+    lib = load(ref=ref)
     a = np.ascontiguousarray(np.asarray(R, dtype=np.float64).T.reshape(-1))
     w = np.zeros(3)
     lib.vo_log(_dp(a), _dp(w))

@@ -1,0 +1,653 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// Harness around the REFERENCE'S OWN SOURCES. The Makefile target `_ref` compiles, unmodified and where
+// they lie under /root/reference,
+//     src/core/point_utils.cpp   src/mapping/octree.cpp   src/mapping/voxel_map.cpp
+//     src/estimation/imu_ekf.cpp src/pipeline/odometry.cpp
+// against the header shims in oracle/ref_shim/ (a minimal eager Eigen, the PCL point/cloud types and the
+// ROS message fields those files touch - none of Eigen / PCL / ROS 2 is installed here), and links them
+// with this file into oracle/_ref/libvina_ref.so. This file supplies only what lives in reference files that
+// cannot be compiled here (they need the whole ROS 2 node):
+//   * the two globals of node.cpp:38 and the VINA_SLAM constructor (node.cpp:52) reduced to nothing,
+//   * the trivial container methods of LidarFactor / NormalFactor (factors.cpp:7-20, 160-183, 348-355),
+//   * the fan-out drivers multi_recut / multi_margi (local_mapping.cpp:17-84, 144-201) and the scan body
+//     of thd_odometry_localmapping (local_mapping.cpp:389-546) - loops that call the reference's real
+//     OctoTree::recut / tras_opt / margi, cut_voxel_multi, var_init, pvec_update, IMUEKF::process and
+//     VINA_SLAM::VNC_lio.
+// It exports the same plain-C API as oracle_capi.cpp, so the Python tests drive the restatement and the
+// reference with identical code and compare them (tests/test_oracle_vs_ref.py).
+// Because the reference keeps its configuration in mutable globals (octree.cpp:67-75) only ONE instance
+// may exist per process.
+#include "vina_slam/platform/ros2/node.hpp"
+#include "vina_slam/core/point_utils.hpp"
+#include "vina_slam/mapping/voxel_map.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "oracle_capi.h"
+
+double dept_err, beam_err;  // node.cpp:38
+
+VINA_SLAM::VINA_SLAM(const rclcpp::Node::SharedPtr& node_in) : node(node_in) {}
+
+// factors.cpp:7-20, 160-168
+LidarFactor::LidarFactor(int _w) : win_size(_w) {}
+void LidarFactor::push_voxel(vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Eigen::Vector3d& eig_value,
+                             Eigen::Matrix3d& eig_vector, PointCluster& pcr_add)
+{
+  plvec_voxels.push_back(vec_orig);
+  sig_vecs.push_back(fix);
+  coeffs.push_back(coe);
+  eig_values.push_back(eig_value);
+  eig_vectors.push_back(eig_vector);
+  pcr_adds.push_back(pcr_add);
+}
+void LidarFactor::clear()
+{
+  sig_vecs.clear();
+  plvec_voxels.clear();
+  eig_values.clear();
+  eig_vectors.clear();
+  pcr_adds.clear();
+  coeffs.clear();
+}
+// factors.cpp:171-183, 348-355
+NormalFactor::NormalFactor(int _w) : win_size(_w) {}
+void NormalFactor::push_voxel(std::vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Eigen::Vector3d& n_ref,
+                              PointCluster& pcr_add)
+{
+  plvec_voxels.push_back(vec_orig);
+  sig_vecs.push_back(fix);
+  coeffs.push_back(coe);
+  n_refs.push_back(n_ref.normalized());
+  pcr_adds.push_back(pcr_add);
+}
+void NormalFactor::clear()
+{
+  sig_vecs.clear();
+  plvec_voxels.clear();
+  coeffs.clear();
+  n_refs.clear();
+  pcr_adds.clear();
+}
+
+namespace
+{
+double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct RefOdom
+{
+  VINA_SLAM vs;
+  LidarFactor voxhess;
+  NormalFactor normalFactor;
+  PLV(3) pwld;
+  int degrade_cnt = 0;
+  double t_odom = 0, t_insert = 0, t_recut = 0, t_margi = 0;
+  pcl::PointCloud<PointType> last_down;
+  RefOdom(int win) : vs(nullptr), voxhess(win), normalFactor(win) {}
+
+  // local_mapping.cpp:144-201 (the overload the per-scan loop calls, :451)
+  void multi_recut(unordered_map<VOXEL_LOC, OctoTree*>& feat_map, int win_count, vector<IMUST>& xs)
+  {
+    auto& sws = vs.sws;
+    int thd_num = vs.thread_num;
+    vector<vector<OctoTree*>> octss(thd_num);
+    int g_size = feat_map.size();
+    if (g_size < thd_num) return;
+    vector<thread*> mthreads(thd_num);
+    double part = 1.0 * g_size / thd_num;
+    int cnt = 0;
+    for (auto iter = feat_map.begin(); iter != feat_map.end(); iter++)
+    {
+      octss[cnt].push_back(iter->second);
+      if (octss[cnt].size() >= part && cnt < thd_num - 1) cnt++;
+    }
+    auto recut_func = [](int win_count, vector<OctoTree*>& oct, vector<IMUST> xxs, vector<SlideWindow*>& sw) {
+      for (OctoTree* oc : oct) oc->recut(win_count, xxs, sw);
+    };
+    for (int i = 1; i < thd_num; i++)
+      mthreads[i] = new thread(recut_func, win_count, ref(octss[i]), xs, ref(sws[i]));
+    for (int i = 0; i < thd_num; i++)
+    {
+      if (i == 0)
+        recut_func(win_count, octss[i], xs, sws[i]);
+      else
+      {
+        mthreads[i]->join();
+        delete mthreads[i];
+      }
+    }
+    for (size_t i = 1; i < sws.size(); i++)
+    {
+      sws[0].insert(sws[0].end(), sws[i].begin(), sws[i].end());
+      sws[i].clear();
+    }
+    for (auto iter = feat_map.begin(); iter != feat_map.end(); iter++)
+    {
+      iter->second->tras_opt(voxhess);
+      iter->second->tras_opt(normalFactor);
+    }
+  }
+
+  // local_mapping.cpp:17-84
+  void multi_margi(unordered_map<VOXEL_LOC, OctoTree*>& feat_map, double jour, int win_count, vector<IMUST>& xs,
+                   vector<SlideWindow*>& sw)
+  {
+    int thd_num = vs.thread_num;
+    vector<vector<OctoTree*>*> octs;
+    for (int i = 0; i < thd_num; i++) octs.push_back(new vector<OctoTree*>());
+    int g_size = feat_map.size();
+    if (g_size < thd_num) return;
+    vector<thread*> mthreads(thd_num);
+    double part = 1.0 * g_size / thd_num;
+    int cnt = 0;
+    for (auto iter = feat_map.begin(); iter != feat_map.end(); iter++)
+    {
+      iter->second->jour = jour;
+      octs[cnt]->push_back(iter->second);
+      if (octs[cnt]->size() >= part && cnt < thd_num - 1) cnt++;
+    }
+    auto margi_func = [](int win_cnt, vector<OctoTree*>* oct, vector<IMUST> xxs, LidarFactor& vh) {
+      for (OctoTree* oc : *oct) oc->margi(win_cnt, 1, xxs, vh);
+    };
+    for (int i = 1; i < thd_num; i++) mthreads[i] = new thread(margi_func, win_count, octs[i], xs, ref(voxhess));
+    for (int i = 0; i < thd_num; i++)
+    {
+      if (i == 0)
+        margi_func(win_count, octs[i], xs, voxhess);
+      else
+      {
+        mthreads[i]->join();
+        delete mthreads[i];
+      }
+    }
+    for (auto iter = feat_map.begin(); iter != feat_map.end();)
+    {
+      if (iter->second->isexist)
+        iter++;
+      else
+      {
+        iter->second->clear_slwd(sw);
+        feat_map.erase(iter++);
+      }
+    }
+    for (int i = 0; i < thd_num; i++) delete octs[i];
+  }
+
+  // local_mapping.cpp:434-451 and 489-546 with if_BA == 0
+  void map_update(PVecPtr pptr)
+  {
+    const int mgsize = 1;
+    vs.win_count++;
+    vs.x_buf.push_back(vs.x_curr);
+    vs.pvec_buf.push_back(pptr);
+    voxhess.clear();
+    voxhess.win_size = vs.win_size;
+    normalFactor.clear();
+    normalFactor.win_size = vs.win_size;
+    double t1 = now_s();
+    cut_voxel_multi(vs.surf_map, vs.pvec_buf[vs.win_count - 1], vs.win_count - 1, vs.surf_map_slide, vs.win_size, pwld,
+                    vs.sws);
+    double t2 = now_s();
+    multi_recut(vs.surf_map_slide, vs.win_count, vs.x_buf);
+    double t3 = now_s();
+    t_insert = t2 - t1;
+    t_recut = t3 - t2;
+    t_margi = 0;
+    if (vs.win_count >= vs.win_size)
+    {
+      vs.x_curr.R = vs.x_buf[vs.win_count - 1].R;
+      vs.x_curr.p = vs.x_buf[vs.win_count - 1].p;
+      double t5 = now_s();
+      multi_margi(vs.surf_map_slide, 0.0, vs.win_count, vs.x_buf, vs.sws[0]);
+      t_margi = now_s() - t5;
+      for (int i = 0; i < vs.win_size; i++)
+      {
+        mp[i] += mgsize;
+        if (mp[i] >= vs.win_size) mp[i] -= vs.win_size;
+      }
+      for (int i = mgsize; i < vs.win_count; i++)
+      {
+        vs.x_buf[i - mgsize] = vs.x_buf[i];
+        PVecPtr pvec_tem = vs.pvec_buf[i - mgsize];
+        vs.pvec_buf[i - mgsize] = vs.pvec_buf[i];
+        vs.pvec_buf[i] = pvec_tem;
+      }
+      for (int i = vs.win_count - mgsize; i < vs.win_count; i++)
+      {
+        vs.x_buf.pop_back();
+        vs.pvec_buf.pop_back();
+      }
+      vs.win_base += mgsize;
+      vs.win_count -= mgsize;
+    }
+  }
+
+  void downsample(pcl::PointCloud<PointType>& pcl_curr, pcl::PointCloud<PointType>& pl_down)
+  {
+    pl_down = pcl_curr;  // local_mapping.cpp:396-403
+    down_sampling_voxel(pl_down, vs.down_size);
+    if (pl_down.size() < 2000)
+    {
+      pl_down = pcl_curr;
+      down_sampling_voxel(pl_down, vs.down_size / 2);
+    }
+    last_down = pl_down;
+  }
+
+  // local_mapping.cpp:389-546
+  int step(pcl::PointCloud<PointType>& pcl_curr, double beg, deque<std::shared_ptr<sensor_msgs::msg::Imu>>& imus,
+           bool iekf_on_full)
+  {
+    double t0 = now_s();
+    vs.odom_ekf.pcl_beg_time = beg;
+    vs.odom_ekf.pcl_end_time = beg + pcl_curr.back().curvature;  // sync.cpp:40
+    if (vs.odom_ekf.last_pcl_end_time - vs.odom_ekf.pcl_beg_time > 0.01) return -1;  // the reference exit(0)s
+    if (vs.odom_ekf.process(vs.x_curr, pcl_curr, imus) == 0) return -2;
+    pcl::PointCloud<PointType> pl_down;
+    downsample(pcl_curr, pl_down);
+    PVecPtr pptr(new PVec);
+    var_init(vs.extrin_para, pl_down, pptr, dept_err, beam_err);
+    auto pcl_curr_temp = pcl_curr;
+    PVecPtr no_ds_pptr(new PVec);
+    var_init(vs.extrin_para, pcl_curr_temp, no_ds_pptr, dept_err, beam_err);
+    bool ok = iekf_on_full ? vs.VNC_lio(no_ds_pptr) : vs.VNC_lio(pptr);  // :413 (production) / 4-iteration budget
+    if (ok)
+    {
+      if (degrade_cnt > 0) degrade_cnt--;
+    }
+    else
+      degrade_cnt++;
+    pwld.clear();
+    pvec_update(pptr, vs.x_curr, pwld);
+    t_odom = now_s() - t0;
+    map_update(pptr);
+    return 0;
+  }
+
+  void bootstrap(pcl::PointCloud<PointType>& pcl_deskewed, const IMUST& x_known)
+  {
+    vs.x_curr = x_known;
+    pcl::PointCloud<PointType> pl_down;
+    downsample(pcl_deskewed, pl_down);
+    PVecPtr pptr(new PVec);
+    var_init(vs.extrin_para, pl_down, pptr, dept_err, beam_err);
+    pwld.clear();
+    pvec_update(pptr, vs.x_curr, pwld);
+    map_update(pptr);
+  }
+};
+
+RefOdom* g_inst = nullptr;
+
+void to_imust(const vo_state* s, IMUST& x)
+{
+  x.t = s->t;
+  memcpy(x.R.data(), s->R, 72);
+  memcpy(x.p.data(), s->p, 24);
+  memcpy(x.v.data(), s->v, 24);
+  memcpy(x.bg.data(), s->bg, 24);
+  memcpy(x.ba.data(), s->ba, 24);
+  memcpy(x.g.data(), s->g, 24);
+  memcpy(x.cov.data(), s->cov, sizeof(s->cov));
+}
+void from_imust(const IMUST& x, vo_state* s)
+{
+  s->t = x.t;
+  memcpy(s->R, x.R.data(), 72);
+  memcpy(s->p, x.p.data(), 24);
+  memcpy(s->v, x.v.data(), 24);
+  memcpy(s->bg, x.bg.data(), 24);
+  memcpy(s->ba, x.ba.data(), 24);
+  memcpy(s->g, x.g.data(), 24);
+  memcpy(s->cov, x.cov.data(), sizeof(s->cov));
+}
+pcl::PointCloud<PointType> to_cloud(const float* xyz4, int n)
+{
+  pcl::PointCloud<PointType> c;
+  c.resize(n);
+  for (int i = 0; i < n; i++)
+  {
+    c[i].x = xyz4[4 * i + 0];
+    c[i].y = xyz4[4 * i + 1];
+    c[i].z = xyz4[4 * i + 2];
+    c[i].curvature = xyz4[4 * i + 3];
+  }
+  return c;
+}
+void from_cloud(const pcl::PointCloud<PointType>& c, float* xyz4)
+{
+  for (size_t i = 0; i < c.size(); i++)
+  {
+    xyz4[4 * i + 0] = c[i].x;
+    xyz4[4 * i + 1] = c[i].y;
+    xyz4[4 * i + 2] = c[i].z;
+    xyz4[4 * i + 3] = c[i].curvature;
+  }
+}
+std::shared_ptr<sensor_msgs::msg::Imu> to_imu(const double* q)
+{
+  auto m = std::make_shared<sensor_msgs::msg::Imu>();
+  m->header.stamp = rclcpp::Time((int64_t)llround(q[0] * 1e9));
+  m->angular_velocity.x = q[1];
+  m->angular_velocity.y = q[2];
+  m->angular_velocity.z = q[3];
+  m->linear_acceleration.x = q[4];
+  m->linear_acceleration.y = q[5];
+  m->linear_acceleration.z = q[6];
+  return m;
+}
+}  // namespace
+
+extern "C" {
+
+void vo_var_init(int n, const float* xyz4, const double ext_R[9], const double ext_t[3], double dept, double beam,
+                 double* pnt, double* var)
+{
+  IMUST ext;
+  memcpy(ext.R.data(), ext_R, 72);
+  memcpy(ext.p.data(), ext_t, 24);
+  auto c = to_cloud(xyz4, n);
+  PVecPtr pptr(new PVec);
+  var_init(ext, c, pptr, dept, beam);
+  for (int i = 0; i < n; i++)
+  {
+    memcpy(pnt + 3 * (size_t)i, (*pptr)[i].pnt.data(), 24);
+    memcpy(var + 9 * (size_t)i, (*pptr)[i].var.data(), 72);
+  }
+}
+void vo_pvec_update(int n, const double* pnt, double* var, const double R[9], const double p[3], const double cov[225],
+                    double* pw)
+{
+  IMUST x;
+  memcpy(x.R.data(), R, 72);
+  memcpy(x.p.data(), p, 24);
+  memcpy(x.cov.data(), cov, 225 * 8);
+  PVecPtr pptr(new PVec(n));
+  for (int i = 0; i < n; i++)
+  {
+    memcpy((*pptr)[i].pnt.data(), pnt + 3 * (size_t)i, 24);
+    memcpy((*pptr)[i].var.data(), var + 9 * (size_t)i, 72);
+  }
+  PLV(3) out;
+  pvec_update(pptr, x, out);
+  for (int i = 0; i < n; i++)
+  {
+    memcpy(var + 9 * (size_t)i, (*pptr)[i].var.data(), 72);
+    memcpy(pw + 3 * (size_t)i, out[i].data(), 24);
+  }
+}
+int vo_down_sampling_voxel(int n, const float* in, double vs, float* out)
+{
+  auto c = to_cloud(in, n);
+  down_sampling_voxel(c, vs);
+  from_cloud(c, out);
+  return (int)c.size();
+}
+void vo_exp(const double w[3], double R[9])
+{
+  Eigen::Matrix3d r = Exp(Eigen::Vector3d(w[0], w[1], w[2]));
+  memcpy(R, r.data(), 72);
+}
+void vo_exp_dt(const double w[3], double dt, double R[9])
+{
+  Eigen::Matrix3d r = Exp(Eigen::Vector3d(w[0], w[1], w[2]), dt);
+  memcpy(R, r.data(), 72);
+}
+void vo_log(const double R[9], double w[3])
+{
+  Eigen::Matrix3d m;
+  memcpy(m.data(), R, 72);
+  Eigen::Vector3d r = Log(m);
+  memcpy(w, r.data(), 24);
+}
+
+void* vo_odom_create(const vo_config* cfg)
+{
+  if (g_inst) return nullptr;  // the reference's globals allow one instance per process
+  RefOdom* o = new RefOdom(cfg->win_size);
+  VINA_SLAM& vs = o->vs;
+  voxel_size = cfg->voxel_size;
+  min_eigen_value = cfg->min_eigen_value;
+  plane_eigen_value_thre.assign(cfg->plane_eigen_value_thre, cfg->plane_eigen_value_thre + 4);
+  for (double& it : plane_eigen_value_thre) it = 1.0 / it;  // node.cpp:256-259
+  min_point << cfg->min_point[0], cfg->min_point[1], cfg->min_point[2], cfg->min_point[3];
+  max_layer = cfg->max_layer;
+  max_points = cfg->max_points;
+  dept_err = cfg->dept_err;
+  beam_err = cfg->beam_err;
+  vs.down_size = cfg->down_size;
+  vs.win_size = cfg->win_size;
+  vs.thread_num = cfg->thread_num;
+  vs.if_BA = 0;
+  vs.sws.resize(cfg->thread_num);  // node.cpp:289
+  mp.resize(cfg->win_size);
+  for (int i = 0; i < cfg->win_size; i++) mp[i] = i;  // node.cpp:431-435
+  memcpy(vs.extrin_para.R.data(), cfg->ext_R, 72);
+  memcpy(vs.extrin_para.p.data(), cfg->ext_t, 24);
+  IMUEKF& e = vs.odom_ekf;
+  e.Lid_rot_to_IMU = vs.extrin_para.R;
+  e.Lid_offset_to_IMU = vs.extrin_para.p;
+  e.cov_gyr << cfg->cov_gyr, cfg->cov_gyr, cfg->cov_gyr;  // node.cpp:211-214
+  e.cov_acc << cfg->cov_acc, cfg->cov_acc, cfg->cov_acc;
+  e.cov_bias_gyr << cfg->rdw_gyr, cfg->rdw_gyr, cfg->rdw_gyr;
+  e.cov_bias_acc << cfg->rdw_acc, cfg->rdw_acc, cfg->rdw_acc;
+  e.init_flag = true;  // the harness bootstraps instead of IMU_init
+  e.pcl_beg_time = e.pcl_end_time = e.last_pcl_end_time = 0;
+  vs.x_curr.g = Eigen::Vector3d(0, 0, -9.8);
+  g_inst = o;
+  return o;
+}
+void vo_odom_destroy(void* h)
+{
+  RefOdom* o = (RefOdom*)h;
+  for (auto& kv : o->vs.surf_map)
+  {
+    kv.second->delete_ptr();
+    delete kv.second;
+  }
+  for (auto& v : o->vs.sws)
+    for (SlideWindow* s : v) delete s;
+  delete o;
+  g_inst = nullptr;
+}
+void vo_odom_set_state(void* h, const vo_state* s) { to_imust(s, ((RefOdom*)h)->vs.x_curr); }
+void vo_odom_get_state(void* h, vo_state* s) { from_imust(((RefOdom*)h)->vs.x_curr, s); }
+void vo_odom_set_imu_anchor(void* h, double last_end, const double last_imu7[7], double scale_gravity)
+{
+  IMUEKF& e = ((RefOdom*)h)->vs.odom_ekf;
+  e.last_pcl_end_time = last_end;
+  e.last_imu = to_imu(last_imu7);
+  e.scale_gravity = scale_gravity;
+}
+void vo_odom_bootstrap(void* h, const float* xyz4, int n, const vo_state* x_known)
+{
+  auto c = to_cloud(xyz4, n);
+  IMUST x;
+  to_imust(x_known, x);
+  ((RefOdom*)h)->bootstrap(c, x);
+}
+int vo_odom_step(void* h, float* xyz4, int n, double beg, const double* imu7, int m, int iekf_on_full, int max_iter)
+{
+  (void)max_iter;  // the reference's VNC_lio budget is fixed at 4 (odometry.cpp:68)
+  auto c = to_cloud(xyz4, n);
+  deque<std::shared_ptr<sensor_msgs::msg::Imu>> imus;
+  for (int i = 0; i < m; i++) imus.push_back(to_imu(imu7 + 7 * (size_t)i));
+  int r = ((RefOdom*)h)->step(c, beg, imus, iekf_on_full != 0);
+  from_cloud(c, xyz4);
+  return r;
+}
+void vo_odom_stage_times(void* h, double t[4])
+{
+  RefOdom* o = (RefOdom*)h;
+  t[0] = o->t_odom;
+  t[1] = o->t_insert;
+  t[2] = o->t_recut;
+  t[3] = o->t_margi;
+}
+int vo_odom_last_down(void* h, float* xyz4, int cap)
+{
+  RefOdom* o = (RefOdom*)h;
+  int n = (int)o->last_down.size();
+  if (xyz4 && cap >= n) from_cloud(o->last_down, xyz4);
+  return n;
+}
+// motion_blur in one piece (the reference does not split propagation and deskew)
+int vo_odom_motion_blur(void* h, float* xyz4, int n, double beg, double end, const double* imu7, int m)
+{
+  RefOdom* o = (RefOdom*)h;
+  auto c = to_cloud(xyz4, n);
+  deque<std::shared_ptr<sensor_msgs::msg::Imu>> imus;
+  for (int i = 0; i < m; i++) imus.push_back(to_imu(imu7 + 7 * (size_t)i));
+  o->vs.odom_ekf.pcl_beg_time = beg;
+  o->vs.odom_ekf.pcl_end_time = end;
+  if (o->vs.odom_ekf.last_pcl_end_time - beg > 0.01) return -1;
+  o->vs.odom_ekf.motion_blur(o->vs.x_curr, c, imus);
+  from_cloud(c, xyz4);
+  return 0;
+}
+int vo_odom_imu_poses(void* h, double* poses22, int cap)
+{
+  RefOdom* o = (RefOdom*)h;
+  auto& ps = o->vs.odom_ekf.imu_poses;
+  int n = (int)ps.size();
+  if (!poses22 || cap < n) return n;
+  for (int i = 0; i < n; i++)
+  {
+    double* q = poses22 + 22 * (size_t)i;
+    q[0] = ps[i].t;
+    memcpy(q + 1, ps[i].R.data(), 72);
+    memcpy(q + 10, ps[i].p.data(), 24);
+    memcpy(q + 13, ps[i].v.data(), 24);
+    memcpy(q + 16, ps[i].bg.data(), 24);
+    memcpy(q + 19, ps[i].ba.data(), 24);
+  }
+  return n;
+}
+// VINA_SLAM::VNC_lio on caller-provided pointVar arrays
+int vo_odom_iekf(void* h, int n, const double* pnt, const double* var, int max_iter)
+{
+  (void)max_iter;
+  RefOdom* o = (RefOdom*)h;
+  PVecPtr pptr(new PVec(n));
+  for (int i = 0; i < n; i++)
+  {
+    memcpy((*pptr)[i].pnt.data(), pnt + 3 * (size_t)i, 24);
+    memcpy((*pptr)[i].var.data(), var + 9 * (size_t)i, 72);
+  }
+  return o->vs.VNC_lio(pptr) ? 1 : 0;
+}
+// match() (voxel_map.cpp:241-266) for world points with given world covariances
+int vo_odom_match(void* h, int n, const double* wld, const double* var, uint8_t* flags, double* sigma, double* centers)
+{
+  RefOdom* o = (RefOdom*)h;
+  int cnt = 0;
+  for (int i = 0; i < n; i++)
+  {
+    Eigen::Vector3d w(wld[3 * (size_t)i], wld[3 * (size_t)i + 1], wld[3 * (size_t)i + 2]);
+    Eigen::Matrix3d v;
+    memcpy(v.data(), var + 9 * (size_t)i, 72);
+    Plane* pla = nullptr;
+    double sd = 0;
+    OctoTree* oc = nullptr;
+    int f = match(o->vs.surf_map, w, pla, v, sd, oc);
+    flags[i] = f ? 1 : 0;
+    sigma[i] = f ? sd : 0.0;
+    for (int k = 0; k < 3; k++) centers[3 * (size_t)i + k] = f ? pla->center[k] : 0.0;
+    cnt += f ? 1 : 0;
+  }
+  return cnt;
+}
+void vo_odom_map_update(void* h, int n, const double* pnt, const double* var)
+{
+  RefOdom* o = (RefOdom*)h;
+  PVecPtr pptr(new PVec(n));
+  for (int i = 0; i < n; i++)
+  {
+    memcpy((*pptr)[i].pnt.data(), pnt + 3 * (size_t)i, 24);
+    memcpy((*pptr)[i].var.data(), var + 9 * (size_t)i, 72);
+  }
+  o->pwld.clear();
+  pvec_update(pptr, o->vs.x_curr, o->pwld);
+  o->map_update(pptr);
+}
+
+static void count_nodes(OctoTree* n, int64_t& c)
+{
+  c++;
+  for (int i = 0; i < 8; i++)
+    if (n->leaves[i]) count_nodes(n->leaves[i], c);
+}
+int64_t vo_odom_map_count(void* h, int64_t* n_roots, int64_t* n_slide)
+{
+  RefOdom* o = (RefOdom*)h;
+  int64_t c = 0;
+  for (auto& kv : o->vs.surf_map) count_nodes(kv.second, c);
+  if (n_roots) *n_roots = (int64_t)o->vs.surf_map.size();
+  if (n_slide) *n_slide = (int64_t)o->vs.surf_map_slide.size();
+  return c;
+}
+static void export_node(RefOdom* o, OctoTree* n, const VOXEL_LOC& key, int path, vo_node_record* out, int64_t cap,
+                        int64_t& c)
+{
+  if (c < cap)
+  {
+    vo_node_record& r = out[c];
+    memset(&r, 0, sizeof(r));
+    r.key[0] = key.x;
+    r.key[1] = key.y;
+    r.key[2] = key.z;
+    r.code = n->layer | (path << 2);
+    r.layer = n->layer;
+    r.octo_state = n->octo_state;
+    r.isexist = n->isexist;
+    r.has_sw = n->sw != nullptr;
+    r.is_plane = n->plane.is_plane;
+    r.last_num = n->last_num;
+    r.opt_state = n->opt_state >= 0 ? 1 : 0;
+    r.N_add = n->pcr_add.N;
+    r.N_fix = n->pcr_fix.N;
+    r.n_point_fix = (int)n->point_fix.size();
+    if (n->sw)
+      for (int i = 0; i < o->vs.win_size && i < 16; i++)
+      {
+        r.N_local[i] = n->sw->pcrs_local[mp[i]].N;
+        r.n_win_points += (int)n->sw->points[mp[i]].size();
+      }
+    memcpy(r.P_add, n->pcr_add.P.data(), 72);
+    memcpy(r.v_add, n->pcr_add.v.data(), 24);
+    memcpy(r.P_fix, n->pcr_fix.P.data(), 72);
+    memcpy(r.v_fix, n->pcr_fix.v.data(), 24);
+    memcpy(r.eig_value, n->eig_value.data(), 24);
+    memcpy(r.eig_vector, n->eig_vector.data(), 72);
+    memcpy(r.center, n->plane.center.data(), 24);
+    memcpy(r.normal, n->plane.normal.data(), 24);
+    memcpy(r.plane_var, n->plane.plane_var.data(), 288);
+    r.radius = n->plane.radius;
+    memcpy(r.cov_add, n->cov_add.data(), 648);
+    memcpy(r.voxel_center, n->voxel_center, 24);
+    r.quater_length = n->quater_length;
+  }
+  c++;
+  for (int i = 0; i < 8; i++)
+    if (n->leaves[i]) export_node(o, n->leaves[i], key, path | (i << (3 * n->layer)), out, cap, c);
+}
+int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap)
+{
+  RefOdom* o = (RefOdom*)h;
+  int64_t c = 0;
+  for (auto& kv : o->vs.surf_map) export_node(o, kv.second, kv.first, 0, out, cap, c);
+  return c;
+}
+int vo_odom_window(void* h, int* win_count, int* mpo, int cap)
+{
+  RefOdom* o = (RefOdom*)h;
+  *win_count = o->vs.win_count;
+  for (int i = 0; i < o->vs.win_size && i < cap; i++) mpo[i] = mp[i];
+  return o->vs.win_size;
+}
+}

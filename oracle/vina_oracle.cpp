@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see vina_oracle.hpp).
+// ORACLE — TEST INFRASTRUCTURE ONLY (pinned against oracle/_ref, see vina_oracle.hpp).
 // CPU restatement of the VINA-SLAM per-scan hot path; each function cites the
 // reference file:line it follows.
 #include "vina_oracle.hpp"

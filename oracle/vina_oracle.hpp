@@ -1,12 +1,17 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY.
 //
 // CPU restatement of the VINA-SLAM per-scan hot path (SURVEY.md §8a rows
-// a1-a13). The reference (/root/reference, C++17 on ROS 2 + PCL + Eigen3)
-// cannot be compiled in this image (no Eigen/PCL/ROS) and has
-// no tests, golden vectors or fixtures, so this restatement cannot be pinned
-// against reference outputs: "parity unpinned". It is validated instead by
-// analytic checks (tests/test_oracle_*.py): numpy eigh / inv, numerical
-// Jacobians, cluster invariants and synthetic scenes with known planes/poses.
+// a1-a13). The reference (/root/reference, C++17 on ROS 2 + PCL + Eigen3) has
+// no tests, golden vectors or fixtures and its own build cannot run here (no
+// Eigen/PCL/ROS). PINNING: the reference's own source files
+// (point_utils.cpp, octree.cpp, voxel_map.cpp, imu_ekf.cpp, odometry.cpp) are
+// compiled unmodified against the header shims of oracle/ref_shim into
+// oracle/_ref/libvina_ref.so (oracle/Makefile, target `ref`); this restatement
+// reproduces that build BIT FOR BIT on whole synthetic sequences
+// (tests/test_oracle_vs_ref.py, golden vectors tests/golden/ref_small.npz).
+// What stays restated on both sides is Eigen itself (absent, version unpinned
+// by the reference): SelfAdjointEigenSolver and inverse() follow Eigen 3.4.0 and
+// are checked against numpy (tests/test_oracle.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may use anything in this directory. The product
