@@ -206,7 +206,12 @@ int vina_odom_step_resident(vina_ctx* ctx, const void* d_xyzt, int n, double pcl
 /* stage-wise pieces of the step, for parity tests */
 int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
                         vina_imu_pose* poses_out, int cap); /* returns #poses */
+/* VINA_SLAM::LioStateEstimation (odometry.cpp:64-255) on the current state. vina_odom_iekf keeps the whole
+ * iteration loop on the device (k_iekf accumulates, its last block solves and updates the device-resident
+ * iterate; one host synchronisation per call). vina_odom_iekf_host is the same loop with the 15x15 update
+ * (odometry.cpp:192-230) on the host, one 34-double readback per iteration - the cross-check of the former. */
 int vina_odom_iekf(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate);
+int vina_odom_iekf_host(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate);
 int vina_odom_map_update(vina_ctx* ctx); /* pvec_update + insert + recut + (margi + shift) with x_curr */
 int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap);
 int vina_get_timings(vina_ctx* ctx, vina_timings* t);

@@ -64,7 +64,8 @@ EXPORTS = [
     "vina_iekf_accumulate", "vina_iekf_accumulate_debug", "vina_iekf_debug_assoc", "vina_map_insert",
     "vina_map_recut", "vina_map_margi", "vina_map_shift_window", "vina_map_count", "vina_map_export",
     "vina_odom_set_state", "vina_odom_get_state", "vina_odom_set_imu_anchor", "vina_odom_bootstrap",
-    "vina_odom_step", "vina_odom_step_resident", "vina_odom_propagate", "vina_odom_iekf", "vina_odom_map_update",
+    "vina_odom_step", "vina_odom_step_resident", "vina_odom_propagate", "vina_odom_iekf", "vina_odom_iekf_host",
+    "vina_odom_map_update",
     "vina_odom_window", "vina_get_timings", "vina_set_profiling",
 ]
 
@@ -338,9 +339,10 @@ class Ctx:
                                                   poses.ctypes.data_as(C.c_void_p), C.c_int(96)))
         return poses[:k]
 
-    def odom_iekf(self, which: int, max_iter: int):
+    def odom_iekf(self, which: int, max_iter: int, host_solve: bool = False):
         it, ok = C.c_int(0), C.c_int(0)
-        self._ck(self.lib.vina_odom_iekf(self.h, C.c_int(which), C.c_int(max_iter), C.byref(it), C.byref(ok)))
+        fn = self.lib.vina_odom_iekf_host if host_solve else self.lib.vina_odom_iekf
+        self._ck(fn(self.h, C.c_int(which), C.c_int(max_iter), C.byref(it), C.byref(ok)))
         return it.value, ok.value
 
     def odom_map_update(self):

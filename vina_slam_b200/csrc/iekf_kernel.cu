@@ -1,124 +1,302 @@
-// The hot kernel: one IEKF iteration of VINA_SLAM::LioStateEstimation's point
-// loop (src/pipeline/odometry.cpp:111-148): world point, cached-leaf test
-// (OctoTree::inside, octree.cpp:732-737), voxel-hash lookup (match,
-// voxel_map.cpp:241-266), octree descent and gate (OctoTree::match,
-// octree.cpp:551-595), residual / Jacobian and the 6x6 H = J^T R^-1 J, b, n n^T
-// reduction (odometry.cpp:136-146).
+// The hot kernel: one IEKF iteration of VINA_SLAM::LioStateEstimation
+// (src/pipeline/odometry.cpp:98-231) for one or several independent sequences:
+//   * the point loop (odometry.cpp:111-148): world point, cached-leaf test (OctoTree::inside,
+//     octree.cpp:732-737), voxel-hash lookup (match, voxel_map.cpp:241-266), octree descent and gate
+//     (OctoTree::match, octree.cpp:551-595), residual / Jacobian and the H = J^T R^-1 J, b, n n^T sums
+//     (odometry.cpp:136-146);
+//   * optionally (VN_IEKF_SOLVE) the update itself (odometry.cpp:192-230): K = (blkdiag(H,0) + P^-1)^-1,
+//     delta, boxplus, convergence / rematch logic and the final P = (I - G) P, done by one warp of the block
+//     that finishes last - the iterate lives in device memory (IekfDev) and the host is not in the loop.
 //
-// Roofline: HBM-bound streaming of the pointVar SoA (72 B/pt + 8 B cache RMW)
-// plus gathers of 16-B hash slots and 256-B leaf records; the dependent chain
-// cache -> leaf record (or key -> slot -> root -> child -> leaf) makes it
-// latency-bound unless enough points are in flight, so the kernel is shaped for
-// occupancy: ONE point per thread, and the 34 sums never live in registers as
-// accumulators - each warp reduces its 32 points at once with a transposed
-// butterfly (reduce-scatter over lanes: 36 double shuffles instead of 170) that
-// leaves two finished sums per lane. No dense contraction -> no tensor cores.
+// Roofline: HBM-bound streaming of the pointVar SoA (72 B/pt + 8 B cache RMW) plus gathers of 16-B hash slots
+// and 256-B leaf records; the dependent chain cache -> leaf record (or key -> slot -> root -> child -> leaf)
+// makes it latency-bound unless enough points are in flight, so the kernel is shaped for occupancy: one
+// 1024-thread block per SM, one point per thread per round, 64 registers.
 //
-// Numerics: every decision-bearing expression (wld, key, child index, inside,
-// the fp32 gate) uses the single-rounding helpers of vn_math.cuh in the order of
-// SURVEY.md Appendix A, so keys and associations are bit-exact against the CPU
-// restatement. sigma_l and the sums use FMA freely (tolerance 1e-4 rel):
-// n^T var_world n is evaluated as (R^T n)^T var (R^T n) + (n x p)^T S_R (n x p)
-// + n^T S_t n, which needs ~1/4 of the flops of forming var_world.
-// The reduction order is fixed (butterfly, warps in order, blocks in order):
-// results are deterministic run to run.
+// Reduction: the 6x6 / 6 / 3x3 sums are a rank-1 update per point, C += a_i b_i^T with
+//   a = [Rinv*j (6), n0, n1],  b = [j (6), r, 0],   j = [p x R^T n ; n]
+// so that C(0:6,0:6) = H, C(0:6,6) = -b, C(6:8,3:6) = rows 0,1 of n n^T. The warp hands its 32 (a, b) pairs to
+// the FP64 tensor pipe: 8 x mma.sync.m8n8k4.f64 (DMMA, 4 points each) per round, operands staged through a
+// per-warp shared-memory tile - 37 TFLOP/s on B200 (scripts/fp64_pipes.cu), the same rate as the vector DFMA
+// pipe but ~40 issue slots per round instead of the ~700 of a shuffle tree. n2*n2 and the match count are
+// per-thread accumulators reduced once at the end. Everything is summed in a fixed order (DMMA chain, warps in
+// order, blocks in order): results are deterministic run to run.
+//
+// Numerics: every decision-bearing expression (wld, key, child index, inside, the fp32 gate) uses the
+// single-rounding helpers of vn_math.cuh in the order of SURVEY.md Appendix A, so keys and associations are
+// bit-exact against the CPU restatement. sigma_l and the sums use FMA freely (tolerance 1e-4 rel):
+// n^T var_world n is evaluated as (R^T n)^T var (R^T n) + (n x p)^T S_R (n x p) + n^T S_t n, which needs ~1/4
+// of the flops of forming var_world.
 #include "vn_kernels.cuh"
 
 #define IEKF_THREADS 1024
 #define IEKF_WARPS (IEKF_THREADS / 32)
-#ifndef IEKF_MIN_BLOCKS
-#define IEKF_MIN_BLOCKS 1
-#endif
+#define IEKF_ROWS 14                        // staged rows per warp: j0..j5, r, 0, Rinv*j0..Rinv*j5
+#define IEKF_LD 36                          // row stride (doubles): 32 points + 4 -> conflict-free fragment loads
+#define IEKF_TILE (IEKF_ROWS * IEKF_LD)     // doubles per warp
+#define IEKF_SMEM (IEKF_WARPS * IEKF_TILE * sizeof(double))
 
-// one reduce-scatter stage: N values per lane -> ceil(N/2); lanes with the `off` bit clear keep the
-// lower half of the index range, the others the upper half
-template <int N, int OFF>
-__device__ __forceinline__ void bfly_stage(const double* in, double* out, bool bit)
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
 {
-  constexpr int H = (N + 1) / 2;
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// where the k-th packed sum (21 HTH upper by rows, 6 HTz, 6 nnt upper, count) sits among the 66 per-warp
+// values: 64 entries of C (row-major 8x8), then n2*n2, then the match count
+__device__ const signed char IEKF_SRC[VN_IEKF_NACC] = { 0,  1,  2,  3,  4,  5,  9,  10, 11, 12, 13, 18,
+                                                        19, 20, 21, 27, 28, 29, 36, 37, 45, 6,  14, 22,
+                                                        30, 38, 46, 51, 52, 53, 60, 61, 64, 65 };
+__device__ __forceinline__ int iekf_src(int k) { return IEKF_SRC[k]; }
+
+// ---------------------------------------------------------------------------
+// a7 on the device: one warp. The reference forms K = (blkdiag(H, 0) + P^-1)^-1 with two 15x15 inversions
+// (odometry.cpp:82, 194) and then only uses K(:, 0:6). With E = [I6 0] the push-through identity gives
+//   K(:, 0:6) = P(:, 0:6) (I6 + H P66)^-1,
+// the same quantity from one well-conditioned 6x6 inversion and without P^-1 (the host variant in
+// host/vina_pipeline.cpp keeps the reference's route; both agree to ~1e-10 relative).
+// Lane j < 6 holds column j of a 6x6 matrix, lanes 6..11 the columns of the identity; Gauss-Jordan
+// elimination with partial (row) pivoting turns the second half into the inverse.
+__device__ __forceinline__ void warp_inverse6(double (&c)[6], int lane)
+{
+  const unsigned int F = 0xffffffffu;
 #pragma unroll
-  for (int i = 0; i < H; i++)
+  for (int k = 0; k < 6; k++)
   {
-    const double lo = in[i];
-    const double hi = (i + H < N) ? in[i + H] : 0.0;
-    const double send = bit ? lo : hi;
-    const double keep = bit ? hi : lo;
-    out[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    int piv = k;
+    double best = fabs(c[k]);
+#pragma unroll
+    for (int i = k + 1; i < 6; i++)
+    {
+      const double a = fabs(c[i]);
+      if (a > best)
+      {
+        best = a;
+        piv = i;
+      }
+    }
+    piv = __shfl_sync(F, piv, k);
+#pragma unroll
+    for (int i = k + 1; i < 6; i++)
+      if (i == piv)
+      {
+        const double t = c[k];
+        c[k] = c[i];
+        c[i] = t;
+      }
+    const double pkk = __shfl_sync(F, c[k], k);
+    const double rk = c[k] / pkk;
+    c[k] = rk;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+      if (i != k)
+      {
+        const double f = __shfl_sync(F, c[i], k);
+        c[i] = fma(-f, rk, c[i]);
+      }
   }
 }
 
-// the 34 per-point contributions, evaluated on demand (k is a compile-time constant after unrolling) so
-// that they never occupy 34 registers at once: 21 x HTH upper triangle (Rinv j_a j_b), 6 x HTz
-// (-Rinv j_a r), 6 x n n^T upper triangle, 1 x match count
-__device__ __forceinline__ double xval(int k, const double* ra, const double* jac, const double* nn, double dotn,
-                                       double cntv)
+// Exp(ang), include/vina_slam/core/math.hpp:12-24
+__device__ void so3_exp(const double* a, double* E)
 {
-  constexpr int HA[21] = { 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5 };
-  constexpr int HB[21] = { 0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5 };
-  constexpr int NA[6] = { 0, 0, 0, 1, 1, 2 }, NB[6] = { 0, 1, 2, 1, 2, 2 };
-  if (k < 21) return ra[HA[k]] * jac[HB[k]];
-  if (k < 27) return -ra[k - 21] * dotn;
-  if (k < 33) return nn[NA[k - 27]] * nn[NB[k - 27]];
-  if (k < 34) return cntv;
-  return 0.0;
+  for (int i = 0; i < 9; i++) E[i] = 0;
+  E[0] = E[4] = E[8] = 1;
+  const double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  if (nrm >= 1e-9)
+  {
+    const double ax[3] = { a[0] / nrm, a[1] / nrm, a[2] / nrm };
+    double K[9], sK[9], KK[9];
+    hat3(ax, K);
+    const double s = sin(nrm), c1 = 1.0 - cos(nrm);
+    for (int i = 0; i < 9; i++) sK[i] = c1 * K[i];
+    mat3_mul(sK, K, KK);
+    for (int i = 0; i < 9; i++) E[i] = (E[i] + s * K[i]) + KK[i];
+  }
+}
+// Log(R), math.hpp:43-48
+__device__ void so3_log(const double* R, double* w)
+{
+  const double tr = (R[0] + R[4]) + R[8];
+  const double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
+  const double K[3] = { R[5] - R[7], R[6] - R[2], R[1] - R[3] };
+  const double f = (fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / sin(theta));
+  for (int i = 0; i < 3; i++) w[i] = f * K[i];
 }
 
-// Warp reduce-scatter of the values [K0, K0 + N) of every lane down to ONE finished sum per lane.
-// Sizes per stage: N -> ceil(N/2) -> ... (5 stages, offsets 16, 8, 4, 2, 1); N <= 32.
-template <int K0, int N>
-__device__ __forceinline__ double bfly_reduce(int lane, const double* ra, const double* jac, const double* nn,
-                                              double dotn, double cntv)
+// The update of one iteration (odometry.cpp:192-230, types.hpp:67-86). fin = the 34 packed sums (shared
+// memory), ws = >= 360 doubles of shared scratch. Executed by ONE warp.
+__device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, double* ws, int lane)
 {
-  constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
-  static_assert((N4 + 1) / 2 == 1, "five halvings must reach one value");
-  double y1[N1], y2[N2], y3[N3], y4[N4], y5[1];
+  double* HTH = ws;        // 6x6 column-major (symmetric)
+  double* HTz = ws + 36;   // 6
+  double* K6 = ws + 48;    // K1(:, 0:6), 15x6 column-major
+  double* G6 = ws + 144;   // G(:, 0:6)
+  double* vec = ws + 240;  // x_prop (-) x_curr
+  double* sol = ws + 256;
+  double* C6 = ws + 272;   // rows 0..5 of the prior covariance, 6x15 (row a, column j at a + 6 j)
+  int* flg = reinterpret_cast<int*>(ws + 368);
+  const int iter = dev->iter, max_iter = dev->max_iter;
+
   {
-    const bool bit = (lane & 16) != 0;
+    int t = 0;
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++, t++)
+        if (lane == 0)
+        {
+          HTH[a + 6 * b] = fin[t];
+          HTH[b + 6 * a] = fin[t];
+        }
+    if (lane < 6) HTz[lane] = fin[21 + lane];
+  }
+  __syncwarp();
+  // T = (I6 + H P66)^-1; K6 = P(:, 0:6) T
+  double c[6];
 #pragma unroll
-    for (int k = 0; k < N1; k++)
+  for (int i = 0; i < 6; i++)
+  {
+    double v = (lane - 6 == i) ? 1.0 : 0.0;
+    if (lane < 6)
     {
-      const double lo = xval(K0 + k, ra, jac, nn, dotn, cntv);
-      const double hi = (k + N1 < N) ? xval(K0 + k + N1, ra, jac, nn, dotn, cntv) : 0.0;
-      y1[k] = (bit ? hi : lo) + __shfl_xor_sync(0xffffffffu, bit ? lo : hi, 16);
+      v = (lane == i) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) v = fma(HTH[i + 6 * k], dev->cov[k + 15 * lane], v);
+    }
+    c[i] = v;
+  }
+  warp_inverse6(c, lane);
+  double* T6 = C6;  // scratch until the final covariance update
+  if (lane >= 6 && lane < 12)
+#pragma unroll
+    for (int i = 0; i < 6; i++) T6[i + 6 * (lane - 6)] = c[i];
+  __syncwarp();
+  for (int e = lane; e < 90; e += 32)
+  {
+    const int i = e % 15, a = e / 15;
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; b++) s = fma(dev->cov[i + 15 * b], T6[b + 6 * a], s);
+    K6[e] = s;
+  }
+  // vec = x_prop (-) x_curr (types.hpp:77-86)
+  if (lane == 0)
+  {
+    double Rt[9], M[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Rt[j + 3 * i] = dev->R[i + 3 * j];
+    mat3_mul(Rt, dev->Rp, M);
+    so3_log(M, vec);
+    for (int k = 0; k < 3; k++)
+    {
+      vec[3 + k] = dev->pp[k] - dev->p[k];
+      vec[6 + k] = dev->vp[k] - dev->v[k];
+      vec[9 + k] = dev->bgp[k] - dev->bg[k];
+      vec[12 + k] = dev->bap[k] - dev->ba[k];
     }
   }
-  bfly_stage<N1, 8>(y1, y2, (lane & 8) != 0);
-  bfly_stage<N2, 4>(y2, y3, (lane & 4) != 0);
-  bfly_stage<N3, 2>(y3, y4, (lane & 2) != 0);
-  bfly_stage<N4, 1>(y4, y5, (lane & 1) != 0);
-  return y5[0];
+  __syncwarp();
+  // G(:, 0:6) = K1(:, 0:6) * HTH
+  for (int e = lane; e < 90; e += 32)
+  {
+    const int i = e % 15, b = e / 15;
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) s = fma(K6[i + 15 * a], HTH[a + 6 * b], s);
+    G6[e] = s;
+  }
+  __syncwarp();
+  // solution = K1(:, 0:6) HTz + vec - G(:, 0:6) vec(0:6)
+  if (lane < 15)
+  {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+    {
+      a = fma(K6[lane + 15 * k], HTz[k], a);
+      b = fma(G6[lane + 15 * k], vec[k], b);
+    }
+    sol[lane] = (a + vec[lane]) - b;
+  }
+  __syncwarp();
+  if (lane == 0)
+  {
+    // x_curr (+)= solution (types.hpp:67-75)
+    double E[9], Rn[9];
+    so3_exp(sol, E);
+    mat3_mul(dev->R, E, Rn);
+    for (int i = 0; i < 9; i++) dev->R[i] = Rn[i];
+    for (int k = 0; k < 3; k++)
+    {
+      dev->p[k] += sol[3 + k];
+      dev->v[k] += sol[6 + k];
+      dev->bg[k] += sol[9 + k];
+      dev->ba[k] += sol[12 + k];
+    }
+    const double nr = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
+    const double nt = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
+    const bool conv = (nr * 57.3 < 0.01) && (nt * 100 < 0.015);
+    int rematch = dev->rematch;
+    if (conv || (rematch == 0 && iter == max_iter - 2)) rematch++;
+    const int fin_it = (rematch >= 2 || iter == max_iter - 1) ? 1 : 0;
+    dev->rematch = rematch;
+    dev->iter = iter + 1;
+    dev->done = fin_it;
+    flg[0] = fin_it;
+  }
+  __syncwarp();
+  if (flg[0])
+  {
+    // cov = (I - G) cov; only the first 6 columns of G are non-zero (odometry.cpp:223)
+    for (int e = lane; e < 90; e += 32) C6[e] = dev->cov[(e % 6) + 15 * (e / 6)];
+    __syncwarp();
+    for (int e = lane; e < 225; e += 32)
+    {
+      const int i = e % 15, j = e / 15;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) s = fma(G6[i + 15 * a], C6[a + 6 * j], s);
+      dev->cov[e] = dev->cov[e] - s;
+    }
+  }
 }
 
-// which value (relative to K0) a lane ends up owning after bfly_reduce<K0, N>; -1 = padding
-template <int N>
-__device__ __forceinline__ int bfly_owner(int lane)
-{
-  constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2, N5 = (N4 + 1) / 2;
-  int k = 0;
-  bool ok = true;
-  k = (lane & 1) ? N5 + k : k;
-  ok = ok && k < N4;
-  k = (lane & 2) ? N4 + k : k;
-  ok = ok && k < N3;
-  k = (lane & 4) ? N3 + k : k;
-  ok = ok && k < N2;
-  k = (lane & 8) ? N2 + k : k;
-  ok = ok && k < N1;
-  k = (lane & 16) ? N1 + k : k;
-  ok = ok && k < N;
-  return ok ? k : -1;
-}
-
+// ---------------------------------------------------------------------------
 template <bool DEBUG>
-__global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
-    k_iekf(ScanView scan, const int* __restrict__ n_ptr, int n_host, int* __restrict__ cache,
-           const HashSlot* __restrict__ slots, unsigned int hmask, const NodeHot* __restrict__ hot,
-           const NodeCold* __restrict__ cold, IekfParams prm, double* __restrict__ partials,
-           unsigned int* __restrict__ ticket, double* __restrict__ result, IekfDebug dbg)
+__global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant__ IekfBatch bt)
 {
-  const int n = n_ptr ? *n_ptr : n_host;
+  const IekfSeq& q = bt.s[blockIdx.y];
+  IekfDev* __restrict__ dev = q.dev;
+  if ((bt.mode & VN_IEKF_SOLVE) && dev->done) return;  // converged in an earlier iteration (uniform over the grid)
+
+  extern __shared__ double smem[];
+  __shared__ double cR[9], cp[3], crv[9], ctv[9];
+  __shared__ double fin[VN_IEKF_NACC];
+  __shared__ bool is_last;
+  if (threadIdx.x < 9)
+  {
+    cR[threadIdx.x] = dev->R[threadIdx.x];
+    crv[threadIdx.x] = dev->rot_var[threadIdx.x];
+    ctv[threadIdx.x] = dev->tsl_var[threadIdx.x];
+  }
+  if (threadIdx.x < 3) cp[threadIdx.x] = dev->p[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double t0 = 0.0, t1 = 0.0;  // the two finished sums this lane owns: one of the 21 HTH terms, one of the 13 others
+  double* Sw = smem + warp * IEKF_TILE;
+  Sw[7 * IEKF_LD + lane] = 0.0;  // b7 = 0, never overwritten
+  __syncthreads();
+
+  const int n = q.n_ptr ? *q.n_ptr : q.n_host;
+  const double* __restrict__ pv = q.pv_base;  // 9 contiguous arrays: p[3], v[6]
+  const size_t pvs = (size_t)q.pv_stride;
+  const NodeHot* __restrict__ hot = q.hot;
+  int* __restrict__ cache = q.cache;
+
+  // DMMA fragment coordinates: this lane holds C[g][2t], C[g][2t+1]; feeds A[g][t] and B[t][g]
+  const int g = lane >> 2, t4 = lane & 3;
+  const double* fa = Sw + (g < 6 ? 8 + g : g - 3) * IEKF_LD + t4;  // a = [Rinv j0..j5, n0 (= j3), n1 (= j4)]
+  const double* fb = Sw + g * IEKF_LD + t4;                        // b = [j0..j5, r, 0]
+  double c0 = 0.0, c1 = 0.0, s22 = 0.0;
+  int cnt = 0;
 
   const int stride = gridDim.x * IEKF_THREADS;
   const int n_round = ((n + stride - 1) / stride) * stride;  // whole warps stay in the loop together
@@ -127,15 +305,16 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
     const bool live = i < n;
     const int ii = live ? i : 0;
     // independent loads first (memory-level parallelism): point, covariance, cached leaf
-    const double pnt[3] = { __ldg(scan.p[0] + ii), __ldg(scan.p[1] + ii), __ldg(scan.p[2] + ii) };
-    const double var6[6] = { __ldg(scan.v[0] + ii), __ldg(scan.v[1] + ii), __ldg(scan.v[2] + ii),
-                             __ldg(scan.v[3] + ii), __ldg(scan.v[4] + ii), __ldg(scan.v[5] + ii) };
+    const double* __restrict__ pi = pv + ii;
+    const double pnt[3] = { __ldg(pi), __ldg(pi + pvs), __ldg(pi + 2 * pvs) };
+    const double var6[6] = { __ldg(pi + 3 * pvs), __ldg(pi + 4 * pvs), __ldg(pi + 5 * pvs),
+                             __ldg(pi + 6 * pvs), __ldg(pi + 7 * pvs), __ldg(pi + 8 * pvs) };
     const int cached = live ? cache[ii] : -1;
     double wld[3];
-    rot_trans(prm.R, prm.p, pnt, wld);
-    if (prm.variant & 16)  // experiment: streaming loads only
+    rot_trans(cR, cp, pnt, wld);
+    if (bt.variant & 16)  // experiment: streaming loads only
     {
-      t0 += wld[0] + wld[1] + wld[2] + var6[0] + var6[1] + var6[2] + var6[3] + var6[4] + var6[5] + (double)cached;
+      s22 += wld[0] + wld[1] + wld[2] + var6[0] + var6[1] + var6[2] + var6[3] + var6[4] + var6[5] + (double)cached;
       continue;
     }
 
@@ -150,24 +329,24 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
     if (DEBUG || (live && node < 0))
     {
 #pragma unroll
-      for (int k = 0; k < 3; k++) kc[k] = voxel_coord(wld[k], prm.voxel_size);
+      for (int k = 0; k < 3; k++) kc[k] = voxel_coord(wld[k], q.voxel_size);
     }
     if (live && node < 0)
     {
       unsigned long long key;
       if (pack_key(kc[0], kc[1], kc[2], &key))
       {
-        unsigned int hh = hash_key(key) & hmask;
-        for (unsigned int probe = 0; probe <= hmask; probe++)
+        unsigned int hh = hash_key(key) & q.hmask;
+        for (unsigned int probe = 0; probe <= q.hmask; probe++)
         {
-          const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2*>(slots + hh));
+          const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2*>(q.slots + hh));
           if (s.x == key)
           {
             node = (int)(unsigned int)(s.y & 0xffffffffull);
             break;
           }
           if (s.x == VN_EMPTY_KEY) break;
-          hh = (hh + 1) & hmask;
+          hh = (hh + 1) & q.hmask;
         }
       }
     }
@@ -182,35 +361,39 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
       node = h->children[child_index(wld, vc)];
     }
 
-    // contributions of this point; all zero unless the gate passes
-    double ra[6] = { 0, 0, 0, 0, 0, 0 }, jac[6] = { 0, 0, 0, 0, 0, 0 }, nn[3] = { 0, 0, 0 };
-    double dotn = 0.0, cntv = 0.0;
+    // contributions of this point (a, b), staged for the warp's DMMA chain; all zero unless the gate passes
+    __syncwarp();  // the previous round's fragment loads are done
     int flag = 0;
     double sigma_l = 0.0;
-    if (node >= 0 && (flags & VN_FLAG_PLANE) && !(prm.variant & 4))
+    if (node >= 0 && (flags & VN_FLAG_PLANE) && !(bt.variant & 4))
     {
-      const NodeHot* h = hot + node;
-      const double c[3] = { h->center[0], h->center[1], h->center[2] };
-      const double nr[3] = { h->normal[0], h->normal[1], h->normal[2] };
+      // line 0 of the leaf record: centre, normal, hoisted plane_var terms - eight 16-byte loads
+      const double2* L = reinterpret_cast<const double2*>(hot + node);
+      const double2 l0 = __ldg(L + 0), l1 = __ldg(L + 1), l2 = __ldg(L + 2);
+      const float radius = hot[node].radius;
+      const double c[3] = { l0.x, l0.y, l1.x };
+      const double nr[3] = { l1.y, l2.x, l2.y };
       const double d[3] = { ds(wld[0], c[0]), ds(wld[1], c[1]), ds(wld[2], c[2]) };
       const double dn = dot3(nr, d);
       const float dis_to_plane = (float)fabs(dn);
       const double e[3] = { ds(c[0], wld[0]), ds(c[1], wld[1]), ds(c[2], wld[2]) };
       const float dis_to_center = (float)dot3(e, e);
       const float range_dis = fs(dis_to_center, fm(dis_to_plane, dis_to_plane));
-      if (range_dis <= fm(9.0f, h->radius))
+      if (range_dis <= fm(9.0f, radius))
       {
         // sigma_l = J plane_var J^T, J = [wld - center, -normal] = d^T A d - 2 d.(B n) + n^T C n (NodeHot)
         {
-          const double A0 = h->qA[0], A1 = h->qA[1], A2 = h->qA[2], A3 = h->qA[3], A4 = h->qA[4], A5 = h->qA[5];
+          // (the rest of the 128-byte line is an L1 hit by now)
+          const double2 l3 = __ldg(L + 3), l4 = __ldg(L + 4), l5 = __ldg(L + 5), l6 = __ldg(L + 6), l7 = __ldg(L + 7);
+          const double A0 = l3.x, A1 = l3.y, A2 = l4.x, A3 = l4.y, A4 = l5.x, A5 = l5.y;
           const double dAd = d[0] * (A0 * d[0] + 2.0 * (A1 * d[1] + A2 * d[2])) + d[1] * (A3 * d[1] + 2.0 * A4 * d[2]) +
                              d[2] * A5 * d[2];
-          sigma_l = dAd - 2.0 * (d[0] * h->qb[0] + d[1] * h->qb[1] + d[2] * h->qb[2]) + h->qk;
+          sigma_l = dAd - 2.0 * (d[0] * l6.x + d[1] * l6.y + d[2] * l7.x) + l7.y;
         }
         // + n^T var_world n
         double m[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) m[k] = prm.R[3 * k] * nr[0] + prm.R[3 * k + 1] * nr[1] + prm.R[3 * k + 2] * nr[2];
+        for (int k = 0; k < 3; k++) m[k] = cR[3 * k] * nr[0] + cR[3 * k + 1] * nr[1] + cR[3 * k + 2] * nr[2];
         const double q1 = m[0] * (var6[0] * m[0] + 2.0 * (var6[1] * m[1] + var6[2] * m[2])) +
                           m[1] * (var6[3] * m[1] + 2.0 * var6[4] * m[2]) + m[2] * var6[5] * m[2];
         const double u[3] = { nr[1] * pnt[2] - nr[2] * pnt[1], nr[2] * pnt[0] - nr[0] * pnt[2],
@@ -219,8 +402,8 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
 #pragma unroll
         for (int a = 0; a < 3; a++)
         {
-          q2 += u[a] * (prm.rot_var[a] * u[0] + prm.rot_var[a + 3] * u[1] + prm.rot_var[a + 6] * u[2]);
-          q3 += nr[a] * (prm.tsl_var[a] * nr[0] + prm.tsl_var[a + 3] * nr[1] + prm.tsl_var[a + 6] * nr[2]);
+          q2 += u[a] * (crv[a] * u[0] + crv[a + 3] * u[1] + crv[a + 6] * u[2]);
+          q3 += nr[a] * (ctv[a] * nr[0] + ctv[a + 3] * nr[1] + ctv[a + 6] * nr[2]);
         }
         sigma_l += q1 + q2 + q3;
         // dis_to_plane < 3 sqrt(sigma_l)  <=>  dis_to_plane^2 < 9 sigma_l (the fp32 value squares exactly in fp64)
@@ -230,77 +413,99 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
           cache[ii] = node;  // oc = this (octree.cpp:571-575)
           const double Rinv = 1.0 / (0.0005 + sigma_l);
           // jac = [hat(p) R^T n ; n] = [p x m ; n]
-          jac[0] = pnt[1] * m[2] - pnt[2] * m[1];
-          jac[1] = pnt[2] * m[0] - pnt[0] * m[2];
-          jac[2] = pnt[0] * m[1] - pnt[1] * m[0];
-          jac[3] = nr[0];
-          jac[4] = nr[1];
-          jac[5] = nr[2];
-#pragma unroll
-          for (int a = 0; a < 6; a++) ra[a] = Rinv * jac[a];
-          nn[0] = nr[0];
-          nn[1] = nr[1];
-          nn[2] = nr[2];
-          dotn = dn;
-          cntv = 1.0;
+          const double j0 = pnt[1] * m[2] - pnt[2] * m[1];
+          const double j1 = pnt[2] * m[0] - pnt[0] * m[2];
+          const double j2 = pnt[0] * m[1] - pnt[1] * m[0];
+          Sw[0 * IEKF_LD + lane] = j0;
+          Sw[1 * IEKF_LD + lane] = j1;
+          Sw[2 * IEKF_LD + lane] = j2;
+          Sw[3 * IEKF_LD + lane] = nr[0];
+          Sw[4 * IEKF_LD + lane] = nr[1];
+          Sw[5 * IEKF_LD + lane] = nr[2];
+          Sw[6 * IEKF_LD + lane] = dn;
+          Sw[8 * IEKF_LD + lane] = Rinv * j0;
+          Sw[9 * IEKF_LD + lane] = Rinv * j1;
+          Sw[10 * IEKF_LD + lane] = Rinv * j2;
+          Sw[11 * IEKF_LD + lane] = Rinv * nr[0];
+          Sw[12 * IEKF_LD + lane] = Rinv * nr[1];
+          Sw[13 * IEKF_LD + lane] = Rinv * nr[2];
+          s22 = fma(nr[2], nr[2], s22);
+          cnt++;
         }
       }
     }
     if (DEBUG && live)
     {
-      dbg.keys[3 * (size_t)i + 0] = kc[0];
-      dbg.keys[3 * (size_t)i + 1] = kc[1];
-      dbg.keys[3 * (size_t)i + 2] = kc[2];
-      dbg.flags[i] = (unsigned char)flag;
-      dbg.codes[i] = flag ? (hot[node].layer | (cold[node].path << 2)) : -1;
-      dbg.sigma[i] = flag ? sigma_l : 0.0;
+      q.dbg.keys[3 * (size_t)i + 0] = kc[0];
+      q.dbg.keys[3 * (size_t)i + 1] = kc[1];
+      q.dbg.keys[3 * (size_t)i + 2] = kc[2];
+      q.dbg.flags[i] = (unsigned char)flag;
+      q.dbg.codes[i] = flag ? (hot[node].layer | (q.cold[node].path << 2)) : -1;
+      q.dbg.sigma[i] = flag ? sigma_l : 0.0;
     }
-    // warp reduce-scatter: the 21 HTH terms (21 -> 11 -> 6 -> 3 -> 2 -> 1) and the 13 others (13 -> 7 -> 4 -> 2 -> 1 -> 1)
-    if (!(prm.variant & 8))
+    if (!flag)
     {
-      t0 += bfly_reduce<0, 21>(lane, ra, jac, nn, dotn, cntv);
-      t1 += bfly_reduce<21, 13>(lane, ra, jac, nn, dotn, cntv);
+#pragma unroll
+      for (int a = 0; a < 7; a++) Sw[a * IEKF_LD + lane] = 0.0;
+#pragma unroll
+      for (int a = 8; a < 14; a++) Sw[a * IEKF_LD + lane] = 0.0;
     }
-    else
-      t0 += ra[0] + dotn + cntv + nn[0] + jac[1];
+    if (bt.variant & 8) continue;
+    // let the FP64 tensor pipe sum the warp's 32 rank-1 updates
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 8; s++) dmma_8x8x4(c0, c1, fa[4 * s], fb[4 * s]);
   }
 
-  // block reduction across the warps in fixed order
-  __shared__ double sm[IEKF_WARPS][VN_IEKF_NACC];
-  __shared__ bool is_last;
-  const int k0 = bfly_owner<21>(lane), k1 = bfly_owner<13>(lane);
-  if (k0 >= 0) sm[warp][k0] = t0;
-  if (k1 >= 0) sm[warp][21 + k1] = t1;
+  // ---- block reduction across the warps in fixed order ------------------------------------------------
+  // per warp: 64 entries of C, then n2*n2 and the count (shuffle tree over the lanes)
+  double s22w = s22;
+  int cntw = cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    s22w += __shfl_xor_sync(0xffffffffu, s22w, o);
+    cntw += __shfl_xor_sync(0xffffffffu, cntw, o);
+  }
+  __syncwarp();
+  Sw[g * 8 + 2 * t4] = c0;
+  Sw[g * 8 + 2 * t4 + 1] = c1;
+  if (lane == 0)
+  {
+    Sw[64] = s22w;
+    Sw[65] = (double)cntw;
+  }
   __syncthreads();
   const unsigned int nblk = gridDim.x;
   if (threadIdx.x < VN_IEKF_NACC)
   {
+    const int src = iekf_src(threadIdx.x);
     double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < IEKF_WARPS; w++) v += sm[w][threadIdx.x];
-    partials[(size_t)threadIdx.x * nblk + blockIdx.x] = v;  // [34][nblk]: the final pass reads it coalesced
+#pragma unroll 8
+    for (int w = 0; w < IEKF_WARPS; w++) v += smem[w * IEKF_TILE + src];
+    if (threadIdx.x >= 21 && threadIdx.x < 27) v = -v;  // HTz -= Rinv j r
+    q.partials[(size_t)threadIdx.x * nblk + blockIdx.x] = v;  // [34][nblk]: the final pass reads it coalesced
     __threadfence();
   }
   __syncthreads();
   if (threadIdx.x == 0)
   {
-    unsigned int t = atomicAdd(ticket, 1u);
+    unsigned int t = atomicAdd(q.ticket, 1u);
     is_last = (t == nblk - 1);
   }
   __syncthreads();
   if (!is_last) return;
-  if (prm.variant & 1)
+  if (bt.variant & 1)
   {
-    if (threadIdx.x == 0) *ticket = 0u;
+    if (threadIdx.x == 0) *q.ticket = 0u;
     return;
   }
-  // last block: one warp per column (34 columns over 32 warps), lanes stride over the <= 148 x IEKF_MIN_BLOCKS
-  // per-block partials with independent loads, then a fixed shuffle tree -> deterministic
+  // last block: one warp per column (34 columns over 32 warps), lanes stride over the per-block partials with
+  // independent loads, then a fixed shuffle tree -> deterministic
   __threadfence();
-  __shared__ double fin[VN_IEKF_NACC];
   for (int k = warp; k < VN_IEKF_NACC; k += IEKF_WARPS)
   {
-    const double* col = partials + (size_t)k * nblk;
+    const double* col = q.partials + (size_t)k * nblk;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0;
     const unsigned int b = lane;
     if (b < nblk) v0 = __ldcg(col + b);
@@ -314,19 +519,23 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_MIN_BLOCKS)
     if (lane == 0) fin[k] = v;
   }
   __syncthreads();
-  // the sums go straight to mapped pinned host memory; the sequence number is written last so that the
-  // host can poll for completion instead of paying a stream synchronisation per IEKF iteration
-  double* out = (prm.variant & 2) ? partials : result;
-  if (threadIdx.x < VN_IEKF_NACC)
+  if (threadIdx.x < VN_IEKF_NACC) dev->sums[threadIdx.x] = fin[threadIdx.x];
+  if (threadIdx.x == 0) *q.ticket = 0u;
+  if (bt.mode & VN_IEKF_SOLVE)
   {
-    out[threadIdx.x] = fin[threadIdx.x];
-    __threadfence_system();
+    if (warp == 0) iekf_solve_warp(dev, fin, smem, lane);
   }
-  __syncthreads();
-  if (threadIdx.x == 0)
+  if (bt.mode & VN_IEKF_PUBLISH)
   {
-    *ticket = 0u;
-    reinterpret_cast<volatile unsigned long long*>(out)[40] = prm.seq;
+    // the sums go straight to mapped pinned host memory; the sequence number is written last so that the
+    // host can poll for completion instead of paying a stream synchronisation per IEKF iteration
+    if (threadIdx.x < VN_IEKF_NACC)
+    {
+      q.result[threadIdx.x] = fin[threadIdx.x];
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) reinterpret_cast<volatile unsigned long long*>(q.result)[40] = q.seq;
   }
 }
 
@@ -338,27 +547,33 @@ __global__ void k_fill_int(int* p, int v, int n)
 
 int iekf_grid_blocks(int n, int sm_count)
 {
-  // one point per thread: every point of the scan is in flight at once (a B200 holds 148 x 4 x 256
-  // = 151 552 threads of this kernel per wave; larger scans take a second wave)
+  // one point per thread and round, one 1024-thread block per SM (the staging tiles take 126 KB of shared
+  // memory); larger scans loop
   int need = (n + IEKF_THREADS - 1) / IEKF_THREADS;
-  int cap = sm_count * IEKF_MIN_BLOCKS;  // one resident wave; larger scans loop
   if (need < 1) need = 1;
-  return need < cap ? need : cap;
+  return need < sm_count ? need : sm_count;
 }
 
-void launch_iekf(cudaStream_t st, const ScanView& scan, const int* n_dev, int n_host, int* cache, const MapView& map,
-                 const IekfParams& prm, double* partials, unsigned int* ticket, double* result, int blocks,
-                 const IekfDebug* dbg)
+int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug)
 {
-  if (dbg)
-    k_iekf<true><<<blocks, IEKF_THREADS, 0, st>>>(scan, n_dev, n_host, cache, map.slots, map.hmask, map.hot, map.cold,
-                                                   prm, partials, ticket, result, *dbg);
-  else
+  static bool attr_set_dev[64] = { false };
+  int dv = 0;
+  cudaGetDevice(&dv);
+  bool& attr_set = attr_set_dev[dv & 63];
+  if (!attr_set)
   {
-    IekfDebug none = { nullptr, nullptr, nullptr, nullptr };
-    k_iekf<false><<<blocks, IEKF_THREADS, 0, st>>>(scan, n_dev, n_host, cache, map.slots, map.hmask, map.hot, map.cold,
-                                                    prm, partials, ticket, result, none);
+    cudaError_t e = cudaFuncSetAttribute(k_iekf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IEKF_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_iekf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IEKF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
   }
+  dim3 grid(blocks, nseq);
+  if (debug)
+    k_iekf<true><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);
+  else
+    k_iekf<false><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);
+  return (int)cudaGetLastError();
 }
 
 void launch_fill_int(cudaStream_t st, int* p, int v, int n)

@@ -132,8 +132,11 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(cudaHostAlloc((void**)&ctx->h_n_down, sizeof(int), cudaHostAllocDefault));
   for (int w = 0; w < 2; w++)
   {
-    for (int k = 0; k < 3; k++) CU(dalloc(&ctx->pv[w].p[k], cap));
-    for (int k = 0; k < 6; k++) CU(dalloc(&ctx->pv[w].v[k], cap));
+    // one allocation per pointVar set: 9 contiguous arrays (k_iekf addresses them as base + k * cap)
+    double* base = nullptr;
+    CU(dalloc(&base, (size_t)9 * cap));
+    for (int k = 0; k < 3; k++) ctx->pv[w].p[k] = base + (size_t)k * cap;
+    for (int k = 0; k < 6; k++) ctx->pv[w].v[k] = base + (size_t)(3 + k) * cap;
   }
   CU(dalloc(&ctx->d_cache, cap));
   CU(dalloc(&ctx->d_poses, 1));
@@ -154,6 +157,9 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(cudaHostAlloc((void**)&ctx->h_result, 64 * sizeof(double), cudaHostAllocMapped));
   CU(cudaHostGetDevicePointer((void**)&ctx->d_result, ctx->h_result, 0));
   memset(ctx->h_result, 0, 64 * sizeof(double));
+  CU(dalloc(&ctx->d_iekf, 1));
+  CU(cudaHostAlloc((void**)&ctx->h_iekf, sizeof(IekfDev), cudaHostAllocDefault));
+  memset(ctx->h_iekf, 0, sizeof(IekfDev));
   CU(dalloc(&ctx->d_status, 1));
   CU(cudaHostAlloc((void**)&ctx->h_status, sizeof(int), cudaHostAllocDefault));
 
@@ -224,11 +230,7 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(ctx->d_down);
   cudaFree(ctx->d_n_down);
   cudaFreeHost(ctx->h_n_down);
-  for (int w = 0; w < 2; w++)
-  {
-    for (int k = 0; k < 3; k++) cudaFree(ctx->pv[w].p[k]);
-    for (int k = 0; k < 6; k++) cudaFree(ctx->pv[w].v[k]);
-  }
+  for (int w = 0; w < 2; w++) cudaFree(ctx->pv[w].p[0]);
   cudaFree(ctx->d_cache);
   cudaFree(ctx->d_poses);
   cudaFreeHost(ctx->h_poses);
@@ -240,6 +242,8 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_ticket);
   cudaFreeHost(ctx->h_result);
+  cudaFree(ctx->d_iekf);
+  cudaFreeHost(ctx->h_iekf);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   cudaFree(ctx->dbg.keys);
@@ -275,6 +279,7 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(ctx->layers.count);
   for (int i = 0; i < 16; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->iekf_ev) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -493,6 +498,10 @@ extern "C" int vina_iekf_begin(vina_ctx* ctx, int which, const double rot_var[9]
   memcpy(ctx->tsl_var, tsl_var, 72);
   ctx->iekf_which = which;
   const int n = ctx->n_pv[which];
+  // the prior blocks of this call live in the device iterate (odometry.cpp:105-106)
+  CU(cudaMemcpyAsync(ctx->d_iekf->rot_var, ctx->rot_var, 72, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_iekf->tsl_var, ctx->tsl_var, 72, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(&ctx->d_iekf->iter, 0, 4 * sizeof(int), ctx->stream));
   launch_fill_int(ctx->stream, ctx->d_cache, -1, n);  // vector<OctoTree*> octos(psize, nullptr), odometry.cpp:79
   ctx->iekf_blocks = iekf_grid_blocks(n, ctx->sm_count);
   ctx->launches += 1;
@@ -510,25 +519,46 @@ static int ensure_debug(vina_ctx* ctx)
   return VINA_OK;
 }
 
+void vn_iekf_fill_seq(vina_ctx* ctx, IekfSeq* q, bool debug)
+{
+  const int w = ctx->iekf_which;
+  q->pv_base = ctx->pv[w].p[0];
+  q->pv_stride = ctx->cap_points;
+  q->n_ptr = nullptr;
+  q->n_host = ctx->n_pv[w];
+  q->hmask = ctx->map.hmask;
+  q->cache = ctx->d_cache;
+  q->slots = ctx->map.slots;
+  q->hot = ctx->map.hot;
+  q->cold = ctx->map.cold;
+  q->dev = ctx->d_iekf;
+  q->partials = ctx->d_partials;
+  q->ticket = ctx->d_ticket;
+  q->result = ctx->d_result;
+  q->voxel_size = ctx->cfg.voxel_size;
+  q->seq = ctx->iekf_seq;
+  IekfDebug none = { nullptr, nullptr, nullptr, nullptr };
+  q->dbg = debug ? ctx->dbg : none;
+}
+
+// low-level accumulate: the caller's (R, p) go into the device iterate, the sums come back through mapped memory
 int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool debug)
 {
   if (ctx->iekf_which < 0) return vn_fail(ctx, VINA_E_STATE, "vina_iekf_accumulate before vina_iekf_begin");
-  IekfParams prm;
-  memcpy(prm.R, R, 72);
-  memcpy(prm.p, p, 24);
-  memcpy(prm.rot_var, ctx->rot_var, 72);
-  memcpy(prm.tsl_var, ctx->tsl_var, 72);
-  prm.voxel_size = ctx->cfg.voxel_size;
-  prm.variant = ctx->iekf_variant;
-  prm.seq = ++ctx->iekf_seq;
-  const int w = ctx->iekf_which;
   if (debug)
   {
     int r = ensure_debug(ctx);
     if (r) return r;
   }
-  launch_iekf(ctx->stream, ctx->pv[w], nullptr, ctx->n_pv[w], ctx->d_cache, ctx->map, prm, ctx->d_partials,
-              ctx->d_ticket, ctx->d_result, ctx->iekf_blocks, debug ? &ctx->dbg : nullptr);
+  CU(cudaMemcpyAsync(ctx->d_iekf->R, R, 72, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_iekf->p, p, 24, cudaMemcpyHostToDevice, ctx->stream));
+  ++ctx->iekf_seq;
+  IekfBatch bt;
+  bt.mode = VN_IEKF_PUBLISH;
+  bt.variant = ctx->iekf_variant;
+  vn_iekf_fill_seq(ctx, &bt.s[0], debug);
+  int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, debug);
+  if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
   ctx->dbg_valid = debug;
   ctx->launches += 1;
   return VINA_OK;
@@ -720,20 +750,21 @@ extern "C" int vina_iekf_time_kernel(vina_ctx* ctx, const double R[9], const dou
                                      int reset_cache, float* ms_per_launch)
 {
   if (!ctx || !R || !p || reps < 1 || !ms_per_launch) return VINA_E_ARG;
-  ctx->iekf_variant = variant;
+  if (ctx->iekf_which < 0) return vn_fail(ctx, VINA_E_STATE, "vina_iekf_time_kernel before vina_iekf_begin");
+  CU(cudaMemcpyAsync(ctx->d_iekf->R, R, 72, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_iekf->p, p, 24, cudaMemcpyHostToDevice, ctx->stream));
+  IekfBatch bt;
+  bt.mode = 0;  // sums stay in the device iterate
+  bt.variant = variant;
+  vn_iekf_fill_seq(ctx, &bt.s[0], false);
   cudaEventRecord(ctx->ev[10], ctx->stream);
   for (int r = 0; r < reps; r++)
   {
     if (reset_cache) launch_fill_int(ctx->stream, ctx->d_cache, -1, ctx->n_pv[ctx->iekf_which]);
-    int rc = vn_iekf_launch(ctx, R, p, false);
-    if (rc)
-    {
-      ctx->iekf_variant = 0;
-      return rc;
-    }
+    int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
+    if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
   }
   cudaEventRecord(ctx->ev[11], ctx->stream);
-  ctx->iekf_variant = 0;
   CU(cudaEventSynchronize(ctx->ev[11]));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]);

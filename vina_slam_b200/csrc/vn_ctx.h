@@ -45,6 +45,8 @@ struct vina_ctx
   unsigned int* d_ticket = nullptr;
   double* h_result = nullptr;  // pinned + mapped; the kernel's last block writes it
   double* d_result = nullptr;  // device alias of h_result
+  IekfDev* d_iekf = nullptr;   // device-resident iterate (state, covariance, flags)
+  IekfDev* h_iekf = nullptr;   // pinned staging / readback copy
   IekfDebug dbg = { nullptr, nullptr, nullptr, nullptr };
   bool dbg_valid = false;
   // map
@@ -59,6 +61,7 @@ struct vina_ctx
   // profiling
   bool profiling = false;
   cudaEvent_t ev[16];
+  std::vector<cudaEvent_t> iekf_ev;  // per-iteration (begin, end) pairs of the device IEKF loop
   vina_timings tm;
   int launches = 0;
 
@@ -71,4 +74,6 @@ int vn_check_cuda(vina_ctx* c, cudaError_t e, const char* what);
 int vn_check_status(vina_ctx* c);
 // wait for the sums of the last k_iekf launch (polls the sequence number in mapped memory)
 int vn_iekf_wait(vina_ctx* c);
+// fill the launch descriptor of this context's sequence (R/p come from c->d_iekf)
+void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 void odom_host_destroy(OdomHost* o);

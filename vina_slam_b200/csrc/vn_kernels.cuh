@@ -19,17 +19,8 @@ struct DownSlot
   int first;
 };
 
-// per-iteration constants of the IEKF accumulate kernel
-struct IekfParams
-{
-  double R[9], p[3];       // x_curr.R / x_curr.p of this iteration
-  double rot_var[9], tsl_var[9];  // prior covariance blocks (odometry.cpp:105-106)
-  double voxel_size;
-  int variant;  // experiment switches (0 = product path), see vina_iekf_time_kernel
-  unsigned long long seq;  // launch sequence number, written after the sums so that the host can poll for them
-};
-
 #define VN_IEKF_NACC 34  // 21 (HTH upper) + 6 (HTz) + 6 (nnt upper) + 1 (count)
+#define VN_MAX_BATCH 16  // sequences per batched k_iekf launch
 
 struct IekfDebug
 {
@@ -37,6 +28,50 @@ struct IekfDebug
   int* codes;
   unsigned char* flags;
   double* sigma;
+};
+
+// Device-resident iterate of VINA_SLAM::LioStateEstimation (odometry.cpp:64-255): the state the IEKF loop
+// reads and updates without going back to the host. k_iekf takes R/p and the prior covariance blocks from here;
+// with VN_IEKF_SOLVE its last block also performs the a7 update (15x15 solve, boxplus, convergence logic).
+struct IekfDev
+{
+  double R[9], p[3], v[3], bg[3], ba[3];       // x_curr (column-major R)
+  double Rp[9], pp[3], vp[3], bgp[3], bap[3];  // x_prop
+  double cov[225];                             // prior covariance; posterior once `done`
+  double rot_var[9], tsl_var[9];               // prior blocks, fixed over the iterations (odometry.cpp:105-106)
+  double sums[40];                             // packed sums of the last iteration (nnt = [27..32], count = [33])
+  int iter, rematch, done, max_iter;
+};
+
+#define VN_IEKF_PUBLISH 1  // write the 34 sums + sequence number to mapped host memory (low-level ABI, tests)
+#define VN_IEKF_SOLVE 2    // last block runs the IEKF update on the device state
+
+// one sequence of a (batched) k_iekf launch
+struct IekfSeq
+{
+  const double* pv_base;  // pointVar SoA: 9 contiguous arrays p[3], v[6] of pv_stride doubles each
+  long long pv_stride;
+  const int* n_ptr;  // device-side point count (or null -> n_host)
+  int n_host;
+  unsigned int hmask;
+  int* cache;
+  const HashSlot* slots;
+  const NodeHot* hot;
+  const NodeCold* cold;
+  IekfDev* dev;
+  double* partials;      // [34][gridDim.x]
+  unsigned int* ticket;
+  double* result;        // mapped pinned host memory (VN_IEKF_PUBLISH)
+  double voxel_size;
+  unsigned long long seq;  // launch sequence number, written after the sums so that the host can poll for them
+  IekfDebug dbg;
+};
+
+struct IekfBatch
+{
+  int mode;     // VN_IEKF_*
+  int variant;  // experiment switches (0 = product path), see vina_iekf_time_kernel
+  IekfSeq s[VN_MAX_BATCH];
 };
 
 // scan_kernels.cu
@@ -49,9 +84,8 @@ int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_si
 
 // iekf_kernel.cu
 int iekf_grid_blocks(int n, int sm_count);
-void launch_iekf(cudaStream_t st, const ScanView& scan, const int* n_dev, int n_host, int* cache, const MapView& map,
-                 const IekfParams& prm, double* partials, unsigned int* ticket, double* result, int blocks,
-                 const IekfDebug* dbg);
+// grid = (blocks, nseq); every sequence gets `blocks` persistent 1024-thread blocks
+int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug);
 void launch_fill_int(cudaStream_t st, int* p, int v, int n);
 
 // map_kernels.cu

@@ -14,6 +14,7 @@
 
 int vn_finish_downsample(vina_ctx* ctx);
 int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool debug);
+extern "C" int vina_odom_iekf_host(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate);
 void vn_iekf_unpack(const double* r, double HTH[36], double HTz[6], double nnt[9], int32_t* match_num);
 
 namespace
@@ -258,9 +259,10 @@ static void state_boxminus(const vina_state& a, const vina_state& b, double* out
   }
 }
 
-// VINA_SLAM::LioStateEstimation (odometry.cpp:64-255), use_vnc == false terms;
-// the per-point loop of each iteration runs on the GPU (vina_iekf_accumulate).
-static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_iter_override, int* not_degenerate)
+// VINA_SLAM::LioStateEstimation (odometry.cpp:64-255), use_vnc == false terms - host variant: the per-point
+// loop of each iteration runs on the GPU (k_iekf publishing its 34 sums to mapped memory), the 15x15 update
+// (a7) here. Kept for vina_odom_iekf(..., host_solve) / cross-checks; the per-scan path uses the device loop.
+static int lio_state_estimation_host(vina_ctx* ctx, OdomHost* o, int which, int max_iter_override, int* not_degenerate)
 {
   vina_state& x_curr = o->x_curr;
   const vina_state x_prop = x_curr;
@@ -281,26 +283,15 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
   int r = vina_iekf_begin(ctx, which, rot_var, tsl_var);
   if (r) return r;
   o->last_iters = 0;
-  cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9];
-  float kernel_ms = 0;
 
   for (int iterCount = 0; iterCount < num_max_iter; iterCount++)
   {
     double HTH[36], HTz[6];
     int32_t match_num = 0;
-    if (ctx->profiling) cudaEventRecord(e0, ctx->stream);
     r = vn_iekf_launch(ctx, x_curr.R, x_curr.p, false);
     if (r) return r;
-    if (ctx->profiling) cudaEventRecord(e1, ctx->stream);
     r = vn_iekf_wait(ctx);
     if (r) return r;
-    if (ctx->profiling)
-    {
-      float ms = 0;
-      cudaEventSynchronize(e1);
-      cudaEventElapsedTime(&ms, e0, e1);
-      kernel_ms += ms;
-    }
     vn_iekf_unpack(ctx->h_result, HTH, HTz, nnt, &match_num);
     o->last_iters = iterCount + 1;
 
@@ -332,12 +323,114 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
       break;
     }
   }
-  ctx->tm.iekf_kernel_ms = kernel_ms;
+  ctx->tm.iekf_kernel_ms = 0;
   ctx->tm.iekf_iters = o->last_iters;
   // degeneracy test on the last iteration's nnt (odometry.cpp:244-254)
   double L[6] = { nnt[0], nnt[1], nnt[2], nnt[4], nnt[5], nnt[8] }, ev[3], Q[9];
   eig3_sym(L, ev, Q);
   *not_degenerate = !(ev[0] < 14);
+  return VINA_OK;
+}
+
+// stage x_curr as the device iterate (x_prop = x_curr, prior covariance and its blocks, loop counters)
+static void stage_iterate(const vina_state& x, int max_iter, IekfDev* h)
+{
+  memcpy(h->R, x.R, 72);
+  memcpy(h->p, x.p, 24);
+  memcpy(h->v, x.v, 24);
+  memcpy(h->bg, x.bg, 24);
+  memcpy(h->ba, x.ba, 24);
+  memcpy(h->Rp, x.R, 72);
+  memcpy(h->pp, x.p, 24);
+  memcpy(h->vp, x.v, 24);
+  memcpy(h->bgp, x.bg, 24);
+  memcpy(h->bap, x.ba, 24);
+  memcpy(h->cov, x.cov, sizeof(x.cov));
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++)
+    {
+      h->rot_var[i + 3 * j] = x.cov[i + 15 * j];
+      h->tsl_var[i + 3 * j] = x.cov[(3 + i) + 15 * (3 + j)];
+    }
+  h->iter = 0;
+  h->rematch = 0;
+  h->done = 0;
+  h->max_iter = max_iter;
+}
+
+// take the converged iterate back (after the stream has been synchronised)
+static void unstage_iterate(const IekfDev* h, vina_state& x, int* iters, int* not_degenerate)
+{
+  memcpy(x.R, h->R, 72);
+  memcpy(x.p, h->p, 24);
+  memcpy(x.v, h->v, 24);
+  memcpy(x.bg, h->bg, 24);
+  memcpy(x.ba, h->ba, 24);
+  memcpy(x.cov, h->cov, sizeof(x.cov));
+  *iters = h->iter;
+  // degeneracy test on the last iteration's nnt (odometry.cpp:244-254)
+  const double* s = h->sums + 27;
+  double L[6] = { s[0], s[1], s[2], s[3], s[4], s[5] }, ev[3], Q[9];
+  eig3_sym(L, ev, Q);
+  *not_degenerate = !(ev[0] < 14);
+}
+
+// enqueue the whole iteration loop on the ctx stream: upload of the iterate, cache reset, max_iter x k_iekf
+// (each launch accumulates, and its last block solves and updates the device iterate; launches after
+// convergence return at once), download of the result. No host synchronisation inside.
+static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
+{
+  stage_iterate(o->x_curr, num_max_iter, ctx->h_iekf);
+  int r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->d_iekf, ctx->h_iekf, sizeof(IekfDev), cudaMemcpyHostToDevice, ctx->stream),
+                        "iterate upload");
+  if (r) return r;
+  ctx->iekf_which = which;
+  const int n = ctx->n_pv[which];
+  launch_fill_int(ctx->stream, ctx->d_cache, -1, n);  // vector<OctoTree*> octos(psize, nullptr), odometry.cpp:79
+  ctx->iekf_blocks = iekf_grid_blocks(n, ctx->sm_count);
+  ctx->launches += 1;
+  IekfBatch bt;
+  bt.mode = VN_IEKF_SOLVE;
+  bt.variant = 0;
+  vn_iekf_fill_seq(ctx, &bt.s[0], false);
+  if (ctx->profiling && (int)ctx->iekf_ev.size() < 2 * num_max_iter)
+  {
+    size_t old = ctx->iekf_ev.size();
+    ctx->iekf_ev.resize(2 * (size_t)num_max_iter);
+    for (size_t i = old; i < ctx->iekf_ev.size(); i++) cudaEventCreate(&ctx->iekf_ev[i]);
+  }
+  for (int it = 0; it < num_max_iter; it++)
+  {
+    if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it], ctx->stream);
+    int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
+    if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
+    if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it + 1], ctx->stream);
+  }
+  ctx->dbg_valid = false;
+  return vn_check_cuda(ctx, cudaMemcpyAsync(ctx->h_iekf, ctx->d_iekf, sizeof(IekfDev), cudaMemcpyDeviceToHost, ctx->stream),
+                       "iterate download");
+}
+
+// VINA_SLAM::LioStateEstimation (odometry.cpp:64-255) with the whole iteration loop on the device: one
+// host synchronisation per call, after the last iteration.
+static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_iter_override, int* not_degenerate)
+{
+  const int num_max_iter = max_iter_override > 0 ? max_iter_override : 20;
+  int r = iekf_enqueue_device(ctx, o, which, num_max_iter);
+  if (r) return r;
+  r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "IEKF loop");
+  if (r) return r;
+  unstage_iterate(ctx->h_iekf, o->x_curr, &o->last_iters, not_degenerate);
+  ctx->tm.iekf_iters = o->last_iters;
+  float kernel_ms = 0;
+  if (ctx->profiling)
+    for (int it = 0; it < o->last_iters; it++)
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->iekf_ev[2 * it], ctx->iekf_ev[2 * it + 1]);
+      kernel_ms += ms;
+    }
+  ctx->tm.iekf_kernel_ms = kernel_ms;
   return VINA_OK;
 }
 
@@ -538,6 +631,18 @@ int vina_odom_iekf(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* 
   OdomHost* o = odom(ctx);
   int ok = 0;
   int r = lio_state_estimation(ctx, o, which, max_iter, &ok);
+  if (r) return r;
+  if (iters_out) *iters_out = o->last_iters;
+  if (not_degenerate) *not_degenerate = ok;
+  return VINA_OK;
+}
+
+int vina_odom_iekf_host(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate)
+{
+  if (!ctx || which < 0 || which > 1) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  int ok = 0;
+  int r = lio_state_estimation_host(ctx, o, which, max_iter, &ok);
   if (r) return r;
   if (iters_out) *iters_out = o->last_iters;
   if (not_degenerate) *not_degenerate = ok;

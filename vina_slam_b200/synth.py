@@ -341,3 +341,14 @@ class Sequence:
 def rot_err_deg(Ra: np.ndarray, Rb: np.ndarray) -> float:
     c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
     return math.degrees(math.acos(max(-1.0, min(1.0, c))))
+
+
+def rot_exp(w: np.ndarray) -> np.ndarray:
+    """Rodrigues: rotation matrix of the rotation vector w."""
+    w = np.asarray(w, dtype=np.float64)
+    th = float(np.linalg.norm(w))
+    if th < 1e-12:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * (K @ K)
