@@ -36,6 +36,8 @@ extern "C" {
 
 #define VINA_MAX_WIN 10   /* LocalBA.win_size of every reference yaml */
 #define VINA_MAX_POSES 96 /* IMU poses per scan (reference: ~20 @200 Hz, ~40 @400 Hz) */
+#define VINA_MAX_WORLD 16 /* ranks a hash-range-sharded map can span */
+#define VINA_SHARD_RECORD_DOUBLES 13 /* one routed point: body p[3], world var (upper) [6], world p[3], int64 scan index */
 
 typedef struct vina_ctx vina_ctx;
 
@@ -181,6 +183,30 @@ int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_buf);
 int vina_map_shift_window(vina_ctx* ctx);
 int64_t vina_map_count(vina_ctx* ctx, int64_t* n_roots, int64_t* n_slide);
 int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t cap);
+
+/* ---- map sharded by voxel-hash range over `world` ranks (one ctx per rank / GPU). A root voxel - and every
+ * leaf below it - lives on rank owner(key) = floor(hash(key) * world / 2^32): cut_voxel_multi only ever
+ * combines points of the same root voxel (voxel_map.cpp:86, 108-134), so insert / recut / margi stay local
+ * once each point has reached its owner. Per scan:
+ *   vina_shard_route          pvec_update (point_utils.cpp:54-65) + key + owner for points [first, first+count)
+ *                             of the ctx's down-sampled pointVar set; writes `count` records to d_send, grouped
+ *                             by owner rank 0..world-1 in scan order (stable); counts_out[r] = records for rank r
+ *   <exchange>                all-to-all of the records (NCCL: ncclSend/ncclRecv or torch.distributed
+ *                             all_to_all_single - see INTEGRATION.md); receive in source-rank order
+ *   vina_shard_insert_begin   received records -> key -> root find/create (voxel_map.cpp:53-87);
+ *                             reports this rank's distinct-root and slide-map counts
+ *   <all-reduce of the two counts: the reference's "fewer roots than threads" early-outs
+ *    (voxel_map.cpp:96-97, local_mapping.cpp:26-28, 150-154) are rules about the WHOLE map>
+ *   vina_shard_insert_finish  OctoTree::allocate/push on the local roots (octree.cpp:151-228)
+ *   vina_map_recut / vina_map_margi / vina_map_shift_window as on one GPU.
+ * The union of the shards equals the single-GPU map bit for bit when ranks route ascending slices of the scan. */
+int vina_shard_owner(int64_t kx, int64_t ky, int64_t kz, int world); /* pure function; -1 = key out of range */
+int vina_shard_route(vina_ctx* ctx, int world, int first, int count, int64_t scan_index_base, const double R[9],
+                     const double p[3], const double cov_rot[9], const double cov_tsl[9], void* d_send,
+                     int32_t* counts_out);
+int vina_shard_insert_begin(vina_ctx* ctx, const void* d_recv, int n, int win_ord, int32_t* local_roots,
+                            int32_t* local_slide);
+int vina_shard_insert_finish(vina_ctx* ctx, int win_ord, int global_roots, int global_slide);
 
 /* ---- the per-scan loop body (src/pipeline/local_mapping.cpp:389-546), host
  * orchestration in C++ inside the library: a1 IMU propagation on the host

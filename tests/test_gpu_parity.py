@@ -462,3 +462,73 @@ def test_device_iekf_loop_matches_host_solve(oracle_lib, gpu_lib):
         # and the update really moved the perturbed state back to the ground truth
         assert np.linalg.norm(sd["p"] - sc.gt_p) < 5e-3
     gx.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_map_equals_single_gpu_map(oracle_lib, gpu_lib, world):
+    """the map partitioned by voxel-hash range. `world` shard contexts (here on one GPU, records
+    exchanged in-process with the permutation tests/test_sharded_cpu.py checks against the real all-to-all) are
+    fed ascending slices of every scan; the union of the shards must equal, byte for byte, the map one context
+    builds from the same scans - through bootstrap, subdivision and the sliding-window marginalisation."""
+    import torch
+
+    from vina_slam_b200 import sharded
+
+    cfg = small_cfg("robosense128", 32, 600)
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)  # only supplies the down-sampled clouds
+    single = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    shards = [sharded.MapShard(gpu_lib.Ctx(cfg, **SMALL_CAPS), r, world) for r in range(world)]
+    routed_to = np.zeros(world, dtype=np.int64)
+    for k in range(cfg.win_size + 5):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        down = od.last_down()
+        st = gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+        single.set_state(st)
+        single.down_upload(down)
+        single.var_init(1)
+        single.odom_map_update()
+        sa = gpu_lib.state_arrays(st)
+        Rc, p = col(sa["R"]), sa["p"]
+        rv, tv = cov_blocks(sa["cov"])
+        sends, counts = [], []
+        for sh in shards:  # every rank holds the scan, routes its slice
+            sh.ctx.down_upload(down)
+            sh.ctx.var_init(1)
+            sh.push_pose(Rc, p)
+            first, cnt = sharded.slice_of(down.shape[0], sh.rank, world)
+            s_, c_ = sh.route(first, cnt, 0, Rc, p, rv, tv)
+            assert int(c_.sum()) == cnt
+            sends.append(s_)
+            counts.append(c_)
+        recvs = sharded.local_exchange(sends, counts)
+        torch.cuda.synchronize()
+        loc = [sh.insert_begin(rv_) for sh, rv_ in zip(shards, recvs)]
+        g_roots, g_slide = sum(a for a, _ in loc), sum(b for _, b in loc)
+        for sh, rv_ in zip(shards, recvs):
+            routed_to[sh.rank] += rv_.shape[0]
+            # ascending scan order at the owner: the property the bit-exactness rests on
+            gi = rv_[:, 12].contiguous().view(torch.int64).cpu().numpy()
+            assert np.all(np.diff(gi) > 0)
+            sh.insert_finish(g_roots, g_slide)
+            sh.recut_margi()
+    ms = sort_nodes(single.map_export())
+    parts = [sh.ctx.map_export() for sh in shards]
+    lib = gpu_lib.load()
+    import ctypes as C
+
+    for r, part in enumerate(parts):  # every node sits on the owner of its root voxel
+        ow = [lib.vina_shard_owner(C.c_int64(int(k[0])), C.c_int64(int(k[1])), C.c_int64(int(k[2])), world)
+              for k in part["key"]]
+        assert part.shape[0] > 100 and all(o == r for o in ow)
+    mu = sort_nodes(np.concatenate(parts))
+    assert mu.shape[0] == ms.shape[0] > 2000
+    for f in ms.dtype.names:
+        assert np.array_equal(ms[f], mu[f]), f"sharded map differs from the single-GPU map in {f}"
+    assert (ms["octo_state"] == 1).sum() > 100 and (ms["N_fix"] > 0).sum() > 100  # subdivision and margi happened
+    assert sum(sh.ctx.map_count()[2] for sh in shards) == single.map_count()[2]  # surf_map_slide
+    assert routed_to.min() > 0.5 * routed_to.mean()  # balanced
+    single.close()
+    for sh in shards:
+        sh.ctx.close()

@@ -66,8 +66,10 @@ EXPORTS = [
     "vina_odom_set_state", "vina_odom_get_state", "vina_odom_set_imu_anchor", "vina_odom_bootstrap",
     "vina_odom_step", "vina_odom_step_resident", "vina_odom_propagate", "vina_odom_iekf", "vina_odom_iekf_host",
     "vina_odom_map_update",
-    "vina_odom_window", "vina_get_timings", "vina_set_profiling",
+    "vina_odom_window", "vina_get_timings", "vina_set_profiling", "vina_shard_owner", "vina_shard_route",
+    "vina_shard_insert_begin", "vina_shard_insert_finish",
 ]
+SHARD_RECORD_DOUBLES = 13
 
 
 class VinaError(RuntimeError):
@@ -291,6 +293,39 @@ class Ctx:
         out = np.zeros(max(n, 1), dtype=NODE_DTYPE)
         k = self._ck(self.lib.vina_map_export(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(out.shape[0])))
         return out[:k]
+
+    def map_recut(self, win_count: int, x_buf: np.ndarray):
+        xb = np.ascontiguousarray(x_buf, dtype=POSE_DTYPE)
+        self._ck(self.lib.vina_map_recut(self.h, C.c_int(win_count), xb.ctypes.data_as(C.c_void_p)))
+
+    def map_margi(self, win_count: int, x_buf: np.ndarray):
+        xb = np.ascontiguousarray(x_buf, dtype=POSE_DTYPE)
+        self._ck(self.lib.vina_map_margi(self.h, C.c_int(win_count), xb.ctypes.data_as(C.c_void_p)))
+        self._ck(self.lib.vina_map_shift_window(self.h))
+
+    def map_insert(self, win_ord: int, R_col, p, cov_rot_col, cov_tsl_col):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (R_col, p, cov_rot_col, cov_tsl_col)]
+        self._ck(self.lib.vina_map_insert(self.h, C.c_int(win_ord), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3])))
+
+    # ---- map sharded by voxel-hash range (device pointers are caller-owned, e.g. torch tensors)
+    def shard_route(self, world: int, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col,
+                    d_send_ptr: int) -> np.ndarray:
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (R_col, p, cov_rot_col, cov_tsl_col)]
+        counts = np.zeros(world, dtype=np.int32)
+        self._ck(self.lib.vina_shard_route(self.h, C.c_int(world), C.c_int(first), C.c_int(count),
+                                           C.c_int64(index_base), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]),
+                                           C.c_void_p(d_send_ptr), counts.ctypes.data_as(C.c_void_p)))
+        return counts
+
+    def shard_insert_begin(self, d_recv_ptr: int, n: int, win_ord: int):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.vina_shard_insert_begin(self.h, C.c_void_p(d_recv_ptr), C.c_int(n), C.c_int(win_ord),
+                                                  C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shard_insert_finish(self, win_ord: int, global_roots: int, global_slide: int):
+        self._ck(self.lib.vina_shard_insert_finish(self.h, C.c_int(win_ord), C.c_int(global_roots),
+                                                   C.c_int(global_slide)))
 
     # ---- odometry (host pipeline inside the library)
     def set_state(self, s: VinaState):

@@ -64,19 +64,27 @@ __device__ int make_child(const MapView& M, int parent, int ci)
 // (voxel_map.cpp:53-87).
 __global__ void __launch_bounds__(256)
     k_insert_root(MapView M, ScanView scan, const int* __restrict__ n_ptr, int n_host, InsertScratch sc, PoseD x,
-                  Cov2 cv)
+                  Cov2 cv, int pre)
 {
   int n = n_ptr ? *n_ptr : n_host;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double pnt[3] = { scan.p[0][i], scan.p[1][i], scan.p[2][i] };
-  double var6[6];
-  for (int k = 0; k < 6; k++) var6[k] = scan.v[k][i];
-  double pw[3], vw[6];
-  rot_trans(x.R, x.p, pnt, pw);
-  world_var(x.R, pnt, var6, cv.rot, cv.tsl, vw);
-  for (int k = 0; k < 3; k++) sc.pw[k][i] = pw[k];
-  for (int k = 0; k < 6; k++) sc.vw[k][i] = vw[k];
+  double pw[3];
+  if (pre)
+  {
+    // sharded map: the sender already ran pvec_update (shard_kernels.cu), sc.pw / sc.vw hold the result
+    for (int k = 0; k < 3; k++) pw[k] = sc.pw[k][i];
+  }
+  else
+  {
+    double pnt[3] = { scan.p[0][i], scan.p[1][i], scan.p[2][i] };
+    double var6[6], vw[6];
+    for (int k = 0; k < 6; k++) var6[k] = scan.v[k][i];
+    rot_trans(x.R, x.p, pnt, pw);
+    world_var(x.R, pnt, var6, cv.rot, cv.tsl, vw);
+    for (int k = 0; k < 3; k++) sc.pw[k][i] = pw[k];
+    for (int k = 0; k < 6; k++) sc.vw[k][i] = vw[k];
+  }
 
   long long kc[3];
   for (int k = 0; k < 3; k++) kc[k] = voxel_coord(pw[k], M.voxel_size);
@@ -558,7 +566,7 @@ __device__ __forceinline__ const int* layer_nodes(const MapView& M, const LayerL
 // next layer's node list.
 __global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, int layer)
 {
-  if (M.slide_count[M.slide_cur] < M.thread_num) return;  // local_mapping.cpp:150-154
+  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:150-154
   int nn;
   const int* nodes = layer_nodes(M, LL, layer, &nn);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
@@ -623,7 +631,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   __shared__ int fill[8];
   __shared__ int wcount[2][8];
   __shared__ unsigned char rows[8][SPLIT_BATCH];
-  if (M.slide_count[M.slide_cur] < M.thread_num) return;
+  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   LaneRole L;
@@ -1041,7 +1049,7 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
 __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb)
 {
-  if (M.slide_count[M.slide_cur] < M.thread_num) return;  // local_mapping.cpp:26-28
+  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
@@ -1054,7 +1062,7 @@ __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, 
 // OctoTree::margi, interior branch (octree.cpp:485-494): isexist = OR over the children, bottom-up
 __global__ void __launch_bounds__(128) k_margi_up(MapView M, LayerLists LL, int layer)
 {
-  if (M.slide_count[M.slide_cur] < M.thread_num) return;
+  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   int nn;
   const int* nodes = layer_nodes(M, LL, layer, &nn);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
@@ -1073,7 +1081,7 @@ __global__ void __launch_bounds__(128) k_margi_up(MapView M, LayerLists LL, int 
 // its SlideWindow back (OctoTree::clear_slwd, octree.cpp:739-756). blockIdx.y = layer.
 __global__ void __launch_bounds__(128) k_margi_clear(MapView M, LayerLists LL)
 {
-  if (M.slide_count[M.slide_cur] < M.thread_num) return;
+  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
@@ -1094,7 +1102,7 @@ __global__ void __launch_bounds__(128) k_slide_compact(MapView M)
 {
   const int cur = M.slide_cur;
   const int nroots = M.slide_count[cur];
-  const bool early_out = nroots < M.thread_num;  // multi_margi returned before its erase loop
+  const bool early_out = nroots + M.slide_others < M.thread_num;  // multi_margi returned before its erase loop
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
   {
     const int root = M.slide_list[cur][j];
@@ -1186,15 +1194,22 @@ __global__ void k_map_init(MapView M, unsigned int nslots)
 // ---------------------------------------------------------------------------
 static int grid_for(int n, int block) { return n <= 0 ? 1 : (n + block - 1) / block; }
 
-int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                      const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
-                      const double* tsl_var)
+int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
+                            const InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
+                            int pre)
 {
   Cov2 cv;
   for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
-  if (n_host <= 0) return 0;
   k_zero_ints<<<1, 32, 0, st>>>(sc.counters, 3);
-  k_insert_root<<<grid_for(n_host, 256), 256, 0, st>>>(map, scan, n_dev, n_host, sc, x, cv);
+  if (n_host <= 0) return 1;
+  k_insert_root<<<grid_for(n_host, 256), 256, 0, st>>>(map, scan, n_dev, n_host, sc, x, cv, pre);
+  return 2;
+}
+
+int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
+                             const InsertScratch& sc, int win_ord)
+{
+  if (n_host <= 0) return 0;
   k_insert_leaf<<<grid_for(n_host, 256), 256, 0, st>>>(map, n_dev, n_host, sc);
   int tg = grid_for(n_host, 128);
   if (tg > 1184) tg = 1184;
@@ -1203,7 +1218,16 @@ int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan,
   int ag = grid_for(n_host, ACC_WARPS);  // at most one warp per point's leaf
   if (ag > 148 * 16) ag = 148 * 16;
   k_insert_accum<<<ag, 32 * ACC_WARPS, 0, st>>>(map, scan, sc, win_ord);
-  return 6;
+  return 4;
+}
+
+int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
+                      const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
+                      const double* tsl_var)
+{
+  if (n_host <= 0) return 0;
+  int k = launch_map_insert_roots(st, map, scan, n_dev, n_host, sc, x, rot_var, tsl_var, 0);
+  return k + launch_map_insert_leaves(st, map, scan, n_dev, n_host, sc, win_ord);
 }
 
 static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)

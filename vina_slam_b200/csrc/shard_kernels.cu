@@ -1,0 +1,161 @@
+// Voxel-hash-range sharding of the map across GPUs (BASELINE.json configs[4]).
+//
+// A root voxel - and with it every leaf, cluster sum and plane below it - belongs to exactly one rank:
+//   owner(key) = floor(hash(key) * world / 2^32)          (contiguous ranges of the 32-bit voxel hash)
+// because a leaf's accumulators depend only on the points of its own root voxel (voxel_map.cpp:86,
+// 108-134). Building the map therefore needs ONE exchange per scan: every rank turns its share of the scan
+// into world-frame point records (pvec_update, point_utils.cpp:54-65), partitions them by owner, and the
+// records travel to their owners (all-to-all over NVLink); insert / recut / margi then run locally and
+// unchanged on what arrived.
+//
+// The partition is STABLE (records of one owner keep the scan order) and ranks hold ascending slices of the
+// scan, so the concatenation an owner receives is in ascending scan order - the order the reference's
+// push_back(i) loop uses (voxel_map.cpp:86). Every cluster sum of the sharded map is therefore bit-identical
+// to the single-GPU map's, which tests/test_gpu_parity.py asserts on the union of the shards.
+//
+// Compiled with -fmad=false like map_kernels.cu: pw / vw must be the bits k_insert_root would compute.
+#include "vn_kernels.cuh"
+
+#define SH_THREADS 256
+#define SH_WARPS (SH_THREADS / 32)
+
+struct ShardCov
+{
+  double rot[9], tsl[9];
+};
+
+// pass 1: owner of every point of the slice + per-block histogram
+__global__ void __launch_bounds__(SH_THREADS)
+    k_shard_count(ScanView scan, int first, int count, PoseD x, double voxel_size, int world,
+                  unsigned char* __restrict__ owner, int* __restrict__ hist, int* __restrict__ status)
+{
+  __shared__ int h[VN_MAX_WORLD];
+  if (threadIdx.x < VN_MAX_WORLD) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  if (i < count)
+  {
+    const int s = first + i;
+    const double pnt[3] = { scan.p[0][s], scan.p[1][s], scan.p[2][s] };
+    double pw[3];
+    rot_trans(x.R, x.p, pnt, pw);
+    long long kc[3];
+    for (int k = 0; k < 3; k++) kc[k] = voxel_coord(pw[k], voxel_size);
+    unsigned long long key;
+    int ow = 0;
+    if (pack_key(kc[0], kc[1], kc[2], &key))
+      ow = shard_owner(key, world);
+    else
+      atomicOr(status, VN_ST_KEY_RANGE);
+    owner[i] = (unsigned char)ow;
+    atomicAdd(&h[ow], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < world) hist[blockIdx.x * world + threadIdx.x] = h[threadIdx.x];
+}
+
+// pass 2 (one block, warp w = owner w): exclusive scan of the histogram over the blocks; segment starts
+__global__ void __launch_bounds__(32 * VN_MAX_WORLD)
+    k_shard_offsets(int* __restrict__ hist, int nblk, int world, int* __restrict__ counts, int* __restrict__ starts)
+{
+  __shared__ int tot[VN_MAX_WORLD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w < world)
+  {
+    int run = 0;
+    for (int b0 = 0; b0 < nblk; b0 += 32)
+    {
+      const int b = b0 + lane;
+      const int v = b < nblk ? hist[b * world + w] : 0;
+      int xs = v;
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const int y = __shfl_up_sync(0xffffffffu, xs, o);
+        if (lane >= o) xs += y;
+      }
+      if (b < nblk) hist[b * world + w] = run + xs - v;
+      run += __shfl_sync(0xffffffffu, xs, 31);
+    }
+    if (lane == 0) tot[w] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    int s = 0;
+    for (int k = 0; k < world; k++)
+    {
+      counts[k] = tot[k];
+      starts[k] = s;
+      s += tot[k];
+    }
+    starts[world] = s;
+  }
+}
+
+// pass 3: pvec_update + stable scatter of the 13-double records into the owner segments
+__global__ void __launch_bounds__(SH_THREADS)
+    k_shard_scatter(ScanView scan, int first, int count, PoseD x, ShardCov cv, int world,
+                    const unsigned char* __restrict__ owner, const int* __restrict__ hist,
+                    const int* __restrict__ starts, double* __restrict__ out, long long gidx_base)
+{
+  __shared__ int wcnt[SH_WARPS][VN_MAX_WORLD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  const int ow = i < count ? (int)owner[i] : -1;
+  int myrank = 0;
+  for (int w = 0; w < world; w++)
+  {
+    const unsigned int m = __ballot_sync(0xffffffffu, ow == w);
+    if (ow == w) myrank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[warp][w] = __popc(m);
+  }
+  __syncthreads();
+  if (ow < 0) return;
+  int base = 0;
+  for (int ww = 0; ww < warp; ww++) base += wcnt[ww][ow];
+  const size_t pos = (size_t)starts[ow] + hist[blockIdx.x * world + ow] + base + myrank;
+  const int s = first + i;
+  const double pnt[3] = { scan.p[0][s], scan.p[1][s], scan.p[2][s] };
+  double var6[6], pw[3], vw[6];
+  for (int k = 0; k < 6; k++) var6[k] = scan.v[k][s];
+  rot_trans(x.R, x.p, pnt, pw);
+  world_var(x.R, pnt, var6, cv.rot, cv.tsl, vw);
+  double* r = out + pos * VINA_SHARD_RECORD_DOUBLES;
+  for (int k = 0; k < 3; k++) r[k] = pnt[k];
+  for (int k = 0; k < 6; k++) r[3 + k] = vw[k];
+  for (int k = 0; k < 3; k++) r[9 + k] = pw[k];
+  reinterpret_cast<long long*>(r)[12] = gidx_base + s;
+}
+
+// received records -> the SoA buffers the insert kernels read (body point, world point, world covariance)
+__global__ void __launch_bounds__(SH_THREADS)
+    k_shard_unpack(const double* __restrict__ rec, int n, ScanView scan, InsertScratch sc)
+{
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const double* r = rec + (size_t)i * VINA_SHARD_RECORD_DOUBLES;
+  for (int k = 0; k < 3; k++) scan.p[k][i] = r[k];
+  for (int k = 0; k < 6; k++) sc.vw[k][i] = r[3 + k];
+  for (int k = 0; k < 3; k++) sc.pw[k][i] = r[9 + k];
+}
+
+int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
+                       const double* rot_var, const double* tsl_var, double voxel_size, int world,
+                       unsigned char* owner, int* hist, int* counts, int* starts, double* out, long long gidx_base,
+                       int* status)
+{
+  ShardCov cv;
+  for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
+  const int nblk = count <= 0 ? 1 : (count + SH_THREADS - 1) / SH_THREADS;
+  k_shard_count<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, voxel_size, world, owner, hist, status);
+  k_shard_offsets<<<1, 32 * VN_MAX_WORLD, 0, st>>>(hist, nblk, world, counts, starts);
+  k_shard_scatter<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, cv, world, owner, hist, starts, out, gidx_base);
+  return 3;
+}
+
+int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc)
+{
+  if (n <= 0) return 0;
+  k_shard_unpack<<<(n + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(rec, n, scan, sc);
+  return 1;
+}

@@ -246,6 +246,10 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFreeHost(ctx->h_iekf);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
+  cudaFree(ctx->d_sh_owner);
+  cudaFree(ctx->d_sh_hist);
+  cudaFree(ctx->d_sh_counts);
+  cudaFreeHost(ctx->h_sh_counts);
   cudaFree(ctx->dbg.keys);
   cudaFree(ctx->dbg.codes);
   cudaFree(ctx->dbg.flags);
@@ -728,6 +732,90 @@ extern "C" int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t
   cudaFree(d_out);
   cudaFree(d_cnt);
   return nn;
+}
+
+// ---------------------------------------------------------------------------
+// map sharded by voxel-hash range (shard_kernels.cu)
+extern "C" int vina_shard_owner(int64_t kx, int64_t ky, int64_t kz, int world)
+{
+  unsigned long long key;
+  if (world < 1 || world > VINA_MAX_WORLD || !pack_key(kx, ky, kz, &key)) return -1;
+  return shard_owner(key, world);
+}
+
+static int ensure_shard(vina_ctx* ctx)
+{
+  if (ctx->d_sh_owner) return VINA_OK;
+  const size_t cap = ctx->cap_points;
+  CU(dalloc(&ctx->d_sh_owner, cap));
+  CU(dalloc(&ctx->d_sh_hist, (cap / 256 + 2) * VINA_MAX_WORLD));
+  CU(dalloc(&ctx->d_sh_counts, 2 * VINA_MAX_WORLD + 2));
+  CU(cudaHostAlloc((void**)&ctx->h_sh_counts, (2 * VINA_MAX_WORLD + 2) * sizeof(int), cudaHostAllocDefault));
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_route(vina_ctx* ctx, int world, int first, int count, int64_t scan_index_base,
+                                const double R[9], const double p[3], const double cov_rot[9],
+                                const double cov_tsl[9], void* d_send, int32_t* counts_out)
+{
+  if (!ctx || world < 1 || world > VINA_MAX_WORLD || first < 0 || count < 0 || !R || !p || !cov_rot || !cov_tsl ||
+      !counts_out || (count > 0 && !d_send))
+    return VINA_E_ARG;
+  if (first + count > ctx->n_pv[1])
+    return vn_fail(ctx, VINA_E_ARG, "slice [%d, %d) exceeds the %d down-sampled points", first, first + count,
+                   ctx->n_pv[1]);
+  int r = ensure_shard(ctx);
+  if (r) return r;
+  PoseD x;
+  memcpy(x.R, R, 72);
+  memcpy(x.p, p, 24);
+  ctx->launches += launch_shard_route(ctx->stream, ctx->pv[1], first, count, x, cov_rot, cov_tsl, ctx->cfg.voxel_size,
+                                      world, ctx->d_sh_owner, ctx->d_sh_hist, ctx->d_sh_counts,
+                                      ctx->d_sh_counts + VINA_MAX_WORLD, (double*)d_send, (long long)scan_index_base,
+                                      ctx->d_status);
+  CU(cudaMemcpyAsync(ctx->h_sh_counts, ctx->d_sh_counts, world * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < world; k++) counts_out[k] = ctx->h_sh_counts[k];
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_insert_begin(vina_ctx* ctx, const void* d_recv, int n, int win_ord, int32_t* local_roots,
+                                       int32_t* local_slide)
+{
+  if (!ctx || n < 0 || (n > 0 && !d_recv) || win_ord < 0 || win_ord >= ctx->cfg.win_size || !local_roots || !local_slide)
+    return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "%d routed points > max_scan_points %d", n, ctx->cap_points);
+  int r = ensure_shard(ctx);
+  if (r) return r;
+  // the received records replace the down-sampled pointVar set of this ctx (body points; the covariance
+  // arrays are not used: the world covariance arrives in the record)
+  ctx->launches += launch_shard_unpack(ctx->stream, (const double*)d_recv, n, ctx->pv[1], ctx->ins);
+  ctx->n_pv[1] = n;
+  ctx->n_down = n;
+  ctx->n_down_pending = false;
+  ctx->ins.stamp++;
+  PoseD x;
+  memset(&x, 0, sizeof(x));
+  double z9[9] = { 0 };
+  ctx->launches += launch_map_insert_roots(ctx->stream, ctx->map, ctx->pv[1], nullptr, n, ctx->ins, x, z9, z9, 1);
+  CU(cudaMemcpyAsync(ctx->h_sh_counts, ctx->ins.counters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_sh_counts + 1, ctx->map.slide_count + ctx->map.slide_cur, sizeof(int),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *local_roots = ctx->h_sh_counts[0];
+  *local_slide = ctx->h_sh_counts[1];
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_insert_finish(vina_ctx* ctx, int win_ord, int global_roots, int global_slide)
+{
+  if (!ctx || win_ord < 0 || win_ord >= ctx->cfg.win_size || global_roots < 0 || global_slide < 0) return VINA_E_ARG;
+  // the early-out of voxel_map.cpp:96-97 compares the scan's distinct roots over the WHOLE map
+  launch_fill_int(ctx->stream, ctx->ins.counters, global_roots, 1);
+  ctx->map.slide_others = global_slide - ctx->h_sh_counts[1];
+  if (ctx->map.slide_others < 0) ctx->map.slide_others = 0;
+  ctx->launches += 1 + launch_map_insert_leaves(ctx->stream, ctx->map, ctx->pv[1], nullptr, ctx->n_pv[1], ctx->ins, win_ord);
+  return VINA_OK;
 }
 
 extern "C" int vina_set_profiling(vina_ctx* ctx, int on)

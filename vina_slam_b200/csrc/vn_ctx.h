@@ -56,6 +56,11 @@ struct vina_ctx
   unsigned int hash_slots = 0;
   int* d_status = nullptr;
   int* h_status = nullptr;  // pinned
+  // hash-range sharding scratch (allocated on first use)
+  unsigned char* d_sh_owner = nullptr;
+  int* d_sh_hist = nullptr;
+  int* d_sh_counts = nullptr;  // [VINA_MAX_WORLD] counts, then [VINA_MAX_WORLD + 1] segment starts
+  int* h_sh_counts = nullptr;  // pinned
   int win_count_last = 0;
 
   // profiling

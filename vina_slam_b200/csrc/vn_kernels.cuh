@@ -105,6 +105,20 @@ struct InsertScratch
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                       const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
                       const double* tsl_var);
+// the two halves of an insert, for the sharded map: (1) key + root find/create on points whose world
+// position / covariance are already in sc.pw / sc.vw (pre != 0) or come from pvec_update; (2) the rest.
+// Between them the caller may overwrite sc.counters[0] (distinct roots) with the all-reduced count.
+int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
+                            const InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
+                            int pre);
+int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
+                             const InsertScratch& sc, int win_ord);
+// shard_kernels.cu
+int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
+                       const double* rot_var, const double* tsl_var, double voxel_size, int world,
+                       unsigned char* owner, int* hist, int* counts, int* starts, double* out, long long gidx_base,
+                       int* status);
+int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc);
 int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
 int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);

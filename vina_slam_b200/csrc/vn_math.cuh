@@ -143,6 +143,11 @@ VN_HD unsigned int hash_key(unsigned long long k)
   k ^= k >> 33;
   return (unsigned int)k;
 }
+// owner rank of a root voxel in a map sharded by hash range over `world` ranks
+VN_HD int shard_owner(unsigned long long key, int world)
+{
+  return (int)(((unsigned long long)hash_key(key) * (unsigned long long)world) >> 32);
+}
 // child index (octree.cpp:211-215 == 584-588): strict >
 VN_HD int child_index(const double* w, const double* c)
 {

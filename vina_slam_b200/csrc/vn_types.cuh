@@ -13,6 +13,7 @@
 #define VN_KEY_BIAS (1 << 20)
 #define VN_KEY_MASK ((1u << 21) - 1)
 #define VN_EMPTY_KEY 0ull
+#define VN_MAX_WORLD VINA_MAX_WORLD
 
 // status bits written by kernels into Ctx::d_status
 #define VN_ST_HASH_FULL 1
@@ -133,6 +134,8 @@ struct MapView
   int* slide_list[2];
   int* slide_count;  // [2]
   int slide_cur;     // which of the two lists is surf_map_slide right now
+  int slide_others;  // roots in the surf_map_slide shards of the OTHER ranks (0 on one GPU): the
+                     // "fewer roots than threads" early-outs are rules about the whole map
   int* status;
   // config
   double voxel_size;

@@ -1,0 +1,134 @@
+"""Voxel map sharded by hash range across GPUs (BASELINE.json configs[4]: "a voxel map sharded by
+hash range across 1/2/4/8 B200 over NVLink").
+
+One process per GPU, one `capi.Ctx` per process holding the shard of the map whose root voxels hash into the
+rank's range (`vina_shard_owner`). Per scan every rank
+  1. routes its slice of the scan's down-sampled pointVar set (`vina_shard_route`: pvec_update + key + owner,
+     stable partition by owner, on the device),
+  2. exchanges the records with one all-to-all (`torch.distributed.all_to_all_single` over NCCL / NVLink - the
+     only collective on the data path; PyTorch is plumbing here: buffers, streams, the process group),
+  3. inserts what it received (`vina_shard_insert_begin/finish` around a 2-int all-reduce that makes the
+     reference's "fewer roots than threads" early-outs global), then recut / margi locally.
+The union of the shards is bit-identical to the map one GPU builds from the same scans (tests/test_gpu_parity.py,
+tests/test_sharded_cpu.py for the exchange logic under gloo).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+
+REC = capi.SHARD_RECORD_DOUBLES
+
+
+def slice_of(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Ascending, contiguous share of n points for `rank` (first, count): the concatenation over ranks is the scan
+    order, which is what makes the sharded sums bit-identical to the single-GPU ones."""
+    base, rem = divmod(n, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def exchange_records(send, counts: Sequence[int], group=None):
+    """All-to-all of routed records. send: (n, REC) float64 tensor grouped by destination rank (counts[r] rows for
+    rank r, in that order). Returns the (m, REC) tensor of rows received, ordered by source rank. Works on CUDA
+    tensors (nccl) and CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    counts = [int(c) for c in counts]
+    world = len(counts)
+    if world == 1 or not dist.is_initialized():
+        return send[: counts[0]]
+    c_out = torch.tensor(counts, dtype=torch.int64, device=send.device)
+    c_in = torch.empty_like(c_out)
+    dist.all_to_all_single(c_in, c_out, group=group)
+    rc = [int(v) for v in c_in.cpu().tolist()]
+    recv = torch.empty((sum(rc), REC), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send[: sum(counts)].contiguous(), output_split_sizes=rc, input_split_sizes=counts,
+                           group=group)
+    return recv
+
+
+def local_exchange(sends: List, counts: List[Sequence[int]]):
+    """The same permutation without a process group: all ranks' send buffers live in this process (several
+    contexts on one GPU, or numpy arrays on the CPU). Returns the per-rank receive buffers."""
+    world = len(sends)
+    starts = [np.concatenate([[0], np.cumsum(np.asarray(c, dtype=np.int64))]) for c in counts]
+    out = []
+    for dst in range(world):
+        parts = [sends[src][int(starts[src][dst]): int(starts[src][dst + 1])] for src in range(world)]
+        if isinstance(parts[0], np.ndarray):
+            out.append(np.concatenate(parts, axis=0))
+        else:
+            import torch
+
+            out.append(torch.cat(parts, dim=0).contiguous())
+    return out
+
+
+class MapShard:
+    """This rank's shard and the sliding-window bookkeeping of `map_update` (host/vina_pipeline.cpp;
+    local_mapping.cpp:425-451, 489-546 with if_BA == 0)."""
+
+    def __init__(self, ctx: capi.Ctx, rank: int, world: int, device=None, group=None):
+        import torch
+
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        # one stream for the kernels of the ctx, torch's copies and the collectives (NCCL orders itself against it)
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.win_count = 0
+        self.x_buf: List[Tuple[np.ndarray, np.ndarray]] = []
+        self._send = None
+
+    # -- step 1
+    def route(self, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col):
+        import torch
+
+        if self._send is None or self._send.shape[0] < max(count, 1):
+            self._send = torch.empty((max(count, 1), REC), dtype=torch.float64, device=self.device)
+        counts = self.ctx.shard_route(self.world, first, count, index_base, R_col, p, cov_rot_col, cov_tsl_col,
+                                      self._send.data_ptr())
+        return self._send[:count], counts
+
+    # -- step 3a / 3b
+    def insert_begin(self, recv):
+        self._recv = recv  # keep the buffer alive until the kernels have consumed it
+        return self.ctx.shard_insert_begin(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), self.win_count - 1)
+
+    def insert_finish(self, global_roots: int, global_slide: int):
+        self.ctx.shard_insert_finish(self.win_count - 1, int(global_roots), int(global_slide))
+
+    def push_pose(self, R_col, p):
+        self.win_count += 1
+        self.x_buf.append((np.array(R_col, dtype=np.float64), np.array(p, dtype=np.float64)))
+
+    def recut_margi(self):
+        xb = np.zeros(len(self.x_buf), dtype=capi.POSE_DTYPE)
+        for i, (R, p) in enumerate(self.x_buf):
+            xb[i]["R"], xb[i]["p"] = R, p
+        self.ctx.map_recut(self.win_count, xb)
+        if self.win_count >= self.ctx.cfg.win_size:
+            self.ctx.map_margi(self.win_count, xb)
+            self.x_buf.pop(0)
+            self.win_count -= 1
+
+    # -- the whole per-scan map update, collectives included
+    def update(self, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col):
+        import torch
+        import torch.distributed as dist
+
+        self.push_pose(R_col, p)
+        send, counts = self.route(first, count, index_base, R_col, p, cov_rot_col, cov_tsl_col)
+        recv = exchange_records(send, counts, self.group)
+        roots, slide = self.insert_begin(recv)
+        tot = torch.tensor([roots, slide], dtype=torch.int64, device=self.device)
+        if self.world > 1 and dist.is_initialized():
+            dist.all_reduce(tot, group=self.group)
+        g = tot.cpu().tolist()
+        self.insert_finish(g[0], g[1])
+        self.recut_margi()
+        return int(recv.shape[0])
