@@ -379,6 +379,98 @@ def main_ours(args, cfg):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- sharded map build
+def main_sharded(args, cfg):
+    """Map partitioned by voxel-hash range over the ranks (BASELINE.json configs[4]). Every rank holds the scan,
+    routes its ascending slice of the down-sampled points to the owners (one all-to-all of 104-byte records over
+    NCCL / NVLink per scan), inserts what it received, recut + margi locally. Strong scaling: the scans are the
+    same at every N. Rank 0 also builds the whole map on its own and the digests are compared (bit-exactness)."""
+    import torch
+    import torch.distributed as dist
+
+    from vina_slam_b200 import capi, sharded
+
+    rank, world, local = dist_env()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = args.warmup, args.steps
+    seq = synth.Sequence(cfg, seed=cfg.seed)
+    scans = [seq.next_scan(deskewed=True) for _ in range(cfg.win_size + W + K)]
+    caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=1 << 20, hash_capacity_log2=21,
+                device=local)
+    sh = sharded.MapShard(capi.Ctx(cfg, **caps), rank, world, device=dev)
+    ref = capi.Ctx(cfg, **caps) if (rank == 0 and args.verify) else None
+    stream = torch.cuda.current_stream(dev)
+    d_scans = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    n_down_tot, n_recv_tot = 0, 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    barrier()
+    for k, sc in enumerate(scans):
+        if k == cfg.win_size + W:
+            barrier()
+            ev0.record(stream)
+        st = capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+        sa = capi.state_arrays(st)
+        Rc = np.ascontiguousarray(sa["R"].T.reshape(-1))
+        rv = np.ascontiguousarray(sa["cov"][0:3, 0:3].T.reshape(-1))
+        tv = np.ascontiguousarray(sa["cov"][3:6, 3:6].T.reshape(-1))
+        # the (already deskewed) scan is resident; down-sample + var_init on every rank, route this rank's slice
+        sh.ctx.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
+        sh.ctx.downsample()
+        nd = sh.ctx.n_down()
+        sh.ctx.var_init(1)
+        first, cnt = sharded.slice_of(nd, rank, world)
+        got = sh.update(first, cnt, 0, Rc, sa["p"], rv, tv)
+        if k >= cfg.win_size + W:
+            n_down_tot += nd
+            n_recv_tot += got
+        if ref is not None:
+            ref.set_state(st)
+            ref.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
+            ref.downsample()
+            ref.n_down()
+            ref.var_init(1)
+            ref.odom_map_update()
+    ev1.record(stream)
+    barrier()
+    t = ev0.elapsed_time(ev1) * 1e-3
+    tt = torch.tensor([t], dtype=torch.float64, device=dev)
+    dig = torch.tensor([sharded.map_digest(sh.ctx.map_export()), sh.ctx.map_count()[0], n_recv_tot], dtype=torch.int64,
+                       device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dig)
+    if rank == 0:
+        pts = sum(sc.xyzt.shape[0] for sc in scans[cfg.win_size + W:])
+        line = {"metric": "pts/s voxel-map build sharded by hash range (down-sample -> var_init -> route -> all-to-all "
+                          "-> insert -> recut -> margi, per scan)", "value": pts / float(tt[0]), "unit": UNIT,
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * float(tt[0]) / K,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(cfg), "mode": "sharded-map", "parallelism": f"hash-range x{world}",
+                           "down_points_per_scan": n_down_tot / K, "routed_points_per_scan": int(dig[2]) / K,
+                           "record_bytes": 8 * sharded.REC, "nodes": int(dig[1])},
+                "gpu_launches": None}
+        if ref is not None:
+            line["config"]["union_equals_single_gpu_map"] = bool(int(dig[0]) == sharded.map_digest(ref.map_export()))
+            line["config"]["single_gpu_nodes"] = ref.map_count()[0]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -388,12 +480,18 @@ def main():
     ap.add_argument("--workload", default="robosense128", choices=sorted(synth.SENSORS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--batch", type=int, default=8, help="concurrent sequences per GPU in the batch-replay leg (0/1 = off)")
+    ap.add_argument("--mode", default="odometry", choices=["odometry", "sharded-map"],
+                    help="odometry = the headline per-scan path (default); sharded-map = map build partitioned by "
+                         "voxel-hash range over the ranks (SURVEY 8e)")
+    ap.add_argument("--verify", action="store_true", help="sharded-map: rank 0 also builds the single-GPU map and compares")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     cfg = synth.SENSORS[args.workload]
     if args.impl == "reference":
         main_reference(args, cfg)
+    elif args.mode == "sharded-map":
+        main_sharded(args, cfg)
     else:
         main_ours(args, cfg)
 

@@ -138,6 +138,7 @@ int vina_ctx_sync(vina_ctx* ctx);
  * (src/estimation/imu_ekf.cpp:114-144). xyzt = n x (x,y,z,curvature) float32,
  * time-sorted (lidar_decoder.cpp:30). The scan stays resident on the device. */
 int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n);
+int vina_scan_upload_device(vina_ctx* ctx, const void* d_xyzt, int n); /* same, from a DEVICE pointer */
 int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap); /* returns n or <0 */
 
@@ -146,6 +147,7 @@ int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap); /* returns n or <0 
  * local_mapping.cpp:396-403. vina_down_upload instead installs a caller-made
  * down-sampled cloud (used by stage-wise parity tests). */
 int vina_downsample(vina_ctx* ctx);
+int vina_down_count(vina_ctx* ctx); /* points after down-sampling incl. the retry (one sync); <0 = error */
 int vina_down_upload(vina_ctx* ctx, const float* xyzt, int n);
 int vina_down_download(vina_ctx* ctx, float* xyzt, int cap); /* returns n_d or <0 */
 

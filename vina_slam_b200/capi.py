@@ -59,7 +59,7 @@ NODE_DTYPE = np.dtype([
 # every symbol include/vina_b200.h declares
 EXPORTS = [
     "vina_config_default", "vina_ctx_create", "vina_ctx_destroy", "vina_last_error", "vina_ctx_set_stream",
-    "vina_ctx_sync", "vina_scan_upload", "vina_deskew", "vina_scan_download", "vina_downsample", "vina_down_upload",
+    "vina_ctx_sync", "vina_scan_upload", "vina_scan_upload_device", "vina_down_count", "vina_deskew", "vina_scan_download", "vina_downsample", "vina_down_upload",
     "vina_down_download", "vina_var_init", "vina_pvec_upload", "vina_pvec_download", "vina_iekf_begin",
     "vina_iekf_accumulate", "vina_iekf_accumulate_debug", "vina_iekf_debug_assoc", "vina_map_insert",
     "vina_map_recut", "vina_map_margi", "vina_map_shift_window", "vina_map_count", "vina_map_export",
@@ -230,8 +230,14 @@ class Ctx:
         k = self._ck(self.lib.vina_scan_download(self.h, _fp(a), C.c_int(n)))
         return a[:k]
 
+    def scan_upload_device(self, d_ptr: int, n: int):
+        self._ck(self.lib.vina_scan_upload_device(self.h, C.c_void_p(d_ptr), C.c_int(n)))
+
     def downsample(self):
         self._ck(self.lib.vina_downsample(self.h))
+
+    def n_down(self) -> int:
+        return self._ck(self.lib.vina_down_count(self.h))
 
     def down_upload(self, xyzt: np.ndarray):
         a = np.ascontiguousarray(xyzt, dtype=np.float32)

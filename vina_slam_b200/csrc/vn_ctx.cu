@@ -316,6 +316,15 @@ extern "C" int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n)
   return VINA_OK;
 }
 
+extern "C" int vina_scan_upload_device(vina_ctx* ctx, const void* d_xyzt, int n)
+{
+  if (!ctx || !d_xyzt || n < 0) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points %d", n, ctx->cap_points);
+  CU(cudaMemcpyAsync(ctx->d_scan, d_xyzt, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->n_scan = n;
+  return VINA_OK;
+}
+
 extern "C" int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9],
                            const double p_end[3])
 {
@@ -396,6 +405,14 @@ int vn_finish_downsample(vina_ctx* ctx)
     if (r) return r;
   }
   return VINA_OK;
+}
+
+extern "C" int vina_down_count(vina_ctx* ctx)
+{
+  if (!ctx) return VINA_E_ARG;
+  int r = vn_finish_downsample(ctx);
+  if (r) return r;
+  return ctx->n_down;
 }
 
 extern "C" int vina_down_upload(vina_ctx* ctx, const float* xyzt, int n)

@@ -177,7 +177,8 @@ class Trajectory:
         rng = np.random.default_rng(seed + 7919)
         sx, sy, sz = world.size
         self.c = np.array([sx / 2, sy / 2, 1.6]) + world.offset
-        self.A = np.array([sx * 0.30, sy * 0.12, 0.25])
+        # the handheld path stays inside the pillar-free corridor (pillars stand at y = centre +- 3 m)
+        self.A = np.array([sx * 0.30, sy * (0.06 if handheld else 0.12), 0.25])
         self.w = np.array([0.045, 0.09, 0.31]) * (2.0 if handheld else 1.0)
         self.ph = rng.uniform(0, 2 * np.pi, 3)
         k = 4.0 if handheld else 1.0
