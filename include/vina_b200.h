@@ -231,6 +231,20 @@ int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time,
  * which the caller knows. The timed "inputs resident" leg of bench.py. */
 int vina_odom_step_resident(vina_ctx* ctx, const void* d_xyzt, int n, double pcl_beg_time, double pcl_end_time,
                             const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out);
+/* ---- batch replay: B independent sequences (contexts on the same GPU) advance one scan each per call.
+ * Per-sequence stages run concurrently on the contexts' own streams; the IEKF iterations of all sequences are
+ * ONE k_iekf launch per iteration (grid blocks x B). Results are identical to B separate vina_odom_step_resident
+ * calls (same kernels, same per-sequence reduction order up to the number of blocks per sequence). */
+typedef struct vina_batch vina_batch;
+int vina_batch_create(vina_ctx** ctxs, int n, vina_batch** out); /* n <= 16 */
+void vina_batch_destroy(vina_batch* b);
+int vina_batch_step_resident(vina_batch* b, const void* const* d_xyzt, const int32_t* n, const double* pcl_beg_time,
+                             const double* pcl_end_time, const vina_imu* const* imus, const int32_t* m,
+                             int iekf_on_full, int max_iter, vina_state* x_out /* [B] or NULL */);
+/* device time of each batched k_iekf launch of the last step (CUDA events on the batch stream) */
+int vina_batch_iekf_time(vina_batch* b, float* ms_per_launch, int cap, int32_t* launches);
+int vina_batch_sync(vina_batch* b);
+
 /* stage-wise pieces of the step, for parity tests */
 int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
                         vina_imu_pose* poses_out, int cap); /* returns #poses */

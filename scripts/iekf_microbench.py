@@ -26,8 +26,14 @@ p = np.ascontiguousarray(sc.gt_p)
 r = gx.iekf_accumulate(R, p)
 print("match", r["match_num"], "of", sc.xyzt.shape[0])
 ms = C.c_float(0)
-for variant, name in [(0, "product"), (2, "result->device"), (1, "no final reduce"), (8, "no butterfly"),
-                      (4, "no gate math"), (12, "no gate, no butterfly"), (13, "assoc only, no reduce"), (16, "stream loads only"), (17, "stream loads, no final")]:
+import os
+BPS = int(os.environ.get("VINA_IEKF_BLOCKS_PER_SM", "1"))
+B18 = (18 * BPS) << 8  # the share of one sequence in a batch of 8 on 148 SMs
+for variant, name in [(0, "product"), (32, "no prefetch"), (1, "no final reduce"), (8, "no DMMA reduction"),
+                      (4, "no gate math"), (12, "no gate, no reduction"), (16, "stream loads only"),
+                      (17, "stream loads, no final"), (B18, "18 blocks"), (B18 | 32, "18 blocks, no prefetch"),
+                      (B18 | 8, "18 blocks, no DMMA"), (B18 | 4, "18 blocks, no gate"), (B18 | 16, "18 blocks, loads only"),
+                      (((37 * BPS) << 8), "37 blocks")]:
     for reset, tag in [(0, "cached"), (1, "cold cache (hash+descent)")]:
         gx.lib.vina_iekf_time_kernel(gx.h, capi._dp(R), capi._dp(p), C.c_int(50), C.c_int(variant), C.c_int(reset),
                                      C.byref(ms))

@@ -532,3 +532,54 @@ def test_sharded_map_equals_single_gpu_map(oracle_lib, gpu_lib, world):
     single.close()
     for sh in shards:
         sh.ctx.close()
+
+
+def test_batch_replay_matches_separate_contexts(oracle_lib, gpu_lib):
+    """vina_batch (config 5): three different sequences advanced in lock step with one k_iekf launch per
+    iteration for all of them, against the same sequences stepped one context at a time. Same kernels; only the
+    number of blocks per sequence (hence the order of the final sum) differs -> states to 1e-9, identical maps."""
+    import torch
+
+    cfg = small_cfg("robosense128", 32, 600)
+    B = 3
+    seqs = [synth.Sequence(cfg, seed=cfg.seed + 11 * b) for b in range(B)]
+    solo = [gpu_lib.Ctx(cfg, **SMALL_CAPS) for _ in range(B)]
+    grp = [gpu_lib.Ctx(cfg, **SMALL_CAPS) for _ in range(B)]
+    last = [None] * B
+    for b in range(B):
+        for _ in range(cfg.win_size):
+            sc = seqs[b].next_scan(deskewed=True)
+            st = gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+            solo[b].bootstrap(sc.xyzt, st)
+            grp[b].bootstrap(sc.xyzt, st)
+            last[b] = sc
+        for g in (solo[b], grp[b]):
+            g.set_imu_anchor(last[b].end_time, last[b].imu[-1])
+    batch = gpu_lib.Batch(grp)
+    dev = torch.device("cuda", 0)
+    for k in range(5):
+        scs = [s.next_scan() for s in seqs]
+        d = [torch.from_numpy(sc.xyzt).to(dev) for sc in scs]
+        torch.cuda.synchronize()
+        outs = batch.step_resident([t.data_ptr() for t in d], [sc.xyzt.shape[0] for sc in scs],
+                                   [sc.beg_time for sc in scs], [sc.end_time for sc in scs], [sc.imu for sc in scs])
+        for b in range(B):
+            so = gpu_lib.state_arrays(solo[b].step_resident(d[b].data_ptr(), scs[b].xyzt.shape[0], scs[b].beg_time,
+                                                            scs[b].end_time, scs[b].imu))
+            sb = gpu_lib.state_arrays(outs[b])
+            for f in ("R", "p", "v", "bg", "ba"):
+                assert np.max(np.abs(so[f] - sb[f])) < 1e-9, (k, b, f)
+            assert rel_err(sb["cov"], so["cov"]) < 1e-7
+            assert np.linalg.norm(sb["p"] - scs[b].gt_p) < 0.02
+            assert solo[b].timings().iekf_iters == grp[b].timings().iekf_iters
+    batch.sync()
+    ms, launches = batch.iekf_time()
+    assert launches == 4 and len(ms) == 4 and ms[0] > 0
+    for b in range(B):
+        ma, mb = sort_nodes(solo[b].map_export()), sort_nodes(grp[b].map_export())
+        assert ma.shape[0] == mb.shape[0]
+        for f in ("key", "code", "N_add", "N_fix", "is_plane", "octo_state"):
+            assert np.array_equal(ma[f], mb[f]), f
+    batch.close()
+    for g in solo + grp:
+        g.close()

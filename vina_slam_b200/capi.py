@@ -67,7 +67,8 @@ EXPORTS = [
     "vina_odom_step", "vina_odom_step_resident", "vina_odom_propagate", "vina_odom_iekf", "vina_odom_iekf_host",
     "vina_odom_map_update",
     "vina_odom_window", "vina_get_timings", "vina_set_profiling", "vina_shard_owner", "vina_shard_route",
-    "vina_shard_insert_begin", "vina_shard_insert_finish",
+    "vina_shard_insert_begin", "vina_shard_insert_finish", "vina_batch_create", "vina_batch_destroy",
+    "vina_batch_step_resident", "vina_batch_iekf_time", "vina_batch_sync",
 ]
 SHARD_RECORD_DOUBLES = 13
 
@@ -92,6 +93,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.vina_last_error.restype = C.c_char_p
     lib.vina_ctx_destroy.restype = None
+    lib.vina_batch_destroy.restype = None
     lib.vina_config_default.restype = None
     lib.vina_map_count.restype = C.c_int64
     lib.vina_map_export.restype = C.c_int64
@@ -394,3 +396,58 @@ class Ctx:
         mp = np.zeros(16, dtype=np.int32)
         ws = self._ck(self.lib.vina_odom_window(self.h, C.byref(wc), mp.ctypes.data_as(C.c_void_p), C.c_int(16)))
         return wc.value, mp[:ws].copy()
+
+
+class Batch:
+    """B independent sequences on one GPU advancing in lock step (vina_batch): per-sequence stages on the
+    contexts' own streams, the IEKF iterations of all sequences as one k_iekf launch per iteration."""
+
+    def __init__(self, ctxs):
+        self.lib = load()
+        self.ctxs = list(ctxs)
+        arr = (C.c_void_p * len(self.ctxs))(*[c.h for c in self.ctxs])
+        h = C.c_void_p()
+        r = self.lib.vina_batch_create(arr, C.c_int(len(self.ctxs)), C.byref(h))
+        if r != 0:
+            raise VinaError(r, "vina_batch_create failed (contexts must live on the same device, at most 16)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vina_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step_resident(self, d_ptrs, ns, begs, ends, imus7, iekf_on_full=True, max_iter=4):
+        B = len(self.ctxs)
+        ims = [imu_array(np.asarray(a, dtype=np.float64)) for a in imus7]
+        dp = (C.c_void_p * B)(*[int(p) for p in d_ptrs])
+        nn = (C.c_int32 * B)(*[int(v) for v in ns])
+        tb = (C.c_double * B)(*[float(v) for v in begs])
+        te = (C.c_double * B)(*[float(v) for v in ends])
+        ip = (C.c_void_p * B)(*[a.ctypes.data for a in ims])
+        mm = (C.c_int32 * B)(*[a.shape[0] for a in ims])
+        out = (VinaState * B)()
+        r = self.lib.vina_batch_step_resident(self.h, dp, nn, tb, te, ip, mm, C.c_int(1 if iekf_on_full else 0),
+                                              C.c_int(max_iter), out)
+        if r < 0:
+            msgs = [self.lib.vina_last_error(c.h).decode() for c in self.ctxs]
+            raise VinaError(int(r), " | ".join(m for m in msgs if m))
+        return list(out)
+
+    def iekf_time(self):
+        """(per-launch device ms of the last step's batched k_iekf launches, number of launches)"""
+        ms = (C.c_float * 32)()
+        k = C.c_int32(0)
+        self.lib.vina_batch_iekf_time(self.h, ms, C.c_int(32), C.byref(k))
+        return [ms[i] for i in range(min(k.value, 32))], k.value
+
+    def sync(self):
+        r = self.lib.vina_batch_sync(self.h)
+        if r < 0:
+            raise VinaError(int(r), "vina_batch_sync")

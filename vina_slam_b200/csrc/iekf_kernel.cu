@@ -11,7 +11,9 @@
 // Roofline: HBM-bound streaming of the pointVar SoA (72 B/pt + 8 B cache RMW) plus gathers of 16-B hash slots
 // and 256-B leaf records; the dependent chain cache -> leaf record (or key -> slot -> root -> child -> leaf)
 // makes it latency-bound unless enough points are in flight, so the kernel is shaped for occupancy: one
-// 1024-thread block per SM, one point per thread per round, 64 registers.
+// persistent 768-thread block per SM, one point per thread per round, 80 registers. A cached leaf costs one
+// gather (line 0 of its record: box, centre, normal, radius) before the fp32 gate and one more (line 1) for
+// sigma_l; the next round's SoA rows are prefetched into L2 while the current round computes.
 //
 // Reduction: the 6x6 / 6 / 3x3 sums are a rank-1 update per point, C += a_i b_i^T with
 //   a = [Rinv*j (6), n0, n1],  b = [j (6), r, 0],   j = [p x R^T n ; n]
@@ -29,7 +31,12 @@
 // of the flops of forming var_world.
 #include "vn_kernels.cuh"
 
-#define IEKF_THREADS 1024
+#ifndef IEKF_THREADS
+#define IEKF_THREADS 768  // 80 registers per thread; 1024 x 64 spills and is ~7 % slower (profiles/r01_iekf_block_sweep.txt)
+#endif
+#ifndef IEKF_BLOCKS_PER_SM
+#define IEKF_BLOCKS_PER_SM 1
+#endif
 #define IEKF_WARPS (IEKF_THREADS / 32)
 #define IEKF_ROWS 14                        // staged rows per warp: j0..j5, r, 0, Rinv*j0..Rinv*j5
 #define IEKF_LD 36                          // row stride (doubles): 32 points + 4 -> conflict-free fragment loads
@@ -263,7 +270,7 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
 
 // ---------------------------------------------------------------------------
 template <bool DEBUG>
-__global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant__ IekfBatch bt)
+__global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const __grid_constant__ IekfBatch bt)
 {
   const IekfSeq& q = bt.s[blockIdx.y];
   IekfDev* __restrict__ dev = q.dev;
@@ -304,6 +311,15 @@ __global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant_
   {
     const bool live = i < n;
     const int ii = live ? i : 0;
+    // the next round of this warp: pull its 9 SoA rows (2 x 128 B each) and the cache row towards L2 now
+    if (!(bt.variant & 32))
+    {
+      const int nx = i - lane + stride;  // first point of the warp's next round
+      if (nx < n && lane < 18)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + (size_t)(lane >> 1) * pvs + nx + 16 * (lane & 1)));
+      else if (nx < n && lane == 18)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cache + nx));
+    }
     // independent loads first (memory-level parallelism): point, covariance, cached leaf
     const double* __restrict__ pi = pv + ii;
     const double pnt[3] = { __ldg(pi), __ldg(pi + pvs), __ldg(pi + 2 * pvs) };
@@ -318,20 +334,37 @@ __global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant_
       continue;
     }
 
+    // ---- association. Cached leaf first (odometry.cpp:124-127): the map does not change during the call and
+    // the cache only ever holds leaves that passed the gate, so a cached node is a plane leaf - if the point
+    // is still inside its box neither the descent nor the flags are needed, and line 0 of the record (box,
+    // centre, normal, radius) arrives in one gather.
     int node = -1;
+    double2 l0, l1, l2;
+    float radius = 0.0f;
+    bool have = false;
     if (cached >= 0)
     {
-      const NodeHot* h = hot + cached;
-      const double vc[3] = { h->vcenter[0], h->vcenter[1], h->vcenter[2] };
-      if (inside_box(wld, vc, h->ql)) node = cached;
+      const double2* L = reinterpret_cast<const double2*>(hot + cached);
+      const double2 l3 = __ldg(L + 3), l4 = __ldg(L + 4);
+      l0 = __ldg(L + 0);
+      l1 = __ldg(L + 1);
+      l2 = __ldg(L + 2);
+      const double vc[3] = { l3.x, l3.y, l4.x };
+      const float2 rq = *reinterpret_cast<const float2*>(&l4.y);  // (radius, quater_length)
+      if (inside_box(wld, vc, rq.y))
+      {
+        node = cached;
+        radius = rq.x;
+        have = true;
+      }
     }
     long long kc[3] = { 0, 0, 0 };
-    if (DEBUG || (live && node < 0))
+    if (DEBUG || (live && !have))
     {
 #pragma unroll
       for (int k = 0; k < 3; k++) kc[k] = voxel_coord(wld[k], q.voxel_size);
     }
-    if (live && node < 0)
+    if (live && !have)
     {
       unsigned long long key;
       if (pack_key(kc[0], kc[1], kc[2], &key))
@@ -349,28 +382,34 @@ __global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant_
           hh = (hh + 1) & q.hmask;
         }
       }
-    }
-    // descend to the leaf (octree.cpp:584-591)
-    int flags = 0;
-    while (node >= 0)
-    {
-      const NodeHot* h = hot + node;
-      flags = h->flags;
-      if (!(flags & VN_FLAG_INTERIOR)) break;
-      const double vc[3] = { h->vcenter[0], h->vcenter[1], h->vcenter[2] };
-      node = h->children[child_index(wld, vc)];
+      // descend to the leaf (octree.cpp:584-591): one line per level
+      int flags = 0;
+      while (node >= 0)
+      {
+        const NodeHot* h = hot + node;
+        flags = h->flags;
+        if (!(flags & VN_FLAG_INTERIOR)) break;
+        const double vc[3] = { h->vcenter[0], h->vcenter[1], h->vcenter[2] };
+        node = h->children[child_index(wld, vc)];
+      }
+      if (node >= 0 && (flags & VN_FLAG_PLANE))
+      {
+        const double2* L = reinterpret_cast<const double2*>(hot + node);
+        l0 = __ldg(L + 0);
+        l1 = __ldg(L + 1);
+        l2 = __ldg(L + 2);
+        radius = hot[node].radius;
+        have = true;
+      }
     }
 
     // contributions of this point (a, b), staged for the warp's DMMA chain; all zero unless the gate passes
     __syncwarp();  // the previous round's fragment loads are done
     int flag = 0;
     double sigma_l = 0.0;
-    if (node >= 0 && (flags & VN_FLAG_PLANE) && !(bt.variant & 4))
+    if (have && !(bt.variant & 4))
     {
-      // line 0 of the leaf record: centre, normal, hoisted plane_var terms - eight 16-byte loads
       const double2* L = reinterpret_cast<const double2*>(hot + node);
-      const double2 l0 = __ldg(L + 0), l1 = __ldg(L + 1), l2 = __ldg(L + 2);
-      const float radius = hot[node].radius;
       const double c[3] = { l0.x, l0.y, l1.x };
       const double nr[3] = { l1.y, l2.x, l2.y };
       const double d[3] = { ds(wld[0], c[0]), ds(wld[1], c[1]), ds(wld[2], c[2]) };
@@ -381,14 +420,14 @@ __global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant_
       const float range_dis = fs(dis_to_center, fm(dis_to_plane, dis_to_plane));
       if (range_dis <= fm(9.0f, radius))
       {
-        // sigma_l = J plane_var J^T, J = [wld - center, -normal] = d^T A d - 2 d.(B n) + n^T C n (NodeHot)
+        // sigma_l = J plane_var J^T, J = [wld - center, -normal] = d^T A d - 2 d.(B n) + n^T C n (NodeHot, line 1)
         {
-          // (the rest of the 128-byte line is an L1 hit by now)
-          const double2 l3 = __ldg(L + 3), l4 = __ldg(L + 4), l5 = __ldg(L + 5), l6 = __ldg(L + 6), l7 = __ldg(L + 7);
-          const double A0 = l3.x, A1 = l3.y, A2 = l4.x, A3 = l4.y, A4 = l5.x, A5 = l5.y;
+          const double2 l8 = __ldg(L + 8), l9 = __ldg(L + 9), l10 = __ldg(L + 10), l11 = __ldg(L + 11);
+          const double qb2 = __ldg(reinterpret_cast<const double*>(L + 12)), qk = __ldg(reinterpret_cast<const double*>(L + 7) + 1);
+          const double A0 = l8.x, A1 = l8.y, A2 = l9.x, A3 = l9.y, A4 = l10.x, A5 = l10.y;
           const double dAd = d[0] * (A0 * d[0] + 2.0 * (A1 * d[1] + A2 * d[2])) + d[1] * (A3 * d[1] + 2.0 * A4 * d[2]) +
                              d[2] * A5 * d[2];
-          sigma_l = dAd - 2.0 * (d[0] * l6.x + d[1] * l6.y + d[2] * l7.x) + l7.y;
+          sigma_l = dAd - 2.0 * (d[0] * l11.x + d[1] * l11.y + d[2] * qb2) + qk;
         }
         // + n^T var_world n
         double m[3];
@@ -410,7 +449,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, 1) k_iekf(const __grid_constant_
         if ((double)dis_to_plane * (double)dis_to_plane < 9.0 * sigma_l)
         {
           flag = 1;
-          cache[ii] = node;  // oc = this (octree.cpp:571-575)
+          if (node != cached) cache[ii] = node;  // oc = this (octree.cpp:571-575)
           const double Rinv = 1.0 / (0.0005 + sigma_l);
           // jac = [hat(p) R^T n ; n] = [p x m ; n]
           const double j0 = pnt[1] * m[2] - pnt[2] * m[1];
@@ -551,7 +590,8 @@ int iekf_grid_blocks(int n, int sm_count)
   // memory); larger scans loop
   int need = (n + IEKF_THREADS - 1) / IEKF_THREADS;
   if (need < 1) need = 1;
-  return need < sm_count ? need : sm_count;
+  const int cap = sm_count * IEKF_BLOCKS_PER_SM;
+  return need < cap ? need : cap;
 }
 
 int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug)

@@ -860,13 +860,14 @@ extern "C" int vina_iekf_time_kernel(vina_ctx* ctx, const double R[9], const dou
   CU(cudaMemcpyAsync(ctx->d_iekf->p, p, 24, cudaMemcpyHostToDevice, ctx->stream));
   IekfBatch bt;
   bt.mode = 0;  // sums stay in the device iterate
-  bt.variant = variant;
+  bt.variant = variant & 0xff;
+  const int blocks = (variant >> 8) > 0 ? (variant >> 8) : ctx->iekf_blocks;  // bits 8.. = grid override
   vn_iekf_fill_seq(ctx, &bt.s[0], false);
   cudaEventRecord(ctx->ev[10], ctx->stream);
   for (int r = 0; r < reps; r++)
   {
     if (reset_cache) launch_fill_int(ctx->stream, ctx->d_cache, -1, ctx->n_pv[ctx->iekf_which]);
-    int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
+    int e = launch_iekf(ctx->stream, bt, 1, blocks, false);
     if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
   }
   cudaEventRecord(ctx->ev[11], ctx->stream);

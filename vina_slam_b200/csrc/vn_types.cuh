@@ -33,26 +33,31 @@ struct __align__(16) HashSlot
 };
 
 // what OctoTree::match / inside read (octree.cpp:551-595, 732-737); one 256-B record = two 128-B lines.
-// Line 0 is everything the gate needs from the plane. sigma_l = J plane_var J^T with J = [w - c, -n]
-// (octree.cpp:564-567) is hoisted per plane: with plane_var = [[A, B], [B^T, C]],
+// Line 0 is what the descent, inside() and the first (fp32) gate test need: plane centre / normal / radius,
+// voxel_center, quater_length, flags and the children mirror - a cached leaf costs ONE gather before the gate.
+// Line 1 holds the sigma_l terms. sigma_l = J plane_var J^T with J = [w - c, -n] (octree.cpp:564-567) is
+// hoisted per plane: with plane_var = [[A, B], [B^T, C]],
 //   J plane_var J^T = d^T A d - 2 d.(B n) + n^T C n,  d = w - c,
 // so the leaf stores A (6), B n (3) and n^T C n (1) instead of the 21 entries; the full plane_var lives in
-// NodeCold (export / parity only). Line 1 is what the descent needs (flags, voxel_center, children).
+// NodeCold (export / parity only).
 struct __align__(128) NodeHot
 {
-  double center[3];   // plane.center
-  double normal[3];   // plane.normal
-  double qA[6];       // upper triangle of plane_var(0:3, 0:3)
-  double qb[3];       // plane_var(0:3, 3:6) * normal
-  double qk;          // normal^T plane_var(3:6, 3:6) normal
-  float radius;       // plane.radius
-  int flags;          // VN_FLAG_*
-  double vcenter[3];  // voxel_center
-  float ql;           // quater_length
-  int layer;
+  // ---- line 0
+  double center[3];   // plane.center                     (double2 #0, #1.x)
+  double normal[3];   // plane.normal                     (#1.y, #2)
+  double vcenter[3];  // voxel_center                     (#3, #4.x)
+  float radius;       // plane.radius                     (#4.y low)
+  float ql;           // quater_length                    (#4.y high)
+  int flags;          // VN_FLAG_*                        (#5.x low)
+  int layer;          //                                  (#5.x high)
   int children[8];    // mirror of NodeCold::children for the IEKF descent (-1 = none)
+  double qk;          // normal^T plane_var(3:6, 3:6) normal   (#7.y)
+  // ---- line 1
+  double qA[6];       // upper triangle of plane_var(0:3, 0:3) (#8, #9, #10)
+  double qb[3];       // plane_var(0:3, 3:6) * normal           (#11, #12.x)
   int pad[14];
 };
+static_assert(sizeof(NodeHot) == 256, "NodeHot is two 128-byte lines");
 
 // PointCluster (types.hpp:115-175); P is symmetric by construction of every
 // cluster the scope builds, stored as (0,0),(1,0),(2,0),(1,1),(2,1),(2,2)

@@ -375,10 +375,8 @@ static void unstage_iterate(const IekfDev* h, vina_state& x, int* iters, int* no
   *not_degenerate = !(ev[0] < 14);
 }
 
-// enqueue the whole iteration loop on the ctx stream: upload of the iterate, cache reset, max_iter x k_iekf
-// (each launch accumulates, and its last block solves and updates the device iterate; launches after
-// convergence return at once), download of the result. No host synchronisation inside.
-static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
+// upload the iterate and reset the per-point leaf cache (ctx stream)
+static int iekf_stage(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
 {
   stage_iterate(o->x_curr, num_max_iter, ctx->h_iekf);
   int r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->d_iekf, ctx->h_iekf, sizeof(IekfDev), cudaMemcpyHostToDevice, ctx->stream),
@@ -389,6 +387,17 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
   launch_fill_int(ctx->stream, ctx->d_cache, -1, n);  // vector<OctoTree*> octos(psize, nullptr), odometry.cpp:79
   ctx->iekf_blocks = iekf_grid_blocks(n, ctx->sm_count);
   ctx->launches += 1;
+  ctx->dbg_valid = false;
+  return VINA_OK;
+}
+
+// enqueue the whole iteration loop on the ctx stream: upload of the iterate, cache reset, max_iter x k_iekf
+// (each launch accumulates, and its last block solves and updates the device iterate; launches after
+// convergence return at once), download of the result. No host synchronisation inside.
+static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
+{
+  int r = iekf_stage(ctx, o, which, num_max_iter);
+  if (r) return r;
   IekfBatch bt;
   bt.mode = VN_IEKF_SOLVE;
   bt.variant = 0;
@@ -404,9 +413,9 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it], ctx->stream);
     int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
     if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
+    ctx->launches += 1;
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it + 1], ctx->stream);
   }
-  ctx->dbg_valid = false;
   return vn_check_cuda(ctx, cudaMemcpyAsync(ctx->h_iekf, ctx->d_iekf, sizeof(IekfDev), cudaMemcpyDeviceToHost, ctx->stream),
                        "iterate download");
 }
@@ -488,11 +497,11 @@ static void collect_timings(vina_ctx* ctx)
   cudaEventElapsedTime(&ctx->tm.total_ms, ev[0], ev[7]);
 }
 
-// the scan body of thd_odometry_localmapping (local_mapping.cpp:389-546); the raw scan is on the device
-static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
-                              const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
+// the scan body of thd_odometry_localmapping (local_mapping.cpp:389-546), first part: a1 IMU propagation on
+// the host, then deskew, down-sampling and var_init of the set the IEKF runs on - all enqueued, no sync
+static int step_front(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
+                      int iekf_on_full, int* which_out)
 {
-  const int l0 = ctx->launches;
   o->pcl_beg_time = pcl_beg_time;
   o->pcl_end_time = pcl_end_time;
   int r = imu_propagate(ctx, o, imus, m);
@@ -520,18 +529,23 @@ static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, d
     if (r) return r;
   }
   if (ctx->profiling) cudaEventRecord(ev[3], ctx->stream);
-  int ok = 0;
-  r = lio_state_estimation(ctx, o, which, max_iter, &ok);
-  if (r) return r;
+  *which_out = which;
+  return VINA_OK;
+}
+
+// ... last part, after the IEKF: degeneracy bookkeeping, var_init of the down-sampled set, map update
+static int step_back(vina_ctx* ctx, OdomHost* o, int iekf_on_full, int ok, vina_state* x_out)
+{
   if (ok)
   {
     if (o->degrade_cnt > 0) o->degrade_cnt--;
   }
   else
     o->degrade_cnt++;
+  int r;
   if (iekf_on_full)
   {
-    // the down-sampled count arrived with the IEKF readbacks: no extra sync in the common case
+    // the down-sampled count arrived with the IEKF readback: no extra sync in the common case
     r = vn_finish_downsample(ctx);
     if (r) return r;
     r = vina_var_init(ctx, 1);
@@ -540,8 +554,166 @@ static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, d
   r = map_update(ctx, o);
   if (r) return r;
   if (x_out) *x_out = o->x_curr;
+  return VINA_OK;
+}
+
+static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
+                              const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
+{
+  const int l0 = ctx->launches;
+  int which = 1, ok = 0;
+  int r = step_front(ctx, o, pcl_beg_time, pcl_end_time, imus, m, iekf_on_full, &which);
+  if (r) return r;
+  r = lio_state_estimation(ctx, o, which, max_iter, &ok);
+  if (r) return r;
+  r = step_back(ctx, o, iekf_on_full, ok, x_out);
+  if (r) return r;
   collect_timings(ctx);
   ctx->tm.kernel_launches = ctx->launches - l0;
+  return VINA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Batch replay (BASELINE.json configs[4]: "batch replay of 8 independent synthetic sequences"): B contexts on one
+// GPU advance one scan each per call. Everything per-sequence (deskew ... var_init, map update) runs on the
+// sequence's own stream, concurrently; the IEKF iterations of ALL sequences run as ONE k_iekf launch per
+// iteration (grid = blocks x B, every sequence with its own device iterate, convergence flag and solve), which
+// is what turns the latency-bound single-scan launch into a bandwidth-shaped one.
+struct vina_batch
+{
+  std::vector<vina_ctx*> c;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> ready;
+  cudaEvent_t done = nullptr;
+  std::vector<cudaEvent_t> tev;  // [i], [i+1] bracket the i-th batched launch of the last step
+  int device = 0;
+  int iekf_launches = 0;
+};
+
+extern "C" int vina_batch_create(vina_ctx** ctxs, int n, vina_batch** out)
+{
+  if (!ctxs || !out || n < 1 || n > VN_MAX_BATCH) return VINA_E_ARG;
+  for (int i = 0; i < n; i++)
+    if (!ctxs[i] || ctxs[i]->device != ctxs[0]->device) return VINA_E_ARG;
+  vina_batch* b = new vina_batch();
+  b->c.assign(ctxs, ctxs + n);
+  b->device = ctxs[0]->device;
+  cudaSetDevice(b->device);
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    delete b;
+    return VINA_E_CUDA;
+  }
+  b->ready.resize(n);
+  for (int i = 0; i < n; i++) cudaEventCreateWithFlags(&b->ready[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming);
+  *out = b;
+  return VINA_OK;
+}
+
+extern "C" void vina_batch_destroy(vina_batch* b)
+{
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->stream);
+  for (cudaEvent_t e : b->ready) cudaEventDestroy(e);
+  cudaEventDestroy(b->done);
+  for (cudaEvent_t e : b->tev) cudaEventDestroy(e);
+  cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+extern "C" int vina_batch_step_resident(vina_batch* b, const void* const* d_xyzt, const int32_t* n,
+                                        const double* pcl_beg_time, const double* pcl_end_time,
+                                        const vina_imu* const* imus, const int32_t* m, int iekf_on_full, int max_iter,
+                                        vina_state* x_out)
+{
+  if (!b || !d_xyzt || !n || !pcl_beg_time || !pcl_end_time || !imus || !m) return VINA_E_ARG;
+  const int B = (int)b->c.size();
+  const int num_max_iter = max_iter > 0 ? max_iter : 20;
+  IekfBatch bt;
+  bt.mode = VN_IEKF_SOLVE;
+  bt.variant = 0;
+  // per sequence, on its own stream: scan in, a1 (host), a2, f1, a3, iterate upload, cache reset
+  for (int i = 0; i < B; i++)
+  {
+    vina_ctx* ctx = b->c[i];
+    if (!d_xyzt[i] || !imus[i] || m[i] <= 0 || n[i] <= 0) return VINA_E_ARG;
+    if (n[i] > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points", n[i]);
+    int r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->d_scan, d_xyzt[i], (size_t)n[i] * sizeof(float4),
+                                                cudaMemcpyDeviceToDevice, ctx->stream), "device-to-device scan copy");
+    if (r) return r;
+    ctx->n_scan = n[i];
+    OdomHost* o = odom(ctx);
+    int which = 1;
+    r = step_front(ctx, o, pcl_beg_time[i], pcl_end_time[i], imus[i], m[i], iekf_on_full, &which);
+    if (r) return r;
+    r = iekf_stage(ctx, o, which, num_max_iter);
+    if (r) return r;
+    vn_iekf_fill_seq(ctx, &bt.s[i], false);
+    cudaEventRecord(b->ready[i], ctx->stream);
+    cudaStreamWaitEvent(b->stream, b->ready[i], 0);
+  }
+  // the IEKF of all sequences: one launch per iteration; every sequence gets an equal share of the SMs
+  int blocks = b->c[0]->sm_count / B;
+  if (blocks < 1) blocks = 1;
+  while ((int)b->tev.size() < num_max_iter + 1)
+  {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    b->tev.push_back(e);
+  }
+  cudaEventRecord(b->tev[0], b->stream);
+  for (int it = 0; it < num_max_iter; it++)
+  {
+    int e = launch_iekf(b->stream, bt, B, blocks, false);
+    if (e) return vn_check_cuda(b->c[0], (cudaError_t)e, "batched k_iekf launch");
+    cudaEventRecord(b->tev[it + 1], b->stream);
+  }
+  cudaEventRecord(b->done, b->stream);
+  b->iekf_launches = num_max_iter;
+  for (int i = 0; i < B; i++)
+  {
+    vina_ctx* ctx = b->c[i];
+    ctx->launches += num_max_iter;
+    cudaStreamWaitEvent(ctx->stream, b->done, 0);
+    int r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->h_iekf, ctx->d_iekf, sizeof(IekfDev), cudaMemcpyDeviceToHost, ctx->stream),
+                          "iterate download");
+    if (r) return r;
+  }
+  // per sequence: take the result back, then the map update (asynchronous, on the sequence's stream)
+  for (int i = 0; i < B; i++)
+  {
+    vina_ctx* ctx = b->c[i];
+    OdomHost* o = odom(ctx);
+    int r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "batched IEKF loop");
+    if (r) return r;
+    int ok = 0;
+    unstage_iterate(ctx->h_iekf, o->x_curr, &o->last_iters, &ok);
+    ctx->tm.iekf_iters = o->last_iters;
+    r = step_back(ctx, o, iekf_on_full, ok, x_out ? &x_out[i] : nullptr);
+    if (r) return r;
+  }
+  return VINA_OK;
+}
+
+extern "C" int vina_batch_iekf_time(vina_batch* b, float* ms_per_launch, int cap, int32_t* launches)
+{
+  if (!b || !ms_per_launch || !launches) return VINA_E_ARG;
+  *launches = b->iekf_launches;
+  for (int it = 0; it < b->iekf_launches && it < cap; it++)
+    cudaEventElapsedTime(&ms_per_launch[it], b->tev[it], b->tev[it + 1]);
+  return VINA_OK;
+}
+
+extern "C" int vina_batch_sync(vina_batch* b)
+{
+  if (!b) return VINA_E_ARG;
+  for (vina_ctx* ctx : b->c)
+  {
+    int r = vn_check_status(ctx);
+    if (r) return r;
+  }
   return VINA_OK;
 }
 
