@@ -125,7 +125,8 @@ def _iekf_compare(oracle_lib, gpu_lib, cfg, n_iter=4, world=None):
         m = d["flags"] > 0
         # sigma_l = J plane_var J^T + n^T var n cancels ~7 digits (plane_var carries the lever arm of a
         # centre tens of metres from the origin), so rounding-level differences show up at ~1e-9
-        assert np.max(np.abs(a["sigma"][m] - d["sigma"][m]) / d["sigma"][m]) < 1e-6
+        sig_err = np.abs(a["sigma"][m] - d["sigma"][m]) / d["sigma"][m]
+        assert np.max(sig_err) < 1e-6, (it, float(np.max(sig_err)), int((sig_err > 1e-6).sum()), int(m.sum()))
         assert rel_err(g["HTH"], d["HTH"]) < 1e-4 and rel_err(g["HTz"], d["HTz"]) < 1e-4
         assert rel_err(g["nnt"], d["nnt"]) < 1e-4
         # the design is far tighter than the contract

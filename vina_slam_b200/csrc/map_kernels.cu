@@ -375,8 +375,10 @@ __device__ __forceinline__ void bf_var_terms(const double* v, const double* p, d
 #define ACC_WARPS 3
 __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, ScanView scan, InsertScratch sc, int win_ord)
 {
+  // the Bf_var terms are staged 16 rows at a time: 9.2 KB of shared memory per warp instead of 15.2 KB, which
+  // is what bounds the number of resident warps of this kernel
   __shared__ double pt_s[ACC_WARPS][32][PT_STRIDE];
-  __shared__ double red_s[ACC_WARPS][32][RED_STRIDE];
+  __shared__ double red_s[ACC_WARPS][16][RED_STRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nt = sc.counters[1];
   const int mord = M.mp[win_ord];
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
       __syncwarp();
       if (lane < cnt) idx[rank] = v;
     }
-    else if (cnt <= 32 * RED_STRIDE * 2)
+    else if (cnt <= 16 * RED_STRIDE * 2)
     {
       // rank sort through shared memory (indices are distinct): rank = number of smaller ones
       int* sidx = reinterpret_cast<int*>(&red[0][0]);
@@ -462,34 +464,43 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
     for (int base = 0; base < cnt; base += 32)
     {
       const int a = base + lane;
+      PointRec pr;
+      double pw[3];
       if (a < cnt)
       {
         const int i = idx[a];
-        PointRec pr;
-        double pw[3];
         for (int k = 0; k < 3; k++) pr.p[k] = scan.p[k][i];
         for (int k = 0; k < 6; k++) pr.v[k] = sc.vw[k][i];
         for (int k = 0; k < 3; k++) pw[k] = sc.pw[k][i];
         for (int k = 0; k < 3; k++) pt[lane][k] = pr.p[k];
         for (int k = 0; k < 3; k++) pt[lane][9 + k] = pw[k];
         if (store) M.win_pool[mord][woff + old_cnt + a] = pr;
-        double o[45];
-        bf_var_terms(pr.v, pw, o);
-#pragma unroll
-        for (int e = 0; e < 45; e++) red[lane][e] = o[e];
       }
-      __syncwarp();
       const int m = min(32, cnt - base);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int half = 0; half < 2; half++)
+      {
+        if ((lane >> 4) == half && a < cnt)
+        {
+          double o[45];
+          bf_var_terms(pr.v, pw, o);
+#pragma unroll
+          for (int e = 0; e < 45; e++) red[lane & 15][e] = o[e];
+        }
+        __syncwarp();
+        const int mh = min(16, m - 16 * half);
+        for (int r = 0; r < mh; r++)
+        {
+          s0 += red[r][lane];
+          if (has2) s1 += red[r][lane + 32];
+        }
+        __syncwarp();
+      }
       if (lane < 9)
         for (int r = 0; r < m; r++) cl = cluster_term(L, cl, pt[r] + 9);
       else if (lane < 18)
         for (int r = 0; r < m; r++) cl = cluster_term(L, cl, pt[r]);
-      double s0 = 0.0, s1 = 0.0;
-      for (int r = 0; r < m; r++)
-      {
-        s0 += red[r][lane];
-        if (has2) s1 += red[r][lane + 32];
-      }
       cv0 += s0;
       cv1 += s1;
       __syncwarp();
@@ -614,26 +625,40 @@ __global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, i
 // The subdivision branch of OctoTree::recut (octree.cpp:375-387): fix_divide (:257-277), subdivide per
 // window frame (:279-300), release of the parent's SlideWindow (:384-387). One 128-thread block per
 // splitting leaf. Source classes in the reference's order: class 0 = point_fix, class 1+si =
-// sw->points[mp[si]]. The parent's points are streamed once, 64 at a time; inside a batch the rows of
-// each child are listed in order (stable compaction) and
+// sw->points[mp[si]]. All classes (and all segments of the point_fix chain) form ONE row stream that is
+// consumed 64 rows at a time - a leaf's ~20 short lists cost a handful of batches instead of one batch each.
+// Inside a batch the rows of each child are listed in stream order (stable compaction) and
 //   thread t < 72  owns the cluster scalar s = t % 9 of child k = t / 9 (pcr_add and pcr_fix /
-//                  pcrs_local[slot]) and applies that child's rows sequentially (exact sums, reference order),
+//                  pcrs_local[slot]) and applies that child's rows sequentially (exact sums, reference order;
+//                  the per-class cluster is flushed whenever the class of the next row changes),
 //   every thread   owns up to three (child, cov_add entry) pairs and sums that child's staged Bf_var terms.
 #define SPLIT_THREADS 128
 #define SPLIT_BATCH 64
+#define SPLIT_MAXSEG 48
+struct SplitSeg
+{
+  const PointRec* src;
+  int start;  // stream index of the first row
+  int cnt;
+  int cls;
+};
+
 __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
 {
   __shared__ double pt[SPLIT_BATCH][PT_STRIDE];
   __shared__ double red[SPLIT_BATCH][RED_STRIDE];
+  __shared__ SplitSeg segs[SPLIT_MAXSEG];
   __shared__ int cnt[11][8];
   __shared__ int off[11][8];
+  __shared__ int fill[11][8];
+  __shared__ int cls_first[11];
   __shared__ int kid[8];
-  __shared__ int fill[8];
-  __shared__ int wcount[2][8];
+  __shared__ unsigned int bm[2][8];
+  __shared__ int clsrow[SPLIT_BATCH];
   __shared__ unsigned char rows[8][SPLIT_BATCH];
+  __shared__ int nseg, total, next_cls, next_seg;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
   LaneRole L;
   role_init(t, L);  // L.ck = t % 9
   const int my_k = t / 9;  // cluster chain of this thread (t < 72)
@@ -651,6 +676,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     {
       (&cnt[0][0])[t] = 0;
       (&off[0][0])[t] = -1;
+      (&fill[0][0])[t] = 0;
     }
     __syncthreads();
     // pass 1: how many points of every class go to every child
@@ -712,134 +738,182 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       }
       kid[k] = id;
     }
+    if (t == 8)
+    {
+      next_cls = has_fix ? 0 : 1;
+      next_seg = has_fix ? c.fix_head : -1;
+    }
     __syncthreads();
 
     // running sums (children are new: they start from zero)
     double clA = 0.0, clB = 0.0;  // thread t < 72: scalar L.ck of child my_k
+    int cur_cls = -1;             // class clB currently accumulates
     double cv[3] = { 0.0, 0.0, 0.0 };  // pairs p = t + 128 q < 360: child p / 45, entry p % 45
 
-    // pass 2: stream the classes in order
-    for (int cls = 0; cls <= win_count; cls++)
+    // pass 2: the row stream, one table of up to SPLIT_MAXSEG segments at a time
+    for (;;)
     {
-      const bool is_fix = cls == 0;
-      if (is_fix && !has_fix) continue;
-      const int si = cls - 1;
-      const int slot = is_fix ? 0 : M.mp[si];
-      int seg_id = is_fix ? c.fix_head : 0;
-      clB = 0.0;
-      if (t < 8) fill[t] = 0;
-      __syncthreads();
-      while (seg_id >= 0)
+      if (t == 0)
       {
-        int np, next_seg;
-        const PointRec* src;
-        if (is_fix)
+        int ns = 0, tot = 0, cls = next_cls, sg = next_seg;
+        for (int q = 0; q < 11; q++) cls_first[q] = -1;
+        while (cls <= win_count && ns < SPLIT_MAXSEG)
         {
-          const FixSeg seg = M.fix_segs[seg_id];
-          np = seg.cnt;
-          src = M.fix_pool + seg.off;
-          next_seg = seg.next;
-        }
-        else
-        {
-          np = c.win_cnt[slot];
-          src = M.win_pool[slot] + c.win_off[slot];
-          next_seg = -1;
-        }
-        for (int base = 0; base < np; base += SPLIT_BATCH)
-        {
-          const int m = min(SPLIT_BATCH, np - base);
-          int kk = -1;
-          PointRec pr;
-          if (t < SPLIT_BATCH)
+          if (cls == 0)
           {
-            const int a = base + t;
-            if (a < np)
+            if (sg < 0)
             {
-              double pw[3];
-              pr = src[a];
-              if (is_fix)
+              cls = 1;
+              continue;
+            }
+            const FixSeg seg = M.fix_segs[sg];
+            if (seg.cnt > 0)
+            {
+              if (cls_first[0] < 0) cls_first[0] = tot;
+              segs[ns].src = M.fix_pool + seg.off;
+              segs[ns].start = tot;
+              segs[ns].cnt = seg.cnt;
+              segs[ns].cls = 0;
+              tot += seg.cnt;
+              ns++;
+            }
+            sg = seg.next;
+          }
+          else
+          {
+            const int slot = M.mp[cls - 1];
+            const int np = c.win_cnt[slot];
+            if (np > 0)
+            {
+              cls_first[cls] = tot;
+              segs[ns].src = M.win_pool[slot] + c.win_off[slot];
+              segs[ns].start = tot;
+              segs[ns].cnt = np;
+              segs[ns].cls = cls;
+              tot += np;
+              ns++;
+            }
+            cls++;
+          }
+        }
+        nseg = ns;
+        total = tot;
+        next_cls = cls;
+        next_seg = sg;
+      }
+      __syncthreads();
+      const int ns = nseg, tot = total;
+      const bool last_table = next_cls > win_count;
+      if (ns == 0) break;
+      for (int base = 0; base < tot; base += SPLIT_BATCH)
+      {
+        const int m = min(SPLIT_BATCH, tot - base);
+        int kk = -1, cls = 0;
+        PointRec pr;
+        if (t < SPLIT_BATCH)
+        {
+          const int g = base + t;
+          if (g < tot)
+          {
+            int sgi = 0;
+            while (sgi + 1 < ns && segs[sgi + 1].start <= g) sgi++;
+            cls = segs[sgi].cls;
+            pr = segs[sgi].src[g - segs[sgi].start];
+            double pw[3];
+            if (cls == 0)
+            {
+              pw[0] = pr.p[0];
+              pw[1] = pr.p[1];
+              pw[2] = pr.p[2];
+            }
+            else
+              rot_trans(xb.x[cls - 1].R, xb.x[cls - 1].p, pr.p, pw);
+            kk = child_index(pw, vc);
+            for (int q = 0; q < 3; q++) pt[t][q] = pr.p[q];
+            for (int q = 0; q < 3; q++) pt[t][9 + q] = pw[q];
+            double o[45];
+            bf_var_terms(pr.v, pw, o);
+#pragma unroll
+            for (int e = 0; e < 45; e++) red[t][e] = o[e];
+            clsrow[t] = cls;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+          {
+            const unsigned mask = __ballot_sync(0xffffffffu, kk == k);
+            if (lane == 0) bm[warp][k] = mask;
+          }
+        }
+        __syncthreads();
+        if (t < SPLIT_BATCH && kk >= 0)
+        {
+          // stable rank of the row inside its child: over the whole batch, and over the rows of its own class
+          const unsigned long long mk = (unsigned long long)bm[0][kk] | ((unsigned long long)bm[1][kk] << 32);
+          const unsigned long long below = (1ull << t) - 1ull;
+          const int cs = cls_first[cls] - base;  // batch-local index of the first row of this class
+          const unsigned long long from = cs <= 0 ? ~0ull : ~((1ull << cs) - 1ull);
+          rows[kk][__popcll(mk & below)] = (unsigned char)t;
+          if (off[cls][kk] >= 0)
+          {
+            const int dst = off[cls][kk] + fill[cls][kk] + __popcll(mk & below & from);
+            if (cls == 0)
+              M.fix_pool[dst] = pr;
+            else
+              M.win_pool[M.mp[cls - 1]][dst] = pr;
+          }
+        }
+        __syncthreads();
+        // push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows
+        if (t < 72)
+        {
+          const int mk = __popc(bm[0][my_k]) + (m > 32 ? __popc(bm[1][my_k]) : 0);
+          for (int i = 0; i < mk; i++)
+          {
+            const int r = rows[my_k][i];
+            const int rc = clsrow[r];
+            if (rc != cur_cls)
+            {
+              // the per-class cluster (pcr_fix or pcrs_local[slot]) of the finished class is complete
+              if (cur_cls >= 0 && kid[my_k] >= 0)
               {
-                pw[0] = pr.p[0];
-                pw[1] = pr.p[1];
-                pw[2] = pr.p[2];
+                NodeCold& kc = M.cold[kid[my_k]];
+                Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
+                cluster_set(dst, L.ck, clB);
+                if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
               }
-              else
-                rot_trans(xb.x[si].R, xb.x[si].p, pr.p, pw);
-              kk = child_index(pw, vc);
-              for (int q = 0; q < 3; q++) pt[t][q] = pr.p[q];
-              for (int q = 0; q < 3; q++) pt[t][9 + q] = pw[q];
-              double o[45];
-              bf_var_terms(pr.v, pw, o);
-#pragma unroll
-              for (int e = 0; e < 45; e++) red[t][e] = o[e];
+              cur_cls = rc;
+              clB = 0.0;
             }
-            // stable rank of the row inside its child, first within the warp ...
-            int myrank = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-            {
-              const unsigned mask = __ballot_sync(0xffffffffu, kk == k);
-              if (kk == k) myrank = __popc(mask & lt_mask);
-              if (lane == 0) wcount[warp][k] = __popc(mask);
-            }
-            // (the two staging warps meet at the block barrier below)
-            pt[t][12] = (double)myrank;
+            const double* q = pt[r];
+            clA = cluster_term(L, clA, q + 9);
+            clB = cluster_term(L, clB, q);
           }
-          __syncthreads();
-          if (t < SPLIT_BATCH && kk >= 0)
-          {
-            // ... then across the two staging warps (rows 0..31 precede rows 32..63)
-            const int rank = (int)pt[t][12] + (warp == 1 ? wcount[0][kk] : 0);
-            rows[kk][rank] = (unsigned char)t;
-            if (off[cls][kk] >= 0)
-            {
-              const int dst = off[cls][kk] + fill[kk] + rank;
-              if (is_fix)
-                M.fix_pool[dst] = pr;
-              else
-                M.win_pool[slot][dst] = pr;
-            }
-          }
-          __syncthreads();
-          // push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows
-          if (t < 72)
-          {
-            const int mk = wcount[0][my_k] + (m > 32 ? wcount[1][my_k] : 0);
-            for (int i = 0; i < mk; i++)
-            {
-              const double* q = pt[rows[my_k][i]];
-              clA = cluster_term(L, clA, q + 9);
-              clB = cluster_term(L, clB, q);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 3; q++)
-          {
-            const int p = t + SPLIT_THREADS * q;
-            if (p < 360)
-            {
-              const int k = p / 45, e = p % 45;
-              const int mk = wcount[0][k] + (m > 32 ? wcount[1][k] : 0);
-              double s = 0.0;
-              for (int i = 0; i < mk; i++) s += red[rows[k][i]][e];
-              cv[q] += s;
-            }
-          }
-          __syncthreads();
-          if (t < 8) fill[t] += wcount[0][t] + (m > 32 ? wcount[1][t] : 0);
         }
-        seg_id = next_seg;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+        {
+          const int p = t + SPLIT_THREADS * q;
+          if (p < 360)
+          {
+            const int k = p / 45, e = p % 45;
+            const int mk = __popc(bm[0][k]) + (m > 32 ? __popc(bm[1][k]) : 0);
+            double s = 0.0;
+            for (int i = 0; i < mk; i++) s += red[rows[k][i]][e];
+            cv[q] += s;
+          }
+        }
+        if (t < SPLIT_BATCH && kk >= 0) atomicAdd(&fill[cls][kk], 1);
+        __syncthreads();
       }
-      // end of class: pcr_fix (class 0) or the per-frame local cluster of every child is complete
-      if (t < 72 && kid[my_k] >= 0 && cnt[cls][my_k] > 0)
-      {
-        NodeCold& kc = M.cold[kid[my_k]];
-        Cluster& dst = is_fix ? kc.pcr_fix : kc.pcrs_local[slot];
-        cluster_set(dst, L.ck, clB);
-        if (L.ck == 0) dst.N += cnt[cls][my_k];
-      }
-      __syncthreads();
+      if (last_table) break;
+    }
+    // last class of every chain
+    if (t < 72 && cur_cls >= 0 && kid[my_k] >= 0)
+    {
+      NodeCold& kc = M.cold[kid[my_k]];
+      Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
+      cluster_set(dst, L.ck, clB);
+      if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
     }
     // children's pcr_add / cov_add
     if (t < 72 && kid[my_k] >= 0)

@@ -216,6 +216,7 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&ctx->layers.split, (size_t)cfg.max_nodes));
   CU(dalloc(&ctx->layers.count, 8));
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaDeviceSynchronize());  // the zero-fills of dalloc ran on the legacy stream (see ensure_debug)
   CU(cudaGetLastError());
   return VINA_OK;
 }
@@ -537,6 +538,9 @@ static int ensure_debug(vina_ctx* ctx)
   CU(dalloc(&ctx->dbg.codes, cap));
   CU(dalloc(&ctx->dbg.flags, cap));
   CU(dalloc(&ctx->dbg.sigma, cap));
+  // dalloc's cudaMemset runs on the legacy default stream, which the ctx stream (cudaStreamNonBlocking) does
+  // not wait for: without this a kernel launched right away can be overtaken by the zero-fill of its output
+  CU(cudaDeviceSynchronize());
   return VINA_OK;
 }
 
@@ -768,6 +772,7 @@ static int ensure_shard(vina_ctx* ctx)
   CU(dalloc(&ctx->d_sh_hist, (cap / 256 + 2) * VINA_MAX_WORLD));
   CU(dalloc(&ctx->d_sh_counts, 2 * VINA_MAX_WORLD + 2));
   CU(cudaHostAlloc((void**)&ctx->h_sh_counts, (2 * VINA_MAX_WORLD + 2) * sizeof(int), cudaHostAllocDefault));
+  CU(cudaDeviceSynchronize());  // see ensure_debug
   return VINA_OK;
 }
 
