@@ -373,18 +373,21 @@ __device__ __forceinline__ void bf_var_terms(const double* v, const double* p, d
 // sequential exact sums. cov_add: every lane computes the 45 Bf_var terms of one staged point, the warp
 // then sums the columns (lane owns packed entries `lane` and `lane + 32`).
 #define ACC_WARPS 3
+#define ACC_PT_STRIDE 19
+#define ACC_RED_ROWS 8
 __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, ScanView scan, InsertScratch sc, int win_ord)
 {
-  // the Bf_var terms are staged 16 rows at a time: 9.2 KB of shared memory per warp instead of 15.2 KB, which
-  // is what bounds the number of resident warps of this kernel
-  __shared__ double pt_s[ACC_WARPS][32][PT_STRIDE];
-  __shared__ double red_s[ACC_WARPS][16][RED_STRIDE];
+  // shared memory per warp bounds the number of resident warps of this kernel: the Bf_var terms are staged
+  // 8 rows at a time (3 KB); per row the 9 + 9 products of PointCluster::push (types.hpp:137-142) for the world
+  // and the body point are formed by the row's lane, so that the sequential chains only add (4.8 KB)
+  __shared__ double pt_s[ACC_WARPS][32][ACC_PT_STRIDE];
+  __shared__ double red_s[ACC_WARPS][ACC_RED_ROWS][RED_STRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nt = sc.counters[1];
   const int mord = M.mp[win_ord];
   LaneRole L;
   role_init(lane, L);
-  double(*pt)[PT_STRIDE] = pt_s[warp];
+  double(*pt)[ACC_PT_STRIDE] = pt_s[warp];
   double(*red)[RED_STRIDE] = red_s[warp];
   const bool has2 = lane + 32 < 45;
 
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
       __syncwarp();
       if (lane < cnt) idx[rank] = v;
     }
-    else if (cnt <= 16 * RED_STRIDE * 2)
+    else if (cnt <= ACC_RED_ROWS * RED_STRIDE * 2)
     {
       // rank sort through shared memory (indices are distinct): rank = number of smaller ones
       int* sidx = reinterpret_cast<int*>(&red[0][0]);
@@ -472,24 +475,39 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
         for (int k = 0; k < 3; k++) pr.p[k] = scan.p[k][i];
         for (int k = 0; k < 6; k++) pr.v[k] = sc.vw[k][i];
         for (int k = 0; k < 3; k++) pw[k] = sc.pw[k][i];
-        for (int k = 0; k < 3; k++) pt[lane][k] = pr.p[k];
-        for (int k = 0; k < 3; k++) pt[lane][9 + k] = pw[k];
+        const double* s3[2] = { pw, pr.p };
+#pragma unroll
+        for (int w = 0; w < 2; w++)
+        {
+          const double* q = s3[w];
+          double* v = pt[lane] + 9 * w;
+          v[0] = dm(q[0], q[0]);
+          v[1] = dm(q[1], q[0]);
+          v[2] = dm(q[2], q[0]);
+          v[3] = dm(q[1], q[1]);
+          v[4] = dm(q[2], q[1]);
+          v[5] = dm(q[2], q[2]);
+          v[6] = q[0];
+          v[7] = q[1];
+          v[8] = q[2];
+        }
         if (store) M.win_pool[mord][woff + old_cnt + a] = pr;
       }
       const int m = min(32, cnt - base);
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int half = 0; half < 2; half++)
+      for (int part = 0; part < 32 / ACC_RED_ROWS; part++)
       {
-        if ((lane >> 4) == half && a < cnt)
+        if (part * ACC_RED_ROWS >= m) break;  // (uniform)
+        if ((lane / ACC_RED_ROWS) == part && a < cnt)
         {
           double o[45];
           bf_var_terms(pr.v, pw, o);
 #pragma unroll
-          for (int e = 0; e < 45; e++) red[lane & 15][e] = o[e];
+          for (int e = 0; e < 45; e++) red[lane % ACC_RED_ROWS][e] = o[e];
         }
         __syncwarp();
-        const int mh = min(16, m - 16 * half);
+        const int mh = min(ACC_RED_ROWS, m - ACC_RED_ROWS * part);
         for (int r = 0; r < mh; r++)
         {
           s0 += red[r][lane];
@@ -497,10 +515,12 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
         }
         __syncwarp();
       }
-      if (lane < 9)
-        for (int r = 0; r < m; r++) cl = cluster_term(L, cl, pt[r] + 9);
-      else if (lane < 18)
-        for (int r = 0; r < m; r++) cl = cluster_term(L, cl, pt[r]);
+      // lanes 0..8: pcr_add (world point), lanes 9..17: pcrs_local[slot] (body point); L.ck = lane % 9
+      if (lane < 18)
+      {
+        const int col = lane;  // 0..8 world terms, 9..17 body terms
+        for (int r = 0; r < m; r++) cl = da(cl, pt[r][col]);
+      }
       cv0 += s0;
       cv1 += s1;
       __syncwarp();
@@ -645,9 +665,10 @@ struct SplitSeg
 
 __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
 {
-  __shared__ double pt[SPLIT_BATCH][PT_STRIDE];
+  __shared__ double val[SPLIT_BATCH][19];  // per row: the 9 push() terms of the world point, then of the stored point
   __shared__ double red[SPLIT_BATCH][RED_STRIDE];
   __shared__ SplitSeg segs[SPLIT_MAXSEG];
+  __shared__ int cbase[9];  // first slot of every child in the child-major row order of the batch
   __shared__ int cnt[11][8];
   __shared__ int off[11][8];
   __shared__ int fill[11][8];
@@ -655,7 +676,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   __shared__ int kid[8];
   __shared__ unsigned int bm[2][8];
   __shared__ int clsrow[SPLIT_BATCH];
-  __shared__ unsigned char rows[8][SPLIT_BATCH];
   __shared__ int nseg, total, next_cls, next_seg;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -807,9 +827,10 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       if (ns == 0) break;
       for (int base = 0; base < tot; base += SPLIT_BATCH)
       {
-        const int m = min(SPLIT_BATCH, tot - base);
+        // phase 1 (rows in stream order): load, world position, child index
         int kk = -1, cls = 0;
         PointRec pr;
+        double pw[3] = { 0.0, 0.0, 0.0 };
         if (t < SPLIT_BATCH)
         {
           const int g = base + t;
@@ -819,7 +840,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
             while (sgi + 1 < ns && segs[sgi + 1].start <= g) sgi++;
             cls = segs[sgi].cls;
             pr = segs[sgi].src[g - segs[sgi].start];
-            double pw[3];
             if (cls == 0)
             {
               pw[0] = pr.p[0];
@@ -829,13 +849,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
             else
               rot_trans(xb.x[cls - 1].R, xb.x[cls - 1].p, pr.p, pw);
             kk = child_index(pw, vc);
-            for (int q = 0; q < 3; q++) pt[t][q] = pr.p[q];
-            for (int q = 0; q < 3; q++) pt[t][9 + q] = pw[q];
-            double o[45];
-            bf_var_terms(pr.v, pw, o);
-#pragma unroll
-            for (int e = 0; e < 45; e++) red[t][e] = o[e];
-            clsrow[t] = cls;
           }
 #pragma unroll
           for (int k = 0; k < 8; k++)
@@ -845,14 +858,45 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           }
         }
         __syncthreads();
+        // phase 2: every row goes to its slot in child-major order (stable: stream order inside a child), so
+        // that the sequential consumers below read contiguous rows; the products of PointCluster::push
+        // (types.hpp:137-142) are formed here, in parallel - the chains only add
+        if (t < 8)
+        {
+          int o = 0;
+          for (int k = 0; k < t; k++) o += __popc(bm[0][k]) + __popc(bm[1][k]);
+          cbase[t] = o;
+          if (t == 7) cbase[8] = o + __popc(bm[0][7]) + __popc(bm[1][7]);
+        }
         if (t < SPLIT_BATCH && kk >= 0)
         {
-          // stable rank of the row inside its child: over the whole batch, and over the rows of its own class
           const unsigned long long mk = (unsigned long long)bm[0][kk] | ((unsigned long long)bm[1][kk] << 32);
           const unsigned long long below = (1ull << t) - 1ull;
           const int cs = cls_first[cls] - base;  // batch-local index of the first row of this class
           const unsigned long long from = cs <= 0 ? ~0ull : ~((1ull << cs) - 1ull);
-          rows[kk][__popcll(mk & below)] = (unsigned char)t;
+          int slot = __popcll(mk & below);
+          for (int k = 0; k < kk; k++) slot += __popc(bm[0][k]) + __popc(bm[1][k]);
+          const double* s3[2] = { pw, pr.p };
+#pragma unroll
+          for (int w = 0; w < 2; w++)
+          {
+            const double* q = s3[w];
+            double* v = val[slot] + 9 * w;
+            v[0] = dm(q[0], q[0]);
+            v[1] = dm(q[1], q[0]);
+            v[2] = dm(q[2], q[0]);
+            v[3] = dm(q[1], q[1]);
+            v[4] = dm(q[2], q[1]);
+            v[5] = dm(q[2], q[2]);
+            v[6] = q[0];
+            v[7] = q[1];
+            v[8] = q[2];
+          }
+          clsrow[slot] = cls;
+          double o[45];
+          bf_var_terms(pr.v, pw, o);
+#pragma unroll
+          for (int e = 0; e < 45; e++) red[slot][e] = o[e];
           if (off[cls][kk] >= 0)
           {
             const int dst = off[cls][kk] + fill[cls][kk] + __popcll(mk & below & from);
@@ -863,13 +907,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           }
         }
         __syncthreads();
-        // push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows
+        // phase 3: push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows
         if (t < 72)
         {
-          const int mk = __popc(bm[0][my_k]) + (m > 32 ? __popc(bm[1][my_k]) : 0);
-          for (int i = 0; i < mk; i++)
+          const int r0 = cbase[my_k], r1 = cbase[my_k + 1];
+          for (int r = r0; r < r1; r++)
           {
-            const int r = rows[my_k][i];
             const int rc = clsrow[r];
             if (rc != cur_cls)
             {
@@ -884,9 +927,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
               cur_cls = rc;
               clB = 0.0;
             }
-            const double* q = pt[r];
-            clA = cluster_term(L, clA, q + 9);
-            clB = cluster_term(L, clB, q);
+            clA = da(clA, val[r][L.ck]);
+            clB = da(clB, val[r][9 + L.ck]);
           }
         }
 #pragma unroll
@@ -896,9 +938,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           if (p < 360)
           {
             const int k = p / 45, e = p % 45;
-            const int mk = __popc(bm[0][k]) + (m > 32 ? __popc(bm[1][k]) : 0);
+            const int r0 = cbase[k], r1 = cbase[k + 1];
             double s = 0.0;
-            for (int i = 0; i < mk; i++) s += red[rows[k][i]][e];
+            for (int r = r0; r < r1; r++) s += red[r][e];
             cv[q] += s;
           }
         }
