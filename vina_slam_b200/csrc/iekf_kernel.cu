@@ -132,9 +132,13 @@ __device__ void so3_log(const double* R, double* w)
   for (int i = 0; i < 3; i++) w[i] = f * K[i];
 }
 
-// The update of one iteration (odometry.cpp:192-230, types.hpp:67-86). fin = the 34 packed sums (shared
-// memory), ws = >= 360 doubles of shared scratch. Executed by ONE warp.
-__device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, double* ws, int lane)
+// The update of one iteration (odometry.cpp:192-230, types.hpp:67-86). fin = the 34 packed sums, ws = >= 376
+// doubles of scratch, cov = the 15x15 prior covariance (replaced by the posterior when the loop ends), st = the
+// first 42 doubles of IekfDev (x_curr: R p v bg ba, then x_prop) - all in SHARED memory, staged and written
+// back by the whole block, so that this single warp never waits on a global load. Returns (to lane 0's
+// callers via ws) whether the loop is finished.
+__device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, double* ws, double* cov, double* st,
+                                             int lane)
 {
   double* HTH = ws;        // 6x6 column-major (symmetric)
   double* HTz = ws + 36;   // 6
@@ -144,6 +148,8 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
   double* sol = ws + 256;
   double* C6 = ws + 272;   // rows 0..5 of the prior covariance, 6x15 (row a, column j at a + 6 j)
   int* flg = reinterpret_cast<int*>(ws + 368);
+  double *R = st, *p = st + 9, *v = st + 12, *bg = st + 15, *ba = st + 18;
+  const double *Rp = st + 21, *pp = st + 30, *vp = st + 33, *bgp = st + 36, *bap = st + 39;
   const int iter = dev->iter, max_iter = dev->max_iter;
 
   {
@@ -163,14 +169,14 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
 #pragma unroll
   for (int i = 0; i < 6; i++)
   {
-    double v = (lane - 6 == i) ? 1.0 : 0.0;
+    double x = (lane - 6 == i) ? 1.0 : 0.0;
     if (lane < 6)
     {
-      v = (lane == i) ? 1.0 : 0.0;
+      x = (lane == i) ? 1.0 : 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; k++) v = fma(HTH[i + 6 * k], dev->cov[k + 15 * lane], v);
+      for (int k = 0; k < 6; k++) x = fma(HTH[i + 6 * k], cov[k + 15 * lane], x);
     }
-    c[i] = v;
+    c[i] = x;
   }
   warp_inverse6(c, lane);
   double* T6 = C6;  // scratch until the final covariance update
@@ -183,7 +189,7 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
     const int i = e % 15, a = e / 15;
     double s = 0.0;
 #pragma unroll
-    for (int b = 0; b < 6; b++) s = fma(dev->cov[i + 15 * b], T6[b + 6 * a], s);
+    for (int b = 0; b < 6; b++) s = fma(cov[i + 15 * b], T6[b + 6 * a], s);
     K6[e] = s;
   }
   // vec = x_prop (-) x_curr (types.hpp:77-86)
@@ -191,15 +197,15 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
   {
     double Rt[9], M[9];
     for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) Rt[j + 3 * i] = dev->R[i + 3 * j];
-    mat3_mul(Rt, dev->Rp, M);
+      for (int j = 0; j < 3; j++) Rt[j + 3 * i] = R[i + 3 * j];
+    mat3_mul(Rt, Rp, M);
     so3_log(M, vec);
     for (int k = 0; k < 3; k++)
     {
-      vec[3 + k] = dev->pp[k] - dev->p[k];
-      vec[6 + k] = dev->vp[k] - dev->v[k];
-      vec[9 + k] = dev->bgp[k] - dev->bg[k];
-      vec[12 + k] = dev->bap[k] - dev->ba[k];
+      vec[3 + k] = pp[k] - p[k];
+      vec[6 + k] = vp[k] - v[k];
+      vec[9 + k] = bgp[k] - bg[k];
+      vec[12 + k] = bap[k] - ba[k];
     }
   }
   __syncwarp();
@@ -231,14 +237,14 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
     // x_curr (+)= solution (types.hpp:67-75)
     double E[9], Rn[9];
     so3_exp(sol, E);
-    mat3_mul(dev->R, E, Rn);
-    for (int i = 0; i < 9; i++) dev->R[i] = Rn[i];
+    mat3_mul(R, E, Rn);
+    for (int i = 0; i < 9; i++) R[i] = Rn[i];
     for (int k = 0; k < 3; k++)
     {
-      dev->p[k] += sol[3 + k];
-      dev->v[k] += sol[6 + k];
-      dev->bg[k] += sol[9 + k];
-      dev->ba[k] += sol[12 + k];
+      p[k] += sol[3 + k];
+      v[k] += sol[6 + k];
+      bg[k] += sol[9 + k];
+      ba[k] += sol[12 + k];
     }
     const double nr = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
     const double nt = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
@@ -255,7 +261,7 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
   if (flg[0])
   {
     // cov = (I - G) cov; only the first 6 columns of G are non-zero (odometry.cpp:223)
-    for (int e = lane; e < 90; e += 32) C6[e] = dev->cov[(e % 6) + 15 * (e / 6)];
+    for (int e = lane; e < 90; e += 32) C6[e] = cov[(e % 6) + 15 * (e / 6)];
     __syncwarp();
     for (int e = lane; e < 225; e += 32)
     {
@@ -263,7 +269,7 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
       double s = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; a++) s = fma(G6[i + 15 * a], C6[a + 6 * j], s);
-      dev->cov[e] = dev->cov[e] - s;
+      cov[e] = cov[e] - s;
     }
   }
 }
@@ -562,7 +568,18 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
   if (threadIdx.x == 0) *q.ticket = 0u;
   if (bt.mode & VN_IEKF_SOLVE)
   {
-    if (warp == 0) iekf_solve_warp(dev, fin, smem, lane);
+    // stage the iterate in shared memory with the whole block, let one warp solve, write back
+    double* ws = smem;
+    double* s_cov = smem + 384;
+    double* s_st = smem + 384 + 232;
+    for (int i = threadIdx.x; i < 225; i += IEKF_THREADS) s_cov[i] = dev->cov[i];
+    if (threadIdx.x < 42) s_st[threadIdx.x] = reinterpret_cast<const double*>(dev)[threadIdx.x];
+    __syncthreads();
+    if (warp == 0) iekf_solve_warp(dev, fin, ws, s_cov, s_st, lane);
+    __syncthreads();
+    if (threadIdx.x < 21) reinterpret_cast<double*>(dev)[threadIdx.x] = s_st[threadIdx.x];
+    if (reinterpret_cast<const int*>(ws + 368)[0])
+      for (int i = threadIdx.x; i < 225; i += IEKF_THREADS) dev->cov[i] = s_cov[i];
   }
   if (bt.mode & VN_IEKF_PUBLISH)
   {
@@ -576,6 +593,26 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
     __syncthreads();
     if (threadIdx.x == 0) reinterpret_cast<volatile unsigned long long*>(q.result)[40] = q.seq;
   }
+}
+
+// Hand the converged iterate to the host through mapped pinned memory: the data first, then (after a
+// system-wide fence) the sequence number the host polls - a few microseconds instead of the wake-up latency of
+// a stream synchronisation, and the host can enqueue the map update right away.
+__global__ void __launch_bounds__(256) k_publish_iterate(const IekfDev* __restrict__ src, IekfDev* __restrict__ dst,
+                                                         volatile unsigned long long* flag, unsigned long long seq)
+{
+  const double* s = reinterpret_cast<const double*>(src);
+  double* d = reinterpret_cast<double*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(IekfDev) / sizeof(double)); i += blockDim.x) d[i] = s[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *flag = seq;
+}
+
+void launch_publish_iterate(cudaStream_t st, const IekfDev* src, IekfDev* dst_mapped, unsigned long long* flag_mapped,
+                            unsigned long long seq)
+{
+  k_publish_iterate<<<1, 256, 0, st>>>(src, dst_mapped, flag_mapped, seq);
 }
 
 __global__ void k_fill_int(int* p, int v, int n)

@@ -160,6 +160,12 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&ctx->d_iekf, 1));
   CU(cudaHostAlloc((void**)&ctx->h_iekf, sizeof(IekfDev), cudaHostAllocDefault));
   memset(ctx->h_iekf, 0, sizeof(IekfDev));
+  CU(cudaHostAlloc((void**)&ctx->h_pub, sizeof(IekfDev), cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_pub, ctx->h_pub, 0));
+  CU(cudaHostAlloc((void**)&ctx->h_pub_flag, 64, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_pub_flag, ctx->h_pub_flag, 0));
+  *ctx->h_pub_flag = 0ull;
+  CU(cudaEventCreateWithFlags(&ctx->ev_poses, cudaEventDisableTiming));
   CU(dalloc(&ctx->d_status, 1));
   CU(cudaHostAlloc((void**)&ctx->h_status, sizeof(int), cudaHostAllocDefault));
 
@@ -245,6 +251,9 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFreeHost(ctx->h_result);
   cudaFree(ctx->d_iekf);
   cudaFreeHost(ctx->h_iekf);
+  cudaFreeHost(ctx->h_pub);
+  cudaFreeHost(ctx->h_pub_flag);
+  if (ctx->ev_poses) cudaEventDestroy(ctx->ev_poses);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   cudaFree(ctx->d_sh_owner);
@@ -331,8 +340,8 @@ extern "C" int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, con
 {
   if (!ctx || !poses || m < 0 || !R_end || !p_end) return VINA_E_ARG;
   if (m > VINA_MAX_POSES) return vn_fail(ctx, VINA_E_CAPACITY, "%d IMU poses > VINA_MAX_POSES", m);
-  // the pinned staging buffer may still be in flight from the previous scan
-  CU(cudaStreamSynchronize(ctx->stream));
+  // the pinned staging buffer may still be in flight from the previous scan (never in steady state)
+  if (ctx->poses_in_flight) CU(cudaEventSynchronize(ctx->ev_poses));
   DeskewPoses* P = ctx->h_poses;
   P->m = m;
   memcpy(P->pose, poses, (size_t)m * sizeof(vina_imu_pose));
@@ -341,6 +350,8 @@ extern "C" int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, con
   memcpy(P->ext_R, ctx->cfg.ext_R, 72);
   memcpy(P->ext_t, ctx->cfg.ext_t, 24);
   CU(cudaMemcpyAsync(ctx->d_poses, P, sizeof(DeskewPoses), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_poses, ctx->stream));
+  ctx->poses_in_flight = true;
   launch_deskew(ctx->stream, ctx->d_scan, ctx->n_scan, ctx->d_poses, ctx->d_status);
   ctx->launches += 1;
   return VINA_OK;
@@ -586,6 +597,36 @@ int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool deb
   if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
   ctx->dbg_valid = debug;
   ctx->launches += 1;
+  return VINA_OK;
+}
+
+int vn_iterate_publish(vina_ctx* ctx, cudaStream_t st)
+{
+  launch_publish_iterate(st, ctx->d_iekf, ctx->d_pub, ctx->d_pub_flag, ++ctx->pub_seq);
+  ctx->launches += 1;
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_publish_iterate");
+}
+
+int vn_iterate_wait(vina_ctx* ctx)
+{
+  volatile unsigned long long* flag = ctx->h_pub_flag;
+  const unsigned long long want = ctx->pub_seq;
+  for (long spins = 0; *flag != want; spins++)
+  {
+    if ((spins & 0xfff) == 0xfff)
+    {
+      // a kernel may have failed: fall back to the stream state
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaSuccess)
+      {
+        if (*flag == want) break;
+        // (the publishing kernel may run on another stream - batch replay - so "idle" is not an error by itself)
+        continue;
+      }
+      if (e != cudaErrorNotReady) return vn_check_cuda(ctx, e, "IEKF loop");
+    }
+  }
+  __sync_synchronize();
   return VINA_OK;
 }
 

@@ -46,7 +46,14 @@ struct vina_ctx
   double* h_result = nullptr;  // pinned + mapped; the kernel's last block writes it
   double* d_result = nullptr;  // device alias of h_result
   IekfDev* d_iekf = nullptr;   // device-resident iterate (state, covariance, flags)
-  IekfDev* h_iekf = nullptr;   // pinned staging / readback copy
+  IekfDev* h_iekf = nullptr;   // pinned staging of the upload
+  IekfDev* h_pub = nullptr;    // mapped pinned: the converged iterate as published by k_publish_iterate
+  IekfDev* d_pub = nullptr;    // device alias of h_pub
+  unsigned long long* h_pub_flag = nullptr;  // mapped pinned sequence number, written after the data
+  unsigned long long* d_pub_flag = nullptr;
+  unsigned long long pub_seq = 0;
+  cudaEvent_t ev_poses = nullptr;  // the pose-table staging buffer has been consumed
+  bool poses_in_flight = false;
   IekfDebug dbg = { nullptr, nullptr, nullptr, nullptr };
   bool dbg_valid = false;
   // map
@@ -79,6 +86,9 @@ int vn_check_cuda(vina_ctx* c, cudaError_t e, const char* what);
 int vn_check_status(vina_ctx* c);
 // wait for the sums of the last k_iekf launch (polls the sequence number in mapped memory)
 int vn_iekf_wait(vina_ctx* c);
+// enqueue the hand-over of the device iterate to the host / wait for it (polls the mapped sequence number)
+int vn_iterate_publish(vina_ctx* c, cudaStream_t st);
+int vn_iterate_wait(vina_ctx* c);
 // fill the launch descriptor of this context's sequence (R/p come from c->d_iekf)
 void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 void odom_host_destroy(OdomHost* o);

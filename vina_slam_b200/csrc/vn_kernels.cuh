@@ -1,5 +1,6 @@
 // Launcher prototypes and small parameter blocks shared by the kernel TUs and the context.
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include "vn_math.cuh"
 #include "vn_types.cuh"
@@ -87,6 +88,11 @@ int iekf_grid_blocks(int n, int sm_count);
 // grid = (blocks, nseq); every sequence gets `blocks` persistent 1024-thread blocks
 int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug);
 void launch_fill_int(cudaStream_t st, int* p, int v, int n);
+static_assert(sizeof(IekfDev) % sizeof(double) == 0, "IekfDev is copied as doubles");
+static_assert(offsetof(IekfDev, Rp) == 21 * sizeof(double) && offsetof(IekfDev, cov) == 42 * sizeof(double),
+              "k_iekf stages x_curr / x_prop as the first 42 doubles of IekfDev");
+void launch_publish_iterate(cudaStream_t st, const IekfDev* src, IekfDev* dst_mapped, unsigned long long* flag_mapped,
+                            unsigned long long seq);
 
 // map_kernels.cu
 struct LayerLists;

@@ -416,8 +416,7 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
     ctx->launches += 1;
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it + 1], ctx->stream);
   }
-  return vn_check_cuda(ctx, cudaMemcpyAsync(ctx->h_iekf, ctx->d_iekf, sizeof(IekfDev), cudaMemcpyDeviceToHost, ctx->stream),
-                       "iterate download");
+  return vn_iterate_publish(ctx, ctx->stream);
 }
 
 // VINA_SLAM::LioStateEstimation (odometry.cpp:64-255) with the whole iteration loop on the device: one
@@ -427,11 +426,18 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
   const int num_max_iter = max_iter_override > 0 ? max_iter_override : 20;
   int r = iekf_enqueue_device(ctx, o, which, num_max_iter);
   if (r) return r;
-  r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "IEKF loop");
+  r = vn_iterate_wait(ctx);
   if (r) return r;
-  unstage_iterate(ctx->h_iekf, o->x_curr, &o->last_iters, not_degenerate);
+  if (ctx->n_down_pending)
+  {
+    // the count's device-to-host copy was enqueued before the loop: it has landed (stream order)
+    ctx->n_down = *ctx->h_n_down;
+    ctx->n_down_pending = false;
+  }
+  unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, not_degenerate);
   ctx->tm.iekf_iters = o->last_iters;
   float kernel_ms = 0;
+  if (ctx->profiling) cudaEventSynchronize(ctx->iekf_ev[2 * num_max_iter - 1]);
   if (ctx->profiling)
     for (int it = 0; it < o->last_iters; it++)
     {
@@ -670,26 +676,30 @@ extern "C" int vina_batch_step_resident(vina_batch* b, const void* const* d_xyzt
     if (e) return vn_check_cuda(b->c[0], (cudaError_t)e, "batched k_iekf launch");
     cudaEventRecord(b->tev[it + 1], b->stream);
   }
-  cudaEventRecord(b->done, b->stream);
   b->iekf_launches = num_max_iter;
   for (int i = 0; i < B; i++)
   {
     vina_ctx* ctx = b->c[i];
     ctx->launches += num_max_iter;
-    cudaStreamWaitEvent(ctx->stream, b->done, 0);
-    int r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->h_iekf, ctx->d_iekf, sizeof(IekfDev), cudaMemcpyDeviceToHost, ctx->stream),
-                          "iterate download");
+    int r = vn_iterate_publish(ctx, b->stream);
     if (r) return r;
   }
+  cudaEventRecord(b->done, b->stream);
+  for (int i = 0; i < B; i++) cudaStreamWaitEvent(b->c[i]->stream, b->done, 0);
   // per sequence: take the result back, then the map update (asynchronous, on the sequence's stream)
   for (int i = 0; i < B; i++)
   {
     vina_ctx* ctx = b->c[i];
     OdomHost* o = odom(ctx);
-    int r = vn_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "batched IEKF loop");
+    int r = vn_iterate_wait(ctx);
     if (r) return r;
+    if (ctx->n_down_pending)
+    {
+      ctx->n_down = *ctx->h_n_down;  // enqueued before the batched launches: has landed
+      ctx->n_down_pending = false;
+    }
     int ok = 0;
-    unstage_iterate(ctx->h_iekf, o->x_curr, &o->last_iters, &ok);
+    unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, &ok);
     ctx->tm.iekf_iters = o->last_iters;
     r = step_back(ctx, o, iekf_on_full, ok, x_out ? &x_out[i] : nullptr);
     if (r) return r;
@@ -701,6 +711,7 @@ extern "C" int vina_batch_iekf_time(vina_batch* b, float* ms_per_launch, int cap
 {
   if (!b || !ms_per_launch || !launches) return VINA_E_ARG;
   *launches = b->iekf_launches;
+  if (b->iekf_launches > 0) cudaEventSynchronize(b->tev[b->iekf_launches]);
   for (int it = 0; it < b->iekf_launches && it < cap; it++)
     cudaEventElapsedTime(&ms_per_launch[it], b->tev[it], b->tev[it + 1]);
   return VINA_OK;
