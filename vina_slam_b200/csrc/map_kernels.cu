@@ -1076,8 +1076,11 @@ __device__ void plane_update(NodeHot& h, NodeCold& c)
   h.qk = qk;
 }
 
-// leaf branch of OctoTree::margi (octree.cpp:397-484), mgsize = 1
-__device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf& xb)
+// leaf branch of OctoTree::margi (octree.cpp:397-484), mgsize = 1. The fold of the oldest frame's points into
+// point_fix (octree.cpp:452-459) is returned as a copy job (source, destination offset, count) that the
+// calling warp executes cooperatively.
+__device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf& xb, const PointRec*& job_src,
+                           int& job_off, int& job_np)
 {
   NodeHot& h = M.hot[n];
   NodeCold& c = M.cold[n];
@@ -1134,15 +1137,9 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
         int off = fix_append(M, c, np);
         if (off >= 0)
         {
-          const PointRec* src = M.win_pool[s0] + c.win_off[s0];
-          for (int a = 0; a < np; a++)
-          {
-            PointRec pr = src[a];
-            double pw[3];
-            rot_trans(xb.x[0].R, xb.x[0].p, pr.p, pw);
-            for (int k = 0; k < 3; k++) pr.p[k] = pw[k];
-            M.fix_pool[off + a] = pr;
-          }
+          job_src = M.win_pool[s0] + c.win_off[s0];
+          job_off = off;
+          job_np = np;
         }
       }
     }
@@ -1168,10 +1165,37 @@ __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, 
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j0 = blockIdx.x * blockDim.x + threadIdx.x - lane; j0 < nn; j0 += stride)  // warp-uniform trip count
   {
-    const int n = nodes[j];
-    if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb);
+    const int j = j0 + lane;
+    const PointRec* job_src = nullptr;
+    int job_off = 0, job_np = 0;
+    if (j < nn)
+    {
+      const int n = nodes[j];
+      if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb, job_src, job_off, job_np);
+    }
+    // the warp's copy jobs, one after the other, 32 points at a time (points go to the world frame of x_buf[0])
+    unsigned int todo = __ballot_sync(0xffffffffu, job_np > 0);
+    while (todo)
+    {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const PointRec* src = reinterpret_cast<const PointRec*>(
+          __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(job_src), l));
+      const int off = __shfl_sync(0xffffffffu, job_off, l);
+      const int np = __shfl_sync(0xffffffffu, job_np, l);
+      for (int a = lane; a < np; a += 32)
+      {
+        PointRec pr = src[a];
+        double pw[3];
+        rot_trans(xb.x[0].R, xb.x[0].p, pr.p, pw);
+        for (int k = 0; k < 3; k++) pr.p[k] = pw[k];
+        M.fix_pool[off + a] = pr;
+      }
+    }
   }
 }
 
