@@ -38,6 +38,7 @@ extern "C" {
 #define VINA_MAX_POSES 96 /* IMU poses per scan (reference: ~20 @200 Hz, ~40 @400 Hz) */
 #define VINA_MAX_WORLD 16 /* ranks a hash-range-sharded map can span */
 #define VINA_SHARD_RECORD_DOUBLES 13 /* one routed point: body p[3], world var (upper) [6], world p[3], int64 scan index */
+#define VINA_SHARD_QUERY_DOUBLES 10  /* one routed association query: body p[3], body var (upper) [6], int64 scan index */
 
 typedef struct vina_ctx vina_ctx;
 
@@ -209,6 +210,24 @@ int vina_shard_route(vina_ctx* ctx, int world, int first, int count, int64_t sca
 int vina_shard_insert_begin(vina_ctx* ctx, const void* d_recv, int n, int win_ord, int32_t* local_roots,
                             int32_t* local_slide);
 int vina_shard_insert_finish(vina_ctx* ctx, int win_ord, int global_roots, int global_slide);
+/* Association against the sharded map (one IEKF iteration, odometry.cpp:98-148): every rank routes points
+ * [first, first+count) of its FULL-scan pointVar set to the owners of the voxels they fall into under (R, p)
+ * (vina_shard_query_route, 10-double records), the records are exchanged (all-to-all), each owner evaluates gate,
+ * residual and Jacobian of what it received against its shard (vina_shard_query_accumulate -> the 34 packed
+ * sums: 21 HTH upper by rows, 6 HTz, 6 nnt upper, match count, written to DEVICE memory d_sums34), the sums
+ * are all-reduced and every rank applies the same update (vina_odom_iekf_host_begin / _update, the reference's
+ * 15x15 route). No per-point leaf cache survives the exchange: every iteration looks its voxel up again, which
+ * differs from the cached path (odometry.cpp:124-127) only for points that sit on a voxel face to within
+ * float rounding of the key. */
+int vina_shard_query_route(vina_ctx* ctx, int world, int first, int count, int64_t scan_index_base, const double R[9],
+                           const double p[3], void* d_send, int32_t* counts_out);
+int vina_shard_query_accumulate(vina_ctx* ctx, const void* d_recv, int n, const double R[9], const double p[3],
+                                const double rot_var[9], const double tsl_var[9], double* d_sums34);
+/* the reference's IEKF update on the host, one iteration at a time, for externally reduced sums
+ * (odometry.cpp:82, 192-230). begin: x_prop = x_curr, P^-1, loop counters. update: returns 1 when the loop is
+ * finished (converged twice or out of iterations; the covariance has then been updated), 0 otherwise. */
+int vina_odom_iekf_host_begin(vina_ctx* ctx, int max_iter);
+int vina_odom_iekf_host_update(vina_ctx* ctx, const double sums34[34]);
 
 /* ---- the per-scan loop body (src/pipeline/local_mapping.cpp:389-546), host
  * orchestration in C++ inside the library: a1 IMU propagation on the host

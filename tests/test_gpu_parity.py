@@ -584,3 +584,98 @@ def test_batch_replay_matches_separate_contexts(oracle_lib, gpu_lib):
     batch.close()
     for g in solo + grp:
         g.close()
+
+
+def test_sharded_association_matches_single_gpu(oracle_lib, gpu_lib):
+    """SURVEY §8e, the query side: the IEKF against a map sharded over 2 contexts (queries routed to the owners,
+    per-shard sums added - here in-process, the permutation is the one the gloo test checks) against the same
+    loop on the single-GPU map with the same host update: identical match counts, sums to 1e-10, states to 1e-10."""
+    import torch
+
+    from vina_slam_b200 import sharded
+
+    world = 2
+    cfg = small_cfg("robosense128", 32, 600)
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)
+    single = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    shards = [sharded.MapShard(gpu_lib.Ctx(cfg, **SMALL_CAPS), r, world) for r in range(world)]
+    for k in range(cfg.win_size):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        down = od.last_down()
+        st = gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+        single.set_state(st)
+        single.down_upload(down)
+        single.var_init(1)
+        single.odom_map_update()
+        sa = gpu_lib.state_arrays(st)
+        Rc, p = col(sa["R"]), sa["p"]
+        rv, tv = cov_blocks(sa["cov"])
+        sends, counts = [], []
+        for sh in shards:
+            sh.ctx.down_upload(down)
+            sh.ctx.var_init(1)
+            sh.push_pose(Rc, p)
+            s_, c_ = sh.route(*sharded.slice_of(down.shape[0], sh.rank, world), 0, Rc, p, rv, tv)
+            sends.append(s_)
+            counts.append(c_)
+        recvs = sharded.local_exchange(sends, counts)
+        torch.cuda.synchronize()
+        loc = [sh.insert_begin(r_) for sh, r_ in zip(shards, recvs)]
+        for sh in shards:
+            sh.insert_finish(sum(a for a, _ in loc), sum(b for _, b in loc))
+            sh.recut_margi()
+    # a new scan, a perturbed start
+    sc = seq.next_scan(deskewed=True)
+    st = gpu_lib.make_state(sc.gt_R @ synth.rot_exp(np.array([2e-3, -1e-3, 1.5e-3])),
+                            sc.gt_p + np.array([0.02, -0.015, 0.01]), sc.gt_v, t=sc.end_time)
+    n = sc.xyzt.shape[0]
+    single.set_state(st)
+    single.scan_upload(sc.xyzt)
+    single.var_init(0)
+    sa = gpu_lib.state_arrays(st)
+    rv, tv = cov_blocks(sa["cov"])
+    single.iekf_begin(0, rv, tv)
+    g0 = single.iekf_accumulate(col(sa["R"]), sa["p"])
+    it_single, _ = single.odom_iekf(0, 4, host_solve=True)
+    s_single = gpu_lib.state_arrays(single.get_state())
+
+    iek = [sharded.ShardedIekf(sh) for sh in shards]
+    for sh in shards:
+        sh.ctx.set_state(st)
+        sh.ctx.scan_upload(sc.xyzt)
+        sh.ctx.var_init(0)
+        sh.ctx.odom_iekf_host_begin(4)
+    iters = 0
+    for it in range(4):
+        cur = gpu_lib.state_arrays(shards[0].ctx.get_state())
+        Rc, p = col(cur["R"]), cur["p"]
+        routed = [q.route(*sharded.slice_of(n, q.sh.rank, world), Rc, p) for q in iek]
+        assert sum(int(c.sum()) for _, c in routed) == n
+        recvs = sharded.local_exchange([s_ for s_, _ in routed], [c_ for _, c_ in routed])
+        torch.cuda.synchronize()
+        tot = np.zeros(34)
+        for q, r_ in zip(iek, recvs):
+            assert r_.shape[1] == sharded.QREC
+            tot += q.accumulate(r_, Rc, p, rv, tv).cpu().numpy()
+        if it == 0:
+            # the same sums as the single-GPU accumulate kernel: count exactly, the rest to rounding
+            assert int(round(tot[33])) == g0["match_num"] > 0.3 * n
+            iu = np.triu_indices(6)
+            assert rel_err(tot[:21], g0["HTH"][iu]) < 1e-10 and rel_err(tot[21:27], g0["HTz"]) < 1e-10
+        done = [sh.ctx.odom_iekf_host_update(tot) for sh in shards]
+        iters = it + 1
+        assert done[0] == done[1]
+        if done[0]:
+            break
+    assert iters == it_single
+    for sh in shards:
+        s_sh = gpu_lib.state_arrays(sh.ctx.get_state())
+        for f in ("R", "p", "v", "bg", "ba"):
+            assert np.max(np.abs(s_sh[f] - s_single[f])) < 1e-10, f
+        assert rel_err(s_sh["cov"], s_single["cov"]) < 1e-9
+    assert np.linalg.norm(s_single["p"] - sc.gt_p) < 5e-3
+    single.close()
+    for sh in shards:
+        sh.ctx.close()

@@ -68,9 +68,11 @@ EXPORTS = [
     "vina_odom_map_update",
     "vina_odom_window", "vina_get_timings", "vina_set_profiling", "vina_shard_owner", "vina_shard_route",
     "vina_shard_insert_begin", "vina_shard_insert_finish", "vina_batch_create", "vina_batch_destroy",
-    "vina_batch_step_resident", "vina_batch_iekf_time", "vina_batch_sync",
+    "vina_batch_step_resident", "vina_batch_iekf_time", "vina_batch_sync", "vina_shard_query_route",
+    "vina_shard_query_accumulate", "vina_odom_iekf_host_begin", "vina_odom_iekf_host_update",
 ]
 SHARD_RECORD_DOUBLES = 13
+SHARD_QUERY_DOUBLES = 10
 
 
 class VinaError(RuntimeError):
@@ -334,6 +336,26 @@ class Ctx:
     def shard_insert_finish(self, win_ord: int, global_roots: int, global_slide: int):
         self._ck(self.lib.vina_shard_insert_finish(self.h, C.c_int(win_ord), C.c_int(global_roots),
                                                    C.c_int(global_slide)))
+
+    def shard_query_route(self, world: int, first: int, count: int, index_base: int, R_col, p, d_send_ptr: int):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (R_col, p)]
+        counts = np.zeros(world, dtype=np.int32)
+        self._ck(self.lib.vina_shard_query_route(self.h, C.c_int(world), C.c_int(first), C.c_int(count),
+                                                 C.c_int64(index_base), _dp(a[0]), _dp(a[1]), C.c_void_p(d_send_ptr),
+                                                 counts.ctypes.data_as(C.c_void_p)))
+        return counts
+
+    def shard_query_accumulate(self, d_recv_ptr: int, n: int, R_col, p, rot_var_col, tsl_var_col, d_sums_ptr: int):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (R_col, p, rot_var_col, tsl_var_col)]
+        self._ck(self.lib.vina_shard_query_accumulate(self.h, C.c_void_p(d_recv_ptr), C.c_int(n), _dp(a[0]), _dp(a[1]),
+                                                      _dp(a[2]), _dp(a[3]), C.c_void_p(d_sums_ptr)))
+
+    def odom_iekf_host_begin(self, max_iter: int):
+        self._ck(self.lib.vina_odom_iekf_host_begin(self.h, C.c_int(max_iter)))
+
+    def odom_iekf_host_update(self, sums34) -> bool:
+        a = np.ascontiguousarray(sums34, dtype=np.float64)
+        return self._ck(self.lib.vina_odom_iekf_host_update(self.h, _dp(a))) == 1
 
     # ---- odometry (host pipeline inside the library)
     def set_state(self, s: VinaState):

@@ -92,7 +92,10 @@ __global__ void __launch_bounds__(32 * VN_MAX_WORLD)
   }
 }
 
-// pass 3: pvec_update + stable scatter of the 13-double records into the owner segments
+// pass 3: stable scatter of the records into the owner segments. QUERY == false: map-build records, 13 doubles
+// (pvec_update: body point, world covariance, world point, scan index). QUERY == true: association records,
+// 10 doubles (body point, body covariance, scan index) - the owner evaluates the gate itself.
+template <bool QUERY>
 __global__ void __launch_bounds__(SH_THREADS)
     k_shard_scatter(ScanView scan, int first, int count, PoseD x, ShardCov cv, int world,
                     const unsigned char* __restrict__ owner, const int* __restrict__ hist,
@@ -116,8 +119,17 @@ __global__ void __launch_bounds__(SH_THREADS)
   const size_t pos = (size_t)starts[ow] + hist[blockIdx.x * world + ow] + base + myrank;
   const int s = first + i;
   const double pnt[3] = { scan.p[0][s], scan.p[1][s], scan.p[2][s] };
-  double var6[6], pw[3], vw[6];
+  double var6[6];
   for (int k = 0; k < 6; k++) var6[k] = scan.v[k][s];
+  if (QUERY)
+  {
+    double* r = out + pos * VINA_SHARD_QUERY_DOUBLES;
+    for (int k = 0; k < 3; k++) r[k] = pnt[k];
+    for (int k = 0; k < 6; k++) r[3 + k] = var6[k];
+    reinterpret_cast<long long*>(r)[9] = gidx_base + s;
+    return;
+  }
+  double pw[3], vw[6];
   rot_trans(x.R, x.p, pnt, pw);
   world_var(x.R, pnt, var6, cv.rot, cv.tsl, vw);
   double* r = out + pos * VINA_SHARD_RECORD_DOUBLES;
@@ -125,6 +137,16 @@ __global__ void __launch_bounds__(SH_THREADS)
   for (int k = 0; k < 6; k++) r[3 + k] = vw[k];
   for (int k = 0; k < 3; k++) r[9 + k] = pw[k];
   reinterpret_cast<long long*>(r)[12] = gidx_base + s;
+}
+
+// received association records -> the pointVar SoA the accumulate kernel reads
+__global__ void __launch_bounds__(SH_THREADS) k_shard_unpack_query(const double* __restrict__ rec, int n, ScanView scan)
+{
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const double* r = rec + (size_t)i * VINA_SHARD_QUERY_DOUBLES;
+  for (int k = 0; k < 3; k++) scan.p[k][i] = r[k];
+  for (int k = 0; k < 6; k++) scan.v[k][i] = r[3 + k];
 }
 
 // received records -> the SoA buffers the insert kernels read (body point, world point, world covariance)
@@ -142,14 +164,17 @@ __global__ void __launch_bounds__(SH_THREADS)
 int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
                        const double* rot_var, const double* tsl_var, double voxel_size, int world,
                        unsigned char* owner, int* hist, int* counts, int* starts, double* out, long long gidx_base,
-                       int* status)
+                       int* status, bool query)
 {
   ShardCov cv;
   for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
   const int nblk = count <= 0 ? 1 : (count + SH_THREADS - 1) / SH_THREADS;
   k_shard_count<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, voxel_size, world, owner, hist, status);
   k_shard_offsets<<<1, 32 * VN_MAX_WORLD, 0, st>>>(hist, nblk, world, counts, starts);
-  k_shard_scatter<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, cv, world, owner, hist, starts, out, gidx_base);
+  if (query)
+    k_shard_scatter<true><<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, cv, world, owner, hist, starts, out, gidx_base);
+  else
+    k_shard_scatter<false><<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, cv, world, owner, hist, starts, out, gidx_base);
   return 3;
 }
 
@@ -157,5 +182,12 @@ int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanVie
 {
   if (n <= 0) return 0;
   k_shard_unpack<<<(n + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(rec, n, scan, sc);
+  return 1;
+}
+
+int launch_shard_unpack_query(cudaStream_t st, const double* rec, int n, const ScanView& scan)
+{
+  if (n <= 0) return 0;
+  k_shard_unpack_query<<<(n + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(rec, n, scan);
   return 1;
 }

@@ -835,10 +835,61 @@ extern "C" int vina_shard_route(vina_ctx* ctx, int world, int first, int count, 
   ctx->launches += launch_shard_route(ctx->stream, ctx->pv[1], first, count, x, cov_rot, cov_tsl, ctx->cfg.voxel_size,
                                       world, ctx->d_sh_owner, ctx->d_sh_hist, ctx->d_sh_counts,
                                       ctx->d_sh_counts + VINA_MAX_WORLD, (double*)d_send, (long long)scan_index_base,
-                                      ctx->d_status);
+                                      ctx->d_status, false);
   CU(cudaMemcpyAsync(ctx->h_sh_counts, ctx->d_sh_counts, world * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < world; k++) counts_out[k] = ctx->h_sh_counts[k];
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_query_route(vina_ctx* ctx, int world, int first, int count, int64_t scan_index_base,
+                                      const double R[9], const double p[3], void* d_send, int32_t* counts_out)
+{
+  if (!ctx || world < 1 || world > VINA_MAX_WORLD || first < 0 || count < 0 || !R || !p || !counts_out ||
+      (count > 0 && !d_send))
+    return VINA_E_ARG;
+  if (first + count > ctx->n_pv[0])
+    return vn_fail(ctx, VINA_E_ARG, "slice [%d, %d) exceeds the %d scan points", first, first + count, ctx->n_pv[0]);
+  int r = ensure_shard(ctx);
+  if (r) return r;
+  PoseD x;
+  memcpy(x.R, R, 72);
+  memcpy(x.p, p, 24);
+  double z9[9] = { 0 };
+  ctx->launches += launch_shard_route(ctx->stream, ctx->pv[0], first, count, x, z9, z9, ctx->cfg.voxel_size, world,
+                                      ctx->d_sh_owner, ctx->d_sh_hist, ctx->d_sh_counts,
+                                      ctx->d_sh_counts + VINA_MAX_WORLD, (double*)d_send, (long long)scan_index_base,
+                                      ctx->d_status, true);
+  CU(cudaMemcpyAsync(ctx->h_sh_counts, ctx->d_sh_counts, world * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < world; k++) counts_out[k] = ctx->h_sh_counts[k];
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_query_accumulate(vina_ctx* ctx, const void* d_recv, int n, const double R[9],
+                                           const double p[3], const double rot_var[9], const double tsl_var[9],
+                                           double* d_sums34)
+{
+  if (!ctx || n < 0 || (n > 0 && !d_recv) || !R || !p || !rot_var || !tsl_var || !d_sums34) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "%d routed points > max_scan_points %d", n, ctx->cap_points);
+  // the received records are evaluated from the query set pv[1] (the full-scan set pv[0] keeps the caller's
+  // points for the next iteration's routing); no leaf cache: every point looks its voxel up
+  ctx->launches += launch_shard_unpack_query(ctx->stream, (const double*)d_recv, n, ctx->pv[1]);
+  ctx->n_pv[1] = n;
+  ctx->n_down = n;
+  ctx->n_down_pending = false;
+  int r = vina_iekf_begin(ctx, 1, rot_var, tsl_var);
+  if (r) return r;
+  CU(cudaMemcpyAsync(ctx->d_iekf->R, R, 72, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_iekf->p, p, 24, cudaMemcpyHostToDevice, ctx->stream));
+  IekfBatch bt;
+  bt.mode = 0;  // sums stay in the device iterate
+  bt.variant = 0;
+  vn_iekf_fill_seq(ctx, &bt.s[0], false);
+  int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
+  if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
+  ctx->launches += 1;
+  CU(cudaMemcpyAsync(d_sums34, ctx->d_iekf->sums, VN_IEKF_NACC * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return VINA_OK;
 }
 

@@ -123,7 +123,8 @@ int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView
 int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
                        const double* rot_var, const double* tsl_var, double voxel_size, int world,
                        unsigned char* owner, int* hist, int* counts, int* starts, double* out, long long gidx_base,
-                       int* status);
+                       int* status, bool query);
+int launch_shard_unpack_query(cudaStream_t st, const double* rec, int n, const ScanView& scan);
 int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc);
 int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)

@@ -99,6 +99,11 @@ struct OdomHost
   int win_count = 0, win_base = 0;
   int degrade_cnt = 0;
   int last_iters = 0;
+  // host IEKF driven one iteration at a time (vina_odom_iekf_host_begin / _update)
+  vina_state hi_prop;
+  double hi_cov_inv[225];
+  int hi_iter = 0, hi_max = 0, hi_rematch = 0;
+  bool hi_active = false;
   OdomHost()
   {
     memset(&x_curr, 0, sizeof(x_curr));
@@ -830,6 +835,60 @@ int vina_odom_iekf_host(vina_ctx* ctx, int which, int max_iter, int* iters_out, 
   if (iters_out) *iters_out = o->last_iters;
   if (not_degenerate) *not_degenerate = ok;
   return VINA_OK;
+}
+
+int vina_odom_iekf_host_begin(vina_ctx* ctx, int max_iter)
+{
+  if (!ctx) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  o->hi_prop = o->x_curr;
+  inverse_lu<15>(o->x_curr.cov, o->hi_cov_inv);  // odometry.cpp:82
+  o->hi_iter = 0;
+  o->hi_max = max_iter > 0 ? max_iter : 20;
+  o->hi_rematch = 0;
+  o->hi_active = true;
+  return VINA_OK;
+}
+
+// one pass of odometry.cpp:192-230 with the sums of this iteration (any source: one GPU, all-reduced shards)
+int vina_odom_iekf_host_update(vina_ctx* ctx, const double sums34[34])
+{
+  if (!ctx || !sums34) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  if (!o->hi_active) return vn_fail(ctx, VINA_E_STATE, "vina_odom_iekf_host_update before vina_odom_iekf_host_begin");
+  vina_state& x_curr = o->x_curr;
+  double HTH[36], HTz[6], nnt[9];
+  int32_t match_num = 0;
+  vn_iekf_unpack(sums34, HTH, HTz, nnt, &match_num);
+  double HTH15[225], tmp[225], K1[225], G6[90];
+  memset(HTH15, 0, sizeof(HTH15));
+  for (int j = 0; j < 6; j++)
+    for (int i = 0; i < 6; i++) HTH15[i + 15 * j] = HTH[i + 6 * j];
+  for (int i = 0; i < 225; i++) tmp[i] = HTH15[i] + o->hi_cov_inv[i];
+  inverse_lu<15>(tmp, K1);
+  mat_mul(15, 6, 6, K1, HTH, G6);
+  double vec[15], sol[15], a[15], b[15];
+  state_boxminus(o->hi_prop, x_curr, vec);
+  mat_mul(15, 6, 1, K1, HTz, a);
+  mat_mul(15, 6, 1, G6, vec, b);
+  for (int i = 0; i < 15; i++) sol[i] = (a[i] + vec[i]) - b[i];
+  state_boxplus(x_curr, sol);
+  const bool conv = (norm3(sol) * 57.3 < 0.01) && (norm3(sol + 3) * 100 < 0.015);
+  if (conv || ((o->hi_rematch == 0) && (o->hi_iter == o->hi_max - 2))) o->hi_rematch++;
+  const bool fin = o->hi_rematch >= 2 || (o->hi_iter == o->hi_max - 1);
+  o->hi_iter++;
+  o->last_iters = o->hi_iter;
+  if (fin)
+  {
+    double IG[225], nc[225];
+    memset(IG, 0, sizeof(IG));
+    for (int i = 0; i < 90; i++) IG[i] = -G6[i];
+    for (int i = 0; i < 15; i++) IG[i + 15 * i] += 1.0;
+    mat_mul(15, 15, 15, IG, x_curr.cov, nc);
+    memcpy(x_curr.cov, nc, sizeof(nc));
+    o->hi_active = false;
+  }
+  return fin ? 1 : 0;
 }
 
 int vina_odom_map_update(vina_ctx* ctx)

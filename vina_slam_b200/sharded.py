@@ -144,3 +144,75 @@ def map_digest(nodes: np.ndarray) -> int:
     cols = [np.ascontiguousarray(nodes[f]).reshape(nodes.shape[0], -1).view(np.uint8) for f in nodes.dtype.names]
     raw = np.ascontiguousarray(np.concatenate(cols, axis=1))
     return int(sum(zlib.crc32(row.tobytes()) for row in raw))
+
+
+QREC = capi.SHARD_QUERY_DOUBLES
+
+
+def exchange_rows(send, counts: Sequence[int], width: int, group=None):
+    """exchange_records for rows of `width` doubles (association queries are 10 wide, map records 13)."""
+    import torch
+    import torch.distributed as dist
+
+    counts = [int(c) for c in counts]
+    if len(counts) == 1 or not dist.is_initialized():
+        return send[: counts[0]]
+    c_out = torch.tensor(counts, dtype=torch.int64, device=send.device)
+    c_in = torch.empty_like(c_out)
+    dist.all_to_all_single(c_in, c_out, group=group)
+    rc = [int(v) for v in c_in.cpu().tolist()]
+    recv = torch.empty((sum(rc), width), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send[: sum(counts)].contiguous(), output_split_sizes=rc, input_split_sizes=counts,
+                           group=group)
+    return recv
+
+
+class ShardedIekf:
+    """LioStateEstimation (odometry.cpp:64-255) against a map sharded by hash range: per iteration every rank
+    routes its slice of the scan to the owners of the voxels the points fall into (all-to-all of 80-byte
+    pointVar records), the owners evaluate gate / residual / Jacobian against their shard, the 34 sums are
+    all-reduced and every rank applies the same update (the reference's 15x15 route on the host)."""
+
+    def __init__(self, shard: MapShard):
+        import torch
+
+        self.sh = shard
+        self._send = None
+        self._sums = torch.zeros(34, dtype=torch.float64, device=shard.device)
+
+    def route(self, first: int, count: int, R_col, p):
+        import torch
+
+        if self._send is None or self._send.shape[0] < max(count, 1):
+            self._send = torch.empty((max(count, 1), QREC), dtype=torch.float64, device=self.sh.device)
+        counts = self.sh.ctx.shard_query_route(self.sh.world, first, count, 0, R_col, p, self._send.data_ptr())
+        return self._send[:count], counts
+
+    def accumulate(self, recv, R_col, p, rot_var_col, tsl_var_col):
+        self._recv = recv
+        self.sh.ctx.shard_query_accumulate(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), R_col, p,
+                                           rot_var_col, tsl_var_col, self._sums.data_ptr())
+        return self._sums
+
+    def run(self, first: int, count: int, max_iter: int = 4):
+        """The whole loop with the collectives; the ctx holds x_curr (same on every rank) and the full scan's
+        pointVar set (vina_var_init(ctx, 0)). Returns the number of iterations."""
+        import torch
+        import torch.distributed as dist
+
+        ctx = self.sh.ctx
+        s0 = capi.state_arrays(ctx.get_state())
+        rv = np.ascontiguousarray(s0["cov"][0:3, 0:3].T.reshape(-1))
+        tv = np.ascontiguousarray(s0["cov"][3:6, 3:6].T.reshape(-1))
+        ctx.odom_iekf_host_begin(max_iter)
+        for it in range(max_iter):
+            s = capi.state_arrays(ctx.get_state())
+            Rc = np.ascontiguousarray(s["R"].T.reshape(-1))
+            send, counts = self.route(first, count, Rc, s["p"])
+            recv = exchange_rows(send, counts, QREC, self.sh.group)
+            sums = self.accumulate(recv, Rc, s["p"], rv, tv)
+            if self.sh.world > 1 and dist.is_initialized():
+                dist.all_reduce(sums, group=self.sh.group)
+            if ctx.odom_iekf_host_update(sums.cpu().numpy()):
+                return it + 1
+        return max_iter
