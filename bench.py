@@ -420,7 +420,9 @@ def main_sharded(args, cfg):
     caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=1 << 20, hash_capacity_log2=21,
                 device=local)
     sh = sharded.MapShard(capi.Ctx(cfg, **caps), rank, world, device=dev)
+    iek = sharded.ShardedIekf(sh) if args.query else None
     ref = capi.Ctx(cfg, **caps) if (rank == 0 and args.verify) else None
+    q_iters, q_err, q_ref_err, q_ref_iters = 0, 0.0, 0.0, 0
     stream = torch.cuda.current_stream(dev)
     d_scans = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
     ev0 = torch.cuda.Event(enable_timing=True)
@@ -444,6 +446,21 @@ def main_sharded(args, cfg):
         tv = np.ascontiguousarray(sa["cov"][3:6, 3:6].T.reshape(-1))
         # the (already deskewed) scan is resident; down-sample + var_init on every rank, route this rank's slice
         sh.ctx.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
+        if iek is not None and k >= cfg.win_size:
+            # association + IEKF against the sharded map from a perturbed start (same on every rank)
+            pert = capi.make_state(sc.gt_R @ synth.rot_exp(np.array([1e-3, -1e-3, 1e-3])),
+                                   sc.gt_p + np.array([0.01, -0.01, 0.005]), sc.gt_v, t=sc.end_time)
+            sh.ctx.set_state(pert)
+            sh.ctx.var_init(0)
+            q_iters += iek.run(*sharded.slice_of(sc.xyzt.shape[0], rank, world), MAX_ITER)
+            got = capi.state_arrays(sh.ctx.get_state())
+            q_err = max(q_err, float(np.linalg.norm(got["p"] - sc.gt_p)))
+            if ref is not None:
+                ref.set_state(pert)
+                ref.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
+                ref.var_init(0)
+                q_ref_iters += ref.odom_iekf(0, MAX_ITER, host_solve=True)[0]
+                q_ref_err = max(q_ref_err, float(np.linalg.norm(got["p"] - capi.state_arrays(ref.get_state())["p"])))
         sh.ctx.downsample()
         nd = sh.ctx.n_down()
         sh.ctx.var_init(1)
@@ -478,6 +495,10 @@ def main_sharded(args, cfg):
                            "down_points_per_scan": n_down_tot / K, "routed_points_per_scan": int(dig[2]) / K,
                            "record_bytes": 8 * sharded.REC, "nodes": int(dig[1])},
                 "gpu_launches": None}
+        if iek is not None:
+            line["config"]["sharded_iekf"] = {"iters_per_scan": q_iters / (W + K), "pos_err_vs_ground_truth_m": q_err,
+                                              "pos_diff_vs_single_gpu_m": q_ref_err if ref is not None else None,
+                                              "iters_per_scan_single_gpu": q_ref_iters / (W + K) if ref is not None else None}
         if ref is not None:
             line["config"]["union_equals_single_gpu_map"] = bool(int(dig[0]) == sharded.map_digest(ref.map_export()))
             line["config"]["single_gpu_nodes"] = ref.map_count()[0]
@@ -499,6 +520,7 @@ def main():
                     help="odometry = the headline per-scan path (default); sharded-map = map build partitioned by "
                          "voxel-hash range over the ranks (SURVEY 8e)")
     ap.add_argument("--verify", action="store_true", help="sharded-map: rank 0 also builds the single-GPU map and compares")
+    ap.add_argument("--query", action="store_true", help="sharded-map: also run the IEKF against the sharded map every scan")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
