@@ -507,6 +507,103 @@ def main_sharded(args, cfg):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- large resident map (configs[3])
+def main_bigmap(args, cfg):
+    """BASELINE.json configs[3]: the per-scan path with ~10^7 root voxels resident. The map is pre-filled on the
+    device through the product path itself (synthetic planar patches, ~25 points per 1 m voxel, far away from the
+    sequence's own world), then the sequence runs as in the headline leg. Reported: ms/scan and pts/s with the
+    large map, the same without it, the resident voxel count and the memory footprint."""
+    import torch
+
+    from vina_slam_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    W, K = args.warmup, args.steps
+    boots, scans = gen_sequence(cfg, cfg.seed, cfg.win_size, W + K)
+    n_vox = int(args.voxels)
+    per_scan_vox, ppv = 10000, 25
+    caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=int(n_vox * 1.15) + (1 << 20),
+                hash_capacity_log2=max(21, int(np.ceil(np.log2(max(n_vox, 1) * 2.5)))),
+                fix_pool_points=int(n_vox * ppv * 1.1) + (16 << 20), device=0)
+    stream = torch.cuda.current_stream(dev)
+    out = {}
+    for label, fill in (("empty", 0), ("filled", n_vox)):
+        free0 = torch.cuda.mem_get_info(dev)[0]
+        gx = capi.Ctx(cfg, **(caps if fill else dict(caps, max_nodes=1 << 20, hash_capacity_log2=21,
+                                                     fix_pool_points=16 << 20)))
+        gx.set_stream(stream.cuda_stream)
+        t_fill = 0.0
+        if fill:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(1234)
+            gx.set_state(capi.make_state(np.eye(3), np.zeros(3), np.zeros(3)))
+            # a slab of voxels 3000 m away from the building: X x Y x 8 layers
+            side = int(np.ceil(np.sqrt(fill / 8)))
+            t0 = time.perf_counter()
+            for v0 in range(0, fill, per_scan_vox):
+                idx = torch.arange(v0, min(v0 + per_scan_vox, fill), device=dev)
+                ix, iy, iz = idx % side, (idx // side) % side, idx // (side * side)
+                c = torch.stack([ix, iy, iz], 1).double() + 0.5 + torch.tensor([3000.0, 3000.0, 100.0], device=dev)
+                nrm = torch.randn((idx.numel(), 3), generator=gen, device=dev, dtype=torch.float64)
+                nrm = nrm / nrm.norm(dim=1, keepdim=True)
+                a = torch.linalg.cross(nrm, torch.tensor([0.3, 0.5, 0.81], device=dev, dtype=torch.float64).expand_as(nrm))
+                a = a / a.norm(dim=1, keepdim=True)
+                b = torch.linalg.cross(nrm, a)
+                uv = (torch.rand((idx.numel(), ppv, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 0.56
+                nz = torch.randn((idx.numel(), ppv, 1), generator=gen, device=dev, dtype=torch.float64) * 0.004
+                pts = c[:, None, :] + uv[..., :1] * a[:, None, :] + uv[..., 1:] * b[:, None, :] + nz * nrm[:, None, :]
+                xyzt = torch.cat([pts.reshape(-1, 3), torch.zeros((idx.numel() * ppv, 1), device=dev, dtype=torch.float64)],
+                                 1).float().contiguous()
+                torch.cuda.synchronize(dev)
+                gx.scan_upload_device(xyzt.data_ptr(), xyzt.shape[0])
+                gx.downsample()
+                gx.n_down()
+                gx.var_init(1)
+                gx.odom_map_update()
+            gx.sync()
+            t_fill = time.perf_counter() - t0
+        nodes, roots, slide = gx.map_count()
+        for sc in boots:
+            gx.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+        d_scans = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        gx.set_profiling(True)
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in scans]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in scans]
+        err, rows = 0.0, []
+        for k, sc in enumerate(scans):
+            flush.fill_(k & 0xFF)
+            ev0[k].record(stream)
+            st = gx.step_resident(d_scans[k].data_ptr(), sc.xyzt.shape[0], sc.beg_time, sc.end_time, sc.imu, True, MAX_ITER)
+            ev1[k].record(stream)
+            if k >= W:
+                rows.append(gx.timings())
+                err = max(err, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
+        torch.cuda.synchronize(dev)
+        ms = float(np.mean([ev0[k].elapsed_time(ev1[k]) for k in range(W, W + K)]))
+        stage = {f: float(np.mean([getattr(t, f) for t in rows])) for f in
+                 ("iekf_ms", "insert_ms", "recut_ms", "margi_ms", "total_ms")}
+        n2, r2, s2 = gx.map_count()
+        out[label] = {"ms_per_scan": ms, "pts_per_s": cfg.n_points / (ms * 1e-3), "prefilled_root_voxels": roots,
+                      "prefilled_nodes": nodes, "nodes_after": n2, "roots_after": r2, "slide_roots": s2,
+                      "prefill_seconds": t_fill, "gt_traj_err_m": err, "stage_ms": stage,
+                      "device_memory_GB": (free0 - torch.cuda.mem_get_info(dev)[0]) / 1e9}
+        gx.close()
+        del d_scans, flush
+        torch.cuda.empty_cache()
+    line = {"metric": METRIC + " with a large resident map", "value": out["filled"]["pts_per_s"], "unit": UNIT, "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": out["filled"]["ms_per_scan"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "mode": "bigmap", "requested_voxels": n_vox,
+                       "l2": "256 MiB buffer written between timed steps"},
+            "with_large_map": out["filled"], "without": out["empty"]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -516,7 +613,8 @@ def main():
     ap.add_argument("--workload", default="robosense128", choices=sorted(synth.SENSORS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--batch", type=int, default=8, help="concurrent sequences per GPU in the batch-replay leg (0/1 = off)")
-    ap.add_argument("--mode", default="odometry", choices=["odometry", "sharded-map"],
+    ap.add_argument("--voxels", type=float, default=1e7, help="bigmap: root voxels to pre-fill")
+    ap.add_argument("--mode", default="odometry", choices=["odometry", "sharded-map", "bigmap"],
                     help="odometry = the headline per-scan path (default); sharded-map = map build partitioned by "
                          "voxel-hash range over the ranks (SURVEY 8e)")
     ap.add_argument("--verify", action="store_true", help="sharded-map: rank 0 also builds the single-GPU map and compares")
@@ -529,6 +627,8 @@ def main():
         main_reference(args, cfg)
     elif args.mode == "sharded-map":
         main_sharded(args, cfg)
+    elif args.mode == "bigmap":
+        main_bigmap(args, cfg)
     else:
         main_ours(args, cfg)
 
