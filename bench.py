@@ -212,34 +212,41 @@ def main_ours(args, cfg):
         torch.cuda.synchronize(dev)
 
     # ---- leg 1: inputs resident in HBM -------------------------------------------------------------
-    gx = new_ctx()
+    # two passes over the same scans on fresh contexts: pass 0 is the timed one (no per-stage events, nothing
+    # but the product path between the step's two CUDA events); pass 1 repeats it with the library's per-stage /
+    # per-launch event timers on, for stage_ms and the kernel's launch duration in the roofline.
     d_scans = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
-    gx.set_profiling(True)
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-    tm_rows, traj_err = [], 0.0
     sampler = None
-    barrier()
-    for k, sc in enumerate(scans):
-        if k == W:
-            barrier()
-            sampler = ClockSampler(local)
-            sampler.start()
-            l_start = None
-        flush.fill_(k & 0xFF)  # evict L2 between timed iterations (outside the timed segments)
-        ev0[k].record(stream)
-        st = gx.step_resident(d_scans[k].data_ptr(), sc.xyzt.shape[0], sc.beg_time, sc.end_time, sc.imu, True,
-                              MAX_ITER)
-        ev1[k].record(stream)
-        if k >= W:
-            tm_rows.append(gx.timings())
-            traj_err = max(traj_err, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
-    barrier()
-    clocks = sampler.stop() if sampler else {}
-    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(W, W + K)])
+    for profiled in (False, True):
+        gx = new_ctx()
+        gx.set_profiling(profiled)
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
+        tm_rows, traj = [], 0.0
+        barrier()
+        for k, sc in enumerate(scans):
+            if k == W:
+                barrier()
+                if not profiled:
+                    sampler = ClockSampler(local)
+                    sampler.start()
+            flush.fill_(k & 0xFF)  # evict L2 between timed iterations (outside the timed segments)
+            ev0[k].record(stream)
+            st = gx.step_resident(d_scans[k].data_ptr(), sc.xyzt.shape[0], sc.beg_time, sc.end_time, sc.imu, True,
+                                  MAX_ITER)
+            ev1[k].record(stream)
+            if k >= W:
+                tm_rows.append(gx.timings())
+                traj = max(traj, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
+        barrier()
+        if not profiled:
+            clocks = sampler.stop() if sampler else {}
+            step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(W, W + K)])
+            t_res = float(step_ms.sum()) * 1e-3
+            launches = int(sum(t.kernel_launches for t in tm_rows))
+            traj_err = traj
+            gx.close()
     pts = sum(sc.xyzt.shape[0] for sc in scans[W:])
-    t_res = float(step_ms.sum()) * 1e-3
-    launches = int(sum(t.kernel_launches for t in tm_rows))
     iters = int(sum(t.iekf_iters for t in tm_rows))
     iekf_kernel_ms = float(sum(t.iekf_kernel_ms for t in tm_rows))
     stage = {f: float(np.mean([getattr(t, f) for t in tm_rows])) for f in
@@ -372,7 +379,8 @@ def main_ours(args, cfg):
             "config": {"workload": workload_name(cfg), "max_iter": MAX_ITER, "iekf_on": "full scan",
                        "vnc_terms": False, "if_BA": 0, "parallelism": f"replicas x{world}",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); steps timed individually "
-                             "with CUDA events on the launching stream and summed",
+                             "with CUDA events on the launching stream and summed; stage_ms / roofline launch times "
+                             "come from a second, instrumented pass over the same scans",
                        "iekf_iters_per_step": iters_per_step, "gt_traj_err_m": traj_err},
             "e2e": {"value": pts_all / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K,
                     "h2d_bytes_per_step": int(16 * n_mean + 17096),

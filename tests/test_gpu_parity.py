@@ -679,3 +679,81 @@ def test_sharded_association_matches_single_gpu(oracle_lib, gpu_lib):
     single.close()
     for sh in shards:
         sh.ctx.close()
+
+
+def test_small_scan_retry_and_new_entry_points_edges(oracle_lib, gpu_lib):
+    """(i) a scan that down-samples to < 2000 points takes the "down_size / 2" retry of local_mapping.cpp:396-403
+    inside the full step, like the oracle; (ii) the device IEKF loop on a map without any plane leaves the state
+    where the host variant leaves it; (iii) argument / state errors of the batch, shard and host-IEKF entry points."""
+    import ctypes as C
+
+    import torch
+
+    # (i) ---------------------------------------------------------------------------------------------
+    cfg = small_cfg("robosense128", 8, 150)  # 1200 points per scan: always below the 2000-point threshold
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, gpu_own_downsample=True)
+    for k in range(4):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        n_d = gx.n_down()
+        assert 0 < n_d < 2000 and n_d == od.last_down().shape[0]  # same voxel set after the retry
+        assert np.linalg.norm(sg["p"] - so["p"]) < 1e-3 and synth.rot_err_deg(sg["R"], so["R"]) < 0.01
+    assert gx.map_count()[0] == od.map_count()[0]
+    gx.close()
+
+    # (ii) --------------------------------------------------------------------------------------------
+    cfg = small_cfg()
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    seq = synth.Sequence(cfg)
+    sc = seq.next_scan(deskewed=True)
+    st = gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+    gx.scan_upload(sc.xyzt)
+    gx.var_init(0)
+    res = []
+    for host in (False, True):
+        gx.set_state(st)
+        it, ok = gx.odom_iekf(0, 4, host_solve=host)
+        res.append((it, ok, gpu_lib.state_arrays(gx.get_state())))
+    assert res[0][0] == res[1][0] == 2 and res[0][1] == res[1][1] == 0  # no matches: converged at once, degenerate
+    for f in ("R", "p", "v", "bg", "ba"):
+        assert np.array_equal(res[0][2][f], gpu_lib.state_arrays(st)[f]) and np.array_equal(res[1][2][f], res[0][2][f])
+    assert rel_err(res[0][2]["cov"], res[1][2]["cov"]) < 1e-9
+
+    # (iii) -------------------------------------------------------------------------------------------
+    lib = gx.lib
+    h = C.c_void_p()
+    arr = (C.c_void_p * 1)(gx.h)
+    assert lib.vina_batch_create(arr, C.c_int(0), C.byref(h)) == -1
+    assert lib.vina_batch_create(arr, C.c_int(17), C.byref(h)) == -1
+    assert lib.vina_batch_create(None, C.c_int(1), C.byref(h)) == -1
+    one = gpu_lib.Batch([gx])  # a batch of one is legal
+    one.close()
+    cnt = (C.c_int32 * 16)()
+    z9, z3 = np.zeros(9), np.zeros(3)
+    dp = gpu_lib._dp
+    buf = torch.empty((sc.xyzt.shape[0], 13), dtype=torch.float64, device="cuda")
+    assert lib.vina_shard_route(gx.h, C.c_int(0), C.c_int(0), C.c_int(1), C.c_int64(0), dp(z9), dp(z3), dp(z9), dp(z9),
+                                C.c_void_p(buf.data_ptr()), cnt) == -1      # world < 1
+    assert lib.vina_shard_route(gx.h, C.c_int(17), C.c_int(0), C.c_int(1), C.c_int64(0), dp(z9), dp(z3), dp(z9), dp(z9),
+                                C.c_void_p(buf.data_ptr()), cnt) == -1      # world > VINA_MAX_WORLD
+    assert lib.vina_shard_route(gx.h, C.c_int(2), C.c_int(0), C.c_int(10 ** 6), C.c_int64(0), dp(z9), dp(z3), dp(z9),
+                                dp(z9), C.c_void_p(buf.data_ptr()), cnt) == -1  # slice beyond the point set
+    assert b"exceeds" in lib.vina_last_error(gx.h)
+    # an empty slice routes nothing; world = 1 routes everything to rank 0, in order
+    gx.down_upload(sc.xyzt[:500])
+    gx.var_init(1)
+    c0 = gx.shard_route(4, 0, 0, 0, col(np.eye(3)), z3, z9, z9, buf.data_ptr())
+    assert c0.tolist() == [0, 0, 0, 0]
+    c1 = gx.shard_route(1, 0, 500, 7, col(np.eye(3)), z3, z9, z9, buf.data_ptr())
+    assert c1.tolist() == [500]
+    assert np.array_equal(buf[:500, 12].contiguous().view(torch.int64).cpu().numpy(), 7 + np.arange(500))
+    # host IEKF update without begin
+    assert lib.vina_odom_iekf_host_update(gx.h, dp(np.zeros(34))) == -6
+    gx.odom_iekf_host_begin(4)
+    assert gx.odom_iekf_host_update(np.zeros(34)) is False  # zero sums: no step, converged once
+    assert gx.odom_iekf_host_update(np.zeros(34)) is True   # ... twice: finished
+    assert lib.vina_odom_iekf_host_update(gx.h, dp(np.zeros(34))) == -6
+    gx.close()

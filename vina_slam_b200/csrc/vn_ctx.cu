@@ -166,6 +166,9 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(cudaHostGetDevicePointer((void**)&ctx->d_pub_flag, ctx->h_pub_flag, 0));
   *ctx->h_pub_flag = 0ull;
   CU(cudaEventCreateWithFlags(&ctx->ev_poses, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_scan_up, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_scan_rd, cudaEventDisableTiming));
   CU(dalloc(&ctx->d_status, 1));
   CU(cudaHostAlloc((void**)&ctx->h_status, sizeof(int), cudaHostAllocDefault));
 
@@ -254,6 +257,13 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFreeHost(ctx->h_pub);
   cudaFreeHost(ctx->h_pub_flag);
   if (ctx->ev_poses) cudaEventDestroy(ctx->ev_poses);
+  if (ctx->ev_scan_up) cudaEventDestroy(ctx->ev_scan_up);
+  if (ctx->ev_scan_rd) cudaEventDestroy(ctx->ev_scan_rd);
+  if (ctx->copy_stream)
+  {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   cudaFree(ctx->d_sh_owner);
@@ -317,11 +327,25 @@ extern "C" int vina_ctx_sync(vina_ctx* ctx)
 }
 
 // ---------------------------------------------------------------------------
+// every entry that reads d_scan marks the stream position after its last reader, so that the next upload
+// (on the copy stream) only waits for those kernels and not for the map update enqueued behind them
+static int mark_scan_read(vina_ctx* ctx)
+{
+  CU(cudaEventRecord(ctx->ev_scan_rd, ctx->stream));
+  ctx->scan_rd_valid = true;
+  return VINA_OK;
+}
+
 extern "C" int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n)
 {
   if (!ctx || !xyzt || n < 0) return VINA_E_ARG;
   if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points %d", n, ctx->cap_points);
-  CU(cudaMemcpyAsync(ctx->d_scan, xyzt, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  // the copy runs on its own stream: it starts as soon as the previous readers of d_scan are done and overlaps
+  // whatever else is still queued on the compute stream (the previous scan's map update)
+  if (ctx->scan_rd_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scan_rd, 0));
+  CU(cudaMemcpyAsync(ctx->d_scan, xyzt, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU(cudaEventRecord(ctx->ev_scan_up, ctx->copy_stream));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan_up, 0));
   ctx->n_scan = n;
   return VINA_OK;
 }
@@ -354,7 +378,7 @@ extern "C" int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, con
   ctx->poses_in_flight = true;
   launch_deskew(ctx->stream, ctx->d_scan, ctx->n_scan, ctx->d_poses, ctx->d_status);
   ctx->launches += 1;
-  return VINA_OK;
+  return mark_scan_read(ctx);
 }
 
 extern "C" int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap)
@@ -362,7 +386,9 @@ extern "C" int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap)
   if (!ctx || !xyzt) return VINA_E_ARG;
   if (cap < ctx->n_scan) return VINA_E_ARG;
   CU(cudaMemcpyAsync(xyzt, ctx->d_scan, (size_t)ctx->n_scan * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-  int r = vn_check_status(ctx);
+  int r = mark_scan_read(ctx);
+  if (r) return r;
+  r = vn_check_status(ctx);
   if (r) return r;
   return ctx->n_scan;
 }
@@ -375,7 +401,7 @@ static int run_downsample(vina_ctx* ctx, double size)
   ctx->launches += k;
   CU(cudaMemcpyAsync(ctx->h_n_down, ctx->d_n_down, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->n_down_pending = true;
-  return VINA_OK;
+  return mark_scan_read(ctx);
 }
 
 // resolve the pending down-sampled count (one stream sync) and apply the
@@ -398,7 +424,7 @@ extern "C" int vina_downsample(vina_ctx* ctx)
                        ctx->stream));
     ctx->n_down = ctx->n_scan;
     ctx->n_down_pending = false;
-    return VINA_OK;
+    return mark_scan_read(ctx);
   }
   return run_downsample(ctx, ctx->cfg.down_size);
 }
@@ -468,7 +494,7 @@ extern "C" int vina_var_init(vina_ctx* ctx, int which)
   launch_var_init(ctx->stream, which == 0 ? ctx->d_scan : ctx->d_down, nullptr, n, ctx->pv[which], prm);
   ctx->n_pv[which] = n;
   ctx->launches += 1;
-  return VINA_OK;
+  return which == 0 ? mark_scan_read(ctx) : VINA_OK;
 }
 
 extern "C" int vina_pvec_upload(vina_ctx* ctx, int which, const double* pnt, const double* var, int n)

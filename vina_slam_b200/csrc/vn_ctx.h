@@ -52,6 +52,10 @@ struct vina_ctx
   unsigned long long* h_pub_flag = nullptr;  // mapped pinned sequence number, written after the data
   unsigned long long* d_pub_flag = nullptr;
   unsigned long long pub_seq = 0;
+  cudaStream_t copy_stream = nullptr;  // host -> device scan uploads: overlap the previous scan's map update
+  cudaEvent_t ev_scan_up = nullptr;    // the upload into d_scan has landed
+  cudaEvent_t ev_scan_rd = nullptr;    // the last enqueued reader of d_scan is done
+  bool scan_rd_valid = false;
   cudaEvent_t ev_poses = nullptr;  // the pose-table staging buffer has been consumed
   bool poses_in_flight = false;
   IekfDebug dbg = { nullptr, nullptr, nullptr, nullptr };
