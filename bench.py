@@ -359,8 +359,8 @@ def main_ours(args, cfg):
                               "launches_timed": batch["launches"]},
                  "note": "vina_batch: B contexts replaying the same seeded sequence in lock step on one GPU; "
                          "per-sequence stages on own streams, IEKF iterations batched into one launch; wall "
-                         "clock over the K steps, no L2 flush (working set of B maps + scans exceeds nothing: "
-                         "kernel inputs are re-written every step)"}
+                         "clock over the K steps; no explicit L2 flush in this leg (the point sets of all B "
+                         "sequences are rewritten every step, the B maps stay hot as they would in production)"}
 
     if rank == 0:
         cpu = None
