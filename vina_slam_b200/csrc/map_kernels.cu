@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, i
 //   every thread   owns up to three (child, cov_add entry) pairs and sums that child's staged Bf_var terms.
 #define SPLIT_THREADS 128
 #define SPLIT_BATCH 64
-#define SPLIT_MAXSEG 48
+#define SPLIT_MAXSEG 128
 struct SplitSeg
 {
   const PointRec* src;
@@ -676,7 +676,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   __shared__ int kid[8];
   __shared__ unsigned int bm[2][8];
   __shared__ int clsrow[SPLIT_BATCH];
-  __shared__ int nseg, total, next_cls, next_seg;
+  __shared__ int nseg, total, nfix, fixtot;
+  __shared__ int wcnt_s[VINA_MAX_WIN], woff_s[VINA_MAX_WIN];
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   LaneRole L;
@@ -699,28 +700,88 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       (&fill[0][0])[t] = 0;
     }
     __syncthreads();
-    // pass 1: how many points of every class go to every child
-    if (has_fix)
-      for (int s = c.fix_head; s >= 0; s = M.fix_segs[s].next)
-      {
-        const FixSeg seg = M.fix_segs[s];
-        for (int a = t; a < seg.cnt; a += SPLIT_THREADS)
-          atomicAdd(&cnt[0][child_index(M.fix_pool[seg.off + a].p, vc)], 1);
-      }
-    for (int si = 0; si < win_count; si++)
+    // the row stream: thread 0 walks the point_fix chain ONCE (dependent loads), threads 1..win_count fetch
+    // the window frames' lists meanwhile; everything below works from this table. A chain has at most
+    // max_points folds + 1 inherited segment (a leaf stops folding at pcr_fix.N >= max_points, octree.cpp:448),
+    // so SPLIT_MAXSEG covers it; a longer one is reported, never truncated silently.
+    if (t == 0)
     {
-      const int slot = M.mp[si];
-      const int np = c.win_cnt[slot];
-      const PointRec* src = M.win_pool[slot] + c.win_off[slot];
-      for (int a = t; a < np; a += SPLIT_THREADS)
+      int ns = 0, tot = 0;
+      bool overflow = false;
+      if (has_fix)
+        for (int sg = c.fix_head; sg >= 0;)
+        {
+          const FixSeg seg = M.fix_segs[sg];
+          if (seg.cnt > 0)
+          {
+            if (ns >= SPLIT_MAXSEG - VINA_MAX_WIN)
+            {
+              overflow = true;
+              break;
+            }
+            segs[ns].src = M.fix_pool + seg.off;
+            segs[ns].start = tot;
+            segs[ns].cnt = seg.cnt;
+            segs[ns].cls = 0;
+            tot += seg.cnt;
+            ns++;
+          }
+          sg = seg.next;
+        }
+      if (overflow) atomicOr(M.status, VN_ST_FIX_FULL);
+      nfix = ns;
+      fixtot = tot;
+    }
+    else if (t <= win_count)
+    {
+      const int slot = M.mp[t - 1];
+      wcnt_s[t - 1] = c.win_cnt[slot];
+      woff_s[t - 1] = c.win_off[slot];
+    }
+    __syncthreads();
+    if (t == 0)
+    {
+      int ns = nfix, tot = fixtot;
+      for (int q = 0; q < 11; q++) cls_first[q] = -1;
+      if (ns > 0) cls_first[0] = 0;
+      for (int si = 0; si < win_count; si++)
+        if (wcnt_s[si] > 0)
+        {
+          cls_first[1 + si] = tot;
+          segs[ns].src = M.win_pool[M.mp[si]] + woff_s[si];
+          segs[ns].start = tot;
+          segs[ns].cnt = wcnt_s[si];
+          segs[ns].cls = 1 + si;
+          tot += wcnt_s[si];
+          ns++;
+        }
+      nseg = ns;
+      total = tot;
+    }
+    __syncthreads();
+    // pass 1: how many points of every class go to every child
+    {
+      const int ns = nseg, tot = total;
+      for (int g = t; g < tot; g += SPLIT_THREADS)
       {
+        int sgi = 0;
+        while (sgi + 1 < ns && segs[sgi + 1].start <= g) sgi++;
+        const int cls = segs[sgi].cls;
+        const PointRec* src = segs[sgi].src + (g - segs[sgi].start);
         double pw[3];
-        rot_trans(xb.x[si].R, xb.x[si].p, src[a].p, pw);
-        atomicAdd(&cnt[1 + si][child_index(pw, vc)], 1);
+        if (cls == 0)
+        {
+          pw[0] = src->p[0];
+          pw[1] = src->p[1];
+          pw[2] = src->p[2];
+        }
+        else
+          rot_trans(xb.x[cls - 1].R, xb.x[cls - 1].p, src->p, pw);
+        atomicAdd(&cnt[cls][child_index(pw, vc)], 1);
       }
     }
     __syncthreads();
-    // children and their storage (thread k owns child k)
+    // children (thread k owns child k), then their storage in parallel over (child, class)
     if (t < 8)
     {
       const int k = t;
@@ -735,33 +796,34 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         {
           NodeCold& kc = M.cold[id];
           if (cnt[0][k] > 0 && store) off[0][k] = fix_append(M, kc, cnt[0][k]);
-          for (int si = 0; si < win_count; si++)
-            if (cnt[1 + si][k] > 0)
-            {
-              const int slot = M.mp[si];
-              kc.has_sw = 1;
-              kc.isexist = 1;
-              if (store)
-              {
-                int woff = atomicAdd(&M.win_cursor[slot], cnt[1 + si][k]);
-                if ((long long)woff + cnt[1 + si][k] > M.win_cap)
-                  atomicOr(M.status, VN_ST_WIN_FULL);
-                else
-                {
-                  off[1 + si][k] = woff;
-                  kc.win_off[slot] = woff;
-                  kc.win_cnt[slot] = cnt[1 + si][k];
-                }
-              }
-            }
+          if (tot > cnt[0][k])
+          {
+            kc.has_sw = 1;
+            kc.isexist = 1;
+          }
         }
       }
       kid[k] = id;
     }
-    if (t == 8)
+    __syncthreads();
+    if (t < 8 * win_count && store)
     {
-      next_cls = has_fix ? 0 : 1;
-      next_seg = has_fix ? c.fix_head : -1;
+      const int k = t & 7, si = t >> 3;
+      const int m = cnt[1 + si][k];
+      if (m > 0 && kid[k] >= 0)
+      {
+        const int slot = M.mp[si];
+        NodeCold& kc = M.cold[kid[k]];
+        const int woff = atomicAdd(&M.win_cursor[slot], m);
+        if ((long long)woff + m > M.win_cap)
+          atomicOr(M.status, VN_ST_WIN_FULL);
+        else
+        {
+          off[1 + si][k] = woff;
+          kc.win_off[slot] = woff;
+          kc.win_cnt[slot] = m;
+        }
+      }
     }
     __syncthreads();
 
@@ -770,61 +832,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     int cur_cls = -1;             // class clB currently accumulates
     double cv[3] = { 0.0, 0.0, 0.0 };  // pairs p = t + 128 q < 360: child p / 45, entry p % 45
 
-    // pass 2: the row stream, one table of up to SPLIT_MAXSEG segments at a time
-    for (;;)
+    // pass 2: the row stream, 64 rows at a time
     {
-      if (t == 0)
-      {
-        int ns = 0, tot = 0, cls = next_cls, sg = next_seg;
-        for (int q = 0; q < 11; q++) cls_first[q] = -1;
-        while (cls <= win_count && ns < SPLIT_MAXSEG)
-        {
-          if (cls == 0)
-          {
-            if (sg < 0)
-            {
-              cls = 1;
-              continue;
-            }
-            const FixSeg seg = M.fix_segs[sg];
-            if (seg.cnt > 0)
-            {
-              if (cls_first[0] < 0) cls_first[0] = tot;
-              segs[ns].src = M.fix_pool + seg.off;
-              segs[ns].start = tot;
-              segs[ns].cnt = seg.cnt;
-              segs[ns].cls = 0;
-              tot += seg.cnt;
-              ns++;
-            }
-            sg = seg.next;
-          }
-          else
-          {
-            const int slot = M.mp[cls - 1];
-            const int np = c.win_cnt[slot];
-            if (np > 0)
-            {
-              cls_first[cls] = tot;
-              segs[ns].src = M.win_pool[slot] + c.win_off[slot];
-              segs[ns].start = tot;
-              segs[ns].cnt = np;
-              segs[ns].cls = cls;
-              tot += np;
-              ns++;
-            }
-            cls++;
-          }
-        }
-        nseg = ns;
-        total = tot;
-        next_cls = cls;
-        next_seg = sg;
-      }
-      __syncthreads();
       const int ns = nseg, tot = total;
-      const bool last_table = next_cls > win_count;
-      if (ns == 0) break;
       for (int base = 0; base < tot; base += SPLIT_BATCH)
       {
         // phase 1 (rows in stream order): load, world position, child index
@@ -947,7 +957,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         if (t < SPLIT_BATCH && kk >= 0) atomicAdd(&fill[cls][kk], 1);
         __syncthreads();
       }
-      if (last_table) break;
     }
     // last class of every chain
     if (t < 72 && cur_cls >= 0 && kid[my_k] >= 0)
