@@ -428,6 +428,8 @@ def main_sharded(args, cfg):
     caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=1 << 20, hash_capacity_log2=21,
                 device=local)
     sh = sharded.MapShard(capi.Ctx(cfg, **caps), rank, world, device=dev)
+    if args.p2p:
+        sh.p2p_setup(caps["max_scan_points"])  # inboxes + CUDA IPC handles all-gathered over the group
     iek = sharded.ShardedIekf(sh) if args.query else None
     ref = capi.Ctx(cfg, **caps) if (rank == 0 and args.verify) else None
     q_iters, q_err, q_ref_err, q_ref_iters = 0, 0.0, 0.0, 0
@@ -473,7 +475,7 @@ def main_sharded(args, cfg):
         nd = sh.ctx.n_down()
         sh.ctx.var_init(1)
         first, cnt = sharded.slice_of(nd, rank, world)
-        got = sh.update(first, cnt, 0, Rc, sa["p"], rv, tv)
+        got = (sh.update_p2p if args.p2p else sh.update)(first, cnt, 0, Rc, sa["p"], rv, tv)
         if k >= cfg.win_size + W:
             n_down_tot += nd
             n_recv_tot += got
@@ -500,6 +502,9 @@ def main_sharded(args, cfg):
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * float(tt[0]) / K,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(cfg), "mode": "sharded-map", "parallelism": f"hash-range x{world}",
+                           "exchange": ("records stored into the owners' inboxes by the routing kernel over peer memory "
+                                        "(CUDA IPC / NVLink), device-side flags" if args.p2p else
+                                        "NCCL all_to_all_single of staged records"),
                            "down_points_per_scan": n_down_tot / K, "routed_points_per_scan": int(dig[2]) / K,
                            "record_bytes": 8 * sharded.REC, "nodes": int(dig[1])},
                 "gpu_launches": None}
@@ -626,6 +631,7 @@ def main():
                     help="odometry = the headline per-scan path (default); sharded-map = map build partitioned by "
                          "voxel-hash range over the ranks (SURVEY 8e)")
     ap.add_argument("--verify", action="store_true", help="sharded-map: rank 0 also builds the single-GPU map and compares")
+    ap.add_argument("--p2p", action="store_true", help="sharded-map: fused route + exchange over peer memory instead of NCCL")
     ap.add_argument("--query", action="store_true", help="sharded-map: also run the IEKF against the sharded map every scan")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

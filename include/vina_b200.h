@@ -210,6 +210,30 @@ int vina_shard_route(vina_ctx* ctx, int world, int first, int count, int64_t sca
 int vina_shard_insert_begin(vina_ctx* ctx, const void* d_recv, int n, int win_ord, int32_t* local_roots,
                             int32_t* local_slide);
 int vina_shard_insert_finish(vina_ctx* ctx, int win_ord, int global_roots, int global_slide);
+/* The same exchange FUSED into the routing kernel over peer memory (NVLink): every record is stored straight into
+ * its owner's inbox at its final, scan-ordered position; the counts table and the completion flags travel the
+ * same way. No staging buffer, no collective call, no host synchronisation between routing and arrival.
+ *   vina_shard_p2p_create    allocates this rank's inbox (inbox_records x 13 doubles) and control block; returns
+ *                            their CUDA IPC handles (2 x 64 bytes) to be all-gathered by the caller
+ *   vina_shard_p2p_connect   opens the peers' handles (world x 128 bytes, rank order)
+ *   vina_shard_p2p_connect_local   peers living in the same process: raw pointers from vina_shard_p2p_pointers
+ *   vina_shard_route_p2p     as vina_shard_route, but asynchronous and with the exchange inside. phase 0 = all of
+ *                            it; phase 1 = only the part that never waits (owners, counts, my counts row to the
+ *                            peers), phase 2 = only the part that waits for the peers' rows, stores the records
+ *                            and signals - for several ranks driven from ONE host thread on ONE GPU (tests),
+ *                            where a kernel must never wait for work that is enqueued after it
+ *   vina_shard_insert_begin_p2p    waits (on the device) for every peer's records, then as vina_shard_insert_begin;
+ *                            also returns the number of records received
+ * A 2-int all-reduce per scan (see above) must separate two scans: it is what guarantees that every rank has
+ * consumed its inbox before the next scan's records arrive. */
+int vina_shard_p2p_create(vina_ctx* ctx, int rank, int world, int64_t inbox_records, void* ipc_handles_out);
+int vina_shard_p2p_connect(vina_ctx* ctx, const void* all_handles);
+int vina_shard_p2p_pointers(vina_ctx* ctx, void** inbox, void** ctrl);
+int vina_shard_p2p_connect_local(vina_ctx* ctx, void* const* inbox_ptrs, void* const* ctrl_ptrs);
+int vina_shard_route_p2p(vina_ctx* ctx, int first, int count, int64_t scan_index_base, const double R[9],
+                         const double p[3], const double cov_rot[9], const double cov_tsl[9], int phase);
+int vina_shard_insert_begin_p2p(vina_ctx* ctx, int win_ord, int32_t* n_recv, int32_t* local_roots, int32_t* local_slide);
+
 /* Association against the sharded map (one IEKF iteration, odometry.cpp:98-148): every rank routes points
  * [first, first+count) of its FULL-scan pointVar set to the owners of the voxels they fall into under (R, p)
  * (vina_shard_query_route, 10-double records), the records are exchanged (all-to-all), each owner evaluates gate,

@@ -757,3 +757,61 @@ def test_small_scan_retry_and_new_entry_points_edges(oracle_lib, gpu_lib):
     assert gx.odom_iekf_host_update(np.zeros(34)) is True   # ... twice: finished
     assert lib.vina_odom_iekf_host_update(gx.h, dp(np.zeros(34))) == -6
     gx.close()
+
+
+def test_sharded_map_p2p_exchange_equals_single_gpu_map(oracle_lib, gpu_lib):
+    """The exchange fused into the routing kernel: three shard contexts on this GPU connected through each
+    other's inbox / control-block pointers (vina_shard_p2p_connect_local; across processes the same pointers come
+    from CUDA IPC). Records are stored by the routing kernel at their final position in the owner's inbox; counts
+    and completion flags travel the same way; nothing synchronises with the host between routing and arrival.
+    The union of the shards must again equal the single-context map byte for byte."""
+    from vina_slam_b200 import sharded
+
+    world = 3
+    cfg = small_cfg("robosense128", 32, 600)
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)
+    single = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    shards = [sharded.MapShard(gpu_lib.Ctx(cfg, **SMALL_CAPS), r, world, own_stream=True) for r in range(world)]
+    for sh in shards:
+        sh.ctx.shard_p2p_create(sh.rank, world, SMALL_CAPS["max_scan_points"])
+    ptrs = [sh.ctx.shard_p2p_pointers() for sh in shards]
+    for sh in shards:
+        sh.ctx.shard_p2p_connect_local([a for a, _ in ptrs], [b for _, b in ptrs])
+    received = np.zeros(world, dtype=np.int64)
+    for k in range(cfg.win_size + 4):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        down = od.last_down()
+        st = gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+        single.set_state(st)
+        single.down_upload(down)
+        single.var_init(1)
+        single.odom_map_update()
+        sa = gpu_lib.state_arrays(st)
+        Rc, p = col(sa["R"]), sa["p"]
+        rv, tv = cov_blocks(sa["cov"])
+        for sh in shards:
+            sh.ctx.down_upload(down)
+            sh.ctx.var_init(1)
+            sh.push_pose(Rc, p)
+        # several ranks on one GPU, one host thread: first everything that never waits, then the waiting parts
+        # (CUDA may put two streams into one hardware queue; a kernel must not wait for work enqueued behind it)
+        for phase in (1, 2):
+            for sh in shards:
+                sh.ctx.shard_route_p2p(*sharded.slice_of(down.shape[0], sh.rank, world), 0, Rc, p, rv, tv, phase)
+        loc = [sh.ctx.shard_insert_begin_p2p(sh.win_count - 1) for sh in shards]
+        assert sum(n for n, _, _ in loc) == down.shape[0]
+        for sh, (n, _, _) in zip(shards, loc):
+            received[sh.rank] += n
+            sh.insert_finish(sum(a for _, a, _ in loc), sum(b for _, _, b in loc))
+            sh.recut_margi()
+    ms = sort_nodes(single.map_export())
+    mu = sort_nodes(np.concatenate([sh.ctx.map_export() for sh in shards]))
+    assert mu.shape[0] == ms.shape[0] > 2000
+    for f in ms.dtype.names:
+        assert np.array_equal(ms[f], mu[f]), f"p2p-sharded map differs from the single-GPU map in {f}"
+    assert received.min() > 0.5 * received.mean()
+    single.close()
+    for sh in shards:
+        sh.ctx.close()

@@ -70,6 +70,8 @@ EXPORTS = [
     "vina_shard_insert_begin", "vina_shard_insert_finish", "vina_batch_create", "vina_batch_destroy",
     "vina_batch_step_resident", "vina_batch_iekf_time", "vina_batch_sync", "vina_shard_query_route",
     "vina_shard_query_accumulate", "vina_odom_iekf_host_begin", "vina_odom_iekf_host_update",
+    "vina_shard_p2p_create", "vina_shard_p2p_connect", "vina_shard_p2p_pointers", "vina_shard_p2p_connect_local",
+    "vina_shard_route_p2p", "vina_shard_insert_begin_p2p",
 ]
 SHARD_RECORD_DOUBLES = 13
 SHARD_QUERY_DOUBLES = 10
@@ -336,6 +338,36 @@ class Ctx:
     def shard_insert_finish(self, win_ord: int, global_roots: int, global_slide: int):
         self._ck(self.lib.vina_shard_insert_finish(self.h, C.c_int(win_ord), C.c_int(global_roots),
                                                    C.c_int(global_slide)))
+
+    # ---- fused route + exchange over peer memory
+    def shard_p2p_create(self, rank: int, world: int, inbox_records: int) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.vina_shard_p2p_create(self.h, C.c_int(rank), C.c_int(world), C.c_int64(inbox_records), buf))
+        return buf.raw
+
+    def shard_p2p_connect(self, all_handles: bytes):
+        self._ck(self.lib.vina_shard_p2p_connect(self.h, C.c_char_p(all_handles)))
+
+    def shard_p2p_pointers(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.vina_shard_p2p_pointers(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def shard_p2p_connect_local(self, inbox_ptrs, ctrl_ptrs):
+        n = len(inbox_ptrs)
+        ia = (C.c_void_p * n)(*inbox_ptrs)
+        ca = (C.c_void_p * n)(*ctrl_ptrs)
+        self._ck(self.lib.vina_shard_p2p_connect_local(self.h, ia, ca))
+
+    def shard_route_p2p(self, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col, phase: int = 0):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (R_col, p, cov_rot_col, cov_tsl_col)]
+        self._ck(self.lib.vina_shard_route_p2p(self.h, C.c_int(first), C.c_int(count), C.c_int64(index_base), _dp(a[0]),
+                                               _dp(a[1]), _dp(a[2]), _dp(a[3]), C.c_int(phase)))
+
+    def shard_insert_begin_p2p(self, win_ord: int):
+        n, a, b = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.vina_shard_insert_begin_p2p(self.h, C.c_int(win_ord), C.byref(n), C.byref(a), C.byref(b)))
+        return n.value, a.value, b.value
 
     def shard_query_route(self, world: int, first: int, count: int, index_base: int, R_col, p, d_send_ptr: int):
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (R_col, p)]

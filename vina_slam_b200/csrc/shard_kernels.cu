@@ -161,6 +161,182 @@ __global__ void __launch_bounds__(SH_THREADS)
   for (int k = 0; k < 3; k++) sc.pw[k][i] = r[9 + k];
 }
 
+// ---------------------------------------------------------------------------
+// Fused route + exchange over peer memory (NVLink). Instead of staging the records for an NCCL all-to-all, the
+// scatter kernel stores every record straight into its owner's inbox (a peer pointer: CUDA IPC between the
+// per-GPU processes), at the position it has in the owner's scan-ordered receive sequence:
+//   position = sum_{r < me} counts_r[owner] + (stable position among my records for that owner).
+// The counts table is exchanged the same way: every rank stores its row into every peer's control block and
+// raises that peer's `ready` flag; after its records a rank raises the peers' `done` flags. Flags carry the scan
+// epoch, so nothing is ever reset. All of it is enqueued without a host synchronisation.
+#define P2P_SPIN_LIMIT 20000000ll  // ~ seconds of polling a local flag: a lost peer is reported (VN_ST_SPIN), never a hang
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p)
+{
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+// my counts row -> every peer's table, then the peers' ready flags (one warp; lane = peer)
+__global__ void __launch_bounds__(32) k_p2p_publish(ShardPeers peers, const int* __restrict__ counts, unsigned long long epoch)
+{
+  const int w = threadIdx.x;
+  if (w < peers.world)
+  {
+    ShardCtrl* pc = peers.ctrl[w];
+    for (int k = 0; k < peers.world; k++) *reinterpret_cast<volatile int*>(&pc->counts[peers.rank][k]) = counts[k];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&pc->ready[peers.rank]) = epoch;
+  }
+}
+
+// wait for every rank's row in MY table and derive my base offset at every owner. Only this single warp ever
+// spins, so a waiting rank cannot starve the kernels it waits for.
+__global__ void __launch_bounds__(32)
+    k_p2p_base(ShardPeers peers, unsigned long long epoch, long long* __restrict__ base, int* __restrict__ status)
+{
+  const int w = threadIdx.x;
+  const ShardCtrl* me = peers.ctrl[peers.rank];
+  if (w < peers.world)
+  {
+    long long spins = 0;
+    while (ld_flag(&me->ready[w]) != epoch)
+      if (++spins > P2P_SPIN_LIMIT)
+      {
+        atomicOr(status, VN_ST_SPIN);
+        break;
+      }
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (w < peers.world)
+  {
+    long long b = 0;
+    for (int r = 0; r < peers.rank; r++) b += *reinterpret_cast<const volatile int*>(&me->counts[r][w]);
+    base[w] = b;
+  }
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+    k_p2p_scatter(ScanView scan, int first, int count, PoseD x, ShardCov cv, ShardPeers peers,
+                  const unsigned char* __restrict__ owner, const int* __restrict__ hist,
+                  const long long* __restrict__ base, long long gidx_base, long long inbox_cap, int* __restrict__ status)
+{
+  __shared__ int wcnt[SH_WARPS][VN_MAX_WORLD];
+  const int world = peers.world;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  const int ow = i < count ? (int)owner[i] : -1;
+  int myrank = 0;
+  for (int w = 0; w < world; w++)
+  {
+    const unsigned int m = __ballot_sync(0xffffffffu, ow == w);
+    if (ow == w) myrank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[warp][w] = __popc(m);
+  }
+  __syncthreads();
+  if (ow >= 0)
+  {
+    int inblk = 0;
+    for (int ww = 0; ww < warp; ww++) inblk += wcnt[ww][ow];
+    const long long pos = base[ow] + hist[blockIdx.x * world + ow] + inblk + myrank;
+    if (pos >= inbox_cap)
+      atomicOr(status, VN_ST_WIN_FULL);
+    else
+    {
+      const int s = first + i;
+      const double pnt[3] = { scan.p[0][s], scan.p[1][s], scan.p[2][s] };
+      double var6[6], pw[3], vw[6];
+      for (int k = 0; k < 6; k++) var6[k] = scan.v[k][s];
+      rot_trans(x.R, x.p, pnt, pw);
+      world_var(x.R, pnt, var6, cv.rot, cv.tsl, vw);
+      double* r = peers.inbox[ow] + pos * VINA_SHARD_RECORD_DOUBLES;  // peer store over NVLink
+      for (int k = 0; k < 3; k++) r[k] = pnt[k];
+      for (int k = 0; k < 6; k++) r[3 + k] = vw[k];
+      for (int k = 0; k < 3; k++) r[9 + k] = pw[k];
+      reinterpret_cast<long long*>(r)[12] = gidx_base + s;
+    }
+  }
+  __threadfence_system();
+}
+
+// my records have landed everywhere: raise the peers' done flags
+__global__ void __launch_bounds__(32) k_p2p_signal(ShardPeers peers, unsigned long long epoch)
+{
+  __threadfence_system();
+  if (threadIdx.x < peers.world)
+    *reinterpret_cast<volatile unsigned long long*>(&peers.ctrl[threadIdx.x]->done[peers.rank]) = epoch;
+}
+
+// wait for every rank's records in MY inbox; the number of records received
+__global__ void __launch_bounds__(32) k_p2p_wait(ShardPeers peers, unsigned long long epoch, int* __restrict__ n_recv,
+                                                 int* __restrict__ status)
+{
+  ShardCtrl* me = peers.ctrl[peers.rank];
+  int mine = 0;
+  if (threadIdx.x < peers.world)
+  {
+    long long spins = 0;
+    while (ld_flag(&me->done[threadIdx.x]) != epoch)
+      if (++spins > P2P_SPIN_LIMIT)
+      {
+        atomicOr(status, VN_ST_SPIN);
+        break;
+      }
+    __threadfence_system();
+    mine = *reinterpret_cast<const volatile int*>(&me->counts[threadIdx.x][peers.rank]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (threadIdx.x == 0) *n_recv = mine;
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+    k_shard_unpack_n(const double* __restrict__ rec, const int* __restrict__ n_ptr, ScanView scan, InsertScratch sc)
+{
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  if (i >= *n_ptr) return;
+  const double* r = rec + (size_t)i * VINA_SHARD_RECORD_DOUBLES;
+  for (int k = 0; k < 3; k++) scan.p[k][i] = r[k];
+  for (int k = 0; k < 6; k++) sc.vw[k][i] = r[3 + k];
+  for (int k = 0; k < 3; k++) sc.pw[k][i] = r[9 + k];
+}
+
+int launch_shard_route_p2p(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
+                           const double* rot_var, const double* tsl_var, double voxel_size, const ShardPeers& peers,
+                           unsigned char* owner, int* hist, int* counts, int* starts, long long* base,
+                           unsigned long long epoch, long long gidx_base, long long inbox_cap, int* status, int phase)
+{
+  ShardCov cv;
+  for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
+  const int nblk = count <= 0 ? 1 : (count + SH_THREADS - 1) / SH_THREADS;
+  int launches = 0;
+  if (phase != 2)
+  {
+    // phase A never waits: owners, counts, my row to every peer
+    k_shard_count<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, voxel_size, peers.world, owner, hist, status);
+    k_shard_offsets<<<1, 32 * VN_MAX_WORLD, 0, st>>>(hist, nblk, peers.world, counts, starts);
+    k_p2p_publish<<<1, 32, 0, st>>>(peers, counts, epoch);
+    launches += 3;
+  }
+  if (phase != 1)
+  {
+    // phase B waits for the peers' rows (one spinning warp), then stores the records and signals
+    k_p2p_base<<<1, 32, 0, st>>>(peers, epoch, base, status);
+    k_p2p_scatter<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, cv, peers, owner, hist, base, gidx_base, inbox_cap,
+                                               status);
+    k_p2p_signal<<<1, 32, 0, st>>>(peers, epoch);
+    launches += 3;
+  }
+  return launches;
+}
+
+int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned long long epoch, int* n_recv, int cap,
+                          const ScanView& scan, const InsertScratch& sc, int* status)
+{
+  k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status);
+  k_shard_unpack_n<<<(cap + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(peers.inbox[peers.rank], n_recv, scan, sc);
+  return 2;
+}
+
 int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
                        const double* rot_var, const double* tsl_var, double voxel_size, int world,
                        unsigned char* owner, int* hist, int* counts, int* starts, double* out, long long gidx_base,

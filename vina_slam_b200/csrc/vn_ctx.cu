@@ -91,6 +91,7 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   memset(&ctx->map, 0, sizeof(ctx->map));
   memset(&ctx->ins, 0, sizeof(ctx->ins));
   memset(&ctx->layers, 0, sizeof(ctx->layers));
+  memset(&ctx->peers, 0, sizeof(ctx->peers));
   memset(ctx->pv, 0, sizeof(ctx->pv));
   if (cfg.win_size < 1 || cfg.win_size > VINA_MAX_WIN || cfg.max_layer < 0 || cfg.max_layer > 3 ||
       cfg.voxel_size <= 0 || cfg.thread_num < 1)
@@ -266,6 +267,12 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   }
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
+  for (void* m : ctx->p2p_opened)
+    if (m) cudaIpcCloseMemHandle(m);
+  cudaFree(ctx->p2p_inbox);
+  cudaFree(ctx->p2p_ctrl);
+  cudaFree(ctx->d_n_recv);
+  cudaFree(ctx->d_p2p_base);
   cudaFree(ctx->d_sh_owner);
   cudaFree(ctx->d_sh_hist);
   cudaFree(ctx->d_sh_counts);
@@ -866,6 +873,123 @@ extern "C" int vina_shard_route(vina_ctx* ctx, int world, int first, int count, 
   CU(cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < world; k++) counts_out[k] = ctx->h_sh_counts[k];
   return VINA_OK;
+}
+
+// ---- the exchange fused into the routing kernel (peer stores over NVLink) -----------------------------
+extern "C" int vina_shard_p2p_create(vina_ctx* ctx, int rank, int world, int64_t inbox_records, void* ipc_handles_out)
+{
+  if (!ctx || world < 1 || world > VINA_MAX_WORLD || rank < 0 || rank >= world || inbox_records < 1) return VINA_E_ARG;
+  if (ctx->p2p_inbox) return vn_fail(ctx, VINA_E_STATE, "vina_shard_p2p_create called twice");
+  int r = ensure_shard(ctx);
+  if (r) return r;
+  if (inbox_records > ctx->cap_points) inbox_records = ctx->cap_points;  // the insert works on max_scan_points at most
+  CU(dalloc(&ctx->p2p_inbox, (size_t)inbox_records * VINA_SHARD_RECORD_DOUBLES, false));
+  CU(dalloc(&ctx->p2p_ctrl, 1));
+  CU(dalloc(&ctx->d_n_recv, 1));
+  CU(dalloc(&ctx->d_p2p_base, VINA_MAX_WORLD));
+  CU(cudaDeviceSynchronize());
+  ctx->p2p_cap = inbox_records;
+  ctx->peers.rank = rank;
+  ctx->peers.world = world;
+  ctx->peers.inbox[rank] = ctx->p2p_inbox;
+  ctx->peers.ctrl[rank] = ctx->p2p_ctrl;
+  if (ipc_handles_out)
+  {
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], ctx->p2p_inbox));
+    CU(cudaIpcGetMemHandle(&h[1], ctx->p2p_ctrl));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64-byte blobs");
+    memcpy(ipc_handles_out, h, sizeof(h));
+  }
+  ctx->p2p_connected = world == 1;
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_p2p_connect(vina_ctx* ctx, const void* all_handles)
+{
+  if (!ctx || !all_handles || !ctx->p2p_inbox) return VINA_E_ARG;
+  const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int q = 0; q < ctx->peers.world; q++)
+  {
+    if (q == ctx->peers.rank) continue;
+    void *pi = nullptr, *pc = nullptr;
+    CU(cudaIpcOpenMemHandle(&pi, h[2 * q + 0], cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&pc, h[2 * q + 1], cudaIpcMemLazyEnablePeerAccess));
+    ctx->p2p_opened[2 * q + 0] = pi;
+    ctx->p2p_opened[2 * q + 1] = pc;
+    ctx->peers.inbox[q] = (double*)pi;
+    ctx->peers.ctrl[q] = (ShardCtrl*)pc;
+  }
+  ctx->p2p_connected = true;
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_p2p_pointers(vina_ctx* ctx, void** inbox, void** ctrl)
+{
+  if (!ctx || !inbox || !ctrl || !ctx->p2p_inbox) return VINA_E_ARG;
+  *inbox = ctx->p2p_inbox;
+  *ctrl = ctx->p2p_ctrl;
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_p2p_connect_local(vina_ctx* ctx, void* const* inbox_ptrs, void* const* ctrl_ptrs)
+{
+  if (!ctx || !inbox_ptrs || !ctrl_ptrs || !ctx->p2p_inbox) return VINA_E_ARG;
+  for (int q = 0; q < ctx->peers.world; q++)
+  {
+    if (!inbox_ptrs[q] || !ctrl_ptrs[q]) return VINA_E_ARG;
+    ctx->peers.inbox[q] = (double*)inbox_ptrs[q];
+    ctx->peers.ctrl[q] = (ShardCtrl*)ctrl_ptrs[q];
+  }
+  ctx->p2p_connected = true;
+  return VINA_OK;
+}
+
+extern "C" int vina_shard_route_p2p(vina_ctx* ctx, int first, int count, int64_t scan_index_base, const double R[9],
+                                    const double p[3], const double cov_rot[9], const double cov_tsl[9], int phase)
+{
+  if (!ctx || first < 0 || count < 0 || !R || !p || !cov_rot || !cov_tsl || phase < 0 || phase > 2) return VINA_E_ARG;
+  if (!ctx->p2p_connected) return vn_fail(ctx, VINA_E_STATE, "vina_shard_route_p2p before the peers are connected");
+  if (first + count > ctx->n_pv[1])
+    return vn_fail(ctx, VINA_E_ARG, "slice [%d, %d) exceeds the %d down-sampled points", first, first + count,
+                   ctx->n_pv[1]);
+  PoseD x;
+  memcpy(x.R, R, 72);
+  memcpy(x.p, p, 24);
+  if (phase != 2) ++ctx->p2p_epoch;
+  ctx->launches += launch_shard_route_p2p(ctx->stream, ctx->pv[1], first, count, x, cov_rot, cov_tsl, ctx->cfg.voxel_size,
+                                          ctx->peers, ctx->d_sh_owner, ctx->d_sh_hist, ctx->d_sh_counts,
+                                          ctx->d_sh_counts + VINA_MAX_WORLD, ctx->d_p2p_base, ctx->p2p_epoch,
+                                          (long long)scan_index_base, ctx->p2p_cap, ctx->d_status, phase);
+  return vn_check_cuda(ctx, cudaGetLastError(), "p2p route");
+}
+
+extern "C" int vina_shard_insert_begin_p2p(vina_ctx* ctx, int win_ord, int32_t* n_recv, int32_t* local_roots,
+                                           int32_t* local_slide)
+{
+  if (!ctx || win_ord < 0 || win_ord >= ctx->cfg.win_size || !n_recv || !local_roots || !local_slide) return VINA_E_ARG;
+  if (!ctx->p2p_connected || ctx->p2p_epoch == 0) return vn_fail(ctx, VINA_E_STATE, "no routed scan to insert");
+  const int cap = (int)ctx->p2p_cap;
+  // wait for the peers' records (device side), unpack; the count stays on the device for the kernels below
+  ctx->launches += launch_shard_recv_p2p(ctx->stream, ctx->peers, ctx->p2p_epoch, ctx->d_n_recv, cap, ctx->pv[1], ctx->ins,
+                                         ctx->d_status);
+  ctx->ins.stamp++;
+  PoseD x;
+  memset(&x, 0, sizeof(x));
+  double z9[9] = { 0 };
+  ctx->launches += launch_map_insert_roots(ctx->stream, ctx->map, ctx->pv[1], ctx->d_n_recv, cap, ctx->ins, x, z9, z9, 1);
+  CU(cudaMemcpyAsync(ctx->h_sh_counts, ctx->ins.counters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_sh_counts + 1, ctx->map.slide_count + ctx->map.slide_cur, sizeof(int),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_sh_counts + 2, ctx->d_n_recv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *local_roots = ctx->h_sh_counts[0];
+  *local_slide = ctx->h_sh_counts[1];
+  *n_recv = ctx->h_sh_counts[2];
+  ctx->n_pv[1] = ctx->h_sh_counts[2];
+  ctx->n_down = ctx->n_pv[1];
+  ctx->n_down_pending = false;
+  return vn_check_status(ctx);
 }
 
 extern "C" int vina_shard_query_route(vina_ctx* ctx, int world, int first, int count, int64_t scan_index_base,

@@ -72,6 +72,16 @@ struct vina_ctx
   int* d_sh_hist = nullptr;
   int* d_sh_counts = nullptr;  // [VINA_MAX_WORLD] counts, then [VINA_MAX_WORLD + 1] segment starts
   int* h_sh_counts = nullptr;  // pinned
+  // P2P record exchange (vina_shard_*_p2p)
+  ShardPeers peers;
+  double* p2p_inbox = nullptr;
+  ShardCtrl* p2p_ctrl = nullptr;
+  long long p2p_cap = 0;
+  unsigned long long p2p_epoch = 0;
+  int* d_n_recv = nullptr;
+  long long* d_p2p_base = nullptr;  // my base offset in every owner's inbox (this scan)
+  void* p2p_opened[2 * VINA_MAX_WORLD] = { nullptr };  // IPC mappings to close
+  bool p2p_connected = false;
   int win_count_last = 0;
 
   // profiling

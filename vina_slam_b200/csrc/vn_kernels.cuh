@@ -125,6 +125,12 @@ int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int cou
                        unsigned char* owner, int* hist, int* counts, int* starts, double* out, long long gidx_base,
                        int* status, bool query);
 int launch_shard_unpack_query(cudaStream_t st, const double* rec, int n, const ScanView& scan);
+int launch_shard_route_p2p(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
+                           const double* rot_var, const double* tsl_var, double voxel_size, const ShardPeers& peers,
+                           unsigned char* owner, int* hist, int* counts, int* starts, long long* base,
+                           unsigned long long epoch, long long gidx_base, long long inbox_cap, int* status, int phase);
+int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned long long epoch, int* n_recv, int cap,
+                          const ScanView& scan, const InsertScratch& sc, int* status);
 int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc);
 int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)

@@ -102,6 +102,20 @@ struct NodeCold
   int children[8];
 };
 
+// control block of the P2P record exchange (shard_kernels.cu); lives in the owner's memory, written by peers
+struct ShardCtrl
+{
+  int counts[VINA_MAX_WORLD][VINA_MAX_WORLD];  // row r: records rank r sends to every destination
+  unsigned long long ready[VINA_MAX_WORLD];    // epoch at which row r is valid
+  unsigned long long done[VINA_MAX_WORLD];     // epoch at which rank r's records have landed in this rank's inbox
+};
+struct ShardPeers
+{
+  int rank, world;
+  double* inbox[VINA_MAX_WORLD];    // peer pointers (own entry = local buffer)
+  ShardCtrl* ctrl[VINA_MAX_WORLD];
+};
+
 struct PoseD
 {
   double R[9];  // column-major

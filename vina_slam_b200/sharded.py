@@ -73,13 +73,16 @@ class MapShard:
     """This rank's shard and the sliding-window bookkeeping of `map_update` (host/vina_pipeline.cpp;
     local_mapping.cpp:425-451, 489-546 with if_BA == 0)."""
 
-    def __init__(self, ctx: capi.Ctx, rank: int, world: int, device=None, group=None):
+    def __init__(self, ctx: capi.Ctx, rank: int, world: int, device=None, group=None, own_stream: bool = False):
         import torch
 
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        # one stream for the kernels of the ctx, torch's copies and the collectives (NCCL orders itself against it)
-        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # one stream for the kernels of the ctx, torch's copies and the collectives (NCCL orders itself against it);
+        # own_stream keeps the context's private stream instead - needed when several ranks live in one process
+        # and exchange through peer memory (a rank waiting on the device must not block the others' kernels)
+        if not own_stream:
+            ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.win_count = 0
         self.x_buf: List[Tuple[np.ndarray, np.ndarray]] = []
         self._send = None
@@ -115,6 +118,33 @@ class MapShard:
             self.ctx.map_margi(self.win_count, xb)
             self.x_buf.pop(0)
             self.win_count -= 1
+
+    # -- fused route + exchange over peer memory (NVLink): no staging, no collective call for the records
+    def p2p_setup(self, inbox_records: int):
+        """Allocate this rank's inbox and connect to the peers' (CUDA IPC handles all-gathered over the group)."""
+        import torch.distributed as dist
+
+        mine = self.ctx.shard_p2p_create(self.rank, self.world, inbox_records)
+        if self.world > 1:
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, mine, group=self.group)
+            self.ctx.shard_p2p_connect(b"".join(blobs))
+        self.p2p = True
+
+    def update_p2p(self, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col):
+        import torch
+        import torch.distributed as dist
+
+        self.push_pose(R_col, p)
+        self.ctx.shard_route_p2p(first, count, index_base, R_col, p, cov_rot_col, cov_tsl_col)
+        n, roots, slide = self.ctx.shard_insert_begin_p2p(self.win_count - 1)
+        tot = torch.tensor([roots, slide], dtype=torch.int64, device=self.device)
+        if self.world > 1 and dist.is_initialized():
+            dist.all_reduce(tot, group=self.group)  # also the barrier that frees the inboxes for the next scan
+        g = tot.cpu().tolist()
+        self.insert_finish(g[0], g[1])
+        self.recut_margi()
+        return n
 
     # -- the whole per-scan map update, collectives included
     def update(self, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col):
