@@ -815,3 +815,27 @@ def test_sharded_map_p2p_exchange_equals_single_gpu_map(oracle_lib, gpu_lib):
     single.close()
     for sh in shards:
         sh.ctx.close()
+
+
+def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
+    """150 scans through the full per-scan path (the window slides 150 times, leaves saturate, point_fix lists
+    are dropped and re-created, the slide map turns over): trajectory within 1 mm / 0.01 deg of the oracle at
+    every scan, same number of octree nodes at the end, pools within their capacity (no error raised)."""
+    cfg = small_cfg("hilti_xt32", 16, 300)  # the handheld path stays in free space for the whole run
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, gpu_own_downsample=True)
+    worst_p, worst_r, worst_gt = 0.0, 0.0, 0.0
+    for k in range(150):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        worst_p = max(worst_p, float(np.linalg.norm(sg["p"] - so["p"])))
+        worst_r = max(worst_r, synth.rot_err_deg(sg["R"], so["R"]))
+        worst_gt = max(worst_gt, float(np.linalg.norm(sg["p"] - sc.gt_p)))
+    gx.sync()  # raises if any pool overflowed on the way
+    assert worst_p < 1e-3 and worst_r < 0.01, (worst_p, worst_r)
+    assert worst_gt < 0.03, worst_gt
+    ng, no = gx.map_count(), od.map_count()
+    assert ng[0] == no[0] and ng[2] == no[2], (ng, no)
+    gx.close()
