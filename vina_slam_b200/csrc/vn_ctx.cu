@@ -324,6 +324,8 @@ extern "C" int vina_ctx_set_stream(vina_ctx* ctx, void* cuda_stream)
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t)cuda_stream;
   ctx->own_stream = false;
+  // uploads run on the copy stream: the new compute stream has to see the last one as well
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   return VINA_OK;
 }
 
