@@ -643,17 +643,22 @@ __global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, i
 }
 
 // The subdivision branch of OctoTree::recut (octree.cpp:375-387): fix_divide (:257-277), subdivide per
-// window frame (:279-300), release of the parent's SlideWindow (:384-387). One 128-thread block per
+// window frame (:279-300), release of the parent's SlideWindow (:384-387). One 256-thread block per
 // splitting leaf. Source classes in the reference's order: class 0 = point_fix, class 1+si =
 // sw->points[mp[si]]. All classes (and all segments of the point_fix chain) form ONE row stream that is
-// consumed 64 rows at a time - a leaf's ~20 short lists cost a handful of batches instead of one batch each.
+// consumed 256 rows at a time (one row per thread) - a leaf's ~20 short lists cost two or three batches
+// instead of one batch each. In steady state only a handful of leaves split per scan, so what matters in
+// this kernel is the latency of one block, not throughput.
 // Inside a batch the rows of each child are listed in stream order (stable compaction) and
 //   thread t < 72  owns the cluster scalar s = t % 9 of child k = t / 9 (pcr_add and pcr_fix /
 //                  pcrs_local[slot]) and applies that child's rows sequentially (exact sums, reference order;
 //                  the per-class cluster is flushed whenever the class of the next row changes),
 //   every thread   owns up to three (child, cov_add entry) pairs and sums that child's staged Bf_var terms.
-#define SPLIT_THREADS 128
-#define SPLIT_BATCH 64
+#define SPLIT_THREADS 256
+#define SPLIT_BATCH 256  // rows per batch = threads: every thread stages one row
+#define SPLIT_WARPS (SPLIT_BATCH / 32)
+#define SPLIT_PAIRS ((360 + SPLIT_THREADS - 1) / SPLIT_THREADS)
+#define SPLIT_SMEM ((SPLIT_BATCH * (19 + RED_STRIDE)) * sizeof(double))
 #define SPLIT_MAXSEG 128
 struct SplitSeg
 {
@@ -663,10 +668,21 @@ struct SplitSeg
   int cls;
 };
 
+// number of rows of child kk among the first i rows of the batch (i in 0..SPLIT_BATCH)
+__device__ __forceinline__ int split_rows_before(const unsigned int (*bm)[8], int kk, int i)
+{
+  int r = 0;
+  const int w = i >> 5;
+  for (int ww = 0; ww < w; ww++) r += __popc(bm[ww][kk]);
+  if (i & 31) r += __popc(bm[w][kk] & ((1u << (i & 31)) - 1u));
+  return r;
+}
+
 __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
 {
-  __shared__ double val[SPLIT_BATCH][19];  // per row: the 9 push() terms of the world point, then of the stored point
-  __shared__ double red[SPLIT_BATCH][RED_STRIDE];
+  extern __shared__ double split_smem[];
+  double(*val)[19] = reinterpret_cast<double(*)[19]>(split_smem);  // per row: the 9 push() terms of the world point, then of the stored point
+  double(*red)[RED_STRIDE] = reinterpret_cast<double(*)[RED_STRIDE]>(split_smem + SPLIT_BATCH * 19);
   __shared__ SplitSeg segs[SPLIT_MAXSEG];
   __shared__ int cbase[9];  // first slot of every child in the child-major row order of the batch
   __shared__ int cnt[11][8];
@@ -674,7 +690,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   __shared__ int fill[11][8];
   __shared__ int cls_first[11];
   __shared__ int kid[8];
-  __shared__ unsigned int bm[2][8];
+  __shared__ unsigned int bm[SPLIT_WARPS][8];  // per staging warp and child: which rows go to that child
   __shared__ int clsrow[SPLIT_BATCH];
   __shared__ int nseg, total, nfix, fixtot;
   __shared__ int wcnt_s[VINA_MAX_WIN], woff_s[VINA_MAX_WIN];
@@ -830,7 +846,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     // running sums (children are new: they start from zero)
     double clA = 0.0, clB = 0.0;  // thread t < 72: scalar L.ck of child my_k
     int cur_cls = -1;             // class clB currently accumulates
-    double cv[3] = { 0.0, 0.0, 0.0 };  // pairs p = t + 128 q < 360: child p / 45, entry p % 45
+    double cv[SPLIT_PAIRS];  // pairs p = t + SPLIT_THREADS q < 360: child p / 45, entry p % 45
+    for (int q = 0; q < SPLIT_PAIRS; q++) cv[q] = 0.0;
 
     // pass 2: the row stream, 64 rows at a time
     {
@@ -874,18 +891,17 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         if (t < 8)
         {
           int o = 0;
-          for (int k = 0; k < t; k++) o += __popc(bm[0][k]) + __popc(bm[1][k]);
+          for (int k = 0; k < t; k++) o += split_rows_before(bm, k, SPLIT_BATCH);
           cbase[t] = o;
-          if (t == 7) cbase[8] = o + __popc(bm[0][7]) + __popc(bm[1][7]);
+          if (t == 7) cbase[8] = o + split_rows_before(bm, 7, SPLIT_BATCH);
         }
         if (t < SPLIT_BATCH && kk >= 0)
         {
-          const unsigned long long mk = (unsigned long long)bm[0][kk] | ((unsigned long long)bm[1][kk] << 32);
-          const unsigned long long below = (1ull << t) - 1ull;
           const int cs = cls_first[cls] - base;  // batch-local index of the first row of this class
-          const unsigned long long from = cs <= 0 ? ~0ull : ~((1ull << cs) - 1ull);
-          int slot = __popcll(mk & below);
-          for (int k = 0; k < kk; k++) slot += __popc(bm[0][k]) + __popc(bm[1][k]);
+          const int before = split_rows_before(bm, kk, t);                       // ... inside its child
+          const int before_cls = before - split_rows_before(bm, kk, cs > 0 ? cs : 0);  // ... and inside its class
+          int slot = before;
+          for (int k = 0; k < kk; k++) slot += split_rows_before(bm, k, SPLIT_BATCH);
           const double* s3[2] = { pw, pr.p };
 #pragma unroll
           for (int w = 0; w < 2; w++)
@@ -909,7 +925,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           for (int e = 0; e < 45; e++) red[slot][e] = o[e];
           if (off[cls][kk] >= 0)
           {
-            const int dst = off[cls][kk] + fill[cls][kk] + __popcll(mk & below & from);
+            const int dst = off[cls][kk] + fill[cls][kk] + before_cls;
             if (cls == 0)
               M.fix_pool[dst] = pr;
             else
@@ -942,7 +958,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           }
         }
 #pragma unroll
-        for (int q = 0; q < 3; q++)
+        for (int q = 0; q < SPLIT_PAIRS; q++)
         {
           const int p = t + SPLIT_THREADS * q;
           if (p < 360)
@@ -979,7 +995,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       }
     }
 #pragma unroll
-    for (int q = 0; q < 3; q++)
+    for (int q = 0; q < SPLIT_PAIRS; q++)
     {
       const int p = t + SPLIT_THREADS * q;
       if (p < 360 && kid[p / 45] >= 0) M.cold[kid[p / 45]].cov_add[p % 45] = cv[q];
@@ -1389,6 +1405,14 @@ static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)
 
 int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf)
 {
+  static bool attr_set[64] = { false };
+  int dv = 0;
+  cudaGetDevice(&dv);
+  if (!attr_set[dv & 63])
+  {
+    cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPLIT_SMEM);
+    attr_set[dv & 63] = true;
+  }
   PoseBuf b = make_posebuf(h_xbuf, win_count);
   k_zero_ints<<<1, 32, 0, st>>>(LL.count, 8);
   int launches = 1;
@@ -1398,7 +1422,7 @@ int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, 
     launches++;
     if (layer < map.max_layer)
     {
-      k_split<<<592, SPLIT_THREADS, 0, st>>>(map, LL, layer, win_count, b);
+      k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, layer, win_count, b);
       launches++;
     }
   }
