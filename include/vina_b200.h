@@ -252,6 +252,28 @@ int vina_shard_query_accumulate(vina_ctx* ctx, const void* d_recv, int n, const 
  * finished (converged twice or out of iterations; the covariance has then been updated), 0 otherwise. */
 int vina_odom_iekf_host_begin(vina_ctx* ctx, int max_iter);
 int vina_odom_iekf_host_update(vina_ctx* ctx, const double sums34[34]);
+/* The same loop (VINA_SLAM::LioStateEstimation, odometry.cpp:64-255, against the sharded map) with the exchange and
+ * the update fused into the kernels - no collective call and no host synchronisation inside the loop. Per
+ * iteration every rank's routing kernel stores its queries straight into the owners' inboxes over peer memory
+ * (vina_shard_p2p_create / _connect; query region behind the map-build region), the owners run the accumulate
+ * kernel on what arrived, store their 34 sums into every peer's control block, and every rank adds the rows in
+ * rank order (bitwise the same total everywhere) and applies the update of odometry.cpp:192-230 to its copy of
+ * the device iterate; iterations after convergence return at once. x_curr (vina_odom_set_state / the previous
+ * scan) must be the same on every rank; points [first, first+count) of the FULL-scan pointVar set are this rank's
+ * share of the scan. phase VINA_SHARD_IEKF_ALL: stage, enqueue max_iter iterations, wait, install the result as
+ * x_curr (one process per GPU). The other phases split that for several ranks driven from one host thread (a kernel
+ * must never wait for work enqueued behind it): STAGE once on every rank; then per iteration ROUTE on every rank
+ * (never waits), SEND on every rank, EVAL on every rank, SOLVE on every rank; FINISH on every rank. Extra
+ * iterations after convergence are no-ops, like in the single-GPU loop. */
+#define VINA_SHARD_IEKF_ALL 0
+#define VINA_SHARD_IEKF_STAGE 1
+#define VINA_SHARD_IEKF_ROUTE 2
+#define VINA_SHARD_IEKF_SEND 3
+#define VINA_SHARD_IEKF_EVAL 4
+#define VINA_SHARD_IEKF_SOLVE 5
+#define VINA_SHARD_IEKF_FINISH 6
+int vina_odom_iekf_sharded_p2p(vina_ctx* ctx, int first, int count, int max_iter, int phase, int* iters_out,
+                               int* not_degenerate);
 
 /* ---- the per-scan loop body (src/pipeline/local_mapping.cpp:389-546), host
  * orchestration in C++ inside the library: a1 IMU propagation on the host

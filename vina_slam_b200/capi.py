@@ -71,8 +71,9 @@ EXPORTS = [
     "vina_batch_step_resident", "vina_batch_iekf_time", "vina_batch_sync", "vina_shard_query_route",
     "vina_shard_query_accumulate", "vina_odom_iekf_host_begin", "vina_odom_iekf_host_update",
     "vina_shard_p2p_create", "vina_shard_p2p_connect", "vina_shard_p2p_pointers", "vina_shard_p2p_connect_local",
-    "vina_shard_route_p2p", "vina_shard_insert_begin_p2p",
+    "vina_shard_route_p2p", "vina_shard_insert_begin_p2p", "vina_odom_iekf_sharded_p2p",
 ]
+SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
 SHARD_QUERY_DOUBLES = 10
 
@@ -388,6 +389,13 @@ class Ctx:
     def odom_iekf_host_update(self, sums34) -> bool:
         a = np.ascontiguousarray(sums34, dtype=np.float64)
         return self._ck(self.lib.vina_odom_iekf_host_update(self.h, _dp(a))) == 1
+
+    def odom_iekf_sharded_p2p(self, first: int, count: int, max_iter: int, phase: int = 0):
+        """vina_odom_iekf_sharded_p2p; returns (iterations, not_degenerate) - meaningful for phase ALL / FINISH."""
+        it, ok = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.vina_odom_iekf_sharded_p2p(self.h, C.c_int(first), C.c_int(count), C.c_int(max_iter),
+                                                     C.c_int(phase), C.byref(it), C.byref(ok)))
+        return it.value, ok.value
 
     # ---- odometry (host pipeline inside the library)
     def set_state(self, s: VinaState):

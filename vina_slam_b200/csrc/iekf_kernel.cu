@@ -274,13 +274,29 @@ __device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, do
   }
 }
 
+// a7 with a whole block: stage the iterate in shared memory (`smem` >= 660 doubles), let warp 0 solve, write back
+__device__ __forceinline__ void iekf_solve_block(IekfDev* dev, const double* fin, double* smem, int nthreads)
+{
+  double* ws = smem;
+  double* s_cov = smem + 384;
+  double* s_st = smem + 384 + 232;
+  for (int i = threadIdx.x; i < 225; i += nthreads) s_cov[i] = dev->cov[i];
+  if (threadIdx.x < 42) s_st[threadIdx.x] = reinterpret_cast<const double*>(dev)[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < 32) iekf_solve_warp(dev, fin, ws, s_cov, s_st, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x < 21) reinterpret_cast<double*>(dev)[threadIdx.x] = s_st[threadIdx.x];
+  if (reinterpret_cast<const int*>(ws + 368)[0])
+    for (int i = threadIdx.x; i < 225; i += nthreads) dev->cov[i] = s_cov[i];
+}
+
 // ---------------------------------------------------------------------------
 template <bool DEBUG>
 __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const __grid_constant__ IekfBatch bt)
 {
   const IekfSeq& q = bt.s[blockIdx.y];
   IekfDev* __restrict__ dev = q.dev;
-  if ((bt.mode & VN_IEKF_SOLVE) && dev->done) return;  // converged in an earlier iteration (uniform over the grid)
+  if ((bt.mode & (VN_IEKF_SOLVE | VN_IEKF_GATED)) && dev->done) return;  // converged earlier (uniform over the grid)
 
   extern __shared__ double smem[];
   __shared__ double cR[9], cp[3], crv[9], ctv[9];
@@ -331,7 +347,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
     const double pnt[3] = { __ldg(pi), __ldg(pi + pvs), __ldg(pi + 2 * pvs) };
     const double var6[6] = { __ldg(pi + 3 * pvs), __ldg(pi + 4 * pvs), __ldg(pi + 5 * pvs),
                              __ldg(pi + 6 * pvs), __ldg(pi + 7 * pvs), __ldg(pi + 8 * pvs) };
-    const int cached = live ? cache[ii] : -1;
+    const int cached = (live && !(bt.mode & VN_IEKF_NOCACHE)) ? cache[ii] : -1;
     double wld[3];
     rot_trans(cR, cp, pnt, wld);
     if (bt.variant & 16)  // experiment: streaming loads only
@@ -455,7 +471,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
         if ((double)dis_to_plane * (double)dis_to_plane < 9.0 * sigma_l)
         {
           flag = 1;
-          if (node != cached) cache[ii] = node;  // oc = this (octree.cpp:571-575)
+          if (node != cached && !(bt.mode & VN_IEKF_NOCACHE)) cache[ii] = node;  // oc = this (octree.cpp:571-575)
           const double Rinv = 1.0 / (0.0005 + sigma_l);
           // jac = [hat(p) R^T n ; n] = [p x m ; n]
           const double j0 = pnt[1] * m[2] - pnt[2] * m[1];
@@ -568,18 +584,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
   if (threadIdx.x == 0) *q.ticket = 0u;
   if (bt.mode & VN_IEKF_SOLVE)
   {
-    // stage the iterate in shared memory with the whole block, let one warp solve, write back
-    double* ws = smem;
-    double* s_cov = smem + 384;
-    double* s_st = smem + 384 + 232;
-    for (int i = threadIdx.x; i < 225; i += IEKF_THREADS) s_cov[i] = dev->cov[i];
-    if (threadIdx.x < 42) s_st[threadIdx.x] = reinterpret_cast<const double*>(dev)[threadIdx.x];
-    __syncthreads();
-    if (warp == 0) iekf_solve_warp(dev, fin, ws, s_cov, s_st, lane);
-    __syncthreads();
-    if (threadIdx.x < 21) reinterpret_cast<double*>(dev)[threadIdx.x] = s_st[threadIdx.x];
-    if (reinterpret_cast<const int*>(ws + 368)[0])
-      for (int i = threadIdx.x; i < 225; i += IEKF_THREADS) dev->cov[i] = s_cov[i];
+    iekf_solve_block(dev, fin, smem, IEKF_THREADS);
   }
   if (bt.mode & VN_IEKF_PUBLISH)
   {
@@ -607,6 +612,65 @@ __global__ void __launch_bounds__(256) k_publish_iterate(const IekfDev* __restri
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) *flag = seq;
+}
+
+// ---- the IEKF against a map sharded over GPUs: the 34 sums of every shard travel through peer memory ----------
+// (shard_kernels.cu has the record exchange). Every rank stores its sums into every peer's control block, then
+// raises the peers' flags; every rank adds the rows in rank order - bitwise the same total everywhere - and applies
+// the same update to its copy of the iterate: the ranks stay in lock step without a collective or the host.
+__global__ void __launch_bounds__(64) k_p2p_sums_publish(ShardPeers peers, const IekfDev* __restrict__ dev, unsigned long long epoch)
+{
+  if (dev->done) return;
+  if (threadIdx.x < VN_IEKF_NACC)
+  {
+    const double v = dev->sums[threadIdx.x];
+    for (int w = 0; w < peers.world; w++)
+      *reinterpret_cast<volatile double*>(&peers.ctrl[w]->sums[peers.rank][threadIdx.x]) = v;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x < peers.world)
+    *reinterpret_cast<volatile unsigned long long*>(&peers.ctrl[threadIdx.x]->sready[peers.rank]) = epoch;
+}
+
+#define P2P_SUMS_SPIN_LIMIT 20000000ll
+__global__ void __launch_bounds__(256) k_p2p_sums_solve(ShardPeers peers, IekfDev* __restrict__ dev, unsigned long long epoch,
+                                                        int* __restrict__ status)
+{
+  if (dev->done) return;
+  __shared__ double smem[672];
+  __shared__ double fin[VN_IEKF_NACC];
+  const ShardCtrl* me = peers.ctrl[peers.rank];
+  if (threadIdx.x < peers.world)
+  {
+    long long spins = 0;
+    while (*reinterpret_cast<const volatile unsigned long long*>(&me->sready[threadIdx.x]) != epoch)
+      if (++spins > P2P_SUMS_SPIN_LIMIT)
+      {
+        atomicOr(status, VN_ST_SPIN);
+        break;
+      }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x < VN_IEKF_NACC)
+  {
+    double v = 0.0;
+    for (int w = 0; w < peers.world; w++) v += *reinterpret_cast<const volatile double*>(&me->sums[w][threadIdx.x]);
+    fin[threadIdx.x] = v;
+    dev->sums[threadIdx.x] = v;
+  }
+  __syncthreads();
+  iekf_solve_block(dev, fin, smem, 256);
+}
+
+void launch_p2p_sums_publish(cudaStream_t st, const ShardPeers& peers, IekfDev* dev, unsigned long long epoch)
+{
+  k_p2p_sums_publish<<<1, 64, 0, st>>>(peers, dev, epoch);
+}
+void launch_p2p_sums_solve(cudaStream_t st, const ShardPeers& peers, IekfDev* dev, unsigned long long epoch, int* status)
+{
+  k_p2p_sums_solve<<<1, 256, 0, st>>>(peers, dev, epoch, status);
 }
 
 void launch_publish_iterate(cudaStream_t st, const IekfDev* src, IekfDev* dst_mapped, unsigned long long* flag_mapped,

@@ -177,12 +177,14 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* 
 }
 
 // my counts row -> every peer's table, then the peers' ready flags (one warp; lane = peer)
-__global__ void __launch_bounds__(32) k_p2p_publish(ShardPeers peers, const int* __restrict__ counts, unsigned long long epoch)
+__global__ void __launch_bounds__(32) k_p2p_publish(ShardPeers peers, const int* __restrict__ counts, unsigned long long epoch,
+                                                    int chan, const IekfDev* __restrict__ gate)
 {
+  if (gate && gate->done) return;  // the sharded IEKF has converged (on every rank alike)
   const int w = threadIdx.x;
   if (w < peers.world)
   {
-    ShardCtrl* pc = peers.ctrl[w];
+    ShardChan* pc = &peers.ctrl[w]->ch[chan];
     for (int k = 0; k < peers.world; k++) *reinterpret_cast<volatile int*>(&pc->counts[peers.rank][k]) = counts[k];
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(&pc->ready[peers.rank]) = epoch;
@@ -192,10 +194,12 @@ __global__ void __launch_bounds__(32) k_p2p_publish(ShardPeers peers, const int*
 // wait for every rank's row in MY table and derive my base offset at every owner. Only this single warp ever
 // spins, so a waiting rank cannot starve the kernels it waits for.
 __global__ void __launch_bounds__(32)
-    k_p2p_base(ShardPeers peers, unsigned long long epoch, long long* __restrict__ base, int* __restrict__ status)
+    k_p2p_base(ShardPeers peers, unsigned long long epoch, long long* __restrict__ base, int* __restrict__ status, int chan,
+               const IekfDev* __restrict__ gate)
 {
+  if (gate && gate->done) return;
   const int w = threadIdx.x;
-  const ShardCtrl* me = peers.ctrl[peers.rank];
+  const ShardChan* me = &peers.ctrl[peers.rank]->ch[chan];
   if (w < peers.world)
   {
     long long spins = 0;
@@ -260,18 +264,25 @@ __global__ void __launch_bounds__(SH_THREADS)
 }
 
 // my records have landed everywhere: raise the peers' done flags
-__global__ void __launch_bounds__(32) k_p2p_signal(ShardPeers peers, unsigned long long epoch)
+__global__ void __launch_bounds__(32) k_p2p_signal(ShardPeers peers, unsigned long long epoch, int chan,
+                                                   const IekfDev* __restrict__ gate)
 {
+  if (gate && gate->done) return;
   __threadfence_system();
   if (threadIdx.x < peers.world)
-    *reinterpret_cast<volatile unsigned long long*>(&peers.ctrl[threadIdx.x]->done[peers.rank]) = epoch;
+    *reinterpret_cast<volatile unsigned long long*>(&peers.ctrl[threadIdx.x]->ch[chan].done[peers.rank]) = epoch;
 }
 
 // wait for every rank's records in MY inbox; the number of records received
 __global__ void __launch_bounds__(32) k_p2p_wait(ShardPeers peers, unsigned long long epoch, int* __restrict__ n_recv,
-                                                 int* __restrict__ status)
+                                                 int* __restrict__ status, int chan, const IekfDev* __restrict__ gate)
 {
-  ShardCtrl* me = peers.ctrl[peers.rank];
+  if (gate && gate->done)
+  {
+    if (threadIdx.x == 0) *n_recv = 0;
+    return;
+  }
+  const ShardChan* me = &peers.ctrl[peers.rank]->ch[chan];
   int mine = 0;
   if (threadIdx.x < peers.world)
   {
@@ -314,16 +325,16 @@ int launch_shard_route_p2p(cudaStream_t st, const ScanView& scan, int first, int
     // phase A never waits: owners, counts, my row to every peer
     k_shard_count<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, voxel_size, peers.world, owner, hist, status);
     k_shard_offsets<<<1, 32 * VN_MAX_WORLD, 0, st>>>(hist, nblk, peers.world, counts, starts);
-    k_p2p_publish<<<1, 32, 0, st>>>(peers, counts, epoch);
+    k_p2p_publish<<<1, 32, 0, st>>>(peers, counts, epoch, VN_CHAN_BUILD, nullptr);
     launches += 3;
   }
   if (phase != 1)
   {
     // phase B waits for the peers' rows (one spinning warp), then stores the records and signals
-    k_p2p_base<<<1, 32, 0, st>>>(peers, epoch, base, status);
+    k_p2p_base<<<1, 32, 0, st>>>(peers, epoch, base, status, VN_CHAN_BUILD, nullptr);
     k_p2p_scatter<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, x, cv, peers, owner, hist, base, gidx_base, inbox_cap,
                                                status);
-    k_p2p_signal<<<1, 32, 0, st>>>(peers, epoch);
+    k_p2p_signal<<<1, 32, 0, st>>>(peers, epoch, VN_CHAN_BUILD, nullptr);
     launches += 3;
   }
   return launches;
@@ -332,9 +343,124 @@ int launch_shard_route_p2p(cudaStream_t st, const ScanView& scan, int first, int
 int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned long long epoch, int* n_recv, int cap,
                           const ScanView& scan, const InsertScratch& sc, int* status)
 {
-  k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status);
+  k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status, VN_CHAN_BUILD, nullptr);
   k_shard_unpack_n<<<(cap + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(peers.inbox[peers.rank], n_recv, scan, sc);
   return 2;
+}
+
+// ---- the association query over the same fused exchange (pose and convergence flag from the device iterate) ----
+__global__ void __launch_bounds__(SH_THREADS)
+    k_shard_count_q(ScanView scan, int first, int count, const IekfDev* __restrict__ it, double voxel_size, int world,
+                    unsigned char* __restrict__ owner, int* __restrict__ hist, int* __restrict__ status)
+{
+  if (it->done) return;
+  __shared__ int h[VN_MAX_WORLD];
+  __shared__ double R[9], p[3];
+  if (threadIdx.x < VN_MAX_WORLD) h[threadIdx.x] = 0;
+  if (threadIdx.x < 9) R[threadIdx.x] = it->R[threadIdx.x];
+  if (threadIdx.x < 3) p[threadIdx.x] = it->p[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  if (i < count)
+  {
+    const int s = first + i;
+    const double pnt[3] = { scan.p[0][s], scan.p[1][s], scan.p[2][s] };
+    double pw[3];
+    rot_trans(R, p, pnt, pw);
+    long long kc[3];
+    for (int k = 0; k < 3; k++) kc[k] = voxel_coord(pw[k], voxel_size);
+    unsigned long long key;
+    int ow = 0;
+    if (pack_key(kc[0], kc[1], kc[2], &key)) ow = shard_owner(key, world);  // (a key out of range matches nothing anywhere)
+    owner[i] = (unsigned char)ow;
+    atomicAdd(&h[ow], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < world) hist[blockIdx.x * world + threadIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+    k_p2p_scatter_q(ScanView scan, int first, int count, ShardPeers peers, const unsigned char* __restrict__ owner,
+                    const int* __restrict__ hist, const long long* __restrict__ base, long long gidx_base, long long inbox_cap,
+                    int* __restrict__ status, const IekfDev* __restrict__ it)
+{
+  if (it->done) return;
+  __shared__ int wcnt[SH_WARPS][VN_MAX_WORLD];
+  const int world = peers.world;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  const int ow = i < count ? (int)owner[i] : -1;
+  int myrank = 0;
+  for (int w = 0; w < world; w++)
+  {
+    const unsigned int m = __ballot_sync(0xffffffffu, ow == w);
+    if (ow == w) myrank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[warp][w] = __popc(m);
+  }
+  __syncthreads();
+  if (ow >= 0)
+  {
+    int inblk = 0;
+    for (int ww = 0; ww < warp; ww++) inblk += wcnt[ww][ow];
+    const long long pos = base[ow] + hist[blockIdx.x * world + ow] + inblk + myrank;
+    if (pos >= inbox_cap)
+      atomicOr(status, VN_ST_WIN_FULL);
+    else
+    {
+      const int s = first + i;
+      // the query region follows the map-build region in the owner's inbox
+      double* r = peers.inbox[ow] + inbox_cap * VINA_SHARD_RECORD_DOUBLES + pos * VINA_SHARD_QUERY_DOUBLES;
+      for (int k = 0; k < 3; k++) r[k] = scan.p[k][s];
+      for (int k = 0; k < 6; k++) r[3 + k] = scan.v[k][s];
+      reinterpret_cast<long long*>(r)[9] = gidx_base + s;
+    }
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+    k_shard_unpack_query_n(const double* __restrict__ rec, const int* __restrict__ n_ptr, ScanView scan)
+{
+  const int i = blockIdx.x * SH_THREADS + threadIdx.x;
+  if (i >= *n_ptr) return;
+  const double* r = rec + (size_t)i * VINA_SHARD_QUERY_DOUBLES;
+  for (int k = 0; k < 3; k++) scan.p[k][i] = r[k];
+  for (int k = 0; k < 6; k++) scan.v[k][i] = r[3 + k];
+}
+
+// one iteration's routing of the association queries: phase 1 never waits (owners, counts, my row to the peers),
+// phase 2 waits for the peers' rows, stores the queries into the owners' inboxes and signals, phase 3 waits for
+// the peers' queries and unpacks them into `recv_set`. phase 0 = all three.
+int launch_shard_query_p2p(cudaStream_t st, const ScanView& scan, int first, int count, const IekfDev* it,
+                           double voxel_size, const ShardPeers& peers, unsigned char* owner, int* hist, int* counts,
+                           int* starts, long long* base, unsigned long long epoch, long long inbox_cap, int* n_recv,
+                           const ScanView& recv_set, int* status, int phase)
+{
+  const int nblk = count <= 0 ? 1 : (count + SH_THREADS - 1) / SH_THREADS;
+  int launches = 0;
+  if (phase == 0 || phase == 1)
+  {
+    k_shard_count_q<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, it, voxel_size, peers.world, owner, hist, status);
+    k_shard_offsets<<<1, 32 * VN_MAX_WORLD, 0, st>>>(hist, nblk, peers.world, counts, starts);
+    k_p2p_publish<<<1, 32, 0, st>>>(peers, counts, epoch, VN_CHAN_QUERY, it);
+    launches += 3;
+  }
+  if (phase == 0 || phase == 2)
+  {
+    k_p2p_base<<<1, 32, 0, st>>>(peers, epoch, base, status, VN_CHAN_QUERY, it);
+    k_p2p_scatter_q<<<nblk, SH_THREADS, 0, st>>>(scan, first, count, peers, owner, hist, base, 0, inbox_cap, status, it);
+    k_p2p_signal<<<1, 32, 0, st>>>(peers, epoch, VN_CHAN_QUERY, it);
+    launches += 3;
+  }
+  if (phase == 0 || phase == 3)
+  {
+    k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status, VN_CHAN_QUERY, it);
+    const int cap = (int)inbox_cap;
+    k_shard_unpack_query_n<<<(cap + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(
+        peers.inbox[peers.rank] + inbox_cap * VINA_SHARD_RECORD_DOUBLES, n_recv, recv_set);
+    launches += 2;
+  }
+  return launches;
 }
 
 int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,

@@ -885,7 +885,8 @@ extern "C" int vina_shard_p2p_create(vina_ctx* ctx, int rank, int world, int64_t
   int r = ensure_shard(ctx);
   if (r) return r;
   if (inbox_records > ctx->cap_points) inbox_records = ctx->cap_points;  // the insert works on max_scan_points at most
-  CU(dalloc(&ctx->p2p_inbox, (size_t)inbox_records * VINA_SHARD_RECORD_DOUBLES, false));
+  // two regions: map-build records (13 doubles each), then association queries (10 doubles each)
+  CU(dalloc(&ctx->p2p_inbox, (size_t)inbox_records * (VINA_SHARD_RECORD_DOUBLES + VINA_SHARD_QUERY_DOUBLES), false));
   CU(dalloc(&ctx->p2p_ctrl, 1));
   CU(dalloc(&ctx->d_n_recv, 1));
   CU(dalloc(&ctx->d_p2p_base, VINA_MAX_WORLD));
@@ -1043,6 +1044,56 @@ extern "C" int vina_shard_query_accumulate(vina_ctx* ctx, const void* d_recv, in
   ctx->launches += 1;
   CU(cudaMemcpyAsync(d_sums34, ctx->d_iekf->sums, VN_IEKF_NACC * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return VINA_OK;
+}
+
+// The IEKF loop against the sharded map with everything on the device (see include/vina_b200.h): per iteration
+// route + peer stores of the queries (query channel of the inboxes), k_iekf on what arrived, the 34 sums to every
+// peer, rank-ordered total and update. The device iterate (ctx->d_iekf) must be staged on every rank alike.
+int vn_shard_iekf_enqueue(vina_ctx* ctx, int first, int count, int max_iter, int part)
+{
+  if (!ctx->p2p_connected) return vn_fail(ctx, VINA_E_STATE, "sharded IEKF before the peers are connected");
+  if (first < 0 || count < 0 || first + count > ctx->n_pv[0])
+    return vn_fail(ctx, VINA_E_ARG, "slice [%d, %d) exceeds the %d scan points", first, first + count, ctx->n_pv[0]);
+  const int cap = (int)ctx->p2p_cap;
+  ctx->iekf_which = 1;  // the received queries are evaluated from the query set pv[1]
+  ctx->n_pv[1] = 0;     // (its size lives on the device: d_n_recv)
+  ctx->n_down = 0;
+  ctx->n_down_pending = false;
+  ctx->iekf_blocks = iekf_grid_blocks(cap, ctx->sm_count);
+  ctx->dbg_valid = false;
+  IekfBatch bt;
+  bt.mode = VN_IEKF_GATED | VN_IEKF_NOCACHE;
+  bt.variant = 0;
+  vn_iekf_fill_seq(ctx, &bt.s[0], false);
+  bt.s[0].n_ptr = ctx->d_n_recv;
+  bt.s[0].n_host = 0;
+  // part 0: max_iter whole iterations; 1..4: the four parts of ONE iteration (1 never waits; 2 waits for the
+  // peers' part 1, 3 for their part 2, 4 for their part 3) - several ranks driven from one host thread
+  const int iters = part == 0 ? max_iter : 1;
+  for (int it = 0; it < iters; it++)
+  {
+    if (part <= 1) ++ctx->p2p_qepoch;
+    const unsigned long long epoch = ctx->p2p_qepoch;
+    for (int ph = 1; ph <= 3; ph++)
+      if (part == 0 || part == ph)
+        ctx->launches += launch_shard_query_p2p(ctx->stream, ctx->pv[0], first, count, ctx->d_iekf, ctx->cfg.voxel_size,
+                                                ctx->peers, ctx->d_sh_owner, ctx->d_sh_hist, ctx->d_sh_counts,
+                                                ctx->d_sh_counts + VINA_MAX_WORLD, ctx->d_p2p_base, epoch, ctx->p2p_cap,
+                                                ctx->d_n_recv, ctx->pv[1], ctx->d_status, ph);
+    if (part == 0 || part == 3)
+    {
+      int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
+      if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
+      launch_p2p_sums_publish(ctx->stream, ctx->peers, ctx->d_iekf, epoch);
+      ctx->launches += 2;
+    }
+    if (part == 0 || part == 4)
+    {
+      launch_p2p_sums_solve(ctx->stream, ctx->peers, ctx->d_iekf, epoch, ctx->d_status);
+      ctx->launches += 1;
+    }
+  }
+  return vn_check_cuda(ctx, cudaGetLastError(), "sharded IEKF loop");
 }
 
 extern "C" int vina_shard_insert_begin(vina_ctx* ctx, const void* d_recv, int n, int win_ord, int32_t* local_roots,

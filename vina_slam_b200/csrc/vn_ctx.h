@@ -78,6 +78,7 @@ struct vina_ctx
   ShardCtrl* p2p_ctrl = nullptr;
   long long p2p_cap = 0;
   unsigned long long p2p_epoch = 0;
+  unsigned long long p2p_qepoch = 0;  // query channel: one epoch per IEKF iteration
   int* d_n_recv = nullptr;
   long long* d_p2p_base = nullptr;  // my base offset in every owner's inbox (this scan)
   void* p2p_opened[2 * VINA_MAX_WORLD] = { nullptr };  // IPC mappings to close
@@ -105,4 +106,6 @@ int vn_iterate_publish(vina_ctx* c, cudaStream_t st);
 int vn_iterate_wait(vina_ctx* c);
 // fill the launch descriptor of this context's sequence (R/p come from c->d_iekf)
 void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
+// enqueue max_iter iterations of the IEKF against the sharded map, exchange and update on the device (vn_ctx.cu)
+int vn_shard_iekf_enqueue(vina_ctx* c, int first, int count, int max_iter, int part);
 void odom_host_destroy(OdomHost* o);

@@ -46,6 +46,8 @@ struct IekfDev
 
 #define VN_IEKF_PUBLISH 1  // write the 34 sums + sequence number to mapped host memory (low-level ABI, tests)
 #define VN_IEKF_SOLVE 2    // last block runs the IEKF update on the device state
+#define VN_IEKF_GATED 4    // return at once when the device iterate says the loop has finished (sharded loop)
+#define VN_IEKF_NOCACHE 8  // no per-point leaf cache: every point looks its voxel up (queries that crossed GPUs)
 
 // one sequence of a (batched) k_iekf launch
 struct IekfSeq
@@ -129,6 +131,13 @@ int launch_shard_route_p2p(cudaStream_t st, const ScanView& scan, int first, int
                            const double* rot_var, const double* tsl_var, double voxel_size, const ShardPeers& peers,
                            unsigned char* owner, int* hist, int* counts, int* starts, long long* base,
                            unsigned long long epoch, long long gidx_base, long long inbox_cap, int* status, int phase);
+int launch_shard_query_p2p(cudaStream_t st, const ScanView& scan, int first, int count, const IekfDev* it,
+                           double voxel_size, const ShardPeers& peers, unsigned char* owner, int* hist, int* counts,
+                           int* starts, long long* base, unsigned long long epoch, long long inbox_cap, int* n_recv,
+                           const ScanView& recv_set, int* status, int phase);
+// the 34 sums of every shard -> every rank, summed in rank order, then the IEKF update (iekf_kernel.cu)
+void launch_p2p_sums_publish(cudaStream_t st, const ShardPeers& peers, IekfDev* dev, unsigned long long epoch);
+void launch_p2p_sums_solve(cudaStream_t st, const ShardPeers& peers, IekfDev* dev, unsigned long long epoch, int* status);
 int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned long long epoch, int* n_recv, int cap,
                           const ScanView& scan, const InsertScratch& sc, int* status);
 int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc);

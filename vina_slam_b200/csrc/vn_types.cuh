@@ -103,11 +103,19 @@ struct NodeCold
 };
 
 // control block of the P2P record exchange (shard_kernels.cu); lives in the owner's memory, written by peers
-struct ShardCtrl
+struct ShardChan
 {
   int counts[VINA_MAX_WORLD][VINA_MAX_WORLD];  // row r: records rank r sends to every destination
   unsigned long long ready[VINA_MAX_WORLD];    // epoch at which row r is valid
   unsigned long long done[VINA_MAX_WORLD];     // epoch at which rank r's records have landed in this rank's inbox
+};
+#define VN_CHAN_BUILD 0  // map-build records (13 doubles), first region of the inbox
+#define VN_CHAN_QUERY 1  // association queries (10 doubles), second region of the inbox
+struct ShardCtrl
+{
+  ShardChan ch[2];
+  double sums[VINA_MAX_WORLD][40];             // row r: the 34 IEKF sums of rank r's shard (this iteration)
+  unsigned long long sready[VINA_MAX_WORLD];   // epoch at which row r of `sums` is valid
 };
 struct ShardPeers
 {

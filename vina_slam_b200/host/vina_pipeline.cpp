@@ -891,6 +891,44 @@ int vina_odom_iekf_host_update(vina_ctx* ctx, const double sums34[34])
   return fin ? 1 : 0;
 }
 
+// LioStateEstimation against a map sharded over GPUs, the whole loop on the devices (vn_shard_iekf_enqueue).
+// No host synchronisation inside the loop. Phases: include/vina_b200.h.
+int vina_odom_iekf_sharded_p2p(vina_ctx* ctx, int first, int count, int max_iter, int phase, int* iters_out,
+                               int* not_degenerate)
+{
+  if (!ctx || phase < VINA_SHARD_IEKF_ALL || phase > VINA_SHARD_IEKF_FINISH) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  const int num_max_iter = max_iter > 0 ? max_iter : 20;
+  int r;
+  if (phase == VINA_SHARD_IEKF_ALL || phase == VINA_SHARD_IEKF_STAGE)
+  {
+    stage_iterate(o->x_curr, num_max_iter, ctx->h_iekf);
+    r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->d_iekf, ctx->h_iekf, sizeof(IekfDev), cudaMemcpyHostToDevice, ctx->stream),
+                      "iterate upload");
+    if (r) return r;
+  }
+  if (phase == VINA_SHARD_IEKF_ALL)
+    r = vn_shard_iekf_enqueue(ctx, first, count, num_max_iter, 0);
+  else if (phase >= VINA_SHARD_IEKF_ROUTE && phase <= VINA_SHARD_IEKF_SOLVE)
+    r = vn_shard_iekf_enqueue(ctx, first, count, 1, phase - VINA_SHARD_IEKF_ROUTE + 1);
+  else
+    r = VINA_OK;
+  if (r) return r;
+  if (phase == VINA_SHARD_IEKF_ALL || phase == VINA_SHARD_IEKF_FINISH)
+  {
+    r = vn_iterate_publish(ctx, ctx->stream);
+    if (r) return r;
+    r = vn_iterate_wait(ctx);
+    if (r) return r;
+    int ok = 0;
+    unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, &ok);
+    if (iters_out) *iters_out = o->last_iters;
+    if (not_degenerate) *not_degenerate = ok;
+    return vn_check_status(ctx);
+  }
+  return VINA_OK;
+}
+
 int vina_odom_map_update(vina_ctx* ctx)
 {
   if (!ctx) return VINA_E_ARG;

@@ -246,3 +246,11 @@ class ShardedIekf:
             if ctx.odom_iekf_host_update(sums.cpu().numpy()):
                 return it + 1
         return max_iter
+
+    def run_p2p(self, first: int, count: int, max_iter: int = 4):
+        """The same loop with the exchange and the update fused into the kernels (vina_odom_iekf_sharded_p2p):
+        queries stored into the owners' inboxes over peer memory, the 34 sums to every peer's control block, the
+        update on every rank's device iterate - no collective call and no host synchronisation inside the loop.
+        Needs MapShard.p2p_setup. Returns the number of iterations."""
+        it, _ = self.sh.ctx.odom_iekf_sharded_p2p(first, count, max_iter, capi.SHARD_IEKF_ALL)
+        return it
