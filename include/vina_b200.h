@@ -324,6 +324,13 @@ int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap);
 int vina_get_timings(vina_ctx* ctx, vina_timings* t);
 /* record per-stage CUDA-event timings (adds event records + one sync per step) */
 int vina_set_profiling(vina_ctx* ctx, int on);
+/* vina_odom_step / _step_resident schedule (default on): down-sampling and the var_init of the map's point set run
+ * on a side stream concurrently with the IEKF loop, and the map update (pvec_update, cut_voxel_multi, multi_recut,
+ * multi_margi - local_mapping.cpp:425-507) is enqueued behind the loop with the new pose and the posterior
+ * covariance blocks read from the device iterate, before the result has reached the host. off: everything in
+ * stream order with the host in between (the schedule the per-stage timers of vina_set_profiling see). Both give
+ * bitwise the same states and maps. */
+int vina_set_overlap(vina_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

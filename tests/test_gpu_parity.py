@@ -901,7 +901,9 @@ def test_sharded_iekf_fused_exchange_matches_single_gpu(oracle_lib, gpu_lib):
             torch.cuda.synchronize()
             tot = np.zeros(34)
             for q, r_ in zip(iek, recvs):
-                tot += q.accumulate(r_, Rc, p, rv, tv).cpu().numpy()
+                sums = q.accumulate(r_, Rc, p, rv, tv)
+                q.sh.ctx.sync()  # the contexts run on private streams here: torch's copy below does not wait for them
+                tot += sums.cpu().numpy()
             done = [sh.ctx.odom_iekf_host_update(tot) for sh in shards]
             it_host = it + 1
             if done[0]:
@@ -921,6 +923,38 @@ def test_sharded_iekf_fused_exchange_matches_single_gpu(oracle_lib, gpu_lib):
     single.close()
     for sh in shards:
         sh.ctx.close()
+
+
+def test_overlapped_step_is_bitwise_the_serial_step(oracle_lib, gpu_lib):
+    """vina_set_overlap: down-sampling on the side stream and the map update enqueued behind the IEKF loop with the
+    pose read from the device iterate must give bitwise the states and the map of the serial schedule (host in
+    between) - over enough scans for the window to slide, leaves to split and the early scans to be marginalised."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq = synth.Sequence(cfg)
+    ctxs = [gpu_lib.Ctx(cfg, **SMALL_CAPS) for _ in range(2)]
+    ctxs[0].set_overlap(True)
+    ctxs[1].set_overlap(False)
+    for k in range(cfg.win_size):
+        sc = seq.next_scan(deskewed=True)
+        for gx in ctxs:
+            gx.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    for gx in ctxs:
+        gx.set_imu_anchor(sc.end_time, sc.imu[-1])
+    for k in range(25):
+        sc = seq.next_scan()
+        sa, sb = [gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)) for gx in ctxs]
+        for f in ("R", "p", "v", "bg", "ba", "cov"):
+            assert np.array_equal(sa[f], sb[f]), (k, f)
+        assert np.linalg.norm(sa["p"] - sc.gt_p) < 0.02
+    for gx in ctxs:
+        gx.sync()
+    ma, mb = [sort_nodes(gx.map_export()) for gx in ctxs]
+    assert ma.shape[0] == mb.shape[0] > 2000
+    for f in ma.dtype.names:
+        assert np.array_equal(ma[f], mb[f]), f
+    assert ctxs[0].window()[0] == ctxs[1].window()[0]
+    for gx in ctxs:
+        gx.close()
 
 
 def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):

@@ -72,6 +72,7 @@ EXPORTS = [
     "vina_shard_query_accumulate", "vina_odom_iekf_host_begin", "vina_odom_iekf_host_update",
     "vina_shard_p2p_create", "vina_shard_p2p_connect", "vina_shard_p2p_pointers", "vina_shard_p2p_connect_local",
     "vina_shard_route_p2p", "vina_shard_insert_begin_p2p", "vina_odom_iekf_sharded_p2p",
+    "vina_set_overlap",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -389,6 +390,9 @@ class Ctx:
     def odom_iekf_host_update(self, sums34) -> bool:
         a = np.ascontiguousarray(sums34, dtype=np.float64)
         return self._ck(self.lib.vina_odom_iekf_host_update(self.h, _dp(a))) == 1
+
+    def set_overlap(self, on: bool):
+        self._ck(self.lib.vina_set_overlap(self.h, C.c_int(1 if on else 0)))
 
     def odom_iekf_sharded_p2p(self, first: int, count: int, max_iter: int, phase: int = 0):
         """vina_odom_iekf_sharded_p2p; returns (iterations, not_degenerate) - meaningful for phase ALL / FINISH."""

@@ -23,6 +23,31 @@ struct Cov2
 {
   double rot[9], tsl[9];
 };
+// The newest frame's pose may still be on its way to the host when the map update is enqueued (the IEKF loop
+// runs on the device): kernels then read frame `idx` from the device iterate instead of the host's copy - the
+// same doubles the host receives a moment later (k_publish_iterate), so nothing changes numerically.
+struct LivePose
+{
+  const IekfDev* dev;  // nullptr: every pose comes from the host
+  int idx;
+};
+__device__ __forceinline__ void pose_sel(const PoseBuf& xb, const LivePose& lv, int i, double (&R)[9], double (&p)[3])
+{
+  if (lv.dev && i == lv.idx)
+  {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = lv.dev->R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = lv.dev->p[k];
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = xb.x[i].R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = xb.x[i].p[k];
+  }
+}
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *((const volatile int*)p); }
 
@@ -63,9 +88,21 @@ __device__ int make_child(const MapView& M, int parent, int ci)
 // insert, phase 1: pvec_update (point_utils.cpp:54-65) + voxel key + root find/create
 // (voxel_map.cpp:53-87).
 __global__ void __launch_bounds__(256)
-    k_insert_root(MapView M, ScanView scan, const int* __restrict__ n_ptr, int n_host, InsertScratch sc, PoseD x,
-                  Cov2 cv, int pre)
+    k_insert_root(MapView M, ScanView scan, const int* __restrict__ n_ptr, int n_host, InsertScratch sc, PoseD x_host,
+                  Cov2 cv_host, int pre, const IekfDev* __restrict__ live)
 {
+  // pose and posterior covariance blocks of pvec_update: from the host, or straight from the device iterate
+  __shared__ PoseD x;
+  __shared__ Cov2 cv;
+  if (threadIdx.x < 9)
+  {
+    const int t = threadIdx.x, a = t % 3, b = t / 3;
+    x.R[t] = live ? live->R[t] : x_host.R[t];
+    cv.rot[t] = live ? live->cov[a + 15 * b] : cv_host.rot[t];
+    cv.tsl[t] = live ? live->cov[(3 + a) + 15 * (3 + b)] : cv_host.tsl[t];
+    if (t < 3) x.p[t] = live ? live->p[t] : x_host.p[t];
+  }
+  __syncthreads();
   int n = n_ptr ? *n_ptr : n_host;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -678,7 +715,8 @@ __device__ __forceinline__ int split_rows_before(const unsigned int (*bm)[8], in
   return r;
 }
 
-__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb)
+__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb,
+                                                         LivePose lv)
 {
   extern __shared__ double split_smem[];
   double(*val)[19] = reinterpret_cast<double(*)[19]>(split_smem);  // per row: the 9 push() terms of the world point, then of the stored point
@@ -792,7 +830,11 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           pw[2] = src->p[2];
         }
         else
-          rot_trans(xb.x[cls - 1].R, xb.x[cls - 1].p, src->p, pw);
+        {
+          double xr[9], xp[3];
+          pose_sel(xb, lv, cls - 1, xr, xp);
+          rot_trans(xr, xp, src->p, pw);
+        }
         atomicAdd(&cnt[cls][child_index(pw, vc)], 1);
       }
     }
@@ -874,7 +916,11 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
               pw[2] = pr.p[2];
             }
             else
-              rot_trans(xb.x[cls - 1].R, xb.x[cls - 1].p, pr.p, pw);
+            {
+              double xr[9], xp[3];
+              pose_sel(xb, lv, cls - 1, xr, xp);
+              rot_trans(xr, xp, pr.p, pw);
+            }
             kk = child_index(pw, vc);
           }
 #pragma unroll
@@ -1104,8 +1150,8 @@ __device__ void plane_update(NodeHot& h, NodeCold& c)
 // leaf branch of OctoTree::margi (octree.cpp:397-484), mgsize = 1. The fold of the oldest frame's points into
 // point_fix (octree.cpp:452-459) is returned as a copy job (source, destination offset, count) that the
 // calling warp executes cooperatively.
-__device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf& xb, const PointRec*& job_src,
-                           int& job_off, int& job_np)
+__device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf& xb, const LivePose& lv,
+                           const PointRec*& job_src, int& job_off, int& job_np)
 {
   NodeHot& h = M.hot[n];
   NodeCold& c = M.cold[n];
@@ -1117,7 +1163,12 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
   if (c.opt_state >= 0)
   {
     c.opt_state = -1;
-    if (c.pcrs_local[s0].N != 0) cluster_transform(world0, c.pcrs_local[s0], xb.x[0].R, xb.x[0].p);
+    if (c.pcrs_local[s0].N != 0)
+    {
+      double xr[9], xp[3];
+      pose_sel(xb, lv, 0, xr, xp);
+      cluster_transform(world0, c.pcrs_local[s0], xr, xp);
+    }
   }
   else
   {
@@ -1128,7 +1179,9 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
       if (loc.N != 0)
       {
         Cluster w;
-        cluster_transform(w, loc, xb.x[i].R, xb.x[i].p);
+        double xr[9], xp[3];
+        pose_sel(xb, lv, i, xr, xp);
+        cluster_transform(w, loc, xr, xp);
         if (i == 0) world0 = w;
         cluster_add(add, w);
       }
@@ -1185,7 +1238,7 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
 }
 
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
-__global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb)
+__global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
 {
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
   int nn;
@@ -1200,7 +1253,7 @@ __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, 
     if (j < nn)
     {
       const int n = nodes[j];
-      if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb, job_src, job_off, job_np);
+      if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb, lv, job_src, job_off, job_np);
     }
     // the warp's copy jobs, one after the other, 32 points at a time (points go to the world frame of x_buf[0])
     unsigned int todo = __ballot_sync(0xffffffffu, job_np > 0);
@@ -1215,8 +1268,9 @@ __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, 
       for (int a = lane; a < np; a += 32)
       {
         PointRec pr = src[a];
-        double pw[3];
-        rot_trans(xb.x[0].R, xb.x[0].p, pr.p, pw);
+        double pw[3], xr[9], xp[3];
+        pose_sel(xb, lv, 0, xr, xp);
+        rot_trans(xr, xp, pr.p, pw);
         for (int k = 0; k < 3; k++) pr.p[k] = pw[k];
         M.fix_pool[off + a] = pr;
       }
@@ -1361,13 +1415,13 @@ static int grid_for(int n, int block) { return n <= 0 ? 1 : (n + block - 1) / bl
 
 int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                             const InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
-                            int pre)
+                            int pre, const IekfDev* live)
 {
   Cov2 cv;
   for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
   k_zero_ints<<<1, 32, 0, st>>>(sc.counters, 3);
   if (n_host <= 0) return 1;
-  k_insert_root<<<grid_for(n_host, 256), 256, 0, st>>>(map, scan, n_dev, n_host, sc, x, cv, pre);
+  k_insert_root<<<grid_for(n_host, 256), 256, 0, st>>>(map, scan, n_dev, n_host, sc, x, cv, pre, live);
   return 2;
 }
 
@@ -1388,10 +1442,10 @@ int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView
 
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                       const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
-                      const double* tsl_var)
+                      const double* tsl_var, const IekfDev* live)
 {
   if (n_host <= 0) return 0;
-  int k = launch_map_insert_roots(st, map, scan, n_dev, n_host, sc, x, rot_var, tsl_var, 0);
+  int k = launch_map_insert_roots(st, map, scan, n_dev, n_host, sc, x, rot_var, tsl_var, 0, live);
   return k + launch_map_insert_leaves(st, map, scan, n_dev, n_host, sc, win_ord);
 }
 
@@ -1403,8 +1457,10 @@ static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)
   return b;
 }
 
-int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf)
+int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
+                     const IekfDev* live)
 {
+  const LivePose lv = { live, win_count - 1 };
   static bool attr_set[64] = { false };
   int dv = 0;
   cudaGetDevice(&dv);
@@ -1422,18 +1478,20 @@ int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, 
     launches++;
     if (layer < map.max_layer)
     {
-      k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, layer, win_count, b);
+      k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, layer, win_count, b, lv);
       launches++;
     }
   }
   return launches;
 }
 
-int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf)
+int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
+                     const IekfDev* live)
 {
+  const LivePose lv = { live, win_count - 1 };
   PoseBuf b = make_posebuf(h_xbuf, win_count);
   int launches = 0;
-  k_margi_leaves<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b);
+  k_margi_leaves<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b, lv);
   launches++;
   for (int layer = map.max_layer - 1; layer >= 0; layer--, launches++) k_margi_up<<<296, 128, 0, st>>>(map, LL, layer);
   k_margi_clear<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL);

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include "vn_ctx.h"
+#include <cstdlib>
 
 #define CU(call)                                               \
   do                                                           \
@@ -170,6 +171,12 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&ctx->ev_scan_up, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&ctx->ev_scan_rd, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  ctx->trace = getenv("VINA_TRACE") != nullptr;
+  if (ctx->trace)
+    for (int i = 0; i < 8; i++) CU(cudaEventCreate(&ctx->tr_ev[i]));
+  CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU(dalloc(&ctx->d_status, 1));
   CU(cudaHostAlloc((void**)&ctx->h_status, sizeof(int), cudaHostAllocDefault));
 
@@ -265,6 +272,24 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
+  if (ctx->side_stream)
+  {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+  }
+  if (ctx->trace && ctx->tr_n > 0)
+  {
+    fprintf(stderr, "[vina trace] %d overlapped steps; host us (propagate, front+iekf enqueued, down count, map enqueued, "
+                    "iterate arrived):", ctx->tr_n);
+    for (int i = 1; i <= 5; i++) fprintf(stderr, " %.1f", ctx->tr_host_us[i] / ctx->tr_n);
+    fprintf(stderr, "; device us since deskew start (iekf done, side stream joined, insert, recut, margi):");
+    for (int i = 1; i <= 5; i++) fprintf(stderr, " %.1f", ctx->tr_dev_us[i] / ctx->tr_n);
+    fprintf(stderr, "\n");
+  }
+  for (int i = 0; i < 8; i++)
+    if (ctx->tr_ev[i]) cudaEventDestroy(ctx->tr_ev[i]);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   for (void* m : ctx->p2p_opened)
@@ -342,6 +367,15 @@ static int mark_scan_read(vina_ctx* ctx)
 {
   CU(cudaEventRecord(ctx->ev_scan_rd, ctx->stream));
   ctx->scan_rd_valid = true;
+  return VINA_OK;
+}
+
+int vn_mark_scan_read(vina_ctx* ctx) { return mark_scan_read(ctx); }
+
+extern "C" int vina_set_overlap(vina_ctx* ctx, int on)
+{
+  if (!ctx) return VINA_E_ARG;
+  ctx->overlap = on != 0;
   return VINA_OK;
 }
 
@@ -773,6 +807,32 @@ extern "C" int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_b
 {
   if (!ctx || win_count < 1 || win_count > ctx->cfg.win_size || !x_buf) return VINA_E_ARG;
   ctx->launches += launch_map_margi(ctx->stream, ctx->map, ctx->layers, win_count, reinterpret_cast<const PoseD*>(x_buf));
+  ctx->map.slide_cur = 1 - ctx->map.slide_cur;
+  return VINA_OK;
+}
+
+// the map update of the scan whose IEKF loop is still in flight: pose of the newest frame and posterior
+// covariance blocks come from the device iterate (x_buf[win_count - 1] is ignored by the kernels)
+int vn_map_insert_live(vina_ctx* ctx, int win_ord)
+{
+  PoseD x;
+  memset(&x, 0, sizeof(x));
+  const double z9[9] = { 0 };
+  ctx->ins.stamp++;
+  const int n = ctx->n_pv[1];
+  ctx->launches += launch_map_insert(ctx->stream, ctx->map, ctx->pv[1], nullptr, n, ctx->ins, win_ord, x, z9, z9, ctx->d_iekf);
+  return VINA_OK;
+}
+int vn_map_recut_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
+{
+  ctx->launches += launch_map_recut(ctx->stream, ctx->map, ctx->layers, win_count, reinterpret_cast<const PoseD*>(x_buf),
+                                    ctx->d_iekf);
+  return VINA_OK;
+}
+int vn_map_margi_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
+{
+  ctx->launches += launch_map_margi(ctx->stream, ctx->map, ctx->layers, win_count, reinterpret_cast<const PoseD*>(x_buf),
+                                    ctx->d_iekf);
   ctx->map.slide_cur = 1 - ctx->map.slide_cur;
   return VINA_OK;
 }

@@ -56,6 +56,10 @@ struct vina_ctx
   cudaEvent_t ev_scan_up = nullptr;    // the upload into d_scan has landed
   cudaEvent_t ev_scan_rd = nullptr;    // the last enqueued reader of d_scan is done
   bool scan_rd_valid = false;
+  bool overlap = true;                 // vina_set_overlap: the per-scan step forks / hands the pose over on the device
+  cudaStream_t side_stream = nullptr;  // down-sampling + var_init of the map's point set, concurrent with the IEKF
+  cudaEvent_t ev_fork = nullptr;       // the deskewed scan is ready (compute stream -> side stream)
+  cudaEvent_t ev_join = nullptr;       // the down-sampled pointVar set is ready (side stream -> compute stream)
   cudaEvent_t ev_poses = nullptr;  // the pose-table staging buffer has been consumed
   bool poses_in_flight = false;
   IekfDebug dbg = { nullptr, nullptr, nullptr, nullptr };
@@ -85,6 +89,12 @@ struct vina_ctx
   bool p2p_connected = false;
   int win_count_last = 0;
 
+  // VINA_TRACE=1: host / device timeline of the overlapped step, printed to stderr when the ctx is destroyed
+  bool trace = false;
+  cudaEvent_t tr_ev[8] = { nullptr };
+  double tr_host_us[8] = { 0 };
+  double tr_dev_us[8] = { 0 };
+  int tr_n = 0;
   // profiling
   bool profiling = false;
   cudaEvent_t ev[16];
@@ -108,4 +118,9 @@ int vn_iterate_wait(vina_ctx* c);
 void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 // enqueue max_iter iterations of the IEKF against the sharded map, exchange and update on the device (vn_ctx.cu)
 int vn_shard_iekf_enqueue(vina_ctx* c, int first, int count, int max_iter, int part);
+int vn_mark_scan_read(vina_ctx* c);
+// map update with the newest pose read from the device iterate (vn_ctx.cu)
+int vn_map_insert_live(vina_ctx* c, int win_ord);
+int vn_map_recut_live(vina_ctx* c, int win_count, const vina_pose* x_buf);
+int vn_map_margi_live(vina_ctx* c, int win_count, const vina_pose* x_buf);
 void odom_host_destroy(OdomHost* o);

@@ -112,13 +112,13 @@ struct InsertScratch
 };
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                       const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
-                      const double* tsl_var);
+                      const double* tsl_var, const IekfDev* live = nullptr);
 // the two halves of an insert, for the sharded map: (1) key + root find/create on points whose world
 // position / covariance are already in sc.pw / sc.vw (pre != 0) or come from pvec_update; (2) the rest.
 // Between them the caller may overwrite sc.counters[0] (distinct roots) with the all-reduced count.
 int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                             const InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
-                            int pre);
+                            int pre, const IekfDev* live = nullptr);
 int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                              const InsertScratch& sc, int win_ord);
 // shard_kernels.cu
@@ -141,9 +141,13 @@ void launch_p2p_sums_solve(cudaStream_t st, const ShardPeers& peers, IekfDev* de
 int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned long long epoch, int* n_recv, int cap,
                           const ScanView& scan, const InsertScratch& sc, int* status);
 int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc);
-int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
+// live != nullptr: the pose of frame win_count - 1 (and, for the insert, the posterior covariance blocks) are read
+// from the device iterate instead of the host arguments (the IEKF result need not have reached the host yet)
+int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
+                     const IekfDev* live = nullptr);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
-int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf);
+int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
+                     const IekfDev* live = nullptr);
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count);
 void launch_map_init(cudaStream_t st, const MapView& map, unsigned int nslots);
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <deque>
 #include <vector>
+#include <chrono>
 #include "../csrc/vn_ctx.h"
 
 int vn_finish_downsample(vina_ctx* ctx);
@@ -568,9 +569,120 @@ static int step_back(vina_ctx* ctx, OdomHost* o, int iekf_on_full, int ok, vina_
   return VINA_OK;
 }
 
+// The same scan body with two things taken off the critical path (vina_set_overlap, the default):
+//  * down-sampling and the var_init of the map's point set do not feed the IEKF (VNC_lio runs on the full scan,
+//    local_mapping.cpp:406-413): they run on a side stream, concurrently with the IEKF loop;
+//  * the map update is enqueued right behind the loop, before its result has reached the host: the kernels read
+//    the new pose and the posterior covariance blocks from the device iterate (LivePose, map_kernels.cu). The
+//    host then picks the iterate up (mapped memory, no stream sync) while the map update is already running.
+static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
+                                const vina_imu* imus, int m, int max_iter, vina_state* x_out)
+{
+  const int l0 = ctx->launches;
+  const bool tr = ctx->trace;
+  double th[8] = { 0 };
+  auto now_us = []() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  if (tr) th[0] = now_us();
+  o->pcl_beg_time = pcl_beg_time;
+  o->pcl_end_time = pcl_end_time;
+  int r = imu_propagate(ctx, o, imus, m);
+  if (r) return r;
+  cudaStream_t A = ctx->stream, B = ctx->side_stream;
+  if (tr) th[1] = now_us(), cudaEventRecord(ctx->tr_ev[0], A);
+  r = vina_deskew(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+  if (r) return r;
+  r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
+  if (r) return r;
+  cudaStreamWaitEvent(B, ctx->ev_fork, 0);
+  ctx->stream = B;
+  r = vina_downsample(ctx);
+  ctx->stream = A;
+  if (r) return r;
+  r = vina_var_init(ctx, 0);
+  if (r) return r;
+  const int num_max_iter = max_iter > 0 ? max_iter : 20;
+  r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
+  if (r) return r;
+  if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
+  // the map's point set: the host needs the down-sampled count (and the "< 2000 points" retry,
+  // local_mapping.cpp:396-403) - a wait on the side stream only, the IEKF keeps running
+  ctx->stream = B;
+  r = vn_finish_downsample(ctx);
+  if (!r) r = vina_var_init(ctx, 1);
+  ctx->stream = A;
+  if (r) return r;
+  if (tr) th[3] = now_us();
+  cudaEventRecord(ctx->ev_join, B);
+  cudaStreamWaitEvent(A, ctx->ev_join, 0);
+  if (tr) cudaEventRecord(ctx->tr_ev[2], A);
+  r = vn_mark_scan_read(ctx);  // (covers the side stream's readers of the scan buffer as well)
+  if (r) return r;
+  // local_mapping.cpp:425-451, 489-546 with if_BA == 0, pose of the new frame from the device
+  o->win_count++;
+  vina_pose ps;
+  memset(&ps, 0, sizeof(ps));
+  o->x_buf.push_back(ps);
+  r = vn_map_insert_live(ctx, o->win_count - 1);
+  if (r) return r;
+  if (tr) cudaEventRecord(ctx->tr_ev[3], A);
+  r = vn_map_recut_live(ctx, o->win_count, o->x_buf.data());
+  if (r) return r;
+  if (tr) cudaEventRecord(ctx->tr_ev[4], A);
+  const bool margi = o->win_count >= ctx->cfg.win_size;
+  if (margi)
+  {
+    r = vn_map_margi_live(ctx, o->win_count, o->x_buf.data());
+    if (r) return r;
+    r = vina_map_shift_window(ctx);
+    if (r) return r;
+  }
+  if (tr) th[4] = now_us(), cudaEventRecord(ctx->tr_ev[5], A);
+  // the result of the loop (it landed while the map update was being enqueued)
+  r = vn_iterate_wait(ctx);
+  if (r) return r;
+  if (tr)
+  {
+    th[5] = now_us();
+    cudaEventSynchronize(ctx->tr_ev[5]);
+    for (int i = 1; i <= 5; i++)
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->tr_ev[0], ctx->tr_ev[i]);
+      ctx->tr_dev_us[i] += 1e3 * ms;
+      ctx->tr_host_us[i] += th[i] - th[0];
+    }
+    ctx->tr_n++;
+  }
+  int ok = 0;
+  unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, &ok);
+  ctx->tm.iekf_iters = o->last_iters;
+  ctx->tm.iekf_kernel_ms = 0;
+  if (ok)
+  {
+    if (o->degrade_cnt > 0) o->degrade_cnt--;
+  }
+  else
+    o->degrade_cnt++;
+  memcpy(o->x_buf.back().R, o->x_curr.R, 72);
+  memcpy(o->x_buf.back().p, o->x_curr.p, 24);
+  if (margi)
+  {
+    o->x_buf.erase(o->x_buf.begin());
+    o->win_base += 1;
+    o->win_count -= 1;
+  }
+  if (x_out) *x_out = o->x_curr;
+  ctx->tm.kernel_launches = ctx->launches - l0;
+  return VINA_OK;
+}
+
 static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
                               const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
 {
+  if (ctx->overlap && !ctx->profiling && iekf_on_full && ctx->side_stream)
+    return odom_step_overlapped(ctx, o, pcl_beg_time, pcl_end_time, imus, m, max_iter, x_out);
   const int l0 = ctx->launches;
   int which = 1, ok = 0;
   int r = step_front(ctx, o, pcl_beg_time, pcl_end_time, imus, m, iekf_on_full, &which);
