@@ -411,6 +411,56 @@ int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap)
   for (auto& kv : o->surf_map) export_node(o, kv.second, out, cap, c);
   return c;
 }
+// ---- BA probe (oracle_capi.h): the restated LidarFactor on the factors captured by the last map update
+void vo_odom_ba_probe(void* h, int on) { ((Odom*)h)->ba_probe = on != 0; }
+int vo_odom_ba_count(void* h) { return (int)((Odom*)h)->ba_factors.plvec_voxels.size(); }
+int vo_odom_ba_poses(void* h, double* poses12, int cap)
+{
+  Odom* o = (Odom*)h;
+  const int n = (int)o->ba_xs.size();
+  for (int i = 0; i < n && i < cap; i++)
+  {
+    memcpy(poses12 + 12 * i, o->ba_xs[i].R.d, 72);
+    memcpy(poses12 + 12 * i + 9, o->ba_xs[i].p.d, 24);
+  }
+  return n;
+}
+static std::vector<IMUST> ba_pose_vec(const double* poses12, int win)
+{
+  std::vector<IMUST> xs(win);
+  for (int i = 0; i < win; i++)
+  {
+    memcpy(xs[i].R.d, poses12 + 12 * i, 72);
+    memcpy(xs[i].p.d, poses12 + 12 * i + 9, 24);
+  }
+  return xs;
+}
+int vo_odom_ba_hess(void* h, const double* poses12, int win, double* Hess, double* JacT, double* residual)
+{
+  Odom* o = (Odom*)h;
+  if (win != o->ba_factors.win_size) return -1;
+  std::vector<IMUST> xs = ba_pose_vec(poses12, win);
+  std::vector<double> H, J;
+  double r = 0;
+  o->ba_factors.acc_evaluate2(xs, 0, (int)o->ba_factors.plvec_voxels.size(), H, J, r);
+  memcpy(Hess, H.data(), H.size() * sizeof(double));
+  memcpy(JacT, J.data(), J.size() * sizeof(double));
+  *residual = r;
+  return 0;
+}
+int vo_odom_ba_residual(void* h, const double* poses12, int win, double* residual, double* lam0, int cap)
+{
+  Odom* o = (Odom*)h;
+  if (win != o->ba_factors.win_size) return -1;
+  std::vector<IMUST> xs = ba_pose_vec(poses12, win);
+  double r = 0;
+  const int n = (int)o->ba_factors.plvec_voxels.size();
+  o->ba_factors.evaluate_only_residual(xs, 0, n, r);
+  *residual = r;
+  if (lam0)
+    for (int a = 0; a < n && a < cap; a++) lam0[a] = o->ba_factors.eig_values[a][0];
+  return 0;
+}
 int vo_odom_window(void* h, int* win_count, int* mp, int cap)
 {
   Odom* o = (Odom*)h;

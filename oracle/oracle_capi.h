@@ -95,6 +95,16 @@ int64_t vo_odom_map_count(void* h, int64_t* n_roots, int64_t* n_slide);
 int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap);
 int vo_odom_window(void* h, int* win_count, int* mp, int cap);
 
+/* ---- BA probe (the data-parallel part): LidarFactor::acc_evaluate2 and
+ * evaluate_only_residual (factors.cpp:22-158) on a copy of the LiDAR factors and window poses taken between
+ * multi_recut and multi_margi of the last map update with a full window (where damping_iter consumes them,
+ * local_mapping.cpp:492-497). poses12 = win x (R 9 column-major, p 3). Hess is (6 win)^2 column-major. */
+void vo_odom_ba_probe(void* h, int on);
+int vo_odom_ba_count(void* h);
+int vo_odom_ba_poses(void* h, double* poses12, int cap);
+int vo_odom_ba_hess(void* h, const double* poses12, int win, double* Hess, double* JacT, double* residual);
+int vo_odom_ba_residual(void* h, const double* poses12, int win, double* residual, double* lam0, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -291,6 +291,43 @@ class Odom:
         ws = self.lib.vo_odom_window(self.h, C.byref(wc), _ptr(mp, C.c_int), C.c_int(16))
         return wc.value, mp[:ws].copy()
 
+    # ---- BA probe: LidarFactor (factors.cpp:22-158) on the factors captured by the last full-window map update
+    def ba_probe(self, on: bool = True):
+        self.lib.vo_odom_ba_probe(self.h, C.c_int(1 if on else 0))
+
+    def ba_count(self) -> int:
+        return int(self.lib.vo_odom_ba_count(self.h))
+
+    def ba_poses(self) -> np.ndarray:
+        """(win, 12): R column-major (9), p (3) of every window frame at capture time."""
+        out = np.zeros((16, 12), dtype=np.float64)
+        n = self.lib.vo_odom_ba_poses(self.h, _ptr(out, C.c_double), C.c_int(16))
+        return out[:n].copy()
+
+    def ba_hess(self, poses12: np.ndarray):
+        """acc_evaluate2 over all factors: (Hess (6w,6w), JacT (6w,), residual)."""
+        ps = np.ascontiguousarray(poses12, dtype=np.float64)
+        w = ps.shape[0]
+        H = np.zeros(36 * w * w, dtype=np.float64)
+        J = np.zeros(6 * w, dtype=np.float64)
+        r = C.c_double(0)
+        rc = self.lib.vo_odom_ba_hess(self.h, _ptr(ps, C.c_double), C.c_int(w), _ptr(H, C.c_double), _ptr(J, C.c_double),
+                                      C.byref(r))
+        assert rc == 0
+        return H.reshape(6 * w, 6 * w).T.copy(), J, r.value
+
+    def ba_residual(self, poses12: np.ndarray):
+        """evaluate_only_residual over all factors (updates the captured factors like the reference's container):
+        (residual, lambda_0 of every factor)."""
+        ps = np.ascontiguousarray(poses12, dtype=np.float64)
+        n = self.ba_count()
+        lam = np.zeros(max(n, 1), dtype=np.float64)
+        r = C.c_double(0)
+        rc = self.lib.vo_odom_ba_residual(self.h, _ptr(ps, C.c_double), C.c_int(ps.shape[0]), C.byref(r),
+                                          _ptr(lam, C.c_double), C.c_int(n))
+        assert rc == 0
+        return r.value, lam[:n]
+
 
 # ---- stateless helpers -----------------------------------------------------
 def eig3(A: np.ndarray):

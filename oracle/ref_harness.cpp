@@ -2,13 +2,12 @@
 // Harness around the REFERENCE'S OWN SOURCES. The Makefile target `_ref` compiles, unmodified and where
 // they lie under /root/reference,
 //     src/core/point_utils.cpp   src/mapping/octree.cpp   src/mapping/voxel_map.cpp
-//     src/estimation/imu_ekf.cpp src/pipeline/odometry.cpp
+//     src/estimation/imu_ekf.cpp src/pipeline/odometry.cpp   src/mapping/factors.cpp
 // against the header shims in oracle/ref_shim/ (a minimal eager Eigen, the PCL point/cloud types and the
 // ROS message fields those files touch - none of Eigen / PCL / ROS 2 is installed here), and links them
 // with this file into oracle/_ref/libvina_ref.so. This file supplies only what lives in reference files that
 // cannot be compiled here (they need the whole ROS 2 node):
 //   * the two globals of node.cpp:38 and the VINA_SLAM constructor (node.cpp:52) reduced to nothing,
-//   * the trivial container methods of LidarFactor / NormalFactor (factors.cpp:7-20, 160-183, 348-355),
 //   * the fan-out drivers multi_recut / multi_margi (local_mapping.cpp:17-84, 144-201) and the scan body
 //     of thd_odometry_localmapping (local_mapping.cpp:389-546) - loops that call the reference's real
 //     OctoTree::recut / tras_opt / margi, cut_voxel_multi, var_init, pvec_update, IMUEKF::process and
@@ -31,47 +30,6 @@ double dept_err, beam_err;  // node.cpp:38
 
 VINA_SLAM::VINA_SLAM(const rclcpp::Node::SharedPtr& node_in) : node(node_in) {}
 
-// factors.cpp:7-20, 160-168
-LidarFactor::LidarFactor(int _w) : win_size(_w) {}
-void LidarFactor::push_voxel(vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Eigen::Vector3d& eig_value,
-                             Eigen::Matrix3d& eig_vector, PointCluster& pcr_add)
-{
-  plvec_voxels.push_back(vec_orig);
-  sig_vecs.push_back(fix);
-  coeffs.push_back(coe);
-  eig_values.push_back(eig_value);
-  eig_vectors.push_back(eig_vector);
-  pcr_adds.push_back(pcr_add);
-}
-void LidarFactor::clear()
-{
-  sig_vecs.clear();
-  plvec_voxels.clear();
-  eig_values.clear();
-  eig_vectors.clear();
-  pcr_adds.clear();
-  coeffs.clear();
-}
-// factors.cpp:171-183, 348-355
-NormalFactor::NormalFactor(int _w) : win_size(_w) {}
-void NormalFactor::push_voxel(std::vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Eigen::Vector3d& n_ref,
-                              PointCluster& pcr_add)
-{
-  plvec_voxels.push_back(vec_orig);
-  sig_vecs.push_back(fix);
-  coeffs.push_back(coe);
-  n_refs.push_back(n_ref.normalized());
-  pcr_adds.push_back(pcr_add);
-}
-void NormalFactor::clear()
-{
-  sig_vecs.clear();
-  plvec_voxels.clear();
-  coeffs.clear();
-  n_refs.clear();
-  pcr_adds.clear();
-}
-
 namespace
 {
 double now_s()
@@ -88,7 +46,12 @@ struct RefOdom
   int degrade_cnt = 0;
   double t_odom = 0, t_insert = 0, t_recut = 0, t_margi = 0;
   pcl::PointCloud<PointType> last_down;
-  RefOdom(int win) : vs(nullptr), voxhess(win), normalFactor(win) {}
+  // BA probe: a copy of the LiDAR factors and the window poses as they are between multi_recut and multi_margi
+  // (where LI_BA_Optimizer::damping_iter consumes them, local_mapping.cpp:492-497)
+  bool ba_probe = false;
+  LidarFactor ba_factors;
+  vector<IMUST> ba_xs;
+  RefOdom(int win) : vs(nullptr), voxhess(win), normalFactor(win), ba_factors(win) {}
 
   // local_mapping.cpp:144-201 (the overload the per-scan loop calls, :451)
   void multi_recut(unordered_map<VOXEL_LOC, OctoTree*>& feat_map, int win_count, vector<IMUST>& xs)
@@ -198,6 +161,11 @@ struct RefOdom
     t_insert = t2 - t1;
     t_recut = t3 - t2;
     t_margi = 0;
+    if (ba_probe && vs.win_count >= vs.win_size)
+    {
+      ba_factors = voxhess;
+      ba_xs = vs.x_buf;
+    }
     if (vs.win_count >= vs.win_size)
     {
       vs.x_curr.R = vs.x_buf[vs.win_count - 1].R;
@@ -643,6 +611,62 @@ int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap)
   for (auto& kv : o->vs.surf_map) export_node(o, kv.second, kv.first, 0, out, cap, c);
   return c;
 }
+// ---- BA probe: the reference's LidarFactor::acc_evaluate2 / evaluate_only_residual (factors.cpp:22-158) on
+// the factors captured by the last map update
+void vo_odom_ba_probe(void* h, int on) { ((RefOdom*)h)->ba_probe = on != 0; }
+int vo_odom_ba_count(void* h) { return (int)((RefOdom*)h)->ba_factors.plvec_voxels.size(); }
+int vo_odom_ba_poses(void* h, double* poses12, int cap)
+{
+  RefOdom* o = (RefOdom*)h;
+  const int n = (int)o->ba_xs.size();
+  for (int i = 0; i < n && i < cap; i++)
+  {
+    memcpy(poses12 + 12 * i, o->ba_xs[i].R.data(), 72);
+    memcpy(poses12 + 12 * i + 9, o->ba_xs[i].p.data(), 24);
+  }
+  return n;
+}
+static vector<IMUST> ba_pose_vec(const double* poses12, int win)
+{
+  vector<IMUST> xs(win);
+  for (int i = 0; i < win; i++)
+  {
+    memcpy(xs[i].R.data(), poses12 + 12 * i, 72);
+    memcpy(xs[i].p.data(), poses12 + 12 * i + 9, 24);
+  }
+  return xs;
+}
+int vo_odom_ba_hess(void* h, const double* poses12, int win, double* Hess, double* JacT, double* residual)
+{
+  RefOdom* o = (RefOdom*)h;
+  if (win != o->ba_factors.win_size) return -1;
+  vector<IMUST> xs = ba_pose_vec(poses12, win);
+  Eigen::MatrixXd H(6 * win, 6 * win);
+  Eigen::VectorXd J(6 * win);
+  double r = 0;
+  o->ba_factors.acc_evaluate2(xs, 0, (int)o->ba_factors.plvec_voxels.size(), H, J, r);
+  for (int j = 0; j < 6 * win; j++)
+    for (int i = 0; i < 6 * win; i++) Hess[i + 6 * win * j] = H(i, j);
+  for (int i = 0; i < 6 * win; i++) JacT[i] = J(i);
+  *residual = r;
+  return 0;
+}
+// evaluate_only_residual overwrites the factors' eig_values / eig_vectors / pcr_adds (factors.cpp:150-153): the
+// captured copy is updated like the reference's container; lam0 (optional) receives every factor's lambda_0
+int vo_odom_ba_residual(void* h, const double* poses12, int win, double* residual, double* lam0, int cap)
+{
+  RefOdom* o = (RefOdom*)h;
+  if (win != o->ba_factors.win_size) return -1;
+  vector<IMUST> xs = ba_pose_vec(poses12, win);
+  double r = 0;
+  const int n = (int)o->ba_factors.plvec_voxels.size();
+  o->ba_factors.evaluate_only_residual(xs, 0, n, r);
+  *residual = r;
+  if (lam0)
+    for (int a = 0; a < n && a < cap; a++) lam0[a] = o->ba_factors.eig_values[a][0];
+  return 0;
+}
+
 int vo_odom_window(void* h, int* win_count, int* mpo, int cap)
 {
   RefOdom* o = (RefOdom*)h;

@@ -81,6 +81,9 @@ struct Base
   double operator()(int i, int j) const { return coeff(i, j); }
   double operator()(int i) const { return lin(i); }
   double operator[](int i) const { return lin(i); }
+  double x() const { return lin(0); }
+  double y() const { return lin(1); }
+  double z() const { return lin(2); }
   operator double() const
   {
     static_assert(R == 1 && C == 1, "only 1x1 converts to a scalar");
@@ -278,6 +281,15 @@ public:
   int cols() const { return c; }
   double& operator()(int i, int j = 0) { return v[i + (size_t)j * r]; }
   double operator()(int i, int j = 0) const { return v[i + (size_t)j * r]; }
+  // fixed-size views into a dynamic matrix (factors.cpp: Hess.block<6, 6>(6 * i, 6 * j) += ...)
+  double coeff(int i, int j) const { return v[i + (size_t)j * r]; }
+  double& ref(int i, int j) { return v[i + (size_t)j * r]; }
+  template <int BR, int BC>
+  Block<Matrix, BR, BC> block(int r0, int c0)
+  {
+    return Block<Matrix, BR, BC>(*this, r0, c0);
+  }
+  const double* data() const { return v.data(); }
 };
 
 typedef Matrix<double, 2, 1> Vector2d;

@@ -445,6 +445,184 @@ static void tras_opt_mark(OctoTree* n, int& counter)
   }
 }
 
+// src/mapping/octree.cpp:498-521 with the container (the BA probe): same traversal, same acceptance test
+static void tras_opt_collect(OctoTree* n, LidarFactor& vox_opt)
+{
+  if (n->octo_state == 0)
+  {
+    if (n->layer >= 0 && n->isexist && n->plane.is_plane && n->sw != nullptr)
+    {
+      if (n->eig_value[0] / n->eig_value[1] > 0.12) return;
+      double coe = 1;
+      std::vector<PointCluster> pcrs(n->wdsize);
+      for (int i = 0; i < n->wdsize; i++) pcrs[i] = n->sw->pcrs_local[n->G->mp[i]];
+      vox_opt.push_voxel(pcrs, n->pcr_fix, coe, n->eig_value, n->eig_vector, n->pcr_add);
+    }
+  }
+  else
+  {
+    for (int i = 0; i < 8; i++)
+      if (n->leaves[i] != nullptr) tras_opt_collect(n->leaves[i], vox_opt);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// src/mapping/factors.cpp:7-168 - the LiDAR BA factor. Expressions keep the reference's grouping and the eager
+// left-to-right product order of omat.hpp, which is also what the reference build (oracle/_ref: factors.cpp
+// compiled against ref_shim) evaluates - the two agree bit for bit in the strict builds.
+void LidarFactor::push_voxel(std::vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Vec3& eig_value,
+                             Mat3& eig_vector, PointCluster& pcr_add)
+{
+  plvec_voxels.push_back(vec_orig);
+  sig_vecs.push_back(fix);
+  coeffs.push_back(coe);
+  eig_values.push_back(eig_value);
+  eig_vectors.push_back(eig_vector);
+  pcr_adds.push_back(pcr_add);
+}
+void LidarFactor::clear()
+{
+  sig_vecs.clear();
+  plvec_voxels.clear();
+  eig_values.clear();
+  eig_vectors.clear();
+  pcr_adds.clear();
+  coeffs.clear();
+}
+
+namespace
+{
+inline Mat3 outer(const Vec3& a, const Vec3& b)  // a * b.transpose()
+{
+  Mat3 r;
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) r(i, j) = a[i] * b[j];
+  return r;
+}
+}  // namespace
+
+void LidarFactor::acc_evaluate2(const std::vector<IMUST>& xs, int head, int end, std::vector<double>& Hess,
+                                std::vector<double>& JacT, double& residual)
+{
+  const int dim = 6 * win_size;
+  Hess.assign((size_t)dim * dim, 0.0);
+  JacT.assign(dim, 0.0);
+  residual = 0;
+  const int kk = 0;
+  auto H = [&](int r, int c) -> double& { return Hess[r + (size_t)dim * c]; };
+  std::vector<Vec3> viRiTuk(win_size);
+  std::vector<Mat3> viRiTukukT(win_size);
+  std::vector<Mat<3, 6>> Auk(win_size);
+  const Mat3 I33 = Mat3::Identity();
+
+  for (int a = head; a < end; a++)
+  {
+    std::vector<PointCluster>& sig_orig = plvec_voxels[a];
+    double coe = coeffs[a];
+    Vec3 lmbd = eig_values[a];
+    Mat3 U = eig_vectors[a];
+    int NN = pcr_adds[a].N;
+    Vec3 vBar = pcr_adds[a].v / (double)NN;
+    Vec3 u[3] = { U.col(0), U.col(1), U.col(2) };
+    Vec3& uk = u[kk];
+    Mat3 ukukT = outer(uk, uk);
+    Mat3 umumT = Mat3::Zero();
+    for (int i = 0; i < 3; i++)
+      if (i != kk) umumT += (2.0 / (lmbd[kk] - lmbd[i])) * u[i] * u[i].transpose();
+
+    for (int i = 0; i < win_size; i++)
+      if (sig_orig[i].N != 0)
+      {
+        Mat3 Pi = sig_orig[i].P;
+        Vec3 vi = sig_orig[i].v;
+        Mat3 Ri = xs[i].R;
+        double ni = sig_orig[i].N;
+        Mat3 vihat = hat(vi);
+        Vec3 RiTuk = Ri.transpose() * uk;
+        Mat3 RiTukhat = hat(RiTuk);
+        Vec3 PiRiTuk = Pi * RiTuk;
+        viRiTuk[i] = vihat * RiTuk;
+        viRiTukukT[i] = viRiTuk[i] * uk.transpose();
+        Vec3 ti_v = xs[i].p - vBar;
+        double ukTti_v = dot(uk, ti_v);
+        Mat3 combo1 = hat(PiRiTuk) + vihat * ukTti_v;
+        Vec3 combo2 = Ri * vi + ni * ti_v;
+        Mat3 blk0 = (Ri * Pi + ti_v * vi.transpose()) * RiTukhat - Ri * combo1;
+        Mat3 blk1 = combo2 * uk.transpose() + dot(combo2, uk) * I33;
+        Auk[i].setBlock<3, 3>(0, 0, blk0);
+        Auk[i].setBlock<3, 3>(0, 3, blk1);
+        Auk[i] = Auk[i] / (double)NN;
+
+        Vec6 jjt = Auk[i].transpose() * uk;
+        for (int q = 0; q < 6; q++) JacT[6 * i + q] = JacT[6 * i + q] + (coe * jjt)[q];
+
+        Mat3 HRt = (2.0 / NN * (1.0 - ni / NN)) * viRiTukukT[i];
+        Mat6 Hb = Auk[i].transpose() * umumT * Auk[i];
+        Vec3 jj3 = jjt.block<3, 1>(0, 0);
+        Mat3 add00 = (2.0 / NN) * (combo1 - RiTukhat * Pi) * RiTukhat - (2.0 / NN / NN) * viRiTuk[i] * viRiTuk[i].transpose() -
+                     0.5 * hat(jj3);
+        Hb.setBlock<3, 3>(0, 0, Hb.block<3, 3>(0, 0) + add00);
+        Hb.setBlock<3, 3>(0, 3, Hb.block<3, 3>(0, 3) + HRt);
+        Hb.setBlock<3, 3>(3, 0, Hb.block<3, 3>(3, 0) + HRt.transpose());
+        Hb.setBlock<3, 3>(3, 3, Hb.block<3, 3>(3, 3) + (2.0 / NN * (ni - ni * ni / NN)) * ukukT);
+        Mat6 cH = coe * Hb;
+        for (int c = 0; c < 6; c++)
+          for (int r = 0; r < 6; r++) H(6 * i + r, 6 * i + c) = H(6 * i + r, 6 * i + c) + cH(r, c);
+      }
+
+    for (int i = 0; i < win_size - 1; i++)
+      if (sig_orig[i].N != 0)
+      {
+        double ni = sig_orig[i].N;
+        for (int j = i + 1; j < win_size; j++)
+          if (sig_orig[j].N != 0)
+          {
+            double nj = sig_orig[j].N;
+            Mat6 Hb = Auk[i].transpose() * umumT * Auk[j];
+            Hb.setBlock<3, 3>(0, 0, Hb.block<3, 3>(0, 0) + (-2.0 / NN / NN) * viRiTuk[i] * viRiTuk[j].transpose());
+            Hb.setBlock<3, 3>(0, 3, Hb.block<3, 3>(0, 3) + (-2.0 * nj / NN / NN) * viRiTukukT[i]);
+            Hb.setBlock<3, 3>(3, 0, Hb.block<3, 3>(3, 0) + (-2.0 * ni / NN / NN) * viRiTukukT[j].transpose());
+            Hb.setBlock<3, 3>(3, 3, Hb.block<3, 3>(3, 3) + (-2.0 * ni * nj / NN / NN) * ukukT);
+            Mat6 cH = coe * Hb;
+            for (int c = 0; c < 6; c++)
+              for (int r = 0; r < 6; r++) H(6 * i + r, 6 * j + c) = H(6 * i + r, 6 * j + c) + cH(r, c);
+          }
+      }
+    residual += coe * lmbd[kk];
+  }
+  for (int i = 1; i < win_size; i++)
+    for (int j = 0; j < i; j++)
+      for (int c = 0; c < 6; c++)
+        for (int r = 0; r < 6; r++) H(6 * i + r, 6 * j + c) = H(6 * j + c, 6 * i + r);
+}
+
+void LidarFactor::evaluate_only_residual(const std::vector<IMUST>& xs, int head, int end, double& residual)
+{
+  residual = 0;
+  int kk = 0;
+  PointCluster pcr;
+  for (int a = head; a < end; a++)
+  {
+    const std::vector<PointCluster>& sig_orig = plvec_voxels[a];
+    PointCluster sig = sig_vecs[a];
+    for (int i = 0; i < win_size; i++)
+      if (sig_orig[i].N != 0)
+      {
+        pcr.transform(sig_orig[i], xs[i]);
+        sig += pcr;
+      }
+    Vec3 vBar = sig.v / (double)sig.N;
+    Mat3 cov;
+    for (int j = 0; j < 3; j++)
+      for (int i = 0; i < 3; i++) cov(i, j) = sig.P(i, j) / (double)sig.N - vBar[i] * vBar[j];
+    SelfAdjointEigen3 saes(cov);
+    eig_values[a] = saes.values;
+    eig_vectors[a] = saes.vectors;
+    pcr_adds[a] = sig;
+    residual += coeffs[a] * saes.values[kk];
+  }
+}
+
 // src/mapping/octree.cpp:551-595
 int OctoTree::match(Vec3& wld, Plane*& pla, double& max_prob, Mat3& var_wld, double& sigma_d, OctoTree*& oc)
 {
@@ -998,6 +1176,15 @@ void Odom::map_update(PVecPtr pptr)
   double t3 = now_s();
   t_insert = t2 - t1;
   t_recut = t3 - t2;
+  if (ba_probe && win_count >= G.win_size)
+  {
+    ba_factors.clear();
+    ba_factors.win_size = G.win_size;
+    if ((int)surf_map_slide.size() >= G.thread_num)  // multi_recut's early-out (local_mapping.cpp:150-154)
+      for (auto iter = surf_map_slide.begin(); iter != surf_map_slide.end(); iter++)
+        tras_opt_collect(iter->second, ba_factors);
+    ba_xs = x_buf;
+  }
   t_margi = 0;
 
   if (win_count >= G.win_size)

@@ -327,6 +327,26 @@ struct IekfIterDump
   double R[9], p[3];           // state the iteration was evaluated at
 };
 
+// include/vina_slam/mapping/factors.hpp:10-40, src/mapping/factors.cpp:7-168: the LiDAR BA factor container
+// (one entry per plane leaf that tras_opt accepted) and its two evaluations
+struct LidarFactor
+{
+  std::vector<PointCluster> sig_vecs;                   // pcr_fix (world frame)
+  std::vector<std::vector<PointCluster>> plvec_voxels;  // pcrs_local[mp[i]] (body frame of window frame i)
+  std::vector<double> coeffs;
+  std::vector<Vec3> eig_values;
+  std::vector<Mat3> eig_vectors;
+  std::vector<PointCluster> pcr_adds;
+  int win_size = 0;
+  void push_voxel(std::vector<PointCluster>& vec_orig, PointCluster& fix, double coe, Vec3& eig_value, Mat3& eig_vector,
+                  PointCluster& pcr_add);                                                        // factors.cpp:11-20
+  void clear();
+  // Hess: (6 win)^2 column-major, JacT: 6 win
+  void acc_evaluate2(const std::vector<IMUST>& xs, int head, int end, std::vector<double>& Hess,
+                     std::vector<double>& JacT, double& residual);                               // factors.cpp:22-126
+  void evaluate_only_residual(const std::vector<IMUST>& xs, int head, int end, double& residual);  // factors.cpp:128-158
+};
+
 // The owner of everything VINA_SLAM keeps for the per-scan loop
 // (include/vina_slam/platform/ros2/node.hpp:30-96; src/pipeline/local_mapping.cpp:258-550)
 class Odom
@@ -352,6 +372,11 @@ public:
   double t_odom = 0, t_insert = 0, t_recut = 0, t_margi = 0;
   PVecPtr last_pptr, last_full_pptr;
   Cloud last_down;
+  // BA probe: copy of the LiDAR factors (tras_opt, octree.cpp:498-521) and of the window poses between
+  // multi_recut and multi_margi, where LI_BA_Optimizer::damping_iter consumes them (local_mapping.cpp:492-497)
+  bool ba_probe = false;
+  LidarFactor ba_factors;
+  std::vector<IMUST> ba_xs;
 
   explicit Odom(const Globals& g);
   ~Odom();

@@ -90,9 +90,53 @@ def run(make_odom, ref_stateless):
     return out
 
 
+def perturbed_poses(poses12, seed=7, rot=2e-3, tsl=0.02):
+    """The captured window poses with a small seeded perturbation per frame (frame 0 included)."""
+    rng = np.random.default_rng(seed)
+    out = poses12.copy()
+    for i in range(out.shape[0]):
+        R = out[i, :9].reshape(3, 3).T
+        R = R @ synth.rot_exp(rng.normal(0, rot, 3))
+        out[i, :9] = R.T.reshape(-1)
+        out[i, 9:] += rng.normal(0, tsl, 3)
+    return out
+
+
+def run_ba(make_odom):
+    """The BA-probe scenario (SURVEY.md section 8f rank 3, LiDAR factor only): LidarFactor::acc_evaluate2 and
+    evaluate_only_residual (factors.cpp:22-158) on the factors tras_opt collected in the last map update."""
+    out = {}
+    cfg = synth.small_sensor("robosense128", 24, 400, seed=31)
+    seq = synth.Sequence(cfg)
+    od = make_odom(cfg)
+    od.ba_probe(True)
+    for _ in range(cfg.win_size + 3):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, op.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    out["n_factors"] = np.array([od.ba_count()])
+    poses = od.ba_poses()
+    out["poses"] = poses
+    out["H0"], out["J0"], r0 = od.ba_hess(poses)
+    pert = perturbed_poses(poses)
+    out["poses_pert"] = pert
+    out["H1"], out["J1"], r1 = od.ba_hess(pert)
+    r2, lam = od.ba_residual(pert)  # overwrites the factors' eig / pcr_add like the reference's container
+    out["lam0_sorted"] = np.sort(lam)
+    out["H2"], out["J2"], r3 = od.ba_hess(pert)
+    out["residuals"] = np.array([r0, r1, r2, r3])
+    od.close()
+    return out
+
+
 if __name__ == "__main__":
     assert op.build_ref(), "oracle/_ref needs /root/reference"
-    o = run(lambda cfg: op.Odom(cfg, ref=True), True)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz")
+    here = os.path.dirname(os.path.abspath(__file__))
+    if "--ba-only" not in sys.argv:
+        o = run(lambda cfg: op.Odom(cfg, ref=True), True)
+        path = os.path.join(here, "ref_small.npz")
+        np.savez_compressed(path, **o)
+        print(path, os.path.getsize(path), "bytes")
+    o = run_ba(lambda cfg: op.Odom(cfg, ref=True))
+    path = os.path.join(here, "ref_ba.npz")
     np.savez_compressed(path, **o)
-    print(path, os.path.getsize(path), "bytes")
+    print(path, os.path.getsize(path), "bytes", "factors:", int(o["n_factors"][0]), "residuals:", o["residuals"])

@@ -89,6 +89,23 @@ def test_oracle_and_reference_side_by_side(oracle_lib):
         rf.close()
 
 
+def test_ba_lidar_factor_reproduces_reference(oracle_lib):
+    """SURVEY section 8f rank 3, the LiDAR factor: the restated LidarFactor::acc_evaluate2 / evaluate_only_residual
+    against the reference's own factors.cpp (golden vectors from oracle/_ref, tests/golden/ref_ba.npz; live side
+    by side when the reference build is present): Hessian, gradient, residuals and eigenvalues bit for bit,
+    including the overwrite of the factors' eig / pcr_add by evaluate_only_residual."""
+    g = dict(np.load(os.path.join(HERE, "golden", "ref_ba.npz")))
+    mod = _scenario()
+    o = mod.run_ba(lambda cfg: oracle_lib.Odom(cfg))
+    assert int(g["n_factors"][0]) > 1000 and np.abs(g["J1"]).max() > 10 * np.abs(g["J0"]).max()
+    assert np.allclose(g["H1"], g["H1"].T, rtol=0, atol=0)  # acc_evaluate2 mirrors the upper blocks
+    assert g["residuals"][2] > 3 * g["residuals"][0]  # the perturbed poses are visibly worse
+    _assert_same(o, g, "oracle BA vs reference golden")
+    if oracle_lib.have_ref():
+        r = mod.run_ba(lambda cfg: oracle_lib.Odom(cfg, ref=True))
+        _assert_same(o, r, "oracle BA vs reference build")
+
+
 def test_vnc_terms_are_unreachable_in_the_reference(oracle_lib):
     """VNC_lio (use_vnc = true) of the reference build == plain point-to-plane IEKF with a 4-iteration budget:
     matchVoxelMap can never succeed because OctoTree::match never writes max_prob (DESIGN.md §1)."""

@@ -594,25 +594,43 @@ __device__ __forceinline__ void child_push_fix(NodeCold& k, const PointRec& pr)
   bf_var_add(k.cov_add, pr.v, pr.p);
 }
 
-// append one segment of `cnt` fixed points to a node's point_fix chain; returns pool offset or -1
+// append one segment of `cnt` fixed points to a node's point_fix chain; returns pool offset or -1. Called by
+// the one thread that owns the node.
 __device__ int fix_append(const MapView& M, NodeCold& c, int cnt)
 {
   int off = atomicAdd(M.fix_cursor, cnt);
-  int sid = atomicAdd(M.fixseg_cursor, 1);
-  if ((long long)off + cnt > M.fix_cap || sid >= M.fixseg_cap)
+  if ((long long)off + cnt > M.fix_cap)
   {
     atomicOr(M.status, VN_ST_FIX_FULL);
     return -1;
   }
-  FixSeg& s = M.fix_segs[sid];
-  s.off = off;
-  s.cnt = cnt;
-  s.next = -1;
-  if (c.fix_tail >= 0)
-    M.fix_segs[c.fix_tail].next = sid;
+  if (c.fix_tail >= 0 && M.fix_segs[c.fix_tail].n < VN_FIXSEG_PER_BLOCK)
+  {
+    FixSeg& b = M.fix_segs[c.fix_tail];
+    const int e = b.n;
+    b.off[e] = off;
+    b.cnt[e] = cnt;
+    b.n = e + 1;
+  }
   else
-    c.fix_head = sid;
-  c.fix_tail = sid;
+  {
+    int sid = atomicAdd(M.fixseg_cursor, 1);
+    if (sid >= M.fixseg_cap)
+    {
+      atomicOr(M.status, VN_ST_FIX_FULL);
+      return -1;
+    }
+    FixSeg& b = M.fix_segs[sid];
+    b.off[0] = off;
+    b.cnt[0] = cnt;
+    b.n = 1;
+    b.next = -1;
+    if (c.fix_tail >= 0)
+      M.fix_segs[c.fix_tail].next = sid;
+    else
+      c.fix_head = sid;
+    c.fix_tail = sid;
+  }
   c.fix_count += cnt;
   return off;
 }
@@ -763,24 +781,27 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       int ns = 0, tot = 0;
       bool overflow = false;
       if (has_fix)
-        for (int sg = c.fix_head; sg >= 0;)
+        for (int sg = c.fix_head; sg >= 0 && !overflow;)
         {
-          const FixSeg seg = M.fix_segs[sg];
-          if (seg.cnt > 0)
+          const FixSeg& blk = M.fix_segs[sg];  // one 128-byte line: 15 segments per dependent load
+          const int nb = blk.n;
+          for (int e = 0; e < nb; e++)
           {
+            const int scnt = blk.cnt[e];
+            if (scnt <= 0) continue;
             if (ns >= SPLIT_MAXSEG - VINA_MAX_WIN)
             {
               overflow = true;
               break;
             }
-            segs[ns].src = M.fix_pool + seg.off;
+            segs[ns].src = M.fix_pool + blk.off[e];
             segs[ns].start = tot;
-            segs[ns].cnt = seg.cnt;
+            segs[ns].cnt = scnt;
             segs[ns].cls = 0;
-            tot += seg.cnt;
+            tot += scnt;
             ns++;
           }
-          sg = seg.next;
+          sg = blk.next;
         }
       if (overflow) atomicOr(M.status, VN_ST_FIX_FULL);
       nfix = ns;
@@ -1255,17 +1276,35 @@ __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, 
       const int n = nodes[j];
       if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb, lv, job_src, job_off, job_np);
     }
-    // the warp's copy jobs, one after the other, 32 points at a time (points go to the world frame of x_buf[0])
-    unsigned int todo = __ballot_sync(0xffffffffu, job_np > 0);
-    while (todo)
+    // the warp's copy jobs as ONE stream of points, 32 per pass (points go to the world frame of x_buf[0]): a
+    // leaf folds only a handful of points per scan, so walking the jobs one after the other would leave most
+    // lanes idle and pay one load latency per leaf instead of one per 32 points
+    int incl = job_np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
     {
-      const int l = __ffs(todo) - 1;
-      todo &= todo - 1;
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - job_np;
+    for (int base = 0; base < total; base += 32)
+    {
+      const int idx = base + lane;
+      // owner = the last lane whose first point is at or before idx (empty jobs share their successor's start)
+      int own = 0;
+#pragma unroll
+      for (int st = 16; st > 0; st >>= 1)
+      {
+        const int cand = own + st;
+        const int e = __shfl_sync(0xffffffffu, excl, cand & 31);
+        if (e <= idx) own = cand;
+      }
       const PointRec* src = reinterpret_cast<const PointRec*>(
-          __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(job_src), l));
-      const int off = __shfl_sync(0xffffffffu, job_off, l);
-      const int np = __shfl_sync(0xffffffffu, job_np, l);
-      for (int a = lane; a < np; a += 32)
+          __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(job_src), own));
+      const int off = __shfl_sync(0xffffffffu, job_off, own);
+      const int a = idx - __shfl_sync(0xffffffffu, excl, own);
+      if (idx < total)
       {
         PointRec pr = src[a];
         double pw[3], xr[9], xp[3];

@@ -195,8 +195,9 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&M.win_cursor, VINA_MAX_WIN));
   M.fix_cap = cfg.fix_pool_points;
   CU(dalloc(&M.fix_pool, (size_t)cfg.fix_pool_points, false));
-  M.fixseg_cap = (int)(cfg.fix_pool_points / 4 > (1 << 30) ? (1 << 30) : cfg.fix_pool_points / 4);
-  if (M.fixseg_cap < 1024) M.fixseg_cap = 1024;
+  // chain blocks of 15 segments (128 B each): one per leaf that keeps fixed points, plus one per 15 folds
+  M.fixseg_cap = (int)(cfg.fix_pool_points / 16 > (1 << 28) ? (1 << 28) : cfg.fix_pool_points / 16);
+  if (M.fixseg_cap < 4096) M.fixseg_cap = 4096;
   CU(dalloc(&M.fix_segs, (size_t)M.fixseg_cap, false));
   CU(dalloc(&M.fix_cursor, 1));
   CU(dalloc(&M.fixseg_cursor, 1));
