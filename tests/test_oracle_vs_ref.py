@@ -98,7 +98,7 @@ def test_ba_lidar_factor_reproduces_reference(oracle_lib):
     mod = _scenario()
     o = mod.run_ba(lambda cfg: oracle_lib.Odom(cfg))
     assert int(g["n_factors"][0]) > 1000 and np.abs(g["J1"]).max() > 10 * np.abs(g["J0"]).max()
-    assert np.allclose(g["H1"], g["H1"].T, rtol=0, atol=0)  # acc_evaluate2 mirrors the upper blocks
+    assert np.array_equal(g["H1"][6:12, 0:6], g["H1"][0:6, 6:12].T)  # acc_evaluate2 mirrors the upper blocks
     assert g["residuals"][2] > 3 * g["residuals"][0]  # the perturbed poses are visibly worse
     _assert_same(o, g, "oracle BA vs reference golden")
     if oracle_lib.have_ref():
