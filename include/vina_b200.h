@@ -322,6 +322,26 @@ int vina_odom_iekf_host(vina_ctx* ctx, int which, int max_iter, int* iters_out, 
 int vina_odom_map_update(vina_ctx* ctx); /* pvec_update + insert + recut + (margi + shift) with x_curr */
 int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap);
 int vina_get_timings(vina_ctx* ctx, vina_timings* t);
+/* ---- sliding-window BA, the LiDAR factor (the data-parallel part of LI_BA_Optimizer::damping_iter,
+ * src/mapping/optimizers.cpp:430-517; the IMU pre-integration factors and the LM loop are host work and not
+ * part of this library yet). The factor store is the device form of the reference's `voxhess` container.
+ *   vina_ba_collect          tras_opt (octree.cpp:498-521, local_mapping.cpp:196-200): copy every plane leaf of the
+ *                            slide map that k_recut marked as a factor (lambda_0 / lambda_1 <= 0.12) into the store.
+ *                            Call between vina_map_recut and vina_map_margi. vina_ba_set_capture(ctx, 1) makes
+ *                            vina_odom_map_update / vina_odom_step do it after every recut with a full window.
+ *   vina_ba_lidar_hessian    LidarFactor::acc_evaluate2 (factors.cpp:22-126) over all factors for the window poses
+ *                            xs: Hess (6 win x 6 win, column-major, lower blocks mirrored), JacT (6 win), residual.
+ *   vina_ba_lidar_residual   LidarFactor::evaluate_only_residual (factors.cpp:128-158): the residual at candidate
+ *                            poses; overwrites the stored factors' eigen-decomposition and pcr_add like the
+ *                            reference's container. lam0 (nullable, cap entries) receives lambda_0 per factor.
+ * Sums over factors run in the store's order (arrival order of an atomic cursor): results agree with the
+ * reference to rounding (tests: 1e-9 of the largest entry), the per-factor eigenvalues bit for bit. */
+int vina_ba_set_capture(vina_ctx* ctx, int on);
+int vina_ba_collect(vina_ctx* ctx, int32_t* n_factors);
+int vina_ba_count(vina_ctx* ctx, int32_t* n_factors);
+int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win, double* Hess, double* JacT, double* residual);
+int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int win, double* residual, double* lam0, int cap);
+
 /* record per-stage CUDA-event timings (adds event records + one sync per step) */
 int vina_set_profiling(vina_ctx* ctx, int on);
 /* vina_odom_step / _step_resident schedule (default on): down-sampling and the var_init of the map's point set run

@@ -957,6 +957,63 @@ def test_overlapped_step_is_bitwise_the_serial_step(oracle_lib, gpu_lib):
         gx.close()
 
 
+def test_ba_lidar_factor_matches_oracle(oracle_lib, gpu_lib):
+    """SURVEY section 8f rank 3, the data-parallel part of the sliding-window BA: the device factor store
+    (tras_opt) and LidarFactor::acc_evaluate2 / evaluate_only_residual (factors.cpp:22-158) against the oracle,
+    which reproduces the reference's own factors.cpp bit for bit (tests/test_oracle_vs_ref.py). Same factor set;
+    Hessian / gradient / residual to 1e-9 of the largest entry (the sum over ~10^3 factors runs in another order);
+    every factor's lambda_0 after evaluate_only_residual bit for bit; the overwrite of the stored eig / pcr_add by
+    evaluate_only_residual is visible in the next Hessian exactly like in the reference's container."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "make_ref_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_ref_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    cfg = synth.small_sensor("robosense128", 24, 400, seed=31)  # the scenario of tests/golden/ref_ba.npz
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    od.ba_probe(True)
+    gx.ba_set_capture(True)
+    for _ in range(cfg.win_size + 3):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.set_state(gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.down_upload(od.last_down())
+        gx.var_init(1)
+        gx.odom_map_update()
+    n = od.ba_count()
+    assert gx.ba_count() == n > 1000
+    poses = od.ba_poses()
+    pert = mod.perturbed_poses(poses)
+
+    def close(a, b, tol=1e-9):
+        return np.max(np.abs(np.asarray(a) - np.asarray(b))) <= tol * max(np.max(np.abs(np.asarray(b))), 1e-300)
+
+    for ps in (poses, pert):
+        Ho, Jo, ro = od.ba_hess(ps)
+        Hg, Jg, rg = gx.ba_hess(ps)
+        assert close(Hg, Ho) and close(Jg, Jo) and abs(rg - ro) <= 1e-12 * abs(ro), (np.max(np.abs(Hg - Ho)), np.max(np.abs(Ho)))
+        assert np.array_equal(Hg[6:12, 0:6], Hg[0:6, 6:12].T)  # lower blocks mirrored (factors.cpp:123-125)
+    ro, lo = od.ba_residual(pert)
+    rg, lg = gx.ba_residual(pert)
+    assert abs(rg - ro) <= 1e-12 * abs(ro) and ro > 0.2  # the perturbed poses are visibly worse (0.10 at the captured ones)
+    assert np.array_equal(np.sort(lg), np.sort(lo)), "per-factor eigenvalues differ"
+    # the stored factors now carry the perturbed eig / pcr_add on both sides
+    Ho, Jo, ro2 = od.ba_hess(pert)
+    Hg, Jg, rg2 = gx.ba_hess(pert)
+    assert close(Hg, Ho) and close(Jg, Jo) and abs(rg2 - ro2) <= 1e-12 * abs(ro2)
+    assert abs(ro2 - ro) <= 1e-12 * ro  # acc_evaluate2 reports the stored lambda_0 sum
+    # and against the reference's golden vectors directly
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ba.npz")))
+    assert int(g["n_factors"][0]) == n and close(Hg, g["H2"]) and close(Jg, g["J2"])
+    gx.close()
+    od.close()
+
+
 def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     """150 scans through the full per-scan path (the window slides 150 times, leaves saturate, point_fix lists
     are dropped and re-created, the slide map turns over): trajectory within 1 mm / 0.01 deg of the oracle at

@@ -72,7 +72,8 @@ EXPORTS = [
     "vina_shard_query_accumulate", "vina_odom_iekf_host_begin", "vina_odom_iekf_host_update",
     "vina_shard_p2p_create", "vina_shard_p2p_connect", "vina_shard_p2p_pointers", "vina_shard_p2p_connect_local",
     "vina_shard_route_p2p", "vina_shard_insert_begin_p2p", "vina_odom_iekf_sharded_p2p",
-    "vina_set_overlap",
+    "vina_set_overlap", "vina_ba_set_capture", "vina_ba_collect", "vina_ba_count", "vina_ba_lidar_hessian",
+    "vina_ba_lidar_residual",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -390,6 +391,40 @@ class Ctx:
     def odom_iekf_host_update(self, sums34) -> bool:
         a = np.ascontiguousarray(sums34, dtype=np.float64)
         return self._ck(self.lib.vina_odom_iekf_host_update(self.h, _dp(a))) == 1
+
+    # ---- BA LiDAR factor (factors.cpp:22-158 on the device factor store)
+    def ba_set_capture(self, on: bool = True):
+        self._ck(self.lib.vina_ba_set_capture(self.h, C.c_int(1 if on else 0)))
+
+    def ba_collect(self) -> int:
+        n = C.c_int32(0)
+        self._ck(self.lib.vina_ba_collect(self.h, C.byref(n)))
+        return n.value
+
+    def ba_count(self) -> int:
+        n = C.c_int32(0)
+        self._ck(self.lib.vina_ba_count(self.h, C.byref(n)))
+        return n.value
+
+    def ba_hess(self, poses12):
+        """poses12: (win, 12) = R column-major + p per window frame. Returns (Hess (6w, 6w), JacT, residual)."""
+        ps = np.ascontiguousarray(poses12, dtype=np.float64)
+        w = ps.shape[0]
+        H = np.zeros(36 * w * w, dtype=np.float64)
+        J = np.zeros(6 * w, dtype=np.float64)
+        r = C.c_double(0)
+        self._ck(self.lib.vina_ba_lidar_hessian(self.h, ps.ctypes.data_as(C.c_void_p), C.c_int(w), _dp(H), _dp(J), C.byref(r)))
+        return H.reshape(6 * w, 6 * w).T.copy(), J, r.value
+
+    def ba_residual(self, poses12):
+        """Returns (residual, lambda_0 per factor); overwrites the stored factors' eig / pcr_add."""
+        ps = np.ascontiguousarray(poses12, dtype=np.float64)
+        n = self.ba_count()
+        lam = np.zeros(max(n, 1), dtype=np.float64)
+        r = C.c_double(0)
+        self._ck(self.lib.vina_ba_lidar_residual(self.h, ps.ctypes.data_as(C.c_void_p), C.c_int(ps.shape[0]), C.byref(r),
+                                                 _dp(lam), C.c_int(n)))
+        return r.value, lam[:n]
 
     def set_overlap(self, on: bool):
         self._ck(self.lib.vina_set_overlap(self.h, C.c_int(1 if on else 0)))

@@ -697,6 +697,38 @@ __global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, i
   }
 }
 
+// tras_opt with the container (octree.cpp:498-521, local_mapping.cpp:196-200): every leaf k_recut_layer marked as a
+// BA factor is copied into the factor store (the reference copies the same fields into LidarFactor's vectors).
+// blockIdx.y = layer. The order of the factors is the order of arrival (atomic cursor).
+__global__ void __launch_bounds__(128) k_ba_collect(MapView M, LayerLists LL, BaFactor* __restrict__ out, int* __restrict__ count,
+                                                    int cap)
+{
+  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // multi_recut's early-out
+  int nn;
+  const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
+  {
+    const int n = nodes[j];
+    if (M.hot[n].flags & VN_FLAG_INTERIOR) continue;
+    const NodeCold& c = M.cold[n];
+    if (c.opt_state < 0) continue;
+    const int a = atomicAdd(count, 1);
+    if (a >= cap)
+    {
+      atomicOr(M.status, VN_ST_NODES_FULL);
+      continue;
+    }
+    BaFactor& f = out[a];
+    for (int i = 0; i < M.win_size; i++) f.local[i] = c.pcrs_local[M.mp[i]];
+    f.fix = c.pcr_fix;
+    f.add = c.pcr_add;
+    for (int k = 0; k < 3; k++) f.eig_value[k] = c.eig_value[k];
+    for (int k = 0; k < 9; k++) f.eig_vector[k] = c.eig_vector[k];
+    f.coe = 1.0;
+    f.node = n;
+  }
+}
+
 // The subdivision branch of OctoTree::recut (octree.cpp:375-387): fix_divide (:257-277), subdivide per
 // window frame (:279-300), release of the parent's SlideWindow (:384-387). One 256-thread block per
 // splitting leaf. Source classes in the reference's order: class 0 = point_fix, class 1+si =
@@ -1537,6 +1569,13 @@ int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, 
   k_zero_ints<<<1, 32, 0, st>>>(map.slide_count + (1 - map.slide_cur), 1);
   k_slide_compact<<<296, 128, 0, st>>>(map);
   return launches + 3;
+}
+
+int launch_ba_collect(cudaStream_t st, const MapView& map, const LayerLists& LL, BaFactor* out, int* count, int cap)
+{
+  k_zero_ints<<<1, 32, 0, st>>>(count, 1);
+  k_ba_collect<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL, out, count, cap);
+  return 2;
 }
 
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count)

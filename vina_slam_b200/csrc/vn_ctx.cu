@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "vn_ctx.h"
 #include <cstdlib>
 
@@ -291,6 +292,11 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
     if (ctx->tr_ev[i]) cudaEventDestroy(ctx->tr_ev[i]);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  cudaFree(ctx->d_ba);
+  cudaFree(ctx->d_ba_n);
+  cudaFree(ctx->d_ba_partial);
+  cudaFree(ctx->d_ba_out);
+  cudaFree(ctx->d_ba_lam);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   for (void* m : ctx->p2p_opened)
@@ -1194,6 +1200,103 @@ extern "C" int vina_shard_insert_finish(vina_ctx* ctx, int win_ord, int global_r
   if (ctx->map.slide_others < 0) ctx->map.slide_others = 0;
   ctx->launches += 1 + launch_map_insert_leaves(ctx->stream, ctx->map, ctx->pv[1], nullptr, ctx->n_pv[1], ctx->ins, win_ord);
   return VINA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// BA LiDAR factor (ba_kernels.cu)
+static int ensure_ba(vina_ctx* ctx)
+{
+  if (ctx->d_ba) return VINA_OK;
+  long long cap = (long long)ctx->map.max_nodes;
+  if (cap > (1 << 20)) cap = 1 << 20;  // 1.1 GB of factors at most
+  CU(dalloc(&ctx->d_ba, (size_t)cap, false));
+  CU(dalloc(&ctx->d_ba_n, 1));
+  CU(dalloc(&ctx->d_ba_partial, ba_partial_doubles(ctx->sm_count), false));
+  CU(dalloc(&ctx->d_ba_out, (size_t)36 * VINA_MAX_WIN * VINA_MAX_WIN + 6 * VINA_MAX_WIN + 8));
+  CU(dalloc(&ctx->d_ba_lam, (size_t)cap, false));
+  CU(cudaDeviceSynchronize());  // see ensure_debug
+  ctx->ba_cap = (int)cap;
+  return VINA_OK;
+}
+
+int vn_ba_collect_enqueue(vina_ctx* ctx)
+{
+  int r = ensure_ba(ctx);
+  if (r) return r;
+  ctx->launches += launch_ba_collect(ctx->stream, ctx->map, ctx->layers, ctx->d_ba, ctx->d_ba_n, ctx->ba_cap);
+  ctx->ba_n = -1;
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_collect");
+}
+
+extern "C" int vina_ba_set_capture(vina_ctx* ctx, int on)
+{
+  if (!ctx) return VINA_E_ARG;
+  ctx->ba_capture = on != 0;
+  return VINA_OK;
+}
+
+extern "C" int vina_ba_collect(vina_ctx* ctx, int32_t* n_factors)
+{
+  if (!ctx) return VINA_E_ARG;
+  int r = vn_ba_collect_enqueue(ctx);
+  if (r) return r;
+  return vina_ba_count(ctx, n_factors);
+}
+
+extern "C" int vina_ba_count(vina_ctx* ctx, int32_t* n_factors)
+{
+  if (!ctx || !n_factors) return VINA_E_ARG;
+  if (!ctx->d_ba) return vn_fail(ctx, VINA_E_STATE, "no BA factors collected yet");
+  if (ctx->ba_n < 0)
+  {
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, ctx->d_ba_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ba_n = n < ctx->ba_cap ? n : ctx->ba_cap;
+  }
+  *n_factors = ctx->ba_n;
+  return vn_check_status(ctx);
+}
+
+extern "C" int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win, double* Hess, double* JacT,
+                                     double* residual)
+{
+  if (!ctx || !xs || win < 1 || win > VINA_MAX_WIN || !Hess || !JacT || !residual) return VINA_E_ARG;
+  if (!ctx->d_ba) return vn_fail(ctx, VINA_E_STATE, "no BA factors collected yet");
+  if (win != ctx->cfg.win_size) return vn_fail(ctx, VINA_E_ARG, "win %d != LocalBA.win_size %d", win, ctx->cfg.win_size);
+  const size_t dim = 6 * (size_t)win;
+  CU(cudaMemsetAsync(ctx->d_ba_out, 0, (dim * dim + dim + 1) * sizeof(double), ctx->stream));
+  ctx->launches += launch_ba_hess(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win, ctx->sm_count,
+                                  ctx->d_ba_partial, ctx->d_ba_out);
+  std::vector<double> h(dim * dim + dim + 1);
+  CU(cudaMemcpyAsync(h.data(), ctx->d_ba_out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(Hess, h.data(), dim * dim * sizeof(double));
+  memcpy(JacT, h.data() + dim * dim, dim * sizeof(double));
+  *residual = h[dim * dim + dim];
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_hess");
+}
+
+extern "C" int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int win, double* residual, double* lam0, int cap)
+{
+  if (!ctx || !xs || win < 1 || win > VINA_MAX_WIN || !residual || (lam0 && cap < 0)) return VINA_E_ARG;
+  if (!ctx->d_ba) return vn_fail(ctx, VINA_E_STATE, "no BA factors collected yet");
+  if (win != ctx->cfg.win_size) return vn_fail(ctx, VINA_E_ARG, "win %d != LocalBA.win_size %d", win, ctx->cfg.win_size);
+  int32_t n = 0;
+  int r = vina_ba_count(ctx, &n);
+  if (r) return r;
+  ctx->launches += launch_ba_residual(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win,
+                                      ctx->sm_count, ctx->d_ba_partial, ctx->d_ba_lam);
+  const int nblk = ctx->sm_count * 2;
+  std::vector<double> part(nblk);
+  CU(cudaMemcpyAsync(part.data(), ctx->d_ba_partial, nblk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (lam0 && n > 0)
+    CU(cudaMemcpyAsync(lam0, ctx->d_ba_lam, (size_t)(n < cap ? n : cap) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double s = 0.0;
+  for (int b = 0; b < nblk; b++) s += part[b];  // block order: deterministic for a given factor order
+  *residual = s;
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_residual");
 }
 
 extern "C" int vina_set_profiling(vina_ctx* ctx, int on)

@@ -95,6 +95,15 @@ struct vina_ctx
   double tr_host_us[8] = { 0 };
   double tr_dev_us[8] = { 0 };
   int tr_n = 0;
+  // BA LiDAR factor store (allocated on first use): the device form of the reference's `voxhess`
+  BaFactor* d_ba = nullptr;
+  int ba_cap = 0;
+  int* d_ba_n = nullptr;
+  int ba_n = -1;             // host copy (valid after vina_ba_collect)
+  double* d_ba_partial = nullptr;
+  double* d_ba_out = nullptr;   // Hess (6 win)^2, JacT (6 win), residual
+  double* d_ba_lam = nullptr;
+  bool ba_capture = false;   // vina_ba_set_capture: collect after every recut with a full window
   // profiling
   bool profiling = false;
   cudaEvent_t ev[16];
@@ -119,6 +128,7 @@ void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 // enqueue max_iter iterations of the IEKF against the sharded map, exchange and update on the device (vn_ctx.cu)
 int vn_shard_iekf_enqueue(vina_ctx* c, int first, int count, int max_iter, int part);
 int vn_mark_scan_read(vina_ctx* c);
+int vn_ba_collect_enqueue(vina_ctx* c);  // tras_opt into the factor store (after recut, before margi)
 // map update with the newest pose read from the device iterate (vn_ctx.cu)
 int vn_map_insert_live(vina_ctx* c, int win_ord);
 int vn_map_recut_live(vina_ctx* c, int win_count, const vina_pose* x_buf);

@@ -109,6 +109,19 @@ struct NodeCold
   int children[8];
 };
 
+// One LiDAR BA factor = one entry of the reference's LidarFactor container (factors.hpp:10-40), filled by
+// tras_opt (octree.cpp:498-521) for every plane leaf of the slide map with lambda_0 / lambda_1 <= 0.12
+struct BaFactor
+{
+  Cluster local[VINA_MAX_WIN];  // sw->pcrs_local[mp[i]], body frame of window frame i
+  Cluster fix;                  // pcr_fix (world frame)
+  Cluster add;                  // pcr_add; overwritten by evaluate_only_residual
+  double eig_value[3];
+  double eig_vector[9];  // column-major
+  double coe;
+  int node, pad;
+};
+
 // control block of the P2P record exchange (shard_kernels.cu); lives in the owner's memory, written by peers
 struct ShardChan
 {

@@ -478,6 +478,11 @@ static int map_update(vina_ctx* ctx, OdomHost* o)
   if (ctx->profiling) cudaEventRecord(ev[5], ctx->stream);
   r = vina_map_recut(ctx, o->win_count, o->x_buf.data());
   if (r) return r;
+  if (ctx->ba_capture && o->win_count >= ctx->cfg.win_size)
+  {
+    r = vn_ba_collect_enqueue(ctx);  // the factors damping_iter would consume (local_mapping.cpp:492-497)
+    if (r) return r;
+  }
   if (ctx->profiling) cudaEventRecord(ev[6], ctx->stream);
   if (o->win_count >= ctx->cfg.win_size)
   {
@@ -631,6 +636,11 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (r) return r;
   if (tr) cudaEventRecord(ctx->tr_ev[4], A);
   const bool margi = o->win_count >= ctx->cfg.win_size;
+  if (margi && ctx->ba_capture)
+  {
+    r = vn_ba_collect_enqueue(ctx);
+    if (r) return r;
+  }
   if (margi)
   {
     r = vn_map_margi_live(ctx, o->win_count, o->x_buf.data());
