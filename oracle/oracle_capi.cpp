@@ -184,6 +184,13 @@ void* vo_odom_create(const vo_config* cfg)
   o->odom_ekf.cov_acc = V3(cfg->cov_acc, cfg->cov_acc, cfg->cov_acc);
   o->odom_ekf.cov_bias_gyr = V3(cfg->rdw_gyr, cfg->rdw_gyr, cfg->rdw_gyr);
   o->odom_ekf.cov_bias_acc = V3(cfg->rdw_acc, cfg->rdw_acc, cfg->rdw_acc);
+  for (int k = 0; k < 3; k++)  // node.cpp:262-265
+  {
+    o->ba_noise.noiseMeas(k, k) = cfg->cov_gyr;
+    o->ba_noise.noiseMeas(3 + k, 3 + k) = cfg->cov_acc;
+    o->ba_noise.noiseWalk(k, k) = cfg->rdw_gyr;
+    o->ba_noise.noiseWalk(3 + k, 3 + k) = cfg->rdw_acc;
+  }
   return o;
 }
 void vo_odom_destroy(void* h) { delete (Odom*)h; }
@@ -200,6 +207,7 @@ void vo_odom_set_imu_anchor(void* h, double last_pcl_end_time, const double last
     o->odom_ekf.last_imu.acc[k] = last_imu7[4 + k];
   }
   o->odom_ekf.scale_gravity = scale_gravity;
+  o->ba_noise.scale_gravity = scale_gravity;  // node.cpp:309
 }
 void vo_odom_bootstrap(void* h, const float* xyz4, int n, const vo_state* x_known)
 {
@@ -460,6 +468,18 @@ int vo_odom_ba_residual(void* h, const double* poses12, int win, double* residua
   if (lam0)
     for (int a = 0; a < n && a < cap; a++) lam0[a] = o->ba_factors.eig_values[a][0];
   return 0;
+}
+void vo_odom_set_ba(void* h, int on, double imu_coef)
+{
+  Odom* o = (Odom*)h;
+  o->if_BA = on != 0;
+  if (imu_coef > 0) o->imu_coef = imu_coef;
+}
+void vo_odom_ba_stats(void* h, int* runs, int* last_iters)
+{
+  Odom* o = (Odom*)h;
+  *runs = o->ba_runs;
+  *last_iters = o->ba_last_iters;
 }
 int vo_odom_window(void* h, int* win_count, int* mp, int cap)
 {

@@ -99,6 +99,11 @@ int vo_odom_window(void* h, int* win_count, int* mp, int cap);
  * evaluate_only_residual (factors.cpp:22-158) on a copy of the LiDAR factors and window poses taken between
  * multi_recut and multi_margi of the last map update with a full window (where damping_iter consumes them,
  * local_mapping.cpp:492-497). poses12 = win x (R 9 column-major, p 3). Hess is (6 win)^2 column-major. */
+/* the whole sliding-window BA (LI_BA_Optimizer::damping_iter, LiDAR + IMU pre-integration factors) inside
+ * vo_odom_step, like local_mapping.cpp:492-497 with if_BA: 1. It runs once every pair of consecutive window frames
+ * has an IMU factor (frames inserted by vo_odom_bootstrap have none). imu_coef <= 0 keeps LocalBA.imu_coef = 1e-4. */
+void vo_odom_set_ba(void* h, int on, double imu_coef);
+void vo_odom_ba_stats(void* h, int* runs, int* last_iters);
 void vo_odom_ba_probe(void* h, int on);
 int vo_odom_ba_count(void* h);
 int vo_odom_ba_poses(void* h, double* poses12, int cap);

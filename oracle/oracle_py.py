@@ -98,7 +98,7 @@ def load(fast: bool = False, ref: bool = False):
     lib.vo_odom_create.argtypes = [C.POINTER(VoConfig)]
     for fn in ("vo_odom_destroy", "vo_odom_set_state", "vo_odom_get_state", "vo_odom_set_imu_anchor",
                "vo_odom_bootstrap", "vo_odom_stage_times", "vo_odom_deskew", "vo_odom_set_dump",
-               "vo_odom_map_update"):
+               "vo_odom_map_update", "vo_odom_set_ba", "vo_odom_ba_stats", "vo_odom_ba_probe"):
         if hasattr(lib, fn):
             getattr(lib, fn).restype = None
     lib.vo_odom_map_count.restype = C.c_int64
@@ -290,6 +290,15 @@ class Odom:
         mp = np.zeros(16, dtype=np.int32)
         ws = self.lib.vo_odom_window(self.h, C.byref(wc), _ptr(mp, C.c_int), C.c_int(16))
         return wc.value, mp[:ws].copy()
+
+    def set_ba(self, on: bool = True, imu_coef: float = 0.0):
+        """if_BA (local_mapping.cpp:492-497): LI_BA_Optimizer after every recut with a full window."""
+        self.lib.vo_odom_set_ba(self.h, C.c_int(1 if on else 0), C.c_double(imu_coef))
+
+    def ba_stats(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self.lib.vo_odom_ba_stats(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     # ---- BA probe: LidarFactor (factors.cpp:22-158) on the factors captured by the last full-window map update
     def ba_probe(self, on: bool = True):

@@ -19,6 +19,8 @@
 #include "vina_slam/platform/ros2/node.hpp"
 #include "vina_slam/core/point_utils.hpp"
 #include "vina_slam/mapping/voxel_map.hpp"
+#include "vina_slam/mapping/optimizers.hpp"
+#include "vina_slam/preintegration.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -51,6 +53,11 @@ struct RefOdom
   bool ba_probe = false;
   LidarFactor ba_factors;
   vector<IMUST> ba_xs;
+  // sliding-window BA (local_mapping.cpp:437-441, 492-497, 541-546); frames inserted by bootstrap carry no
+  // pre-integration factor (nullptr): BA runs once every pair of consecutive window frames has one
+  bool if_BA = false;
+  deque<IMU_PRE*> imu_pre_buf;
+  int ba_runs = 0, ba_last_iters = 0;
   RefOdom(int win) : vs(nullptr), voxhess(win), normalFactor(win), ba_factors(win) {}
 
   // local_mapping.cpp:144-201 (the overload the per-scan loop calls, :451)
@@ -142,12 +149,22 @@ struct RefOdom
   }
 
   // local_mapping.cpp:434-451 and 489-546 with if_BA == 0
-  void map_update(PVecPtr pptr)
+  void map_update(PVecPtr pptr, deque<std::shared_ptr<sensor_msgs::msg::Imu>>* imus = nullptr)
   {
     const int mgsize = 1;
     vs.win_count++;
     vs.x_buf.push_back(vs.x_curr);
     vs.pvec_buf.push_back(pptr);
+    if (vs.win_count > 1)
+    {
+      IMU_PRE* f = nullptr;
+      if (imus)
+      {
+        f = new IMU_PRE(vs.x_buf[vs.win_count - 2].bg, vs.x_buf[vs.win_count - 2].ba);
+        f->push_imu(*imus);
+      }
+      imu_pre_buf.push_back(f);
+    }
     voxhess.clear();
     voxhess.win_size = vs.win_size;
     normalFactor.clear();
@@ -168,6 +185,15 @@ struct RefOdom
     }
     if (vs.win_count >= vs.win_size)
     {
+      bool all_imu = (int)imu_pre_buf.size() == vs.win_count - 1;
+      for (IMU_PRE* f : imu_pre_buf) all_imu = all_imu && f != nullptr;
+      if (if_BA && all_imu && (int)vs.surf_map_slide.size() >= vs.thread_num)
+      {
+        LI_BA_Optimizer opt_lsv;  // local_mapping.cpp:492-497
+        Eigen::MatrixXd hess;
+        opt_lsv.damping_iter(vs.x_buf, voxhess, imu_pre_buf, &hess);
+        ba_runs++;
+      }
       vs.x_curr.R = vs.x_buf[vs.win_count - 1].R;
       vs.x_curr.p = vs.x_buf[vs.win_count - 1].p;
       double t5 = now_s();
@@ -189,6 +215,8 @@ struct RefOdom
       {
         vs.x_buf.pop_back();
         vs.pvec_buf.pop_back();
+        delete imu_pre_buf.front();
+        imu_pre_buf.pop_front();
       }
       vs.win_base += mgsize;
       vs.win_count -= mgsize;
@@ -233,7 +261,7 @@ struct RefOdom
     pwld.clear();
     pvec_update(pptr, vs.x_curr, pwld);
     t_odom = now_s() - t0;
-    map_update(pptr);
+    map_update(pptr, &imus);
     return 0;
   }
 
@@ -404,6 +432,11 @@ void* vo_odom_create(const vo_config* cfg)
   e.cov_acc << cfg->cov_acc, cfg->cov_acc, cfg->cov_acc;
   e.cov_bias_gyr << cfg->rdw_gyr, cfg->rdw_gyr, cfg->rdw_gyr;
   e.cov_bias_acc << cfg->rdw_acc, cfg->rdw_acc, cfg->rdw_acc;
+  noiseMeas.setZero();  // node.cpp:262-265
+  noiseWalk.setZero();
+  noiseMeas.diagonal() << cfg->cov_gyr, cfg->cov_gyr, cfg->cov_gyr, cfg->cov_acc, cfg->cov_acc, cfg->cov_acc;
+  noiseWalk.diagonal() << cfg->rdw_gyr, cfg->rdw_gyr, cfg->rdw_gyr, cfg->rdw_acc, cfg->rdw_acc, cfg->rdw_acc;
+  imupre_scale_gravity = 1.0;
   e.init_flag = true;  // the harness bootstraps instead of IMU_init
   e.pcl_beg_time = e.pcl_end_time = e.last_pcl_end_time = 0;
   vs.x_curr.g = Eigen::Vector3d(0, 0, -9.8);
@@ -431,6 +464,7 @@ void vo_odom_set_imu_anchor(void* h, double last_end, const double last_imu7[7],
   e.last_pcl_end_time = last_end;
   e.last_imu = to_imu(last_imu7);
   e.scale_gravity = scale_gravity;
+  imupre_scale_gravity = scale_gravity;  // node.cpp:309
 }
 void vo_odom_bootstrap(void* h, const float* xyz4, int n, const vo_state* x_known)
 {
@@ -610,6 +644,16 @@ int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap)
   int64_t c = 0;
   for (auto& kv : o->vs.surf_map) export_node(o, kv.second, kv.first, 0, out, cap, c);
   return c;
+}
+void vo_odom_set_ba(void* h, int on, double coef)
+{
+  ((RefOdom*)h)->if_BA = on != 0;
+  if (coef > 0) imu_coef = coef;  // optimizers.cpp:8
+}
+void vo_odom_ba_stats(void* h, int* runs, int* last_iters)
+{
+  *runs = ((RefOdom*)h)->ba_runs;
+  *last_iters = ((RefOdom*)h)->ba_last_iters;
 }
 // ---- BA probe: the reference's LidarFactor::acc_evaluate2 / evaluate_only_residual (factors.cpp:22-158) on
 // the factors captured by the last map update

@@ -267,7 +267,44 @@ public:
   Matrix<double, Dynamic, 1> head(int n) const;
 };
 
-// minimal dynamic matrix: enough for the declarations in factors.hpp / optimizers (not on the hot path)
+// dynamic matrix / vector (eager, runtime dimensions): what factors.cpp, imu_preintegration.cpp and optimizers.cpp
+// use - fixed-size block views, topRows / leftCols / head / tail views, diagonal(), +, -, scalar and matrix
+// products, dot, ldlt().solve()
+template <typename P>
+struct DynView  // rows [r0, r0+nr) x cols [c0, c0+nc) of a dynamic matrix
+{
+  P& p;
+  int r0, c0, nr, nc;
+  DynView(P& p_, int r, int c, int rr, int cc) : p(p_), r0(r), c0(c), nr(rr), nc(cc) {}
+  void setZero()
+  {
+    for (int j = 0; j < nc; j++)
+      for (int i = 0; i < nr; i++) p.ref(r0 + i, c0 + j) = 0.0;
+  }
+  template <typename Q>
+  DynView& operator+=(const DynView<Q>& o)
+  {
+    for (int j = 0; j < nc; j++)
+      for (int i = 0; i < nr; i++) p.ref(r0 + i, c0 + j) = p.ref(r0 + i, c0 + j) + o.p.coeff(o.r0 + i, o.c0 + j);
+    return *this;
+  }
+  double coeff(int i, int j = 0) const { return p.coeff(r0 + i, c0 + j); }
+};
+template <typename P>
+struct DynDiag
+{
+  P& p;
+  explicit DynDiag(P& p_) : p(p_) {}
+  DynDiag& operator=(const DynDiag& o)
+  {
+    for (int i = 0; i < p.rows(); i++) p.ref(i, i) = o.p.coeff(i, i);
+    return *this;
+  }
+};
+template <int C>
+class Matrix<double, Dynamic, C>;
+struct DynLDLT;
+
 template <int C>
 class Matrix<double, Dynamic, C>
 {
@@ -276,21 +313,226 @@ public:
   int r = 0, c = 0;
   Matrix() {}
   Matrix(int rr, int cc = 1) : v((size_t)rr * cc, 0.0), r(rr), c(cc) {}
+  template <typename O, int R2, int C2>
+  Matrix(const Base<O, R2, C2>& o) : v((size_t)R2 * C2), r(R2), c(C2)
+  {
+    for (int j = 0; j < C2; j++)
+      for (int i = 0; i < R2; i++) v[i + (size_t)j * r] = o.coeff(i, j);
+  }
+  template <typename O, int R2, int C2>
+  Matrix& operator=(const Base<O, R2, C2>& o)
+  {
+    Matrix<double, R2, C2> t(o);
+    resize(R2, C2);
+    for (int j = 0; j < C2; j++)
+      for (int i = 0; i < R2; i++) v[i + (size_t)j * r] = t.coeff(i, j);
+    return *this;
+  }
+  void resize(int rr, int cc = 1)
+  {
+    if (rr != r || cc != c)
+    {
+      v.assign((size_t)rr * cc, 0.0);
+      r = rr;
+      c = cc;
+    }
+  }
   void setZero() { std::fill(v.begin(), v.end(), 0.0); }
+  void setIdentity()
+  {
+    setZero();
+    for (int i = 0; i < (r < c ? r : c); i++) v[i + (size_t)i * r] = 1.0;
+  }
   int rows() const { return r; }
   int cols() const { return c; }
+  int size() const { return r * c; }
   double& operator()(int i, int j = 0) { return v[i + (size_t)j * r]; }
   double operator()(int i, int j = 0) const { return v[i + (size_t)j * r]; }
-  // fixed-size views into a dynamic matrix (factors.cpp: Hess.block<6, 6>(6 * i, 6 * j) += ...)
-  double coeff(int i, int j) const { return v[i + (size_t)j * r]; }
-  double& ref(int i, int j) { return v[i + (size_t)j * r]; }
+  double& operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double coeff(int i, int j = 0) const { return v[i + (size_t)j * r]; }
+  double& ref(int i, int j = 0) { return v[i + (size_t)j * r]; }
+  const double* data() const { return v.data(); }
+  double* data() { return v.data(); }
+  // fixed-size views (factors.cpp: Hess.block<6, 6>(6 * i, 6 * j) += ...)
   template <int BR, int BC>
   Block<Matrix, BR, BC> block(int r0, int c0)
   {
     return Block<Matrix, BR, BC>(*this, r0, c0);
   }
-  const double* data() const { return v.data(); }
+  template <int BR, int BC>
+  Matrix<double, BR, BC> block(int r0, int c0) const
+  {
+    Matrix<double, BR, BC> t;
+    for (int j = 0; j < BC; j++)
+      for (int i = 0; i < BR; i++) t.ref(i, j) = coeff(r0 + i, c0 + j);
+    return t;
+  }
+  DynView<Matrix> topRows(int n) { return DynView<Matrix>(*this, 0, 0, n, c); }
+  DynView<Matrix> leftCols(int n) { return DynView<Matrix>(*this, 0, 0, r, n); }
+  DynView<Matrix> head(int n) { return DynView<Matrix>(*this, 0, 0, n, 1); }
+  DynView<Matrix> tail(int n) { return DynView<Matrix>(*this, r - n, 0, n, 1); }
+  DynDiag<Matrix> diagonal() { return DynDiag<Matrix>(*this); }
+  Matrix& operator+=(const Matrix& o)
+  {
+    for (size_t i = 0; i < v.size(); i++) v[i] = v[i] + o.v[i];
+    return *this;
+  }
+  Matrix& operator*=(double s)
+  {
+    for (size_t i = 0; i < v.size(); i++) v[i] = v[i] * s;
+    return *this;
+  }
+  double dot(const Matrix& o) const
+  {
+    double s = v[0] * o.v[0];
+    for (size_t i = 1; i < v.size(); i++) s = s + v[i] * o.v[i];
+    return s;
+  }
+  inline DynLDLT ldlt() const;
 };
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<double, Dynamic, 1> VectorXd;
+
+// a fixed vector += a runtime tail / head of a dynamic one (optimizers.cpp: x.g += dxi.tail(3))
+template <int C, int R2>
+Matrix<double, R2, 1>& operator+=(Matrix<double, R2, 1>& a, const DynView<Matrix<double, Dynamic, C>>& o)
+{
+  for (int i = 0; i < R2; i++) a[i] = a[i] + o.coeff(i, 0);
+  return a;
+}
+template <int C>
+Matrix<double, Dynamic, C> operator+(const Matrix<double, Dynamic, C>& a, const Matrix<double, Dynamic, C>& b)
+{
+  Matrix<double, Dynamic, C> t(a.r, a.c);
+  for (size_t i = 0; i < t.v.size(); i++) t.v[i] = a.v[i] + b.v[i];
+  return t;
+}
+template <int C>
+Matrix<double, Dynamic, C> operator-(const Matrix<double, Dynamic, C>& a, const Matrix<double, Dynamic, C>& b)
+{
+  Matrix<double, Dynamic, C> t(a.r, a.c);
+  for (size_t i = 0; i < t.v.size(); i++) t.v[i] = a.v[i] - b.v[i];
+  return t;
+}
+template <int C>
+Matrix<double, Dynamic, C> operator-(const Matrix<double, Dynamic, C>& a)
+{
+  Matrix<double, Dynamic, C> t(a.r, a.c);
+  for (size_t i = 0; i < t.v.size(); i++) t.v[i] = -a.v[i];
+  return t;
+}
+template <int C>
+Matrix<double, Dynamic, C> operator*(double s, const Matrix<double, Dynamic, C>& a)
+{
+  Matrix<double, Dynamic, C> t(a.r, a.c);
+  for (size_t i = 0; i < t.v.size(); i++) t.v[i] = s * a.v[i];
+  return t;
+}
+template <int C>
+Matrix<double, Dynamic, C> operator*(const Matrix<double, Dynamic, C>& a, double s)
+{
+  Matrix<double, Dynamic, C> t(a.r, a.c);
+  for (size_t i = 0; i < t.v.size(); i++) t.v[i] = a.v[i] * s;
+  return t;
+}
+template <int C1, int C2>
+Matrix<double, Dynamic, C2> operator*(const Matrix<double, Dynamic, C1>& a, const Matrix<double, Dynamic, C2>& b)
+{
+  Matrix<double, Dynamic, C2> t(a.r, b.c);
+  for (int j = 0; j < b.c; j++)
+    for (int i = 0; i < a.r; i++)
+    {
+      double s = a.coeff(i, 0) * b.coeff(0, j);
+      for (int k = 1; k < a.c; k++) s = s + a.coeff(i, k) * b.coeff(k, j);
+      t.ref(i, j) = s;
+    }
+  return t;
+}
+
+// A.ldlt().solve(b): Eigen's LDLT (robust Cholesky with diagonal pivoting) restated as the textbook unblocked
+// algorithm on the lower triangle: pivot = largest |diagonal| of the trailing block, symmetric swap,
+// A21 <- (A21 - A20 (D .* A10^T)) / d_k. Eigen itself is absent: parity UNPINNED at this call;
+// oracle/omat.hpp holds the same routine so restatement and reference build agree with each other.
+struct DynLDLT
+{
+  int n = 0;
+  std::vector<double> L;  // column-major n x n, unit lower triangle below the diagonal, D on the diagonal
+  std::vector<int> perm;  // transpositions
+  explicit DynLDLT(const MatrixXd& A) : n(A.rows()), L(A.v), perm(A.rows())
+  {
+    auto a = [&](int i, int j) -> double& { return L[i + (size_t)j * n]; };
+    std::vector<double> temp(n);
+    for (int k = 0; k < n; k++)
+    {
+      int p = k;
+      double best = std::fabs(a(k, k));
+      for (int i = k + 1; i < n; i++)
+        if (std::fabs(a(i, i)) > best)
+        {
+          best = std::fabs(a(i, i));
+          p = i;
+        }
+      perm[k] = p;
+      if (p != k)
+      {
+        // symmetric swap of rows / columns k and p within the lower triangle
+        for (int j = 0; j < k; j++) std::swap(a(k, j), a(p, j));
+        for (int i = p + 1; i < n; i++) std::swap(a(i, k), a(i, p));
+        std::swap(a(k, k), a(p, p));
+        for (int i = k + 1; i < p; i++) std::swap(a(i, k), a(p, i));
+      }
+      if (k > 0)
+      {
+        for (int j = 0; j < k; j++) temp[j] = a(j, j) * a(k, j);
+        double s = a(k, k);
+        for (int j = 0; j < k; j++) s = s - a(k, j) * temp[j];
+        a(k, k) = s;
+        for (int i = k + 1; i < n; i++)
+        {
+          double t = a(i, k);
+          for (int j = 0; j < k; j++) t = t - a(i, j) * temp[j];
+          a(i, k) = t;
+        }
+      }
+      const double d = a(k, k);
+      if (std::fabs(d) > 0.0)
+        for (int i = k + 1; i < n; i++) a(i, k) = a(i, k) / d;
+    }
+  }
+  VectorXd solve(const VectorXd& b) const
+  {
+    auto a = [&](int i, int j) -> double { return L[i + (size_t)j * n]; };
+    VectorXd x = b;
+    for (int k = 0; k < n; k++)
+      if (perm[k] != k) std::swap(x[k], x[perm[k]]);
+    for (int i = 0; i < n; i++)
+    {
+      double s = x[i];
+      for (int j = 0; j < i; j++) s = s - a(i, j) * x[j];
+      x[i] = s;
+    }
+    for (int i = 0; i < n; i++)
+    {
+      const double d = a(i, i);
+      x[i] = std::fabs(d) > 2.2250738585072014e-308 ? x[i] / d : 0.0;
+    }
+    for (int i = n - 1; i >= 0; i--)
+    {
+      double s = x[i];
+      for (int j = i + 1; j < n; j++) s = s - a(j, i) * x[j];
+      x[i] = s;
+    }
+    for (int k = n - 1; k >= 0; k--)
+      if (perm[k] != k) std::swap(x[k], x[perm[k]]);
+    return x;
+  }
+};
+template <int C>
+inline DynLDLT Matrix<double, Dynamic, C>::ldlt() const
+{
+  return DynLDLT(*this);
+}
 
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;
@@ -298,8 +540,6 @@ typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, 2, 2> Matrix2d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 4, 4> Matrix4d;
-typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
-typedef Matrix<double, Dynamic, 1> VectorXd;
 
 // ---- views -------------------------------------------------------------------------------------------
 template <typename P, int BR, int BC>
@@ -349,6 +589,25 @@ struct Block : public Base<Block<P, BR, BC>, BR, BC>
   {
     for (int j = 0; j < BC; j++)
       for (int i = 0; i < BR; i++) ref(i, j) = 0.0;
+  }
+  void setIdentity()
+  {
+    for (int j = 0; j < BC; j++)
+      for (int i = 0; i < BR; i++) ref(i, j) = i == j ? 1.0 : 0.0;
+  }
+  template <int C2>
+  Block& operator+=(const Matrix<double, Dynamic, C2>& o)  // a dynamic matrix of the block's size
+  {
+    for (int j = 0; j < BC; j++)
+      for (int i = 0; i < BR; i++) ref(i, j) = ref(i, j) + o.coeff(i, j);
+    return *this;
+  }
+  template <typename Q>
+  Block& operator+=(const DynView<Q>& o)
+  {
+    for (int j = 0; j < BC; j++)
+      for (int i = 0; i < BR; i++) ref(i, j) = ref(i, j) + o.coeff(i, j);
+    return *this;
   }
   template <typename T, typename = typename std::enable_if<std::is_arithmetic<T>::value>::type>
   CommaInit<Block> operator<<(T v)

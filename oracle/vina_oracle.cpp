@@ -446,7 +446,7 @@ static void tras_opt_mark(OctoTree* n, int& counter)
 }
 
 // src/mapping/octree.cpp:498-521 with the container (the BA probe): same traversal, same acceptance test
-static void tras_opt_collect(OctoTree* n, LidarFactor& vox_opt)
+static void tras_opt_collect(OctoTree* n, LidarFactor& vox_opt, std::vector<OctoTree*>* nodes = nullptr)
 {
   if (n->octo_state == 0)
   {
@@ -457,12 +457,13 @@ static void tras_opt_collect(OctoTree* n, LidarFactor& vox_opt)
       std::vector<PointCluster> pcrs(n->wdsize);
       for (int i = 0; i < n->wdsize; i++) pcrs[i] = n->sw->pcrs_local[n->G->mp[i]];
       vox_opt.push_voxel(pcrs, n->pcr_fix, coe, n->eig_value, n->eig_vector, n->pcr_add);
+      if (nodes) nodes->push_back(n);
     }
   }
   else
   {
     for (int i = 0; i < 8; i++)
-      if (n->leaves[i] != nullptr) tras_opt_collect(n->leaves[i], vox_opt);
+      if (n->leaves[i] != nullptr) tras_opt_collect(n->leaves[i], vox_opt, nodes);
   }
 }
 
@@ -881,8 +882,15 @@ int IMUEKF::propagate(IMUST& xc, std::deque<ImuSample>& imus)
   xc.p = pos_imu + note * vel_imu * dt + note * 0.5 * acc_imu * dt * dt;
   xc.t = pcl_end_time;
 
+  // imu_ekf.cpp:95-104: the deque handed on to the pre-integration gets copies of its first / last sample
+  // re-stamped to the scan boundaries (integer nanoseconds, rclcpp::Time)
+  ImuSample imu1 = imus.front(), imu2 = imus.back();
+  imu1.t = (double)static_cast<int64_t>(last_pcl_end_time * 1e9) * 1e-9;
+  imu2.t = (double)static_cast<int64_t>(pcl_end_time * 1e9) * 1e-9;
   last_imu = imus.back();
   last_pcl_end_time = pcl_end_time;
+  imus.front() = imu1;
+  imus.back() = imu2;
   return 0;
 }
 
@@ -944,6 +952,7 @@ Odom::~Odom()
   }
   for (auto& v : sws)
     for (SlideWindow* s : v) delete s;
+  for (IMU_PRE* f : imu_pre_buf) delete f;
 }
 
 // src/pipeline/odometry.cpp:64-255 (use_vnc == false path; VNC terms are additive, :151-190)
@@ -1161,13 +1170,23 @@ void Odom::multi_margi(VoxelMap& feat_map, int win_count, std::vector<IMUST>& xs
   }
 }
 
-// src/pipeline/local_mapping.cpp:434-451 and 489-546 (if_BA == 0)
-void Odom::map_update(PVecPtr pptr)
+// src/pipeline/local_mapping.cpp:434-451 and 489-546
+void Odom::map_update(PVecPtr pptr, std::deque<ImuSample>* imus)
 {
   const int mgsize = 1;
   win_count++;
   x_buf.push_back(x_curr);
   pvec_buf.push_back(pptr);
+  if (win_count > 1)
+  {
+    IMU_PRE* f = nullptr;
+    if (imus)
+    {
+      f = new IMU_PRE(x_buf[win_count - 2].bg, x_buf[win_count - 2].ba);
+      f->push_imu(*imus, ba_noise);
+    }
+    imu_pre_buf.push_back(f);
+  }
 
   double t1 = now_s();
   cut_voxel_multi(&G, surf_map, pvec_buf[win_count - 1], win_count - 1, surf_map_slide, G.win_size, pwld, sws);
@@ -1189,6 +1208,26 @@ void Odom::map_update(PVecPtr pptr)
 
   if (win_count >= G.win_size)
   {
+    bool all_imu = (int)imu_pre_buf.size() == win_count - 1;
+    for (IMU_PRE* f : imu_pre_buf) all_imu = all_imu && f != nullptr;
+    if (if_BA && all_imu && (int)surf_map_slide.size() >= G.thread_num)
+    {
+      // local_mapping.cpp:492-497: LI_BA_Optimizer on the factors tras_opt collected in multi_recut
+      LidarFactor voxhess;
+      voxhess.win_size = G.win_size;
+      std::vector<OctoTree*> nodes;
+      for (auto iter = surf_map_slide.begin(); iter != surf_map_slide.end(); iter++)
+        tras_opt_collect(iter->second, voxhess, &nodes);
+      ba_last_iters = ba_damping_iter(x_buf, voxhess, imu_pre_buf, imu_coef, nullptr);
+      ba_runs++;
+      // OctoTree::margi takes the factors' (possibly re-evaluated) pcr_add / eig back (octree.cpp:410-416)
+      for (size_t a = 0; a < nodes.size(); a++)
+      {
+        nodes[a]->pcr_add = voxhess.pcr_adds[a];
+        nodes[a]->eig_value = voxhess.eig_values[a];
+        nodes[a]->eig_vector = voxhess.eig_vectors[a];
+      }
+    }
     x_curr.R = x_buf[win_count - 1].R;
     x_curr.p = x_buf[win_count - 1].p;
     double t5 = now_s();
@@ -1211,6 +1250,8 @@ void Odom::map_update(PVecPtr pptr)
     {
       x_buf.pop_back();
       pvec_buf.pop_back();
+      delete imu_pre_buf.front();
+      imu_pre_buf.pop_front();
     }
     win_base += mgsize;
     win_count -= mgsize;
@@ -1256,7 +1297,7 @@ int Odom::step(Cloud& pcl_curr, double pcl_beg_time, std::deque<ImuSample>& imus
   pvec_update(pptr, x_curr, pwld);
   t_odom = now_s() - t0;
 
-  map_update(pptr);
+  map_update(pptr, &imus);
   return 0;
 }
 

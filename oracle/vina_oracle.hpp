@@ -347,6 +347,31 @@ struct LidarFactor
   void evaluate_only_residual(const std::vector<IMUST>& xs, int head, int end, double& residual);  // factors.cpp:128-158
 };
 
+// src/estimation/imu_preintegration.cpp, include/vina_slam/preintegration.hpp: one IMU pre-integration factor
+// between two consecutive window frames (vina_oracle_ba.cpp)
+struct BaNoise  // the globals of imu_preintegration.cpp:3-5 (node.cpp:262-265, 309)
+{
+  Mat6 noiseMeas = Mat6::Zero(), noiseWalk = Mat6::Zero();
+  double scale_gravity = 1.0;
+};
+struct IMU_PRE
+{
+  Mat3 R_delta;
+  Vec3 p_delta, v_delta, bg, ba;
+  Mat3 R_bg, p_bg, p_ba, v_bg, v_ba;
+  double dtime;
+  Mat15 cov;
+  Vec3 dbg, dba, dbg_buf, dba_buf;
+  IMU_PRE(const Vec3& bg1, const Vec3& ba1);
+  void push_imu(std::deque<ImuSample>& imu_buffer, const BaNoise& nz);
+  void add_imu(Vec3& cur_gyr, Vec3& cur_acc, double dt, const BaNoise& nz);
+  double give_evaluate(IMUST& st1, IMUST& st2, Mat<30, 30>& jtj, Mat<30, 1>& gg, bool jac_enable);
+  void update_state(const Vec15& dxi);
+};
+// LI_BA_Optimizer::damping_iter (src/mapping/optimizers.cpp:430-517); returns the number of LM iterations
+int ba_damping_iter(std::vector<IMUST>& x_stats, LidarFactor& voxhess, std::deque<IMU_PRE*>& imus_factor, double imu_coef,
+                    std::vector<double>* hess_out);
+
 // The owner of everything VINA_SLAM keeps for the per-scan loop
 // (include/vina_slam/platform/ros2/node.hpp:30-96; src/pipeline/local_mapping.cpp:258-550)
 class Odom
@@ -377,6 +402,14 @@ public:
   bool ba_probe = false;
   LidarFactor ba_factors;
   std::vector<IMUST> ba_xs;
+  // sliding-window BA (local_mapping.cpp:437-441, 492-497, 541-546). The harness bootstraps the window without
+  // IMU data: those frames carry no pre-integration factor (nullptr) and BA only runs once every pair of
+  // consecutive window frames has one.
+  bool if_BA = false;
+  double imu_coef = 1e-4;
+  BaNoise ba_noise;
+  std::deque<IMU_PRE*> imu_pre_buf;
+  int ba_runs = 0, ba_last_iters = 0;
 
   explicit Odom(const Globals& g);
   ~Odom();
@@ -389,7 +422,7 @@ public:
   void multi_margi(VoxelMap& feat_map, int win_count, std::vector<IMUST>& xs,
                    std::vector<SlideWindow*>& sw);                                   // local_mapping.cpp:17-84
   // local_mapping.cpp:434-451 + 489-546: push frame, insert, recut, margi, window shift
-  void map_update(PVecPtr pptr);
+  void map_update(PVecPtr pptr, std::deque<ImuSample>* imus = nullptr);
   // local_mapping.cpp:389-546, one scan. iekf_on_full: feed the un-downsampled
   // scan to the IEKF (production, :413) or the down-sampled one (:412).
   int step(Cloud& pcl_curr, double pcl_beg_time, std::deque<ImuSample>& imus, bool iekf_on_full, int max_iter);

@@ -128,6 +128,32 @@ def run_ba(make_odom):
     return out
 
 
+def run_ba_odometry(make_odom, steps=14):
+    """The per-scan loop with if_BA: 1 (local_mapping.cpp:437-441, 492-497, 541-546): IMU pre-integration factors,
+    LI_BA_Optimizer::damping_iter (LM, 10 frames x 15 states), margi taking the re-evaluated factors back."""
+    cfg = synth.small_sensor("robosense128", 24, 350, seed=77)
+    seq = synth.Sequence(cfg)
+    od = make_odom(cfg)
+    od.set_ba(True)
+    for _ in range(cfg.win_size):
+        a = seq.next_scan(deskewed=True)
+        od.bootstrap(a.xyzt, op.make_state(a.gt_R, a.gt_p, a.gt_v, t=a.end_time))
+    od.set_imu_anchor(a.end_time, quantise_imu(a.imu)[-1])
+    traj = []
+    for k in range(steps):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, quantise_imu(sc.imu), True, 4)
+        assert r == 0
+        s = op.state_arrays(od.get_state())
+        traj.append(np.concatenate([s["p"], s["v"], s["R"].reshape(-1), s["cov"].reshape(-1)]))
+    out = {"ba_traj": np.array(traj), "ba_runs": np.array([od.ba_stats()[0]])}
+    m = sorted_map(od)
+    for f in ("key", "code", "octo_state", "is_plane", "N_add", "P_add", "v_add", "center", "normal"):
+        out["ba_end_" + f] = m[f]
+    od.close()
+    return out
+
+
 if __name__ == "__main__":
     assert op.build_ref(), "oracle/_ref needs /root/reference"
     here = os.path.dirname(os.path.abspath(__file__))
@@ -137,6 +163,7 @@ if __name__ == "__main__":
         np.savez_compressed(path, **o)
         print(path, os.path.getsize(path), "bytes")
     o = run_ba(lambda cfg: op.Odom(cfg, ref=True))
+    o.update(run_ba_odometry(lambda cfg: op.Odom(cfg, ref=True)))
     path = os.path.join(here, "ref_ba.npz")
     np.savez_compressed(path, **o)
     print(path, os.path.getsize(path), "bytes", "factors:", int(o["n_factors"][0]), "residuals:", o["residuals"])
