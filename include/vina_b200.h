@@ -336,6 +336,14 @@ int vina_get_timings(vina_ctx* ctx, vina_timings* t);
  *                            reference's container. lam0 (nullable, cap entries) receives lambda_0 per factor.
  * Sums over factors run in the store's order (arrival order of an atomic cursor): results agree with the
  * reference to rounding (tests: 1e-9 of the largest entry), the per-factor eigenvalues bit for bit. */
+/* The whole sliding-window BA inside vina_odom_step (LocalBA.if_BA: 1 of mid360.yaml / velodyne.yaml,
+ * local_mapping.cpp:437-441, 492-497, 541-546): IMU pre-integration factors (imu_preintegration.cpp) and the
+ * Levenberg-Marquardt loop of LI_BA_Optimizer::damping_iter (optimizers.cpp:430-517) on the host, the LiDAR factor on
+ * the device, OctoTree::margi taking the re-evaluated factors back. Call before the first frame enters the window;
+ * imu_coef <= 0 keeps LocalBA.imu_coef = 1e-4. BA runs once every pair of consecutive window frames has an IMU
+ * factor (frames from vina_odom_bootstrap have none). */
+int vina_odom_set_ba(vina_ctx* ctx, int on, double imu_coef);
+int vina_odom_ba_stats(vina_ctx* ctx, int32_t* runs, int32_t* last_iters);
 int vina_ba_set_capture(vina_ctx* ctx, int on);
 int vina_ba_collect(vina_ctx* ctx, int32_t* n_factors);
 int vina_ba_count(vina_ctx* ctx, int32_t* n_factors);

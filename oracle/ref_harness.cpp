@@ -187,7 +187,7 @@ struct RefOdom
     {
       bool all_imu = (int)imu_pre_buf.size() == vs.win_count - 1;
       for (IMU_PRE* f : imu_pre_buf) all_imu = all_imu && f != nullptr;
-      if (if_BA && all_imu && (int)vs.surf_map_slide.size() >= vs.thread_num)
+      if (if_BA && all_imu)
       {
         LI_BA_Optimizer opt_lsv;  // local_mapping.cpp:492-497
         Eigen::MatrixXd hess;

@@ -1210,14 +1210,16 @@ void Odom::map_update(PVecPtr pptr, std::deque<ImuSample>* imus)
   {
     bool all_imu = (int)imu_pre_buf.size() == win_count - 1;
     for (IMU_PRE* f : imu_pre_buf) all_imu = all_imu && f != nullptr;
-    if (if_BA && all_imu && (int)surf_map_slide.size() >= G.thread_num)
+    if (if_BA && all_imu)
     {
-      // local_mapping.cpp:492-497: LI_BA_Optimizer on the factors tras_opt collected in multi_recut
+      // local_mapping.cpp:492-497: LI_BA_Optimizer on the factors tras_opt collected in multi_recut (none when
+      // multi_recut took its early-out, local_mapping.cpp:150-154)
       LidarFactor voxhess;
       voxhess.win_size = G.win_size;
       std::vector<OctoTree*> nodes;
-      for (auto iter = surf_map_slide.begin(); iter != surf_map_slide.end(); iter++)
-        tras_opt_collect(iter->second, voxhess, &nodes);
+      if ((int)surf_map_slide.size() >= G.thread_num)
+        for (auto iter = surf_map_slide.begin(); iter != surf_map_slide.end(); iter++)
+          tras_opt_collect(iter->second, voxhess, &nodes);
       ba_last_iters = ba_damping_iter(x_buf, voxhess, imu_pre_buf, imu_coef, nullptr);
       ba_runs++;
       // OctoTree::margi takes the factors' (possibly re-evaluated) pcr_add / eig back (octree.cpp:410-416)

@@ -1014,6 +1014,54 @@ def test_ba_lidar_factor_matches_oracle(oracle_lib, gpu_lib):
     od.close()
 
 
+def test_ba_odometry_matches_oracle(oracle_lib, gpu_lib):
+    """The per-scan loop with LocalBA.if_BA: 1 (mid360.yaml / velodyne.yaml; local_mapping.cpp:437-441, 492-497,
+    541-546) through vina_odom_step: IMU pre-integration factors and the LM loop on the host, the LiDAR factor on the
+    device, margi taking the re-evaluated factors back - against the oracle, whose BA reproduces the reference's own
+    imu_preintegration.cpp / optimizers.cpp / factors.cpp bit for bit (tests/test_oracle_vs_ref.py). Same number of
+    BA runs and LM iterations, trajectory within the north-star's 1 mm / 0.01 deg at every scan, and BA visibly
+    changes the result (it is not a no-op)."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    g0 = gpu_lib.Ctx(cfg, **SMALL_CAPS)  # the same sequence without BA
+    od.set_ba(True)
+    gx.set_ba(True)
+    for _ in range(cfg.win_size):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        for g in (gx, g0):
+            g.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    od.set_imu_anchor(sc.end_time, sc.imu[-1])
+    for g in (gx, g0):
+        g.set_imu_anchor(sc.end_time, sc.imu[-1])
+    worst_p, worst_r, moved = 0.0, 0.0, 0.0
+    for k in range(14):
+        sc = seq.next_scan()
+        imu = sc.imu.copy()
+        imu[:, 0] = np.round(imu[:, 0] * 1e9) * 1e-9  # the reference keeps IMU stamps as integer nanoseconds
+        r, _ = od.step(sc.xyzt, sc.beg_time, imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, imu, iekf_on_full=True, max_iter=4))
+        s0 = gpu_lib.state_arrays(g0.step(sc.xyzt, sc.beg_time, imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        worst_p = max(worst_p, float(np.linalg.norm(sg["p"] - so["p"])))
+        worst_r = max(worst_r, synth.rot_err_deg(sg["R"], so["R"]))
+        moved = max(moved, float(np.linalg.norm(sg["p"] - s0["p"])))
+        assert np.linalg.norm(sg["p"] - sc.gt_p) < 0.02
+        assert gx.ba_stats() == od.ba_stats(), (k, gx.ba_stats(), od.ba_stats())
+    gx.sync()
+    assert od.ba_stats()[0] >= 5
+    assert worst_p < 1e-3 and worst_r < 0.01, (worst_p, worst_r)
+    assert moved > 1e-6, "BA changed nothing"
+    ng, no = gx.map_count(), od.map_count()
+    assert ng[0] == no[0] and ng[2] == no[2], (ng, no)
+    for g in (gx, g0):
+        g.close()
+    od.close()
+
+
 def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     """150 scans through the full per-scan path (the window slides 150 times, leaves saturate, point_fix lists
     are dropped and re-created, the slide map turns over): trajectory within 1 mm / 0.01 deg of the oracle at

@@ -30,8 +30,10 @@ UNITS = [
     (os.path.join(CSRC, "ba_kernels.cu"), []),
     (os.path.join(CSRC, "vn_ctx.cu"), []),
     (os.path.join(HOST, "vina_pipeline.cpp"), ["-x", "cu"]),
+    (os.path.join(HOST, "vina_ba.cpp"), ["-x", "cu"]),
 ]
 HEADERS = [os.path.join(CSRC, f) for f in ("vn_types.cuh", "vn_math.cuh", "vn_kernels.cuh", "vn_ctx.h")] + [
+    os.path.join(HOST, "vina_ba.h"),
     os.path.join(HERE, "..", "include", "vina_b200.h")]
 
 

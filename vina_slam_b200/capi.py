@@ -73,7 +73,7 @@ EXPORTS = [
     "vina_shard_p2p_create", "vina_shard_p2p_connect", "vina_shard_p2p_pointers", "vina_shard_p2p_connect_local",
     "vina_shard_route_p2p", "vina_shard_insert_begin_p2p", "vina_odom_iekf_sharded_p2p",
     "vina_set_overlap", "vina_ba_set_capture", "vina_ba_collect", "vina_ba_count", "vina_ba_lidar_hessian",
-    "vina_ba_lidar_residual",
+    "vina_ba_lidar_residual", "vina_odom_set_ba", "vina_odom_ba_stats",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -391,6 +391,14 @@ class Ctx:
     def odom_iekf_host_update(self, sums34) -> bool:
         a = np.ascontiguousarray(sums34, dtype=np.float64)
         return self._ck(self.lib.vina_odom_iekf_host_update(self.h, _dp(a))) == 1
+
+    def set_ba(self, on: bool = True, imu_coef: float = 0.0):
+        self._ck(self.lib.vina_odom_set_ba(self.h, C.c_int(1 if on else 0), C.c_double(imu_coef)))
+
+    def ba_stats(self):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.vina_odom_ba_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # ---- BA LiDAR factor (factors.cpp:22-158 on the device factor store)
     def ba_set_capture(self, on: bool = True):

@@ -342,6 +342,25 @@ __global__ void __launch_bounds__(128)
   if (threadIdx.x == 0) partial[blockIdx.x] = ((red[0] + red[1]) + red[2]) + red[3];
 }
 
+// OctoTree::margi takes the factors' re-evaluated pcr_add / eig back into the leaves (octree.cpp:410-416)
+__global__ void __launch_bounds__(128) k_ba_writeback(MapView M, const BaFactor* __restrict__ fac, const int* __restrict__ n_ptr)
+{
+  const int n = *n_ptr;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x)
+  {
+    const BaFactor& f = fac[a];
+    NodeCold& c = M.cold[f.node];
+    c.pcr_add = f.add;
+    for (int k = 0; k < 3; k++) c.eig_value[k] = f.eig_value[k];
+    for (int k = 0; k < 9; k++) c.eig_vector[k] = f.eig_vector[k];
+  }
+}
+int launch_ba_writeback(cudaStream_t st, const MapView& map, const BaFactor* fac, const int* n_dev, int sm_count)
+{
+  k_ba_writeback<<<sm_count * 2, 128, 0, st>>>(map, fac, n_dev);
+  return 1;
+}
+
 int ba_hess_warps(int sm_count) { return sm_count * 2 * BA_WARPS; }
 size_t ba_partial_doubles(int sm_count) { return (size_t)ba_hess_warps(sm_count) * BA_ENTRIES; }
 

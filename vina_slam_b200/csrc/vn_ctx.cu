@@ -1228,6 +1228,13 @@ int vn_ba_collect_enqueue(vina_ctx* ctx)
   return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_collect");
 }
 
+int vn_ba_writeback_enqueue(vina_ctx* ctx)
+{
+  if (!ctx->d_ba) return VINA_OK;
+  ctx->launches += launch_ba_writeback(ctx->stream, ctx->map, ctx->d_ba, ctx->d_ba_n, ctx->sm_count);
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_writeback");
+}
+
 extern "C" int vina_ba_set_capture(vina_ctx* ctx, int on)
 {
   if (!ctx) return VINA_E_ARG;

@@ -128,7 +128,8 @@ void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 // enqueue max_iter iterations of the IEKF against the sharded map, exchange and update on the device (vn_ctx.cu)
 int vn_shard_iekf_enqueue(vina_ctx* c, int first, int count, int max_iter, int part);
 int vn_mark_scan_read(vina_ctx* c);
-int vn_ba_collect_enqueue(vina_ctx* c);  // tras_opt into the factor store (after recut, before margi)
+int vn_ba_collect_enqueue(vina_ctx* c);
+int vn_ba_writeback_enqueue(vina_ctx* c);  // factor store -> leaves (octree.cpp:410-416), before margi  // tras_opt into the factor store (after recut, before margi)
 // map update with the newest pose read from the device iterate (vn_ctx.cu)
 int vn_map_insert_live(vina_ctx* c, int win_ord);
 int vn_map_recut_live(vina_ctx* c, int win_count, const vina_pose* x_buf);

@@ -154,6 +154,7 @@ int ba_hess_warps(int sm_count);
 size_t ba_partial_doubles(int sm_count);
 int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
                    double* partial, double* d_out);
+int launch_ba_writeback(cudaStream_t st, const MapView& map, const BaFactor* fac, const int* n_dev, int sm_count);
 int launch_ba_residual(cudaStream_t st, BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
                        double* partial, double* lam0);
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count);

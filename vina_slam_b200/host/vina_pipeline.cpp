@@ -12,6 +12,7 @@
 #include <vector>
 #include <chrono>
 #include "../csrc/vn_ctx.h"
+#include "vina_ba.h"
 
 int vn_finish_downsample(vina_ctx* ctx);
 int vn_iekf_launch(vina_ctx* ctx, const double R[9], const double p[3], bool debug);
@@ -105,6 +106,18 @@ struct OdomHost
   double hi_cov_inv[225];
   int hi_iter = 0, hi_max = 0, hi_rematch = 0;
   bool hi_active = false;
+  // sliding-window BA (local_mapping.cpp:437-441, 492-497, 541-546); vina_odom_set_ba
+  bool if_BA = false;
+  double imu_coef = 1e-4;               // LocalBA.imu_coef (node.cpp:247)
+  std::vector<vina_state> xs_buf;       // x_buf with the full states (v, bg, ba, g): what BA optimises
+  std::deque<ImuPre*> imu_pre_buf;      // imu_pre_buf; nullptr for frames that came without IMU data (bootstrap)
+  std::deque<vina_imu> ba_imus;         // the scan's IMU batch, ends re-stamped to the scan boundaries (imu_ekf.cpp:95-104)
+  bool ba_imus_valid = false;
+  int ba_runs = 0, ba_last_iters = 0;
+  ~OdomHost()
+  {
+    for (ImuPre* f : imu_pre_buf) ba_imu_factor_delete(f);
+  }
   OdomHost()
   {
     memset(&x_curr, 0, sizeof(x_curr));
@@ -229,6 +242,15 @@ static int imu_propagate(vina_ctx* ctx, OdomHost* o, const vina_imu* imus_in, in
   for (int k = 0; k < 3; k++)
     xc.p[k] = (pos_imu[k] + (note * vel_imu[k]) * dt) + (((note * 0.5) * acc_imu[k]) * dt) * dt;
   xc.t = o->pcl_end_time;
+  if (o->if_BA)
+  {
+    // imu_ekf.cpp:95-104: the batch handed to the pre-integration, first / last sample re-stamped to the scan
+    // boundaries (integer nanoseconds, rclcpp::Time)
+    o->ba_imus.assign(imus.begin(), imus.end());
+    o->ba_imus.front().t = (double)static_cast<int64_t>(o->last_pcl_end_time * 1e9) * 1e-9;
+    o->ba_imus.back().t = (double)static_cast<int64_t>(o->pcl_end_time * 1e9) * 1e-9;
+    o->ba_imus_valid = true;
+  }
   o->last_imu = imus.back();
   o->last_pcl_end_time = o->pcl_end_time;
   return VINA_OK;
@@ -455,7 +477,7 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
   return VINA_OK;
 }
 
-// local_mapping.cpp:425-451 and 489-546 with if_BA == 0
+// local_mapping.cpp:425-451 and 489-546
 static int map_update(vina_ctx* ctx, OdomHost* o)
 {
   vina_state& x = o->x_curr;
@@ -471,6 +493,18 @@ static int map_update(vina_ctx* ctx, OdomHost* o)
   memcpy(ps.R, x.R, 72);
   memcpy(ps.p, x.p, 24);
   o->x_buf.push_back(ps);
+  if (o->if_BA)
+  {
+    o->xs_buf.push_back(x);
+    if (o->win_count > 1)
+    {
+      // imu_pre_buf.push_back(new IMU_PRE(x_buf[win_count - 2].bg, .ba)); ->push_imu(imus) (local_mapping.cpp:437-441)
+      const vina_state& prev = o->xs_buf[o->win_count - 2];
+      o->imu_pre_buf.push_back(o->ba_imus_valid ? ba_imu_factor_new(prev.bg, prev.ba, o->ba_imus, o->scale_gravity, ctx->cfg)
+                                                 : nullptr);
+    }
+    o->ba_imus_valid = false;
+  }
   cudaEvent_t* ev = ctx->ev;
   if (ctx->profiling) cudaEventRecord(ev[4], ctx->stream);
   int r = vina_map_insert(ctx, o->win_count - 1, x.R, x.p, rot_var, tsl_var);  // pvec_update + cut_voxel_multi
@@ -478,20 +512,46 @@ static int map_update(vina_ctx* ctx, OdomHost* o)
   if (ctx->profiling) cudaEventRecord(ev[5], ctx->stream);
   r = vina_map_recut(ctx, o->win_count, o->x_buf.data());
   if (r) return r;
-  if (ctx->ba_capture && o->win_count >= ctx->cfg.win_size)
+  const bool full = o->win_count >= ctx->cfg.win_size;
+  bool run_ba = o->if_BA && full && (int)o->imu_pre_buf.size() == o->win_count - 1;
+  if (run_ba)
+    for (ImuPre* f : o->imu_pre_buf) run_ba = run_ba && f != nullptr;
+  if (full && (ctx->ba_capture || run_ba))
   {
-    r = vn_ba_collect_enqueue(ctx);  // the factors damping_iter would consume (local_mapping.cpp:492-497)
+    r = vn_ba_collect_enqueue(ctx);  // tras_opt: the factors damping_iter consumes (local_mapping.cpp:196-200)
     if (r) return r;
   }
   if (ctx->profiling) cudaEventRecord(ev[6], ctx->stream);
-  if (o->win_count >= ctx->cfg.win_size)
+  if (run_ba)
   {
-    // x_curr.R/p = x_buf.back() is the identity without BA (local_mapping.cpp:501-502)
+    // LI_BA_Optimizer::damping_iter (local_mapping.cpp:492-497): LM on the host around the device LiDAR factor
+    r = ba_damping_iter(ctx, o->xs_buf, o->imu_pre_buf, o->imu_coef, &o->ba_last_iters);
+    if (r) return r;
+    o->ba_runs++;
+    for (int i = 0; i < o->win_count; i++)
+    {
+      memcpy(o->x_buf[i].R, o->xs_buf[i].R, 72);
+      memcpy(o->x_buf[i].p, o->xs_buf[i].p, 24);
+    }
+    r = vn_ba_writeback_enqueue(ctx);  // margi takes the re-evaluated pcr_add / eig back (octree.cpp:410-416)
+    if (r) return r;
+  }
+  if (full)
+  {
+    // x_curr.R/p = x_buf.back() (local_mapping.cpp:501-502): the identity without BA
+    memcpy(x.R, o->x_buf.back().R, 72);
+    memcpy(x.p, o->x_buf.back().p, 24);
     r = vina_map_margi(ctx, o->win_count, o->x_buf.data());
     if (r) return r;
     r = vina_map_shift_window(ctx);
     if (r) return r;
     o->x_buf.erase(o->x_buf.begin());
+    if (o->if_BA)
+    {
+      o->xs_buf.erase(o->xs_buf.begin());
+      ba_imu_factor_delete(o->imu_pre_buf.front());
+      o->imu_pre_buf.pop_front();
+    }
     o->win_base += 1;
     o->win_count -= 1;
   }
@@ -691,7 +751,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
 static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
                               const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
 {
-  if (ctx->overlap && !ctx->profiling && iekf_on_full && ctx->side_stream)
+  if (ctx->overlap && !ctx->profiling && iekf_on_full && ctx->side_stream && !o->if_BA)
     return odom_step_overlapped(ctx, o, pcl_beg_time, pcl_end_time, imus, m, max_iter, x_out);
   const int l0 = ctx->launches;
   int which = 1, ok = 0;
@@ -1048,6 +1108,27 @@ int vina_odom_iekf_sharded_p2p(vina_ctx* ctx, int first, int count, int max_iter
     if (not_degenerate) *not_degenerate = ok;
     return vn_check_status(ctx);
   }
+  return VINA_OK;
+}
+
+// LocalBA.if_BA / LocalBA.imu_coef (node.cpp:96, 247). Set before the first frame enters the window. With BA on,
+// vina_odom_step runs LI_BA_Optimizer::damping_iter between recut and margi (local_mapping.cpp:492-497) once every
+// pair of consecutive window frames has an IMU pre-integration factor (frames inserted by vina_odom_bootstrap /
+// vina_odom_map_update have none); the step then uses the serial schedule (the LM loop needs the host).
+int vina_odom_set_ba(vina_ctx* ctx, int on, double imu_coef)
+{
+  if (!ctx) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  if (o->win_count > 0 && (on != 0) != o->if_BA) return vn_fail(ctx, VINA_E_STATE, "vina_odom_set_ba after frames entered the window");
+  o->if_BA = on != 0;
+  if (imu_coef > 0) o->imu_coef = imu_coef;
+  return VINA_OK;
+}
+int vina_odom_ba_stats(vina_ctx* ctx, int32_t* runs, int32_t* last_iters)
+{
+  if (!ctx || !runs || !last_iters) return VINA_E_ARG;
+  *runs = odom(ctx)->ba_runs;
+  *last_iters = odom(ctx)->ba_last_iters;
   return VINA_OK;
 }
 
