@@ -95,7 +95,10 @@ def gen_sequence(cfg, seed, n_boot, n_steps):
 
 
 # --------------------------------------------------------------------------- reference arm / cpu baseline
-def run_cpu(cfg, boots, scans, warmup, steps, ref=False):
+BA_WARMUP = 9  # scans until every pair of consecutive window frames carries an IMU factor: BA runs from then on
+
+
+def run_cpu(cfg, boots, scans, warmup, steps, ref=False, ba=False):
     """The reference's CPU implementation of the path with its own release flags (-O3 -ffast-math,
     CMakeLists.txt:92-96), IEKF single-threaded, insert/recut/margi on thread_num = 5 std::threads, exactly as the
     reference does. ref=False: the oracle port (kind "port") - bit-identical results to the reference build
@@ -108,6 +111,8 @@ def run_cpu(cfg, boots, scans, warmup, steps, ref=False):
     op.build()
     use_ref = ref and op.have_ref() and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libvina_ref_fast.so"))
     od = op.Odom(cfg, fast=True, ref=use_ref)
+    if ba:
+        od.set_ba(True)
     for sc in boots:
         od.bootstrap(sc.xyzt, op.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
     od.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
@@ -131,13 +136,15 @@ def main_reference(args, cfg):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    if args.ba:
+        args.warmup = max(args.warmup, BA_WARMUP)
     boots, scans = gen_sequence(cfg, cfg.seed, cfg.win_size, args.warmup + args.steps)
-    r = run_cpu(cfg, boots, scans, args.warmup, args.steps)
+    r = run_cpu(cfg, boots, scans, args.warmup, args.steps, ba=args.ba)
     sample = (f"{r['steps']} full scans of {cfg.n_points} pts after {args.warmup} warm-up scans; IEKF 1 thread, "
               f"map ops {cfg.thread_num} threads (reference threading)")
     ref_build = None
     try:  # informational: the reference's own sources (header-shim build), a few scans
-        rr = run_cpu(cfg, boots, scans, min(args.warmup, 1), min(args.steps, 3), ref=True)
+        rr = run_cpu(cfg, boots, scans, args.warmup if args.ba else min(args.warmup, 1), min(args.steps, 3), ref=True, ba=args.ba)
         if rr["kind"] == "reference":
             ref_build = {"value": rr["value"], "unit": UNIT, "ms_per_step": rr["ms_per_step"], "steps": rr["steps"],
                          "note": "reference sources compiled against oracle/ref_shim (eager Eigen stand-in, incl. the "
@@ -149,7 +156,7 @@ def main_reference(args, cfg):
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "max_iter": MAX_ITER, "iekf_on": "full scan", "vnc_terms": False,
-                   "if_BA": 0},
+                   "if_BA": int(args.ba)},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
                          "stage_ms": dict(zip(["odom", "insert", "recut", "margi"], r["stage_ms"]))},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -181,6 +188,9 @@ def main_ours(args, cfg):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    if args.ba:
+        args.warmup = max(args.warmup, BA_WARMUP)
+        args.batch = 0
     W, K = args.warmup, args.steps
     from vina_slam_b200 import replicas as _rep
 
@@ -201,6 +211,8 @@ def main_ours(args, cfg):
     def new_ctx():
         gx = capi.Ctx(cfg, **caps)
         gx.set_stream(stream.cuda_stream)
+        if args.ba:
+            gx.set_ba(True)
         for sc in boots:
             gx.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
         gx.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
@@ -245,6 +257,7 @@ def main_ours(args, cfg):
             t_res = float(step_ms.sum()) * 1e-3
             launches = int(sum(t.kernel_launches for t in tm_rows))
             traj_err = traj
+            ba_runs, ba_iters = (gx.ba_stats()[0] - (W - BA_WARMUP + 1), gx.ba_stats()[1]) if args.ba else (0, 0)
             gx.close()
     pts = sum(sc.xyzt.shape[0] for sc in scans[W:])
     iters = int(sum(t.iekf_iters for t in tm_rows))
@@ -366,7 +379,7 @@ def main_ours(args, cfg):
         cpu = None
         if world == 1 and not args.no_cpu:
             n_cpu = min(K, 8)
-            r = run_cpu(cfg, boots, scans, min(W, 2), n_cpu)
+            r = run_cpu(cfg, boots, scans, W if args.ba else min(W, 2), n_cpu, ba=args.ba)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                    "sample": f"{r['steps']} full scans of the same workload ({cfg.n_points} pts each); IEKF 1 thread, "
                              f"map ops {cfg.thread_num} threads",
@@ -377,11 +390,15 @@ def main_ours(args, cfg):
             "ms_per_step": 1e3 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg), "max_iter": MAX_ITER, "iekf_on": "full scan",
-                       "vnc_terms": False, "if_BA": 0, "parallelism": f"replicas x{world}",
+                       "vnc_terms": False, "if_BA": int(args.ba), "parallelism": f"replicas x{world}",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); steps timed individually "
                              "with CUDA events on the launching stream and summed; stage_ms / roofline launch times "
                              "come from a second, instrumented pass over the same scans",
-                       "iekf_iters_per_step": iters_per_step, "gt_traj_err_m": traj_err},
+                       "iekf_iters_per_step": iters_per_step, "gt_traj_err_m": traj_err,
+                       **({"ba": {"runs_in_timed_steps": ba_runs, "lm_iters_last": ba_iters,
+                                  "note": "LI_BA_Optimizer every scan: IMU factors + LM on the host, LiDAR factor "
+                                          "(Hessian / residual over the plane voxels of the window) on the device"}}
+                          if args.ba else {})},
             "e2e": {"value": pts_all / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K,
                     "h2d_bytes_per_step": int(16 * n_mean + 17096),
                     "d2h_bytes_per_step": int(iters_e2e / K * 34 * 8 + 4)},
@@ -633,6 +650,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="robosense128", choices=sorted(synth.SENSORS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ba", action="store_true", help="LocalBA.if_BA: 1 (mid360.yaml / velodyne.yaml): sliding-window BA every scan")
     ap.add_argument("--batch", type=int, default=8, help="concurrent sequences per GPU in the batch-replay leg (0/1 = off)")
     ap.add_argument("--voxels", type=float, default=1e7, help="bigmap: root voxels to pre-fill")
     ap.add_argument("--mode", default="odometry", choices=["odometry", "sharded-map", "bigmap"],

@@ -268,29 +268,40 @@ __global__ void __launch_bounds__(BA_THREADS)
   if (lane == 0) out[36 * BA_NPAIR + 6 * VINA_MAX_WIN] = resid;
 }
 
-// sum of the warps' partials in warp order; Hess (6 win)^2 column-major with the lower blocks mirrored
-// (factors.cpp:123-125), JacT, residual
+// sum of the warps' partials; Hess (6 win)^2 column-major with the lower blocks mirrored (factors.cpp:123-125),
+// JacT, residual. A block owns 32 consecutive entries; its 8 warps each add a fixed, interleaved subset of the
+// partial rows (coalesced 256-byte loads), then the 8 slice sums are added in slice order: fixed order, so the
+// same bits for the same factor order.
 __global__ void __launch_bounds__(256)
     k_ba_reduce(const double* __restrict__ partial, int nwarps, int win, double* __restrict__ Hess, double* __restrict__ JacT,
                 double* __restrict__ residual)
 {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= BA_ENTRIES) return;
+  __shared__ double part[8][33];
+  const int el = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + el;
   const int npair = win * (win + 1) / 2;
   const int dim = 6 * win;
   double s = 0.0;
-  bool used = false;
-  if (e < 36 * BA_NPAIR)
-    used = e / 36 < npair;
-  else if (e < 36 * BA_NPAIR + 6 * VINA_MAX_WIN)
-    used = (e - 36 * BA_NPAIR) / 6 < win;
-  else
-    used = true;
-  if (!used) return;
-  for (int w = 0; w < nwarps; w++) s += partial[(size_t)w * BA_ENTRIES + e];
+  if (e < BA_ENTRIES)
+  {
+    double s0 = 0.0, s1 = 0.0;
+    int w = slice;
+    for (; w + 8 < nwarps; w += 16)
+    {
+      s0 += partial[(size_t)w * BA_ENTRIES + e];
+      s1 += partial[(size_t)(w + 8) * BA_ENTRIES + e];
+    }
+    if (w < nwarps) s0 += partial[(size_t)w * BA_ENTRIES + e];
+    s = s0 + s1;
+  }
+  part[slice][el] = s;
+  __syncthreads();
+  if (slice != 0 || e >= BA_ENTRIES) return;
+  s = ((part[0][el] + part[1][el]) + (part[2][el] + part[3][el])) + ((part[4][el] + part[5][el]) + (part[6][el] + part[7][el]));
   if (e < 36 * BA_NPAIR)
   {
     int q = e / 36, i = 0;
+    if (q >= npair) return;
     const int r = (e % 36) % 6, c = (e % 36) / 6;
     while (q >= win - i)
     {
@@ -302,7 +313,9 @@ __global__ void __launch_bounds__(256)
     if (i != j) Hess[(6 * j + c) + (size_t)dim * (6 * i + r)] = s;
   }
   else if (e < 36 * BA_NPAIR + 6 * VINA_MAX_WIN)
-    JacT[e - 36 * BA_NPAIR] = s;
+  {
+    if ((e - 36 * BA_NPAIR) / 6 < win) JacT[e - 36 * BA_NPAIR] = s;
+  }
   else
     *residual = s;
 }
@@ -361,7 +374,7 @@ int launch_ba_writeback(cudaStream_t st, const MapView& map, const BaFactor* fac
   return 1;
 }
 
-int ba_hess_warps(int sm_count) { return sm_count * 2 * BA_WARPS; }
+int ba_hess_warps(int sm_count) { return sm_count * BA_WARPS; }
 size_t ba_partial_doubles(int sm_count) { return (size_t)ba_hess_warps(sm_count) * BA_ENTRIES; }
 
 int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
@@ -370,11 +383,11 @@ int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const
   BaPoses xs;
   memset(&xs, 0, sizeof(xs));
   for (int i = 0; i < win && i < VINA_MAX_WIN; i++) xs.x[i] = h_xs[i];
-  const int blocks = sm_count * 2;
+  const int blocks = sm_count;
   k_ba_hess<<<blocks, BA_THREADS, 0, st>>>(fac, n_dev, xs, win, partial);
   const int dim = 6 * win;
-  k_ba_reduce<<<(BA_ENTRIES + 255) / 256, 256, 0, st>>>(partial, blocks * BA_WARPS, win, d_out, d_out + (size_t)dim * dim,
-                                                        d_out + (size_t)dim * dim + dim);
+  k_ba_reduce<<<(BA_ENTRIES + 31) / 32, 256, 0, st>>>(partial, blocks * BA_WARPS, win, d_out, d_out + (size_t)dim * dim,
+                                                      d_out + (size_t)dim * dim + dim);
   return 2;
 }
 

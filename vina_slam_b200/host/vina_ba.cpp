@@ -8,7 +8,9 @@
 // csrc/ba_kernels.cu through vina_ba_lidar_hessian / vina_ba_lidar_residual.
 // Third-party arithmetic (Eigen is not a dependency here): Matrix<15,15>::inverse() = LU with partial pivoting,
 // LDLT::solve = LDL^T with diagonal pivoting, AngleAxisd(Matrix3d) = trace / antisymmetric-part formula.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <vector>
@@ -237,12 +239,14 @@ M15 inverse15(const M15& A)
   }
   return inv;
 }
-// x = A^-1 b for the symmetric (damped) normal matrix: LDL^T with diagonal pivoting on the lower triangle
+// x = A^-1 b for the symmetric (damped) normal matrix: LDL^T with diagonal pivoting on the lower triangle,
+// right-looking (every elimination step updates the trailing columns with unit-stride inner loops, which the
+// host compiler vectorises: the 150 x 150 system of a 10-frame window costs tens of microseconds)
 std::vector<double> ldlt_solve(std::vector<double> L, int n, const std::vector<double>& b)
 {
   auto a = [&](int i, int j) -> double& { return L[i + (size_t)j * n]; };
   std::vector<int> perm(n);
-  std::vector<double> temp(n);
+  std::vector<double> col(n);
   for (int k = 0; k < n; k++)
   {
     int p = k;
@@ -257,41 +261,39 @@ std::vector<double> ldlt_solve(std::vector<double> L, int n, const std::vector<d
       std::swap(a(k, k), a(p, p));
       for (int i = k + 1; i < p; i++) std::swap(a(i, k), a(p, i));
     }
-    if (k > 0)
-    {
-      for (int j = 0; j < k; j++) temp[j] = a(j, j) * a(k, j);
-      double s = a(k, k);
-      for (int j = 0; j < k; j++) s = s - a(k, j) * temp[j];
-      a(k, k) = s;
-      for (int i = k + 1; i < n; i++)
-      {
-        double t = a(i, k);
-        for (int j = 0; j < k; j++) t = t - a(i, j) * temp[j];
-        a(i, k) = t;
-      }
-    }
     const double d = a(k, k);
     if (std::fabs(d) > 0.0)
-      for (int i = k + 1; i < n; i++) a(i, k) = a(i, k) / d;
+    {
+      double* ck = &L[(size_t)k * n];
+      for (int i = k + 1; i < n; i++) col[i] = ck[i];          // d * l_i
+      for (int i = k + 1; i < n; i++) ck[i] = ck[i] / d;       // l_i
+      for (int j = k + 1; j < n; j++)
+      {
+        const double f = col[j];  // d * l_j
+        double* cj = &L[(size_t)j * n];
+        for (int i = j; i < n; i++) cj[i] -= ck[i] * f;
+      }
+    }
   }
   std::vector<double> x = b;
   for (int k = 0; k < n; k++)
     if (perm[k] != k) std::swap(x[k], x[perm[k]]);
-  for (int i = 0; i < n; i++)
+  for (int j = 0; j < n; j++)  // L y = b, column oriented
   {
-    double s = x[i];
-    for (int j = 0; j < i; j++) s = s - a(i, j) * x[j];
-    x[i] = s;
+    const double xj = x[j];
+    const double* cj = &L[(size_t)j * n];
+    for (int i = j + 1; i < n; i++) x[i] -= cj[i] * xj;
   }
   for (int i = 0; i < n; i++)
   {
     const double d = a(i, i);
     x[i] = std::fabs(d) > 2.2250738585072014e-308 ? x[i] / d : 0.0;
   }
-  for (int i = n - 1; i >= 0; i--)
+  for (int i = n - 1; i >= 0; i--)  // L^T x = y
   {
     double s = x[i];
-    for (int j = i + 1; j < n; j++) s = s - a(j, i) * x[j];
+    const double* ci = &L[(size_t)i * n];
+    for (int j = i + 1; j < n; j++) s -= ci[j] * x[j];
     x[i] = s;
   }
   for (int k = n - 1; k >= 0; k--)
@@ -306,7 +308,7 @@ struct ImuPre
   M3 R_delta, R_bg, p_bg, p_ba, v_bg, v_ba;
   V3 p_delta, v_delta, bg, ba, dbg, dba, dbg_buf, dba_buf;
   double dtime = 0;
-  M15 cov;
+  M15 cov, cov_inv;  // cov_inv: the covariance does not change once the batch is integrated
   ImuPre(const double* bg1, const double* ba1)
   {
     bg = v3(bg1), ba = v3(ba1);
@@ -369,6 +371,7 @@ struct ImuPre
       c = c * scale_gravity - ba;
       add_imu(g, c, dt, cfg);
     }
+    cov_inv = inverse15(cov);
   }
   // imu_preintegration.cpp:102-163; jtj 30x30 column-major, gg 30
   double evaluate(const vina_state& s1, const vina_state& s2, HM<30, 30>* jtj, HM<30, 1>* gg) const
@@ -389,7 +392,6 @@ struct ImuPre
     rr.set<3, 1>(6, 0, res_v);
     rr.set<3, 1>(9, 0, v3(s2.bg) - v3(s1.bg));
     rr.set<3, 1>(12, 0, v3(s2.ba) - v3(s1.ba));
-    M15 cov_inv = inverse15(cov);
     if (jtj && gg)
     {
       M15 joca = M15::zero(), jocb = M15::zero();
@@ -469,6 +471,13 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
   bool is_calc_hess = true;
   std::vector<vina_state> xt = xs;
   int iters = 0;
+  // VINA_TRACE: where a BA run spends its time (host IMU factors / device LiDAR factor / solve)
+  static double tr_us[5] = { 0, 0, 0, 0, 0 };
+  static int tr_calls = 0;
+  auto now_us = []() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  double t0 = 0;
   for (int it = 0; it < 10; it++)
   {
     iters++;
@@ -480,6 +489,7 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
       double residual = 0;
       HM<30, 30> jtj;
       HM<30, 1> gg;
+      t0 = now_us();
       for (int i = 0; i < win - 1; i++)
       {
         residual += imus_factor[i]->evaluate(xs[i], xs[i + 1], &jtj, &gg);
@@ -490,10 +500,13 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
       for (double& h : Hess) h *= imu_coef;
       for (double& j : JacT) j *= imu_coef;
       residual *= (imu_coef * 0.5);
+      tr_us[0] += now_us() - t0;
       set_poses(xs);
       double rl = 0;
+      t0 = now_us();
       int r = vina_ba_lidar_hessian(ctx, poses.data(), win, hl.data(), jl.data(), &rl);
       if (r) return r;
+      tr_us[1] += now_us() - t0;
       for (int a = 0; a < win; a++)  // hess_plus (optimizers.cpp:171-179)
       {
         for (int k = 0; k < DVEL; k++) JacT[a * DIM + k] += jl[a * DVEL + k];
@@ -510,10 +523,21 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
     for (int c = 0; c < DIM; c++) H(c, c) = 1.0;
     for (int r = 0; r < DIM; r++) JacT[r] = 0.0;
     for (int k = 0; k < n; k++) D[k + (size_t)n * k] = H(k, k);
-    std::vector<double> A((size_t)n * n), nb(n);
-    for (size_t k = 0; k < A.size(); k++) A[k] = Hess[k] + u * D[k];
-    for (int k = 0; k < n; k++) nb[k] = -JacT[k];
-    dxi = ldlt_solve(A, n, nb);
+    t0 = now_us();
+    {
+      // dxi = (Hess + u D).ldlt().solve(-JacT). The first frame is fixed: its rows / columns are the identity
+      // and its gradient is zero, so dxi(0:15) = 0 and the remaining (n - 15)^2 block is solved on its own.
+      const int m = n - DIM;
+      std::vector<double> A((size_t)m * m), nb(m);
+      for (int c = 0; c < m; c++)
+        for (int r = 0; r < m; r++)
+          A[r + (size_t)m * c] = Hess[(DIM + r) + (size_t)n * (DIM + c)] + u * D[(DIM + r) + (size_t)n * (DIM + c)];
+      for (int k = 0; k < m; k++) nb[k] = -JacT[DIM + k];
+      std::vector<double> sol = ldlt_solve(A, m, nb);
+      for (int k = 0; k < DIM; k++) dxi[k] = 0.0;
+      for (int k = 0; k < m; k++) dxi[DIM + k] = sol[k];
+    }
+    tr_us[2] += now_us() - t0;
     for (int j = 0; j < win; j++)
     {
       V3 d0;
@@ -539,12 +563,16 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
     // only_residual (optimizers.cpp:340-376)
     {
       double r1 = 0;
+      t0 = now_us();
       for (int i = 0; i < win - 1; i++) r1 += imus_factor[i]->evaluate(xt[i], xt[i + 1], nullptr, nullptr);
       r1 *= (imu_coef * 0.5);
+      tr_us[3] += now_us() - t0;
       set_poses(xt);
       double rl = 0;
+      t0 = now_us();
       int r = vina_ba_lidar_residual(ctx, poses.data(), win, &rl, nullptr, 0);
       if (r) return r;
+      tr_us[4] += now_us() - t0;
       residual2 = r1 + rl;
     }
     q = residual1 - residual2;
@@ -572,5 +600,9 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
     if (std::fabs((residual1 - residual2) / residual1) < 1e-6) break;
   }
   if (iters_out) *iters_out = iters;
+  if (ctx->trace && (++tr_calls % 10) == 0)
+    fprintf(stderr, "[vina trace] BA, us per run over %d runs: imu jac %.1f, lidar hess (device) %.1f, solve %.1f, imu res %.1f, "
+                    "lidar res (device) %.1f\n", tr_calls, tr_us[0] / tr_calls, tr_us[1] / tr_calls, tr_us[2] / tr_calls,
+            tr_us[3] / tr_calls, tr_us[4] / tr_calls);
   return VINA_OK;
 }
