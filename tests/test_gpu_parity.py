@@ -1062,6 +1062,62 @@ def test_ba_odometry_matches_oracle(oracle_lib, gpu_lib):
     od.close()
 
 
+def test_ba_and_fused_loop_entry_points_edges(oracle_lib, gpu_lib):
+    """Error behaviour of the newer entry points: codes, never exit() / exceptions across the ABI; a BA over an empty
+    factor store (multi_recut's early-out leaves voxhess empty) gives zero Hessian / gradient / residual."""
+    import ctypes as C
+
+    cfg = small_cfg()
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    lib, dp = gx.lib, gpu_lib._dp
+    w = cfg.win_size
+    poses = np.zeros((w, 12))
+    poses[:, 0] = poses[:, 4] = poses[:, 8] = 1.0
+    H, J, r, n = np.zeros(36 * w * w), np.zeros(6 * w), C.c_double(0), C.c_int32(0)
+    vp = poses.ctypes.data_as(C.c_void_p)
+    # nothing collected yet
+    assert lib.vina_ba_lidar_hessian(gx.h, vp, C.c_int(w), dp(H), dp(J), C.byref(r)) == -6
+    assert lib.vina_ba_lidar_residual(gx.h, vp, C.c_int(w), C.byref(r), None, C.c_int(0)) == -6
+    assert lib.vina_ba_count(gx.h, C.byref(n)) == -6
+    assert b"no BA factors" in lib.vina_last_error(gx.h)
+    # bad arguments
+    assert lib.vina_ba_lidar_hessian(gx.h, None, C.c_int(w), dp(H), dp(J), C.byref(r)) == -1
+    assert lib.vina_ba_lidar_hessian(gx.h, vp, C.c_int(11), dp(H), dp(J), C.byref(r)) == -1
+    assert lib.vina_ba_collect(None, C.byref(n)) == -1
+    assert lib.vina_odom_set_ba(None, C.c_int(1), C.c_double(0)) == -1
+    assert lib.vina_set_overlap(None, C.c_int(1)) == -1
+    # an empty map: collect finds nothing, the evaluations are all zero
+    assert gx.ba_collect() == 0
+    Hh, Jj, rr = gx.ba_hess(poses)
+    assert not Hh.any() and not Jj.any() and rr == 0.0
+    rr, lam = gx.ba_residual(poses)
+    assert rr == 0.0 and lam.shape == (0,)
+    assert lib.vina_ba_lidar_hessian(gx.h, vp, C.c_int(w - 1), dp(H), dp(J), C.byref(r)) == -1  # win != LocalBA.win_size
+    # if_BA can only be chosen before frames enter the window
+    seq = synth.Sequence(cfg)
+    sc = seq.next_scan(deskewed=True)
+    gx.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    assert lib.vina_odom_set_ba(gx.h, C.c_int(1), C.c_double(0)) == -6
+    assert lib.vina_odom_set_ba(gx.h, C.c_int(0), C.c_double(1e-3)) == 0  # unchanged mode: fine
+    assert gx.ba_stats() == (0, 0)
+    # the fused sharded IEKF needs connected peers and a valid slice
+    it, ok = C.c_int(0), C.c_int(0)
+    assert lib.vina_odom_iekf_sharded_p2p(gx.h, C.c_int(0), C.c_int(10), C.c_int(4), C.c_int(0), C.byref(it), C.byref(ok)) == -6
+    assert lib.vina_odom_iekf_sharded_p2p(gx.h, C.c_int(0), C.c_int(10), C.c_int(4), C.c_int(7), C.byref(it), C.byref(ok)) == -1
+    gx.shard_p2p_create(0, 1, SMALL_CAPS["max_scan_points"])  # a world of one is connected to itself
+    gx.scan_upload(sc.xyzt)
+    gx.var_init(0)
+    assert lib.vina_odom_iekf_sharded_p2p(gx.h, C.c_int(0), C.c_int(10 ** 7), C.c_int(4), C.c_int(0), C.byref(it), C.byref(ok)) == -1
+    # world = 1 through the fused loop = the single-GPU loop without a leaf cache (one frame in the map: no planes
+    # yet, so nothing matches and the state stays where it was)
+    st = gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+    gx.set_state(st)
+    iters, _ = gx.odom_iekf_sharded_p2p(0, sc.xyzt.shape[0], 4)
+    assert iters == 2
+    assert np.array_equal(gpu_lib.state_arrays(gx.get_state())["p"], gpu_lib.state_arrays(st)["p"])
+    gx.close()
+
+
 def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     """150 scans through the full per-scan path (the window slides 150 times, leaves saturate, point_fix lists
     are dropped and re-created, the slide map turns over): trajectory within 1 mm / 0.01 deg of the oracle at

@@ -297,6 +297,7 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(ctx->d_ba_partial);
   cudaFree(ctx->d_ba_out);
   cudaFree(ctx->d_ba_lam);
+  cudaFreeHost(ctx->h_ba_out);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   for (void* m : ctx->p2p_opened)
@@ -1214,6 +1215,8 @@ static int ensure_ba(vina_ctx* ctx)
   CU(dalloc(&ctx->d_ba_partial, ba_partial_doubles(ctx->sm_count), false));
   CU(dalloc(&ctx->d_ba_out, (size_t)36 * VINA_MAX_WIN * VINA_MAX_WIN + 6 * VINA_MAX_WIN + 8));
   CU(dalloc(&ctx->d_ba_lam, (size_t)cap, false));
+  CU(cudaHostAlloc((void**)&ctx->h_ba_out, ((size_t)36 * VINA_MAX_WIN * VINA_MAX_WIN + 6 * VINA_MAX_WIN + 8 + 4096) * sizeof(double),
+                   cudaHostAllocDefault));
   CU(cudaDeviceSynchronize());  // see ensure_debug
   ctx->ba_cap = (int)cap;
   return VINA_OK;
@@ -1272,14 +1275,14 @@ extern "C" int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win
   if (!ctx->d_ba) return vn_fail(ctx, VINA_E_STATE, "no BA factors collected yet");
   if (win != ctx->cfg.win_size) return vn_fail(ctx, VINA_E_ARG, "win %d != LocalBA.win_size %d", win, ctx->cfg.win_size);
   const size_t dim = 6 * (size_t)win;
-  CU(cudaMemsetAsync(ctx->d_ba_out, 0, (dim * dim + dim + 1) * sizeof(double), ctx->stream));
+  // (every entry of Hess / JacT / residual is written by k_ba_reduce: no clearing needed)
   ctx->launches += launch_ba_hess(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win, ctx->sm_count,
                                   ctx->d_ba_partial, ctx->d_ba_out);
-  std::vector<double> h(dim * dim + dim + 1);
-  CU(cudaMemcpyAsync(h.data(), ctx->d_ba_out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  double* h = ctx->h_ba_out;  // pinned: the read-back is one asynchronous copy + one wait
+  CU(cudaMemcpyAsync(h, ctx->d_ba_out, (dim * dim + dim + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  memcpy(Hess, h.data(), dim * dim * sizeof(double));
-  memcpy(JacT, h.data() + dim * dim, dim * sizeof(double));
+  memcpy(Hess, h, dim * dim * sizeof(double));
+  memcpy(JacT, h + dim * dim, dim * sizeof(double));
   *residual = h[dim * dim + dim];
   return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_hess");
 }
@@ -1295,8 +1298,8 @@ extern "C" int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int wi
   ctx->launches += launch_ba_residual(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win,
                                       ctx->sm_count, ctx->d_ba_partial, ctx->d_ba_lam);
   const int nblk = ctx->sm_count * 2;
-  std::vector<double> part(nblk);
-  CU(cudaMemcpyAsync(part.data(), ctx->d_ba_partial, nblk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  double* part = ctx->h_ba_out;  // pinned (nblk <= 4096)
+  CU(cudaMemcpyAsync(part, ctx->d_ba_partial, nblk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (lam0 && n > 0)
     CU(cudaMemcpyAsync(lam0, ctx->d_ba_lam, (size_t)(n < cap ? n : cap) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

@@ -103,6 +103,7 @@ struct vina_ctx
   double* d_ba_partial = nullptr;
   double* d_ba_out = nullptr;   // Hess (6 win)^2, JacT (6 win), residual
   double* d_ba_lam = nullptr;
+  double* h_ba_out = nullptr;   // pinned read-back buffer
   bool ba_capture = false;   // vina_ba_set_capture: collect after every recut with a full window
   // profiling
   bool profiling = false;

@@ -242,7 +242,9 @@ M15 inverse15(const M15& A)
 // x = A^-1 b for the symmetric (damped) normal matrix: LDL^T with diagonal pivoting on the lower triangle,
 // right-looking (every elimination step updates the trailing columns with unit-stride inner loops, which the
 // host compiler vectorises: the 150 x 150 system of a 10-frame window costs tens of microseconds)
-std::vector<double> ldlt_solve(std::vector<double> L, int n, const std::vector<double>& b)
+// (compiled twice, AVX2 and baseline x86-64; the loader picks one - the trailing update is where the time goes)
+__attribute__((target_clones("avx2", "default"))) std::vector<double> ldlt_solve(std::vector<double> L, int n,
+                                                                                 const std::vector<double>& b)
 {
   auto a = [&](int i, int j) -> double& { return L[i + (size_t)j * n]; };
   std::vector<int> perm(n);
