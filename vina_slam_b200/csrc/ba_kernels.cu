@@ -252,20 +252,39 @@ __global__ void __launch_bounds__(BA_THREADS)
       }
     }
   }
-  // this warp's partial: [36 * pair + e], then the gradient, then the residual
-  double* out = partial + (size_t)gw * BA_ENTRIES;
-#pragma unroll
-  for (int s = 0; s < 2; s++)
+  // the block's partial: [36 * pair + e], then the gradient, then the residual. The four warps add their
+  // registers into one shared-memory image in warp order, the block writes it out coalesced.
+  __shared__ double blk[BA_ENTRIES];
+  __syncthreads();
+  for (int w = 0; w < BA_WARPS; w++)
   {
-    const int q = lane + 32 * s;
-    if (q < npair)
+    if (warp == w)
+    {
 #pragma unroll
-      for (int e = 0; e < 36; e++) out[36 * q + e] = acc[s][e];
+      for (int s = 0; s < 2; s++)
+      {
+        const int q = lane + 32 * s;
+        if (q < npair)
+#pragma unroll
+          for (int e = 0; e < 36; e++) blk[36 * q + e] = (w == 0 ? 0.0 : blk[36 * q + e]) + acc[s][e];
+      }
+      if (lane < win)
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+        {
+          const int e = 36 * BA_NPAIR + 6 * lane + c;
+          blk[e] = (w == 0 ? 0.0 : blk[e]) + jac[c];
+        }
+      if (lane == 0)
+      {
+        const int e = 36 * BA_NPAIR + 6 * VINA_MAX_WIN;
+        blk[e] = (w == 0 ? 0.0 : blk[e]) + resid;
+      }
+    }
+    __syncthreads();
   }
-  if (lane < win)
-#pragma unroll
-    for (int c = 0; c < 6; c++) out[36 * BA_NPAIR + 6 * lane + c] = jac[c];
-  if (lane == 0) out[36 * BA_NPAIR + 6 * VINA_MAX_WIN] = resid;
+  double* out = partial + (size_t)blockIdx.x * BA_ENTRIES;
+  for (int e = threadIdx.x; e < BA_ENTRIES; e += BA_THREADS) out[e] = blk[e];
 }
 
 // sum of the warps' partials; Hess (6 win)^2 column-major with the lower blocks mirrored (factors.cpp:123-125),
@@ -374,7 +393,7 @@ int launch_ba_writeback(cudaStream_t st, const MapView& map, const BaFactor* fac
   return 1;
 }
 
-int ba_hess_warps(int sm_count) { return sm_count * BA_WARPS; }
+int ba_hess_warps(int sm_count) { return sm_count * 2; }  // partial rows = blocks (2 per SM: 255 registers per thread)
 size_t ba_partial_doubles(int sm_count) { return (size_t)ba_hess_warps(sm_count) * BA_ENTRIES; }
 
 int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
@@ -383,10 +402,10 @@ int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const
   BaPoses xs;
   memset(&xs, 0, sizeof(xs));
   for (int i = 0; i < win && i < VINA_MAX_WIN; i++) xs.x[i] = h_xs[i];
-  const int blocks = sm_count;
+  const int blocks = ba_hess_warps(sm_count);
   k_ba_hess<<<blocks, BA_THREADS, 0, st>>>(fac, n_dev, xs, win, partial);
   const int dim = 6 * win;
-  k_ba_reduce<<<(BA_ENTRIES + 31) / 32, 256, 0, st>>>(partial, blocks * BA_WARPS, win, d_out, d_out + (size_t)dim * dim,
+  k_ba_reduce<<<(BA_ENTRIES + 31) / 32, 256, 0, st>>>(partial, blocks, win, d_out, d_out + (size_t)dim * dim,
                                                       d_out + (size_t)dim * dim + dim);
   return 2;
 }
