@@ -163,7 +163,7 @@ def main_reference(args, cfg):
     }
     if ref_build:
         line["reference_build"] = ref_build
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_name(cfg):
@@ -414,7 +414,7 @@ def main_ours(args, cfg):
             line["cpu_baseline"] = cpu
         if batch:
             line["batch"] = batch
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -540,7 +540,7 @@ def main_sharded(args, cfg):
         if ref is not None:
             line["config"]["union_equals_single_gpu_map"] = bool(int(dig[0]) == sharded.map_digest(ref.map_export()))
             line["config"]["single_gpu_nodes"] = ref.map_count()[0]
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -639,10 +639,25 @@ def main_bigmap(args, cfg):
             "config": {"workload": workload_name(cfg), "mode": "bigmap", "requested_voxels": n_vox,
                        "l2": "256 MiB buffer written between timed steps"},
             "with_large_map": out["filled"], "without": out["empty"]}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+_JSON_OUT = None
+
+
+def emit(text):
+    """The one JSON line goes to the process's real stdout; everything else any library writes to file descriptor 1
+    (NCCL prints its version banner there) has been sent to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
