@@ -11,6 +11,7 @@
 // points in ascending index order), so those sums - and through them every
 // eigen-decomposition and plane decision - are reproduced bit for bit; only
 // the order in which independent nodes are visited differs.
+#include <cstdio>
 #include "vn_kernels.cuh"
 
 #define SPIN_LIMIT 4000000
@@ -741,6 +742,20 @@ __global__ void __launch_bounds__(128) k_ba_collect(MapView M, LayerLists LL, Ba
 //                  pcrs_local[slot]) and applies that child's rows sequentially (exact sums, reference order;
 //                  the per-class cluster is flushed whenever the class of the next row changes),
 //   every thread   owns up to three (child, cov_add entry) pairs and sums that child's staged Bf_var terms.
+// VINA_SPLIT_TRACE build: cycle stamps of the first splitting leaf's block at the phase boundaries (debugging)
+#ifdef VINA_SPLIT_TRACE
+__device__ long long g_split_ts[2][8];
+#define VN_SPLIT_STAMP(k) \
+  do \
+  { \
+    if (threadIdx.x == 0 && j == 0) g_split_ts[layer & 1][k] = clock64(); \
+  } while (0)
+#else
+#define VN_SPLIT_STAMP(k) \
+  do \
+  { \
+  } while (0)
+#endif
 #define SPLIT_THREADS 256
 #define SPLIT_BATCH 256  // rows per batch = threads: every thread stages one row
 #define SPLIT_WARPS (SPLIT_BATCH / 32)
@@ -785,8 +800,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   LaneRole L;
-  role_init(t, L);  // L.ck = t % 9
-  const int my_k = t / 9;  // cluster chain of this thread (t < 72)
+  // the 72 (child, cluster scalar) chains belong to the LAST 72 threads: those own one (child, cov entry) pair
+  // each, the first 104 threads own two - the sequential chains no longer sit on the busiest threads
+  const int ct = t - (SPLIT_THREADS - 72);
+  const bool chain = ct >= 0;
+  role_init(chain ? ct : 0, L);  // L.ck = ct % 9
+  const int my_k = chain ? ct / 9 : 0;  // cluster chain of this thread
   const int nsplit = LL.count[4 + layer];
   for (int j = blockIdx.x; j < nsplit; j += gridDim.x)
   {
@@ -804,6 +823,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       (&fill[0][0])[t] = 0;
     }
     __syncthreads();
+    VN_SPLIT_STAMP(0);
     // the row stream: thread 0 walks the point_fix chain ONCE (dependent loads), threads 1..win_count fetch
     // the window frames' lists meanwhile; everything below works from this table. A chain has at most
     // max_points folds + 1 inherited segment (a leaf stops folding at pcr_fix.N >= max_points, octree.cpp:448),
@@ -866,6 +886,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       total = tot;
     }
     __syncthreads();
+    VN_SPLIT_STAMP(1);
     // pass 1: how many points of every class go to every child
     {
       const int ns = nseg, tot = total;
@@ -892,6 +913,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       }
     }
     __syncthreads();
+    VN_SPLIT_STAMP(2);
     // children (thread k owns child k), then their storage in parallel over (child, class)
     if (t < 8)
     {
@@ -917,6 +939,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       kid[k] = id;
     }
     __syncthreads();
+    VN_SPLIT_STAMP(3);
     if (t < 8 * win_count && store)
     {
       const int k = t & 7, si = t >> 3;
@@ -937,6 +960,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       }
     }
     __syncthreads();
+    VN_SPLIT_STAMP(4);
 
     // running sums (children are new: they start from zero)
     double clA = 0.0, clB = 0.0;  // thread t < 72: scalar L.ck of child my_k
@@ -1032,28 +1056,45 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           }
         }
         __syncthreads();
-        // phase 3: push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows
-        if (t < 72)
+        // phase 3: push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows. The adds are
+        // sequential (reference order, exact sums); the shared-memory loads are not: 8 rows are fetched ahead of
+        // the chain so that a row costs one dependent add instead of a load-to-use latency
+        if (chain)
         {
           const int r0 = cbase[my_k], r1 = cbase[my_k + 1];
-          for (int r = r0; r < r1; r++)
+          for (int rb = r0; rb < r1; rb += 8)
           {
-            const int rc = clsrow[r];
-            if (rc != cur_cls)
+            double va[8], vb[8];
+            int rcs[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
             {
-              // the per-class cluster (pcr_fix or pcrs_local[slot]) of the finished class is complete
-              if (cur_cls >= 0 && kid[my_k] >= 0)
-              {
-                NodeCold& kc = M.cold[kid[my_k]];
-                Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
-                cluster_set(dst, L.ck, clB);
-                if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
-              }
-              cur_cls = rc;
-              clB = 0.0;
+              const int r = rb + u < r1 ? rb + u : r1 - 1;
+              va[u] = val[r][L.ck];
+              vb[u] = val[r][9 + L.ck];
+              rcs[u] = clsrow[r];
             }
-            clA = da(clA, val[r][L.ck]);
-            clB = da(clB, val[r][9 + L.ck]);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+              if (rb + u >= r1) break;
+              const int rc = rcs[u];
+              if (rc != cur_cls)
+              {
+                // the per-class cluster (pcr_fix or pcrs_local[slot]) of the finished class is complete
+                if (cur_cls >= 0 && kid[my_k] >= 0)
+                {
+                  NodeCold& kc = M.cold[kid[my_k]];
+                  Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
+                  cluster_set(dst, L.ck, clB);
+                  if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
+                }
+                cur_cls = rc;
+                clB = 0.0;
+              }
+              clA = da(clA, va[u]);
+              clB = da(clB, vb[u]);
+            }
           }
         }
 #pragma unroll
@@ -1064,17 +1105,27 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           {
             const int k = p / 45, e = p % 45;
             const int r0 = cbase[k], r1 = cbase[k + 1];
-            double s = 0.0;
-            for (int r = r0; r < r1; r++) s += red[r][e];
-            cv[q] += s;
+            // (cov_add is toleranced, 1e-12: four interleaved partial sums break the add chain)
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int r = r0;
+            for (; r + 3 < r1; r += 4)
+            {
+              s0 += red[r][e];
+              s1 += red[r + 1][e];
+              s2 += red[r + 2][e];
+              s3 += red[r + 3][e];
+            }
+            for (; r < r1; r++) s0 += red[r][e];
+            cv[q] += (s0 + s1) + (s2 + s3);
           }
         }
         if (t < SPLIT_BATCH && kk >= 0) atomicAdd(&fill[cls][kk], 1);
         __syncthreads();
+        VN_SPLIT_STAMP(5);
       }
     }
     // last class of every chain
-    if (t < 72 && cur_cls >= 0 && kid[my_k] >= 0)
+    if (chain && cur_cls >= 0 && kid[my_k] >= 0)
     {
       NodeCold& kc = M.cold[kid[my_k]];
       Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
@@ -1082,7 +1133,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
     }
     // children's pcr_add / cov_add
-    if (t < 72 && kid[my_k] >= 0)
+    if (chain && kid[my_k] >= 0)
     {
       NodeCold& kc = M.cold[kid[my_k]];
       cluster_set(kc.pcr_add, L.ck, clA);
@@ -1121,8 +1172,22 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       int pos = atomicAdd(&LL.count[layer + 1], 1);
       LL.list[layer + 1][pos] = kid[t];
     }
+    VN_SPLIT_STAMP(6);
   }
 }
+#ifdef VINA_SPLIT_TRACE
+void vn_split_trace_dump()
+{
+  long long h[2][8];
+  cudaMemcpyFromSymbol(h, g_split_ts, sizeof(h));
+  for (int l = 0; l < 2; l++)
+  {
+    fprintf(stderr, "[vina trace] k_split layer %d, cycles since block start of the first leaf:", l);
+    for (int k = 1; k <= 6; k++) fprintf(stderr, " %lld", h[l][k] - h[l][0]);
+    fprintf(stderr, "\n");
+  }
+}
+#endif
 
 
 

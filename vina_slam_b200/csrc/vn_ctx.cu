@@ -240,6 +240,9 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   return VINA_OK;
 }
 
+#ifdef VINA_SPLIT_TRACE
+void vn_split_trace_dump();  // map_kernels.cu
+#endif
 extern "C" void vina_ctx_destroy(vina_ctx* ctx)
 {
   if (!ctx) return;
@@ -279,6 +282,9 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
   }
+#ifdef VINA_SPLIT_TRACE
+  if (ctx->trace) vn_split_trace_dump();
+#endif
   if (ctx->trace && ctx->tr_n > 0)
   {
     fprintf(stderr, "[vina trace] %d overlapped steps; host us (propagate, front+iekf enqueued, down count, map enqueued, "
