@@ -57,19 +57,10 @@ __device__ __forceinline__ void compensate(const DeskewPoses& P, int k, float cu
   xyz[2] = (float)d[2];
 }
 
-__global__ void __launch_bounds__(256) k_deskew(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg,
-                                                int* __restrict__ status)
+// one point of the deskew loop (imu_ekf.cpp:114-144); returns the point as the scan keeps it
+__device__ __forceinline__ float4 deskew_point(const DeskewPoses& P, const float4* __restrict__ pts, int i, int n,
+                                               int* __restrict__ status)
 {
-  __shared__ DeskewPoses P;
-  {
-    const int words = sizeof(DeskewPoses) / 4;
-    const int* src = reinterpret_cast<const int*>(Pg);
-    int* dst = reinterpret_cast<int*>(&P);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   float4 q = pts[i];
   // the contract of lidar_decoder.cpp:30: sorted by curvature
   if (i + 1 < n && pts[i + 1].w < q.w) atomicOr(status, VN_ST_UNSORTED);
@@ -85,23 +76,36 @@ __global__ void __launch_bounds__(256) k_deskew(float4* __restrict__ pts, int n,
       hi = mid;
   }
   int k = lo - 1;
-  if (k < 0) return;
+  if (k < 0) return q;  // points at or before the first pose are left untouched (imu_ekf.cpp:124)
   float xyz[3] = { q.x, q.y, q.z };
   compensate(P, k, q.w, xyz);
   if (i == 0)
     for (int kk = k - 1; kk >= 0; kk--) compensate(P, kk, q.w, xyz);
-  pts[i] = make_float4(xyz[0], xyz[1], xyz[2], q.w);
+  return make_float4(xyz[0], xyz[1], xyz[2], q.w);
+}
+
+__global__ void __launch_bounds__(256) k_deskew(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg,
+                                                int* __restrict__ status)
+{
+  __shared__ DeskewPoses P;
+  {
+    const int words = sizeof(DeskewPoses) / 4;
+    const int* src = reinterpret_cast<const int*>(Pg);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 r = deskew_point(P, pts, i, n, status);
+  // (a thread reads its right-hand neighbour's time stamp, which deskewing never changes)
+  pts[i] = r;
 }
 
 // ---------------------------------------------------------------------------
 // a3 var_init: src/core/point_utils.cpp:3-52 (calcBodyVar + extrinsic).
-__global__ void __launch_bounds__(256)
-    k_var_init(const float4* __restrict__ pts, const int* __restrict__ n_ptr, int n_host, ScanView out, VarInitParams prm)
+__device__ __forceinline__ void var_init_point(const float4 q, const int i, const ScanView& out, const VarInitParams& prm)
 {
-  int n = n_ptr ? *n_ptr : n_host;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 q = pts[i];
   double pb[3] = { (double)q.x, (double)q.y, (double)q.z };
   if (pb[2] == 0) pb[2] = 0.0001;
   float range = (float)sqrt(pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2]);
@@ -178,6 +182,38 @@ __global__ void __launch_bounds__(256)
     int r = ui[k], c = uj[k];
     out.v[k][i] = (T[r] * prm.ext_R[c] + T[r + 3] * prm.ext_R[c + 3]) + T[r + 6] * prm.ext_R[c + 6];
   }
+}
+
+__global__ void __launch_bounds__(256)
+    k_var_init(const float4* __restrict__ pts, const int* __restrict__ n_ptr, int n_host, ScanView out, VarInitParams prm)
+{
+  int n = n_ptr ? *n_ptr : n_host;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  var_init_point(pts[i], i, out, prm);
+}
+
+// a2 + a3 of the full scan in one pass (the production schedule: VNC_lio runs on the un-downsampled scan,
+// local_mapping.cpp:406-413): deskew, store the float point, var_init from that float value - exactly what the
+// two kernels do one after the other - and reset the IEKF's per-point leaf cache (odometry.cpp:79)
+__global__ void __launch_bounds__(256)
+    k_deskew_var_init(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg, int* __restrict__ status,
+                      ScanView out, VarInitParams prm, int* __restrict__ cache)
+{
+  __shared__ DeskewPoses P;
+  {
+    const int words = sizeof(DeskewPoses) / 4;
+    const int* src = reinterpret_cast<const int*>(Pg);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 r = deskew_point(P, pts, i, n, status);
+  pts[i] = r;
+  var_init_point(r, i, out, prm);
+  cache[i] = -1;
 }
 
 // ---------------------------------------------------------------------------
@@ -335,6 +371,11 @@ void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_pos
 {
   if (n <= 0) return;
   k_deskew<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status);
+}
+void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
+                            const VarInitParams& prm, int* cache)
+{
+  if (n > 0) k_deskew_var_init<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status, out, prm, cache);
 }
 void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n_host, ScanView out,
                      const VarInitParams& prm)

@@ -532,9 +532,8 @@ extern "C" int vina_down_download(vina_ctx* ctx, float* xyzt, int cap)
   return ctx->n_down;
 }
 
-extern "C" int vina_var_init(vina_ctx* ctx, int which)
+static VarInitParams var_init_params(const vina_ctx* ctx)
 {
-  if (!ctx || which < 0 || which > 1) return VINA_E_ARG;
   VarInitParams prm;
   const float range_inc = (float)ctx->cfg.dept_err, degree_inc = (float)ctx->cfg.beam_err;  // point_utils.cpp:3
   prm.range_var = range_inc * range_inc;
@@ -542,6 +541,36 @@ extern "C" int vina_var_init(vina_ctx* ctx, int which)
   prm.dir_var = s * s;
   memcpy(prm.ext_R, ctx->cfg.ext_R, 72);
   memcpy(prm.ext_t, ctx->cfg.ext_t, 24);
+  return prm;
+}
+
+// vina_deskew + vina_var_init(ctx, 0) + the IEKF's leaf-cache reset as one kernel (the per-scan step)
+int vn_deskew_var_init(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3])
+{
+  if (m > VINA_MAX_POSES) return vn_fail(ctx, VINA_E_CAPACITY, "%d IMU poses > VINA_MAX_POSES", m);
+  if (ctx->poses_in_flight) CU(cudaEventSynchronize(ctx->ev_poses));
+  DeskewPoses* P = ctx->h_poses;
+  P->m = m;
+  memcpy(P->pose, poses, (size_t)m * sizeof(vina_imu_pose));
+  memcpy(P->R_end, R_end, 72);
+  memcpy(P->p_end, p_end, 24);
+  memcpy(P->ext_R, ctx->cfg.ext_R, 72);
+  memcpy(P->ext_t, ctx->cfg.ext_t, 24);
+  CU(cudaMemcpyAsync(ctx->d_poses, P, sizeof(DeskewPoses), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_poses, ctx->stream));
+  ctx->poses_in_flight = true;
+  launch_deskew_var_init(ctx->stream, ctx->d_scan, ctx->n_scan, ctx->d_poses, ctx->d_status, ctx->pv[0], var_init_params(ctx),
+                         ctx->d_cache);
+  ctx->n_pv[0] = ctx->n_scan;
+  ctx->cache_is_reset = true;
+  ctx->launches += 1;
+  return mark_scan_read(ctx);
+}
+
+extern "C" int vina_var_init(vina_ctx* ctx, int which)
+{
+  if (!ctx || which < 0 || which > 1) return VINA_E_ARG;
+  VarInitParams prm = var_init_params(ctx);
   if (which == 1)
   {
     int r = resolve_n_down(ctx);

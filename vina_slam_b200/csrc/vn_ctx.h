@@ -29,6 +29,7 @@ struct vina_ctx
   ScanView pv[2];            // [0] full scan, [1] down-sampled
   int n_pv[2] = { 0, 0 };
   int* d_cache = nullptr;
+  bool cache_is_reset = false;  // the fused deskew + var_init kernel has just written -1 everywhere
   DeskewPoses* d_poses = nullptr;
   DeskewPoses* h_poses = nullptr;  // pinned
   // down-sampling scratch
@@ -129,6 +130,7 @@ void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 // enqueue max_iter iterations of the IEKF against the sharded map, exchange and update on the device (vn_ctx.cu)
 int vn_shard_iekf_enqueue(vina_ctx* c, int first, int count, int max_iter, int part);
 int vn_mark_scan_read(vina_ctx* c);
+int vn_deskew_var_init(vina_ctx* c, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vn_ba_collect_enqueue(vina_ctx* c);
 int vn_ba_writeback_enqueue(vina_ctx* c);  // factor store -> leaves (octree.cpp:410-416), before margi  // tras_opt into the factor store (after recut, before margi)
 // map update with the newest pose read from the device iterate (vn_ctx.cu)

@@ -81,6 +81,9 @@ struct IekfBatch
 void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status);
 void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n_host, ScanView out,
                      const VarInitParams& prm);
+// deskew + var_init of the full scan + leaf-cache reset in one pass
+void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
+                            const VarInitParams& prm, int* cache);
 void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots);
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
                       int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status);

@@ -412,9 +412,13 @@ static int iekf_stage(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
   if (r) return r;
   ctx->iekf_which = which;
   const int n = ctx->n_pv[which];
-  launch_fill_int(ctx->stream, ctx->d_cache, -1, n);  // vector<OctoTree*> octos(psize, nullptr), odometry.cpp:79
+  if (!(ctx->cache_is_reset && which == 0))
+  {
+    launch_fill_int(ctx->stream, ctx->d_cache, -1, n);  // vector<OctoTree*> octos(psize, nullptr), odometry.cpp:79
+    ctx->launches += 1;
+  }
+  ctx->cache_is_reset = false;
   ctx->iekf_blocks = iekf_grid_blocks(n, ctx->sm_count);
-  ctx->launches += 1;
   ctx->dbg_valid = false;
   return VINA_OK;
 }
@@ -656,7 +660,8 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (r) return r;
   cudaStream_t A = ctx->stream, B = ctx->side_stream;
   if (tr) th[1] = now_us(), cudaEventRecord(ctx->tr_ev[0], A);
-  r = vina_deskew(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+  // deskew, var_init of the full scan and the leaf-cache reset are one kernel
+  r = vn_deskew_var_init(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
   if (r) return r;
   r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
   if (r) return r;
@@ -664,8 +669,6 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   ctx->stream = B;
   r = vina_downsample(ctx);
   ctx->stream = A;
-  if (r) return r;
-  r = vina_var_init(ctx, 0);
   if (r) return r;
   const int num_max_iter = max_iter > 0 ? max_iter : 20;
   r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
