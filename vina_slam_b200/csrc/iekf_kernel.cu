@@ -585,6 +585,18 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
   if (bt.mode & VN_IEKF_SOLVE)
   {
     iekf_solve_block(dev, fin, smem, IEKF_THREADS);
+    if ((bt.mode & VN_IEKF_HANDOVER) && reinterpret_cast<const int*>(smem + 368)[0])
+    {
+      // the loop has just finished: hand the iterate to the host (data, system-wide fence, then the flag)
+      __syncthreads();
+      __threadfence();
+      const double* sd = reinterpret_cast<const double*>(dev);
+      double* dd = reinterpret_cast<double*>(q.pub);
+      for (int i = threadIdx.x; i < (int)(sizeof(IekfDev) / sizeof(double)); i += IEKF_THREADS) dd[i] = __ldcg(sd + i);
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(q.pub_flag) = q.pub_seq;
+    }
   }
   if (bt.mode & VN_IEKF_PUBLISH)
   {

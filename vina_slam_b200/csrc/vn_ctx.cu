@@ -685,6 +685,9 @@ void vn_iekf_fill_seq(vina_ctx* ctx, IekfSeq* q, bool debug)
   q->result = ctx->d_result;
   q->voxel_size = ctx->cfg.voxel_size;
   q->seq = ctx->iekf_seq;
+  q->pub = ctx->d_pub;
+  q->pub_flag = ctx->d_pub_flag;
+  q->pub_seq = ctx->pub_seq;
   IekfDebug none = { nullptr, nullptr, nullptr, nullptr };
   q->dbg = debug ? ctx->dbg : none;
 }

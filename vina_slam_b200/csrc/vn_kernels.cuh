@@ -47,6 +47,7 @@ struct IekfDev
 #define VN_IEKF_PUBLISH 1  // write the 34 sums + sequence number to mapped host memory (low-level ABI, tests)
 #define VN_IEKF_SOLVE 2    // last block runs the IEKF update on the device state
 #define VN_IEKF_GATED 4    // return at once when the device iterate says the loop has finished (sharded loop)
+#define VN_IEKF_HANDOVER 16  // with VN_IEKF_SOLVE: publish the iterate to the host from the launch that ends the loop
 #define VN_IEKF_NOCACHE 8  // no per-point leaf cache: every point looks its voxel up (queries that crossed GPUs)
 
 // one sequence of a (batched) k_iekf launch
@@ -67,6 +68,11 @@ struct IekfSeq
   double* result;        // mapped pinned host memory (VN_IEKF_PUBLISH)
   double voxel_size;
   unsigned long long seq;  // launch sequence number, written after the sums so that the host can poll for them
+  // VN_IEKF_HANDOVER: the block that finishes the loop copies the iterate to mapped host memory (pub) and then
+  // writes pub_seq to pub_flag - the host has the pose without a separate publishing kernel
+  IekfDev* pub;
+  unsigned long long* pub_flag;
+  unsigned long long pub_seq;
   IekfDebug dbg;
 };
 

@@ -431,8 +431,9 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
   int r = iekf_stage(ctx, o, which, num_max_iter);
   if (r) return r;
   IekfBatch bt;
-  bt.mode = VN_IEKF_SOLVE;
+  bt.mode = VN_IEKF_SOLVE | VN_IEKF_HANDOVER;  // the launch that ends the loop publishes the iterate itself
   bt.variant = 0;
+  ++ctx->pub_seq;
   vn_iekf_fill_seq(ctx, &bt.s[0], false);
   if (ctx->profiling && (int)ctx->iekf_ev.size() < 2 * num_max_iter)
   {
@@ -448,7 +449,7 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
     ctx->launches += 1;
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it + 1], ctx->stream);
   }
-  return vn_iterate_publish(ctx, ctx->stream);
+  return VINA_OK;
 }
 
 // VINA_SLAM::LioStateEstimation (odometry.cpp:64-255) with the whole iteration loop on the device: one
