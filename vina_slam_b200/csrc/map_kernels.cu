@@ -1358,6 +1358,8 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
 __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
 {
+  // (the slide list the compaction fills after this kernel starts empty)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) M.slide_count[1 - M.slide_cur] = 0;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
@@ -1455,6 +1457,45 @@ __global__ void __launch_bounds__(128) k_margi_clear(MapView M, LayerLists LL)
 // surviving roots go to the other slide list (the caller flips slide_cur)
 __global__ void __launch_bounds__(128) k_slide_compact(MapView M)
 {
+  const int cur = M.slide_cur;
+  const int nroots = M.slide_count[cur];
+  const bool early_out = nroots + M.slide_others < M.thread_num;  // multi_margi returned before its erase loop
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
+  {
+    const int root = M.slide_list[cur][j];
+    if (early_out || M.cold[root].isexist)
+    {
+      int pos = atomicAdd(&M.slide_count[1 - cur], 1);
+      M.slide_list[1 - cur][pos] = root;
+    }
+    else
+      M.cold[root].in_slide = 0;
+  }
+}
+
+// k_margi_clear (blockIdx.y <= max_layer) and k_slide_compact (blockIdx.y == max_layer + 1) in one launch: both
+// only read the roots' isexist, which is final after the last k_margi_up. The counter of the list the compaction
+// fills has been zeroed by the caller before this launch.
+__global__ void __launch_bounds__(128) k_margi_clear_compact(MapView M, LayerLists LL)
+{
+  if ((int)blockIdx.y <= M.max_layer)
+  {
+    if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
+    int nn;
+    const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
+    {
+      NodeCold& c = M.cold[nodes[j]];
+      if (M.cold[c.root].isexist || !c.has_sw) continue;
+      for (int s = 0; s < M.win_size; s++)
+      {
+        c.win_cnt[s] = 0;
+        cluster_clear(c.pcrs_local[s]);
+      }
+      c.has_sw = 0;
+    }
+    return;
+  }
   const int cur = M.slide_cur;
   const int nroots = M.slide_count[cur];
   const bool early_out = nroots + M.slide_others < M.thread_num;  // multi_margi returned before its erase loop
@@ -1630,10 +1671,8 @@ int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, 
   k_margi_leaves<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b, lv);
   launches++;
   for (int layer = map.max_layer - 1; layer >= 0; layer--, launches++) k_margi_up<<<296, 128, 0, st>>>(map, LL, layer);
-  k_margi_clear<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL);
-  k_zero_ints<<<1, 32, 0, st>>>(map.slide_count + (1 - map.slide_cur), 1);
-  k_slide_compact<<<296, 128, 0, st>>>(map);
-  return launches + 3;
+  k_margi_clear_compact<<<dim3(296, map.max_layer + 2), 128, 0, st>>>(map, LL);
+  return launches + 1;
 }
 
 int launch_ba_collect(cudaStream_t st, const MapView& map, const LayerLists& LL, BaFactor* out, int* count, int cap)
