@@ -128,10 +128,10 @@ def run_ba(make_odom):
     return out
 
 
-def run_ba_odometry(make_odom, steps=14):
+def run_ba_odometry(make_odom, steps=14, sensor=("robosense128", 24, 350, 77)):
     """The per-scan loop with if_BA: 1 (local_mapping.cpp:437-441, 492-497, 541-546): IMU pre-integration factors,
     LI_BA_Optimizer::damping_iter (LM, 10 frames x 15 states), margi taking the re-evaluated factors back."""
-    cfg = synth.small_sensor("robosense128", 24, 350, seed=77)
+    cfg = synth.small_sensor(sensor[0], sensor[1], sensor[2], seed=sensor[3])
     seq = synth.Sequence(cfg)
     od = make_odom(cfg)
     od.set_ba(True)

@@ -1014,14 +1014,15 @@ def test_ba_lidar_factor_matches_oracle(oracle_lib, gpu_lib):
     od.close()
 
 
-def test_ba_odometry_matches_oracle(oracle_lib, gpu_lib):
+@pytest.mark.parametrize("base,beams,steps", [("robosense128", 32, 600), ("velodyne32", 32, 500)])
+def test_ba_odometry_matches_oracle(oracle_lib, gpu_lib, base, beams, steps):
     """The per-scan loop with LocalBA.if_BA: 1 (mid360.yaml / velodyne.yaml; local_mapping.cpp:437-441, 492-497,
     541-546) through vina_odom_step: IMU pre-integration factors and the LM loop on the host, the LiDAR factor on the
     device, margi taking the re-evaluated factors back - against the oracle, whose BA reproduces the reference's own
     imu_preintegration.cpp / optimizers.cpp / factors.cpp bit for bit (tests/test_oracle_vs_ref.py). Same number of
     BA runs and LM iterations, trajectory within the north-star's 1 mm / 0.01 deg at every scan, and BA visibly
-    changes the result (it is not a no-op)."""
-    cfg = small_cfg("robosense128", 32, 600)
+    changes the result (it is not a no-op). velodyne32: 3 octree layers, non-identity extrinsic (its yaml has if_BA: 1)."""
+    cfg = small_cfg(base, beams, steps)
     seq = synth.Sequence(cfg)
     od = oracle_lib.Odom(cfg)
     gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)

@@ -135,6 +135,19 @@ def test_ba_odometry_reproduces_reference(oracle_lib):
         _assert_same(o, r, "oracle BA odometry vs reference build")
 
 
+def test_ba_odometry_side_by_side_velodyne(oracle_lib):
+    """if_BA: 1 is the yaml setting of velodyne.yaml (3 octree layers, non-identity extrinsic): the same loop on a
+    Velodyne-32-shaped sequence, restatement and reference build live, bit for bit."""
+    if not oracle_lib.have_ref():
+        pytest.skip("oracle/_ref is not built here (needs /root/reference)")
+    mod = _scenario()
+    sensor = ("velodyne32", 16, 300, 5)
+    o = mod.run_ba_odometry(lambda cfg: oracle_lib.Odom(cfg), steps=12, sensor=sensor)
+    r = mod.run_ba_odometry(lambda cfg: oracle_lib.Odom(cfg, ref=True), steps=12, sensor=sensor)
+    assert int(o["ba_runs"][0]) >= 3
+    _assert_same(o, r, "oracle BA odometry vs reference build (velodyne32)")
+
+
 def test_vnc_terms_are_unreachable_in_the_reference(oracle_lib):
     """VNC_lio (use_vnc = true) of the reference build == plain point-to-plane IEKF with a 4-iteration budget:
     matchVoxelMap can never succeed because OctoTree::match never writes max_prob (DESIGN.md §1)."""
