@@ -688,6 +688,28 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (tr) cudaEventRecord(ctx->tr_ev[2], A);
   r = vn_mark_scan_read(ctx);  // (covers the side stream's readers of the scan buffer as well)
   if (r) return r;
+  if (o->if_BA)
+  {
+    // the LM loop of the BA needs the host between recut and margi: take the IEKF result first, then the map
+    // update with host poses (the front of the step has still run fused / on the side stream)
+    r = vn_iterate_wait(ctx);
+    if (r) return r;
+    int ok = 0;
+    unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, &ok);
+    ctx->tm.iekf_iters = o->last_iters;
+    ctx->tm.iekf_kernel_ms = 0;
+    if (ok)
+    {
+      if (o->degrade_cnt > 0) o->degrade_cnt--;
+    }
+    else
+      o->degrade_cnt++;
+    r = map_update(ctx, o);
+    if (r) return r;
+    if (x_out) *x_out = o->x_curr;
+    ctx->tm.kernel_launches = ctx->launches - l0;
+    return VINA_OK;
+  }
   // local_mapping.cpp:425-451, 489-546 with if_BA == 0, pose of the new frame from the device
   o->win_count++;
   vina_pose ps;
@@ -755,7 +777,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
 static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pcl_end_time,
                               const vina_imu* imus, int m, int iekf_on_full, int max_iter, vina_state* x_out)
 {
-  if (ctx->overlap && !ctx->profiling && iekf_on_full && ctx->side_stream && !o->if_BA)
+  if (ctx->overlap && !ctx->profiling && iekf_on_full && ctx->side_stream)
     return odom_step_overlapped(ctx, o, pcl_beg_time, pcl_end_time, imus, m, max_iter, x_out);
   const int l0 = ctx->launches;
   int which = 1, ok = 0;
