@@ -1434,48 +1434,11 @@ __global__ void __launch_bounds__(128) k_margi_up(MapView M, LayerLists LL, int 
   }
 }
 
-// erase loop of multi_margi (local_mapping.cpp:67-78): every node whose root left surf_map_slide gives
-// its SlideWindow back (OctoTree::clear_slwd, octree.cpp:739-756). blockIdx.y = layer.
-__global__ void __launch_bounds__(128) k_margi_clear(MapView M, LayerLists LL)
-{
-  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
-  int nn;
-  const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
-  {
-    NodeCold& c = M.cold[nodes[j]];
-    if (M.cold[c.root].isexist || !c.has_sw) continue;
-    for (int s = 0; s < M.win_size; s++)
-    {
-      c.win_cnt[s] = 0;
-      cluster_clear(c.pcrs_local[s]);
-    }
-    c.has_sw = 0;
-  }
-}
-
-// surviving roots go to the other slide list (the caller flips slide_cur)
-__global__ void __launch_bounds__(128) k_slide_compact(MapView M)
-{
-  const int cur = M.slide_cur;
-  const int nroots = M.slide_count[cur];
-  const bool early_out = nroots + M.slide_others < M.thread_num;  // multi_margi returned before its erase loop
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
-  {
-    const int root = M.slide_list[cur][j];
-    if (early_out || M.cold[root].isexist)
-    {
-      int pos = atomicAdd(&M.slide_count[1 - cur], 1);
-      M.slide_list[1 - cur][pos] = root;
-    }
-    else
-      M.cold[root].in_slide = 0;
-  }
-}
-
-// k_margi_clear (blockIdx.y <= max_layer) and k_slide_compact (blockIdx.y == max_layer + 1) in one launch: both
-// only read the roots' isexist, which is final after the last k_margi_up. The counter of the list the compaction
-// fills has been zeroed by the caller before this launch.
+// The erase loop of multi_margi (local_mapping.cpp:67-78) in one launch. blockIdx.y <= max_layer: every node whose
+// root left surf_map_slide gives its SlideWindow back (OctoTree::clear_slwd, octree.cpp:739-756);
+// blockIdx.y == max_layer + 1: the surviving roots go to the other slide list (the caller flips slide_cur). Both
+// only read the roots' isexist, which is final after the last k_margi_up; the counter of the list being filled
+// was zeroed by k_margi_leaves.
 __global__ void __launch_bounds__(128) k_margi_clear_compact(MapView M, LayerLists LL)
 {
   if ((int)blockIdx.y <= M.max_layer)
