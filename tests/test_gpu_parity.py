@@ -1119,6 +1119,50 @@ def test_ba_and_fused_loop_entry_points_edges(oracle_lib, gpu_lib):
     gx.close()
 
 
+def test_ba_full_size_mid360_properties(gpu_lib):
+    """BASELINE configs[0] at full size (Mid-360 shape, 20 000 points per scan, mid360.yaml has if_BA: 1), too
+    large for the oracle to follow in the GPU suite: size-independent properties of the BA instead. The LiDAR
+    Hessian has mirrored off-diagonal blocks and is finite, the per-factor eigenvalues are non-negative, a
+    perturbation of the window poses raises the residual, BA runs every scan once the window has IMU factors,
+    and the trajectory stays on the synthetic ground truth."""
+    cfg = synth.SENSORS["mid360"]
+    caps = dict(max_scan_points=32768, max_nodes=1 << 18, hash_capacity_log2=19)
+    seq = synth.Sequence(cfg)
+    gx = gpu_lib.Ctx(cfg, **caps)
+    gx.set_ba(True)
+    gx.ba_set_capture(True)
+    for _ in range(cfg.win_size):
+        sc = seq.next_scan(deskewed=True)
+        gx.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    gx.set_imu_anchor(sc.end_time, sc.imu[-1])
+    poses_gt = []
+    for k in range(13):
+        sc = seq.next_scan()
+        st = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        assert np.linalg.norm(st["p"] - sc.gt_p) < 0.02, k
+        poses_gt.append(np.concatenate([sc.gt_R.T.reshape(-1), sc.gt_p]))
+    gx.sync()
+    runs, iters = gx.ba_stats()
+    assert runs == 13 - 8 and 1 <= iters <= 10
+    n = gx.ba_count()
+    assert n > 500
+    w = cfg.win_size
+    ps = np.array(poses_gt[-w:])  # the window the last BA worked on (ground-truth poses)
+    H, J, r0 = gx.ba_hess(ps)
+    for i in range(w):
+        for j in range(i + 1, w):
+            assert np.array_equal(H[6 * i:6 * i + 6, 6 * j:6 * j + 6], H[6 * j:6 * j + 6, 6 * i:6 * i + 6].T)
+    assert np.isfinite(H).all() and np.isfinite(J).all() and np.linalg.eigvalsh(0.5 * (H + H.T))[-1] > 0
+    res_gt, lam = gx.ba_residual(ps)
+    assert lam.shape == (n,) and (lam >= -1e-12).all()
+    rng = np.random.default_rng(3)
+    pert = ps.copy()
+    pert[:, 9:] += rng.normal(0, 0.03, (w, 3))
+    res_pert, _ = gx.ba_residual(pert)
+    assert res_pert > 1.5 * res_gt, (res_gt, res_pert)
+    gx.close()
+
+
 def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     """150 scans through the full per-scan path (the window slides 150 times, leaves saturate, point_fix lists
     are dropped and re-created, the slide map turns over): trajectory within 1 mm / 0.01 deg of the oracle at

@@ -1306,23 +1306,37 @@ extern "C" int vina_ba_count(vina_ctx* ctx, int32_t* n_factors)
   return vn_check_status(ctx);
 }
 
-extern "C" int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win, double* Hess, double* JacT,
-                                     double* residual)
+// the two halves of vina_ba_lidar_hessian: the host can do its own work (the IMU factors) while the kernels run
+int vn_ba_hess_enqueue(vina_ctx* ctx, const vina_pose* xs, int win)
 {
-  if (!ctx || !xs || win < 1 || win > VINA_MAX_WIN || !Hess || !JacT || !residual) return VINA_E_ARG;
   if (!ctx->d_ba) return vn_fail(ctx, VINA_E_STATE, "no BA factors collected yet");
   if (win != ctx->cfg.win_size) return vn_fail(ctx, VINA_E_ARG, "win %d != LocalBA.win_size %d", win, ctx->cfg.win_size);
   const size_t dim = 6 * (size_t)win;
   // (every entry of Hess / JacT / residual is written by k_ba_reduce: no clearing needed)
   ctx->launches += launch_ba_hess(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win, ctx->sm_count,
                                   ctx->d_ba_partial, ctx->d_ba_out);
-  double* h = ctx->h_ba_out;  // pinned: the read-back is one asynchronous copy + one wait
-  CU(cudaMemcpyAsync(h, ctx->d_ba_out, (dim * dim + dim + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // pinned: the read-back is one asynchronous copy + one wait
+  CU(cudaMemcpyAsync(ctx->h_ba_out, ctx->d_ba_out, (dim * dim + dim + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return VINA_OK;
+}
+int vn_ba_hess_finish(vina_ctx* ctx, int win, double* Hess, double* JacT, double* residual)
+{
+  const size_t dim = 6 * (size_t)win;
   CU(cudaStreamSynchronize(ctx->stream));
+  const double* h = ctx->h_ba_out;
   memcpy(Hess, h, dim * dim * sizeof(double));
   memcpy(JacT, h + dim * dim, dim * sizeof(double));
   *residual = h[dim * dim + dim];
   return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_hess");
+}
+
+extern "C" int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win, double* Hess, double* JacT,
+                                     double* residual)
+{
+  if (!ctx || !xs || win < 1 || win > VINA_MAX_WIN || !Hess || !JacT || !residual) return VINA_E_ARG;
+  int r = vn_ba_hess_enqueue(ctx, xs, win);
+  if (r) return r;
+  return vn_ba_hess_finish(ctx, win, Hess, JacT, residual);
 }
 
 extern "C" int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int win, double* residual, double* lam0, int cap)

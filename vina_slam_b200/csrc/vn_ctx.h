@@ -132,7 +132,9 @@ int vn_shard_iekf_enqueue(vina_ctx* c, int first, int count, int max_iter, int p
 int vn_mark_scan_read(vina_ctx* c);
 int vn_deskew_var_init(vina_ctx* c, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vn_ba_collect_enqueue(vina_ctx* c);
-int vn_ba_writeback_enqueue(vina_ctx* c);  // factor store -> leaves (octree.cpp:410-416), before margi  // tras_opt into the factor store (after recut, before margi)
+int vn_ba_writeback_enqueue(vina_ctx* c);
+int vn_ba_hess_enqueue(vina_ctx* c, const vina_pose* xs, int win);  // vina_ba_lidar_hessian in two halves
+int vn_ba_hess_finish(vina_ctx* c, int win, double* Hess, double* JacT, double* residual);  // factor store -> leaves (octree.cpp:410-416), before margi  // tras_opt into the factor store (after recut, before margi)
 // map update with the newest pose read from the device iterate (vn_ctx.cu)
 int vn_map_insert_live(vina_ctx* c, int win_ord);
 int vn_map_recut_live(vina_ctx* c, int win_count, const vina_pose* x_buf);

@@ -535,28 +535,31 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
     iters++;
     if (is_calc_hess)
     {
-      // divide_thread (optimizers.cpp:181-245): IMU factors on the host, the LiDAR factor on the device
+      // divide_thread (optimizers.cpp:181-245): the LiDAR factor on the device, the IMU factors on the host
+      // meanwhile (the reference overlaps the same two with its worker threads)
       std::fill(Hess.begin(), Hess.end(), 0.0);
       std::fill(JacT.begin(), JacT.end(), 0.0);
+      set_poses(xs);
+      t0 = now_us();
+      int r = vn_ba_hess_enqueue(ctx, poses.data(), win);
+      if (r) return r;
       double residual = 0;
       HM<30, 30> jtj;
       HM<30, 1> gg;
-      t0 = now_us();
       for (int i = 0; i < win - 1; i++)
       {
         residual += imus_factor[i]->evaluate(xs[i], xs[i + 1], &jtj, &gg);
         for (int c = 0; c < 2 * DIM; c++)
-          for (int r = 0; r < 2 * DIM; r++) H(i * DIM + r, i * DIM + c) += jtj(r, c);
-        for (int r = 0; r < 2 * DIM; r++) JacT[i * DIM + r] += gg[r];
+          for (int r2 = 0; r2 < 2 * DIM; r2++) H(i * DIM + r2, i * DIM + c) += jtj(r2, c);
+        for (int r2 = 0; r2 < 2 * DIM; r2++) JacT[i * DIM + r2] += gg[r2];
       }
       for (double& h : Hess) h *= imu_coef;
       for (double& j : JacT) j *= imu_coef;
       residual *= (imu_coef * 0.5);
       tr_us[0] += now_us() - t0;
-      set_poses(xs);
       double rl = 0;
       t0 = now_us();
-      int r = vina_ba_lidar_hessian(ctx, poses.data(), win, hl.data(), jl.data(), &rl);
+      r = vn_ba_hess_finish(ctx, win, hl.data(), jl.data(), &rl);
       if (r) return r;
       tr_us[1] += now_us() - t0;
       for (int a = 0; a < win; a++)  // hess_plus (optimizers.cpp:171-179)
@@ -653,7 +656,7 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
   }
   if (iters_out) *iters_out = iters;
   if (ctx->trace && (++tr_calls % 10) == 0)
-    fprintf(stderr, "[vina trace] BA, us per run over %d runs: imu jac %.1f, lidar hess (device) %.1f, solve %.1f, imu res %.1f, "
+    fprintf(stderr, "[vina trace] BA, us per run over %d runs: imu jac (device Hessian in flight) %.1f, wait for the device Hessian %.1f, solve %.1f, imu res %.1f, "
                     "lidar res (device) %.1f\n", tr_calls, tr_us[0] / tr_calls, tr_us[1] / tr_calls, tr_us[2] / tr_calls,
             tr_us[3] / tr_calls, tr_us[4] / tr_calls);
   return VINA_OK;
