@@ -1185,3 +1185,42 @@ def test_long_run_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     ng, no = gx.map_count(), od.map_count()
     assert ng[0] == no[0] and ng[2] == no[2], (ng, no)
     gx.close()
+
+
+def test_long_run_with_ba_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
+    """60 scans with the sliding-window BA every scan (52 BA runs, the window turning over six times, factor store
+    refilled every scan, IMU factors created and retired): trajectory within 1 mm / 0.01 deg of the oracle at every
+    scan, same BA / LM iteration counts throughout, same number of octree nodes at the end."""
+    cfg = small_cfg("hilti_xt32", 16, 300)
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)
+    gx = gpu_lib.Ctx(cfg, **SMALL_CAPS)
+    od.set_ba(True)
+    gx.set_ba(True)
+    for _ in range(cfg.win_size):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    od.set_imu_anchor(sc.end_time, sc.imu[-1])
+    gx.set_imu_anchor(sc.end_time, sc.imu[-1])
+    worst_p, worst_r, worst_gt = 0.0, 0.0, 0.0
+    for k in range(60):
+        sc = seq.next_scan()
+        imu = sc.imu.copy()
+        imu[:, 0] = np.round(imu[:, 0] * 1e9) * 1e-9
+        r, _ = od.step(sc.xyzt, sc.beg_time, imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        worst_p = max(worst_p, float(np.linalg.norm(sg["p"] - so["p"])))
+        worst_r = max(worst_r, synth.rot_err_deg(sg["R"], so["R"]))
+        worst_gt = max(worst_gt, float(np.linalg.norm(sg["p"] - sc.gt_p)))
+        assert gx.ba_stats() == od.ba_stats(), (k, gx.ba_stats(), od.ba_stats())
+    gx.sync()
+    assert od.ba_stats()[0] == 60 - 8
+    assert worst_p < 1e-3 and worst_r < 0.01, (worst_p, worst_r)
+    assert worst_gt < 0.03, worst_gt
+    ng, no = gx.map_count(), od.map_count()
+    assert ng[0] == no[0] and ng[2] == no[2], (ng, no)
+    gx.close()
+    od.close()
