@@ -666,15 +666,16 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (r) return r;
   r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
   if (r) return r;
+  // the IEKF launches go out first: they are on the critical path, the side stream has slack
+  const int num_max_iter = max_iter > 0 ? max_iter : 20;
+  r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
+  if (r) return r;
+  if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
   cudaStreamWaitEvent(B, ctx->ev_fork, 0);
   ctx->stream = B;
   r = vina_downsample(ctx);
   ctx->stream = A;
   if (r) return r;
-  const int num_max_iter = max_iter > 0 ? max_iter : 20;
-  r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
-  if (r) return r;
-  if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
   // the map's point set: the host needs the down-sampled count (and the "< 2000 points" retry,
   // local_mapping.cpp:396-403) - a wait on the side stream only, the IEKF keeps running
   ctx->stream = B;
