@@ -400,8 +400,10 @@ def main_ours(args, cfg):
                                           "(Hessian / residual over the plane voxels of the window) on the device"}}
                           if args.ba else {})},
             "e2e": {"value": pts_all / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K,
-                    "h2d_bytes_per_step": int(16 * n_mean + 17096),
-                    "d2h_bytes_per_step": int(iters_e2e / K * 34 * 8 + 4)},
+                    # scan (16 B / point) + pose table (DeskewPoses) + the iterate (IekfDev, 2 616 B) up; the
+                    # converged iterate + its sequence number + the down-sampled count back
+                    "h2d_bytes_per_step": int(16 * n_mean + 17096 + 2616),
+                    "d2h_bytes_per_step": 2616 + 8 + 4},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_iekf", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
