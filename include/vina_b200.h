@@ -344,6 +344,14 @@ int vina_get_timings(vina_ctx* ctx, vina_timings* t);
  * factor (frames from vina_odom_bootstrap have none). */
 int vina_odom_set_ba(vina_ctx* ctx, int on, double imu_coef);
 int vina_odom_ba_stats(vina_ctx* ctx, int32_t* runs, int32_t* last_iters);
+/* host-side pieces of the BA, stateless (no context, no device): one IMU pre-integration factor built from `m`
+ * IMU samples (IMU_PRE::push_imu, imu_preintegration.cpp:32-100) and evaluated between two states
+ * (give_evaluate, :102-163): residual r^T cov^-1 r, and - when jtj / gg are not null - J^T cov^-1 J (30 x 30,
+ * column-major) and J^T cov^-1 r (30); the symmetric solve of the LM step (lower triangle of A is read). */
+int vina_ba_imu_evaluate(const vina_config* cfg, const double bg[3], const double ba[3], const vina_imu* imus, int m,
+                         double scale_gravity, const vina_state* s1, const vina_state* s2, double* residual, double* jtj,
+                         double* gg);
+int vina_ba_solve(const double* A, int n, const double* b, double* x);
 int vina_ba_set_capture(vina_ctx* ctx, int on);
 int vina_ba_collect(vina_ctx* ctx, int32_t* n_factors);
 int vina_ba_count(vina_ctx* ctx, int32_t* n_factors);

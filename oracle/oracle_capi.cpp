@@ -469,6 +469,48 @@ int vo_odom_ba_residual(void* h, const double* poses12, int win, double* residua
     for (int a = 0; a < n && a < cap; a++) lam0[a] = o->ba_factors.eig_values[a][0];
   return 0;
 }
+// one IMU_PRE built from m samples and evaluated between two states (imu_preintegration.cpp:32-163)
+double vo_ba_imu_evaluate(const vo_config* cfg, const double bg[3], const double ba[3], const double* imu7, int m,
+                          double scale_gravity, const vo_state* s1, const vo_state* s2, double* jtj, double* gg)
+{
+  BaNoise nz;
+  for (int k = 0; k < 3; k++)
+  {
+    nz.noiseMeas(k, k) = cfg->cov_gyr;
+    nz.noiseMeas(3 + k, 3 + k) = cfg->cov_acc;
+    nz.noiseWalk(k, k) = cfg->rdw_gyr;
+    nz.noiseWalk(3 + k, 3 + k) = cfg->rdw_acc;
+  }
+  nz.scale_gravity = scale_gravity;
+  std::deque<ImuSample> buf;
+  for (int i = 0; i < m; i++)
+  {
+    ImuSample s;
+    s.t = imu7[7 * i];
+    for (int k = 0; k < 3; k++)
+    {
+      s.gyr[k] = imu7[7 * i + 1 + k];
+      s.acc[k] = imu7[7 * i + 4 + k];
+    }
+    buf.push_back(s);
+  }
+  IMU_PRE f(v3(bg), v3(ba));
+  f.push_imu(buf, nz);
+  IMUST a, b;
+  to_imust(s1, a);
+  to_imust(s2, b);
+  Mat<30, 30> J;
+  Mat<30, 1> g;
+  J.setZero();
+  g.setZero();
+  double r = f.give_evaluate(a, b, J, g, jtj != nullptr && gg != nullptr);
+  if (jtj && gg)
+  {
+    memcpy(jtj, J.d, sizeof(J.d));
+    memcpy(gg, g.d, sizeof(g.d));
+  }
+  return r;
+}
 void vo_odom_set_ba(void* h, int on, double imu_coef)
 {
   Odom* o = (Odom*)h;

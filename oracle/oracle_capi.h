@@ -102,6 +102,8 @@ int vo_odom_window(void* h, int* win_count, int* mp, int cap);
 /* the whole sliding-window BA (LI_BA_Optimizer::damping_iter, LiDAR + IMU pre-integration factors) inside
  * vo_odom_step, like local_mapping.cpp:492-497 with if_BA: 1. It runs once every pair of consecutive window frames
  * has an IMU factor (frames inserted by vo_odom_bootstrap have none). imu_coef <= 0 keeps LocalBA.imu_coef = 1e-4. */
+double vo_ba_imu_evaluate(const vo_config* cfg, const double bg[3], const double ba[3], const double* imu7, int m,
+                          double scale_gravity, const vo_state* s1, const vo_state* s2, double* jtj, double* gg);
 void vo_odom_set_ba(void* h, int on, double imu_coef);
 void vo_odom_ba_stats(void* h, int* runs, int* last_iters);
 void vo_odom_ba_probe(void* h, int on);

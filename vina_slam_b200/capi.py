@@ -74,6 +74,7 @@ EXPORTS = [
     "vina_shard_route_p2p", "vina_shard_insert_begin_p2p", "vina_odom_iekf_sharded_p2p",
     "vina_set_overlap", "vina_ba_set_capture", "vina_ba_collect", "vina_ba_count", "vina_ba_lidar_hessian",
     "vina_ba_lidar_residual", "vina_odom_set_ba", "vina_odom_ba_stats",
+    "vina_ba_imu_evaluate", "vina_ba_solve",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13

@@ -661,3 +661,34 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
             tr_us[3] / tr_calls, tr_us[4] / tr_calls);
   return VINA_OK;
 }
+
+// ---- stateless host entry points (no CUDA context needed): the CPU test-suite checks the host side of the BA
+// against the oracle with them
+extern "C" int vina_ba_imu_evaluate(const vina_config* cfg, const double bg[3], const double ba[3], const vina_imu* imus, int m,
+                                    double scale_gravity, const vina_state* s1, const vina_state* s2, double* residual,
+                                    double* jtj, double* gg)
+{
+  if (!cfg || !bg || !ba || !imus || m < 2 || !s1 || !s2 || !residual) return VINA_E_ARG;
+  std::deque<vina_imu> buf(imus, imus + m);
+  ImuPre f(bg, ba);
+  f.push_imu(buf, scale_gravity, *cfg);
+  HM<30, 30> J;
+  HM<30, 1> g;
+  if (jtj && gg)
+  {
+    *residual = f.evaluate(*s1, *s2, &J, &g);
+    memcpy(jtj, J.d, sizeof(J.d));
+    memcpy(gg, g.d, sizeof(g.d));
+  }
+  else
+    *residual = f.evaluate(*s1, *s2, nullptr, nullptr);
+  return VINA_OK;
+}
+
+extern "C" int vina_ba_solve(const double* A, int n, const double* b, double* x)
+{
+  if (!A || !b || !x || n < 1) return VINA_E_ARG;
+  std::vector<double> sol = ldlt_solve(std::vector<double>(A, A + (size_t)n * n), n, std::vector<double>(b, b + n));
+  memcpy(x, sol.data(), (size_t)n * sizeof(double));
+  return VINA_OK;
+}
