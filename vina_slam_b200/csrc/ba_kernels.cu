@@ -29,6 +29,25 @@ struct BaPoses
   PoseD x[VINA_MAX_WIN];
 };
 
+// Results go straight to mapped pinned host memory; the block that finishes last (atomic ticket) raises a sequence
+// number there, after a system-wide fence - the host polls it instead of paying a copy and a stream synchronisation
+// per evaluation (the LM loop makes four evaluations per iteration pair).
+__device__ __forceinline__ void ba_signal_done(const BaDone& d)
+{
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned int t = atomicAdd(d.ticket, 1u);
+    if (t == gridDim.x * gridDim.y - 1)
+    {
+      *d.ticket = 0u;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(d.flag) = d.seq;
+    }
+  }
+}
+
 __device__ __forceinline__ void cross3(const double* a, const double* b, double* c)
 {
   c[0] = a[1] * b[2] - a[2] * b[1];
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 // same bits for the same factor order.
 __global__ void __launch_bounds__(256)
     k_ba_reduce(const double* __restrict__ partial, int nwarps, int win, double* __restrict__ Hess, double* __restrict__ JacT,
-                double* __restrict__ residual)
+                double* __restrict__ residual, BaDone done)
 {
   __shared__ double part[8][33];
   const int el = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -315,35 +334,40 @@ __global__ void __launch_bounds__(256)
   }
   part[slice][el] = s;
   __syncthreads();
-  if (slice != 0 || e >= BA_ENTRIES) return;
-  s = ((part[0][el] + part[1][el]) + (part[2][el] + part[3][el])) + ((part[4][el] + part[5][el]) + (part[6][el] + part[7][el]));
-  if (e < 36 * BA_NPAIR)
+  if (slice == 0 && e < BA_ENTRIES)
   {
-    int q = e / 36, i = 0;
-    if (q >= npair) return;
-    const int r = (e % 36) % 6, c = (e % 36) / 6;
-    while (q >= win - i)
+    s = ((part[0][el] + part[1][el]) + (part[2][el] + part[3][el])) + ((part[4][el] + part[5][el]) + (part[6][el] + part[7][el]));
+    if (e < 36 * BA_NPAIR)
     {
-      q -= win - i;
-      i++;
+      int q = e / 36, i = 0;
+      if (q < npair)
+      {
+        const int r = (e % 36) % 6, c = (e % 36) / 6;
+        while (q >= win - i)
+        {
+          q -= win - i;
+          i++;
+        }
+        const int j = i + q;
+        Hess[(6 * i + r) + (size_t)dim * (6 * j + c)] = s;
+        if (i != j) Hess[(6 * j + c) + (size_t)dim * (6 * i + r)] = s;
+      }
     }
-    const int j = i + q;
-    Hess[(6 * i + r) + (size_t)dim * (6 * j + c)] = s;
-    if (i != j) Hess[(6 * j + c) + (size_t)dim * (6 * i + r)] = s;
+    else if (e < 36 * BA_NPAIR + 6 * VINA_MAX_WIN)
+    {
+      if ((e - 36 * BA_NPAIR) / 6 < win) JacT[e - 36 * BA_NPAIR] = s;
+    }
+    else
+      *residual = s;
   }
-  else if (e < 36 * BA_NPAIR + 6 * VINA_MAX_WIN)
-  {
-    if ((e - 36 * BA_NPAIR) / 6 < win) JacT[e - 36 * BA_NPAIR] = s;
-  }
-  else
-    *residual = s;
+  ba_signal_done(done);
 }
 
 // LidarFactor::evaluate_only_residual: thread per factor. The factor's eig / pcr_add are overwritten like in the
 // reference's container; lam0[a] = lambda_0 of factor a; block sums of coe * lambda_0 go to `partial`.
 __global__ void __launch_bounds__(128)
     k_ba_residual(BaFactor* __restrict__ fac, const int* __restrict__ n_ptr, BaPoses xs, int win, double* __restrict__ partial,
-                  double* __restrict__ lam0)
+                  double* __restrict__ lam0, BaDone done)
 {
   __shared__ double red[4];
   const int n = *n_ptr;
@@ -372,6 +396,7 @@ __global__ void __launch_bounds__(128)
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
   __syncthreads();
   if (threadIdx.x == 0) partial[blockIdx.x] = ((red[0] + red[1]) + red[2]) + red[3];
+  ba_signal_done(done);
 }
 
 // OctoTree::margi takes the factors' re-evaluated pcr_add / eig back into the leaves (octree.cpp:410-416)
@@ -397,7 +422,7 @@ int ba_hess_warps(int sm_count) { return sm_count * 2; }  // partial rows = bloc
 size_t ba_partial_doubles(int sm_count) { return (size_t)ba_hess_warps(sm_count) * BA_ENTRIES; }
 
 int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
-                   double* partial, double* d_out)
+                   double* partial, double* d_out, const BaDone& done)
 {
   BaPoses xs;
   memset(&xs, 0, sizeof(xs));
@@ -406,16 +431,16 @@ int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const
   k_ba_hess<<<blocks, BA_THREADS, 0, st>>>(fac, n_dev, xs, win, partial);
   const int dim = 6 * win;
   k_ba_reduce<<<(BA_ENTRIES + 31) / 32, 256, 0, st>>>(partial, blocks, win, d_out, d_out + (size_t)dim * dim,
-                                                      d_out + (size_t)dim * dim + dim);
+                                                      d_out + (size_t)dim * dim + dim, done);
   return 2;
 }
 
 int launch_ba_residual(cudaStream_t st, BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
-                       double* partial, double* lam0)
+                       double* partial, double* lam0, const BaDone& done)
 {
   BaPoses xs;
   memset(&xs, 0, sizeof(xs));
   for (int i = 0; i < win && i < VINA_MAX_WIN; i++) xs.x[i] = h_xs[i];
-  k_ba_residual<<<sm_count * 2, 128, 0, st>>>(fac, n_dev, xs, win, partial, lam0);
+  k_ba_residual<<<sm_count * 2, 128, 0, st>>>(fac, n_dev, xs, win, partial, lam0, done);
   return 1;
 }

@@ -304,6 +304,8 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(ctx->d_ba_out);
   cudaFree(ctx->d_ba_lam);
   cudaFreeHost(ctx->h_ba_out);
+  cudaFreeHost(ctx->h_ba_flag);
+  cudaFree(ctx->d_ba_ticket);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
   for (void* m : ctx->p2p_opened)
@@ -1253,8 +1255,14 @@ static int ensure_ba(vina_ctx* ctx)
   CU(dalloc(&ctx->d_ba_partial, ba_partial_doubles(ctx->sm_count), false));
   CU(dalloc(&ctx->d_ba_out, (size_t)36 * VINA_MAX_WIN * VINA_MAX_WIN + 6 * VINA_MAX_WIN + 8));
   CU(dalloc(&ctx->d_ba_lam, (size_t)cap, false));
+  // results are written by the kernels straight into mapped pinned memory, completion is a polled sequence number
   CU(cudaHostAlloc((void**)&ctx->h_ba_out, ((size_t)36 * VINA_MAX_WIN * VINA_MAX_WIN + 6 * VINA_MAX_WIN + 8 + 4096) * sizeof(double),
-                   cudaHostAllocDefault));
+                   cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_ba_map, ctx->h_ba_out, 0));
+  CU(cudaHostAlloc((void**)&ctx->h_ba_flag, 64, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_ba_flag, ctx->h_ba_flag, 0));
+  *ctx->h_ba_flag = 0ull;
+  CU(dalloc(&ctx->d_ba_ticket, 1));
   CU(cudaDeviceSynchronize());  // see ensure_debug
   ctx->ba_cap = (int)cap;
   return VINA_OK;
@@ -1306,28 +1314,48 @@ extern "C" int vina_ba_count(vina_ctx* ctx, int32_t* n_factors)
   return vn_check_status(ctx);
 }
 
+// wait for the completion flag of the last BA evaluation (mapped memory, polled; falls back to the stream state so
+// that a failed kernel is reported instead of spinning forever)
+static int ba_wait(vina_ctx* ctx, const char* what)
+{
+  volatile unsigned long long* flag = ctx->h_ba_flag;
+  const unsigned long long want = ctx->ba_seq;
+  for (long spins = 0; *flag != want; spins++)
+    if ((spins & 0xfff) == 0xfff)
+    {
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaSuccess)
+      {
+        if (*flag == want) break;
+        return vn_fail(ctx, VINA_E_CUDA, "%s finished without signalling", what);
+      }
+      if (e != cudaErrorNotReady) return vn_check_cuda(ctx, e, what);
+    }
+  __sync_synchronize();
+  return VINA_OK;
+}
+
 // the two halves of vina_ba_lidar_hessian: the host can do its own work (the IMU factors) while the kernels run
 int vn_ba_hess_enqueue(vina_ctx* ctx, const vina_pose* xs, int win)
 {
   if (!ctx->d_ba) return vn_fail(ctx, VINA_E_STATE, "no BA factors collected yet");
   if (win != ctx->cfg.win_size) return vn_fail(ctx, VINA_E_ARG, "win %d != LocalBA.win_size %d", win, ctx->cfg.win_size);
-  const size_t dim = 6 * (size_t)win;
   // (every entry of Hess / JacT / residual is written by k_ba_reduce: no clearing needed)
+  const BaDone done = { ctx->d_ba_ticket, ctx->d_ba_flag, ++ctx->ba_seq };
   ctx->launches += launch_ba_hess(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win, ctx->sm_count,
-                                  ctx->d_ba_partial, ctx->d_ba_out);
-  // pinned: the read-back is one asynchronous copy + one wait
-  CU(cudaMemcpyAsync(ctx->h_ba_out, ctx->d_ba_out, (dim * dim + dim + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  return VINA_OK;
+                                  ctx->d_ba_partial, ctx->d_ba_map, done);
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_hess");
 }
 int vn_ba_hess_finish(vina_ctx* ctx, int win, double* Hess, double* JacT, double* residual)
 {
   const size_t dim = 6 * (size_t)win;
-  CU(cudaStreamSynchronize(ctx->stream));
+  int r = ba_wait(ctx, "k_ba_hess");
+  if (r) return r;
   const double* h = ctx->h_ba_out;
   memcpy(Hess, h, dim * dim * sizeof(double));
   memcpy(JacT, h + dim * dim, dim * sizeof(double));
   *residual = h[dim * dim + dim];
-  return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_hess");
+  return VINA_OK;
 }
 
 extern "C" int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win, double* Hess, double* JacT,
@@ -1347,17 +1375,23 @@ extern "C" int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int wi
   int32_t n = 0;
   int r = vina_ba_count(ctx, &n);
   if (r) return r;
-  ctx->launches += launch_ba_residual(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win,
-                                      ctx->sm_count, ctx->d_ba_partial, ctx->d_ba_lam);
   const int nblk = ctx->sm_count * 2;
-  double* part = ctx->h_ba_out;  // pinned (nblk <= 4096)
-  CU(cudaMemcpyAsync(part, ctx->d_ba_partial, nblk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (lam0 && n > 0)
-    CU(cudaMemcpyAsync(lam0, ctx->d_ba_lam, (size_t)(n < cap ? n : cap) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  const BaDone done = { ctx->d_ba_ticket, ctx->d_ba_flag, ++ctx->ba_seq };
+  ctx->launches += launch_ba_residual(ctx->stream, ctx->d_ba, ctx->d_ba_n, reinterpret_cast<const PoseD*>(xs), win,
+                                      ctx->sm_count, ctx->d_ba_map, ctx->d_ba_lam, done);  // block sums -> mapped memory
+  r = vn_check_cuda(ctx, cudaGetLastError(), "k_ba_residual");
+  if (r) return r;
+  r = ba_wait(ctx, "k_ba_residual");
+  if (r) return r;
+  const double* part = ctx->h_ba_out;
   double s = 0.0;
   for (int b = 0; b < nblk; b++) s += part[b];  // block order: deterministic for a given factor order
   *residual = s;
+  if (lam0 && n > 0)
+  {
+    CU(cudaMemcpyAsync(lam0, ctx->d_ba_lam, (size_t)(n < cap ? n : cap) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_residual");
 }
 

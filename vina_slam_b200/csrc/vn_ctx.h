@@ -104,7 +104,12 @@ struct vina_ctx
   double* d_ba_partial = nullptr;
   double* d_ba_out = nullptr;   // Hess (6 win)^2, JacT (6 win), residual
   double* d_ba_lam = nullptr;
-  double* h_ba_out = nullptr;   // pinned read-back buffer
+  double* h_ba_out = nullptr;   // mapped pinned: the kernels write Hess / JacT / residual (or block sums) here
+  double* d_ba_map = nullptr;   // device alias of h_ba_out
+  unsigned long long* h_ba_flag = nullptr;  // mapped pinned completion sequence number
+  unsigned long long* d_ba_flag = nullptr;
+  unsigned int* d_ba_ticket = nullptr;
+  unsigned long long ba_seq = 0;
   bool ba_capture = false;   // vina_ba_set_capture: collect after every recut with a full window
   // profiling
   bool profiling = false;

@@ -158,14 +158,20 @@ int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, 
 int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
                      const IekfDev* live = nullptr);
 // BA LiDAR factor (map_kernels.cu: collect; ba_kernels.cu: Hessian / residual). d_out = Hess (6 win)^2, JacT, residual
+struct BaDone  // completion signal of a BA evaluation (ba_kernels.cu)
+{
+  unsigned int* ticket;        // device counter, zero between launches
+  unsigned long long* flag;    // mapped pinned host memory
+  unsigned long long seq;
+};
 int launch_ba_collect(cudaStream_t st, const MapView& map, const LayerLists& LL, BaFactor* out, int* count, int cap);
 int ba_hess_warps(int sm_count);
 size_t ba_partial_doubles(int sm_count);
 int launch_ba_hess(cudaStream_t st, const BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
-                   double* partial, double* d_out);
+                   double* partial, double* d_out, const BaDone& done);
 int launch_ba_writeback(cudaStream_t st, const MapView& map, const BaFactor* fac, const int* n_dev, int sm_count);
 int launch_ba_residual(cudaStream_t st, BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
-                       double* partial, double* lam0);
+                       double* partial, double* lam0, const BaDone& done);
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count);
 void launch_map_init(cudaStream_t st, const MapView& map, unsigned int nslots);
 
