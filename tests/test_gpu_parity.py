@@ -1224,3 +1224,21 @@ def test_long_run_with_ba_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     assert ng[0] == no[0] and ng[2] == no[2], (ng, no)
     gx.close()
     od.close()
+
+
+def test_replay_front_end(gpu_lib, tmp_path):
+    """vina_slam_b200.replay: a sequence through vina_odom_step, trajectory written in the reference's TUM format
+    (io.cpp:67-77), with and without the sliding-window BA."""
+    from vina_slam_b200 import replay
+
+    cfg = small_cfg("robosense128", 16, 300)
+    for ba in (False, True):
+        boots, scans = replay.synthetic_frames(cfg, 12)
+        out = str(tmp_path / f"traj_{int(ba)}.txt")
+        rows, dt, worst = replay.replay(cfg, boots, scans, out=out, ba=ba, caps=SMALL_CAPS)
+        assert rows.shape == (12, 8) and worst < 0.02 and dt > 0
+        lines = open(out).read().splitlines()
+        assert len(lines) == 12
+        vals = np.array([[float(v) for v in l.split()] for l in lines])
+        assert vals.shape == (12, 8) and np.max(np.abs(vals - rows)) < 1e-8
+        assert np.all(np.diff(vals[:, 0]) > 0) and np.allclose(np.linalg.norm(vals[:, 4:], axis=1), 1.0, atol=1e-8)

@@ -85,3 +85,37 @@ def test_replicas_world_size_2_gloo():
 def test_single_process_reduce_is_identity():
     tot, ts = replicas.reduce_throughput(10.0, [1.0, 2.0])
     assert tot == 10.0 and ts == [1.0, 2.0]
+
+
+def test_replay_tum_format_and_npz_reader(tmp_path):
+    """The file-replay front end's host logic (no GPU): TUM lines like FileReaderWriter::save_pose_tum
+    (io.cpp:67-77) and the recording reader."""
+    from vina_slam_b200 import replay
+
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        R = synth.rot_exp(rng.normal(0, 2.0, 3))
+        q = replay.quat_xyzw(R)
+        x, y, z, w = q
+        Rq = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert abs(np.linalg.norm(q) - 1) < 1e-12 and w >= 0 and np.max(np.abs(Rq - R)) < 1e-12
+    line = replay.tum_line(12.5, np.array([1.0, -2.0, 0.25]), np.eye(3))
+    assert line == "12.500000000 1.000000000 -2.000000000 0.250000000 0.000000000 0.000000000 0.000000000 1.000000000\n"
+    cfg = synth.small_sensor("robosense128", 4, 50)
+    seq = synth.Sequence(cfg)
+    boots = [seq.next_scan(deskewed=True) for _ in range(cfg.win_size)]
+    scans = [seq.next_scan() for _ in range(2)]
+    d = {}
+    for k, f in enumerate(boots + scans):
+        d[f"xyzt_{k}"], d[f"beg_{k}"], d[f"imu_{k}"] = f.xyzt, f.beg_time, f.imu
+    d["boot_R"] = np.array([f.gt_R for f in boots])
+    d["boot_p"] = np.array([f.gt_p for f in boots])
+    d["boot_v"] = np.array([f.gt_v for f in boots])
+    path = str(tmp_path / "rec.npz")
+    np.savez(path, **d)
+    b2, s2 = replay.npz_frames(path, cfg.win_size)
+    assert len(b2) == cfg.win_size and len(s2) == 2
+    assert np.array_equal(s2[0].xyzt, scans[0].xyzt) and s2[1].beg_time == scans[1].beg_time
+    assert np.array_equal(b2[3].gt_R, boots[3].gt_R) and abs(b2[-1].end_time - boots[-1].end_time) < 1e-6
