@@ -193,6 +193,15 @@ int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_buf);
 int vina_map_shift_window(vina_ctx* ctx);
 int64_t vina_map_count(vina_ctx* ctx, int64_t* n_roots, int64_t* n_slide);
 int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t cap);
+/* ---- map pruning behind the vehicle: the `else if (release_flag)` branch of the idle path of
+ * thd_odometry_localmapping (src/pipeline/local_mapping.cpp:317-341) with OctoTree::tras_ptr
+ * (src/mapping/octree.cpp:597-608). vina_map_set_journey sets the `jour` argument of multi_margi (:36, :507): the
+ * value the next vina_map_margi stamps into every root of surf_map_slide. vina_map_prune erases every root voxel
+ * (with its subtree) for which (int)(jour - root.jour) >= horizon; horizon <= 0 = the reference's 700 (metres of
+ * travel). Roots still in surf_map_slide are kept. The node ids and fixed-point chain blocks go back to the
+ * allocators, the hash table is rebuilt from the surviving roots and the fixed-point pool is compacted. */
+int vina_map_set_journey(vina_ctx* ctx, double jour);
+int vina_map_prune(vina_ctx* ctx, double jour, int horizon, int64_t* roots_erased, int64_t* nodes_freed);
 
 /* ---- map sharded by voxel-hash range over `world` ranks (one ctx per rank / GPU). A root voxel - and every
  * leaf below it - lives on rank owner(key) = floor(hash(key) * world / 2^32): cut_voxel_multi only ever
@@ -328,6 +337,11 @@ int vina_odom_iekf(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* 
 int vina_odom_iekf_host(vina_ctx* ctx, int which, int max_iter, int* iters_out, int* not_degenerate);
 int vina_odom_map_update(vina_ctx* ctx); /* pvec_update + insert + recut + (margi + shift) with x_curr */
 int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap);
+/* distance travelled (`jour`, `last_pos`, `release_flag`: local_mapping.cpp:262-263, 272, 509-519), kept by
+ * vina_odom_step / _step_resident / the batch step; and the idle path of the loop (:303-341), to be called when no
+ * scan is waiting: prunes the map (vina_map_prune with the current journey) if release_flag is set. */
+int vina_odom_journey(vina_ctx* ctx, double* jour, int* release_flag);
+int vina_odom_idle(vina_ctx* ctx, int horizon, int64_t* roots_erased, int64_t* nodes_freed);
 int vina_get_timings(vina_ctx* ctx, vina_timings* t);
 /* ---- sliding-window BA, the LiDAR factor (the data-parallel part of LI_BA_Optimizer::damping_iter,
  * src/mapping/optimizers.cpp:430-517; the IMU pre-integration factors and the LM loop are host work and not

@@ -530,4 +530,11 @@ int vo_odom_window(void* h, int* win_count, int* mp, int cap)
   for (int i = 0; i < o->G.win_size && i < cap; i++) mp[i] = o->G.mp[i];
   return o->G.win_size;
 }
+void vo_odom_journey(void* h, double* jour, int* release_flag)
+{
+  Odom* o = (Odom*)h;
+  if (jour) *jour = o->jour;
+  if (release_flag) *release_flag = o->release_flag ? 1 : 0;
+}
+int vo_odom_idle(void* h, int horizon, int* nodes_freed) { return ((Odom*)h)->idle_release(horizon, nodes_freed); }
 }

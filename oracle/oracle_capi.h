@@ -94,6 +94,11 @@ void vo_odom_map_update(void* h, int n, const double* pnt, const double* var);
 int64_t vo_odom_map_count(void* h, int64_t* n_roots, int64_t* n_slide);
 int64_t vo_odom_map_export(void* h, vo_node_record* out, int64_t cap);
 int vo_odom_window(void* h, int* win_count, int* mp, int cap);
+/* distance travelled / pruning of the map behind the vehicle (local_mapping.cpp:317-341, 509-519): the journey
+ * bookkeeping runs inside vo_odom_step; vo_odom_idle is the `release_flag` branch of the idle path with the
+ * reference's 700 m as a parameter. Returns the number of root voxels erased. */
+void vo_odom_journey(void* h, double* jour, int* release_flag);
+int vo_odom_idle(void* h, int horizon, int* nodes_freed);
 
 /* ---- BA probe (the data-parallel part): LidarFactor::acc_evaluate2 and
  * evaluate_only_residual (factors.cpp:22-158) on a copy of the LiDAR factors and window poses taken between

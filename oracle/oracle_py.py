@@ -291,6 +291,18 @@ class Odom:
         ws = self.lib.vo_odom_window(self.h, C.byref(wc), _ptr(mp, C.c_int), C.c_int(16))
         return wc.value, mp[:ws].copy()
 
+    def journey(self):
+        """(jour, release_flag) of the per-scan loop (local_mapping.cpp:509-519)."""
+        j, f = C.c_double(0), C.c_int(0)
+        self.lib.vo_odom_journey(self.h, C.byref(j), C.byref(f))
+        return j.value, bool(f.value)
+
+    def idle(self, horizon: int = 700):
+        """The `release_flag` branch of the idle path (local_mapping.cpp:317-341); (roots erased, nodes freed)."""
+        nf = C.c_int(0)
+        r = self.lib.vo_odom_idle(self.h, C.c_int(horizon), C.byref(nf))
+        return int(r), nf.value
+
     def set_ba(self, on: bool = True, imu_coef: float = 0.0):
         """if_BA (local_mapping.cpp:492-497): LI_BA_Optimizer after every recut with a full window."""
         self.lib.vo_odom_set_ba(self.h, C.c_int(1 if on else 0), C.c_double(imu_coef))

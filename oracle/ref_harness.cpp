@@ -58,6 +58,10 @@ struct RefOdom
   bool if_BA = false;
   deque<IMU_PRE*> imu_pre_buf;
   int ba_runs = 0, ba_last_iters = 0;
+  // locals of thd_odometry_localmapping (local_mapping.cpp:262-263, 272)
+  Eigen::Vector3d last_pos = Eigen::Vector3d(0, 0, 0);
+  double jour = 0.0;
+  bool release_flag = false;
   RefOdom(int win) : vs(nullptr), voxhess(win), normalFactor(win), ba_factors(win) {}
 
   // local_mapping.cpp:144-201 (the overload the per-scan loop calls, :451)
@@ -197,8 +201,18 @@ struct RefOdom
       vs.x_curr.R = vs.x_buf[vs.win_count - 1].R;
       vs.x_curr.p = vs.x_buf[vs.win_count - 1].p;
       double t5 = now_s();
-      multi_margi(vs.surf_map_slide, 0.0, vs.win_count, vs.x_buf, vs.sws[0]);
+      multi_margi(vs.surf_map_slide, jour, vs.win_count, vs.x_buf, vs.sws[0]);
       t_margi = now_s() - t5;
+      if ((vs.win_base + vs.win_count) % 10 == 0)  // local_mapping.cpp:509-519
+      {
+        double spat = (vs.x_curr.p - last_pos).norm();
+        if (spat > 0.5)
+        {
+          jour += spat;
+          last_pos = vs.x_curr.p;
+          release_flag = true;
+        }
+      }
       for (int i = 0; i < vs.win_size; i++)
       {
         mp[i] += mgsize;
@@ -221,6 +235,41 @@ struct RefOdom
       vs.win_base += mgsize;
       vs.win_count -= mgsize;
     }
+  }
+
+  // local_mapping.cpp:317-341, the `else if (release_flag)` branch of the idle path, with the 700 as a
+  // parameter; OctoTree::tras_ptr and the deletes are the reference's own. Roots still in surf_map_slide are
+  // kept (they would dangle there; unreachable with the reference's 700 m, see vina_oracle.cpp).
+  int idle_release(int horizon, int* nodes_freed)
+  {
+    if (nodes_freed) *nodes_freed = 0;
+    if (!release_flag) return 0;
+    release_flag = false;
+    auto& surf_map = vs.surf_map;
+    vector<OctoTree*> octos;
+    int roots = 0;
+    for (auto iter = surf_map.begin(); iter != surf_map.end();)
+    {
+      int dis = jour - iter->second->jour;
+      if (dis < horizon || vs.surf_map_slide.count(iter->first))
+      {
+        iter++;
+      }
+      else
+      {
+        octos.push_back(iter->second);
+        iter->second->tras_ptr(octos);
+        surf_map.erase(iter++);
+        roots++;
+      }
+    }
+    int ocsize = octos.size();
+    if (nodes_freed) *nodes_freed = ocsize;
+    for (int i = 0; i < ocsize; i++)
+    {
+      delete octos[i];
+    }
+    return roots;
   }
 
   void downsample(pcl::PointCloud<PointType>& pcl_curr, pcl::PointCloud<PointType>& pl_down)
@@ -718,4 +767,11 @@ int vo_odom_window(void* h, int* win_count, int* mpo, int cap)
   for (int i = 0; i < o->vs.win_size && i < cap; i++) mpo[i] = mp[i];
   return o->vs.win_size;
 }
+void vo_odom_journey(void* h, double* jour, int* release_flag)
+{
+  RefOdom* o = (RefOdom*)h;
+  if (jour) *jour = o->jour;
+  if (release_flag) *release_flag = o->release_flag ? 1 : 0;
+}
+int vo_odom_idle(void* h, int horizon, int* nodes_freed) { return ((RefOdom*)h)->idle_release(horizon, nodes_freed); }
 }

@@ -1141,6 +1141,7 @@ void Odom::multi_margi(VoxelMap& feat_map, int win_count, std::vector<IMUST>& xs
   int cnt = 0;
   for (auto iter = feat_map.begin(); iter != feat_map.end(); iter++)
   {
+    iter->second->jour = jour;  // local_mapping.cpp:36
     octs[cnt].push_back(iter->second);
     if (octs[cnt].size() >= part && cnt < thd_num - 1) cnt++;
   }
@@ -1236,6 +1237,17 @@ void Odom::map_update(PVecPtr pptr, std::deque<ImuSample>* imus)
     multi_margi(surf_map_slide, win_count, x_buf, sws[0]);
     t_margi = now_s() - t5;
 
+    if ((win_base + win_count) % 10 == 0)  // local_mapping.cpp:509-519
+    {
+      double spat = norm(x_curr.p - last_pos);
+      if (spat > 0.5)
+      {
+        jour += spat;
+        last_pos = x_curr.p;
+        release_flag = true;
+      }
+    }
+
     for (int i = 0; i < G.win_size; i++)
     {
       G.mp[i] += mgsize;
@@ -1258,6 +1270,48 @@ void Odom::map_update(PVecPtr pptr, std::deque<ImuSample>* imus)
     win_base += mgsize;
     win_count -= mgsize;
   }
+}
+
+// src/mapping/octree.cpp:597-608
+void Odom::tras_ptr(OctoTree* ot, std::vector<OctoTree*>& octos_release)
+{
+  if (ot->octo_state == 1)
+    for (int i = 0; i < 8; i++)
+      if (ot->leaves[i] != nullptr)
+      {
+        octos_release.push_back(ot->leaves[i]);
+        tras_ptr(ot->leaves[i], octos_release);
+      }
+}
+
+// src/pipeline/local_mapping.cpp:317-341
+int Odom::idle_release(int horizon, int* nodes_freed)
+{
+  if (nodes_freed) *nodes_freed = 0;
+  if (!release_flag) return 0;
+  release_flag = false;
+  std::vector<OctoTree*> octos;
+  int roots = 0;
+  for (auto iter = surf_map.begin(); iter != surf_map.end();)
+  {
+    int dis = jour - iter->second->jour;  // double -> int, truncation toward zero
+    if (dis < horizon || surf_map_slide.count(iter->first))  // (see below for the second condition)
+      iter++;
+    else
+    {
+      octos.push_back(iter->second);
+      tras_ptr(iter->second, octos);
+      surf_map.erase(iter++);
+      roots++;
+    }
+  }
+  if (nodes_freed) *nodes_freed = (int)octos.size();
+  // `delete octos[i]` (the reference's OctoTree has no destructor: the children are in the list themselves). A
+  // root that is still in surf_map_slide would dangle there - with the reference's 700 m horizon it cannot be
+  // (its stamp is at most one marginalisation old), with the small horizons the tests use it could: such roots
+  // are kept, here, in the reference harness and on the device alike.
+  for (OctoTree* o : octos) delete o;
+  return roots;
 }
 
 // src/pipeline/local_mapping.cpp:389-546

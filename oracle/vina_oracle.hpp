@@ -410,6 +410,10 @@ public:
   BaNoise ba_noise;
   std::deque<IMU_PRE*> imu_pre_buf;
   int ba_runs = 0, ba_last_iters = 0;
+  // distance travelled and map pruning (local_mapping.cpp:262-263, 272, 317-341, 509-519)
+  double jour = 0;
+  Vec3 last_pos = Vec3::Zero();
+  bool release_flag = false;
 
   explicit Odom(const Globals& g);
   ~Odom();
@@ -429,5 +433,10 @@ public:
   // harness bootstrap (replaces initialization()): deskewed scan
   // at a known state -> downsample, var_init, pvec_update, map_update.
   void bootstrap(Cloud& pcl_deskewed, const IMUST& x_known);
+  // the `else if (release_flag)` branch of the idle path, local_mapping.cpp:317-341: erase every root voxel (and
+  // its subtree) whose last marginalisation is `horizon` metres of travel or more behind (700 in the reference).
+  // Returns the number of roots erased, nodes_freed counts the subtrees' nodes too.
+  int idle_release(int horizon, int* nodes_freed);
+  void tras_ptr(OctoTree* ot, std::vector<OctoTree*>& octos_release);  // octree.cpp:597-608
 };
 }  // namespace vo

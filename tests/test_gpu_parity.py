@@ -1226,6 +1226,72 @@ def test_long_run_with_ba_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
     od.close()
 
 
+def test_map_pruning_matches_oracle(oracle_lib, gpu_lib):
+    """The idle path's map pruning (local_mapping.cpp:317-341, 509-519) with the 700 m horizon shrunk to 1 m so
+    that a 40-scan walk exercises it: same poses on both sides, the journey bookkeeping is compared exactly, every
+    pruning erases the same roots / nodes, and the WHOLE map is compared after each one and again after further
+    scans have re-used the released node ids, chain blocks and the compacted fixed-point pool."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg)
+    assert od.journey() == gx.journey()
+    prunings, erased = 0, 0
+    for k in range(40):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.set_state(gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        gx.down_upload(od.last_down())
+        gx.var_init(1)
+        gx.odom_map_update()
+        jo, jg = od.journey(), gx.journey()
+        assert jo == jg, (k, jo, jg)
+        flagged = jo[1]
+        ro, rg = od.idle(1), gx.idle(1)
+        assert ro == rg, (k, ro, rg)
+        assert od.journey() == gx.journey() and not gx.journey()[1]
+        if not flagged:
+            assert rg == (0, 0)
+        if rg[0] > 0:
+            prunings += 1
+            erased += rg[0]
+            co, cg = od.map_count(), gx.map_count()
+            assert co == cg, (k, co, cg)
+            _compare_maps(od.map_export(), gx.map_export())
+    assert prunings >= 2 and erased > 200, (prunings, erased)
+    _compare_maps(od.map_export(), gx.map_export())
+    assert od.map_count() == gx.map_count()
+    # a pruning with nothing stale leaves the map as it is; the reference's own horizon never fires on this walk
+    assert gx.map_prune(gx.journey()[0], 700) == (0, 0)
+    _compare_maps(od.map_export(), gx.map_export())
+    gx.close()
+
+
+def test_odometry_with_map_pruning_stays_on_the_oracle_trajectory(oracle_lib, gpu_lib):
+    """Full per-scan path (vina_odom_step) with the idle path called after every scan, 1 m horizon: the IEKF then
+    matches against a map whose hash table was rebuilt and whose nodes were recycled. Trajectory within 1 mm /
+    0.01 deg of the oracle, same prunings, same node / root / slide counts at the end."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, gpu_own_downsample=True)
+    worst_p, worst_r, erased = 0.0, 0.0, 0
+    for k in range(45):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        worst_p = max(worst_p, float(np.linalg.norm(sg["p"] - so["p"])))
+        worst_r = max(worst_r, synth.rot_err_deg(sg["R"], so["R"]))
+        jo, jg = od.journey(), gx.journey()
+        assert jo[1] == jg[1] and abs(jo[0] - jg[0]) < 1e-3, (k, jo, jg)
+        ro, rg = od.idle(1), gx.idle(1)
+        assert ro == rg, (k, ro, rg)
+        erased += rg[0]
+    gx.sync()
+    assert erased > 200, erased
+    assert worst_p < 1e-3 and worst_r < 0.01, (worst_p, worst_r)
+    assert od.map_count() == gx.map_count()
+    gx.close()
+
+
 def test_replay_front_end(gpu_lib, tmp_path):
     """vina_slam_b200.replay: a sequence through vina_odom_step, trajectory written in the reference's TUM format
     (io.cpp:67-77), with and without the sliding-window BA."""

@@ -89,6 +89,57 @@ def test_oracle_and_reference_side_by_side(oracle_lib):
         rf.close()
 
 
+def test_map_pruning_side_by_side(oracle_lib):
+    """Distance travelled + the idle path's map pruning (local_mapping.cpp:317-341, 509-519; OctoTree::tras_ptr,
+    octree.cpp:597-608): restatement and reference build side by side with the 700 m horizon shrunk to 1 m, the
+    idle path called after every scan. Journey, flag, erased roots / freed nodes, trajectory and the final map must
+    agree bit for bit; with the reference's own horizon nothing is erased on this walk."""
+    if not oracle_lib.have_ref():
+        pytest.skip("oracle/_ref is not built here (needs /root/reference)")
+    mod = _scenario()
+    cfg = synth.small_sensor("robosense128", 24, 350, seed=77)
+    seq = synth.Sequence(cfg)
+    od, rf = oracle_lib.Odom(cfg), oracle_lib.Odom(cfg, ref=True)
+    try:
+        for _ in range(cfg.win_size):
+            a = seq.next_scan(deskewed=True)
+            for o in (od, rf):
+                o.bootstrap(a.xyzt, oracle_lib.make_state(a.gt_R, a.gt_p, a.gt_v, t=a.end_time))
+        anchor = mod.quantise_imu(a.imu)[-1]
+        od.set_imu_anchor(a.end_time, anchor)
+        rf.set_imu_anchor(a.end_time, anchor)
+        assert od.journey() == rf.journey() and od.journey()[1]  # the last bootstrap frame marginalised
+        assert od.idle(700) == rf.idle(700) == (0, 0)
+        assert not od.journey()[1] and not rf.journey()[1]
+        prunings, erased, freed = 0, 0, 0
+        for k in range(32):
+            sc = seq.next_scan()
+            imu = mod.quantise_imu(sc.imu)
+            ro, _ = od.step(sc.xyzt, sc.beg_time, imu, True, 4)
+            rr, _ = rf.step(sc.xyzt, sc.beg_time, imu, True, 4)
+            assert ro == rr == 0
+            assert od.journey() == rf.journey(), k
+            io, ir = od.idle(1), rf.idle(1)
+            assert io == ir, (k, io, ir)
+            assert od.map_count() == rf.map_count(), k
+            if io[0]:
+                prunings += 1
+                erased += io[0]
+                freed += io[1]
+            so, sr = oracle_lib.state_arrays(od.get_state()), oracle_lib.state_arrays(rf.get_state())
+            for f in ("R", "p", "v", "cov"):
+                assert np.array_equal(so[f], sr[f]), f"state.{f} differs at step {k}"
+        assert prunings >= 2 and erased > 500 and freed >= erased, (prunings, erased, freed)
+        mo, mr = mod.sorted_map(od), mod.sorted_map(rf)
+        assert mo.shape == mr.shape
+        for f in mo.dtype.names:
+            if f not in ("eig_value", "eig_vector"):
+                assert np.array_equal(mo[f], mr[f]), f
+    finally:
+        od.close()
+        rf.close()
+
+
 def test_ba_lidar_factor_reproduces_reference(oracle_lib):
     """SURVEY section 8f rank 3, the LiDAR factor: the restated LidarFactor::acc_evaluate2 / evaluate_only_residual
     against the reference's own factors.cpp (golden vectors from oracle/_ref, tests/golden/ref_ba.npz; live side

@@ -75,6 +75,7 @@ EXPORTS = [
     "vina_set_overlap", "vina_ba_set_capture", "vina_ba_collect", "vina_ba_count", "vina_ba_lidar_hessian",
     "vina_ba_lidar_residual", "vina_odom_set_ba", "vina_odom_ba_stats",
     "vina_ba_imu_evaluate", "vina_ba_solve",
+    "vina_map_set_journey", "vina_map_prune", "vina_odom_journey", "vina_odom_idle",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -309,6 +310,29 @@ class Ctx:
         out = np.zeros(max(n, 1), dtype=NODE_DTYPE)
         k = self._ck(self.lib.vina_map_export(self.h, out.ctypes.data_as(C.c_void_p), C.c_int64(out.shape[0])))
         return out[:k]
+
+    # ---- map pruning behind the vehicle (local_mapping.cpp:317-341)
+    def map_set_journey(self, jour: float):
+        """The `jour` argument of multi_margi (local_mapping.cpp:36, 507) for the next map_margi."""
+        self._ck(self.lib.vina_map_set_journey(self.h, C.c_double(jour)))
+
+    def map_prune(self, jour: float, horizon: int = 700):
+        """Erase every root voxel with (int)(jour - root.jour) >= horizon; returns (roots erased, nodes freed)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.vina_map_prune(self.h, C.c_double(jour), C.c_int(horizon), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def journey(self):
+        """(jour, release_flag) of the per-scan loop (local_mapping.cpp:509-519)."""
+        j, f = C.c_double(0), C.c_int(0)
+        self._ck(self.lib.vina_odom_journey(self.h, C.byref(j), C.byref(f)))
+        return j.value, bool(f.value)
+
+    def idle(self, horizon: int = 700):
+        """The idle path of the loop (local_mapping.cpp:303-341): prune if release_flag is set."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.vina_odom_idle(self.h, C.c_int(horizon), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def map_recut(self, win_count: int, x_buf: np.ndarray):
         xb = np.ascontiguousarray(x_buf, dtype=POSE_DTYPE)

@@ -54,6 +54,13 @@ __device__ __forceinline__ int ld_volatile(const int* p) { return *((const volat
 
 __device__ int alloc_node(const MapView& M)
 {
+  // ids released by the pruning first (records are zero, like never-used pool memory)
+  if (ld_volatile(M.free_count) > 0)
+  {
+    const int k = atomicSub(M.free_count, 1);
+    if (k > 0) return M.free_nodes[k - 1];
+    atomicAdd(M.free_count, 1);
+  }
   int id = atomicAdd(M.node_count, 1);
   if (id >= M.max_nodes)
   {
@@ -615,7 +622,16 @@ __device__ int fix_append(const MapView& M, NodeCold& c, int cnt)
   }
   else
   {
-    int sid = atomicAdd(M.fixseg_cursor, 1);
+    int sid = -1;
+    if (ld_volatile(M.free_seg_count) > 0)
+    {
+      const int k = atomicSub(M.free_seg_count, 1);
+      if (k > 0)
+        sid = M.free_segs[k - 1];
+      else
+        atomicAdd(M.free_seg_count, 1);
+    }
+    if (sid < 0) sid = atomicAdd(M.fixseg_cursor, 1);
     if (sid >= M.fixseg_cap)
     {
       atomicOr(M.status, VN_ST_FIX_FULL);
@@ -1465,6 +1481,7 @@ __global__ void __launch_bounds__(128) k_margi_clear_compact(MapView M, LayerLis
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
   {
     const int root = M.slide_list[cur][j];
+    if (!early_out) M.cold[root].jour = M.jour;  // iter->second->jour = jour (local_mapping.cpp:36)
     if (early_out || M.cold[root].isexist)
     {
       int pos = atomicAdd(&M.slide_count[1 - cur], 1);
@@ -1491,6 +1508,11 @@ __global__ void __launch_bounds__(128) k_export(MapView M, vina_node_record* out
     const NodeHot& h = M.hot[n];
     const NodeCold& c = M.cold[n];
     vina_node_record& r = out[n];
+    if (h.layer < 0)
+    {
+      r.layer = -1;  // a record on the free stack (map pruning); vina_map_export drops these
+      continue;
+    }
     long long k3[3];
     unpack_key(c.rootkey, k3);
     for (int k = 0; k < 3; k++) r.key[k] = k3[k];
@@ -1548,6 +1570,156 @@ __global__ void k_map_init(MapView M, unsigned int nslots)
     M.slots[i].root = -2;
     M.slots[i].pad = 0;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Map pruning: the `else if (release_flag)` branch of the idle path of thd_odometry_localmapping
+// (local_mapping.cpp:317-341). A root voxel whose last multi_margi is `horizon` metres of travel or more behind
+// (700 in the reference) is erased from surf_map with its whole subtree (OctoTree::tras_ptr, octree.cpp:597-608).
+// On the device the subtree's records are zeroed (the state of never-used pool memory, which the allocators rely
+// on) and their ids pushed onto the free stack, the hash table is rebuilt from the surviving roots, and the
+// fixed-point pool is compacted: every live chain is copied, in order, into one contiguous segment.
+// counters: [0] roots erased [1] nodes freed [2] fixed points kept (cursor of the compacted pool).
+
+// phase 1: mark the stale roots. Roots still in surf_map_slide are kept (they cannot be stale with the reference's
+// horizon: their stamp is at most one marginalisation old; the oracle and the reference harness skip them too).
+__global__ void __launch_bounds__(256) k_prune_mark(MapView M, double jour, int horizon, int* __restrict__ counters)
+{
+  const int nn = min(*M.node_count, M.max_nodes);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += gridDim.x * blockDim.x)
+  {
+    NodeHot& h = M.hot[n];
+    if (h.layer != 0 || (h.flags & VN_FLAG_DEAD)) continue;
+    const NodeCold& c = M.cold[n];
+    if (c.root != n || c.in_slide) continue;
+    const int dis = (int)(jour - c.jour);  // int dis = jour - iter->second->jour (local_mapping.cpp:323)
+    if (dis < horizon) continue;
+    h.flags |= VN_FLAG_DEAD;
+    atomicAdd(&counters[0], 1);
+  }
+}
+
+__device__ __forceinline__ void push_free_seg(const MapView& M, int sid)
+{
+  const int k = atomicAdd(M.free_seg_count, 1);
+  M.free_segs[k] = sid;
+}
+
+// phase 2, one thread per node: a node under a marked root gives its chain blocks and its id back and is zeroed;
+// a surviving node with fixed points moves them to `tmp` (contiguous) and keeps one chain block.
+__global__ void __launch_bounds__(128) k_prune_sweep(MapView M, PointRec* __restrict__ tmp, int* __restrict__ counters)
+{
+  const int nn = min(*M.node_count, M.max_nodes);
+  constexpr int HOT_WORDS = sizeof(NodeHot) / 4, COLD_WORDS = sizeof(NodeCold) / 4;
+  constexpr int FLAGS_WORD = offsetof(NodeHot, flags) / 4, LAYER_WORD = offsetof(NodeHot, layer) / 4;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += gridDim.x * blockDim.x)
+  {
+    NodeHot& h = M.hot[n];
+    NodeCold& c = M.cold[n];
+    if (h.layer < 0) continue;  // already on the free stack
+    const int root = c.root;
+    if (M.hot[root].flags & VN_FLAG_DEAD)
+    {
+      for (int sg = c.fix_head; sg >= 0;)
+      {
+        const int nx = M.fix_segs[sg].next;
+        push_free_seg(M, sg);
+        sg = nx;
+      }
+      // the other threads of this subtree read hot[root].flags: that word is never written with anything but
+      // DEAD here
+      int* hw = reinterpret_cast<int*>(&h);
+      for (int w = 0; w < HOT_WORDS; w++)
+        if (w != FLAGS_WORD) hw[w] = (w == LAYER_WORD) ? -1 : 0;
+      if (n != root) h.flags = VN_FLAG_DEAD;
+      int* cw = reinterpret_cast<int*>(&c);
+      for (int w = 0; w < COLD_WORDS; w++) cw[w] = 0;
+      const int k = atomicAdd(M.free_count, 1);
+      M.free_nodes[k] = n;
+      atomicAdd(&counters[1], 1);
+      continue;
+    }
+    if (!tmp) continue;
+    if (c.fix_head < 0 || c.fix_count <= 0)
+    {
+      // (an empty chain keeps no block)
+      for (int sg = c.fix_head; sg >= 0;)
+      {
+        const int nx = M.fix_segs[sg].next;
+        push_free_seg(M, sg);
+        sg = nx;
+      }
+      c.fix_head = c.fix_tail = -1;
+      continue;
+    }
+    const int base = atomicAdd(&counters[2], c.fix_count);
+    int w = base;
+    const int head = c.fix_head;
+    for (int sg = head; sg >= 0;)
+    {
+      const FixSeg& blk = M.fix_segs[sg];
+      for (int e = 0; e < blk.n; e++)
+        for (int a = 0; a < blk.cnt[e]; a++) tmp[w++] = M.fix_pool[blk.off[e] + a];
+      const int nx = blk.next;
+      if (sg != head) push_free_seg(M, sg);
+      sg = nx;
+    }
+    FixSeg& hb = M.fix_segs[head];
+    hb.off[0] = base;
+    hb.cnt[0] = w - base;
+    hb.n = 1;
+    hb.next = -1;
+    c.fix_tail = head;
+  }
+}
+
+// phase 3 (after the table has been cleared): the surviving roots go back into the hash table
+__global__ void __launch_bounds__(256) k_prune_rehash(MapView M)
+{
+  const int nn = min(*M.node_count, M.max_nodes);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += gridDim.x * blockDim.x)
+  {
+    if (M.hot[n].layer != 0 || M.cold[n].root != n) continue;
+    const unsigned long long key = M.cold[n].rootkey;
+    unsigned int h = hash_key(key) & M.hmask;
+    for (unsigned int probe = 0; probe <= M.hmask; probe++)
+    {
+      if (atomicCAS(&M.slots[h].key, VN_EMPTY_KEY, key) == VN_EMPTY_KEY)
+      {
+        M.slots[h].root = n;
+        break;
+      }
+      h = (h + 1) & M.hmask;
+    }
+  }
+}
+
+// phase 4 (after the compacted points are back in the pool): root count and the pool's cursor
+__global__ void k_prune_finish(MapView M, const int* __restrict__ counters, int compacted)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    atomicSub(M.root_count, counters[0]);
+    if (compacted) *M.fix_cursor = counters[2];
+  }
+}
+
+void launch_map_prune_mark(cudaStream_t st, const MapView& map, double jour, int horizon, int* d_counters)
+{
+  cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), st);
+  k_prune_mark<<<592, 256, 0, st>>>(map, jour, horizon, d_counters);
+}
+
+void launch_map_prune_sweep(cudaStream_t st, const MapView& map, unsigned int nslots, PointRec* d_tmp, int* d_counters)
+{
+  k_prune_sweep<<<1184, 128, 0, st>>>(map, d_tmp, d_counters);
+  k_map_init<<<(nslots + 255) / 256, 256, 0, st>>>(map, nslots);
+  k_prune_rehash<<<592, 256, 0, st>>>(map);
+}
+
+void launch_map_prune_finish(cudaStream_t st, const MapView& map, const int* d_counters, int compacted)
+{
+  k_prune_finish<<<1, 32, 0, st>>>(map, d_counters, compacted);
 }
 
 // ---------------------------------------------------------------------------

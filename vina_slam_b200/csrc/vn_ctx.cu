@@ -202,6 +202,13 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&M.fix_segs, (size_t)M.fixseg_cap, false));
   CU(dalloc(&M.fix_cursor, 1));
   CU(dalloc(&M.fixseg_cursor, 1));
+  // free stacks of the map pruning (4 B per node / chain block)
+  CU(dalloc(&M.free_nodes, (size_t)cfg.max_nodes, false));
+  CU(dalloc(&M.free_count, 1));
+  CU(dalloc(&M.free_segs, (size_t)M.fixseg_cap, false));
+  CU(dalloc(&M.free_seg_count, 1));
+  CU(dalloc(&ctx->d_prune, 4));
+  M.jour = 0.0;
   CU(dalloc(&M.slide_list[0], (size_t)cfg.max_nodes));
   CU(dalloc(&M.slide_list[1], (size_t)cfg.max_nodes));
   CU(dalloc(&M.slide_count, 2));
@@ -334,6 +341,11 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(M.fix_segs);
   cudaFree(M.fix_cursor);
   cudaFree(M.fixseg_cursor);
+  cudaFree(M.free_nodes);
+  cudaFree(M.free_count);
+  cudaFree(M.free_segs);
+  cudaFree(M.free_seg_count);
+  cudaFree(ctx->d_prune);
   cudaFree(M.slide_list[0]);
   cudaFree(M.slide_list[1]);
   cudaFree(M.slide_count);
@@ -904,8 +916,10 @@ extern "C" int64_t vina_map_count(vina_ctx* ctx, int64_t* n_roots, int64_t* n_sl
   if (!ctx) return VINA_E_ARG;
   int r = vn_check_status(ctx);
   if (r) return r;
-  int nn = 0, sc[2] = { 0, 0 };
+  int nn = 0, nfree = 0, sc[2] = { 0, 0 };
   CU(cudaMemcpy(&nn, ctx->map.node_count, 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&nfree, ctx->map.free_count, 4, cudaMemcpyDeviceToHost));
+  if (nfree > 0) nn -= nfree;  // ids on the free stack of the map pruning
   CU(cudaMemcpy(sc, ctx->map.slide_count, 8, cudaMemcpyDeviceToHost));
   if (n_slide) *n_slide = sc[ctx->map.slide_cur];
   if (n_roots)
@@ -925,18 +939,89 @@ extern "C" int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t
   int nn = 0;
   CU(cudaMemcpy(&nn, ctx->map.node_count, 4, cudaMemcpyDeviceToHost));
   if (nn > ctx->map.max_nodes) nn = ctx->map.max_nodes;
-  if (cap < nn) return VINA_E_ARG;
   if (nn == 0) return 0;
+  int nfree = 0;
+  CU(cudaMemcpy(&nfree, ctx->map.free_count, 4, cudaMemcpyDeviceToHost));
+  if (nfree < 0) nfree = 0;
+  if (cap < nn - nfree) return VINA_E_ARG;
   vina_node_record* d_out = nullptr;
   long long* d_cnt = nullptr;
   CU(cudaMalloc((void**)&d_out, (size_t)nn * sizeof(vina_node_record)));
   CU(cudaMalloc((void**)&d_cnt, 8));
   launch_map_export(ctx->stream, ctx->map, d_out, nn, d_cnt);
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(out, d_out, (size_t)nn * sizeof(vina_node_record), cudaMemcpyDeviceToHost));
+  if (nfree == 0)
+    CU(cudaMemcpy(out, d_out, (size_t)nn * sizeof(vina_node_record), cudaMemcpyDeviceToHost));
+  else
+  {
+    // records on the free stack (layer == -1) are dropped
+    std::vector<vina_node_record> all((size_t)nn);
+    CU(cudaMemcpy(all.data(), d_out, (size_t)nn * sizeof(vina_node_record), cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    for (int i = 0; i < nn; i++)
+      if (all[i].layer >= 0)
+      {
+        if (k >= cap)
+        {
+          cudaFree(d_out);
+          cudaFree(d_cnt);
+          return VINA_E_ARG;
+        }
+        out[k++] = all[i];
+      }
+    nn = (int)k;
+  }
   cudaFree(d_out);
   cudaFree(d_cnt);
   return nn;
+}
+
+// ---------------------------------------------------------------------------
+// map pruning: the `else if (release_flag)` branch of the idle path (local_mapping.cpp:317-341)
+extern "C" int vina_map_set_journey(vina_ctx* ctx, double jour)
+{
+  if (!ctx) return VINA_E_ARG;
+  ctx->map.jour = jour;
+  return VINA_OK;
+}
+
+extern "C" int vina_map_prune(vina_ctx* ctx, double jour, int horizon, int64_t* roots_erased, int64_t* nodes_freed)
+{
+  if (!ctx) return VINA_E_ARG;
+  if (roots_erased) *roots_erased = 0;
+  if (nodes_freed) *nodes_freed = 0;
+  if (horizon <= 0) horizon = 700;
+  launch_map_prune_mark(ctx->stream, ctx->map, jour, horizon, ctx->d_prune);
+  ctx->launches += 1;
+  int cnt[4] = { 0, 0, 0, 0 }, cursor = 0;
+  CU(cudaMemcpyAsync(cnt, ctx->d_prune, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&cursor, ctx->map.fix_cursor, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int r = vn_check_status(ctx);
+  if (r) return r;
+  if (cnt[0] == 0) return VINA_OK;  // nothing is stale: the map is left exactly as it is
+  // scratch for the compaction of the fixed-point pool (an idle-time operation: a transient allocation of at
+  // most the pool's used part; without it the nodes and the hash slots are still given back)
+  PointRec* d_tmp = nullptr;
+  if (cursor > 0 && cudaMalloc((void**)&d_tmp, (size_t)cursor * sizeof(PointRec)) != cudaSuccess)
+  {
+    cudaGetLastError();
+    d_tmp = nullptr;
+  }
+  launch_map_prune_sweep(ctx->stream, ctx->map, ctx->hash_slots, d_tmp, ctx->d_prune);
+  ctx->launches += 3;
+  CU(cudaMemcpyAsync(cnt, ctx->d_prune, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (d_tmp && cnt[2] > 0)
+    CU(cudaMemcpyAsync(ctx->map.fix_pool, d_tmp, (size_t)cnt[2] * sizeof(PointRec), cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  launch_map_prune_finish(ctx->stream, ctx->map, ctx->d_prune, d_tmp ? 1 : 0);
+  ctx->launches += 1;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (d_tmp) cudaFree(d_tmp);
+  if (roots_erased) *roots_erased = cnt[0];
+  if (nodes_freed) *nodes_freed = cnt[1];
+  return vn_check_status(ctx);
 }
 
 // ---------------------------------------------------------------------------

@@ -70,6 +70,7 @@ struct vina_ctx
   InsertScratch ins;
   LayerLists layers;
   unsigned int hash_slots = 0;
+  int* d_prune = nullptr;  // counters of vina_map_prune
   int* d_status = nullptr;
   int* h_status = nullptr;  // pinned
   // hash-range sharding scratch (allocated on first use)

@@ -173,6 +173,11 @@ int launch_ba_writeback(cudaStream_t st, const MapView& map, const BaFactor* fac
 int launch_ba_residual(cudaStream_t st, BaFactor* fac, const int* n_dev, const PoseD* h_xs, int win, int sm_count,
                        double* partial, double* lam0, const BaDone& done);
 int launch_map_export(cudaStream_t st, const MapView& map, vina_node_record* d_out, long long cap, long long* d_count);
+// map pruning (local_mapping.cpp:317-341): mark stale roots -> [sync, read counters] -> sweep + hash rebuild ->
+// [copy the compacted fixed points back] -> finish. d_counters: 4 ints (roots erased, nodes freed, points kept).
+void launch_map_prune_mark(cudaStream_t st, const MapView& map, double jour, int horizon, int* d_counters);
+void launch_map_prune_sweep(cudaStream_t st, const MapView& map, unsigned int nslots, PointRec* d_tmp, int* d_counters);
+void launch_map_prune_finish(cudaStream_t st, const MapView& map, const int* d_counters, int compacted);
 void launch_map_init(cudaStream_t st, const MapView& map, unsigned int nslots);
 
 // per-layer node lists of the roots in surf_map_slide, rebuilt by every multi_recut and reused by the

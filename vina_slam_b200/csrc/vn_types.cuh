@@ -10,6 +10,7 @@
 
 #define VN_FLAG_PLANE 1     // Plane::is_plane
 #define VN_FLAG_INTERIOR 2  // octo_state == 1
+#define VN_FLAG_DEAD 4      // released by the map pruning (k_prune_*): the record is zero, layer == -1, id on the free stack
 #define VN_KEY_BIAS (1 << 20)
 #define VN_KEY_MASK ((1u << 21) - 1)
 #define VN_EMPTY_KEY 0ull
@@ -107,6 +108,7 @@ struct NodeCold
   int pend_cnt, pend_off;  // per-insert scratch: points of this scan landing in the leaf
   int touch_stamp, in_slide;
   int children[8];
+  double jour;  // OctoTree::jour of a root: distance travelled at its last multi_margi (local_mapping.cpp:36)
 };
 
 // One LiDAR BA factor = one entry of the reference's LidarFactor container (factors.hpp:10-40), filled by
@@ -178,6 +180,13 @@ struct MapView
   int* fixseg_cursor;   // segments
   long long fix_cap;
   int fixseg_cap;
+  // ids / chain blocks given back by the map pruning (local_mapping.cpp:317-341); the allocators pop these
+  // stacks before they bump node_count / fixseg_cursor. Only the pruning pushes, and never while an insert runs.
+  int* free_nodes;
+  int* free_count;
+  int* free_segs;
+  int* free_seg_count;
+  double jour;  // the value multi_margi stamps into the roots of surf_map_slide (local_mapping.cpp:36, 507)
   int* slide_list[2];
   int* slide_count;  // [2]
   int slide_cur;     // which of the two lists is surf_map_slide right now

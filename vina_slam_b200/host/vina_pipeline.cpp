@@ -114,6 +114,10 @@ struct OdomHost
   std::deque<vina_imu> ba_imus;         // the scan's IMU batch, ends re-stamped to the scan boundaries (imu_ekf.cpp:95-104)
   bool ba_imus_valid = false;
   int ba_runs = 0, ba_last_iters = 0;
+  // distance travelled / map pruning (local_mapping.cpp:262-263, 272, 317-341, 509-519)
+  double jour = 0.0;
+  double last_pos[3] = { 0, 0, 0 };
+  bool release_flag = false;
   ~OdomHost()
   {
     for (ImuPre* f : imu_pre_buf) ba_imu_factor_delete(f);
@@ -483,6 +487,20 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
 }
 
 // local_mapping.cpp:425-451 and 489-546
+// local_mapping.cpp:509-519, evaluated right after multi_margi with the window counters as they are there
+static void journey_update(OdomHost* o)
+{
+  if ((o->win_base + o->win_count) % 10 != 0) return;
+  const double d[3] = { o->x_curr.p[0] - o->last_pos[0], o->x_curr.p[1] - o->last_pos[1], o->x_curr.p[2] - o->last_pos[2] };
+  const double spat = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (spat > 0.5)
+  {
+    o->jour += spat;
+    memcpy(o->last_pos, o->x_curr.p, 24);
+    o->release_flag = true;
+  }
+}
+
 static int map_update(vina_ctx* ctx, OdomHost* o)
 {
   vina_state& x = o->x_curr;
@@ -546,8 +564,10 @@ static int map_update(vina_ctx* ctx, OdomHost* o)
     // x_curr.R/p = x_buf.back() (local_mapping.cpp:501-502): the identity without BA
     memcpy(x.R, o->x_buf.back().R, 72);
     memcpy(x.p, o->x_buf.back().p, 24);
+    ctx->map.jour = o->jour;  // multi_margi(surf_map_slide, jour, ...) (local_mapping.cpp:507)
     r = vina_map_margi(ctx, o->win_count, o->x_buf.data());
     if (r) return r;
+    journey_update(o);
     r = vina_map_shift_window(ctx);
     if (r) return r;
     o->x_buf.erase(o->x_buf.begin());
@@ -730,6 +750,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   }
   if (margi)
   {
+    ctx->map.jour = o->jour;  // (the journey only advances after multi_margi: known before the pose is)
     r = vn_map_margi_live(ctx, o->win_count, o->x_buf.data());
     if (r) return r;
     r = vina_map_shift_window(ctx);
@@ -766,6 +787,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   memcpy(o->x_buf.back().p, o->x_curr.p, 24);
   if (margi)
   {
+    journey_update(o);
     o->x_buf.erase(o->x_buf.begin());
     o->win_base += 1;
     o->win_count -= 1;
@@ -1163,6 +1185,26 @@ int vina_odom_map_update(vina_ctx* ctx)
 {
   if (!ctx) return VINA_E_ARG;
   return map_update(ctx, odom(ctx));
+}
+
+int vina_odom_journey(vina_ctx* ctx, double* jour, int* release_flag)
+{
+  if (!ctx) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  if (jour) *jour = o->jour;
+  if (release_flag) *release_flag = o->release_flag ? 1 : 0;
+  return VINA_OK;
+}
+
+int vina_odom_idle(vina_ctx* ctx, int horizon, int64_t* roots_erased, int64_t* nodes_freed)
+{
+  if (!ctx) return VINA_E_ARG;
+  if (roots_erased) *roots_erased = 0;
+  if (nodes_freed) *nodes_freed = 0;
+  OdomHost* o = odom(ctx);
+  if (!o->release_flag) return VINA_OK;
+  o->release_flag = false;
+  return vina_map_prune(ctx, o->jour, horizon, roots_erased, nodes_freed);
 }
 
 int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap)
