@@ -562,7 +562,8 @@ def main_bigmap(args, cfg):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     W, K = args.warmup, args.steps
-    boots, scans = gen_sequence(cfg, cfg.seed, cfg.win_size, W + K)
+    EXTRA = 5  # scans run after the pruning of the pre-filled map
+    boots, scans = gen_sequence(cfg, cfg.seed, cfg.win_size, W + K + EXTRA)
     n_vox = int(args.voxels)
     per_scan_vox, ppv = 10000, 25
     caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=int(n_vox * 1.15) + (1 << 20),
@@ -570,6 +571,14 @@ def main_bigmap(args, cfg):
                 fix_pool_points=int(n_vox * ppv * 1.1) + (16 << 20), device=0)
     stream = torch.cuda.current_stream(dev)
     out = {}
+    # one pruning on a throw-away context first: the first call in a process pays one-time costs (≈0.9 s measured:
+    # lazy loading of the pruning kernels, first cudaMalloc outside the pools) that are not the operation's
+    warm = capi.Ctx(cfg, max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=1 << 18, hash_capacity_log2=18,
+                    fix_pool_points=4 << 20, device=0)
+    for sc in boots:
+        warm.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    warm.map_prune(1e6, 700)
+    warm.close()
     for label, fill in (("empty", 0), ("filled", n_vox)):
         free0 = torch.cuda.mem_get_info(dev)[0]
         gx = capi.Ctx(cfg, **(caps if fill else dict(caps, max_nodes=1 << 20, hash_capacity_log2=21,
@@ -615,23 +624,41 @@ def main_bigmap(args, cfg):
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in scans]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in scans]
         err, rows = 0.0, []
+        prune = None
         for k, sc in enumerate(scans):
+            if k == W + K:
+                # the idle path's map pruning (local_mapping.cpp:317-341) with the journey advanced by 1000 m:
+                # everything that is not in the sliding window's map is 700 m or more behind and is erased. Wall
+                # clock around the call (it synchronises: mark -> sweep + hash rebuild -> pool compaction).
+                torch.cuda.synchronize(dev)
+                n_b, r_b, s_b = gx.map_count()
+                t0 = time.perf_counter()
+                er, fr = gx.map_prune(gx.journey()[0] + 1000.0, 700)
+                t_pr = time.perf_counter() - t0
+                n_a, r_a, _ = gx.map_count()
+                prune = {"ms": 1e3 * t_pr, "roots_erased": er, "nodes_freed": fr, "nodes_before": n_b,
+                         "roots_before": r_b, "nodes_after": n_a, "roots_after": r_a}
             flush.fill_(k & 0xFF)
             ev0[k].record(stream)
             st = gx.step_resident(d_scans[k].data_ptr(), sc.xyzt.shape[0], sc.beg_time, sc.end_time, sc.imu, True, MAX_ITER)
             ev1[k].record(stream)
-            if k >= W:
+            if W <= k < W + K:
                 rows.append(gx.timings())
                 err = max(err, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
+            elif k >= W + K:
+                prune["gt_traj_err_m_after"] = max(prune.get("gt_traj_err_m_after", 0.0),
+                                                   float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
         torch.cuda.synchronize(dev)
+        prune["ms_per_scan_after"] = float(np.mean([ev0[k].elapsed_time(ev1[k]) for k in range(W + K + 1, W + K + EXTRA)]))
+        prune["nodes_end"] = gx.map_count()[0]
         ms = float(np.mean([ev0[k].elapsed_time(ev1[k]) for k in range(W, W + K)]))
         stage = {f: float(np.mean([getattr(t, f) for t in rows])) for f in
                  ("iekf_ms", "insert_ms", "recut_ms", "margi_ms", "total_ms")}
-        n2, r2, s2 = gx.map_count()
+        n2, r2, s2 = n_b, r_b, s_b  # at the end of the timed scans, before the pruning
         out[label] = {"ms_per_scan": ms, "pts_per_s": cfg.n_points / (ms * 1e-3), "prefilled_root_voxels": roots,
                       "prefilled_nodes": nodes, "nodes_after": n2, "roots_after": r2, "slide_roots": s2,
                       "prefill_seconds": t_fill, "gt_traj_err_m": err, "stage_ms": stage,
-                      "device_memory_GB": (free0 - torch.cuda.mem_get_info(dev)[0]) / 1e9}
+                      "device_memory_GB": (free0 - torch.cuda.mem_get_info(dev)[0]) / 1e9, "prune": prune}
         gx.close()
         del d_scans, flush
         torch.cuda.empty_cache()

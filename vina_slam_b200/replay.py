@@ -83,8 +83,12 @@ def npz_frames(path: str, win_size: int):
     return boots, scans
 
 
-def replay(cfg, boots, scans, out=None, ba=False, max_iter=4, caps=None):
-    """Returns (trajectory rows (K, 8): t, p, q_xyzw; seconds per scan; worst position error vs ground truth or None)."""
+def replay(cfg, boots, scans, out=None, ba=False, max_iter=4, caps=None, prune_horizon=700, stats=None):
+    """Returns (trajectory rows (K, 8): t, p, q_xyzw; seconds per scan; worst position error vs ground truth or None).
+
+    After every scan the idle path of the reference's loop runs (local_mapping.cpp:303-341: a live system is idle
+    between two scans): when the vehicle has moved on, root voxels last marginalised `prune_horizon` metres of
+    travel ago are erased (700 in the reference; 0 = never). `stats`, if a dict, receives the totals."""
     caps = caps or dict(max_scan_points=max(300000, max(f.xyzt.shape[0] for f in boots + scans) + 1024))
     gx = capi.Ctx(cfg, **caps)  # raises without a CUDA device: there is no CPU path
     if ba:
@@ -93,6 +97,7 @@ def replay(cfg, boots, scans, out=None, ba=False, max_iter=4, caps=None):
         gx.bootstrap(f.xyzt, capi.make_state(f.gt_R, f.gt_p, f.gt_v, t=f.end_time))
     gx.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
     rows, worst = [], None
+    erased = freed = 0
     fh = open(out, "w") if out else None
     t0 = time.perf_counter()
     for f in scans:
@@ -103,7 +108,12 @@ def replay(cfg, boots, scans, out=None, ba=False, max_iter=4, caps=None):
         if f.gt_p is not None:
             e = float(np.linalg.norm(s["p"] - f.gt_p))
             worst = e if worst is None else max(worst, e)
+        if prune_horizon > 0:
+            a, b = gx.idle(prune_horizon)
+            erased, freed = erased + a, freed + b
     gx.sync()
+    if stats is not None:
+        stats.update(roots_erased=erased, nodes_freed=freed, journey=gx.journey()[0], map_count=gx.map_count())
     dt = (time.perf_counter() - t0) / max(len(scans), 1)
     if fh:
         fh.close()
@@ -119,11 +129,15 @@ def main(argv=None):
     ap.add_argument("--scans", type=int, default=30)
     ap.add_argument("--ba", action="store_true", help="LocalBA.if_BA: 1")
     ap.add_argument("--out", default=None, help="TUM trajectory file")
+    ap.add_argument("--prune-horizon", type=int, default=700,
+                    help="metres of travel after which unvisited root voxels are erased (reference: 700; 0 = never)")
     a = ap.parse_args(argv)
     cfg = synth.SENSORS[a.config or a.workload]
     boots, scans = npz_frames(a.npz, cfg.win_size) if a.npz else synthetic_frames(cfg, a.scans)
-    rows, dt, worst = replay(cfg, boots, scans, out=a.out, ba=a.ba)
+    st = {}
+    rows, dt, worst = replay(cfg, boots, scans, out=a.out, ba=a.ba, prune_horizon=a.prune_horizon, stats=st)
     msg = f"{len(rows)} scans, {1e3 * dt:.3f} ms/scan (wall clock, Python loop included)"
+    msg += f", journey {st['journey']:.1f} m, {st['roots_erased']} root voxels pruned"
     if worst is not None:
         msg += f", max |p - p_gt| = {worst:.4f} m"
     if a.out:
