@@ -514,6 +514,13 @@ def test_sharded_map_equals_single_gpu_map(oracle_lib, gpu_lib, world):
             assert np.all(np.diff(gi) > 0)
             sh.insert_finish(g_roots, g_slide)
             sh.recut_margi()
+        if k == cfg.win_size + 2:
+            # the idle path's pruning (1 m horizon), every rank on its own shard with the replicated journey: the
+            # shards erase, together, exactly the roots the single map erases; two more scans follow on the pruned maps
+            assert all((sh.jour, sh.release_flag) == single.journey() for sh in shards) and single.journey()[1]
+            es = single.idle(1)
+            ep = [sh.idle(1) for sh in shards]
+            assert es[0] > 20 and (sum(a for a, _ in ep), sum(b for _, b in ep)) == es, (es, ep)
     ms = sort_nodes(single.map_export())
     parts = [sh.ctx.map_export() for sh in shards]
     lib = gpu_lib.load()

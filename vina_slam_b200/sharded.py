@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import List, Sequence, Tuple
 
+import math
+
 import numpy as np
 
 from . import capi
@@ -84,8 +86,12 @@ class MapShard:
         if not own_stream:
             ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.win_count = 0
+        self.win_base = 0
         self.x_buf: List[Tuple[np.ndarray, np.ndarray]] = []
         self._send = None
+        # distance travelled / pruning (local_mapping.cpp:262-263, 272, 509-519): every rank sees every pose, so the
+        # bookkeeping is replicated and each rank prunes its own shard - no collective
+        self.jour, self.last_pos, self.release_flag = 0.0, (0.0, 0.0, 0.0), False
 
     # -- step 1
     def route(self, first: int, count: int, index_base: int, R_col, p, cov_rot_col, cov_tsl_col):
@@ -115,9 +121,26 @@ class MapShard:
             xb[i]["R"], xb[i]["p"] = R, p
         self.ctx.map_recut(self.win_count, xb)
         if self.win_count >= self.ctx.cfg.win_size:
+            self.ctx.map_set_journey(self.jour)  # the stamp of multi_margi (local_mapping.cpp:36, 507)
             self.ctx.map_margi(self.win_count, xb)
+            if (self.win_base + self.win_count) % 10 == 0:
+                p = [float(v) for v in self.x_buf[-1][1]]
+                d = [p[i] - self.last_pos[i] for i in range(3)]
+                spat = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+                if spat > 0.5:
+                    self.jour += spat
+                    self.last_pos = tuple(p)
+                    self.release_flag = True
             self.x_buf.pop(0)
+            self.win_base += 1
             self.win_count -= 1
+
+    def idle(self, horizon: int = 700):
+        """The idle path's map pruning on this rank's shard (local_mapping.cpp:317-341); (roots erased, nodes freed)."""
+        if not self.release_flag:
+            return 0, 0
+        self.release_flag = False
+        return self.ctx.map_prune(self.jour, horizon)
 
     # -- fused route + exchange over peer memory (NVLink): no staging, no collective call for the records
     def p2p_setup(self, inbox_records: int):
