@@ -149,6 +149,18 @@ int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n);
 int vina_scan_upload_device(vina_ctx* ctx, const void* d_xyzt, int n); /* same, from a DEVICE pointer */
 int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap); /* returns n or <0 */
+/* ---- scan front end, between the sensor driver and IMUEKF::process: the keep rule every decoder handler applies
+ * (src/sensor/lidar_pointcloud_decoder.cpp:70, 96, 161, 190: point i stays iff i % point_filter_num == 0 and
+ * x*x + y*y + z*z > blind2; blind2 = General.blind SQUARED as node.cpp:210 leaves it) and pcl_handler
+ * (src/sensor/lidar_decoder.cpp:16-34: two dummy points for an empty cloud, sort by time offset, cut at 0.11 s) on
+ * the device. xyzt = raw points in arrival order, any time order. The result (time-sorted; equal stamps keep their
+ * arrival order, which the reference's std::sort leaves unspecified) becomes the context's scan, like
+ * vina_scan_upload; n_out / t_last = its size and last time offset (one synchronisation). vina_odom_step_prepared
+ * is vina_odom_step on that scan. VINA_E_ARG if no kept point lies within 0.11 s. */
+int vina_scan_prepare(vina_ctx* ctx, const float* xyzt, int n, int point_filter_num, double blind2, int* n_out,
+                      float* t_last);
+int vina_scan_prepare_device(vina_ctx* ctx, const void* d_xyzt, int n, int point_filter_num, double blind2, int* n_out,
+                             float* t_last);
 
 /* ---- f1: down_sampling_voxel (include/vina_slam/core/point_utils.hpp:7-44) on
  * the device-resident scan, incl. the "<2000 points -> down_size/2" retry of
@@ -306,6 +318,8 @@ int vina_odom_bootstrap(vina_ctx* ctx, const float* xyzt, int n, const vina_stat
  * max_iter <= 0: the reference's 20 (plain variant); 4 = the VNC_lio budget. */
 int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time, const vina_imu* imus, int m,
                    int iekf_on_full, int max_iter, vina_state* x_out);
+int vina_odom_step_prepared(vina_ctx* ctx, double pcl_beg_time, const vina_imu* imus, int m, int iekf_on_full,
+                            int max_iter, vina_state* x_out);
 /* same scan, but the raw points are already in HBM: d_xyzt is a DEVICE pointer
  * (n x 4 float32) that is copied device-to-device into the ctx's scan buffer;
  * pcl_end_time = pcl_beg_time + curvature of the last point (sync.cpp:40),

@@ -1,4 +1,5 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (pinned against oracle/_ref, see vina_oracle.hpp).
+#include <algorithm>
 #include "oracle_capi.h"
 #include "vina_oracle.hpp"
 #include <cstring>
@@ -156,6 +157,37 @@ int vo_down_sampling_voxel(int n, const float* xyz4_in, double voxel_size, float
   down_sampling_voxel(c, voxel_size);
   from_cloud(c, xyz4_out);
   return (int)c.size();
+}
+
+// The scan front end between the sensor driver and IMUEKF::process: the keep rule every decoder handler applies
+// (src/sensor/lidar_pointcloud_decoder.cpp:70, 96, 161, 190: point i stays iff i % point_filter_num == 0 and
+// x*x + y*y + z*z > blind, float products compared with the double `blind`, which node.cpp:210 has already
+// squared) followed by pcl_handler (src/sensor/lidar_decoder.cpp:16-34): two dummy points for an empty cloud,
+// sort by time offset, drop the tail beyond 0.11 s. The reference's std::sort leaves the order of equal stamps
+// unspecified; this restatement (and the device) fix it as the arrival order (stable sort).
+// Returns the number of points written, or -1 where the reference would call back() on an empty cloud.
+int vo_scan_prepare(int n, const float* xyz4_in, int point_filter_num, double blind2, float* xyz4_out)
+{
+  struct P
+  {
+    float x, y, z, t;
+  };
+  std::vector<P> pl;
+  for (int i = 0; i < n; i++)
+  {
+    P pt = { xyz4_in[4 * i], xyz4_in[4 * i + 1], xyz4_in[4 * i + 2], xyz4_in[4 * i + 3] };
+    if ((i % point_filter_num) == 0 && (pt.x * pt.x + pt.y * pt.y + pt.z * pt.z) > blind2) pl.push_back(pt);
+  }
+  if (pl.empty())
+  {
+    pl.push_back({ 0, 0, 0, 0 });
+    pl.push_back({ 0, 0, 0, 0.09f });
+  }
+  std::stable_sort(pl.begin(), pl.end(), [](const P& a, const P& b) { return a.t < b.t; });
+  while (!pl.empty() && pl.back().t > 0.11) pl.pop_back();
+  if (pl.empty()) return -1;
+  memcpy(xyz4_out, pl.data(), pl.size() * sizeof(P));
+  return (int)pl.size();
 }
 
 void* vo_odom_create(const vo_config* cfg)

@@ -61,6 +61,9 @@ void vo_pvec_update(int n, const double* pnt, double* var, const double R[9], co
                     const double cov[225], double* pwld);
 void vo_voxel_keys(int n, const double* pw, double voxel_size, int64_t* keys);
 int vo_down_sampling_voxel(int n, const float* xyz4_in, double voxel_size, float* xyz4_out);
+/* decoder keep rule + pcl_handler (lidar_pointcloud_decoder.cpp:70; lidar_decoder.cpp:16-34): filter, stable sort by
+ * time offset, cut at 0.11 s; blind2 = General.blind squared (node.cpp:210). Returns the point count, -1 if none. */
+int vo_scan_prepare(int n, const float* xyz4_in, int point_filter_num, double blind2, float* xyz4_out);
 
 /* ---- per-sequence odometry (VINA_SLAM members of the per-scan loop) ---- */
 void* vo_odom_create(const vo_config* cfg);

@@ -1299,6 +1299,90 @@ def test_odometry_with_map_pruning_stays_on_the_oracle_trajectory(oracle_lib, gp
     gx.close()
 
 
+def test_scan_front_end_matches_oracle(oracle_lib, gpu_lib):
+    """vina_scan_prepare (decoder keep rule + pcl_handler on the device: filter, stable radix sort by time offset,
+    cut at 0.11 s) against the oracle's restatement, bit for bit including the order of equal stamps: many ties,
+    blind-zone points, decimation, stamps beyond the cut, negative stamps, sizes around the sort's tile, the empty
+    cloud's two-point stand-in, the error the reference cannot survive, and the device-pointer entry."""
+    import torch
+
+    cfg = small_cfg()
+    gx = gpu_lib.Ctx(cfg, **dict(SMALL_CAPS, max_scan_points=300000))
+    rng = np.random.default_rng(11)
+
+    def cloud(n, ties=True):
+        a = np.zeros((n, 4), dtype=np.float32)
+        a[:, :3] = rng.uniform(-30, 30, (n, 3))
+        a[::7, :3] *= 0.01
+        if ties:
+            a[:, 3] = rng.integers(0, 1300, n).astype(np.float32) * np.float32(1e-4)
+        else:
+            a[:, 3] = rng.uniform(-0.01, 0.12, n).astype(np.float32)
+        return a
+
+    for n, pfn, blind2, ties in ((50000, 1, 0.01, True), (50000, 3, 0.01, True), (240000, 2, 4.0, False),
+                                 (2048, 1, 0.01, True), (2049, 1, 0.01, False), (5, 1, 0.01, True), (1, 1, 0.01, True)):
+        a = cloud(n, ties)
+        if n <= 5:
+            a[:, :3] = 5.0
+            a[:, 3] = np.float32(0.05)
+        o = oracle_lib.scan_prepare(a, pfn, blind2)
+        k, tl = gx.scan_prepare(a, pfn, blind2)
+        g = gx.scan_download(k)
+        assert k == o.shape[0] and np.array_equal(g, o), (n, pfn, k, o.shape)
+        assert tl == o[-1, 3]
+    a = cloud(70000, False)
+    o = oracle_lib.scan_prepare(a, 2, 0.25)
+    d = torch.from_numpy(a).cuda()
+    k, tl = gx.scan_prepare(a.shape[0], 2, 0.25, d_ptr=d.data_ptr())
+    assert k == o.shape[0] and np.array_equal(gx.scan_download(k), o) and tl == o[-1, 3]
+    dummy = np.array([[0, 0, 0, 0], [0, 0, 0, 0.09]], dtype=np.float32)
+    near = cloud(3000)
+    near[:, :3] *= 1e-4
+    for b in (near, np.zeros((0, 4), dtype=np.float32)):
+        k, tl = gx.scan_prepare(b, 1, 0.01)
+        assert k == 2 and tl == np.float32(0.09) and np.array_equal(gx.scan_download(2), dummy)
+    late = cloud(3000)
+    late[:, 3] += np.float32(0.2)
+    with pytest.raises(gpu_lib.VinaError) as e:
+        gx.scan_prepare(late, 1, 0.01)
+    assert e.value.code == -1  # VINA_E_ARG
+    with pytest.raises(gpu_lib.VinaError):
+        gx.step_prepared(0.0, np.zeros((5, 7)))  # no prepared scan
+    gx.close()
+
+
+def test_odometry_from_unsorted_scans(oracle_lib, gpu_lib):
+    """Raw scans as a driver delivers them - shuffled in time, with blind-zone returns and stragglers beyond 0.11 s -
+    through vina_scan_prepare + vina_odom_step_prepared vs the oracle's front end + step: 1 mm / 0.01 deg."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, gpu_own_downsample=True)
+    rng = np.random.default_rng(3)
+    worst_p, worst_r = 0.0, 0.0
+    for k in range(6):
+        sc = seq.next_scan()
+        junk = np.zeros((500, 4), dtype=np.float32)
+        junk[:250, :3] = rng.uniform(-0.05, 0.05, (250, 3))          # inside the blind zone
+        junk[:250, 3] = rng.uniform(0, 0.09, 250)
+        junk[250:, :3] = rng.uniform(5, 20, (250, 3))                # stragglers
+        junk[250:, 3] = rng.uniform(0.111, 0.2, 250)
+        raw = np.concatenate([sc.xyzt, junk])[rng.permutation(sc.xyzt.shape[0] + 500)]
+        prep = oracle_lib.scan_prepare(raw, 1, 0.01)
+        assert prep.shape[0] == sc.xyzt.shape[0]
+        r, _ = od.step(prep, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        n, tl = gx.scan_prepare(raw, 1, 0.01)
+        assert n == prep.shape[0] and tl == prep[-1, 3]
+        sg = gpu_lib.state_arrays(gx.step_prepared(sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        worst_p = max(worst_p, float(np.linalg.norm(sg["p"] - so["p"])))
+        worst_r = max(worst_r, synth.rot_err_deg(sg["R"], so["R"]))
+        assert np.linalg.norm(sg["p"] - sc.gt_p) < 0.02
+    gx.sync()
+    assert worst_p < 1e-3 and worst_r < 0.01, (worst_p, worst_r)
+    gx.close()
+
+
 def test_replay_front_end(gpu_lib, tmp_path):
     """vina_slam_b200.replay: a sequence through vina_odom_step, trajectory written in the reference's TUM format
     (io.cpp:67-77), with and without the sliding-window BA."""

@@ -232,3 +232,40 @@ def test_golden_vectors(oracle_lib):
         assert np.array_equal(o[k], g[k]), k
     for k in ("deskewed", "it0_HTH", "it0_HTz", "it0_nnt", "state_R", "state_p", "traj", "map_eig"):
         assert np.allclose(o[k], g[k], rtol=1e-9, atol=1e-12), k
+
+
+def _scan_prepare_numpy(a, pfn, blind2):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 4)
+    x, y, z = a[:, 0], a[:, 1], a[:, 2]
+    r2 = (x * x + y * y) + z * z  # float32 products and sums, left to right
+    keep = (np.arange(a.shape[0]) % pfn == 0) & (r2.astype(np.float64) > blind2)
+    b = a[keep]
+    if b.shape[0] == 0:
+        b = np.array([[0, 0, 0, 0], [0, 0, 0, 0.09]], dtype=np.float32)
+    b = b[np.argsort(b[:, 3], kind="stable")]
+    b = b[~(b[:, 3].astype(np.float64) > 0.11)]
+    return b if b.shape[0] else None
+
+
+def test_scan_front_end_restatement(oracle_lib):
+    """Decoder keep rule + pcl_handler (lidar_pointcloud_decoder.cpp:70; lidar_decoder.cpp:16-34): the C++ restatement
+    against an independent numpy one - decimation, blind zone, stable time sort with many equal stamps, the 0.11 s
+    cut, the two-point stand-in for an empty cloud, and the case the reference cannot survive."""
+    rng = np.random.default_rng(11)
+    n = 50000
+    a = np.zeros((n, 4), dtype=np.float32)
+    a[:, :3] = rng.uniform(-30, 30, (n, 3))
+    a[::7, :3] *= 0.01  # inside the blind zone
+    a[:, 3] = rng.integers(0, 1300, n).astype(np.float32) * np.float32(1e-4)  # many ties, some beyond 0.11 s
+    for pfn, blind2 in ((1, 0.01), (3, 0.01), (2, 4.0)):
+        o, g = oracle_lib.scan_prepare(a, pfn, blind2), _scan_prepare_numpy(a, pfn, blind2)
+        assert o.shape == g.shape and o.shape[0] > 1000 and np.array_equal(o, g)
+        assert np.all(np.diff(o[:, 3]) >= 0) and o[-1, 3] <= np.float32(0.11)
+    near = a.copy()
+    near[:, :3] *= 1e-4
+    o = oracle_lib.scan_prepare(near, 1, 0.01)  # everything in the blind zone -> lidar_decoder.cpp:16-27
+    assert np.array_equal(o, np.array([[0, 0, 0, 0], [0, 0, 0, 0.09]], dtype=np.float32))
+    assert np.array_equal(oracle_lib.scan_prepare(np.zeros((0, 4), dtype=np.float32), 1, 0.01), o)
+    late = a.copy()
+    late[:, 3] += np.float32(0.2)
+    assert oracle_lib.scan_prepare(late, 1, 0.01) is None and _scan_prepare_numpy(late, 1, 0.01) is None

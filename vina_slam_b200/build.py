@@ -24,6 +24,7 @@ COMMON = (["-DVINA_SPLIT_TRACE"] if os.environ.get("VINA_SPLIT_TRACE") else []) 
 UNITS = [
     (os.path.join(CSRC, "scan_kernels.cu"), ["-fmad=false"]),
     (os.path.join(CSRC, "map_kernels.cu"), ["-fmad=false"]),
+    (os.path.join(CSRC, "front_kernels.cu"), ["-fmad=false"]),
     (os.path.join(CSRC, "shard_kernels.cu"), ["-fmad=false"]),
     (os.path.join(CSRC, "iekf_kernel.cu"), ["-DIEKF_THREADS=" + os.environ.get("VINA_IEKF_THREADS", "768"),
                                             "-DIEKF_BLOCKS_PER_SM=" + os.environ.get("VINA_IEKF_BLOCKS_PER_SM", "1")]),

@@ -76,6 +76,7 @@ EXPORTS = [
     "vina_ba_lidar_residual", "vina_odom_set_ba", "vina_odom_ba_stats",
     "vina_ba_imu_evaluate", "vina_ba_solve",
     "vina_map_set_journey", "vina_map_prune", "vina_odom_journey", "vina_odom_idle",
+    "vina_scan_prepare", "vina_scan_prepare_device", "vina_odom_step_prepared",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -240,6 +241,28 @@ class Ctx:
         a = np.zeros((n, 4), dtype=np.float32)
         k = self._ck(self.lib.vina_scan_download(self.h, _fp(a), C.c_int(n)))
         return a[:k]
+
+    def scan_prepare(self, xyzt: np.ndarray, point_filter_num: int, blind2: float, d_ptr: int = 0):
+        """Decoder keep rule + pcl_handler on the device (filter, stable sort by time offset, cut at 0.11 s); the
+        result becomes the context's scan. Returns (points, last time offset). d_ptr: raw points already in HBM."""
+        n, t = C.c_int(0), C.c_float(0)
+        if d_ptr:
+            self._ck(self.lib.vina_scan_prepare_device(self.h, C.c_void_p(d_ptr), C.c_int(int(xyzt)), C.c_int(point_filter_num),
+                                                       C.c_double(blind2), C.byref(n), C.byref(t)))
+        else:
+            a = np.ascontiguousarray(xyzt, dtype=np.float32).reshape(-1, 4)
+            self._ck(self.lib.vina_scan_prepare(self.h, _fp(a), C.c_int(a.shape[0]), C.c_int(point_filter_num),
+                                                C.c_double(blind2), C.byref(n), C.byref(t)))
+        return n.value, t.value
+
+    def step_prepared(self, beg_time: float, imu7: np.ndarray, iekf_on_full: bool = True, max_iter: int = 4):
+        """vina_odom_step on the scan left by scan_prepare."""
+        im = imu_array(np.asarray(imu7, dtype=np.float64))
+        out = VinaState()
+        self._ck(self.lib.vina_odom_step_prepared(self.h, C.c_double(beg_time), im.ctypes.data_as(C.c_void_p),
+                                                  C.c_int(im.shape[0]), C.c_int(1 if iekf_on_full else 0),
+                                                  C.c_int(max_iter), C.byref(out)))
+        return out
 
     def scan_upload_device(self, d_ptr: int, n: int):
         self._ck(self.lib.vina_scan_upload_device(self.h, C.c_void_p(d_ptr), C.c_int(n)))

@@ -341,6 +341,15 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(M.fix_segs);
   cudaFree(M.fix_cursor);
   cudaFree(M.fixseg_cursor);
+  cudaFree(ctx->d_raw);
+  for (int k = 0; k < 2; k++)
+  {
+    cudaFree(ctx->d_fkey[k]);
+    cudaFree(ctx->d_fidx[k]);
+  }
+  cudaFree(ctx->d_fhist);
+  cudaFree(ctx->d_fcnt);
+  if (ctx->h_fcnt) cudaFreeHost(ctx->h_fcnt);
   cudaFree(M.free_nodes);
   cudaFree(M.free_count);
   cudaFree(M.free_segs);
@@ -418,6 +427,7 @@ extern "C" int vina_scan_upload(vina_ctx* ctx, const float* xyzt, int n)
   CU(cudaEventRecord(ctx->ev_scan_up, ctx->copy_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan_up, 0));
   ctx->n_scan = n;
+  ctx->front_valid = false;
   return VINA_OK;
 }
 
@@ -428,6 +438,82 @@ extern "C" int vina_scan_upload_device(vina_ctx* ctx, const void* d_xyzt, int n)
   CU(cudaMemcpyAsync(ctx->d_scan, d_xyzt, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->n_scan = n;
   return VINA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// scan front end: decoder keep rule + pcl_handler (lidar_pointcloud_decoder.cpp:70; lidar_decoder.cpp:16-34)
+static int ensure_front(vina_ctx* ctx)
+{
+  if (ctx->d_fcnt) return VINA_OK;
+  const size_t cap = ctx->cap_points;
+  CU(dalloc(&ctx->d_raw, cap, false));
+  for (int k = 0; k < 2; k++)
+  {
+    CU(dalloc(&ctx->d_fkey[k], cap, false));
+    CU(dalloc(&ctx->d_fidx[k], cap, false));
+  }
+  CU(dalloc(&ctx->d_fhist, 256 * (cap / 2048 + 1)));
+  CU(dalloc(&ctx->d_fcnt, 4));
+  CU(cudaHostAlloc((void**)&ctx->h_fcnt, 4 * sizeof(int), cudaHostAllocDefault));
+  CU(cudaDeviceSynchronize());
+  return VINA_OK;
+}
+
+static int front_run(vina_ctx* ctx, const float4* d_raw, int n, int point_filter_num, double blind2, int* n_out,
+                     float* t_last)
+{
+  ctx->front_valid = false;
+  int kept = 0, keep = 0;
+  float tl = 0.f;
+  if (n > 0)
+  {
+    ctx->launches += launch_front_prepare(ctx->stream, d_raw, n, point_filter_num, blind2, ctx->d_fkey, ctx->d_fidx,
+                                          ctx->d_fhist, ctx->d_fcnt, ctx->d_scan, reinterpret_cast<float*>(ctx->d_fcnt + 2));
+    CU(cudaMemcpyAsync(ctx->h_fcnt, ctx->d_fcnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    kept = ctx->h_fcnt[0];
+    keep = ctx->h_fcnt[1];
+    memcpy(&tl, &ctx->h_fcnt[2], 4);
+  }
+  if (kept == 0)
+  {
+    // pcl_handler's stand-in for an empty cloud (lidar_decoder.cpp:16-27): two points at the origin, 0 s and 0.09 s
+    const float dummy[8] = { 0, 0, 0, 0, 0, 0, 0, 0.09f };
+    if (ctx->cap_points < 2) return vn_fail(ctx, VINA_E_CAPACITY, "max_scan_points < 2");
+    CU(cudaMemcpyAsync(ctx->d_scan, dummy, sizeof(dummy), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    keep = 2;
+    tl = 0.09f;
+  }
+  else if (keep == 0)
+    return vn_fail(ctx, VINA_E_ARG, "no point of the scan lies within 0.11 s (the reference pops an empty cloud here)");
+  ctx->n_scan = keep;
+  ctx->front_t_last = tl;
+  ctx->front_valid = true;
+  if (n_out) *n_out = keep;
+  if (t_last) *t_last = tl;
+  return VINA_OK;
+}
+
+extern "C" int vina_scan_prepare(vina_ctx* ctx, const float* xyzt, int n, int point_filter_num, double blind2, int* n_out,
+                                 float* t_last)
+{
+  if (!ctx || (!xyzt && n > 0) || n < 0 || point_filter_num < 1) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points %d", n, ctx->cap_points);
+  int r = ensure_front(ctx);
+  if (r) return r;
+  if (n > 0) CU(cudaMemcpyAsync(ctx->d_raw, xyzt, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  return front_run(ctx, ctx->d_raw, n, point_filter_num, blind2, n_out, t_last);
+}
+
+extern "C" int vina_scan_prepare_device(vina_ctx* ctx, const void* d_xyzt, int n, int point_filter_num, double blind2,
+                                        int* n_out, float* t_last)
+{
+  if (!ctx || (!d_xyzt && n > 0) || n < 0 || point_filter_num < 1) return VINA_E_ARG;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points %d", n, ctx->cap_points);
+  int r = ensure_front(ctx);
+  if (r) return r;
+  return front_run(ctx, reinterpret_cast<const float4*>(d_xyzt), n, point_filter_num, blind2, n_out, t_last);
 }
 
 extern "C" int vina_deskew(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9],

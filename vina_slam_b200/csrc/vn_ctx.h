@@ -32,6 +32,15 @@ struct vina_ctx
   bool cache_is_reset = false;  // the fused deskew + var_init kernel has just written -1 everywhere
   DeskewPoses* d_poses = nullptr;
   DeskewPoses* h_poses = nullptr;  // pinned
+  // scan front end (vina_scan_prepare; allocated on first use)
+  float4* d_raw = nullptr;
+  unsigned int* d_fkey[2] = { nullptr, nullptr };
+  int* d_fidx[2] = { nullptr, nullptr };
+  int* d_fhist = nullptr;
+  int* d_fcnt = nullptr;     // 2 counters + the last point's time offset
+  int* h_fcnt = nullptr;     // pinned copy
+  float front_t_last = 0.f;  // time offset of the last point of the prepared scan (pcl_end_time - pcl_beg_time)
+  bool front_valid = false;  // d_scan holds a scan made by vina_scan_prepare
   // down-sampling scratch
   DownSlot* d_dtab = nullptr;
   unsigned int dmask = 0;

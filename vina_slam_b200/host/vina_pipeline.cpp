@@ -1030,6 +1030,17 @@ int vina_odom_step_resident(vina_ctx* ctx, const void* d_xyzt, int n, double pcl
   return odom_step_resident(ctx, odom(ctx), pcl_beg_time, pcl_end_time, imus, m, iekf_on_full, max_iter, x_out);
 }
 
+int vina_odom_step_prepared(vina_ctx* ctx, double pcl_beg_time, const vina_imu* imus, int m, int iekf_on_full,
+                            int max_iter, vina_state* x_out)
+{
+  if (!ctx || !imus || m <= 0) return VINA_E_ARG;
+  if (!ctx->front_valid) return vn_fail(ctx, VINA_E_ARG, "vina_odom_step_prepared without a scan from vina_scan_prepare");
+  ctx->front_valid = false;
+  // pcl_end_time = pcl_beg_time + back().curvature (sync.cpp:40)
+  return odom_step_resident(ctx, odom(ctx), pcl_beg_time, pcl_beg_time + (double)ctx->front_t_last, imus, m, iekf_on_full,
+                            max_iter, x_out);
+}
+
 int vina_odom_propagate(vina_ctx* ctx, double pcl_beg_time, double pcl_end_time, const vina_imu* imus, int m,
                         vina_imu_pose* poses_out, int cap)
 {
