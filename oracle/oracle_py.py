@@ -405,10 +405,10 @@ def down_sampling_voxel(xyz4: np.ndarray, voxel_size: float, ref: bool = False) 
     return out[:n].copy()
 
 
-def scan_prepare(xyz4: np.ndarray, point_filter_num: int, blind2: float) -> np.ndarray:
+def scan_prepare(xyz4: np.ndarray, point_filter_num: int, blind2: float, fast: bool = False) -> np.ndarray:
     """Decoder keep rule + pcl_handler (filter, stable sort by time offset, cut at 0.11 s); None where the reference
     would be left with an empty cloud."""
-    lib = load()
+    lib = load(fast=fast)
     a = np.ascontiguousarray(xyz4, dtype=np.float32).reshape(-1, 4)
     out = np.zeros((max(a.shape[0], 2), 4), dtype=np.float32)
     n = lib.vo_scan_prepare(C.c_int(a.shape[0]), _fp(a), C.c_int(point_filter_num), C.c_double(blind2), _fp(out))
