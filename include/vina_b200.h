@@ -393,6 +393,25 @@ int vina_ba_count(vina_ctx* ctx, int32_t* n_factors);
 int vina_ba_lidar_hessian(vina_ctx* ctx, const vina_pose* xs, int win, double* Hess, double* JacT, double* residual);
 int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int win, double* residual, double* lam0, int cap);
 
+/* ---- pairing of scans and IMU samples in front of the step: the buffers of src/sensor/sync.cpp:5-16 and
+ * sync_packages (:18-96) as a host object (no device, no context; thread-safe like the reference's mBuf).
+ * push_imu = imu_handler (src/platform/ros2/subscribers.cpp:11-20); push_scan = the tail of pcl_handler
+ * (src/sensor/lidar_decoder.cpp:36-43): t_start = the message stamp, t_last = back().curvature of the prepared
+ * scan (vina_scan_prepare's t_last), tag = whatever identifies the scan for the caller. vina_sync_next =
+ * sync_packages: 1 = a package is ready (tag, pcl_beg_time, pcl_end_time, the m IMU samples up to pcl_end_time);
+ * 0 = the reference returns false and nothing was consumed (no scan, or the IMU stream has not passed the scan's
+ * end yet); 2 = the reference returns false and scan `tag` is gone (<= 4 IMU samples, or the first scan with
+ * point_notime); VINA_E_STATE = the IMU buffer ran dry (the reference exit(0)s, sync.cpp:79-82); VINA_E_CAPACITY =
+ * more samples than `cap`. point_notime != 0: scans without per-point time, frame interval as in sync.cpp:43-56. */
+typedef struct vina_sync vina_sync;
+int vina_sync_create(int point_notime, vina_sync** out);
+void vina_sync_destroy(vina_sync* s);
+int vina_sync_push_imu(vina_sync* s, const vina_imu* imu);
+int vina_sync_push_scan(vina_sync* s, double t_start, double t_last, int64_t tag);
+int vina_sync_pending(vina_sync* s, int32_t* scans, int32_t* imus);
+int vina_sync_next(vina_sync* s, int64_t* tag, double* pcl_beg_time, double* pcl_end_time, vina_imu* imus, int cap,
+                   int32_t* m);
+
 /* record per-stage CUDA-event timings (adds event records + one sync per step) */
 int vina_set_profiling(vina_ctx* ctx, int on);
 /* vina_odom_step / _step_resident schedule (default on): down-sampling and the var_init of the map's point set run

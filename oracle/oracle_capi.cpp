@@ -1,5 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (pinned against oracle/_ref, see vina_oracle.hpp).
 #include <algorithm>
+#include <deque>
+#include <vector>
 #include "oracle_capi.h"
 #include "vina_oracle.hpp"
 #include <cstring>
@@ -188,6 +190,99 @@ int vo_scan_prepare(int n, const float* xyz4_in, int point_filter_num, double bl
   if (pl.empty()) return -1;
   memcpy(xyz4_out, pl.data(), pl.size() * sizeof(P));
   return (int)pl.size();
+}
+
+// src/sensor/sync.cpp:5-96 restated with its globals (imu_buf, pcl_buf, time_buf, imu_last_time, point_notime,
+// last_pcl_time) and the function-local static pl_ready as members of one object; a scan is represented by
+// back().curvature and a tag. imu_handler = src/platform/ros2/subscribers.cpp:11-20, the scan push = the tail of
+// pcl_handler (src/sensor/lidar_decoder.cpp:36-43). Return of vo_sync_next: 1 = sync_packages returned true,
+// 0 = false with nothing consumed, 2 = false and the scan is gone, -6 = the reference exit(0)s (:79-82).
+namespace
+{
+struct SyncRef
+{
+  std::deque<ImuSample> imu_buf;
+  std::deque<std::pair<double, int64_t>> pcl_buf;  // (back().curvature, tag)
+  std::deque<double> time_buf;
+  double imu_last_time = -1;
+  int point_notime = 0;
+  double last_pcl_time = -1;
+  bool pl_ready = false;
+  std::pair<double, int64_t> pl;
+  double pcl_beg_time = 0, pcl_end_time = 0;
+};
+}  // namespace
+void* vo_sync_create(int point_notime)
+{
+  SyncRef* s = new SyncRef();
+  s->point_notime = point_notime;
+  return s;
+}
+void vo_sync_destroy(void* h) { delete (SyncRef*)h; }
+void vo_sync_push_imu(void* h, const double imu7[7])
+{
+  SyncRef* s = (SyncRef*)h;
+  ImuSample m;
+  m.t = imu7[0];
+  for (int k = 0; k < 3; k++) m.gyr[k] = imu7[1 + k], m.acc[k] = imu7[4 + k];
+  s->imu_last_time = m.t;
+  s->imu_buf.push_back(m);
+}
+void vo_sync_push_scan(void* h, double t_start, double t_last, int64_t tag)
+{
+  SyncRef* s = (SyncRef*)h;
+  s->time_buf.push_back(t_start);
+  s->pcl_buf.push_back({ t_last, tag });
+}
+int vo_sync_next(void* h, int64_t* tag, double* beg, double* end, double* imu7, int cap, int* m)
+{
+  SyncRef* s = (SyncRef*)h;
+  *m = 0;
+  if (!s->pl_ready)
+  {
+    if (s->pcl_buf.empty()) return 0;
+    s->pl = s->pcl_buf.front();
+    s->pcl_buf.pop_front();
+    s->pcl_beg_time = s->time_buf.front();
+    s->time_buf.pop_front();
+    s->pcl_end_time = s->pcl_beg_time + s->pl.first;
+    if (s->point_notime)
+    {
+      if (s->last_pcl_time < 0)
+      {
+        s->last_pcl_time = s->pcl_beg_time;
+        *tag = s->pl.second;
+        return 2;
+      }
+      s->pcl_end_time = s->pcl_beg_time;
+      s->pcl_beg_time = s->last_pcl_time;
+      s->last_pcl_time = s->pcl_end_time;
+    }
+    s->pl_ready = true;
+  }
+  if (!s->pl_ready || s->imu_last_time <= s->pcl_end_time) return 0;
+  std::vector<ImuSample> imus;
+  double imu_time = s->imu_buf.front().t;
+  while ((!s->imu_buf.empty()) && (imu_time < s->pcl_end_time))
+  {
+    imu_time = s->imu_buf.front().t;
+    if (imu_time > s->pcl_end_time) break;
+    imus.push_back(s->imu_buf.front());
+    s->imu_buf.pop_front();
+  }
+  *tag = s->pl.second;
+  *beg = s->pcl_beg_time;
+  *end = s->pcl_end_time;
+  s->pl_ready = false;
+  if (s->imu_buf.empty()) return -6;
+  if ((int)imus.size() > cap) return -3;
+  for (size_t i = 0; i < imus.size(); i++)
+  {
+    imu7[7 * i] = imus[i].t;
+    for (int k = 0; k < 3; k++) imu7[7 * i + 1 + k] = imus[i].gyr[k], imu7[7 * i + 4 + k] = imus[i].acc[k];
+  }
+  *m = (int)imus.size();
+  return imus.size() > 4 ? 1 : 2;
 }
 
 void* vo_odom_create(const vo_config* cfg)

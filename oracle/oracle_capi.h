@@ -65,6 +65,15 @@ int vo_down_sampling_voxel(int n, const float* xyz4_in, double voxel_size, float
  * time offset, cut at 0.11 s; blind2 = General.blind squared (node.cpp:210). Returns the point count, -1 if none. */
 int vo_scan_prepare(int n, const float* xyz4_in, int point_filter_num, double blind2, float* xyz4_out);
 
+/* ---- sync_packages and its buffers (src/sensor/sync.cpp:5-96; imu_handler subscribers.cpp:11-20; the tail of
+ * pcl_handler lidar_decoder.cpp:36-43). vo_sync_next: 1 = true, 0 = false / nothing consumed, 2 = false / scan gone,
+ * -6 = the reference exit(0)s, -3 = more IMU samples than cap. */
+void* vo_sync_create(int point_notime);
+void vo_sync_destroy(void* h);
+void vo_sync_push_imu(void* h, const double imu7[7]);
+void vo_sync_push_scan(void* h, double t_start, double t_last, int64_t tag);
+int vo_sync_next(void* h, int64_t* tag, double* beg, double* end, double* imu7, int cap, int* m);
+
 /* ---- per-sequence odometry (VINA_SLAM members of the per-scan loop) ---- */
 void* vo_odom_create(const vo_config* cfg);
 void vo_odom_destroy(void* h);

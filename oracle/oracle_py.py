@@ -101,6 +101,12 @@ def load(fast: bool = False, ref: bool = False):
                "vo_odom_map_update", "vo_odom_set_ba", "vo_odom_ba_stats", "vo_odom_ba_probe"):
         if hasattr(lib, fn):
             getattr(lib, fn).restype = None
+    if hasattr(lib, "vo_sync_create"):
+        lib.vo_sync_create.restype = C.c_void_p
+        lib.vo_sync_destroy.restype = None
+        lib.vo_sync_destroy.argtypes = [C.c_void_p]
+        lib.vo_sync_push_imu.restype = None
+        lib.vo_sync_push_scan.restype = None
     lib.vo_odom_map_count.restype = C.c_int64
     lib.vo_odom_map_export.restype = C.c_int64
     _LIBS[name] = lib
@@ -403,6 +409,33 @@ def down_sampling_voxel(xyz4: np.ndarray, voxel_size: float, ref: bool = False) 
     out = np.zeros_like(a)
     n = lib.vo_down_sampling_voxel(C.c_int(a.shape[0]), _fp(a), C.c_double(voxel_size), _fp(out))
     return out[:n].copy()
+
+
+class Sync:
+    """sync_packages and its buffers (src/sensor/sync.cpp:5-96)."""
+
+    def __init__(self, point_notime: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p(self.lib.vo_sync_create(C.c_int(point_notime)))
+
+    def close(self):
+        if self.h:
+            self.lib.vo_sync_destroy(self.h)
+            self.h = None
+
+    def push_imu(self, imu7):
+        a = np.ascontiguousarray(imu7, dtype=np.float64)
+        self.lib.vo_sync_push_imu(self.h, _dp(a))
+
+    def push_scan(self, t_start: float, t_last: float, tag: int):
+        self.lib.vo_sync_push_scan(self.h, C.c_double(t_start), C.c_double(t_last), C.c_int64(tag))
+
+    def next(self, cap: int = 256):
+        """(code, tag, beg, end, imu7[m, 7])"""
+        tag, beg, end, m = C.c_int64(-1), C.c_double(0), C.c_double(0), C.c_int(0)
+        buf = np.zeros((cap, 7), dtype=np.float64)
+        r = self.lib.vo_sync_next(self.h, C.byref(tag), C.byref(beg), C.byref(end), _dp(buf), C.c_int(cap), C.byref(m))
+        return r, tag.value, beg.value, end.value, buf[:m.value].copy()
 
 
 def scan_prepare(xyz4: np.ndarray, point_filter_num: int, blind2: float, fast: bool = False) -> np.ndarray:

@@ -77,6 +77,8 @@ EXPORTS = [
     "vina_ba_imu_evaluate", "vina_ba_solve",
     "vina_map_set_journey", "vina_map_prune", "vina_odom_journey", "vina_odom_idle",
     "vina_scan_prepare", "vina_scan_prepare_device", "vina_odom_step_prepared",
+    "vina_sync_create", "vina_sync_destroy", "vina_sync_push_imu", "vina_sync_push_scan", "vina_sync_pending",
+    "vina_sync_next",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -105,6 +107,8 @@ def load():
     lib.vina_ctx_destroy.restype = None
     lib.vina_batch_destroy.restype = None
     lib.vina_config_default.restype = None
+    lib.vina_sync_destroy.restype = None
+    lib.vina_sync_destroy.argtypes = [C.c_void_p]
     lib.vina_map_count.restype = C.c_int64
     lib.vina_map_export.restype = C.c_int64
     _LIB = lib
@@ -553,6 +557,50 @@ class Ctx:
         mp = np.zeros(16, dtype=np.int32)
         ws = self._ck(self.lib.vina_odom_window(self.h, C.byref(wc), mp.ctypes.data_as(C.c_void_p), C.c_int(16)))
         return wc.value, mp[:ws].copy()
+
+
+class Sync:
+    """Pairing of scans and IMU samples (vina_sync_*: sync_packages and its buffers, src/sensor/sync.cpp:5-96).
+    Host-only: works without a CUDA device."""
+
+    def __init__(self, point_notime: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        r = self.lib.vina_sync_create(C.c_int(point_notime), C.byref(h))
+        if r:
+            raise VinaError(r, "vina_sync_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.vina_sync_destroy(self.h)
+            self.h = None
+
+    def push_imu(self, imu7):
+        im = imu_array(np.asarray(imu7, dtype=np.float64).reshape(1, 7))
+        r = self.lib.vina_sync_push_imu(self.h, im.ctypes.data_as(C.c_void_p))
+        if r:
+            raise VinaError(r, "vina_sync_push_imu")
+
+    def push_scan(self, t_start: float, t_last: float, tag: int):
+        r = self.lib.vina_sync_push_scan(self.h, C.c_double(t_start), C.c_double(t_last), C.c_int64(tag))
+        if r:
+            raise VinaError(r, "vina_sync_push_scan")
+
+    def pending(self):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self.lib.vina_sync_pending(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def next(self, cap: int = 256):
+        """(code, tag, beg, end, imu7[m, 7]); code as vina_sync_next returns it (negative = VINA_E_*)."""
+        tag, beg, end, m = C.c_int64(-1), C.c_double(0), C.c_double(0), C.c_int32(0)
+        buf = np.zeros(max(cap, 1), dtype=IMU_DTYPE)
+        r = self.lib.vina_sync_next(self.h, C.byref(tag), C.byref(beg), C.byref(end), buf.ctypes.data_as(C.c_void_p),
+                                    C.c_int(cap), C.byref(m))
+        out = np.zeros((m.value, 7), dtype=np.float64)
+        out[:, 0], out[:, 1:4], out[:, 4:7] = buf["t"][:m.value], buf["gyr"][:m.value], buf["acc"][:m.value]
+        return r, tag.value, beg.value, end.value, out
 
 
 class Batch:

@@ -83,6 +83,83 @@ def npz_frames(path: str, win_size: int):
     return boots, scans
 
 
+def stream_packages(scans, point_notime: int = 0, t_last_of=None):
+    """The scans and their IMU samples as the two message streams a live system sees - every IMU sample arrives at
+    its stamp, a scan when it is complete - paired by `vina_sync` (sync_packages, src/sensor/sync.cpp:18-96; host
+    only). Yields (index into scans, pcl_beg_time, pcl_end_time, imu (m, 7)) for every package; the last scan of the
+    list stays pending (its package closes with the first IMU sample after its end, sync.cpp:60-63).
+    t_last_of(k) = back().curvature of scan k once prepared (default: of the scan as given)."""
+    sync = capi.Sync(point_notime)
+    msgs = []
+    for k, f in enumerate(scans):
+        for row in f.imu:
+            msgs.append((float(row[0]), 0, k, row))
+        msgs.append((f.end_time, 1, k, None))
+    msgs.sort(key=lambda m: (m[0], m[1]))
+    try:
+        for _, kind, k, row in msgs:
+            if kind == 0:
+                sync.push_imu(row)
+            else:
+                tl = float(scans[k].xyzt[-1, 3]) if t_last_of is None else float(t_last_of(k))
+                sync.push_scan(scans[k].beg_time, tl, k)
+            while True:
+                r, tag, beg, end, imu = sync.next()
+                if r < 0:
+                    raise capi.VinaError(r, "vina_sync_next")
+                if r == 0:
+                    break
+                if r == 1:
+                    yield tag, beg, end, imu
+    finally:
+        sync.close()
+
+
+def replay_stream(cfg, boots, scans, out=None, max_iter=4, caps=None, point_filter_num=1, shuffle_seed=0,
+                  prune_horizon=700):
+    """Like `replay`, but from RAW message streams: every scan is handed over the way a driver delivers it (points
+    in arbitrary time order - here shuffled), goes through the device front end (`vina_scan_prepare`: decoder keep
+    rule, time sort, 0.11 s cut) and is paired with its IMU samples by `vina_sync`; the step is
+    `vina_odom_step_prepared`. Returns (trajectory rows, seconds per scan, worst position error or None)."""
+    caps = caps or dict(max_scan_points=max(300000, max(f.xyzt.shape[0] for f in boots + scans) + 1024))
+    gx = capi.Ctx(cfg, **caps)
+    for f in boots:
+        gx.bootstrap(f.xyzt, capi.make_state(f.gt_R, f.gt_p, f.gt_v, t=f.end_time))
+    gx.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+    rng = np.random.default_rng(shuffle_seed)
+    raws = [f.xyzt[rng.permutation(f.xyzt.shape[0])] for f in scans]
+    blind2 = float(cfg.blind) ** 2  # node.cpp:210
+    prepared = {"k": -1, "t_last": 0.0}
+
+    def prepare(k):
+        if prepared["k"] != k:
+            _, prepared["t_last"] = gx.scan_prepare(raws[k], point_filter_num, blind2)
+            prepared["k"] = k
+        return prepared["t_last"]
+
+    rows, worst = [], None
+    fh = open(out, "w") if out else None
+    t0 = time.perf_counter()
+    for k, beg, end, imu in stream_packages(scans, 0, t_last_of=prepare):
+        prepare(k)
+        prepared["k"] = -1  # the step consumes the prepared scan
+        s = capi.state_arrays(gx.step_prepared(beg, imu, True, max_iter))
+        rows.append(np.concatenate([[s["t"]], s["p"], quat_xyzw(s["R"])]))
+        if fh:
+            fh.write(tum_line(s["t"], s["p"], s["R"]))
+        if scans[k].gt_p is not None:
+            e = float(np.linalg.norm(s["p"] - scans[k].gt_p))
+            worst = e if worst is None else max(worst, e)
+        if prune_horizon > 0:
+            gx.idle(prune_horizon)
+    gx.sync()
+    dt = (time.perf_counter() - t0) / max(len(rows), 1)
+    if fh:
+        fh.close()
+    gx.close()
+    return np.array(rows), dt, worst
+
+
 def replay(cfg, boots, scans, out=None, ba=False, max_iter=4, caps=None, prune_horizon=700, stats=None):
     """Returns (trajectory rows (K, 8): t, p, q_xyzw; seconds per scan; worst position error vs ground truth or None).
 
@@ -129,15 +206,21 @@ def main(argv=None):
     ap.add_argument("--scans", type=int, default=30)
     ap.add_argument("--ba", action="store_true", help="LocalBA.if_BA: 1")
     ap.add_argument("--out", default=None, help="TUM trajectory file")
+    ap.add_argument("--raw", action="store_true",
+                    help="feed raw message streams: shuffled scans through vina_scan_prepare, pairing by vina_sync")
     ap.add_argument("--prune-horizon", type=int, default=700,
                     help="metres of travel after which unvisited root voxels are erased (reference: 700; 0 = never)")
     a = ap.parse_args(argv)
     cfg = synth.SENSORS[a.config or a.workload]
     boots, scans = npz_frames(a.npz, cfg.win_size) if a.npz else synthetic_frames(cfg, a.scans)
     st = {}
-    rows, dt, worst = replay(cfg, boots, scans, out=a.out, ba=a.ba, prune_horizon=a.prune_horizon, stats=st)
+    if a.raw:
+        rows, dt, worst = replay_stream(cfg, boots, scans, out=a.out, prune_horizon=a.prune_horizon)
+    else:
+        rows, dt, worst = replay(cfg, boots, scans, out=a.out, ba=a.ba, prune_horizon=a.prune_horizon, stats=st)
     msg = f"{len(rows)} scans, {1e3 * dt:.3f} ms/scan (wall clock, Python loop included)"
-    msg += f", journey {st['journey']:.1f} m, {st['roots_erased']} root voxels pruned"
+    if st:
+        msg += f", journey {st['journey']:.1f} m, {st['roots_erased']} root voxels pruned"
     if worst is not None:
         msg += f", max |p - p_gt| = {worst:.4f} m"
     if a.out:
