@@ -18,13 +18,15 @@
  *    independent (replicas / other GPUs).
  *  - there is NO CPU fallback: without a CUDA device vina_ctx_create fails
  *    with VINA_E_CUDA. (The only entry points that run without a device are the
- *    stateless host pieces of the BA, vina_ba_imu_evaluate / vina_ba_solve, and
- *    vina_shard_owner / vina_config_default: they are host work in the product too.)
+ *    stateless host pieces of the BA, vina_ba_imu_evaluate / vina_ba_solve, the
+ *    scan / IMU pairing vina_sync_* and vina_shard_owner / vina_config_default:
+ *    they are host work in the product too.)
  *
  * Groups: lifetime | deskew, down-sampling, var_init | IEKF accumulate / device loop |
  * map insert, recut, margi | map sharded over GPUs (records and IEKF queries through
  * NCCL or through peer memory) | the per-scan loop body (vina_odom_*) | batch replay |
- * sliding-window BA (vina_ba_*, vina_odom_set_ba).
+ * sliding-window BA (vina_ba_*, vina_odom_set_ba) | scan front end (vina_scan_prepare) and scan / IMU pairing
+ * (vina_sync_*) | map pruning behind the vehicle (vina_map_prune, vina_odom_idle).
  */
 #ifndef VINA_B200_H
 #define VINA_B200_H
