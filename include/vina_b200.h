@@ -19,7 +19,8 @@
  *  - there is NO CPU fallback: without a CUDA device vina_ctx_create fails
  *    with VINA_E_CUDA. (The only entry points that run without a device are the
  *    stateless host pieces of the BA, vina_ba_imu_evaluate / vina_ba_solve, the
- *    scan / IMU pairing vina_sync_* and vina_shard_owner / vina_config_default:
+ *    scan / IMU pairing vina_sync_*, the message unpacking vina_decode_* and
+ *    vina_shard_owner / vina_config_default:
  *    they are host work in the product too.)
  *
  * Groups: lifetime | deskew, down-sampling, var_init | IEKF accumulate / device loop |
@@ -413,6 +414,46 @@ int vina_sync_push_scan(vina_sync* s, double t_start, double t_last, int64_t tag
 int vina_sync_pending(vina_sync* s, int32_t* scans, int32_t* imus);
 int vina_sync_next(vina_sync* s, int64_t* tag, double* pcl_beg_time, double* pcl_end_time, vina_imu* imus, int cap,
                    int32_t* m);
+
+/* ---- unpacking of the driver messages: LidarPointCloudDecoder::process and its handlers
+ * (src/sensor/lidar_pointcloud_decoder.cpp:21-240), host functions (no device, no context). A PointCloud2 is its
+ * data pointer, the point count (width * height) and the byte offsets of the fields pcl::fromROSMsg maps by name
+ * into the handler's point struct (include/vina_slam/lidar_pointcloud_decoder.hpp:44-109): x, y, z FLOAT32 and the
+ * time field (`time` FLOAT32 for Velodyne, `t` UINT32 ns for Ouster, `timestamp` FLOAT64 for Hesai / RoboSense;
+ * t_datatype = the sensor_msgs::PointField datatype 6 / 7 / 8). Output: n_kept x (x, y, z, curvature) float32 in
+ * arrival order, each handler's own time rule and keep rule applied (RoboSense: planar blind test; Velodyne without
+ * usable stamps: time from the azimuth at omega_l deg/s) - to be handed to vina_scan_prepare with
+ * point_filter_num = 1 and blind2 < 0 (sort + 0.11 s cut). blind2 = General.blind squared (node.cpp:210).
+ * Returns the number of points written, VINA_E_CAPACITY if cap is too small. */
+enum
+{
+  VINA_LIDAR_LIVOX = 0,
+  VINA_LIDAR_VELODYNE = 1,
+  VINA_LIDAR_OUSTER = 2,
+  VINA_LIDAR_HESAI = 3,
+  VINA_LIDAR_ROBOSENSE = 4,
+  VINA_LIDAR_TARTANAIR = 5 /* LID_TYPE, lidar_pointcloud_decoder.hpp:20-28 */
+};
+typedef struct vina_pc2_layout
+{
+  int32_t point_step;
+  int32_t off_x, off_y, off_z;
+  int32_t off_t;      /* -1: none (TartanAir) */
+  int32_t t_datatype; /* 6 = UINT32, 7 = FLOAT32, 8 = FLOAT64 */
+  int32_t is_bigendian;
+} vina_pc2_layout;
+/* livox_ros_driver2::msg::CustomPoint */
+typedef struct vina_livox_point
+{
+  uint32_t offset_time; /* ns from the message stamp */
+  float x, y, z;
+  uint8_t reflectivity, tag, line, pad;
+} vina_livox_point;
+int64_t vina_decode_pointcloud2(int lidar_type, const uint8_t* data, int64_t n_points, const vina_pc2_layout* layout,
+                                double header_stamp, double omega_l, double blind2, int point_filter_num, float* xyzt,
+                                int64_t cap);
+int64_t vina_decode_livox(const vina_livox_point* pts, int64_t n_points, double blind2, int point_filter_num,
+                          float* xyzt, int64_t cap);
 
 /* record per-stage CUDA-event timings (adds event records + one sync per step) */
 int vina_set_profiling(vina_ctx* ctx, int on);

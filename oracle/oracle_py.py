@@ -465,3 +465,66 @@ def log_so3(R, ref: bool = False):
     w = np.zeros(3)
     lib.vo_log(_dp(a), _dp(w))
     return w
+
+
+# ---- the decoders' handlers (src/sensor/lidar_pointcloud_decoder.cpp:55-240), restated in numpy. PARITY UNPINNED: the
+# reference's handlers need pcl::fromROSMsg (PCL / ROS 2 are not installed) and the reference holds no vectors for
+# them; this restatement follows the source line by line and is what the library is checked against.
+def decode_handler(lidar_type: int, pts: np.ndarray, header_stamp: float, blind2: float, point_filter_num: int,
+                   omega_l: float = 3610.0) -> np.ndarray:
+    """pts: structured array with float32 x, y, z and the handler's time field `t` (float32 seconds for Velodyne,
+    uint32 ns for Ouster / Livox, float64 seconds for Hesai / RoboSense; absent for TartanAir), i.e. what
+    pcl::fromROSMsg leaves in the handler's point struct. Returns (n_kept, 4) float32 = x, y, z, curvature."""
+    n = pts.shape[0]
+    x, y, z = (pts[k].astype(np.float32) for k in ("x", "y", "z"))
+    i = np.arange(n)
+    r2 = (x * x + y * y) + z * z  # float32, left to right
+    dec = (i % point_filter_num) == 0
+    if n == 0:
+        return np.zeros((0, 4), dtype=np.float32)
+    if lidar_type == 5:  # tartanair_handler (:228-239)
+        c, keep = np.zeros(n, dtype=np.float32), np.ones(n, dtype=bool)
+    elif lidar_type == 0:  # livox_handler (:55-75)
+        c = (pts["t"].astype(np.float64) * 1e-9).astype(np.float32)
+        keep = dec & (r2.astype(np.float64) > blind2)
+    elif lidar_type == 2:  # ouster_handler (:143-165)
+        c = (pts["t"].astype(np.float64) / 1e9).astype(np.float32)
+        keep = dec & (r2.astype(np.float64) > blind2)
+    elif lidar_type == 3:  # hesai_handler (:167-194)
+        c = (pts["t"].astype(np.float64) - float(pts["t"][0])).astype(np.float32)
+        keep = dec & (r2.astype(np.float64) > blind2)
+    elif lidar_type == 4:  # robosense_handler (:196-224): planar blind test
+        c = (pts["t"].astype(np.float64) - header_stamp).astype(np.float32)
+        keep = dec & ((x * x + y * y).astype(np.float64) > blind2)
+    elif lidar_type == 1:  # velodyne_handler (:77-141)
+        tl = np.float32(pts["t"][-1])
+        if tl > 0.01 and tl < 0.12:
+            c = pts["t"].astype(np.float32)
+            keep = dec & (r2.astype(np.float64) > blind2)
+        else:
+            out, first, yaw0, yaw_last, bias, cool = [], True, 0.0, 0.0, 0.0, 0
+            for k in range(n):
+                if abs(float(x[k])) < 0.1:
+                    continue
+                yaw = float(np.arctan2(y[k], x[k])) * 57.2957795 - bias
+                if first:
+                    yaw0 = yaw_last = yaw
+                    first = False
+                if float(r2[k]) < blind2:
+                    continue
+                if (yaw - yaw_last) > 180:
+                    cool -= 1
+                    if cool + 1 <= 0:
+                        bias += 360
+                        yaw -= 360
+                        cool = 1000
+                if abs(yaw - yaw_last) > 180:
+                    yaw += 360
+                cur = np.float32((yaw0 - yaw) / omega_l)
+                yaw_last = yaw
+                if cur >= 0 and cur < 0.1 and (k % point_filter_num) == 0:
+                    out.append((x[k], y[k], z[k], cur))
+            return np.array(out, dtype=np.float32).reshape(-1, 4)
+    else:
+        raise ValueError("Unsupported lidar type")
+    return np.stack([x, y, z, c], axis=1)[keep].astype(np.float32)

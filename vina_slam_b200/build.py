@@ -33,6 +33,7 @@ UNITS = [
     (os.path.join(HOST, "vina_pipeline.cpp"), ["-x", "cu"]),
     (os.path.join(HOST, "vina_ba.cpp"), ["-x", "cu"]),
     (os.path.join(HOST, "vina_sync.cpp"), ["-x", "cu"]),
+    (os.path.join(HOST, "vina_decode.cpp"), ["-x", "cu"]),
 ]
 HEADERS = [os.path.join(CSRC, f) for f in ("vn_types.cuh", "vn_math.cuh", "vn_kernels.cuh", "vn_ctx.h")] + [
     os.path.join(HOST, "vina_ba.h"),

@@ -78,7 +78,7 @@ EXPORTS = [
     "vina_map_set_journey", "vina_map_prune", "vina_odom_journey", "vina_odom_idle",
     "vina_scan_prepare", "vina_scan_prepare_device", "vina_odom_step_prepared",
     "vina_sync_create", "vina_sync_destroy", "vina_sync_push_imu", "vina_sync_push_scan", "vina_sync_pending",
-    "vina_sync_next",
+    "vina_sync_next", "vina_decode_pointcloud2", "vina_decode_livox",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -107,6 +107,8 @@ def load():
     lib.vina_ctx_destroy.restype = None
     lib.vina_batch_destroy.restype = None
     lib.vina_config_default.restype = None
+    lib.vina_decode_pointcloud2.restype = C.c_int64
+    lib.vina_decode_livox.restype = C.c_int64
     lib.vina_sync_destroy.restype = None
     lib.vina_sync_destroy.argtypes = [C.c_void_p]
     lib.vina_map_count.restype = C.c_int64
@@ -557,6 +559,46 @@ class Ctx:
         mp = np.zeros(16, dtype=np.int32)
         ws = self._ck(self.lib.vina_odom_window(self.h, C.byref(wc), mp.ctypes.data_as(C.c_void_p), C.c_int(16)))
         return wc.value, mp[:ws].copy()
+
+
+LIDAR_LIVOX, LIDAR_VELODYNE, LIDAR_OUSTER, LIDAR_HESAI, LIDAR_ROBOSENSE, LIDAR_TARTANAIR = range(6)
+LIVOX_POINT_DTYPE = np.dtype([("offset_time", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("reflectivity", "u1"),
+                              ("tag", "u1"), ("line", "u1"), ("pad", "u1")])
+
+
+class Pc2Layout(C.Structure):
+    _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_t", C.c_int32), ("t_datatype", C.c_int32), ("is_bigendian", C.c_int32)]
+
+
+def decode_pointcloud2(lidar_type: int, data: bytes, n_points: int, point_step: int, off_xyz, off_t: int, t_datatype: int,
+                       header_stamp: float, blind2: float, point_filter_num: int, omega_l: float = 3610.0,
+                       is_bigendian: bool = False, cap: int | None = None) -> np.ndarray:
+    """vina_decode_pointcloud2 (host only): the bytes of a sensor_msgs/PointCloud2 -> (n_kept, 4) float32."""
+    lib = load()
+    L = Pc2Layout(point_step, off_xyz[0], off_xyz[1], off_xyz[2], off_t, t_datatype, 1 if is_bigendian else 0)
+    cap = n_points if cap is None else cap
+    out = np.zeros((max(cap, 1), 4), dtype=np.float32)
+    buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if len(data) else b"\0")
+    r = lib.vina_decode_pointcloud2(C.c_int(lidar_type), buf, C.c_int64(n_points), C.byref(L), C.c_double(header_stamp),
+                                    C.c_double(omega_l), C.c_double(blind2), C.c_int(point_filter_num), _fp(out),
+                                    C.c_int64(cap))
+    if r < 0:
+        raise VinaError(int(r), "vina_decode_pointcloud2")
+    return out[:r].copy()
+
+
+def decode_livox(pts: np.ndarray, blind2: float, point_filter_num: int, cap: int | None = None) -> np.ndarray:
+    """vina_decode_livox (host only): livox CustomMsg points (LIVOX_POINT_DTYPE) -> (n_kept, 4) float32."""
+    lib = load()
+    a = np.ascontiguousarray(pts, dtype=LIVOX_POINT_DTYPE)
+    cap = a.shape[0] if cap is None else cap
+    out = np.zeros((max(cap, 1), 4), dtype=np.float32)
+    r = lib.vina_decode_livox(a.ctypes.data_as(C.c_void_p), C.c_int64(a.shape[0]), C.c_double(blind2),
+                              C.c_int(point_filter_num), _fp(out), C.c_int64(cap))
+    if r < 0:
+        raise VinaError(int(r), "vina_decode_livox")
+    return out[:r].copy()
 
 
 class Sync:
