@@ -414,9 +414,12 @@ def down_sampling_voxel(xyz4: np.ndarray, voxel_size: float, ref: bool = False) 
 class Sync:
     """sync_packages and its buffers (src/sensor/sync.cpp:5-96)."""
 
-    def __init__(self, point_notime: int = 0):
-        self.lib = load()
+    def __init__(self, point_notime: int = 0, ref: bool = False):
+        """ref: the reference's own sync.cpp (oracle/_ref) - its state is global, ONE instance per process."""
+        self.lib = load(ref=ref)
         self.h = C.c_void_p(self.lib.vo_sync_create(C.c_int(point_notime)))
+        if not self.h:
+            raise RuntimeError("the reference's sync_packages keeps its state in globals: one instance per process")
 
     def close(self):
         if self.h:

@@ -21,6 +21,7 @@
 #include "vina_slam/mapping/voxel_map.hpp"
 #include "vina_slam/mapping/optimizers.hpp"
 #include "vina_slam/preintegration.hpp"
+#include "vina_slam/sensor/sync.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -767,6 +768,87 @@ int vo_odom_window(void* h, int* win_count, int* mpo, int cap)
   for (int i = 0; i < o->vs.win_size && i < cap; i++) mpo[i] = mp[i];
   return o->vs.win_size;
 }
+// ---- the reference's own sync_packages (src/sensor/sync.cpp, compiled unmodified) behind the vo_sync_* API. Its
+// state is the file's globals plus a function-local static, so only ONE instance may ever exist per process. A scan is
+// a one-point cloud: curvature = the time offset of the scan's last point, normal_x = the tag (small integers).
+namespace
+{
+bool g_sync_made = false, g_sync_held = false;
+IMUEKF g_sync_ekf;
+pcl::PointCloud<PointType>::Ptr g_sync_pl;
+}  // namespace
+void* vo_sync_create(int notime)
+{
+  if (g_sync_made) return nullptr;
+  g_sync_made = true;
+  point_notime = notime;
+  return &g_sync_ekf;
+}
+void vo_sync_destroy(void*) {}
+void vo_sync_push_imu(void*, const double imu7[7])
+{
+  // imu_handler (src/platform/ros2/subscribers.cpp:11-20); the stamp is integer nanoseconds like a ROS stamp
+  auto msg = std::make_shared<sensor_msgs::msg::Imu>();
+  const int64_t ns = (int64_t)llround(imu7[0] * 1e9);
+  msg->header.stamp.sec = (int32_t)(ns / 1000000000LL);
+  msg->header.stamp.nanosec = (uint32_t)(ns % 1000000000LL);
+  msg->angular_velocity.x = imu7[1], msg->angular_velocity.y = imu7[2], msg->angular_velocity.z = imu7[3];
+  msg->linear_acceleration.x = imu7[4], msg->linear_acceleration.y = imu7[5], msg->linear_acceleration.z = imu7[6];
+  mBuf.lock();
+  imu_last_time = rclcpp::Time(msg->header.stamp).seconds();
+  imu_buf.push_back(msg);
+  mBuf.unlock();
+}
+void vo_sync_push_scan(void*, double t_start, double t_last, int64_t tag)
+{
+  // the tail of pcl_handler (src/sensor/lidar_decoder.cpp:36-43)
+  pcl::PointCloud<PointType>::Ptr pl_ptr(new pcl::PointCloud<PointType>());
+  PointType ap;
+  ap.x = ap.y = ap.z = 0;
+  ap.curvature = (float)t_last;
+  ap.normal_x = (float)tag;
+  pl_ptr->push_back(ap);
+  mBuf.lock();
+  time_buf.push_back(t_start);
+  pcl_buf.push_back(pl_ptr);
+  mBuf.unlock();
+}
+int vo_sync_next(void*, int64_t* tag, double* beg, double* end, double* imu7, int cap, int* m)
+{
+  *m = 0;
+  const size_t nbuf = pcl_buf.size();
+  const bool seeding = point_notime && !g_sync_held && last_pcl_time < 0;
+  deque<std::shared_ptr<sensor_msgs::msg::Imu>> imus;  // a fresh deque per loop iteration (local_mapping.cpp:300)
+  const bool ok = sync_packages(g_sync_pl, imus, g_sync_ekf);
+  const bool popped = pcl_buf.size() < nbuf;
+  if (!ok && !popped && !g_sync_held) return 0;
+  *tag = (int64_t)g_sync_pl->back().normal_x;
+  if (!ok && popped && seeding)
+  {
+    g_sync_held = false;
+    return 2;
+  }
+  if (!ok && !(imu_last_time > g_sync_ekf.pcl_end_time))
+  {
+    g_sync_held = true;  // the IMU stream has not passed the scan's end: sync_packages keeps the scan
+    return 0;
+  }
+  g_sync_held = false;
+  *beg = g_sync_ekf.pcl_beg_time;
+  *end = g_sync_ekf.pcl_end_time;
+  if ((int)imus.size() > cap) return -3;
+  for (size_t i = 0; i < imus.size(); i++)
+  {
+    imu7[7 * i] = rclcpp::Time(imus[i]->header.stamp).seconds();
+    imu7[7 * i + 1] = imus[i]->angular_velocity.x, imu7[7 * i + 2] = imus[i]->angular_velocity.y;
+    imu7[7 * i + 3] = imus[i]->angular_velocity.z;
+    imu7[7 * i + 4] = imus[i]->linear_acceleration.x, imu7[7 * i + 5] = imus[i]->linear_acceleration.y;
+    imu7[7 * i + 6] = imus[i]->linear_acceleration.z;
+  }
+  *m = (int)imus.size();
+  return ok ? 1 : 2;
+}
+
 void vo_odom_journey(void* h, double* jour, int* release_flag)
 {
   RefOdom* o = (RefOdom*)h;

@@ -228,3 +228,19 @@ def test_vnc_terms_are_unreachable_in_the_reference(oracle_lib):
     finally:
         od.close()
         rf.close()
+
+
+@pytest.mark.parametrize("point_notime", [0, 1])
+def test_sync_packages_restatement_against_the_reference(oracle_lib, point_notime):
+    """sync_packages (src/sensor/sync.cpp, compiled unmodified into oracle/_ref) vs the oracle's restatement on a
+    6000-event random stream of IMU samples, scans and calls: every return value, tag, pcl_beg / pcl_end and IMU batch
+    must agree. One process per mode (the reference keeps this state in globals and a function-local static)."""
+    import subprocess
+
+    if not oracle_lib.have_ref():
+        pytest.skip("oracle/_ref is not built here (needs /root/reference)")
+    script = os.path.join(HERE, "golden", "sync_vs_ref.py")
+    r = subprocess.run([sys.executable, script, str(point_notime), "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    tok = r.stdout.split()
+    assert tok[0] == "OK" and int(tok[1]) > 50 and int(tok[2]) > 50, r.stdout
