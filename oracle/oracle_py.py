@@ -441,10 +441,10 @@ class Sync:
         return r, tag.value, beg.value, end.value, buf[:m.value].copy()
 
 
-def scan_prepare(xyz4: np.ndarray, point_filter_num: int, blind2: float, fast: bool = False) -> np.ndarray:
+def scan_prepare(xyz4: np.ndarray, point_filter_num: int, blind2: float, fast: bool = False, ref: bool = False) -> np.ndarray:
     """Decoder keep rule + pcl_handler (filter, stable sort by time offset, cut at 0.11 s); None where the reference
     would be left with an empty cloud."""
-    lib = load(fast=fast)
+    lib = load(fast=fast, ref=ref)  # ref: the reference's own pcl_handler + velodyne_handler (oracle/_ref)
     a = np.ascontiguousarray(xyz4, dtype=np.float32).reshape(-1, 4)
     out = np.zeros((max(a.shape[0], 2), 4), dtype=np.float32)
     n = lib.vo_scan_prepare(C.c_int(a.shape[0]), _fp(a), C.c_int(point_filter_num), C.c_double(blind2), _fp(out))
@@ -470,9 +470,8 @@ def log_so3(R, ref: bool = False):
     return w
 
 
-# ---- the decoders' handlers (src/sensor/lidar_pointcloud_decoder.cpp:55-240), restated in numpy. PARITY UNPINNED: the
-# reference's handlers need pcl::fromROSMsg (PCL / ROS 2 are not installed) and the reference holds no vectors for
-# them; this restatement follows the source line by line and is what the library is checked against.
+# ---- the decoders' handlers (src/sensor/lidar_pointcloud_decoder.cpp:55-240), restated in numpy; pinned against the
+# reference's own file compiled into oracle/_ref (decode_handler_ref below; tests/test_oracle_vs_ref.py).
 def decode_handler(lidar_type: int, pts: np.ndarray, header_stamp: float, blind2: float, point_filter_num: int,
                    omega_l: float = 3610.0) -> np.ndarray:
     """pts: structured array with float32 x, y, z and the handler's time field `t` (float32 seconds for Velodyne,
@@ -531,3 +530,31 @@ def decode_handler(lidar_type: int, pts: np.ndarray, header_stamp: float, blind2
     else:
         raise ValueError("Unsupported lidar type")
     return np.stack([x, y, z, c], axis=1)[keep].astype(np.float32)
+
+
+def decode_handler_ref(lidar_type: int, data: bytes, n_points: int, point_step: int, off_xyz, off_t: int, t_datatype: int,
+                       header_stamp: float, blind2: float, point_filter_num: int, omega_l: float = 3610.0) -> np.ndarray:
+    """The reference's own LidarPointCloudDecoder::process (oracle/_ref, compiled unmodified; pcl::fromROSMsg from the
+    shim) on the bytes of a PointCloud2."""
+    lib = load(ref=True)
+    lib.vo_decode_handler.restype = C.c_int64
+    out = np.zeros((max(n_points, 1), 4), dtype=np.float32)
+    buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if len(data) else b"\0")
+    r = lib.vo_decode_handler(C.c_int(lidar_type), buf, C.c_int64(n_points), C.c_int(point_step), C.c_int(off_xyz[0]),
+                              C.c_int(off_xyz[1]), C.c_int(off_xyz[2]), C.c_int(off_t), C.c_int(t_datatype),
+                              C.c_double(header_stamp), C.c_double(omega_l), C.c_double(blind2), C.c_int(point_filter_num),
+                              _fp(out), C.c_int64(out.shape[0]))
+    assert r >= 0
+    return out[:r].copy()
+
+
+def decode_livox_ref(offset_time: np.ndarray, xyz: np.ndarray, blind2: float, point_filter_num: int) -> np.ndarray:
+    lib = load(ref=True)
+    lib.vo_decode_livox.restype = C.c_int64
+    t = np.ascontiguousarray(offset_time, dtype=np.uint32)
+    p = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((max(t.shape[0], 1), 4), dtype=np.float32)
+    r = lib.vo_decode_livox(t.ctypes.data_as(C.c_void_p), _fp(p), C.c_int64(t.shape[0]), C.c_double(blind2),
+                            C.c_int(point_filter_num), _fp(out), C.c_int64(out.shape[0]))
+    assert r >= 0
+    return out[:r].copy()

@@ -22,6 +22,7 @@
 #include "vina_slam/mapping/optimizers.hpp"
 #include "vina_slam/preintegration.hpp"
 #include "vina_slam/sensor/sync.hpp"
+#include "vina_slam/sensor/lidar_decoder.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -847,6 +848,96 @@ int vo_sync_next(void*, int64_t* tag, double* beg, double* end, double* imu7, in
   }
   *m = (int)imus.size();
   return ok ? 1 : 2;
+}
+
+// ---- the reference's own message handlers (src/sensor/lidar_pointcloud_decoder.cpp) and pcl_handler
+// (src/sensor/lidar_decoder.cpp), compiled unmodified; pcl::fromROSMsg comes from the shim (fields mapped by name).
+namespace
+{
+builtin_interfaces::msg::Time stamp_of(double t)
+{
+  builtin_interfaces::msg::Time s;
+  const int64_t ns = (int64_t)llround(t * 1e9);
+  s.sec = (int32_t)(ns / 1000000000LL);
+  s.nanosec = (uint32_t)(ns % 1000000000LL);
+  return s;
+}
+int64_t cloud_out(pcl::PointCloud<PointType>& pl, float* xyz4_out, int64_t cap)
+{
+  if ((int64_t)pl.size() > cap) return -3;
+  for (size_t i = 0; i < pl.size(); i++)
+  {
+    xyz4_out[4 * i] = pl[i].x, xyz4_out[4 * i + 1] = pl[i].y, xyz4_out[4 * i + 2] = pl[i].z;
+    xyz4_out[4 * i + 3] = pl[i].curvature;
+  }
+  return (int64_t)pl.size();
+}
+}  // namespace
+int64_t vo_decode_handler(int lidar_type, const uint8_t* data, int64_t n, int point_step, int off_x, int off_y, int off_z,
+                          int off_t, int t_datatype, double header_stamp, double omega_l, double blind2,
+                          int point_filter_num, float* xyz4_out, int64_t cap)
+{
+  auto msg = std::make_shared<sensor_msgs::msg::PointCloud2>();
+  msg->header.stamp = stamp_of(header_stamp);
+  msg->width = (uint32_t)n;
+  msg->height = 1;
+  msg->point_step = (uint32_t)point_step;
+  msg->row_step = (uint32_t)(point_step * n);
+  msg->data.assign(data, data + (size_t)n * point_step);
+  const char* tname = lidar_type == VELODYNE ? "time" : lidar_type == OUSTER ? "t" : "timestamp";
+  msg->fields = { { "x", (uint32_t)off_x, 7, 1 }, { "y", (uint32_t)off_y, 7, 1 }, { "z", (uint32_t)off_z, 7, 1 } };
+  if (off_t >= 0) msg->fields.push_back({ tname, (uint32_t)off_t, (uint8_t)t_datatype, 1 });
+  feat.lidar_type = lidar_type;
+  feat.point_filter_num = point_filter_num;
+  feat.blind = blind2;
+  feat.omega_l = omega_l;
+  pcl::PointCloud<PointType> pl_full;
+  const sensor_msgs::msg::PointCloud2::SharedPtr cmsg = msg;
+  feat.process(cmsg, pl_full);
+  return cloud_out(pl_full, xyz4_out, cap);
+}
+int64_t vo_decode_livox(const uint32_t* offset_time, const float* xyz, int64_t n, double blind2, int point_filter_num,
+                        float* xyz4_out, int64_t cap)
+{
+  auto msg = std::make_shared<livox_ros_driver2::msg::CustomMsg>();
+  msg->point_num = (uint32_t)n;
+  msg->points.resize(n);
+  for (int64_t i = 0; i < n; i++)
+  {
+    msg->points[i].offset_time = offset_time[i];
+    msg->points[i].x = xyz[3 * i], msg->points[i].y = xyz[3 * i + 1], msg->points[i].z = xyz[3 * i + 2];
+  }
+  feat.lidar_type = LIVOX;
+  feat.point_filter_num = point_filter_num;
+  feat.blind = blind2;
+  pcl::PointCloud<PointType> pl_full;
+  const livox_ros_driver2::msg::CustomMsg::SharedPtr cmsg = msg;
+  feat.process(cmsg, pl_full);
+  return cloud_out(pl_full, xyz4_out, cap);
+}
+// pcl_handler on a scan given as n x (x, y, z, time offset): packed as a Velodyne message with a float `time` field
+// (the handler that passes the stamps through unchanged; the LAST input point's stamp must lie in (0.01, 0.12),
+// lidar_pointcloud_decoder.cpp:86), result taken back out of pcl_buf / time_buf.
+int vo_scan_prepare(int n, const float* xyz4_in, int point_filter_num, double blind2, float* xyz4_out)
+{
+  auto msg = std::make_shared<sensor_msgs::msg::PointCloud2>();
+  msg->width = (uint32_t)n;
+  msg->height = 1;
+  msg->point_step = 16;
+  msg->data.resize((size_t)n * 16);
+  if (n > 0) memcpy(msg->data.data(), xyz4_in, (size_t)n * 16);
+  msg->fields = { { "x", 0, 7, 1 }, { "y", 4, 7, 1 }, { "z", 8, 7, 1 }, { "time", 12, 7, 1 } };
+  feat.lidar_type = VELODYNE;
+  feat.point_filter_num = point_filter_num;
+  feat.blind = blind2;
+  const sensor_msgs::msg::PointCloud2::SharedPtr cmsg = msg;
+  pcl_handler(cmsg);
+  mBuf.lock();
+  pcl::PointCloud<PointType>::Ptr pl = pcl_buf.back();
+  pcl_buf.pop_back();
+  time_buf.pop_back();
+  mBuf.unlock();
+  return (int)cloud_out(*pl, xyz4_out, (int64_t)(n > 2 ? n : 2));
 }
 
 void vo_odom_journey(void* h, double* jour, int* release_flag)

@@ -25,4 +25,9 @@ struct alignas(16) PointXYZINormal
   float pad_[2];
   PointXYZINormal() : data{ 0, 0, 0, 1 }, data_n{ 0, 0, 0, 0 } {}
 };
+struct alignas(16) PointXYZ
+{
+  float x = 0, y = 0, z = 0;
+  float pad_ = 1;
+};
 }  // namespace pcl

@@ -147,3 +147,23 @@ def test_livox_and_error_codes(capi_host):
     with pytest.raises(capi_host.VinaError) as e:
         capi_host.decode_pointcloud2(3, a.tobytes(), 100, dt.itemsize, [0, 4, 8], 16, code, 5.0, 0.01, 1, cap=5)
     assert e.value.code == -3
+
+
+def test_library_against_the_reference_handlers(capi_host):
+    """The library's unpacking against the REFERENCE'S OWN handlers (lidar_pointcloud_decoder.cpp compiled unmodified
+    into oracle/_ref): bit for bit for every sensor type, the azimuth-derived Velodyne stamps included (both sides call
+    libm's atan2f)."""
+    if not op.have_ref():
+        pytest.skip("oracle/_ref is not built here (needs /root/reference)")
+    stamp = float(1000250000000) * 1e-9
+    for lidar_type in (1, 2, 3, 4, 5):
+        rng = np.random.default_rng(70 + lidar_type)
+        dt, tname, code = LAYOUTS[lidar_type]
+        off_t = dt.fields[tname][1] if tname else -1
+        for n, pfn, blind2, spin in ((4000, 1, 0.01, False), (4000, 3, 0.25, False), (3000, 1, 0.01, True), (3000, 2, 0.5, True)):
+            if spin and lidar_type != 1:
+                continue
+            a = _cloud(lidar_type, n, rng, stamp, spin=spin)
+            g = capi_host.decode_pointcloud2(lidar_type, a.tobytes(), n, dt.itemsize, [0, 4, 8], off_t, code, stamp, blind2, pfn)
+            r = op.decode_handler_ref(lidar_type, a.tobytes(), n, dt.itemsize, [0, 4, 8], off_t, code, stamp, blind2, pfn)
+            assert g.shape == r.shape and g.shape[0] > 500 and np.array_equal(g, r), (lidar_type, n, pfn, spin)

@@ -244,3 +244,67 @@ def test_sync_packages_restatement_against_the_reference(oracle_lib, point_notim
     assert r.returncode == 0, r.stderr[-2000:]
     tok = r.stdout.split()
     assert tok[0] == "OK" and int(tok[1]) > 50 and int(tok[2]) > 50, r.stdout
+
+
+def test_message_handlers_and_pcl_handler_against_the_reference(oracle_lib):
+    """The reference's own lidar_pointcloud_decoder.cpp and lidar_decoder.cpp (compiled unmodified into oracle/_ref;
+    pcl::fromROSMsg from the shim maps the fields by name) against (i) the numpy restatement of the six handlers on
+    synthetic PointCloud2 / CustomMsg buffers - bit for bit, the azimuth path of the Velodyne fallback included - and
+    (ii) the restatement of the keep rule + pcl_handler: identical for distinct stamps; with equal stamps (where the
+    reference's std::sort leaves the order open) the same stamps in the same order and, per stamp, the same points."""
+    if not oracle_lib.have_ref():
+        pytest.skip("oracle/_ref is not built here (needs /root/reference)")
+    spec = importlib.util.spec_from_file_location("test_decode_cpu", os.path.join(HERE, "test_decode_cpu.py"))
+    td = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(td)
+    stamp = float(1000250000000) * 1e-9  # a ROS stamp (integer ns) as rclcpp::Time::seconds() returns it
+    for lidar_type in (1, 2, 3, 4, 5):
+        rng = np.random.default_rng(40 + lidar_type)
+        dt, tname, code = td.LAYOUTS[lidar_type]
+        off_t = dt.fields[tname][1] if tname else -1
+        for n, pfn, blind2, spin in ((4000, 1, 0.01, False), (4000, 3, 0.25, False), (3000, 2, 0.01, True)):
+            if spin and lidar_type != 1:
+                continue
+            a = td._cloud(lidar_type, n, rng, stamp, spin=spin)
+            r = oracle_lib.decode_handler_ref(lidar_type, a.tobytes(), n, dt.itemsize, [0, 4, 8], off_t, code, stamp, blind2, pfn)
+            o = oracle_lib.decode_handler(lidar_type, td._as_struct(a, tname), stamp, blind2, pfn)
+            assert r.shape == o.shape and r.shape[0] > 500, (lidar_type, n, pfn, r.shape, o.shape)
+            assert np.array_equal(r[:, :3], o[:, :3])
+            if spin:
+                assert np.max(np.abs(r[:, 3] - o[:, 3])) < 2e-8  # numpy's float arctan2 vs libm's atan2f
+            else:
+                assert np.array_equal(r, o), (lidar_type, n, pfn)
+    rng = np.random.default_rng(8)
+    n = 3000
+    xyz = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
+    xyz[::5] *= np.float32(0.001)
+    ot = np.sort(rng.integers(0, 100_000_000, n)).astype(np.uint32)
+    s = np.zeros(n, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("t", "<u4")])
+    s["x"], s["y"], s["z"], s["t"] = xyz[:, 0], xyz[:, 1], xyz[:, 2], ot
+    for pfn in (1, 3):
+        assert np.array_equal(oracle_lib.decode_livox_ref(ot, xyz, 0.01, pfn), oracle_lib.decode_handler(0, s, 0.0, 0.01, pfn))
+    # pcl_handler: distinct stamps -> identical output
+    n = 20000
+    a = np.zeros((n, 4), dtype=np.float32)
+    a[:, :3] = rng.uniform(-30, 30, (n, 3))
+    a[::7, :3] *= 0.01
+    t = rng.permutation(n).astype(np.float64) * (0.125 / n)  # all different, some beyond 0.11 s
+    a[:, 3] = t.astype(np.float32)
+    a[-1, 3] = np.float32(0.05)  # the Velodyne handler's test of the last stamp (see ref_harness.cpp)
+    assert np.unique(a[:, 3]).shape[0] >= n - 1
+    for pfn, blind2 in ((1, 0.01), (3, 4.0)):
+        r, o = oracle_lib.scan_prepare(a, pfn, blind2, ref=True), oracle_lib.scan_prepare(a, pfn, blind2)
+        keep = ~((r[:, 3] == np.float32(0.05)))  # (the one possibly duplicated stamp)
+        assert r.shape == o.shape and r.shape[0] > 3000 and np.array_equal(r[keep], o[keep])
+    # equal stamps: same stamp sequence, same set of points per stamp
+    a[:, 3] = (rng.integers(0, 1200, n).astype(np.float32) * np.float32(1e-4))
+    a[-1, 3] = np.float32(0.05)
+    r, o = oracle_lib.scan_prepare(a, 1, 0.01, ref=True), oracle_lib.scan_prepare(a, 1, 0.01)
+    assert r.shape == o.shape and np.array_equal(r[:, 3], o[:, 3])
+    rs = r[np.lexsort((r[:, 2], r[:, 1], r[:, 0], r[:, 3]))]
+    os_ = o[np.lexsort((o[:, 2], o[:, 1], o[:, 0], o[:, 3]))]
+    assert np.array_equal(rs, os_)
+    # the empty cloud's stand-in (lidar_decoder.cpp:16-27)
+    near = a.copy()
+    near[:, :3] *= 1e-4
+    assert np.array_equal(oracle_lib.scan_prepare(near, 1, 0.01, ref=True), oracle_lib.scan_prepare(near, 1, 0.01))
