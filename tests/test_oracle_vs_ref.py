@@ -308,3 +308,16 @@ def test_message_handlers_and_pcl_handler_against_the_reference(oracle_lib):
     near = a.copy()
     near[:, :3] *= 1e-4
     assert np.array_equal(oracle_lib.scan_prepare(near, 1, 0.01, ref=True), oracle_lib.scan_prepare(near, 1, 0.01))
+
+
+def test_front_end_and_pruning_golden_vectors(oracle_lib):
+    """Runs everywhere: the restatements of the six message handlers (numpy), of the keep rule + pcl_handler and of the
+    idle path's map pruning against vectors produced by the reference build (tests/golden/ref_front.npz, generator
+    make_ref_front_golden.py) - journey, flag, erased roots / freed nodes and map counts after each of 34 scans."""
+    spec = importlib.util.spec_from_file_location("make_ref_front_golden", os.path.join(HERE, "golden", "make_ref_front_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = dict(np.load(os.path.join(HERE, "golden", "ref_front.npz")))
+    o = mod.scenario(False)
+    assert g["prune_rows"][:, 2].sum() > 300 and (g["prune_rows"][:, 2] > 0).sum() >= 2
+    _assert_same(o, g, "restatements vs reference golden (front end, pruning)")
