@@ -454,6 +454,10 @@ int64_t vina_decode_pointcloud2(int lidar_type, const uint8_t* data, int64_t n_p
                                 int64_t cap);
 int64_t vina_decode_livox(const vina_livox_point* pts, int64_t n_points, double blind2, int point_filter_num,
                           float* xyzt, int64_t cap);
+/* back().curvature of the scan pcl_handler would queue for these decoded points (lidar_decoder.cpp:16-34): the largest
+ * time offset not beyond 0.11 s, 0.09 for an empty cloud - the t_last of vina_sync_push_scan when the scan is sorted
+ * and cut later, on the device. VINA_E_ARG if every stamp is beyond 0.11 s. */
+int vina_scan_last_stamp(const float* xyzt, int64_t n, float* t_last);
 
 /* record per-stage CUDA-event timings (adds event records + one sync per step) */
 int vina_set_profiling(vina_ctx* ctx, int on);

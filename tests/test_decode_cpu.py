@@ -167,3 +167,16 @@ def test_library_against_the_reference_handlers(capi_host):
             g = capi_host.decode_pointcloud2(lidar_type, a.tobytes(), n, dt.itemsize, [0, 4, 8], off_t, code, stamp, blind2, pfn)
             r = op.decode_handler_ref(lidar_type, a.tobytes(), n, dt.itemsize, [0, 4, 8], off_t, code, stamp, blind2, pfn)
             assert g.shape == r.shape and g.shape[0] > 500 and np.array_equal(g, r), (lidar_type, n, pfn, spin)
+
+
+def test_scan_last_stamp_is_what_the_prepared_scan_ends_with(capi_host):
+    rng = np.random.default_rng(2)
+    a = np.zeros((5000, 4), dtype=np.float32)
+    a[:, :3] = rng.uniform(1, 30, (5000, 3))
+    a[:, 3] = rng.uniform(0, 0.13, 5000)
+    assert capi_host.scan_last_stamp(a) == op.scan_prepare(a, 1, -1.0)[-1, 3]
+    assert capi_host.scan_last_stamp(np.zeros((0, 4), dtype=np.float32)) == np.float32(0.09)
+    a[:, 3] += np.float32(0.2)
+    with pytest.raises(capi_host.VinaError) as e:
+        capi_host.scan_last_stamp(a)
+    assert e.value.code == -1

@@ -78,7 +78,7 @@ EXPORTS = [
     "vina_map_set_journey", "vina_map_prune", "vina_odom_journey", "vina_odom_idle",
     "vina_scan_prepare", "vina_scan_prepare_device", "vina_odom_step_prepared",
     "vina_sync_create", "vina_sync_destroy", "vina_sync_push_imu", "vina_sync_push_scan", "vina_sync_pending",
-    "vina_sync_next", "vina_decode_pointcloud2", "vina_decode_livox",
+    "vina_sync_next", "vina_decode_pointcloud2", "vina_decode_livox", "vina_scan_last_stamp",
 ]
 SHARD_IEKF_ALL, SHARD_IEKF_STAGE, SHARD_IEKF_ROUTE, SHARD_IEKF_SEND, SHARD_IEKF_EVAL, SHARD_IEKF_SOLVE, SHARD_IEKF_FINISH = range(7)
 SHARD_RECORD_DOUBLES = 13
@@ -599,6 +599,17 @@ def decode_livox(pts: np.ndarray, blind2: float, point_filter_num: int, cap: int
     if r < 0:
         raise VinaError(int(r), "vina_decode_livox")
     return out[:r].copy()
+
+
+def scan_last_stamp(xyzt: np.ndarray) -> float:
+    """vina_scan_last_stamp (host only): the time offset of the last point the prepared scan will have."""
+    lib = load()
+    a = np.ascontiguousarray(xyzt, dtype=np.float32).reshape(-1, 4)
+    t = C.c_float(0)
+    r = lib.vina_scan_last_stamp(_fp(a), C.c_int64(a.shape[0]), C.byref(t))
+    if r:
+        raise VinaError(r, "vina_scan_last_stamp")
+    return t.value
 
 
 class Sync:

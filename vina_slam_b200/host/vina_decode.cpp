@@ -163,4 +163,30 @@ int64_t vina_decode_livox(const vina_livox_point* pts, int64_t n_points, double 
   }
   return out;
 }
+
+// back().curvature of the scan pcl_handler would queue for these points (src/sensor/lidar_decoder.cpp:16-34): the
+// largest time offset that is not beyond 0.11 s; 0.09 for an empty cloud (its two-point stand-in). What
+// vina_sync_push_scan needs when the scan is only prepared (sorted, cut) later, on the device. Returns 0, or
+// VINA_E_ARG where the reference would be left with an empty cloud (every stamp beyond 0.11 s).
+int vina_scan_last_stamp(const float* xyzt, int64_t n, float* t_last)
+{
+  if ((!xyzt && n > 0) || n < 0 || !t_last) return VINA_E_ARG;
+  if (n == 0)
+  {
+    *t_last = 0.09f;
+    return VINA_OK;
+  }
+  bool any = false;
+  float best = 0.f;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const float t = xyzt[4 * i + 3];
+    if ((double)t > 0.11) continue;
+    if (!any || t > best) best = t;
+    any = true;
+  }
+  if (!any) return VINA_E_ARG;
+  *t_last = best;
+  return VINA_OK;
+}
 }
