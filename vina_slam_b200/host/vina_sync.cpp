@@ -3,7 +3,8 @@
 // src/sensor/lidar_decoder.cpp:36-43) and sync_packages (src/sensor/sync.cpp:18-96) as a small host object
 // behind the C ABI. Pure C++: no device, no context - the scan itself stays with the caller (or on the device,
 // vina_scan_prepare); the queue carries its start time, its last time offset and an opaque tag.
-// The reference's globals and the function-local `static bool pl_ready` become members, the mutex stays (handlers
+// The reference's globals (imu_buf, pcl_buf + time_buf, last_pcl_time) and the function-local `static bool pl_ready`
+// become the members imu_q, scan_q, prev_stamp and holding; the mutex stays (handlers
 // and the odometry thread are different threads there), and exit(0) on a drained IMU buffer becomes VINA_E_STATE.
 #include <deque>
 #include <mutex>
@@ -12,19 +13,19 @@
 
 struct vina_sync
 {
-  std::mutex mBuf;
-  std::deque<vina_imu> imu_buf;
+  std::mutex mtx;
+  std::deque<vina_imu> imu_q;
   struct Scan
   {
     double t_start;
     double t_last;
     int64_t tag;
   };
-  std::deque<Scan> pcl_buf;  // pcl_buf + time_buf
+  std::deque<Scan> scan_q;  // scan_q + time_buf
   double imu_last_time = -1;
   int point_notime = 0;
-  double last_pcl_time = -1;
-  bool pl_ready = false;
+  double prev_stamp = -1;
+  bool holding = false;
   Scan cur = { 0, 0, 0 };            // pl_ptr of the caller, held across calls while the IMU lags behind
   double pcl_beg_time = 0, pcl_end_time = 0;  // p_imu.pcl_beg_time / pcl_end_time
 };
@@ -45,26 +46,26 @@ void vina_sync_destroy(vina_sync* s) { delete s; }
 int vina_sync_push_imu(vina_sync* s, const vina_imu* imu)
 {
   if (!s || !imu) return VINA_E_ARG;
-  std::lock_guard<std::mutex> lk(s->mBuf);
+  std::lock_guard<std::mutex> lk(s->mtx);
   s->imu_last_time = imu->t;
-  s->imu_buf.push_back(*imu);
+  s->imu_q.push_back(*imu);
   return VINA_OK;
 }
 
 int vina_sync_push_scan(vina_sync* s, double t_start, double t_last, int64_t tag)
 {
   if (!s) return VINA_E_ARG;
-  std::lock_guard<std::mutex> lk(s->mBuf);
-  s->pcl_buf.push_back({ t_start, t_last, tag });
+  std::lock_guard<std::mutex> lk(s->mtx);
+  s->scan_q.push_back({ t_start, t_last, tag });
   return VINA_OK;
 }
 
 int vina_sync_pending(vina_sync* s, int32_t* scans, int32_t* imus)
 {
   if (!s) return VINA_E_ARG;
-  std::lock_guard<std::mutex> lk(s->mBuf);
-  if (scans) *scans = (int32_t)s->pcl_buf.size() + (s->pl_ready ? 1 : 0);
-  if (imus) *imus = (int32_t)s->imu_buf.size();
+  std::lock_guard<std::mutex> lk(s->mtx);
+  if (scans) *scans = (int32_t)s->scan_q.size() + (s->holding ? 1 : 0);
+  if (imus) *imus = (int32_t)s->imu_q.size();
   return VINA_OK;
 }
 
@@ -73,48 +74,48 @@ int vina_sync_next(vina_sync* s, int64_t* tag, double* pcl_beg_time, double* pcl
 {
   if (!s || !tag || !pcl_beg_time || !pcl_end_time || !imus || !m || cap < 0) return VINA_E_ARG;
   *m = 0;
-  if (!s->pl_ready)
+  if (!s->holding)
   {
-    std::unique_lock<std::mutex> lk(s->mBuf);
-    if (s->pcl_buf.empty()) return 0;
-    s->cur = s->pcl_buf.front();
-    s->pcl_buf.pop_front();
+    std::unique_lock<std::mutex> lk(s->mtx);
+    if (s->scan_q.empty()) return 0;
+    s->cur = s->scan_q.front();
+    s->scan_q.pop_front();
     lk.unlock();
     s->pcl_beg_time = s->cur.t_start;
     s->pcl_end_time = s->pcl_beg_time + s->cur.t_last;  // + pl_ptr->back().curvature
     if (s->point_notime)
     {
-      if (s->last_pcl_time < 0)
+      if (s->prev_stamp < 0)
       {
-        s->last_pcl_time = s->pcl_beg_time;
+        s->prev_stamp = s->pcl_beg_time;
         *tag = s->cur.tag;
         return 2;  // the first scan only seeds the frame interval
       }
       s->pcl_end_time = s->pcl_beg_time;
-      s->pcl_beg_time = s->last_pcl_time;
-      s->last_pcl_time = s->pcl_end_time;
+      s->pcl_beg_time = s->prev_stamp;
+      s->prev_stamp = s->pcl_end_time;
     }
-    s->pl_ready = true;
+    s->holding = true;
   }
-  std::unique_lock<std::mutex> lk(s->mBuf);
+  std::unique_lock<std::mutex> lk(s->mtx);
   if (s->imu_last_time <= s->pcl_end_time) return 0;
   int n = 0;
   bool overflow = false;
-  double imu_time = s->imu_buf.front().t;  // (not empty: the sample stamped imu_last_time is never consumed below)
-  while (!s->imu_buf.empty() && imu_time < s->pcl_end_time)
+  double stamp = s->imu_q.front().t;  // (not empty: the sample stamped imu_last_time is never consumed below)
+  while (!s->imu_q.empty() && stamp < s->pcl_end_time)
   {
-    imu_time = s->imu_buf.front().t;
-    if (imu_time > s->pcl_end_time) break;
+    stamp = s->imu_q.front().t;
+    if (stamp > s->pcl_end_time) break;
     if (n < cap)
-      imus[n] = s->imu_buf.front();
+      imus[n] = s->imu_q.front();
     else
       overflow = true;
     n++;
-    s->imu_buf.pop_front();
+    s->imu_q.pop_front();
   }
-  const bool drained = s->imu_buf.empty();
+  const bool drained = s->imu_q.empty();
   lk.unlock();
-  s->pl_ready = false;
+  s->holding = false;
   *tag = s->cur.tag;
   *pcl_beg_time = s->pcl_beg_time;
   *pcl_end_time = s->pcl_end_time;
