@@ -172,7 +172,7 @@ def test_point_to_plane_jacobian_and_convergence(oracle_lib):
     R0 = nxt.gt_R @ oracle_lib.exp_so3(np.array([0.002, -0.001, 0.0015]))
     p0 = nxt.gt_p + np.array([0.01, -0.02, 0.01])
     d0 = sums(R0, p0)
-    assert d0["match_num"] > 0.5 * n
+    assert d0["match_num"] > 0.4 * n  # sparse 16-beam scan: voxels further than ~10 m stay below min_point
     H, b = d0["HTH"], d0["HTz"]
     assert np.allclose(H, H.T, rtol=1e-12) and np.all(np.linalg.eigvalsh(H) > 0)
     # Gauss-Newton step from the sums moves the pose towards the ground truth

@@ -43,7 +43,7 @@ def test_oracle_reproduces_reference_golden_vectors(oracle_lib):
     mod = _scenario()
     o = mod.run(lambda cfg: oracle_lib.Odom(cfg), False)
     assert g["boot_key"].shape[0] > 1500 and (g["boot_is_plane"] > 0).sum() > 100 and (g["boot_octo_state"] == 1).sum() > 50
-    assert g["match_flags"].mean() > 0.5 and g["traj"].shape == (4, 3 + 3 + 9 + 225)
+    assert g["match_flags"].mean() > 0.4 and g["traj"].shape == (4, 3 + 3 + 9 + 225)
     _assert_same(o, g, "oracle vs reference golden")
 
 

@@ -128,9 +128,11 @@ class World:
                     # partial walls from both long sides leaving a corridor in the middle
                     rects.append((0, x, oy + 0.0, oy + sy * 0.3, 0.0, sz))
                     rects.append((0, x, oy + sy * 0.7, oy + sy, 0.0, sz))
-                    for j in range(1, ny):
-                        y = oy + j * pitch
-                        if abs(y - (oy + sy / 2)) < pitch * 0.75:
+                    # square pillars one pitch either side of the centre line: the corridor between them (and between
+                    # the wall stubs) stays wider than the largest blind zone of the bundled sensors (3 m) around
+                    # every trajectory, so each rank's seed yields full scans
+                    for y in (oy + sy / 2 - pitch, oy + sy / 2 + pitch):
+                        if ny > 2:
                             h = 0.4  # pillar half-size
                             xc = x + pitch / 2
                             rects.append((0, xc - h, y - h, y + h, 0.0, sz))
@@ -177,8 +179,9 @@ class Trajectory:
         rng = np.random.default_rng(seed + 7919)
         sx, sy, sz = world.size
         self.c = np.array([sx / 2, sy / 2, 1.6]) + world.offset
-        # the handheld path stays inside the pillar-free corridor (pillars stand at y = centre +- 3 m)
-        self.A = np.array([sx * 0.30, sy * (0.06 if handheld else 0.12), 0.25])
+        # every path stays inside the pillar-free corridor (pillars stand at y = centre +- 6 m, faces at +- 5.6 m):
+        # y amplitude 1.8 m (handheld) / 2.1 m leaves >= 3.5 m to the nearest surface beside the path
+        self.A = np.array([sx * 0.30, sy * (0.06 if handheld else 0.07), 0.25])
         self.w = np.array([0.045, 0.09, 0.31]) * (2.0 if handheld else 1.0)
         self.ph = rng.uniform(0, 2 * np.pi, 3)
         k = 4.0 if handheld else 1.0
@@ -330,6 +333,9 @@ class Sequence:
         else:
             pts, keep = self._measure(t_abs, None, rng)
         xyzt = np.concatenate([pts[keep], toff32[keep, None].astype(np.float64)], axis=1).astype(np.float32)
+        if xyzt.shape[0] == 0:
+            raise RuntimeError(f"synthetic scan {k} of seed {self.seed} ({cfg.name}) has no returns outside the "
+                               f"{cfg.blind} m blind zone: the sensor is inside or against a surface of the world")
         end_time = beg + float(xyzt[-1, 3])
         # IMU samples with stamp <= end_time not yet handed out (sync.cpp:63-72)
         k1 = int(math.floor((end_time - self.t0) / self._imu_dt + 1e-9)) + 1
