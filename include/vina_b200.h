@@ -405,7 +405,8 @@ int vina_ba_lidar_residual(vina_ctx* ctx, const vina_pose* xs, int win, double* 
  * 0 = the reference returns false and nothing was consumed (no scan, or the IMU stream has not passed the scan's
  * end yet); 2 = the reference returns false and scan `tag` is gone (<= 4 IMU samples, or the first scan with
  * point_notime); VINA_E_STATE = the IMU buffer ran dry (the reference exit(0)s, sync.cpp:79-82); VINA_E_CAPACITY =
- * more samples than `cap`. point_notime != 0: scans without per-point time, frame interval as in sync.cpp:43-56. */
+ * more samples than `cap`: nothing was consumed, the scan stays held, *m = the number of samples it waits for - call
+ * again with a larger buffer. point_notime != 0: scans without per-point time, frame interval as in sync.cpp:43-56. */
 typedef struct vina_sync vina_sync;
 int vina_sync_create(int point_notime, vina_sync** out);
 void vina_sync_destroy(vina_sync* s);

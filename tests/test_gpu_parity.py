@@ -7,7 +7,8 @@ relative; trajectory within 1 mm / 0.01 deg. Tighter bars are asserted where the
 import numpy as np
 import pytest
 
-from helpers import SMALL_CAPS, bootstrap_pair, col, cov_blocks, rel_err, small_cfg, sort_nodes, ulp_diff_f32
+from helpers import (SMALL_CAPS, bootstrap_pair, col, compare_maps as _compare_maps, cov_blocks, iekf_compare as _iekf_compare,
+                     rel_err, small_cfg, sort_nodes, ulp_diff_f32)
 from vina_slam_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -96,50 +97,6 @@ def test_deskew_rejects_unsorted_scan(oracle_lib, gpu_lib):
     gx.close()
 
 
-def _iekf_compare(oracle_lib, gpu_lib, cfg, n_iter=4, world=None):
-    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, world=world)
-    sc = seq.next_scan(deskewed=True)
-    pnt, var = oracle_lib.var_init(sc.xyzt, cfg)
-    n = pnt.shape[0]
-    # start from a perturbed state so that several iterations and re-associations happen
-    R0 = sc.gt_R @ oracle_lib.exp_so3(np.array([0.004, -0.003, 0.005]))
-    p0 = sc.gt_p + np.array([0.03, -0.02, 0.015])
-    od.set_state(oracle_lib.make_state(R0, p0, sc.gt_v, t=sc.end_time))
-    od.set_dump(True)
-    od.iekf(pnt, var, n_iter)
-    iters = od.last_iters()
-    assert iters >= 2
-    cov = oracle_lib.state_arrays(oracle_lib.make_state())["cov"]
-    rot_var, tsl_var = cov_blocks(cov)
-    gx.pvec_upload(0, pnt, var)
-    gx.iekf_begin(0, rot_var, tsl_var)
-    total = 0
-    for it in range(iters):
-        d = od.iter_dump(it, n)
-        g = gx.iekf_accumulate(d["R_col"], d["p"], debug=True)
-        a = gx.iekf_debug_assoc(n)
-        assert np.array_equal(a["keys"], d["keys"]), f"voxel keys differ at iteration {it}"
-        assert np.array_equal(a["flags"], d["flags"]), f"match flags differ at iteration {it}"
-        assert np.array_equal(a["codes"], d["codes"]), f"associated leaves differ at iteration {it}"
-        assert g["match_num"] == d["match_num"] and d["match_num"] > 0.3 * n
-        m = d["flags"] > 0
-        # sigma_l = J plane_var J^T + n^T var n cancels ~7 digits (plane_var carries the lever arm of a
-        # centre tens of metres from the origin), so rounding-level differences show up at ~1e-9
-        sig_err = np.abs(a["sigma"][m] - d["sigma"][m]) / d["sigma"][m]
-        assert np.max(sig_err) < 1e-6, (it, float(np.max(sig_err)), int((sig_err > 1e-6).sum()), int(m.sum()))
-        assert rel_err(g["HTH"], d["HTH"]) < 1e-4 and rel_err(g["HTz"], d["HTz"]) < 1e-4
-        assert rel_err(g["nnt"], d["nnt"]) < 1e-4
-        # the design is far tighter than the contract
-        assert rel_err(g["HTH"], d["HTH"]) < 1e-7 and rel_err(g["HTz"], d["HTz"]) < 1e-7
-        assert rel_err(g["nnt"], d["nnt"]) < 1e-12
-        # same sums from the non-debug kernel
-        g2 = gx.iekf_accumulate(d["R_col"], d["p"], debug=False)
-        assert np.array_equal(g2["HTH"], g["HTH"]) and g2["match_num"] == g["match_num"]
-        total += d["match_num"]
-    gx.close()
-    return total
-
-
 def test_iekf_association_and_sums_robosense(oracle_lib, gpu_lib):
     _iekf_compare(oracle_lib, gpu_lib, small_cfg("robosense128", 32, 600))
 
@@ -153,37 +110,6 @@ def test_iekf_association_and_sums_mid360_negative_keys(oracle_lib, gpu_lib):
     cfg = synth.small_sensor("mid360", 1, 12000)
     total = _iekf_compare(oracle_lib, gpu_lib, cfg, world=synth.World(offset=(-70.0, -40.0, -9.5)))
     assert total > 0
-
-
-def _compare_maps(mo, mg, exact_cov=False, eig_planes_only=False):
-    mo, mg = sort_nodes(mo), sort_nodes(mg)
-    assert mo.shape[0] == mg.shape[0], "different number of octree nodes"
-    for f in ("key", "code", "layer", "octo_state", "isexist", "has_sw", "is_plane", "last_num", "opt_state",
-              "N_add", "N_fix", "n_point_fix", "n_win_points", "N_local"):
-        assert np.array_equal(mo[f], mg[f]), f"map field {f} differs"
-    assert np.array_equal(mo["voxel_center"], mg["voxel_center"])
-    assert np.array_equal(mo["quater_length"], mg["quater_length"])
-    leaf = mo["octo_state"] == 0
-    # cluster sums: lower triangle + v, bit for bit (same summation order as the reference)
-    low = [0, 1, 2, 4, 5, 8]
-    for f in ("P_add", "P_fix"):
-        assert np.array_equal(mo[f][leaf][:, low], mg[f][leaf][:, low]), f"{f} differs"
-    assert np.array_equal(mo["v_add"][leaf], mg["v_add"][leaf])
-    assert np.array_equal(mo["v_fix"][leaf], mg["v_fix"][leaf])
-    # eigen-decomposition and plane parameters derived from them: bit for bit
-    # (the reference build leaves eig_* uninitialised until a leaf has been judged)
-    em = leaf & (mo["is_plane"] > 0) if eig_planes_only else leaf
-    assert np.array_equal(mo["eig_value"][em], mg["eig_value"][em])
-    assert np.array_equal(mo["eig_vector"][em], mg["eig_vector"][em])
-    assert np.array_equal(mo["center"], mg["center"]) and np.array_equal(mo["normal"], mg["normal"])
-    assert np.array_equal(mo["radius"], mg["radius"])
-    # covariance-derived quantities: the device stores point covariances symmetric -> tolerance
-    # (plane_var = u_c cov_add u_c^T cancels several digits, like sigma_l)
-    # (the plane of an interior node is dead state: the device reuses its storage for the children index)
-    for f, tol, sel in (("cov_add", 1e-12, slice(None)), ("plane_var", 1e-7, leaf)):
-        den = np.maximum(np.abs(mo[f][sel]).max(axis=1, keepdims=True), 1e-300)
-        assert np.max(np.abs(mo[f][sel] - mg[f][sel]) / den) < tol, f"{f} differs"
-    return mo, mg
 
 
 @pytest.mark.parametrize("base,beams,steps", [("robosense128", 32, 600), ("velodyne32", 32, 500)])
@@ -680,7 +606,9 @@ def test_sharded_association_matches_single_gpu(oracle_lib, gpu_lib):
     for sh in shards:
         s_sh = gpu_lib.state_arrays(sh.ctx.get_state())
         for f in ("R", "p", "v", "bg", "ba"):
-            assert np.max(np.abs(s_sh[f] - s_single[f])) < 1e-10, f
+            # (sums in another order, and a point within float rounding of a voxel face keeps its cached leaf on one
+            # GPU but is looked up by key here: nanometres)
+            assert np.max(np.abs(s_sh[f] - s_single[f])) < 5e-9, f
         assert rel_err(s_sh["cov"], s_single["cov"]) < 1e-9
     assert np.linalg.norm(s_single["p"] - sc.gt_p) < 5e-3
     single.close()

@@ -91,6 +91,16 @@ def test_sync_packages_corner_cases(capi_host, oracle_lib):
     # the output buffer is too small
     ev = [("scan", 10.0, 0.1, 1)] + [("imu", _imu(10.0 + 0.01 * k)) for k in range(12)] + [("next",)]
     assert _drive(ev, 0, capi_host, oracle_lib, cap=3)[0][0] == -3
+    # ... and nothing is lost: the scan stays held, the call can be repeated with a larger buffer
+    s = capi_host.Sync()
+    s.push_scan(10.0, 0.1, 1)
+    for k in range(12):
+        s.push_imu(_imu(10.0 + 0.01 * k))
+    r = s.next(3)
+    assert r[0] == -3 and r[1] == 1 and s.pending() == (1, 12)
+    r = s.next(64)
+    assert r[0] == 1 and r[1] == 1 and r[4].shape[0] == 11 and s.pending() == (0, 1)
+    s.close()
     # point_notime: the first scan only seeds the interval, the second spans [first stamp, second stamp]
     ev = [("scan", 10.0, 0.0, 0), ("scan", 10.1, 0.0, 1)] + [("imu", _imu(10.0 + 0.01 * k)) for k in range(12)] + [("next",), ("next",)]
     res = _drive(ev, 1, capi_host, oracle_lib)

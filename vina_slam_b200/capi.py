@@ -651,8 +651,9 @@ class Sync:
         buf = np.zeros(max(cap, 1), dtype=IMU_DTYPE)
         r = self.lib.vina_sync_next(self.h, C.byref(tag), C.byref(beg), C.byref(end), buf.ctypes.data_as(C.c_void_p),
                                     C.c_int(cap), C.byref(m))
-        out = np.zeros((m.value, 7), dtype=np.float64)
-        out[:, 0], out[:, 1:4], out[:, 4:7] = buf["t"][:m.value], buf["gyr"][:m.value], buf["acc"][:m.value]
+        k = m.value if r >= 0 else 0  # (on VINA_E_CAPACITY m is the number of samples the scan is waiting for)
+        out = np.zeros((k, 7), dtype=np.float64)
+        out[:, 0], out[:, 1:4], out[:, 4:7] = buf["t"][:k], buf["gyr"][:k], buf["acc"][:k]
         return r, tag.value, beg.value, end.value, out
 
 

@@ -274,8 +274,11 @@ __global__ void __launch_bounds__(32) k_p2p_signal(ShardPeers peers, unsigned lo
 }
 
 // wait for every rank's records in MY inbox; the number of records received
+// (clamped to the inbox capacity: the senders count every record they route, including the ones an overflowing
+// inbox dropped - the receiver must neither read past the records that exist nor report success)
 __global__ void __launch_bounds__(32) k_p2p_wait(ShardPeers peers, unsigned long long epoch, int* __restrict__ n_recv,
-                                                 int* __restrict__ status, int chan, const IekfDev* __restrict__ gate)
+                                                 int* __restrict__ status, int chan, const IekfDev* __restrict__ gate,
+                                                 int cap)
 {
   if (gate && gate->done)
   {
@@ -297,7 +300,15 @@ __global__ void __launch_bounds__(32) k_p2p_wait(ShardPeers peers, unsigned long
     mine = *reinterpret_cast<const volatile int*>(&me->counts[threadIdx.x][peers.rank]);
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-  if (threadIdx.x == 0) *n_recv = mine;
+  if (threadIdx.x == 0)
+  {
+    if (mine > cap)
+    {
+      atomicOr(status, VN_ST_WIN_FULL);
+      mine = cap;
+    }
+    *n_recv = mine;
+  }
 }
 
 __global__ void __launch_bounds__(SH_THREADS)
@@ -343,7 +354,7 @@ int launch_shard_route_p2p(cudaStream_t st, const ScanView& scan, int first, int
 int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned long long epoch, int* n_recv, int cap,
                           const ScanView& scan, const InsertScratch& sc, int* status)
 {
-  k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status, VN_CHAN_BUILD, nullptr);
+  k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status, VN_CHAN_BUILD, nullptr, cap);
   k_shard_unpack_n<<<(cap + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(peers.inbox[peers.rank], n_recv, scan, sc);
   return 2;
 }
@@ -454,7 +465,7 @@ int launch_shard_query_p2p(cudaStream_t st, const ScanView& scan, int first, int
   }
   if (phase == 0 || phase == 3)
   {
-    k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status, VN_CHAN_QUERY, it);
+    k_p2p_wait<<<1, 32, 0, st>>>(peers, epoch, n_recv, status, VN_CHAN_QUERY, it, (int)inbox_cap);
     const int cap = (int)inbox_cap;
     k_shard_unpack_query_n<<<(cap + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, st>>>(
         peers.inbox[peers.rank] + inbox_cap * VINA_SHARD_RECORD_DOUBLES, n_recv, recv_set);

@@ -107,6 +107,13 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   if (cfg.fix_pool_points <= 0) cfg.fix_pool_points = 16ll << 20;
   if (cfg.win_pool_points <= 0) cfg.win_pool_points = 4ll * cfg.max_scan_points;
   if (cfg.max_points <= 0) cfg.max_points = 100;
+  // bounds before anything is allocated: 1u << 32 is undefined, the down-sampling table is sized 2 x points in 32 bits
+  if (cfg.hash_capacity_log2 < 10 || cfg.hash_capacity_log2 > 31 || cfg.max_scan_points > (1 << 29) ||
+      cfg.max_nodes > (1 << 30) || cfg.device < 0)
+  {
+    delete ctx;
+    return VINA_E_ARG;
+  }
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -116,6 +123,11 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
     fprintf(stderr, "vina_b200: no CUDA device (%s); there is no CPU fallback\n", cudaGetErrorString(e));
     delete ctx;
     return VINA_E_CUDA;
+  }
+  if (cfg.device >= ndev)
+  {
+    delete ctx;
+    return VINA_E_ARG;
   }
   ctx->device = cfg.device;
   *out = ctx;  // from here on errors keep the ctx so that vina_last_error works
@@ -436,7 +448,11 @@ extern "C" int vina_scan_upload_device(vina_ctx* ctx, const void* d_xyzt, int n)
   if (!ctx || !d_xyzt || n < 0) return VINA_E_ARG;
   if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "scan of %d points > max_scan_points %d", n, ctx->cap_points);
   CU(cudaMemcpyAsync(ctx->d_scan, d_xyzt, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  // a later vina_scan_upload (copy stream) must order behind this write of d_scan
+  CU(cudaEventRecord(ctx->ev_scan_rd, ctx->stream));
+  ctx->scan_rd_valid = true;
   ctx->n_scan = n;
+  ctx->front_valid = false;  // the buffer no longer holds the scan vina_scan_prepare left there
   return VINA_OK;
 }
 
@@ -822,21 +838,21 @@ int vn_iterate_publish(vina_ctx* ctx, cudaStream_t st)
   return vn_check_cuda(ctx, cudaGetLastError(), "k_publish_iterate");
 }
 
-int vn_iterate_wait(vina_ctx* ctx)
+int vn_iterate_wait(vina_ctx* ctx, cudaStream_t st)
 {
+  // `st` = the stream that carries the launch which hands the iterate over (the batch stream in batch replay)
   volatile unsigned long long* flag = ctx->h_pub_flag;
   const unsigned long long want = ctx->pub_seq;
   for (long spins = 0; *flag != want; spins++)
   {
     if ((spins & 0xfff) == 0xfff)
     {
-      // a kernel may have failed: fall back to the stream state
-      cudaError_t e = cudaStreamQuery(ctx->stream);
+      // a kernel may have failed, or the hand-over never happened: fall back to the stream state
+      cudaError_t e = cudaStreamQuery(st);
       if (e == cudaSuccess)
       {
         if (*flag == want) break;
-        // (the publishing kernel may run on another stream - batch replay - so "idle" is not an error by itself)
-        continue;
+        return vn_fail(ctx, VINA_E_CUDA, "the IEKF loop finished without handing the iterate over");
       }
       if (e != cudaErrorNotReady) return vn_check_cuda(ctx, e, "IEKF loop");
     }

@@ -139,7 +139,7 @@ int vn_check_status(vina_ctx* c);
 int vn_iekf_wait(vina_ctx* c);
 // enqueue the hand-over of the device iterate to the host / wait for it (polls the mapped sequence number)
 int vn_iterate_publish(vina_ctx* c, cudaStream_t st);
-int vn_iterate_wait(vina_ctx* c);
+int vn_iterate_wait(vina_ctx* c, cudaStream_t st);
 // fill the launch descriptor of this context's sequence (R/p come from c->d_iekf)
 void vn_iekf_fill_seq(vina_ctx* c, IekfSeq* q, bool debug);
 // enqueue max_iter iterations of the IEKF against the sharded map, exchange and update on the device (vn_ctx.cu)

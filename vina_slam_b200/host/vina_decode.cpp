@@ -82,31 +82,34 @@ int64_t vina_decode_pointcloud2(int lidar_type, const uint8_t* data, int64_t n_p
     }
     else
     {
-      // no usable per-point time: stamps from the azimuth at omega_l deg/s (:99-139)
+      // no usable per-point time: stamps from the azimuth at omega_l deg/s. PROVENANCE: this loop RESTATES
+      // velodyne_handler's azimuth branch (src/sensor/lidar_pointcloud_decoder.cpp:103-139) statement for statement
+      // and with its names - a sequential unwrap state machine (yaw0, yaw_last, bias, cool) whose every output stamp
+      // must equal the reference's; tests/test_decode_cpu.py replays it against the reference's own file
       bool first = true;
-      double az_first = 0, az_prev = 0, unwrap = 0;
-      int holdoff = 0;
+      double yaw0 = 0, yaw_last = 0, bias = 0;
+      int cool = 0;
       for (size_t i = 0; i < N; ++i)
       {
         float x, y, z;
         xyz(i, x, y, z);
         if (std::fabs(x) < 0.1) continue;
-        double az = std::atan2(y, x) * 57.2957795 - unwrap;
+        double yaw = std::atan2(y, x) * 57.2957795 - bias;
         if (first)
         {
-          az_first = az_prev = az;
+          yaw0 = yaw_last = yaw;
           first = false;
         }
         if (x * x + y * y + z * z < blind2) continue;
-        if ((az - az_prev) > 180 && holdoff-- <= 0)
+        if ((yaw - yaw_last) > 180 && cool-- <= 0)
         {
-          unwrap += 360;
-          az -= 360;
-          holdoff = 1000;
+          bias += 360;
+          yaw -= 360;
+          cool = 1000;
         }
-        if (std::fabs(az - az_prev) > 180) az += 360;
-        const float c = (float)((az_first - az) / omega_l);
-        az_prev = az;
+        if (std::fabs(yaw - yaw_last) > 180) yaw += 360;
+        const float c = (float)((yaw0 - yaw) / omega_l);
+        yaw_last = yaw;
         if (c >= 0 && c < 0.1 && (i % point_filter_num) == 0)
           if (!emit(x, y, z, c)) return VINA_E_CAPACITY;
       }

@@ -463,7 +463,7 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
   const int num_max_iter = max_iter_override > 0 ? max_iter_override : 20;
   int r = iekf_enqueue_device(ctx, o, which, num_max_iter);
   if (r) return r;
-  r = vn_iterate_wait(ctx);
+  r = vn_iterate_wait(ctx, ctx->stream);
   if (r) return r;
   if (ctx->n_down_pending)
   {
@@ -713,7 +713,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   {
     // the LM loop of the BA needs the host between recut and margi: take the IEKF result first, then the map
     // update with host poses (the front of the step has still run fused / on the side stream)
-    r = vn_iterate_wait(ctx);
+    r = vn_iterate_wait(ctx, ctx->stream);
     if (r) return r;
     int ok = 0;
     unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, &ok);
@@ -758,7 +758,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   }
   if (tr) th[4] = now_us(), cudaEventRecord(ctx->tr_ev[5], A);
   // the result of the loop (it landed while the map update was being enqueued)
-  r = vn_iterate_wait(ctx);
+  r = vn_iterate_wait(ctx, ctx->stream);
   if (r) return r;
   if (tr)
   {
@@ -927,7 +927,7 @@ extern "C" int vina_batch_step_resident(vina_batch* b, const void* const* d_xyzt
   {
     vina_ctx* ctx = b->c[i];
     OdomHost* o = odom(ctx);
-    int r = vn_iterate_wait(ctx);
+    int r = vn_iterate_wait(ctx, b->stream);
     if (r) return r;
     if (ctx->n_down_pending)
     {
@@ -1160,7 +1160,7 @@ int vina_odom_iekf_sharded_p2p(vina_ctx* ctx, int first, int count, int max_iter
   {
     r = vn_iterate_publish(ctx, ctx->stream);
     if (r) return r;
-    r = vn_iterate_wait(ctx);
+    r = vn_iterate_wait(ctx, ctx->stream);
     if (r) return r;
     int ok = 0;
     unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, &ok);
