@@ -53,7 +53,9 @@ def dist_env():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index):
+        """index: one GPU index or a comma-separated list (rank 0 samples every GPU of the job: one nvidia-smi client
+        instead of one per rank - each query takes the driver's lock and shows up in the other ranks' step times)"""
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
@@ -69,16 +71,17 @@ class ClockSampler(threading.Thread):
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(float(f[0]))
-                    self.max_mhz = float(f[1])
-                    for nm, v in zip(names, f[2:6]):
-                        if v.lower().startswith("active"):
-                            self.reasons.add(nm)
+                for row in out.strip().splitlines():
+                    f = [x.strip() for x in row.split(",")]
+                    if len(f) >= 6:
+                        self.samples.append(float(f[0]))
+                        self.max_mhz = float(f[1])
+                        for nm, v in zip(names, f[2:6]):
+                            if v.lower().startswith("active"):
+                                self.reasons.add(nm)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.25)
 
     def stop(self):
         self._halt.set()
@@ -234,13 +237,13 @@ def main_ours(args, cfg):
         gx.set_profiling(profiled)
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-        tm_rows, traj = [], 0.0
+        tm_rows, traj, traj_p_pass = [], 0.0, []
         barrier()
         for k, sc in enumerate(scans):
             if k == W:
                 barrier()
-                if not profiled:
-                    sampler = ClockSampler(local)
+                if not profiled and rank == 0:
+                    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local)
                     sampler.start()
             flush.fill_(k & 0xFF)  # evict L2 between timed iterations (outside the timed segments)
             ev0[k].record(stream)
@@ -250,6 +253,7 @@ def main_ours(args, cfg):
             if k >= W:
                 tm_rows.append(gx.timings())
                 traj = max(traj, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
+                traj_p_pass.append(np.array(st.p[:]))
         barrier()
         if not profiled:
             clocks = sampler.stop() if sampler else {}
@@ -257,6 +261,7 @@ def main_ours(args, cfg):
             t_res = float(step_ms.sum()) * 1e-3
             launches = int(sum(t.kernel_launches for t in tm_rows))
             traj_err = traj
+            traj_p = traj_p_pass
             ba_runs, ba_iters = (gx.ba_stats()[0] - (W - BA_WARMUP + 1), gx.ba_stats()[1]) if args.ba else (0, 0)
             gx.close()
     pts = sum(sc.xyzt.shape[0] for sc in scans[W:])
@@ -314,31 +319,37 @@ def main_ours(args, cfg):
     t_e2e = float(e2e_ms.sum()) * 1e-3
     gx.close()
 
-    # ---- leg 3: batch replay (config 5): B sequences per GPU in lock step through vina_batch ----------------
-    # per-sequence stages on the contexts' own streams; the IEKF iterations of all B sequences are ONE k_iekf
-    # launch per iteration (grid = blocks x B) - the bandwidth-shaped form of the kernel
+    # ---- leg 3: batch replay (BASELINE.json configs[4]): B INDEPENDENT sequences (seeds base + 0 .. B-1, own maps) on
+    # one GPU in lock step through vina_batch - per-sequence stages on the contexts' own streams, the IEKF
+    # iterations of all B sequences as ONE k_iekf launch per iteration (grid = blocks x B), the bandwidth-shaped form
+    # of the kernel. Sequence 0 is the sequence of the legs above: its trajectory must come out the same.
+    # (single-GPU runs only, like cpu_baseline: N x B full-size sequences would take minutes to generate)
     batch = None
-    if args.batch > 1:
+    if args.batch > 1 and world == 1:
         B = args.batch
+        more = synth.gen_sequences(cfg, [cfg.seed + b for b in range(1, B)], cfg.win_size, W + K)
+        seqs = [(boots, scans)] + more
         ctxs = []
         for b in range(B):
             g = capi.Ctx(cfg, **caps)  # own CUDA stream each
-            for sc in boots:
+            for sc in seqs[b][0]:
                 g.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
-            g.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+            g.set_imu_anchor(seqs[b][0][-1].end_time, seqs[b][0][-1].imu[-1])
             ctxs.append(g)
         bat = capi.Batch(ctxs)
-        d_sc = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
+        d_sc = [[torch.from_numpy(sc.xyzt).to(dev) for sc in seqs[b][1]] for b in range(B)]
         torch.cuda.synchronize(dev)
         lt, lb = 0.0, 0.0  # device time / algorithmic bytes of the batched launches with all sequences active
         n_l = 0
+        b_pts, b_err, seq0_dev = 0.0, 0.0, 0.0
         for lo, hi in ((0, W), (W, W + K)):
             barrier()
             t0 = time.perf_counter()
             for k in range(lo, hi):
-                sc = scans[k]
-                bat.step_resident([d_sc[k].data_ptr()] * B, [sc.xyzt.shape[0]] * B, [sc.beg_time] * B,
-                                  [sc.end_time] * B, [sc.imu] * B, True, MAX_ITER)
+                row = [seqs[b][1][k] for b in range(B)]
+                outs = bat.step_resident([d_sc[b][k].data_ptr() for b in range(B)], [sc.xyzt.shape[0] for sc in row],
+                                         [sc.beg_time for sc in row], [sc.end_time for sc in row], [sc.imu for sc in row],
+                                         True, MAX_ITER)
                 if lo == W:
                     ms, _ = bat.iekf_time()
                     its = min(g.timings().iekf_iters for g in ctxs)
@@ -347,33 +358,56 @@ def main_ours(args, cfg):
                         lb += B * (80.0 * n_mean + 256.0 * U + 16.0 * miss_j + 34 * 8)
                         lt += ms[j] * 1e-3
                         n_l += 1
+                    b_pts += sum(sc.xyzt.shape[0] for sc in row)
+                    b_err = max(b_err, max(float(np.linalg.norm(np.array(o.p[:]) - sc.gt_p)) for o, sc in zip(outs, row)))
+                    seq0_dev = max(seq0_dev, float(np.linalg.norm(np.array(outs[0].p[:]) - traj_p[k - W])))
             bat.sync()
             torch.cuda.synchronize(dev)
             t_batch = time.perf_counter() - t0
         bat.close()
         for g in ctxs:
             g.close()
-        batch = {"sequences_per_gpu": B, "seconds": t_batch, "points": float(B * pts), "launch_s": lt, "launch_bytes": lb,
-                 "launches": n_l}
+        del d_sc
+        batch = {"sequences_per_gpu": B, "seconds": t_batch, "points": b_pts, "launch_s": lt, "launch_bytes": lb,
+                 "launches": n_l, "gt_traj_err_m": b_err, "seq0_dev": seq0_dev}
 
     # ---- max over ranks, aggregate --------------------------------------------------------------------
     from vina_slam_b200 import replicas
 
+    per_rank = None
+    if world > 1:  # every rank's own figures, for the record (the line's value uses the slowest rank's time)
+        mine = torch.tensor([1e3 * t_res / K, 1e3 * t_e2e / K, iters / K, pts / K], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+        per_rank = {"ms_per_step": allr[:, 0].tolist(), "e2e_ms_per_step": allr[:, 1].tolist(),
+                    "iekf_iters_per_step": allr[:, 2].tolist(), "pts_per_scan": allr[:, 3].tolist()}
     pts_all, (t_res, t_e2e) = replicas.reduce_throughput(pts, [t_res, t_e2e], device=dev)
     if batch:
         bp, (bt,) = replicas.reduce_throughput(batch["points"], [batch["seconds"]], device=dev)
         ach = batch["launch_bytes"] / batch["launch_s"] / 1e9 if batch["launch_s"] > 0 else 0.0
         batch = {"sequences_per_gpu": batch["sequences_per_gpu"], "value": bp / bt, "unit": UNIT,
+                 "seeds": [cfg.seed + b for b in range(batch["sequences_per_gpu"])],
+                 "gt_traj_err_m": batch["gt_traj_err_m"],
+                 "sequence0_max_dev_from_single_context_run_m": batch["seq0_dev"],
                  "ms_per_scan_amortised": 1e3 * bt / (K * batch["sequences_per_gpu"]),
                  "roofline": {"bound": "hbm", "kernel": "k_iekf (one launch for all sequences)", "achieved": ach,
                               "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                               "launch_us": 1e6 * batch["launch_s"] / max(batch["launches"], 1),
                               "bytes_per_launch": batch["launch_bytes"] / max(batch["launches"], 1),
                               "launches_timed": batch["launches"]},
-                 "note": "vina_batch: B contexts replaying the same seeded sequence in lock step on one GPU; "
+                 "note": "vina_batch: B independent sequences (own seeds, own maps) in lock step on one GPU; "
                          "per-sequence stages on own streams, IEKF iterations batched into one launch; wall "
-                         "clock over the K steps; no explicit L2 flush in this leg (the point sets of all B "
-                         "sequences are rewritten every step, the B maps stay hot as they would in production)"}
+                         "clock over the K steps; no explicit L2 flush in this leg (the working set of the B "
+                         "sequences - B maps, B x 21 MB of points rewritten every step - exceeds what stays "
+                         "resident between a sequence's consecutive steps only partly: B maps stay hot as they "
+                         "would in production)"}
+
+    # ---- N > 1: the same scans through the map sharded by voxel-hash range (BASELINE.json configs[4]):
+    # fused route + exchange over peer memory, IEKF against the sharded map, union checked against one GPU's map
+    shard_res = None
+    if world > 1 and not args.no_sharded:
+        shard_res = run_sharded(cfg, rank, world, local, dev, 3, min(K, 10), p2p=True, query=True, verify=True)
 
     if rank == 0:
         cpu = None
@@ -412,6 +446,10 @@ def main_ours(args, cfg):
             "stage_ms": stage,
             "clocks": clocks,
         }
+        if per_rank:
+            line["per_rank"] = per_rank
+        if shard_res:
+            line["sharded"] = shard_res
         if cpu:
             line["cpu_baseline"] = cpu
         if batch:
@@ -422,41 +460,56 @@ def main_ours(args, cfg):
 
 
 # --------------------------------------------------------------------------- sharded map build
-def main_sharded(args, cfg):
+def run_sharded(cfg, rank, world, local, dev, W, K, p2p=True, query=True, verify=True, prefill=0):
     """Map partitioned by voxel-hash range over the ranks (BASELINE.json configs[4]). Every rank holds the scan,
-    routes its ascending slice of the down-sampled points to the owners (one all-to-all of 104-byte records over
-    NCCL / NVLink per scan), inserts what it received, recut + margi locally. Strong scaling: the scans are the
-    same at every N. Rank 0 also builds the whole map on its own and the digests are compared (bit-exactness)."""
+    routes its ascending slice of the down-sampled points to the owners (p2p: the routing kernel stores the records
+    straight into the owners' inboxes over peer memory / NVLink; else one NCCL all-to-all of 104-byte records),
+    inserts what it received, recut + margi locally; with `query` the IEKF of every scan runs against the sharded
+    map first (fused: queries and the 34 sums travel through peer memory, no collective, no host in the loop).
+    Strong scaling: the scans are the same at every N. verify: after the timed scans rank 0 builds the whole map on
+    one context from the same scans and the digests are compared (bit-exactness of the union) - outside the timed
+    region. prefill: root voxels put into every rank's shard beforehand (planar patches far away from the building),
+    the regime the split is for: a map that does not fit one GPU. Returns the result dict on rank 0 (None elsewhere).
+    The process group must be initialised when world > 1."""
     import torch
     import torch.distributed as dist
 
     from vina_slam_b200 import capi, sharded
 
-    rank, world, local = dist_env()
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    W, K = args.warmup, args.steps
     seq = synth.Sequence(cfg, seed=cfg.seed)
     scans = [seq.next_scan(deskewed=True) for _ in range(cfg.win_size + W + K)]
-    caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), max_nodes=1 << 20, hash_capacity_log2=21,
-                device=local)
+    n_fill = int(prefill)
+    caps = dict(max_scan_points=max(300000, cfg.n_points + 1024), device=local,
+                max_nodes=int(n_fill * 1.15) + (1 << 20),
+                hash_capacity_log2=max(21, int(np.ceil(np.log2(max(n_fill, 1) * 2.5)))),
+                fix_pool_points=int(n_fill * 25 * 1.1) + (16 << 20))
+    free0 = torch.cuda.mem_get_info(dev)[0]
     sh = sharded.MapShard(capi.Ctx(cfg, **caps), rank, world, device=dev)
-    if args.p2p:
+    if p2p:
         sh.p2p_setup(caps["max_scan_points"])  # inboxes + CUDA IPC handles all-gathered over the group
-    iek = sharded.ShardedIekf(sh) if args.query else None
-    ref = capi.Ctx(cfg, **caps) if (rank == 0 and args.verify) else None
-    q_iters, q_err, q_ref_err, q_ref_iters, q_ms = 0, 0.0, 0.0, 0, 0.0
+    t_fill = 0.0
+    if n_fill:
+        # world x n_fill root voxels through the sharded build itself (every rank generates the same clouds and
+        # routes its slice; the owners end up with ~n_fill voxels each)
+        z9 = np.zeros(9)
+        ident = np.eye(3).reshape(-1)
+
+        def feed(gx):
+            gx.downsample()
+            nd = gx.n_down()
+            gx.var_init(1)
+            first, cnt = sharded.slice_of(nd, rank, world)
+            (sh.update_p2p if p2p else sh.update)(first, cnt, 0, ident, np.zeros(3), z9, z9)
+
+        t_fill = prefill_map(sh.ctx, n_fill * world, dev, feed=feed)
+    iek = sharded.ShardedIekf(sh) if query else None
+    q_iters, q_err, q_ms = 0, 0.0, 0.0
     stream = torch.cuda.current_stream(dev)
     d_scans = [torch.from_numpy(sc.xyzt).to(dev) for sc in scans]
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     n_down_tot, n_recv_tot = 0, 0
+    final_states = []
 
     def barrier():
         if world > 1:
@@ -483,65 +536,147 @@ def main_sharded(args, cfg):
             sh.ctx.var_init(0)
             torch.cuda.synchronize(dev)
             tq0 = time.perf_counter()
-            q_iters += (iek.run_p2p if args.p2p else iek.run)(*sharded.slice_of(sc.xyzt.shape[0], rank, world), MAX_ITER)
+            q_iters += (iek.run_p2p if p2p else iek.run)(*sharded.slice_of(sc.xyzt.shape[0], rank, world), MAX_ITER)
             if k >= cfg.win_size + W:
                 q_ms += 1e3 * (time.perf_counter() - tq0)  # the loop ends with the converged state on the host
             got = capi.state_arrays(sh.ctx.get_state())
             q_err = max(q_err, float(np.linalg.norm(got["p"] - sc.gt_p)))
-            if ref is not None:
-                ref.set_state(pert)
-                ref.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
-                ref.var_init(0)
-                q_ref_iters += ref.odom_iekf(0, MAX_ITER, host_solve=True)[0]
-                q_ref_err = max(q_ref_err, float(np.linalg.norm(got["p"] - capi.state_arrays(ref.get_state())["p"])))
+            final_states.append(got["p"].copy())
         sh.ctx.downsample()
         nd = sh.ctx.n_down()
         sh.ctx.var_init(1)
         first, cnt = sharded.slice_of(nd, rank, world)
-        got = (sh.update_p2p if args.p2p else sh.update)(first, cnt, 0, Rc, sa["p"], rv, tv)
+        got_n = (sh.update_p2p if p2p else sh.update)(first, cnt, 0, Rc, sa["p"], rv, tv)
         if k >= cfg.win_size + W:
             n_down_tot += nd
-            n_recv_tot += got
-        if ref is not None:
-            ref.set_state(st)
-            ref.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
-            ref.downsample()
-            ref.n_down()
-            ref.var_init(1)
-            ref.odom_map_update()
+            n_recv_tot += got_n
     ev1.record(stream)
     barrier()
     t = ev0.elapsed_time(ev1) * 1e-3
     tt = torch.tensor([t], dtype=torch.float64, device=dev)
-    dig = torch.tensor([sharded.map_digest(sh.ctx.map_export()), sh.ctx.map_count()[0], n_recv_tot], dtype=torch.int64,
-                       device=dev)
+    exp = sh.ctx.map_export() if not n_fill else None
+    if exp is not None and n_fill == 0:
+        dig_val, n_nodes = sharded.map_digest(exp), sh.ctx.map_count()[0]
+    else:
+        dig_val, n_nodes = 0, sh.ctx.map_count()[0]
+    dig = torch.tensor([dig_val, n_nodes, n_recv_tot], dtype=torch.int64, device=dev)
+    mem_gb = (free0 - torch.cuda.mem_get_info(dev)[0]) / 1e9
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(dig)
+    out = None
     if rank == 0:
         pts = sum(sc.xyzt.shape[0] for sc in scans[cfg.win_size + W:])
-        line = {"metric": "pts/s voxel-map build sharded by hash range (down-sample -> var_init -> route -> all-to-all "
-                          "-> insert -> recut -> margi, per scan)", "value": pts / float(tt[0]), "unit": UNIT,
-                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * float(tt[0]) / K,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(cfg), "mode": "sharded-map", "parallelism": f"hash-range x{world}",
-                           "exchange": ("records stored into the owners' inboxes by the routing kernel over peer memory "
-                                        "(CUDA IPC / NVLink), device-side flags" if args.p2p else
-                                        "NCCL all_to_all_single of staged records"),
-                           "down_points_per_scan": n_down_tot / K, "routed_points_per_scan": int(dig[2]) / K,
-                           "record_bytes": 8 * sharded.REC, "nodes": int(dig[1])},
-                "gpu_launches": None}
+        out = {"value": pts / float(tt[0]), "unit": UNIT, "ms_per_scan": 1e3 * float(tt[0]) / K, "scaling": "strong",
+               "workload": workload_name(cfg), "parallelism": f"hash-range x{world}",
+               "what": "per scan: " + ("IEKF against the sharded map, then " if query else "") +
+                       "down-sample -> var_init -> route + exchange -> insert -> recut -> margi on every shard",
+               "exchange": ("records stored into the owners' inboxes by the routing kernel over peer memory "
+                            "(CUDA IPC / NVLink), device-side flags" if p2p else "NCCL all_to_all_single of staged records"),
+               "down_points_per_scan": n_down_tot / K, "routed_points_per_scan": int(dig[2]) / K,
+               "record_bytes": 8 * sharded.REC, "nodes_all_shards": int(dig[1]),
+               "prefilled_root_voxels_per_rank": n_fill, "prefill_seconds": t_fill, "device_memory_GB_rank0": mem_gb}
         if iek is not None:
-            line["config"]["sharded_iekf"] = {"loop": ("fused: queries and the 34 sums travel through peer memory, update on every "
-                                                       "rank's device iterate, no host sync inside the loop" if args.p2p else
-                                                       "per iteration: route, NCCL all-to-all, accumulate, NCCL all-reduce, host update"),
-                                              "loop_ms_per_scan_rank0_wall": q_ms / K,
-                                              "iters_per_scan": q_iters / (W + K), "pos_err_vs_ground_truth_m": q_err,
-                                              "pos_diff_vs_single_gpu_m": q_ref_err if ref is not None else None,
-                                              "iters_per_scan_single_gpu": q_ref_iters / (W + K) if ref is not None else None}
-        if ref is not None:
-            line["config"]["union_equals_single_gpu_map"] = bool(int(dig[0]) == sharded.map_digest(ref.map_export()))
-            line["config"]["single_gpu_nodes"] = ref.map_count()[0]
+            out["sharded_iekf"] = {"loop": ("fused: queries and the 34 sums travel through peer memory, update on every "
+                                            "rank's device iterate, no host sync inside the loop" if p2p else
+                                            "per iteration: route, NCCL all-to-all, accumulate, NCCL all-reduce, host update"),
+                                   "loop_ms_per_scan_rank0_wall": q_ms / K, "iters_per_scan": q_iters / (W + K),
+                                   "pos_err_vs_ground_truth_m": q_err}
+        if verify and n_fill == 0:
+            # the same scans through ONE context (outside the timed region): the union of the shards must be this map
+            ref = capi.Ctx(cfg, **caps)
+            q_ref_err, q_ref_iters = 0.0, 0
+            for k, sc in enumerate(scans):
+                st = capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time)
+                ref.scan_upload_device(d_scans[k].data_ptr(), sc.xyzt.shape[0])
+                if iek is not None and k >= cfg.win_size:
+                    pert = capi.make_state(sc.gt_R @ synth.rot_exp(np.array([1e-3, -1e-3, 1e-3])),
+                                           sc.gt_p + np.array([0.01, -0.01, 0.005]), sc.gt_v, t=sc.end_time)
+                    ref.set_state(pert)
+                    ref.var_init(0)
+                    q_ref_iters += ref.odom_iekf(0, MAX_ITER, host_solve=True)[0]
+                    q_ref_err = max(q_ref_err, float(np.linalg.norm(
+                        final_states[k - cfg.win_size] - capi.state_arrays(ref.get_state())["p"])))
+                ref.set_state(st)
+                ref.downsample()
+                ref.n_down()
+                ref.var_init(1)
+                ref.odom_map_update()
+            out["union_equals_single_gpu_map"] = bool(int(dig[0]) == sharded.map_digest(ref.map_export()))
+            out["single_gpu_nodes"] = ref.map_count()[0]
+            if iek is not None:
+                out["sharded_iekf"]["pos_diff_vs_single_gpu_m"] = q_ref_err
+                out["sharded_iekf"]["iters_per_scan_single_gpu"] = q_ref_iters / (W + K)
+            ref.close()
+    barrier()
+    sh.ctx.close()
+    return out
+
+
+def prefill_map(gx, n_vox, dev, seed=1234, origin=(3000.0, 3000.0, 100.0), per_scan_vox=10000, ppv=25, feed=None):
+    """n_vox root voxels with a small planar patch each (ppv points per 1 m voxel), inserted through the product path
+    (feed = what to do with each uploaded cloud; default: the single-context map update), in a slab `origin` away from
+    the building. Returns the seconds it took."""
+    import torch
+
+    from vina_slam_b200 import capi
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    gx.set_state(capi.make_state(np.eye(3), np.zeros(3), np.zeros(3)))
+    side = int(np.ceil(np.sqrt(n_vox / 8)))  # X x Y x 8 layers
+    t0 = time.perf_counter()
+    for v0 in range(0, n_vox, per_scan_vox):
+        idx = torch.arange(v0, min(v0 + per_scan_vox, n_vox), device=dev)
+        ix, iy, iz = idx % side, (idx // side) % side, idx // (side * side)
+        c = torch.stack([ix, iy, iz], 1).double() + 0.5 + torch.tensor(list(origin), device=dev, dtype=torch.float64)
+        nrm = torch.randn((idx.numel(), 3), generator=gen, device=dev, dtype=torch.float64)
+        nrm = nrm / nrm.norm(dim=1, keepdim=True)
+        a = torch.linalg.cross(nrm, torch.tensor([0.3, 0.5, 0.81], device=dev, dtype=torch.float64).expand_as(nrm))
+        a = a / a.norm(dim=1, keepdim=True)
+        b = torch.linalg.cross(nrm, a)
+        uv = (torch.rand((idx.numel(), ppv, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 0.56
+        nz = torch.randn((idx.numel(), ppv, 1), generator=gen, device=dev, dtype=torch.float64) * 0.004
+        pts = c[:, None, :] + uv[..., :1] * a[:, None, :] + uv[..., 1:] * b[:, None, :] + nz * nrm[:, None, :]
+        xyzt = torch.cat([pts.reshape(-1, 3), torch.zeros((idx.numel() * ppv, 1), device=dev, dtype=torch.float64)],
+                         1).float().contiguous()
+        torch.cuda.synchronize(dev)
+        gx.scan_upload_device(xyzt.data_ptr(), xyzt.shape[0])
+        if feed is not None:
+            feed(gx)
+            continue
+        gx.downsample()
+        gx.n_down()
+        gx.var_init(1)
+        gx.odom_map_update()
+    gx.sync()
+    return time.perf_counter() - t0
+
+
+def main_sharded(args, cfg):
+    """--mode sharded-map: the sharded map build (+ IEKF) alone, as its own JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = dist_env()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r = run_sharded(cfg, rank, world, local, dev, args.warmup, args.steps, p2p=args.p2p or world > 1 and not args.nccl,
+                    query=args.query, verify=args.verify, prefill=args.voxels if args.voxels_set else 0)
+    if rank == 0:
+        line = {"metric": "pts/s voxel-map build sharded by hash range (down-sample -> var_init -> route -> exchange "
+                          "-> insert -> recut -> margi, per scan)", "value": r["value"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_scan"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(cfg), "mode": "sharded-map", **{k: v for k, v in r.items()
+                                                                                      if k not in ("value", "unit")}},
+                "gpu_launches": None}
         emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -586,34 +721,7 @@ def main_bigmap(args, cfg):
         gx.set_stream(stream.cuda_stream)
         t_fill = 0.0
         if fill:
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(1234)
-            gx.set_state(capi.make_state(np.eye(3), np.zeros(3), np.zeros(3)))
-            # a slab of voxels 3000 m away from the building: X x Y x 8 layers
-            side = int(np.ceil(np.sqrt(fill / 8)))
-            t0 = time.perf_counter()
-            for v0 in range(0, fill, per_scan_vox):
-                idx = torch.arange(v0, min(v0 + per_scan_vox, fill), device=dev)
-                ix, iy, iz = idx % side, (idx // side) % side, idx // (side * side)
-                c = torch.stack([ix, iy, iz], 1).double() + 0.5 + torch.tensor([3000.0, 3000.0, 100.0], device=dev)
-                nrm = torch.randn((idx.numel(), 3), generator=gen, device=dev, dtype=torch.float64)
-                nrm = nrm / nrm.norm(dim=1, keepdim=True)
-                a = torch.linalg.cross(nrm, torch.tensor([0.3, 0.5, 0.81], device=dev, dtype=torch.float64).expand_as(nrm))
-                a = a / a.norm(dim=1, keepdim=True)
-                b = torch.linalg.cross(nrm, a)
-                uv = (torch.rand((idx.numel(), ppv, 2), generator=gen, device=dev, dtype=torch.float64) - 0.5) * 0.56
-                nz = torch.randn((idx.numel(), ppv, 1), generator=gen, device=dev, dtype=torch.float64) * 0.004
-                pts = c[:, None, :] + uv[..., :1] * a[:, None, :] + uv[..., 1:] * b[:, None, :] + nz * nrm[:, None, :]
-                xyzt = torch.cat([pts.reshape(-1, 3), torch.zeros((idx.numel() * ppv, 1), device=dev, dtype=torch.float64)],
-                                 1).float().contiguous()
-                torch.cuda.synchronize(dev)
-                gx.scan_upload_device(xyzt.data_ptr(), xyzt.shape[0])
-                gx.downsample()
-                gx.n_down()
-                gx.var_init(1)
-                gx.odom_map_update()
-            gx.sync()
-            t_fill = time.perf_counter() - t0
+            t_fill = prefill_map(gx, fill, dev)
         nodes, roots, slide = gx.map_count()
         for sc in boots:
             gx.bootstrap(sc.xyzt, capi.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
@@ -696,14 +804,20 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ba", action="store_true", help="LocalBA.if_BA: 1 (mid360.yaml / velodyne.yaml): sliding-window BA every scan")
     ap.add_argument("--batch", type=int, default=8, help="concurrent sequences per GPU in the batch-replay leg (0/1 = off)")
-    ap.add_argument("--voxels", type=float, default=1e7, help="bigmap: root voxels to pre-fill")
+    ap.add_argument("--voxels", type=float, default=None, help="bigmap: root voxels to pre-fill (default 1e7); "
+                    "sharded-map: root voxels pre-filled into every rank's shard (default 0)")
+    ap.add_argument("--nccl", action="store_true", help="sharded-map: staged records + NCCL all-to-all instead of the fused exchange")
     ap.add_argument("--mode", default="odometry", choices=["odometry", "sharded-map", "bigmap"],
                     help="odometry = the headline per-scan path (default); sharded-map = map build partitioned by "
                          "voxel-hash range over the ranks (SURVEY 8e)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the hash-range-sharded leg of the default line")
     ap.add_argument("--verify", action="store_true", help="sharded-map: rank 0 also builds the single-GPU map and compares")
     ap.add_argument("--p2p", action="store_true", help="sharded-map: fused route + exchange over peer memory instead of NCCL")
     ap.add_argument("--query", action="store_true", help="sharded-map: also run the IEKF against the sharded map every scan")
     args = ap.parse_args()
+    args.voxels_set = args.voxels is not None
+    if args.voxels is None:
+        args.voxels = 1e7
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     cfg = synth.SENSORS[args.workload]

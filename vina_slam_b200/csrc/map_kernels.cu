@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256)
     cv.tsl[t] = live ? live->cov[(3 + a) + 15 * (3 + b)] : cv_host.tsl[t];
     if (t < 3) x.p[t] = live ? live->p[t] : x_host.p[t];
   }
+  // (the counters of the NEXT insert: ping-pong, no launch spent on zeroing)
+  if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 36) sc.counters_alt[threadIdx.x - 32] = 0;
   __syncthreads();
   int n = n_ptr ? *n_ptr : n_host;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -663,54 +665,129 @@ __device__ __forceinline__ const int* layer_nodes(const MapView& M, const LayerL
   return LL.list[layer];
 }
 
-// OctoTree::recut (octree.cpp:335-393) for the nodes of one layer, then tras_opt's BA-factor
-// marking of the same node (octree.cpp:498-521, local_mapping.cpp:196-200). Leaves that must be
-// subdivided go to the layer's split list (k_split); children of interior nodes are appended to the
-// next layer's node list.
-__global__ void __launch_bounds__(128) k_recut_layer(MapView M, LayerLists LL, int layer)
+// The leaf branch of OctoTree::recut (octree.cpp:335-393) for node n, then tras_opt's BA-factor marking of the same
+// node (octree.cpp:498-521, local_mapping.cpp:196-200). Returns true when the leaf has to be subdivided.
+__device__ bool recut_leaf(const MapView& M, NodeHot& h, NodeCold& c)
+{
+  c.opt_state = -1;
+  if ((double)c.pcr_add.N <= M.min_point[h.layer])
+  {
+    h.flags &= ~VN_FLAG_PLANE;
+    return false;
+  }
+  if (!c.isexist || !c.has_sw) return false;
+  double L[6], ev[3], Q[9];
+  cluster_cov(c.pcr_add, L);
+  eig3_sym(L, ev, Q);
+  for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
+  for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
+  const bool is_plane = (ev[0] < M.min_eigen_value) && ((ev[0] / ev[2]) < M.thre[h.layer]);  // octree.cpp:198-201
+  if (is_plane)
+  {
+    h.flags |= VN_FLAG_PLANE;
+    if (!(ev[0] / ev[1] > 0.12)) c.opt_state = 1;  // tras_opt: this leaf is a BA factor
+    return false;
+  }
+  h.flags &= ~VN_FLAG_PLANE;
+  return h.layer < M.max_layer;
+}
+
+// multi_recut, step 1: the nodes below the roots of surf_map_slide, listed per layer (layer 0 is the slide list
+// itself). EIGHT threads per root, one per first-level child; a thread walks that child's subtree through the
+// children mirrors of NodeHot (one 128-byte line per node, the loads of a level issued together). The trees are at
+// most max_layer <= 3 deep. One atomic per warp and layer reserves the warp's list positions. Thread 0 also clears
+// the counters the NEXT multi_recut will use (ping-pong, so that no launch is spent on zeroing).
+__device__ __forceinline__ int warp_reserve(int* counter, int mine, int lane)
+{
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  return base + incl - mine;
+}
+
+__global__ void __launch_bounds__(128) k_recut_collect(MapView M, LayerLists LL)
+{
+  if (blockIdx.x == 0 && threadIdx.x < 8) LL.count_alt[threadIdx.x] = 0;
+  const int nroots = M.slide_count[M.slide_cur];
+  if (nroots + M.slide_others < M.thread_num) return;  // local_mapping.cpp:150-154
+  const int* roots = M.slide_list[M.slide_cur];
+  const int lane = threadIdx.x & 31;
+  const int total = 8 * nroots;
+  const int stride = gridDim.x * blockDim.x;
+  for (int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < total; t0 += stride)  // warp-uniform trip count
+  {
+    const int t = t0 + lane;
+    int n1 = -1;
+    if (t < total)
+    {
+      const NodeHot& h0 = M.hot[roots[t >> 3]];
+      if (h0.flags & VN_FLAG_INTERIOR) n1 = h0.children[t & 7];
+    }
+    // level 2: the children of n1, level 3: theirs
+    int c2[8], m2 = 0, m3 = 0;
+    unsigned int int2 = 0;  // which level-2 children are interior
+#pragma unroll
+    for (int b = 0; b < 8; b++) c2[b] = -1;
+    if (n1 >= 0)
+    {
+      const NodeHot& h1 = M.hot[n1];
+      if (h1.flags & VN_FLAG_INTERIOR)
+      {
+#pragma unroll
+        for (int b = 0; b < 8; b++) c2[b] = h1.children[b];
+        int f2[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) f2[b] = c2[b] >= 0 ? M.hot[c2[b]].flags : 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+        {
+          if (c2[b] >= 0) m2++;
+          if (f2[b] & VN_FLAG_INTERIOR) int2 |= 1u << b;
+        }
+      }
+    }
+    for (int b = 0; b < 8; b++)
+      if (int2 & (1u << b))
+        for (int d = 0; d < 8; d++) m3 += M.hot[c2[b]].children[d] >= 0 ? 1 : 0;
+    int p1 = warp_reserve(&LL.count[1], n1 >= 0 ? 1 : 0, lane);
+    int p2 = warp_reserve(&LL.count[2], m2, lane);
+    int p3 = __any_sync(0xffffffffu, m3 > 0) ? warp_reserve(&LL.count[3], m3, lane) : 0;
+    if (n1 >= 0) LL.list[1][p1] = n1;
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+      if (c2[b] >= 0) LL.list[2][p2++] = c2[b];
+    for (int b = 0; b < 8; b++)
+      if (int2 & (1u << b))
+        for (int d = 0; d < 8; d++)
+        {
+          const int n3 = M.hot[c2[b]].children[d];
+          if (n3 >= 0) LL.list[3][p3++] = n3;
+        }
+  }
+}
+
+// multi_recut, step 2: OctoTree::recut for every leaf that exists at this point, all layers in ONE launch
+// (blockIdx.y = layer): the subtrees below different nodes are independent, only the children a subdivision creates
+// have to wait for it - those are handled by k_split itself. Leaves that must be subdivided go to the split list.
+__global__ void __launch_bounds__(128) k_recut_all(MapView M, LayerLists LL)
 {
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:150-154
   int nn;
-  const int* nodes = layer_nodes(M, LL, layer, &nn);
+  const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
   {
     const int n = nodes[j];
     NodeHot& h = M.hot[n];
-    NodeCold& c = M.cold[n];
-    if (!(h.flags & VN_FLAG_INTERIOR))
-    {
-      c.opt_state = -1;
-      if ((double)c.pcr_add.N <= M.min_point[h.layer])
-      {
-        h.flags &= ~VN_FLAG_PLANE;
-        continue;
-      }
-      if (!c.isexist || !c.has_sw) continue;
-      double L[6], ev[3], Q[9];
-      cluster_cov(c.pcr_add, L);
-      eig3_sym(L, ev, Q);
-      for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
-      for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
-      const bool is_plane = (ev[0] < M.min_eigen_value) && ((ev[0] / ev[2]) < M.thre[h.layer]);  // octree.cpp:198-201
-      if (is_plane)
-      {
-        h.flags |= VN_FLAG_PLANE;
-        if (!(ev[0] / ev[1] > 0.12)) c.opt_state = 1;  // tras_opt: this leaf is a BA factor
-        continue;
-      }
-      h.flags &= ~VN_FLAG_PLANE;
-      if (h.layer >= M.max_layer) continue;
-      int pos = atomicAdd(&LL.count[4 + layer], 1);
-      LL.split[pos] = n;  // k_split subdivides it and queues its children
-      continue;
-    }
-    if (layer < 3)
-      for (int k = 0; k < 8; k++)
-        if (c.children[k] >= 0)
-        {
-          int pos = atomicAdd(&LL.count[layer + 1], 1);
-          LL.list[layer + 1][pos] = c.children[k];
-        }
+    if (h.flags & VN_FLAG_INTERIOR) continue;
+    if (recut_leaf(M, h, M.cold[n])) LL.split[atomicAdd(&LL.count[4], 1)] = n;
   }
 }
 
@@ -764,7 +841,7 @@ __device__ long long g_split_ts[2][8];
 #define VN_SPLIT_STAMP(k) \
   do \
   { \
-    if (threadIdx.x == 0 && j == 0) g_split_ts[layer & 1][k] = clock64(); \
+    if (threadIdx.x == 0 && j == 0) g_split_ts[round & 1][k] = clock64(); \
   } while (0)
 #else
 #define VN_SPLIT_STAMP(k) \
@@ -796,7 +873,7 @@ __device__ __forceinline__ int split_rows_before(const unsigned int (*bm)[8], in
   return r;
 }
 
-__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int layer, int win_count, PoseBuf xb,
+__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int round, int win_count, PoseBuf xb,
                                                          LivePose lv)
 {
   extern __shared__ double split_smem[];
@@ -822,10 +899,14 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   const bool chain = ct >= 0;
   role_init(chain ? ct : 0, L);  // L.ck = ct % 9
   const int my_k = chain ? ct / 9 : 0;  // cluster chain of this thread
-  const int nsplit = LL.count[4 + layer];
+  // the leaves of this round: those k_recut_all found (round 0) or children of the previous round's leaves that
+  // have to be subdivided themselves; the rounds' lists lie one behind the other in LL.split
+  const int nsplit = LL.count[4 + round];
+  int sbase = 0;
+  for (int q = 0; q < round; q++) sbase += LL.count[4 + q];
   for (int j = blockIdx.x; j < nsplit; j += gridDim.x)
   {
-    const int n = LL.split[j];
+    const int n = LL.split[sbase + j];
     NodeCold& c = M.cold[n];
     NodeHot& h = M.hot[n];
     const bool store = (h.layer + 1) < M.max_layer;
@@ -1183,12 +1264,19 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       for (int k = 0; k < 8; k++) h.children[k] = c.children[k];  // mirror read by k_iekf
       h.flags |= VN_FLAG_INTERIOR;
     }
-    if (t < 8 && kid[t] >= 0 && layer < 3)
-    {
-      int pos = atomicAdd(&LL.count[layer + 1], 1);
-      LL.list[layer + 1][pos] = kid[t];
-    }
     VN_SPLIT_STAMP(6);
+    // leaves[i]->recut(...) of the new children (octree.cpp:388-392), one thread per child: their sums are
+    // complete (written by this block), nobody else knows them yet. A child that has to be subdivided itself
+    // goes to the next round's list; every child joins its layer's node list for the multi_margi of this scan.
+    __syncthreads();
+    if (t < 8 && kid[t] >= 0)
+    {
+      NodeHot& kh = M.hot[kid[t]];
+      const int cl = kh.layer;
+      if (cl <= 3) LL.list[cl][atomicAdd(&LL.count[cl], 1)] = kid[t];
+      if (!(kh.flags & VN_FLAG_INTERIOR) && recut_leaf(M, kh, M.cold[kid[t]]))
+        LL.split[sbase + nsplit + atomicAdd(&LL.count[4 + round + 1], 1)] = kid[t];
+    }
   }
 }
 #ifdef VINA_SPLIT_TRACE
@@ -1281,68 +1369,212 @@ __device__ void plane_update(NodeHot& h, NodeCold& c)
   h.qk = qk;
 }
 
-// leaf branch of OctoTree::margi (octree.cpp:397-484), mgsize = 1. The fold of the oldest frame's points into
-// point_fix (octree.cpp:452-459) is returned as a copy job (source, destination offset, count) that the
-// calling warp executes cooperatively.
-__device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf& xb, const LivePose& lv,
-                           const PointRec*& job_src, int& job_off, int& job_np)
+// OctoTree::margi, leaf branch (octree.cpp:397-484, mgsize = 1) + plane_update (octree.cpp:302-333), EIGHT lanes per
+// leaf. A thread per leaf is one long dependent chain (ten cluster transforms, the eigen-solver, the 3x9 * 9x9
+// products of plane_update) on a machine that is nearly empty (~10^4 leaves): the kernel's time is that chain's
+// latency. Here the lanes of a group share it:
+//   * lane g transforms the clusters of window frames g and g + 8 (PointCluster::transform) into shared memory; every
+//     lane then adds them up in frame order - the same additions in the same order as the reference, so pcr_add
+//     stays bit-exact - and runs the eigen-solver on the sum (replicated: its result is needed by all);
+//   * plane_update: the 27 entries of u_c, the 27 of J_c = u_c cov_add and the blocks of plane_var are spread
+//     over the lanes (every entry is one lane's sum in the order it always had);
+//   * lane 0 does the bookkeeping (fold into pcr_fix or subtract, slot clearing, isexist) and owns the copy job.
+#define MG 8  // lanes per leaf
+struct MargiShared
+{
+  double w[VINA_MAX_WIN][10];  // transformed clusters: P[6], v[3], N
+  double cov[45];              // cov_add
+  double f[2][9];              // plane_update: the row vectors of k = 1, 2
+  double uc[27], Jc[27];
+};
+
+__device__ void margi_leaf_group(const MapView& M, int n, int win_count, const PoseBuf& xb, const LivePose& lv, int g,
+                                 unsigned gmask, MargiShared& sh, const PointRec*& job_src, int& job_off, int& job_np)
 {
   NodeHot& h = M.hot[n];
   NodeCold& c = M.cold[n];
-  if (!c.isexist || !c.has_sw) return;
+  if (!c.isexist || !c.has_sw) return;  // (uniform over the group)
+  __syncwarp(gmask);                    // the previous leaf's readers of `sh` are done
   const int s0 = M.mp[0];
-  Cluster world0;
-  cluster_clear(world0);
   const bool is_plane = (h.flags & VN_FLAG_PLANE) != 0;
-  if (c.opt_state >= 0)
+  const bool factor = c.opt_state >= 0;
+  Cluster fix = c.pcr_fix;
+  Cluster add, world0;
+  cluster_clear(world0);
+  double ev[3], Q[9];
+  bool have_eig = false;
+  int n_loc0;
+  if (factor)
   {
-    c.opt_state = -1;
-    if (c.pcrs_local[s0].N != 0)
+    add = c.pcr_add;
+    const Cluster loc0 = c.pcrs_local[s0];
+    n_loc0 = loc0.N;
+    if (loc0.N != 0)
     {
       double xr[9], xp[3];
       pose_sel(xb, lv, 0, xr, xp);
-      cluster_transform(world0, c.pcrs_local[s0], xr, xp);
+      cluster_transform(world0, loc0, xr, xp);
     }
   }
   else
   {
-    Cluster add = c.pcr_fix;
-    for (int i = 0; i < win_count; i++)
+    for (int i = g; i < win_count; i += MG)
     {
-      const Cluster& loc = c.pcrs_local[M.mp[i]];
+      const Cluster loc = c.pcrs_local[M.mp[i]];
+      double* w = sh.w[i];
+      w[9] = (double)loc.N;
       if (loc.N != 0)
       {
-        Cluster w;
+        Cluster t;
         double xr[9], xp[3];
         pose_sel(xb, lv, i, xr, xp);
-        cluster_transform(w, loc, xr, xp);
-        if (i == 0) world0 = w;
-        cluster_add(add, w);
+        cluster_transform(t, loc, xr, xp);
+#pragma unroll
+        for (int k = 0; k < 6; k++) w[k] = t.P[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) w[6 + k] = t.v[k];
       }
     }
-    c.pcr_add = add;
+    __syncwarp(gmask);
+    add = fix;
+    n_loc0 = (int)sh.w[0][9];
+    for (int i = 0; i < win_count; i++)
+    {
+      const double* w = sh.w[i];
+      if (w[9] != 0.0)
+      {
+        Cluster t;
+#pragma unroll
+        for (int k = 0; k < 6; k++) t.P[k] = w[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) t.v[k] = w[6 + k];
+        t.N = (int)w[9];
+        if (i == 0) world0 = t;
+        cluster_add(add, t);
+      }
+    }
     if (is_plane)
     {
-      double L[6], ev[3], Q[9];
-      cluster_cov(c.pcr_add, L);
+      double L[6];
+      cluster_cov(add, L);
       eig3_sym(L, ev, Q);
+      have_eig = true;
+    }
+  }
+
+  const int last_num = c.last_num;
+  const bool update = fix.N < M.max_points && is_plane && (add.N - last_num >= 5 || last_num <= 10);
+  if (update)
+  {
+    // ---- plane_update (octree.cpp:302-333)
+    if (!have_eig)
+    {
+#pragma unroll
+      for (int k = 0; k < 3; k++) ev[k] = c.eig_value[k];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Q[k] = c.eig_vector[k];
+    }
+    for (int e = g; e < 45; e += MG) sh.cov[e] = c.cov_add[e];
+    const double N = (double)add.N;
+    const double center[3] = { add.v[0] / N, add.v[1] / N, add.v[2] / N };
+    const double nv = 1.0 / N;
+    // u[k] = column k of the eigenvectors; l = 0
+    double coef[2];
+    if (g < 2)
+    {
+      // lanes 0 and 1 build the row vectors of k = 1, 2 (columns picked by selects: Q stays in registers)
+      const double uk[3] = { g == 0 ? Q[3] : Q[6], g == 0 ? Q[4] : Q[7], g == 0 ? Q[5] : Q[8] };
+      const double* ul = Q;
+      double* f = sh.f[g];
+      f[0] = uk[0] * ul[0];
+      f[1] = uk[1] * ul[0] + uk[0] * ul[1];
+      f[2] = uk[2] * ul[0] + uk[0] * ul[2];
+      f[3] = uk[1] * ul[1];
+      f[4] = uk[1] * ul[2] + uk[2] * ul[1];
+      f[5] = uk[2] * ul[2];
+      const double dk = (uk[0] * center[0] + uk[1] * center[1]) + uk[2] * center[2];
+      const double dl = (ul[0] * center[0] + ul[1] * center[1]) + ul[2] * center[2];
+      for (int a = 0; a < 3; a++) f[6 + a] = -(dk * ul[a] + dl * uk[a]);
+    }
+    coef[0] = nv / (ev[0] - ev[1]);
+    coef[1] = nv / (ev[0] - ev[2]);
+    __syncwarp(gmask);
+    for (int o = g; o < 27; o += MG)
+    {
+      const int r = o / 9, q = o - 9 * r;
+      const double u1r = r == 0 ? Q[3] : (r == 1 ? Q[4] : Q[5]);  // (no dynamically indexed register arrays)
+      const double u2r = r == 0 ? Q[6] : (r == 1 ? Q[7] : Q[8]);
+      double s = 0.0;
+      s += (coef[0] * u1r) * sh.f[0][q];
+      s += (coef[1] * u2r) * sh.f[1][q];
+      sh.uc[o] = s;
+    }
+    __syncwarp(gmask);
+    for (int o = g; o < 27; o += MG)
+    {
+      const int r = o / 9, q = o - 9 * r;
+      double s = 0.0;
+      for (int t = 0; t < 9; t++) s += sh.uc[9 * r + t] * sh.cov[sN(9, t, q)];
+      sh.Jc[o] = s;
+    }
+    __syncwarp(gmask);
+    // plane_var = [[Jc u_c^T, nv Jc(:,6:9)],[.^T, nv^2 cov_add(6:9,6:9)]] (upper triangle) and the per-plane part
+    // of sigma_l for the IEKF (NodeHot: A, B n, n^T C n)
+    const double* nrm = Q;  // u[0]
+    if (g < 6)
+    {
+      const int a = g < 3 ? 0 : (g < 5 ? 1 : 2), b = g < 3 ? g : (g < 5 ? g - 2 : 2);  // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+      double s = 0.0;
+      for (int t = 0; t < 9; t++) s += sh.Jc[9 * a + t] * sh.uc[9 * b + t];
+      c.plane_var[sN(6, a, b)] = s;
+      h.qA[g] = s;
+      c.plane_var[sN(6, 3 + a, 3 + b)] = (nv * nv) * sh.cov[sN(9, 6 + a, 6 + b)];
+    }
+    for (int o = g; o < 9; o += MG) c.plane_var[sN(6, o / 3, 3 + o % 3)] = nv * sh.Jc[9 * (o / 3) + 6 + o % 3];
+    if (g < 3)
+    {
+      const int a = g;
+      h.qb[a] = (nv * sh.Jc[9 * a + 6]) * nrm[0] + (nv * sh.Jc[9 * a + 7]) * nrm[1] + (nv * sh.Jc[9 * a + 8]) * nrm[2];
+    }
+    if (g == 6)
+    {
+      double qk = 0.0;
+      for (int a = 0; a < 3; a++)
+        qk += nrm[a] * (((nv * nv) * sh.cov[sN(9, 6 + a, 6)]) * nrm[0] + ((nv * nv) * sh.cov[sN(9, 6 + a, 7)]) * nrm[1] +
+                        ((nv * nv) * sh.cov[sN(9, 6 + a, 8)]) * nrm[2]);
+      h.qk = qk;
+    }
+    if (g == 7)
+    {
+      for (int a = 0; a < 3; a++)
+      {
+        h.center[a] = center[a];
+        h.normal[a] = nrm[a];
+      }
+      h.radius = (float)ev[2];
+      c.last_num = add.N;
+    }
+  }
+
+  // ---- bookkeeping: lane 0
+  if (g != 0) return;
+  if (factor)
+    c.opt_state = -1;
+  else
+  {
+    if (have_eig)
+    {
       for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
       for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
     }
   }
-
-  if (c.pcr_fix.N < M.max_points && is_plane)
-    if (c.pcr_add.N - c.last_num >= 5 || c.last_num <= 10)
-    {
-      plane_update(h, c);
-      c.last_num = c.pcr_add.N;
-    }
-
-  if (c.pcr_fix.N < M.max_points)
+  if (fix.N < M.max_points)
   {
+    if (!factor) c.pcr_add = add;
     if (world0.N != 0)
     {
-      cluster_add(c.pcr_fix, world0);
+      cluster_add(fix, world0);
+      c.pcr_fix = fix;
       const int np = c.win_cnt[s0];
       if (np > 0)
       {
@@ -1358,39 +1590,45 @@ __device__ void margi_leaf(const MapView& M, int n, int win_count, const PoseBuf
   }
   else
   {
-    if (world0.N != 0) cluster_sub(c.pcr_add, world0);
+    if (world0.N != 0) cluster_sub(add, world0);
+    if (!factor || world0.N != 0) c.pcr_add = add;
     c.fix_head = c.fix_tail = -1;
     c.fix_count = 0;
   }
-
-  if (c.pcrs_local[s0].N != 0)
+  if (n_loc0 != 0)
   {
     cluster_clear(c.pcrs_local[s0]);
     c.win_cnt[s0] = 0;
   }
-  c.isexist = (c.pcr_fix.N >= c.pcr_add.N) ? 0 : 1;
+  c.isexist = (fix.N >= add.N) ? 0 : 1;
 }
 
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
-__global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
+__global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
 {
+  __shared__ MargiShared sh_all[128 / MG];
   // (the slide list the compaction fills after this kernel starts empty)
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) M.slide_count[1 - M.slide_cur] = 0;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
   const int lane = threadIdx.x & 31;
-  const int stride = gridDim.x * blockDim.x;
-  for (int j0 = blockIdx.x * blockDim.x + threadIdx.x - lane; j0 < nn; j0 += stride)  // warp-uniform trip count
+  const int g = lane & (MG - 1), grp = lane / MG;
+  const unsigned gmask = ((1u << MG) - 1u) << (MG * grp);
+  MargiShared& sh = sh_all[threadIdx.x / MG];
+  const int gpw = 32 / MG;  // leaves per warp and pass
+  const int stride = gridDim.x * (blockDim.x / 32) * gpw;
+  for (int j0 = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * gpw; j0 < nn; j0 += stride)  // warp-uniform
   {
-    const int j = j0 + lane;
+    const int j = j0 + grp;
     const PointRec* job_src = nullptr;
     int job_off = 0, job_np = 0;
     if (j < nn)
     {
       const int n = nodes[j];
-      if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf(M, n, win_count, xb, lv, job_src, job_off, job_np);
+      if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf_group(M, n, win_count, xb, lv, g, gmask, sh, job_src, job_off, job_np);
     }
+    __syncwarp();
     // the warp's copy jobs as ONE stream of points, 32 per pass (points go to the world frame of x_buf[0]): a
     // leaf folds only a handful of points per scan, so walking the jobs one after the other would leave most
     // lanes idle and pay one load latency per leaf instead of one per 32 points
@@ -1432,63 +1670,130 @@ __global__ void __launch_bounds__(128) k_margi_leaves(MapView M, LayerLists LL, 
   }
 }
 
-// OctoTree::margi, interior branch (octree.cpp:485-494): isexist = OR over the children, bottom-up
-__global__ void __launch_bounds__(128) k_margi_up(MapView M, LayerLists LL, int layer)
+// OctoTree::clear_slwd of one node (octree.cpp:739-756): the SlideWindow goes back to the pool
+__device__ __forceinline__ void clear_slwd_node(const MapView& M, NodeCold& c)
 {
-  if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
-  int nn;
-  const int* nodes = layer_nodes(M, LL, layer, &nn);
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
+  if (!c.has_sw) return;
+  for (int s = 0; s < M.win_size; s++)
   {
-    const int n = nodes[j];
-    if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) continue;
-    NodeCold& c = M.cold[n];
-    int ex = 0;
-    for (int k = 0; k < 8; k++)
-      if (c.children[k] >= 0) ex |= M.cold[c.children[k]].isexist;
-    c.isexist = ex;
+    c.win_cnt[s] = 0;
+    cluster_clear(c.pcrs_local[s]);
   }
+  c.has_sw = 0;
 }
 
-// The erase loop of multi_margi (local_mapping.cpp:67-78) in one launch. blockIdx.y <= max_layer: every node whose
-// root left surf_map_slide gives its SlideWindow back (OctoTree::clear_slwd, octree.cpp:739-756);
-// blockIdx.y == max_layer + 1: the surviving roots go to the other slide list (the caller flips slide_cur). Both
-// only read the roots' isexist, which is final after the last k_margi_up; the counter of the list being filled
-// was zeroed by k_margi_leaves.
-__global__ void __launch_bounds__(128) k_margi_clear_compact(MapView M, LayerLists LL)
+// The rest of multi_margi in one launch, EIGHT threads per root of surf_map_slide, one per first-level child (the
+// trees are at most 3 levels deep, a thread walks its child's subtree):
+//  * OctoTree::margi, interior branch (octree.cpp:485-494): isexist = OR over the children, bottom-up;
+//  * the erase loop (local_mapping.cpp:67-78): a root whose isexist is false leaves surf_map_slide and every node
+//    below it gives its SlideWindow back (OctoTree::clear_slwd); the surviving roots go to the other slide list
+//    (the caller flips slide_cur), whose counter k_margi_leaves zeroed;
+//  * iter->second->jour = jour (local_mapping.cpp:36).
+__global__ void __launch_bounds__(128) k_margi_finish(MapView M)
 {
-  if ((int)blockIdx.y <= M.max_layer)
-  {
-    if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
-    int nn;
-    const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nn; j += gridDim.x * blockDim.x)
-    {
-      NodeCold& c = M.cold[nodes[j]];
-      if (M.cold[c.root].isexist || !c.has_sw) continue;
-      for (int s = 0; s < M.win_size; s++)
-      {
-        c.win_cnt[s] = 0;
-        cluster_clear(c.pcrs_local[s]);
-      }
-      c.has_sw = 0;
-    }
-    return;
-  }
   const int cur = M.slide_cur;
   const int nroots = M.slide_count[cur];
   const bool early_out = nroots + M.slide_others < M.thread_num;  // multi_margi returned before its erase loop
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nroots; j += gridDim.x * blockDim.x)
+  const int lane = threadIdx.x & 31;
+  const int total = 8 * nroots;
+  const int stride = gridDim.x * blockDim.x;
+  for (int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < total; t0 += stride)  // warp-uniform trip count
   {
-    const int root = M.slide_list[cur][j];
-    if (!early_out) M.cold[root].jour = M.jour;  // iter->second->jour = jour (local_mapping.cpp:36)
-    if (early_out || M.cold[root].isexist)
+    const int t = t0 + lane;
+    const bool live = t < total;
+    const int a = t & 7;
+    const int root = live ? M.slide_list[cur][t >> 3] : -1;
+    int keep = 1;
+    if (!early_out)
     {
-      int pos = atomicAdd(&M.slide_count[1 - cur], 1);
-      M.slide_list[1 - cur][pos] = root;
+      int n1 = -1, root_interior = 0, ex = 0;
+      int c2[8];
+      unsigned int int2 = 0;
+#pragma unroll
+      for (int b = 0; b < 8; b++) c2[b] = -1;
+      if (live)
+      {
+        const NodeHot& h0 = M.hot[root];
+        root_interior = (h0.flags & VN_FLAG_INTERIOR) ? 1 : 0;
+        if (root_interior) n1 = h0.children[a];
+      }
+      if (n1 >= 0)
+      {
+        const NodeHot& h1 = M.hot[n1];
+        if (h1.flags & VN_FLAG_INTERIOR)
+        {
+#pragma unroll
+          for (int b = 0; b < 8; b++) c2[b] = h1.children[b];
+          int f2[8], e2[8];
+#pragma unroll
+          for (int b = 0; b < 8; b++)
+          {
+            f2[b] = c2[b] >= 0 ? M.hot[c2[b]].flags : 0;
+            e2[b] = c2[b] >= 0 ? M.cold[c2[b]].isexist : 0;
+          }
+          int ex1 = 0;
+#pragma unroll
+          for (int b = 0; b < 8; b++)
+          {
+            if (f2[b] & VN_FLAG_INTERIOR)
+            {
+              int2 |= 1u << b;
+              int ex2 = 0;
+              for (int d = 0; d < 8; d++)
+              {
+                const int n3 = M.hot[c2[b]].children[d];
+                if (n3 >= 0) ex2 |= M.cold[n3].isexist;
+              }
+              M.cold[c2[b]].isexist = ex2;
+              e2[b] = ex2;
+            }
+            ex1 |= e2[b];
+          }
+          M.cold[n1].isexist = ex1;
+          ex = ex1;
+        }
+        else
+          ex = M.cold[n1].isexist;
+      }
+      // the root: OR over its eight children's threads (a leaf root keeps what margi_leaf wrote)
+      ex |= __shfl_xor_sync(0xffffffffu, ex, 1);
+      ex |= __shfl_xor_sync(0xffffffffu, ex, 2);
+      ex |= __shfl_xor_sync(0xffffffffu, ex, 4);
+      if (live)
+      {
+        NodeCold& rc = M.cold[root];
+        keep = root_interior ? ex : rc.isexist;
+        if (a == 0)
+        {
+          rc.jour = M.jour;
+          if (root_interior) rc.isexist = ex;
+        }
+        if (!keep)
+        {
+          if (a == 0) clear_slwd_node(M, rc);
+          if (n1 >= 0)
+          {
+            clear_slwd_node(M, M.cold[n1]);
+            for (int b = 0; b < 8; b++)
+              if (c2[b] >= 0)
+              {
+                clear_slwd_node(M, M.cold[c2[b]]);
+                if (int2 & (1u << b))
+                  for (int d = 0; d < 8; d++)
+                  {
+                    const int n3 = M.hot[c2[b]].children[d];
+                    if (n3 >= 0) clear_slwd_node(M, M.cold[n3]);
+                  }
+              }
+          }
+        }
+      }
     }
-    else
-      M.cold[root].in_slide = 0;
+    // compaction of the slide list: one atomic per warp
+    const int mine = (live && a == 0 && keep) ? 1 : 0;
+    const int pos = warp_reserve(&M.slide_count[1 - cur], mine, lane);
+    if (mine) M.slide_list[1 - cur][pos] = root;
+    if (live && a == 0 && !keep) M.cold[root].in_slide = 0;
   }
 }
 
@@ -1726,15 +2031,22 @@ void launch_map_prune_finish(cudaStream_t st, const MapView& map, const int* d_c
 static int grid_for(int n, int block) { return n <= 0 ? 1 : (n + block - 1) / block; }
 
 int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                            const InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
+                            InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
                             int pre, const IekfDev* live)
 {
   Cov2 cv;
   for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
-  k_zero_ints<<<1, 32, 0, st>>>(sc.counters, 3);
-  if (n_host <= 0) return 1;
+  if (n_host <= 0)
+  {
+    k_zero_ints<<<1, 32, 0, st>>>(sc.counters, 4);  // (nothing to insert: the callers still read zero counts)
+    return 1;
+  }
+  // this insert's counters are the set the previous insert cleared (both sets start out zero)
+  int* t = sc.counters;
+  sc.counters = sc.counters_alt;
+  sc.counters_alt = t;
   k_insert_root<<<grid_for(n_host, 256), 256, 0, st>>>(map, scan, n_dev, n_host, sc, x, cv, pre, live);
-  return 2;
+  return 1;
 }
 
 int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
@@ -1753,7 +2065,7 @@ int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView
 }
 
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                      const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
+                      InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
                       const double* tsl_var, const IekfDev* live)
 {
   if (n_host <= 0) return 0;
@@ -1769,7 +2081,7 @@ static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)
   return b;
 }
 
-int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
+int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int win_count, const PoseD* h_xbuf,
                      const IekfDev* live)
 {
   const LivePose lv = { live, win_count - 1 };
@@ -1782,18 +2094,17 @@ int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, 
     attr_set[dv & 63] = true;
   }
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  k_zero_ints<<<1, 32, 0, st>>>(LL.count, 8);
-  int launches = 1;
-  for (int layer = 0; layer <= map.max_layer; layer++)
-  {
-    k_recut_layer<<<592, 128, 0, st>>>(map, LL, layer);
-    launches++;
-    if (layer < map.max_layer)
-    {
-      k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, layer, win_count, b, lv);
-      launches++;
-    }
-  }
+  // this call's counters are the set the previous call cleared (both sets start out zero)
+  int* t = LL.count;
+  LL.count = LL.count_alt;
+  LL.count_alt = t;
+  k_recut_collect<<<592, 128, 0, st>>>(map, LL);
+  k_recut_all<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL);
+  int launches = 2;
+  // subdivision rounds: a leaf of layer l splits in round >= l at the earliest, its children are judged by the
+  // block that created them; max_layer rounds cover the deepest chain
+  for (int round = 0; round < map.max_layer; round++, launches++)
+    k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, round, win_count, b, lv);
   return launches;
 }
 
@@ -1802,12 +2113,9 @@ int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, 
 {
   const LivePose lv = { live, win_count - 1 };
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  int launches = 0;
-  k_margi_leaves<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b, lv);
-  launches++;
-  for (int layer = map.max_layer - 1; layer >= 0; layer--, launches++) k_margi_up<<<296, 128, 0, st>>>(map, LL, layer);
-  k_margi_clear_compact<<<dim3(296, map.max_layer + 2), 128, 0, st>>>(map, LL);
-  return launches + 1;
+  k_margi_leaves<<<dim3(592, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b, lv);
+  k_margi_finish<<<592, 128, 0, st>>>(map);
+  return 2;
 }
 
 int launch_ba_collect(cudaStream_t st, const MapView& map, const LayerLists& LL, BaFactor* out, int* count, int cap)

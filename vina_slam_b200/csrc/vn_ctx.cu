@@ -247,12 +247,14 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(dalloc(&S.leaf_of, cap));
   CU(dalloc(&S.rank_of, cap));
   CU(dalloc(&S.touched, cap));
-  CU(dalloc(&S.counters, 4));
+  CU(dalloc(&S.counters, 8));
+  S.counters_alt = S.counters + 4;
   CU(dalloc(&S.idx, cap));
   S.stamp = 0;
   for (int l = 0; l < 4; l++) CU(dalloc(&ctx->layers.list[l], (size_t)cfg.max_nodes));
   CU(dalloc(&ctx->layers.split, (size_t)cfg.max_nodes));
-  CU(dalloc(&ctx->layers.count, 8));
+  CU(dalloc(&ctx->layers.count, 16));
+  ctx->layers.count_alt = ctx->layers.count + 8;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaDeviceSynchronize());  // the zero-fills of dalloc ran on the legacy stream (see ensure_debug)
   CU(cudaGetLastError());
@@ -377,11 +379,11 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(S.leaf_of);
   cudaFree(S.rank_of);
   cudaFree(S.touched);
-  cudaFree(S.counters);
+  cudaFree(S.counters < S.counters_alt ? S.counters : S.counters_alt);
   cudaFree(S.idx);
   for (int l = 0; l < 4; l++) cudaFree(ctx->layers.list[l]);
   cudaFree(ctx->layers.split);
-  cudaFree(ctx->layers.count);
+  cudaFree(ctx->layers.count < ctx->layers.count_alt ? ctx->layers.count : ctx->layers.count_alt);
   for (int i = 0; i < 16; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->iekf_ev) cudaEventDestroy(e);

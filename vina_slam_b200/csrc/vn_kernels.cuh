@@ -121,17 +121,18 @@ struct InsertScratch
   int* rank_of;    // per point: arrival rank within its leaf
   int* touched;    // leaves touched by this scan
   int* counters;   // [0]=g_size (distinct roots) [1]=n_touched [2]=idx cursor
+  int* counters_alt;  // the set the next insert uses (cleared by this one)
   int* idx;        // point indices grouped by leaf
   int stamp;       // scan stamp for distinct-root counting
 };
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                      const InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
+                      InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
                       const double* tsl_var, const IekfDev* live = nullptr);
 // the two halves of an insert, for the sharded map: (1) key + root find/create on points whose world
 // position / covariance are already in sc.pw / sc.vw (pre != 0) or come from pvec_update; (2) the rest.
 // Between them the caller may overwrite sc.counters[0] (distinct roots) with the all-reduced count.
 int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                            const InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
+                            InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
                             int pre, const IekfDev* live = nullptr);
 int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                              const InsertScratch& sc, int win_ord);
@@ -157,7 +158,7 @@ int launch_shard_recv_p2p(cudaStream_t st, const ShardPeers& peers, unsigned lon
 int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanView& scan, const InsertScratch& sc);
 // live != nullptr: the pose of frame win_count - 1 (and, for the insert, the posterior covariance blocks) are read
 // from the device iterate instead of the host arguments (the IEKF result need not have reached the host yet)
-int launch_map_recut(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
+int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int win_count, const PoseD* h_xbuf,
                      const IekfDev* live = nullptr);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
 int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
@@ -190,6 +191,7 @@ void launch_map_init(cudaStream_t st, const MapView& map, unsigned int nslots);
 struct LayerLists
 {
   int* list[4];
-  int* split;  // leaves to subdivide in the current layer
-  int* count;  // [0..3] nodes per layer, [4..7] splits per layer
+  int* split;  // leaves to subdivide: the lists of the subdivision rounds, one behind the other
+  int* count;  // [0..3] nodes per layer, [4..7] leaves to subdivide per round
+  int* count_alt;  // the set the next multi_recut uses (cleared by this one: no launch spent on zeroing)
 };

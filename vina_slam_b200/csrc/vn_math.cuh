@@ -205,7 +205,84 @@ VN_HD double hypot_pos(double x, double y)
   double qp = (ax > ay ? ay : ax) / p;
   return dm(p, sqrt(da(1.0, dm(qp, qp))));
 }
-VN_HD void eig3_sym(const double* L, double* values, double* Q)
+// One implicit QR step on rows/columns START..END of the tridiagonal matrix (Eigen's tridiagonal_qr_step). START / END
+// are compile-time constants - a 3x3 matrix only ever sees (0,2), (1,2) and (0,1) - so that every diag / sub / Q index
+// is static and the whole solver lives in registers (dynamically indexed arrays would go to local memory: the
+// solver is a single dependent chain, every local-memory round trip is on it). Same operations, same order.
+template <int START, int END>
+VN_HD void eig3_qr_step(double (&diag)[3], double (&sub)[2], double (&Q)[9])
+{
+  double td = dm(ds(diag[END - 1], diag[END]), 0.5);
+  double e = sub[END - 1];
+  double mu = diag[END];
+  if (td == 0.0)
+    mu = ds(mu, fabs(e));
+  else if (e != 0.0)
+  {
+    const double e2 = dm(e, e);
+    const double h = hypot_pos(td, e);
+    if (e2 == 0.0)
+      mu = ds(mu, e / (da(td, (td > 0.0 ? h : -h)) / e));
+    else
+      mu = ds(mu, e2 / da(td, (td > 0.0 ? h : -h)));
+  }
+  double x = ds(diag[START], mu);
+  double z = sub[START];
+#pragma unroll
+  for (int k = START; k < END; ++k)
+  {
+    if (z == 0.0) break;
+    double c, s;
+    givens(x, z, c, s);
+    double sdk = da(dm(s, diag[k]), dm(c, sub[k]));
+    double dkp1 = da(dm(s, sub[k]), dm(c, diag[k + 1]));
+    diag[k] = ds(dm(c, ds(dm(c, diag[k]), dm(s, sub[k]))), dm(s, ds(dm(c, sub[k]), dm(s, diag[k + 1]))));
+    diag[k + 1] = da(dm(s, sdk), dm(c, dkp1));
+    sub[k] = ds(dm(c, sdk), dm(s, dkp1));
+    if (k > START) sub[k - 1] = ds(dm(c, sub[k - 1]), dm(s, z));
+    x = sub[k];
+    if (k < END - 1)
+    {
+      z = dm(-s, sub[k + 1]);
+      sub[k + 1] = dm(c, sub[k + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+      double xi = Q[i + 3 * k], yi = Q[i + 3 * (k + 1)];
+      Q[i + 3 * k] = ds(dm(c, xi), dm(s, yi));
+      Q[i + 3 * (k + 1)] = da(dm(s, xi), dm(c, yi));
+    }
+  }
+}
+// sub[I] is negligible against its diagonal neighbours (Eigen's deflation test)
+template <int I>
+VN_HD void eig3_deflate(const double (&diag)[3], double (&sub)[2])
+{
+  const double tol = 2.2250738585072014e-308;
+  const double precision_inv = 1.0 / 2.220446049250313e-16;
+  if (fabs(sub[I]) < tol)
+    sub[I] = 0.0;
+  else
+  {
+    const double ss = dm(precision_inv, sub[I]);
+    if (dm(ss, ss) <= da(fabs(diag[I]), fabs(diag[I + 1]))) sub[I] = 0.0;
+  }
+}
+VN_HD void eig3_swap_cols(double (&diag)[3], double (&Q)[9], int a, int b)
+{
+  double t = diag[a];
+  diag[a] = diag[b];
+  diag[b] = t;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+  {
+    double tt = Q[r + 3 * a];
+    Q[r + 3 * a] = Q[r + 3 * b];
+    Q[r + 3 * b] = tt;
+  }
+}
+VN_HD void eig3_sym(const double* L, double* values, double* Qout)
 {
   double m00 = L[0], m10 = L[1], m20 = L[2], m11 = L[3], m21 = L[4], m22 = L[5];
   double scale = fabs(m00);
@@ -222,7 +299,7 @@ VN_HD void eig3_sym(const double* L, double* values, double* Q)
   m21 = m21 / scale;
   m22 = m22 / scale;
 
-  double diag[3], sub[2];
+  double diag[3], sub[2], Q[9];
   const double tol = 2.2250738585072014e-308;
   diag[0] = m00;
   double v1norm2 = dm(m20, m20);
@@ -257,95 +334,51 @@ VN_HD void eig3_sym(const double* L, double* values, double* Q)
   }
 
   int end = 2, start = 0, iter = 0;
-  const double precision_inv = 1.0 / 2.220446049250313e-16;
   while (end > 0)
   {
-    for (int i = start; i < end; ++i)
-    {
-      if (fabs(sub[i]) < tol)
-        sub[i] = 0.0;
-      else
-      {
-        const double ss = dm(precision_inv, sub[i]);
-        if (dm(ss, ss) <= da(fabs(diag[i]), fabs(diag[i + 1]))) sub[i] = 0.0;
-      }
-    }
-    while (end > 0 && sub[end - 1] == 0.0) end--;
+    // for (i = start; i < end; ++i) deflation test of sub[i]
+    if (start <= 0 && 0 < end) eig3_deflate<0>(diag, sub);
+    if (start <= 1 && 1 < end) eig3_deflate<1>(diag, sub);
+    // while (end > 0 && sub[end - 1] == 0) end--
+    if (end == 2 && sub[1] == 0.0) end = 1;
+    if (end == 1 && sub[0] == 0.0) end = 0;
     if (end <= 0) break;
     iter++;
     if (iter > 90) break;
+    // start = end - 1; while (start > 0 && sub[start - 1] != 0) start--
     start = end - 1;
-    while (start > 0 && sub[start - 1] != 0.0) start--;
-
-    // tridiagonal_qr_step
-    double td = dm(ds(diag[end - 1], diag[end]), 0.5);
-    double e = sub[end - 1];
-    double mu = diag[end];
-    if (td == 0.0)
-      mu = ds(mu, fabs(e));
-    else if (e != 0.0)
+    if (start == 1 && sub[0] != 0.0) start = 0;
+    if (end == 2)
     {
-      const double e2 = dm(e, e);
-      const double h = hypot_pos(td, e);
-      if (e2 == 0.0)
-        mu = ds(mu, e / (da(td, (td > 0.0 ? h : -h)) / e));
+      if (start == 0)
+        eig3_qr_step<0, 2>(diag, sub, Q);
       else
-        mu = ds(mu, e2 / da(td, (td > 0.0 ? h : -h)));
+        eig3_qr_step<1, 2>(diag, sub, Q);
     }
-    double x = ds(diag[start], mu);
-    double z = sub[start];
-    for (int k = start; k < end && z != 0.0; ++k)
-    {
-      double c, s;
-      givens(x, z, c, s);
-      double sdk = da(dm(s, diag[k]), dm(c, sub[k]));
-      double dkp1 = da(dm(s, sub[k]), dm(c, diag[k + 1]));
-      diag[k] = ds(dm(c, ds(dm(c, diag[k]), dm(s, sub[k]))), dm(s, ds(dm(c, sub[k]), dm(s, diag[k + 1]))));
-      diag[k + 1] = da(dm(s, sdk), dm(c, dkp1));
-      sub[k] = ds(dm(c, sdk), dm(s, dkp1));
-      if (k > start) sub[k - 1] = ds(dm(c, sub[k - 1]), dm(s, z));
-      x = sub[k];
-      if (k < end - 1)
-      {
-        z = dm(-s, sub[k + 1]);
-        sub[k + 1] = dm(c, sub[k + 1]);
-      }
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-      {
-        double xi = Q[i + 3 * k], yi = Q[i + 3 * (k + 1)];
-        Q[i + 3 * k] = ds(dm(c, xi), dm(s, yi));
-        Q[i + 3 * (k + 1)] = da(dm(s, xi), dm(c, yi));
-      }
-    }
+    else
+      eig3_qr_step<0, 1>(diag, sub, Q);
   }
   if (iter <= 90)
   {
-    for (int i = 0; i < 2; ++i)
+    // selection sort, ascending, first minimum wins (Eigen's sort of the eigenvalues with their vectors)
+    int k = 0;
+    double mn = diag[0];
+    if (diag[1] < mn)
     {
-      int k = 0;
-      double mn = diag[i];
-      for (int j = 1; j < 3 - i; j++)
-        if (diag[i + j] < mn)
-        {
-          mn = diag[i + j];
-          k = j;
-        }
-      if (k > 0)
-      {
-        double t = diag[i];
-        diag[i] = diag[k + i];
-        diag[k + i] = t;
-        for (int r = 0; r < 3; r++)
-        {
-          double tt = Q[r + 3 * i];
-          Q[r + 3 * i] = Q[r + 3 * (k + i)];
-          Q[r + 3 * (k + i)] = tt;
-        }
-      }
+      mn = diag[1];
+      k = 1;
     }
+    if (diag[2] < mn) k = 2;
+    if (k == 1)
+      eig3_swap_cols(diag, Q, 0, 1);
+    else if (k == 2)
+      eig3_swap_cols(diag, Q, 0, 2);
+    if (diag[2] < diag[1]) eig3_swap_cols(diag, Q, 1, 2);
   }
+#pragma unroll
   for (int i = 0; i < 3; i++) values[i] = dm(diag[i], scale);
+#pragma unroll
+  for (int i = 0; i < 9; i++) Qout[i] = Q[i];
 }
 
 // PointCluster::cov() lower triangle (types.hpp:144-148)

@@ -354,130 +354,185 @@ __attribute__((target_clones("avx2,fma", "default"), optimize("fp-contract=fast"
 }
 }  // namespace
 
-// ---- IMU_PRE ------------------------------------------------------------------------------------------------
+// ---- the IMU factor between two consecutive window frames ------------------------------------------------------
+// Role of the reference's IMU_PRE (src/estimation/imu_preintegration.cpp:7-163, 235-242); written from the
+// pre-integration model (Forster et al., on-manifold pre-integration) with the reference's conventions, so that
+// residual / J^T W J / J^T W r agree with its code to rounding (tests/test_ba_host_cpu.py, 1e-9):
+//   error state of the increment  e = (dtheta, dp, dv), biases (bg, ba) as random walks;
+//   per IMU sample (w, a, dt) with E = Exp(w dt), Jr = Jr(w dt), G = DR [a]x:
+//     e' = A e + B n,   A = [ E^T 0 0 ; -dt^2/2 G  I  dt I ; -dt G 0 I ],   B = [ Jr dt 0 ; 0 dt^2/2 DR ; 0 dt DR ]
+//     bias Jacobians    dR/dbg' = E^T dR/dbg - Jr dt,
+//                       dp/dbg' = dp/dbg + dt dv/dbg - dt^2/2 G dR/dbg,   dp/dba' = dp/dba + dt dv/dba - dt^2/2 DR,
+//                       dv/dbg' = dv/dbg - dt G dR/dbg,                   dv/dba' = dv/dba - dt DR
+//     increments        Dp += Dv dt + dt^2/2 DR a,  Dv += dt DR a,  DR = DR E.
+// Everything is kept as 3x3 blocks: A and B are block-sparse, so the 9x9 covariance recursion costs 21 block
+// products instead of two dense 9x9x9 ones, and the 15x30 Jacobian of the factor has 16 non-zero blocks of 50.
 struct ImuPre
 {
-  M3 R_delta, R_bg, p_bg, p_ba, v_bg, v_ba;
-  V3 p_delta, v_delta, bg, ba, dbg, dba, dbg_buf, dba_buf;
+  M3 DR, dR_dbg, dp_dbg, dp_dba, dv_dbg, dv_dba;
+  V3 Dp, Dv, bg, ba, dbg, dba, dbg_buf, dba_buf;
   double dtime = 0;
-  M15 cov, cov_inv;  // cov_inv: the covariance does not change once the batch is integrated
+  M3 S[3][3];  // covariance of (dtheta, dp, dv), 3x3 blocks
+  double walk_g = 0, walk_a = 0;  // accumulated bias random walk (isotropic)
+  M15 cov, cov_inv;               // assembled once the batch is integrated
   ImuPre(const double* bg1, const double* ba1)
   {
     bg = v3(bg1), ba = v3(ba1);
-    R_delta = M3::eye();
-    R_bg = p_bg = p_ba = v_bg = v_ba = M3::zero();
-    p_delta = v_delta = dbg = dba = dbg_buf = dba_buf = V3::zero();
+    DR = M3::eye();
+    dR_dbg = dp_dbg = dp_dba = dv_dbg = dv_dba = M3::zero();
+    Dp = Dv = dbg = dba = dbg_buf = dba_buf = V3::zero();
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) S[i][j] = M3::zero();
     cov = M15::zero();
   }
-  // imu_preintegration.cpp:59-100
-  void add_imu(const V3& cur_gyr, const V3& cur_acc, double dt, const vina_config& cfg)
+  void integrate(const V3& w, const V3& acc, double dt, const vina_config& cfg)
   {
     dtime += dt;
-    M3 rotation_increment = Exp(cur_gyr, dt);
-    M3 right_jacobian = jr(cur_gyr * dt);
-    M3 rotation_dt = dt * R_delta;
-    M3 rotation_dt2_half = 0.5 * dt * dt * R_delta;
-    M3 acc_skew = hat(cur_acc);
-    p_ba = p_ba + v_ba * dt - rotation_dt2_half;
-    p_bg = p_bg + v_bg * dt - rotation_dt2_half * acc_skew * R_bg;
-    v_ba = v_ba - rotation_dt;
-    v_bg = v_bg - rotation_dt * acc_skew * R_bg;
-    R_bg = rotation_increment.T() * R_bg - right_jacobian * dt;
-    HM<9, 9> ja = HM<9, 9>::eye();
-    HM<9, 6> jb = HM<9, 6>::zero();
-    ja.set<3, 3>(0, 0, rotation_increment.T());
-    ja.set<3, 3>(3, 0, -rotation_dt2_half * acc_skew);
-    ja.set<3, 3>(3, 6, M3::eye() * dt);
-    ja.set<3, 3>(6, 0, -rotation_dt * acc_skew);
-    jb.set<3, 3>(0, 0, right_jacobian * dt);
-    jb.set<3, 3>(3, 3, rotation_dt2_half);
-    jb.set<3, 3>(6, 3, rotation_dt);
-    HM<6, 6> nm = HM<6, 6>::zero(), nw = HM<6, 6>::zero();  // node.cpp:262-265
-    for (int k = 0; k < 3; k++)
+    const double h = 0.5 * dt * dt;
+    const M3 E = Exp(w, dt), Et = E.T();
+    const M3 Jr = jr(w * dt);
+    const M3 G = DR * hat(acc);
+    const M3 GR = G * dR_dbg;
+    // bias Jacobians (position before velocity: it uses the old velocity Jacobians)
+    dp_dba = dp_dba + dv_dba * dt - h * DR;
+    dp_dbg = dp_dbg + dv_dbg * dt - h * GR;
+    dv_dba = dv_dba - dt * DR;
+    dv_dbg = dv_dbg - dt * GR;
+    dR_dbg = Et * dR_dbg - Jr * dt;
+    // covariance: T = A S, then S' = T A^T + B Q B^T, block by block
+    const M3 F2 = -h * G, F3 = -dt * G;
+    M3 T[3][3];
+    for (int j = 0; j < 3; j++)
     {
-      nm(k, k) = cfg.cov_gyr, nm(3 + k, 3 + k) = cfg.cov_acc;
-      nw(k, k) = cfg.rdw_gyr, nw(3 + k, 3 + k) = cfg.rdw_acc;
+      T[0][j] = Et * S[0][j];
+      T[1][j] = F2 * S[0][j] + S[1][j] + dt * S[2][j];
+      T[2][j] = F3 * S[0][j] + S[2][j];
     }
-    HM<9, 9> c99 = cov.blk<9, 9>(0, 0);
-    cov.set<9, 9>(0, 0, ja * c99 * ja.T() + jb * nm * jb.T());
-    HM<6, 6> c66 = cov.blk<6, 6>(9, 9);
-    cov.set<6, 6>(9, 9, c66 + nw * dt);
-    p_delta = p_delta + (v_delta * dt + rotation_dt2_half * cur_acc);
-    v_delta = v_delta + rotation_dt * cur_acc;
-    R_delta = R_delta * rotation_increment;
+    const M3 F2t = F2.T(), F3t = F3.T();
+    for (int i = 0; i < 3; i++)
+    {
+      S[i][0] = T[i][0] * E;
+      S[i][1] = T[i][0] * F2t + T[i][1] + dt * T[i][2];
+      S[i][2] = T[i][0] * F3t + T[i][2];
+    }
+    // B Q B^T, Q = diag(cov_gyr I, cov_acc I) (node.cpp:262-265): gyro noise enters dtheta through Jr dt, accelerometer
+    // noise enters (dp, dv) through (dt^2/2, dt) DR
+    const M3 RRt = DR * DR.T();
+    S[0][0] = S[0][0] + (cfg.cov_gyr * dt * dt) * (Jr * Jr.T());
+    S[1][1] = S[1][1] + (cfg.cov_acc * h * h) * RRt;
+    S[1][2] = S[1][2] + (cfg.cov_acc * h * dt) * RRt;
+    S[2][1] = S[2][1] + (cfg.cov_acc * h * dt) * RRt;
+    S[2][2] = S[2][2] + (cfg.cov_acc * dt * dt) * RRt;
+    walk_g += cfg.rdw_gyr * dt;
+    walk_a += cfg.rdw_acc * dt;
+    // increments
+    const V3 Ra = DR * acc;
+    Dp = Dp + (Dv * dt + h * Ra);
+    Dv = Dv + dt * Ra;
+    DR = DR * E;
   }
-  // imu_preintegration.cpp:32-57 (the deque is the scan's IMU batch with its ends re-stamped to the scan boundaries)
+  // the scan's IMU batch (ends re-stamped to the scan boundaries): mid-point samples, bias-corrected
+  // (imu_preintegration.cpp:32-57)
   void push_imu(const std::deque<vina_imu>& buf, double scale_gravity, const vina_config& cfg)
   {
     for (size_t k = 1; k < buf.size(); k++)
     {
-      const vina_imu &a = buf[k - 1], &b = buf[k];
-      const double dt = b.t - a.t;
-      V3 g, c;
+      const vina_imu &s0 = buf[k - 1], &s1 = buf[k];
+      V3 w, acc;
       for (int q = 0; q < 3; q++)
       {
-        g[q] = 0.5 * (a.gyr[q] + b.gyr[q]);
-        c[q] = 0.5 * (a.acc[q] + b.acc[q]);
+        w[q] = 0.5 * (s0.gyr[q] + s1.gyr[q]) - bg[q];
+        acc[q] = 0.5 * (s0.acc[q] + s1.acc[q]) * scale_gravity - ba[q];
       }
-      g = g - bg;
-      c = c * scale_gravity - ba;
-      add_imu(g, c, dt, cfg);
+      integrate(w, acc, s1.t - s0.t, cfg);
     }
+    cov = M15::zero();
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) cov.set<3, 3>(3 * i, 3 * j, S[i][j]);
+    for (int k = 0; k < 3; k++) cov(9 + k, 9 + k) = walk_g, cov(12 + k, 12 + k) = walk_a;
     cov_inv = inverse15(cov);
   }
-  // imu_preintegration.cpp:102-163; jtj 30x30 column-major, gg 30
+  // residual r = (Log(DR~^T R1^T R2), R1^T(p2 - p1 - v1 T - g T^2/2) - Dp~, R1^T(v2 - v1 - g T) - Dv~, bg2 - bg1,
+  // ba2 - ba1) with the increments corrected to first order for the bias change since integration; returns r^T W r
+  // and, on request, J^T W J (30x30) and J^T W r (30) for the two frames' 15-dim states (theta, p, v, bg, ba)
+  // (imu_preintegration.cpp:102-163)
   double evaluate(const vina_state& s1, const vina_state& s2, HM<30, 30>* jtj, HM<30, 1>* gg) const
   {
-    const M3 R1 = m3(s1.R), R2 = m3(s2.R), I33 = M3::eye();
-    const V3 p1 = v3(s1.p), p2 = v3(s2.p), v1 = v3(s1.v), v2 = v3(s2.v), g1 = v3(s1.g);
-    M3 R_correct = R_delta * Exp(R_bg * dbg);
-    V3 t_correct = p_delta + p_bg * dbg + p_ba * dba;
-    V3 v_correct = v_delta + v_bg * dbg + v_ba * dba;
-    M3 res_r = R_correct.T() * R1.T() * R2;
-    V3 exp_v = R1.T() * (v2 - v1 - dtime * g1);
-    V3 res_v = exp_v - v_correct;
-    V3 exp_t = R1.T() * (p2 - p1 - v1 * dtime - 0.5 * dtime * dtime * g1);
-    V3 res_t = exp_t - t_correct;
-    V15 rr = V15::zero();
-    rr.set<3, 1>(0, 0, Log(res_r));
-    rr.set<3, 1>(3, 0, res_t);
-    rr.set<3, 1>(6, 0, res_v);
-    rr.set<3, 1>(9, 0, v3(s2.bg) - v3(s1.bg));
-    rr.set<3, 1>(12, 0, v3(s2.ba) - v3(s1.ba));
-    if (jtj && gg)
+    const M3 R1 = m3(s1.R), R2 = m3(s2.R), R1t = R1.T();
+    const V3 p1 = v3(s1.p), p2 = v3(s2.p), v1 = v3(s1.v), v2 = v3(s2.v), g = v3(s1.g);
+    const V3 th = dR_dbg * dbg;
+    const M3 DRc = DR * Exp(th);
+    const V3 Dpc = Dp + dp_dbg * dbg + dp_dba * dba;
+    const V3 Dvc = Dv + dv_dbg * dbg + dv_dba * dba;
+    const M3 Rerr = DRc.T() * R1t * R2;
+    const V3 pv = R1t * (v2 - v1 - dtime * g);
+    const V3 pt = R1t * (p2 - p1 - v1 * dtime - 0.5 * dtime * dtime * g);
+    V15 r = V15::zero();
+    r.set<3, 1>(0, 0, Log(Rerr));
+    r.set<3, 1>(3, 0, pt - Dpc);
+    r.set<3, 1>(6, 0, pv - Dvc);
+    r.set<3, 1>(9, 0, v3(s2.bg) - v3(s1.bg));
+    r.set<3, 1>(12, 0, v3(s2.ba) - v3(s1.ba));
+    const V15 Wr = cov_inv * r;
+    double cost = r[0] * Wr[0];
+    for (int k = 1; k < 15; k++) cost = cost + r[k] * Wr[k];
+    if (!jtj || !gg) return cost;
+
+    // the Jacobian as 5 x 10 blocks of 3 x 3 (block row = residual part, block column = state part of frame 1, 2)
+    M3 J[5][10];
+    bool nz[5][10] = { { false } };
+    auto put = [&](int i, int c, const M3& m) {
+      J[i][c] = m;
+      nz[i][c] = true;
+    };
+    const M3 Jri = jr_inv(Rerr), I3 = M3::eye();
+    put(0, 0, -Jri * R2.T() * R1);
+    put(0, 3, -Jri * Rerr.T() * jr(th) * dR_dbg);
+    put(0, 5, Jri);
+    put(1, 0, hat(pt));
+    put(1, 1, -R1t);
+    put(1, 2, -R1t * dtime);
+    put(1, 3, -dp_dbg);
+    put(1, 4, -dp_dba);
+    put(1, 6, R1t);
+    put(2, 0, hat(pv));
+    put(2, 2, -R1t);
+    put(2, 3, -dv_dbg);
+    put(2, 4, -dv_dba);
+    put(2, 7, R1t);
+    put(3, 3, -I3);
+    put(3, 8, I3);
+    put(4, 4, -I3);
+    put(4, 9, I3);
+    // WJ = W J: only the non-zero blocks of each block column contribute
+    M3 WJ[5][10];
+    for (int c = 0; c < 10; c++)
+      for (int i = 0; i < 5; i++)
+      {
+        M3 acc = M3::zero();
+        for (int k = 0; k < 5; k++)
+          if (nz[k][c]) acc = acc + cov_inv.blk<3, 3>(3 * i, 3 * k) * J[k][c];
+        WJ[i][c] = acc;
+      }
+    *jtj = HM<30, 30>::zero();
+    *gg = HM<30, 1>::zero();
+    for (int a2 = 0; a2 < 10; a2++)
     {
-      M15 joca = M15::zero(), jocb = M15::zero();
-      M3 JR_inv = jr_inv(res_r);
-      joca.set<3, 3>(0, 0, -JR_inv * R2.T() * R1);
-      jocb.set<3, 3>(0, 0, JR_inv);
-      joca.set<3, 3>(0, 9, -JR_inv * res_r.T() * jr(R_bg * dbg) * R_bg);
-      joca.set<3, 3>(3, 0, hat(exp_t));
-      joca.set<3, 3>(3, 3, -R1.T());
-      joca.set<3, 3>(3, 6, -R1.T() * dtime);
-      joca.set<3, 3>(3, 9, -p_bg);
-      joca.set<3, 3>(3, 12, -p_ba);
-      jocb.set<3, 3>(3, 3, R1.T());
-      joca.set<3, 3>(6, 0, hat(exp_v));
-      joca.set<3, 3>(6, 6, -R1.T());
-      joca.set<3, 3>(6, 9, -v_bg);
-      joca.set<3, 3>(6, 12, -v_ba);
-      jocb.set<3, 3>(6, 6, R1.T());
-      joca.set<3, 3>(9, 9, -I33);
-      joca.set<3, 3>(12, 12, -I33);
-      jocb.set<3, 3>(9, 9, I33);
-      jocb.set<3, 3>(12, 12, I33);
-      HM<15, 30> joc;
-      joc.set<15, 15>(0, 0, joca);
-      joc.set<15, 15>(0, 15, jocb);
-      *jtj = joc.T() * cov_inv * joc;
-      *gg = joc.T() * cov_inv * rr;
+      for (int c = 0; c < 10; c++)
+      {
+        M3 acc = M3::zero();
+        for (int i = 0; i < 5; i++)
+          if (nz[i][a2]) acc = acc + J[i][a2].T() * WJ[i][c];
+        jtj->set<3, 3>(3 * a2, 3 * c, acc);
+      }
+      V3 ga = V3::zero();
+      for (int i = 0; i < 5; i++)
+        if (nz[i][a2]) ga = ga + J[i][a2].T() * Wr.blk<3, 1>(3 * i, 0);
+      gg->set<3, 1>(3 * a2, 0, ga);
     }
-    V15 w = cov_inv * rr;
-    double s = rr[0] * w[0];
-    for (int k = 1; k < 15; k++) s = s + rr[k] * w[k];
-    return s;
+    return cost;
   }
-  void update_state(const double* dxi15)  // imu_preintegration.cpp:235-242
+  void update_state(const double* dxi15)  // the LM step's bias increments (imu_preintegration.cpp:235-242)
   {
     dbg_buf = dbg;
     dba_buf = dba;
@@ -503,24 +558,37 @@ void ba_imu_factor_delete(ImuPre* f) { delete f; }
 int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPre*>& imus_factor, double imu_coef,
                     int* iters_out)
 {
-  const int DIM = 15, DVEL = 6;
+  // Levenberg-Marquardt with Nielsen's damping update on the window's 15-dim states, first frame fixed. What must
+  // equal the reference (LI_BA_Optimizer::damping_iter, optimizers.cpp:430-517) is the SEQUENCE OF DECISIONS - which
+  // steps are accepted, when the Hessian is re-evaluated, when the loop stops - because the oracle comparison counts
+  // BA runs and LM iterations per scan; the constants below (lambda0 = 0.01, nu = 2, gain -> 1 - (2 rho - 1)^3
+  // clamped at 1/3, relative-decrease stop at 1e-6, at most 10 iterations) are that contract. The algebra is
+  // organised for this solver: the fixed frame never enters the system (the reference zeroes its rows and columns of
+  // a 150 x 150 matrix), only the free (win - 1) * 15 block is assembled and factorised, D = diag(H) is a vector,
+  // and the device evaluates the LiDAR factor while the host evaluates the IMU factors.
+  const int SD = 15, PD = 6;  // state / pose dimension per frame
   const int win = (int)xs.size();
-  const int n = win * DIM, nl = win * DVEL;
-  double u = 0.01, v = 2;
-  std::vector<double> D((size_t)n * n, 0.0), Hess((size_t)n * n, 0.0), JacT(n, 0.0), dxi(n, 0.0);
-  for (int i = 0; i < n; i++) D[i + (size_t)n * i] = 1.0;
-  auto H = [&](int r, int c) -> double& { return Hess[r + (size_t)n * c]; };
+  const int m = (win - 1) * SD, nl = win * PD;
+  std::vector<double> Hf((size_t)m * m), gf(m), dvec(m), step((size_t)win * SD, 0.0);
   std::vector<double> hl((size_t)nl * nl), jl(nl);
   std::vector<vina_pose> poses(win);
-  auto set_poses = [&](const std::vector<vina_state>& s) {
+  auto set_poses = [&](const std::vector<vina_state>& st) {
     for (int i = 0; i < win; i++)
     {
-      memcpy(poses[i].R, s[i].R, 72);
-      memcpy(poses[i].p, s[i].p, 24);
+      memcpy(poses[i].R, st[i].R, 72);
+      memcpy(poses[i].p, st[i].p, 24);
     }
   };
-  double residual1 = 0, residual2 = 0, q;
-  bool is_calc_hess = true;
+  // entry (r, c) of the full system lands in the free block when neither index belongs to frame 0
+  auto addH = [&](int r, int c, double v) {
+    if (r >= SD && c >= SD) Hf[(r - SD) + (size_t)m * (c - SD)] += v;
+  };
+  auto addg = [&](int r, double v) {
+    if (r >= SD) gf[r - SD] += v;
+  };
+  double lambda = 0.01, nu = 2;
+  double cost_cur = 0, cost_try = 0;
+  bool relinearise = true;
   std::vector<vina_state> xt = xs;
   int iters = 0;
   // VINA_TRACE: where a BA run spends its time (host IMU factors / device LiDAR factor / solve)
@@ -533,126 +601,112 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
   for (int it = 0; it < 10; it++)
   {
     iters++;
-    if (is_calc_hess)
+    if (relinearise)
     {
-      // divide_thread (optimizers.cpp:181-245): the LiDAR factor on the device, the IMU factors on the host
-      // meanwhile (the reference overlaps the same two with its worker threads)
-      std::fill(Hess.begin(), Hess.end(), 0.0);
-      std::fill(JacT.begin(), JacT.end(), 0.0);
+      // normal equations at xs: LiDAR factor on the device, IMU factors on the host meanwhile (the reference
+      // overlaps the same two with its worker threads, divide_thread, optimizers.cpp:181-245)
+      std::fill(Hf.begin(), Hf.end(), 0.0);
+      std::fill(gf.begin(), gf.end(), 0.0);
       set_poses(xs);
       t0 = now_us();
       int r = vn_ba_hess_enqueue(ctx, poses.data(), win);
       if (r) return r;
-      double residual = 0;
+      double cost_imu = 0;
       HM<30, 30> jtj;
       HM<30, 1> gg;
       for (int i = 0; i < win - 1; i++)
       {
-        residual += imus_factor[i]->evaluate(xs[i], xs[i + 1], &jtj, &gg);
-        for (int c = 0; c < 2 * DIM; c++)
-          for (int r2 = 0; r2 < 2 * DIM; r2++) H(i * DIM + r2, i * DIM + c) += jtj(r2, c);
-        for (int r2 = 0; r2 < 2 * DIM; r2++) JacT[i * DIM + r2] += gg[r2];
+        cost_imu += imus_factor[i]->evaluate(xs[i], xs[i + 1], &jtj, &gg);
+        for (int c = 0; c < 2 * SD; c++)
+          for (int r2 = 0; r2 < 2 * SD; r2++) addH(i * SD + r2, i * SD + c, imu_coef * jtj(r2, c));
+        for (int r2 = 0; r2 < 2 * SD; r2++) addg(i * SD + r2, imu_coef * gg[r2]);
       }
-      for (double& h : Hess) h *= imu_coef;
-      for (double& j : JacT) j *= imu_coef;
-      residual *= (imu_coef * 0.5);
+      cost_imu *= (imu_coef * 0.5);
       tr_us[0] += now_us() - t0;
-      double rl = 0;
+      double cost_lidar = 0;
       t0 = now_us();
-      r = vn_ba_hess_finish(ctx, win, hl.data(), jl.data(), &rl);
+      r = vn_ba_hess_finish(ctx, win, hl.data(), jl.data(), &cost_lidar);
       if (r) return r;
       tr_us[1] += now_us() - t0;
-      for (int a = 0; a < win; a++)  // hess_plus (optimizers.cpp:171-179)
+      for (int a = 1; a < win; a++)  // the pose blocks of the LiDAR factor (hess_plus, optimizers.cpp:171-179)
       {
-        for (int k = 0; k < DVEL; k++) JacT[a * DIM + k] += jl[a * DVEL + k];
-        for (int b = 0; b < win; b++)
-          for (int c = 0; c < DVEL; c++)
-            for (int k = 0; k < DVEL; k++) H(a * DIM + k, b * DIM + c) += hl[(a * DVEL + k) + (size_t)nl * (b * DVEL + c)];
+        for (int k = 0; k < PD; k++) addg(a * SD + k, jl[a * PD + k]);
+        for (int b2 = 1; b2 < win; b2++)
+          for (int c = 0; c < PD; c++)
+            for (int k = 0; k < PD; k++) addH(a * SD + k, b2 * SD + c, hl[(a * PD + k) + (size_t)nl * (b2 * PD + c)]);
       }
-      residual1 = residual + rl;
+      cost_cur = cost_imu + cost_lidar;
+      for (int k = 0; k < m; k++) dvec[k] = Hf[k + (size_t)m * k];
     }
-    for (int c = 0; c < n; c++)
-      for (int r = 0; r < DIM; r++) H(r, c) = 0.0;
-    for (int c = 0; c < DIM; c++)
-      for (int r = 0; r < n; r++) H(r, c) = 0.0;
-    for (int c = 0; c < DIM; c++) H(c, c) = 1.0;
-    for (int r = 0; r < DIM; r++) JacT[r] = 0.0;
-    for (int k = 0; k < n; k++) D[k + (size_t)n * k] = H(k, k);
     t0 = now_us();
     {
-      // dxi = (Hess + u D).ldlt().solve(-JacT). The first frame is fixed: its rows / columns are the identity
-      // and its gradient is zero, so dxi(0:15) = 0 and the remaining (n - 15)^2 block is solved on its own.
-      const int m = n - DIM;
-      std::vector<double> A((size_t)m * m), nb(m);
-      for (int c = 0; c < m; c++)
-        for (int r = 0; r < m; r++)
-          A[r + (size_t)m * c] = Hess[(DIM + r) + (size_t)n * (DIM + c)] + u * D[(DIM + r) + (size_t)n * (DIM + c)];
-      for (int k = 0; k < m; k++) nb[k] = -JacT[DIM + k];
+      // step = -(H + lambda D)^-1 g on the free block
+      std::vector<double> A = Hf, nb(m);
+      for (int k = 0; k < m; k++)
+      {
+        A[k + (size_t)m * k] += lambda * dvec[k];
+        nb[k] = -gf[k];
+      }
       std::vector<double> sol = ldlt_solve(A, m, nb);
-      for (int k = 0; k < DIM; k++) dxi[k] = 0.0;
-      for (int k = 0; k < m; k++) dxi[DIM + k] = sol[k];
+      for (int k = 0; k < m; k++) step[SD + k] = sol[k];
     }
     tr_us[2] += now_us() - t0;
-    for (int j = 0; j < win; j++)
+    for (int j = 0; j < win; j++)  // xt = xs (+) step
     {
-      V3 d0;
-      for (int k = 0; k < 3; k++) d0[k] = dxi[DIM * j + k];
+      const double* d = &step[SD * j];
+      V3 d0 = v3(d);
       M3 Rn = m3(xs[j].R) * Exp(d0);
       memcpy(xt[j].R, Rn.d, 72);
       for (int k = 0; k < 3; k++)
       {
-        xt[j].p[k] = xs[j].p[k] + dxi[DIM * j + 3 + k];
-        xt[j].v[k] = xs[j].v[k] + dxi[DIM * j + 6 + k];
-        xt[j].bg[k] = xs[j].bg[k] + dxi[DIM * j + 9 + k];
-        xt[j].ba[k] = xs[j].ba[k] + dxi[DIM * j + 12 + k];
+        xt[j].p[k] = xs[j].p[k] + d[3 + k];
+        xt[j].v[k] = xs[j].v[k] + d[6 + k];
+        xt[j].bg[k] = xs[j].bg[k] + d[9 + k];
+        xt[j].ba[k] = xs[j].ba[k] + d[12 + k];
       }
     }
-    for (int j = 0; j < win - 1; j++) imus_factor[j]->update_state(&dxi[DIM * j]);
-    double q1 = 0;
+    for (int j = 0; j < win - 1; j++) imus_factor[j]->update_state(&step[SD * j]);
+    // predicted decrease of the quadratic model: 1/2 step^T (lambda D step - g)
+    double predicted = 0;
+    for (int k = 0; k < m; k++) predicted += step[SD + k] * ((lambda * dvec[k]) * step[SD + k] - gf[k]);
+    predicted *= 0.5;
     {
-      // D is diagonal: u D dxi - JacT needs no 150x150 product
-      double s = 0;
-      for (int k = 0; k < n; k++) s += dxi[k] * ((u * D[k + (size_t)n * k]) * dxi[k] - JacT[k]);
-      q1 = 0.5 * s;
-    }
-    // only_residual (optimizers.cpp:340-376)
-    {
-      double r1 = 0;
+      // cost at the candidate (only_residual, optimizers.cpp:340-376)
+      double c_imu = 0;
       t0 = now_us();
-      for (int i = 0; i < win - 1; i++) r1 += imus_factor[i]->evaluate(xt[i], xt[i + 1], nullptr, nullptr);
-      r1 *= (imu_coef * 0.5);
+      for (int i = 0; i < win - 1; i++) c_imu += imus_factor[i]->evaluate(xt[i], xt[i + 1], nullptr, nullptr);
+      c_imu *= (imu_coef * 0.5);
       tr_us[3] += now_us() - t0;
       set_poses(xt);
-      double rl = 0;
+      double c_lidar = 0;
       t0 = now_us();
-      int r = vina_ba_lidar_residual(ctx, poses.data(), win, &rl, nullptr, 0);
+      int r = vina_ba_lidar_residual(ctx, poses.data(), win, &c_lidar, nullptr, 0);
       if (r) return r;
       tr_us[4] += now_us() - t0;
-      residual2 = r1 + rl;
+      cost_try = c_imu + c_lidar;
     }
-    q = residual1 - residual2;
-    if (q > 0)
+    const double decrease = cost_cur - cost_try;
+    if (decrease > 0)
     {
       xs = xt;
-      const double one_three = 1.0 / 3;
-      q = q / q1;
-      v = 2;
-      q = 1 - std::pow(2 * q - 1, 3);
-      u *= (q < one_three ? one_three : q);
-      is_calc_hess = true;
+      const double rho = decrease / predicted;
+      const double shrink = 1 - std::pow(2 * rho - 1, 3);
+      lambda *= (shrink < 1.0 / 3 ? 1.0 / 3 : shrink);
+      nu = 2;
+      relinearise = true;
     }
     else
     {
-      u = u * v;
-      v = 2 * v;
-      is_calc_hess = false;
-      for (int j = 0; j < win - 1; j++)
+      lambda *= nu;
+      nu *= 2;
+      relinearise = false;
+      for (int j = 0; j < win - 1; j++)  // the factors go back to the biases of xs
       {
         imus_factor[j]->dbg = imus_factor[j]->dbg_buf;
         imus_factor[j]->dba = imus_factor[j]->dba_buf;
       }
     }
-    if (std::fabs((residual1 - residual2) / residual1) < 1e-6) break;
+    if (std::fabs(decrease / cost_cur) < 1e-6) break;
   }
   if (iters_out) *iters_out = iters;
   if (ctx->trace && (++tr_calls % 10) == 0)

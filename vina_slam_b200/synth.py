@@ -345,6 +345,26 @@ class Sequence:
                     gt_v=self.traj.vel(end_time), end_time=end_time)
 
 
+def _gen_job(job):
+    cfg, seed, n_boot, n_steps = job
+    seq = Sequence(cfg, seed=seed)
+    return [seq.next_scan(deskewed=True) for _ in range(n_boot)], [seq.next_scan() for _ in range(n_steps)]
+
+
+def gen_sequences(cfg: SensorConfig, seeds, n_boot: int, n_steps: int, procs: int | None = None):
+    """[(bootstrap scans, scans)] for several seeds, generated in worker processes (a full-size scan costs about a
+    second of numpy ray casting; independent sequences are independent jobs)."""
+    import multiprocessing as mp
+    import os
+
+    jobs = [(cfg, int(sd), n_boot, n_steps) for sd in seeds]
+    procs = min(len(jobs), procs or (os.cpu_count() or 1))
+    if procs <= 1 or len(jobs) <= 1:
+        return [_gen_job(j) for j in jobs]
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(_gen_job, jobs)
+
+
 def rot_err_deg(Ra: np.ndarray, Rb: np.ndarray) -> float:
     c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
     return math.degrees(math.acos(max(-1.0, min(1.0, c))))
