@@ -342,6 +342,18 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
       else if (nx < n && lane == 18)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(cache + nx));
     }
+    // the leaf this thread's NEXT point is cached on: pull both lines of its record towards L1 now, a whole round
+    // ahead of their use (the record is two dependent gathers otherwise)
+    if (!(bt.mode & VN_IEKF_NOCACHE) && i + stride < n)
+    {
+      const int nc = cache[i + stride];
+      if (nc >= 0)
+      {
+        const char* rec = reinterpret_cast<const char*>(hot + nc);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 128));
+      }
+    }
     // independent loads first (memory-level parallelism): point, covariance, cached leaf
     const double* __restrict__ pi = pv + ii;
     const double pnt[3] = { __ldg(pi), __ldg(pi + pvs), __ldg(pi + 2 * pvs) };
@@ -367,6 +379,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
     if (cached >= 0)
     {
       const double2* L = reinterpret_cast<const double2*>(hot + cached);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 8));  // line 1 (sigma_l terms): on its way before the gate asks
       const double2 l3 = __ldg(L + 3), l4 = __ldg(L + 4);
       l0 = __ldg(L + 0);
       l1 = __ldg(L + 1);
@@ -417,6 +430,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
       if (node >= 0 && (flags & VN_FLAG_PLANE))
       {
         const double2* L = reinterpret_cast<const double2*>(hot + node);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 8));
         l0 = __ldg(L + 0);
         l1 = __ldg(L + 1);
         l2 = __ldg(L + 2);

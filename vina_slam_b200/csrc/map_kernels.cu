@@ -52,6 +52,54 @@ __device__ __forceinline__ void pose_sel(const PoseBuf& xb, const LivePose& lv, 
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *((const volatile int*)p); }
 
+// The map kernels are latency chains over a nearly empty machine: a node's NodeCold record (1.6 KB, 13 lines) is read
+// field by field along a dependent computation, every first touch of a line a DRAM round trip. Pulling the lines
+// towards L1 as soon as the node id is known turns all but the first into cache hits.
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#define VN_COLD_LINES ((int)((sizeof(NodeCold) + 127) / 128) + 1)  // (+1: records are not line-aligned)
+__device__ __forceinline__ void prefetch_cold(const NodeCold* c, int part, int parts)
+{
+  const char* b = reinterpret_cast<const char*>(c);
+  for (int l = part; l < VN_COLD_LINES; l += parts) prefetch_line(b + 128 * l);
+}
+
+// VINA_SPLIT_TRACE build (debugging): cycle stamps along the work of one unit (a leaf's group / block), collected
+// per kernel and summarised by vn_split_trace_dump (mean and maximum of every phase, the slowest unit)
+#ifdef VINA_SPLIT_TRACE
+#define KT_SLOTS 8192
+#define KT_PH 24
+__device__ long long g_kt[3][KT_SLOTS][KT_PH];
+__device__ int g_kt_n[3];
+#define KT_DECL      \
+  long long kt_[KT_PH]; \
+  int kt_k = 0
+#define KT() \
+  do \
+  { \
+    if (kt_k < KT_PH) kt_[kt_k++] = clock64(); \
+  } while (0)
+#define KT_COMMIT(which) \
+  do \
+  { \
+    const int s_ = atomicAdd(&g_kt_n[which], 1); \
+    if (s_ < KT_SLOTS) \
+      for (int i_ = 0; i_ < KT_PH; i_++) g_kt[which][s_][i_] = i_ < kt_k ? kt_[i_] : 0; \
+  } while (0)
+#else
+#define KT_DECL \
+  do \
+  { \
+  } while (0)
+#define KT() \
+  do \
+  { \
+  } while (0)
+#define KT_COMMIT(which) \
+  do \
+  { \
+  } while (0)
+#endif
+
 __device__ int alloc_node(const MapView& M)
 {
   // ids released by the pruning first (records are zero, like never-used pool memory)
@@ -440,9 +488,13 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
 
   for (int j = blockIdx.x * ACC_WARPS + warp; j < nt; j += gridDim.x * ACC_WARPS)
   {
+    KT_DECL;
+    KT();
     const int leaf = sc.touched[j];
     NodeCold& c = M.cold[leaf];
+    prefetch_cold(&c, lane, 32);
     const int cnt = c.pend_cnt;
+    KT();
     int* idx = sc.idx + c.pend_off;
     // ascending point order
     if (cnt <= 32)
@@ -485,6 +537,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
       }
     }
     __syncwarp();
+    KT();
     const bool store = M.hot[leaf].layer < M.max_layer;
     const int old_cnt = c.win_cnt[mord];
     int woff = 0;
@@ -511,6 +564,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
       cl = cluster_get(c.pcrs_local[mord], L.ck);
     double cv0 = c.cov_add[lane];
     double cv1 = has2 ? c.cov_add[lane + 32] : 0.0;
+    KT();
     for (int base = 0; base < cnt; base += 32)
     {
       const int a = base + lane;
@@ -572,6 +626,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
       cv1 += s1;
       __syncwarp();
     }
+    KT();
     if (lane < 9)
       cluster_set(c.pcr_add, L.ck, cl);
     else if (lane < 18)
@@ -590,6 +645,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
         c.win_cnt[mord] = cnt + old_cnt;
       }
       c.pend_cnt = 0;
+      KT();
+      KT_COMMIT(2);
     }
     __syncwarp();
   }
@@ -786,6 +843,13 @@ __global__ void __launch_bounds__(128) k_recut_all(MapView M, LayerLists LL)
   {
     const int n = nodes[j];
     NodeHot& h = M.hot[n];
+    {
+      // what recut_leaf touches: pcr_add (front of the record), the eigen-decomposition and the flags (back)
+      const char* b = reinterpret_cast<const char*>(&M.cold[n]);
+      prefetch_line(b);
+      prefetch_line(b + offsetof(NodeCold, eig_value));
+      prefetch_line(b + offsetof(NodeCold, last_num));
+    }
     if (h.flags & VN_FLAG_INTERIOR) continue;
     if (recut_leaf(M, h, M.cold[n])) LL.split[atomicAdd(&LL.count[4], 1)] = n;
   }
@@ -835,20 +899,11 @@ __global__ void __launch_bounds__(128) k_ba_collect(MapView M, LayerLists LL, Ba
 //                  pcrs_local[slot]) and applies that child's rows sequentially (exact sums, reference order;
 //                  the per-class cluster is flushed whenever the class of the next row changes),
 //   every thread   owns up to three (child, cov_add entry) pairs and sums that child's staged Bf_var terms.
-// VINA_SPLIT_TRACE build: cycle stamps of the first splitting leaf's block at the phase boundaries (debugging)
-#ifdef VINA_SPLIT_TRACE
-__device__ long long g_split_ts[2][8];
 #define VN_SPLIT_STAMP(k) \
   do \
   { \
-    if (threadIdx.x == 0 && j == 0) g_split_ts[round & 1][k] = clock64(); \
+    if (threadIdx.x == 0) KT(); \
   } while (0)
-#else
-#define VN_SPLIT_STAMP(k) \
-  do \
-  { \
-  } while (0)
-#endif
 #define SPLIT_THREADS 256
 #define SPLIT_BATCH 256  // rows per batch = threads: every thread stages one row
 #define SPLIT_WARPS (SPLIT_BATCH / 32)
@@ -873,8 +928,45 @@ __device__ __forceinline__ int split_rows_before(const unsigned int (*bm)[8], in
   return r;
 }
 
-__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int round, int win_count, PoseBuf xb,
-                                                         LivePose lv)
+// The work queue of k_split: LL.split holds the leaves to subdivide, LL.count[4] = pushed, [5] = claimed, [6] =
+// completed. k_recut_all pushes the leaves it finds; a block that subdivides a leaf judges the children it creates
+// and pushes those that have to be subdivided themselves - all levels in ONE launch, a child's subdivision starts
+// as soon as its parent's block is through instead of a launch later. Slots hold -1 until their item is written
+// (the claim of a position and the write of the item are two steps) and are reset by the consumer.
+// Returns the node to subdivide, or -1 when every pushed item has been completed (nothing can be pushed any more).
+#define SPLIT_POP_LIMIT 4000000
+__device__ int split_pop(const MapView& M, const LayerLists& LL, int* index)
+{
+  for (int spins = 0; spins < SPLIT_POP_LIMIT; spins++)
+  {
+    const int done = ld_volatile(&LL.count[6]);
+    __threadfence();  // `done` is read before `tail`: done == tail then means nothing was in flight at that moment
+    const int tail = ld_volatile(&LL.count[4]);
+    const int head = ld_volatile(&LL.count[5]);
+    if (head < tail)
+    {
+      if (atomicCAS(&LL.count[5], head, head + 1) != head) continue;
+      int v = ld_volatile(&LL.split[head]);
+      for (int w = 0; v < 0 && w < SPLIT_POP_LIMIT; w++) v = ld_volatile(&LL.split[head]);
+      if (v < 0) break;
+      LL.split[head] = -1;
+      *index = head;
+      return v;
+    }
+    if (done == tail) return -1;
+    __nanosleep(100);
+  }
+  atomicOr(M.status, VN_ST_SPIN);
+  return -1;
+}
+__device__ __forceinline__ void split_push(const LayerLists& LL, int node)
+{
+  __threadfence();  // the node's record (written by this block, behind a barrier) before the item
+  const int pos = atomicAdd(&LL.count[4], 1);
+  *((volatile int*)&LL.split[pos]) = node;
+}
+
+__global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
 {
   extern __shared__ double split_smem[];
   double(*val)[19] = reinterpret_cast<double(*)[19]>(split_smem);  // per row: the 9 push() terms of the world point, then of the stored point
@@ -890,6 +982,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   __shared__ int clsrow[SPLIT_BATCH];
   __shared__ int nseg, total, nfix, fixtot;
   __shared__ int wcnt_s[VINA_MAX_WIN], woff_s[VINA_MAX_WIN];
+  __shared__ int s_item, s_index;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   LaneRole L;
@@ -899,14 +992,15 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   const bool chain = ct >= 0;
   role_init(chain ? ct : 0, L);  // L.ck = ct % 9
   const int my_k = chain ? ct / 9 : 0;  // cluster chain of this thread
-  // the leaves of this round: those k_recut_all found (round 0) or children of the previous round's leaves that
-  // have to be subdivided themselves; the rounds' lists lie one behind the other in LL.split
-  const int nsplit = LL.count[4 + round];
-  int sbase = 0;
-  for (int q = 0; q < round; q++) sbase += LL.count[4 + q];
-  for (int j = blockIdx.x; j < nsplit; j += gridDim.x)
+  for (;;)
   {
-    const int n = LL.split[sbase + j];
+    __syncthreads();  // the previous leaf's shared state is no longer in use
+    if (t == 0) s_item = split_pop(M, LL, &s_index);
+    __syncthreads();
+    const int n = s_item;
+    if (n < 0) return;
+    __threadfence();  // acquire: the leaf may have been written by another block of this launch
+    KT_DECL;
     NodeCold& c = M.cold[n];
     NodeHot& h = M.hot[n];
     const bool store = (h.layer + 1) < M.max_layer;
@@ -1105,6 +1199,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           }
         }
         __syncthreads();
+        VN_SPLIT_STAMP(51);
         // phase 2: every row goes to its slot in child-major order (stable: stream order inside a child), so
         // that the sequential consumers below read contiguous rows; the products of PointCluster::push
         // (types.hpp:137-142) are formed here, in parallel - the chains only add
@@ -1153,6 +1248,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
           }
         }
         __syncthreads();
+        VN_SPLIT_STAMP(52);
         // phase 3: push_fix (octree.cpp:179-188) / push (octree.cpp:151-177) of this batch's rows. The adds are
         // sequential (reference order, exact sums); the shared-memory loads are not: 8 rows are fetched ahead of
         // the chain so that a row costs one dependent add instead of a load-to-use latency
@@ -1247,7 +1343,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       const int p = t + SPLIT_THREADS * q;
       if (p < 360 && kid[p / 45] >= 0) M.cold[kid[p / 45]].cov_add[p % 45] = cv[q];
     }
-    // PVec().swap(point_fix); sw->clear(); sws.push_back(sw); sw = nullptr; octo_state = 1
+    // PVec().swap(point_fix); sw->clear(); sws.push_back(sw); sw = nullptr; octo_state = 1 (spread over threads:
+    // one thread doing the ~120 stores and 8 loads in a row is 3 us of this block's latency)
     if (t == 0)
     {
       if (has_fix)
@@ -1255,39 +1352,77 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         c.fix_head = c.fix_tail = -1;
         c.fix_count = 0;
       }
-      for (int s = 0; s < M.win_size; s++)
-      {
-        c.win_cnt[s] = 0;
-        cluster_clear(c.pcrs_local[s]);
-      }
       c.has_sw = 0;
-      for (int k = 0; k < 8; k++) h.children[k] = c.children[k];  // mirror read by k_iekf
       h.flags |= VN_FLAG_INTERIOR;
     }
+    else if (t >= 32 && t < 32 + M.win_size)
+    {
+      c.win_cnt[t - 32] = 0;
+      cluster_clear(c.pcrs_local[t - 32]);
+    }
+    else if (t >= 64 && t < 72)
+      h.children[t - 64] = c.children[t - 64];  // mirror read by k_iekf
     VN_SPLIT_STAMP(6);
     // leaves[i]->recut(...) of the new children (octree.cpp:388-392), one thread per child: their sums are
     // complete (written by this block), nobody else knows them yet. A child that has to be subdivided itself
-    // goes to the next round's list; every child joins its layer's node list for the multi_margi of this scan.
+    // goes into the queue; every child joins its layer's node list for the multi_margi of this scan.
     __syncthreads();
     if (t < 8 && kid[t] >= 0)
     {
       NodeHot& kh = M.hot[kid[t]];
       const int cl = kh.layer;
       if (cl <= 3) LL.list[cl][atomicAdd(&LL.count[cl], 1)] = kid[t];
-      if (!(kh.flags & VN_FLAG_INTERIOR) && recut_leaf(M, kh, M.cold[kid[t]]))
-        LL.split[sbase + nsplit + atomicAdd(&LL.count[4 + round + 1], 1)] = kid[t];
+      if (!(kh.flags & VN_FLAG_INTERIOR) && recut_leaf(M, kh, M.cold[kid[t]])) split_push(LL, kid[t]);
+    }
+    __syncthreads();
+    if (t == 0)
+    {
+      KT();
+#ifdef VINA_SPLIT_TRACE
+      kt_[KT_PH - 1] = total;  // (rows of the leaf, shown as the last "stamp")
+      kt_k = KT_PH;
+#endif
+      KT_COMMIT(0);
+      __threadfence();
+      atomicAdd(&LL.count[6], 1);  // this leaf is complete (its pushes are in)
     }
   }
 }
 #ifdef VINA_SPLIT_TRACE
 void vn_split_trace_dump()
 {
-  long long h[2][8];
-  cudaMemcpyFromSymbol(h, g_split_ts, sizeof(h));
-  for (int l = 0; l < 2; l++)
+  static long long h[3][KT_SLOTS][KT_PH];
+  int n[3];
+  cudaMemcpyFromSymbol(h, g_kt, sizeof(h));
+  cudaMemcpyFromSymbol(n, g_kt_n, sizeof(n));
+  const char* names[3] = { "k_split (per leaf: block thread 0)", "k_margi_leaves (per leaf: lane 0 of the group)", "k_insert_accum (per leaf: lane 0)" };
+  for (int w = 0; w < 3; w++)
   {
-    fprintf(stderr, "[vina trace] k_split layer %d, cycles since block start of the first leaf:", l);
-    for (int k = 1; k <= 6; k++) fprintf(stderr, " %lld", h[l][k] - h[l][0]);
+    const int cnt = n[w] < KT_SLOTS ? n[w] : KT_SLOTS;
+    if (cnt == 0) continue;
+    double mean[KT_PH] = { 0 }, mx[KT_PH] = { 0 };
+    int worst = 0;
+    long long worst_t = 0;
+    int np = 0;
+    for (int s = 0; s < cnt; s++)
+    {
+      int k = 0;
+      while (k < KT_PH - 1 && h[w][s][k] != 0) k++;
+      if (k > np) np = k;
+      for (int i = 1; i < k; i++)
+      {
+        const double d = (double)(h[w][s][i] - h[w][s][i - 1]);
+        mean[i] += d / cnt;
+        if (d > mx[i]) mx[i] = d;
+      }
+      if (k > 1 && h[w][s][k - 1] - h[w][s][0] > worst_t) worst_t = h[w][s][k - 1] - h[w][s][0], worst = s;
+    }
+    fprintf(stderr, "[vina ktrace] %s: %d units (all scans), phases in cycles\n  mean:", names[w], n[w]);
+    for (int i = 1; i < np; i++) fprintf(stderr, " %.0f", mean[i]);
+    fprintf(stderr, "\n  max: ");
+    for (int i = 1; i < np; i++) fprintf(stderr, " %.0f", mx[i]);
+    fprintf(stderr, "\n  slowest unit (%lld cycles, tag %lld):", worst_t, h[w][worst][KT_PH - 1]);
+    for (int i = 1; i < np && h[w][worst][i] != 0; i++) fprintf(stderr, " %lld", h[w][worst][i] - h[w][worst][i - 1]);
     fprintf(stderr, "\n");
   }
 }
@@ -1388,54 +1523,87 @@ struct MargiShared
   double uc[27], Jc[27];
 };
 
-__device__ void margi_leaf_group(const MapView& M, int n, int win_count, const PoseBuf& xb, const LivePose& lv, int g,
-                                 unsigned gmask, MargiShared& sh, const PointRec*& job_src, int& job_off, int& job_np)
+// One pass of a warp: the four leaves nodes[j0 .. j0 + 3], one per 8-lane group. The groups take different branches
+// (BA-factor leaf or not, plane or not, update due or not); the phases are separated by FULL-warp barriers so that
+// the groups reconverge after every phase and run the common ones in lock step - without them four diverged groups
+// execute one after the other and a warp takes the sum of its leaves' times instead of the longest.
+__device__ void margi_warp_pass(const MapView& M, const int* __restrict__ nodes, int nn, int j0, int win_count,
+                                const PoseBuf& xb, const LivePose& lv, int lane, MargiShared* sh4,
+                                const PointRec*& job_src, int& job_off, int& job_np)
 {
+  const int g = lane & (MG - 1), grp = lane / MG;
+  MargiShared& sh = sh4[grp];
+  const int j = j0 + grp;
+  KT_DECL;
+  KT();
+  int n = 0;
+  bool active = false;
+  if (j < nn)
+  {
+    n = nodes[j];
+    active = !(M.hot[n].flags & VN_FLAG_INTERIOR);
+  }
   NodeHot& h = M.hot[n];
   NodeCold& c = M.cold[n];
-  if (!c.isexist || !c.has_sw) return;  // (uniform over the group)
-  __syncwarp(gmask);                    // the previous leaf's readers of `sh` are done
-  const int s0 = M.mp[0];
-  const bool is_plane = (h.flags & VN_FLAG_PLANE) != 0;
-  const bool factor = c.opt_state >= 0;
-  Cluster fix = c.pcr_fix;
-  Cluster add, world0;
-  cluster_clear(world0);
-  double ev[3], Q[9];
-  bool have_eig = false;
-  int n_loc0;
-  if (factor)
+  if (active)
   {
-    add = c.pcr_add;
-    const Cluster loc0 = c.pcrs_local[s0];
-    n_loc0 = loc0.N;
-    if (loc0.N != 0)
-    {
-      double xr[9], xp[3];
-      pose_sel(xb, lv, 0, xr, xp);
-      cluster_transform(world0, loc0, xr, xp);
-    }
+    prefetch_cold(&c, g, MG);
+    active = c.isexist && c.has_sw;
   }
-  else
+  KT();
+  const int s0 = M.mp[0];
+  bool is_plane = false, factor = false, have_eig = false;
+  Cluster fix, add, world0;
+  cluster_clear(world0);
+  cluster_clear(fix);
+  cluster_clear(add);
+  double ev[3] = { 0, 0, 0 }, Q[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  int n_loc0 = 0;
+  // ---- phase A: the frames' clusters into the world frame (PointCluster::transform)
+  if (active)
   {
-    for (int i = g; i < win_count; i += MG)
+    is_plane = (h.flags & VN_FLAG_PLANE) != 0;
+    factor = c.opt_state >= 0;
+    fix = c.pcr_fix;
+    if (factor)
     {
-      const Cluster loc = c.pcrs_local[M.mp[i]];
-      double* w = sh.w[i];
-      w[9] = (double)loc.N;
-      if (loc.N != 0)
+      add = c.pcr_add;
+      const Cluster loc0 = c.pcrs_local[s0];
+      n_loc0 = loc0.N;
+      if (loc0.N != 0)
       {
-        Cluster t;
         double xr[9], xp[3];
-        pose_sel(xb, lv, i, xr, xp);
-        cluster_transform(t, loc, xr, xp);
-#pragma unroll
-        for (int k = 0; k < 6; k++) w[k] = t.P[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) w[6 + k] = t.v[k];
+        pose_sel(xb, lv, 0, xr, xp);
+        cluster_transform(world0, loc0, xr, xp);
       }
     }
-    __syncwarp(gmask);
+    else
+    {
+      for (int i = g; i < win_count; i += MG)
+      {
+        const Cluster loc = c.pcrs_local[M.mp[i]];
+        double* w = sh.w[i];
+        w[9] = (double)loc.N;
+        if (loc.N != 0)
+        {
+          Cluster t;
+          double xr[9], xp[3];
+          pose_sel(xb, lv, i, xr, xp);
+          cluster_transform(t, loc, xr, xp);
+#pragma unroll
+          for (int k = 0; k < 6; k++) w[k] = t.P[k];
+#pragma unroll
+          for (int k = 0; k < 3; k++) w[6 + k] = t.v[k];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  KT();
+  // ---- phase B: pcr_add = pcr_fix + the frames in order (the reference's additions, octree.cpp:425-431), then the
+  // eigen-decomposition of a plane (:432-438)
+  if (active && !factor)
+  {
     add = fix;
     n_loc0 = (int)sh.w[0][9];
     for (int i = 0; i < win_count; i++)
@@ -1453,20 +1621,25 @@ __device__ void margi_leaf_group(const MapView& M, int n, int win_count, const P
         cluster_add(add, t);
       }
     }
-    if (is_plane)
-    {
-      double L[6];
-      cluster_cov(add, L);
-      eig3_sym(L, ev, Q);
-      have_eig = true;
-    }
   }
-
-  const int last_num = c.last_num;
-  const bool update = fix.N < M.max_points && is_plane && (add.N - last_num >= 5 || last_num <= 10);
+  __syncwarp();
+  KT();
+  if (active && !factor && is_plane)
+  {
+    double L[6];
+    cluster_cov(add, L);
+    eig3_sym(L, ev, Q);
+    have_eig = true;
+  }
+  __syncwarp();
+  KT();
+  // ---- phase C: plane_update (octree.cpp:302-333, 441-446)
+  const int last_num = active ? c.last_num : 0;
+  const bool update = active && fix.N < M.max_points && is_plane && (add.N - last_num >= 5 || last_num <= 10);
+  double nv = 0.0, coef0 = 0.0, coef1 = 0.0;
+  double center[3] = { 0, 0, 0 };
   if (update)
   {
-    // ---- plane_update (octree.cpp:302-333)
     if (!have_eig)
     {
 #pragma unroll
@@ -1476,13 +1649,13 @@ __device__ void margi_leaf_group(const MapView& M, int n, int win_count, const P
     }
     for (int e = g; e < 45; e += MG) sh.cov[e] = c.cov_add[e];
     const double N = (double)add.N;
-    const double center[3] = { add.v[0] / N, add.v[1] / N, add.v[2] / N };
-    const double nv = 1.0 / N;
-    // u[k] = column k of the eigenvectors; l = 0
-    double coef[2];
+    center[0] = add.v[0] / N;
+    center[1] = add.v[1] / N;
+    center[2] = add.v[2] / N;
+    nv = 1.0 / N;
     if (g < 2)
     {
-      // lanes 0 and 1 build the row vectors of k = 1, 2 (columns picked by selects: Q stays in registers)
+      // lanes 0 and 1 build the row vectors of k = 1, 2 (l = 0; columns picked by selects: Q stays in registers)
       const double uk[3] = { g == 0 ? Q[3] : Q[6], g == 0 ? Q[4] : Q[7], g == 0 ? Q[5] : Q[8] };
       const double* ul = Q;
       double* f = sh.f[g];
@@ -1496,36 +1669,56 @@ __device__ void margi_leaf_group(const MapView& M, int n, int win_count, const P
       const double dl = (ul[0] * center[0] + ul[1] * center[1]) + ul[2] * center[2];
       for (int a = 0; a < 3; a++) f[6 + a] = -(dk * ul[a] + dl * uk[a]);
     }
-    coef[0] = nv / (ev[0] - ev[1]);
-    coef[1] = nv / (ev[0] - ev[2]);
-    __syncwarp(gmask);
+    coef0 = nv / (ev[0] - ev[1]);
+    coef1 = nv / (ev[0] - ev[2]);
+  }
+  __syncwarp();
+  if (update)
     for (int o = g; o < 27; o += MG)
     {
       const int r = o / 9, q = o - 9 * r;
       const double u1r = r == 0 ? Q[3] : (r == 1 ? Q[4] : Q[5]);  // (no dynamically indexed register arrays)
       const double u2r = r == 0 ? Q[6] : (r == 1 ? Q[7] : Q[8]);
       double s = 0.0;
-      s += (coef[0] * u1r) * sh.f[0][q];
-      s += (coef[1] * u2r) * sh.f[1][q];
+      s += (coef0 * u1r) * sh.f[0][q];
+      s += (coef1 * u2r) * sh.f[1][q];
       sh.uc[o] = s;
     }
-    __syncwarp(gmask);
+  __syncwarp();
+  if (update)
     for (int o = g; o < 27; o += MG)
     {
       const int r = o / 9, q = o - 9 * r;
-      double s = 0.0;
-      for (int t = 0; t < 9; t++) s += sh.uc[9 * r + t] * sh.cov[sN(9, t, q)];
-      sh.Jc[o] = s;
+      // (plane_var is toleranced, 1e-7: three interleaved fused partial sums instead of one chain of nine
+      // multiply-add pairs - a dependent fp64 operation costs ~25-30 cycles here)
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; t++)
+      {
+        s0 = fma(sh.uc[9 * r + t], sh.cov[sN(9, t, q)], s0);
+        s1 = fma(sh.uc[9 * r + 3 + t], sh.cov[sN(9, 3 + t, q)], s1);
+        s2 = fma(sh.uc[9 * r + 6 + t], sh.cov[sN(9, 6 + t, q)], s2);
+      }
+      sh.Jc[o] = (s0 + s1) + s2;
     }
-    __syncwarp(gmask);
+  __syncwarp();
+  if (update)
+  {
     // plane_var = [[Jc u_c^T, nv Jc(:,6:9)],[.^T, nv^2 cov_add(6:9,6:9)]] (upper triangle) and the per-plane part
     // of sigma_l for the IEKF (NodeHot: A, B n, n^T C n)
     const double* nrm = Q;  // u[0]
     if (g < 6)
     {
       const int a = g < 3 ? 0 : (g < 5 ? 1 : 2), b = g < 3 ? g : (g < 5 ? g - 2 : 2);  // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
-      double s = 0.0;
-      for (int t = 0; t < 9; t++) s += sh.Jc[9 * a + t] * sh.uc[9 * b + t];
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 3; t++)
+      {
+        s0 = fma(sh.Jc[9 * a + t], sh.uc[9 * b + t], s0);
+        s1 = fma(sh.Jc[9 * a + 3 + t], sh.uc[9 * b + 3 + t], s1);
+        s2 = fma(sh.Jc[9 * a + 6 + t], sh.uc[9 * b + 6 + t], s2);
+      }
+      const double s = (s0 + s1) + s2;
       c.plane_var[sN(6, a, b)] = s;
       h.qA[g] = s;
       c.plane_var[sN(6, 3 + a, 3 + b)] = (nv * nv) * sh.cov[sN(9, 6 + a, 6 + b)];
@@ -1555,18 +1748,16 @@ __device__ void margi_leaf_group(const MapView& M, int n, int win_count, const P
       c.last_num = add.N;
     }
   }
-
-  // ---- bookkeeping: lane 0
-  if (g != 0) return;
+  __syncwarp();  // (the next pass reuses `sh`)
+  KT();
+  // ---- bookkeeping (octree.cpp:448-481): lane 0 of the group
+  if (!active || g != 0) return;
   if (factor)
     c.opt_state = -1;
-  else
+  else if (have_eig)
   {
-    if (have_eig)
-    {
-      for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
-      for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
-    }
+    for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
+    for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
   }
   if (fix.N < M.max_points)
   {
@@ -1601,6 +1792,8 @@ __device__ void margi_leaf_group(const MapView& M, int n, int win_count, const P
     c.win_cnt[s0] = 0;
   }
   c.isexist = (fix.N >= add.N) ? 0 : 1;
+  KT();
+  KT_COMMIT(1);
 }
 
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
@@ -1613,21 +1806,14 @@ __global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists L
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
   const int lane = threadIdx.x & 31;
-  const int g = lane & (MG - 1), grp = lane / MG;
-  const unsigned gmask = ((1u << MG) - 1u) << (MG * grp);
-  MargiShared& sh = sh_all[threadIdx.x / MG];
+  MargiShared* sh4 = sh_all + (threadIdx.x >> 5) * (32 / MG);
   const int gpw = 32 / MG;  // leaves per warp and pass
   const int stride = gridDim.x * (blockDim.x / 32) * gpw;
   for (int j0 = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * gpw; j0 < nn; j0 += stride)  // warp-uniform
   {
-    const int j = j0 + grp;
     const PointRec* job_src = nullptr;
     int job_off = 0, job_np = 0;
-    if (j < nn)
-    {
-      const int n = nodes[j];
-      if (!(M.hot[n].flags & VN_FLAG_INTERIOR)) margi_leaf_group(M, n, win_count, xb, lv, g, gmask, sh, job_src, job_off, job_np);
-    }
+    margi_warp_pass(M, nodes, nn, j0, win_count, xb, lv, lane, sh4, job_src, job_off, job_np);
     __syncwarp();
     // the warp's copy jobs as ONE stream of points, 32 per pass (points go to the world frame of x_buf[0]): a
     // leaf folds only a handful of points per scan, so walking the jobs one after the other would leave most
@@ -2101,10 +2287,13 @@ int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int wi
   k_recut_collect<<<592, 128, 0, st>>>(map, LL);
   k_recut_all<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL);
   int launches = 2;
-  // subdivision rounds: a leaf of layer l splits in round >= l at the earliest, its children are judged by the
-  // block that created them; max_layer rounds cover the deepest chain
-  for (int round = 0; round < map.max_layer; round++, launches++)
-    k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, round, win_count, b, lv);
+  // every subdivision of this multi_recut, all levels, through the kernel's work queue (two blocks per SM: all
+  // 296 are resident; a block that finds the queue empty but work in flight polls)
+  if (map.max_layer > 0)
+  {
+    k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, win_count, b, lv);
+    launches++;
+  }
   return launches;
 }
 

@@ -84,16 +84,24 @@ __device__ __forceinline__ float4 deskew_point(const DeskewPoses& P, const float
   return make_float4(xyz[0], xyz[1], xyz[2], q.w);
 }
 
+// the pose table into shared memory: the header, the m poses in use (of VINA_MAX_POSES slots - a scan has 20 to 40),
+// the end pose and the extrinsic behind the array
+__device__ __forceinline__ void stage_poses(DeskewPoses& P, const DeskewPoses* __restrict__ Pg)
+{
+  const int m = Pg->m;
+  const int head = (int)(offsetof(DeskewPoses, pose) / 4) + m * (int)(sizeof(vina_imu_pose) / 4);
+  const int tail0 = (int)(offsetof(DeskewPoses, R_end) / 4), words = (int)(sizeof(DeskewPoses) / 4);
+  const int* src = reinterpret_cast<const int*>(Pg);
+  int* dst = reinterpret_cast<int*>(&P);
+  for (int i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
+  for (int i = tail0 + threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+
 __global__ void __launch_bounds__(256) k_deskew(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg,
                                                 int* __restrict__ status)
 {
   __shared__ DeskewPoses P;
-  {
-    const int words = sizeof(DeskewPoses) / 4;
-    const int* src = reinterpret_cast<const int*>(Pg);
-    int* dst = reinterpret_cast<int*>(&P);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-  }
+  stage_poses(P, Pg);
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -201,12 +209,7 @@ __global__ void __launch_bounds__(256)
                       ScanView out, VarInitParams prm, int* __restrict__ cache)
 {
   __shared__ DeskewPoses P;
-  {
-    const int words = sizeof(DeskewPoses) / 4;
-    const int* src = reinterpret_cast<const int*>(Pg);
-    int* dst = reinterpret_cast<int*>(&P);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-  }
+  stage_poses(P, Pg);
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -253,6 +253,7 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   S.stamp = 0;
   for (int l = 0; l < 4; l++) CU(dalloc(&ctx->layers.list[l], (size_t)cfg.max_nodes));
   CU(dalloc(&ctx->layers.split, (size_t)cfg.max_nodes));
+  CU(cudaMemset(ctx->layers.split, 0xFF, (size_t)cfg.max_nodes * sizeof(int)));  // k_split's queue: -1 = slot not written yet
   CU(dalloc(&ctx->layers.count, 16));
   ctx->layers.count_alt = ctx->layers.count + 8;
   CU(cudaStreamSynchronize(ctx->stream));
