@@ -354,6 +354,25 @@ int vo_odom_step(void* h, float* xyz4, int n, double pcl_beg_time, const double*
   from_cloud(c, xyz4);
   return r;
 }
+// the start-up phase (VINA_SLAM::initialization, node.cpp:293-366): switch a freshly created odometry to a cold start,
+// then feed scans until 1 comes back
+void vo_odom_cold_start(void* h)
+{
+  Odom* o = (Odom*)h;
+  o->odom_ekf.init_flag = false;
+  o->odom_ekf.init_num = 0;
+  o->odom_ekf.mean_acc.setZero();
+  o->odom_ekf.mean_gyr.setZero();
+  o->x_curr.setZero();
+  o->pl_tree.clear();
+}
+int vo_odom_init_scan(void* h, const float* xyz4, int n, double beg, const double* imu7, int m)
+{
+  Odom* o = (Odom*)h;
+  Cloud c = to_cloud(xyz4, n);
+  std::deque<ImuSample> imus = to_imus(imu7, m);
+  return o->init_scan(c, beg, imus);
+}
 void vo_odom_stage_times(void* h, double t[4])
 {
   Odom* o = (Odom*)h;

@@ -84,6 +84,10 @@ void vo_odom_bootstrap(void* h, const float* xyz4, int n, const vo_state* x_know
 /* full scan: xyz4 = (x,y,z,curvature) in/out (deskewed on return); imu7 = m x (t,gx,gy,gz,ax,ay,az) */
 int vo_odom_step(void* h, float* xyz4, int n, double pcl_beg_time, const double* imu7, int m, int iekf_on_full,
                  int max_iter);
+/* start-up phase (VINA_SLAM::initialization, node.cpp:293-366 + local_mapping.cpp:362-388): cold_start switches a
+ * freshly created odometry to it; init_scan: 0 = collecting, 1 = initialised (go on with vo_odom_step), -1 = failed */
+void vo_odom_cold_start(void* h);
+int vo_odom_init_scan(void* h, const float* xyz4, int n, double pcl_beg_time, const double* imu7, int m);
 void vo_odom_stage_times(void* h, double t[4]); /* odom(deskew+var+iekf+pvec_update), insert, recut, margi */
 int vo_odom_last_iters(void* h);
 int vo_odom_last_down(void* h, float* xyz4, int cap); /* the down-sampled cloud of the last step */

@@ -98,7 +98,7 @@ def load(fast: bool = False, ref: bool = False):
     lib.vo_odom_create.argtypes = [C.POINTER(VoConfig)]
     for fn in ("vo_odom_destroy", "vo_odom_set_state", "vo_odom_get_state", "vo_odom_set_imu_anchor",
                "vo_odom_bootstrap", "vo_odom_stage_times", "vo_odom_deskew", "vo_odom_set_dump",
-               "vo_odom_map_update", "vo_odom_set_ba", "vo_odom_ba_stats", "vo_odom_ba_probe"):
+               "vo_odom_map_update", "vo_odom_set_ba", "vo_odom_ba_stats", "vo_odom_ba_probe", "vo_odom_cold_start"):
         if hasattr(lib, fn):
             getattr(lib, fn).restype = None
     if hasattr(lib, "vo_sync_create"):
@@ -204,6 +204,18 @@ class Odom:
         r = self.lib.vo_odom_step(self.h, _fp(a), C.c_int(a.shape[0]), C.c_double(beg_time), _dp(im),
                                   C.c_int(im.shape[0]), C.c_int(1 if iekf_on_full else 0), C.c_int(max_iter))
         return r, a
+
+    def cold_start(self):
+        """Forget the bootstrap: the next scans go through init_scan (VINA_SLAM::initialization)."""
+        self.lib.vo_odom_cold_start(self.h)
+
+    def init_scan(self, xyz4: np.ndarray, beg_time: float, imu7: np.ndarray) -> int:
+        """One scan of the start-up phase (node.cpp:293-366 + local_mapping.cpp:362-388): 0 = collecting,
+        1 = initialised (go on with step), -1 = motion_init failed, system reset."""
+        a = np.ascontiguousarray(xyz4, dtype=np.float32)
+        im = np.ascontiguousarray(imu7, dtype=np.float64)
+        return self.lib.vo_odom_init_scan(self.h, _fp(a), C.c_int(a.shape[0]), C.c_double(beg_time), _dp(im),
+                                          C.c_int(im.shape[0]))
 
     def stage_times(self):
         t = np.zeros(4)

@@ -23,6 +23,7 @@
 #include "vina_slam/preintegration.hpp"
 #include "vina_slam/sensor/sync.hpp"
 #include "vina_slam/sensor/lidar_decoder.hpp"
+#include "vina_slam/pipeline/initialization.hpp"
 
 #include <chrono>
 #include <cstring>
@@ -189,6 +190,13 @@ struct RefOdom
       ba_factors = voxhess;
       ba_xs = vs.x_buf;
     }
+    window_tail();
+  }
+
+  // local_mapping.cpp:489-546: BA, margi, journey, window shift - once the window is full
+  void window_tail()
+  {
+    const int mgsize = 1;
     if (vs.win_count >= vs.win_size)
     {
       bool all_imu = (int)imu_pre_buf.size() == vs.win_count - 1;
@@ -237,6 +245,104 @@ struct RefOdom
       vs.win_base += mgsize;
       vs.win_count -= mgsize;
     }
+  }
+
+  // ---- VINA_SLAM::initialization (node.cpp:293-366), system_reset (node.cpp:368-408) and the loop's handling of
+  // the result (local_mapping.cpp:362-388, then :489-546 on success) - restated here because node.cpp needs the
+  // whole ROS node; everything they call is the reference's own code: IMUEKF::process / IMU_init, down_sampling_voxel,
+  // down_sampling_close, var_init, VINA_SLAM::lio_state_estimation_kdtree (odometry.cpp:267-439), pvec_update,
+  // IMU_PRE and Initialization::motion_init (initialization.cpp:158-367: re-deskew, cut_voxel, recut, tras_opt,
+  // LI_BA_OptimizerGravity::damping_iter, align_gravity).
+  vector<pcl::PointCloud<PointType>::Ptr> pl_origs;
+  vector<double> beg_times;
+  vector<deque<std::shared_ptr<sensor_msgs::msg::Imu>>> vec_imus;
+  Eigen::MatrixXd init_hess;
+  int motion_init_rounds = 0;
+
+  int initialization(deque<std::shared_ptr<sensor_msgs::msg::Imu>>& imus, pcl::PointCloud<PointType>::Ptr pcl_curr)
+  {
+    pcl::PointCloud<PointType>::Ptr orig(new pcl::PointCloud<PointType>(*pcl_curr));
+    if (vs.odom_ekf.process(vs.x_curr, *pcl_curr, imus) == 0) return 0;
+    if (vs.win_count == 0) imupre_scale_gravity = vs.odom_ekf.scale_gravity;
+    PVecPtr pptr(new PVec);
+    double downkd = vs.down_size >= 0.5 ? vs.down_size : 0.5;
+    down_sampling_voxel(*pcl_curr, downkd);
+    var_init(vs.extrin_para, *pcl_curr, pptr, dept_err, beam_err);
+    vs.lio_state_estimation_kdtree(pptr);
+    pwld.clear();
+    pvec_update(pptr, vs.x_curr, pwld);
+    vs.win_count++;
+    vs.x_buf.push_back(vs.x_curr);
+    vs.pvec_buf.push_back(pptr);
+    if (vs.win_count > 1)
+    {
+      imu_pre_buf.push_back(new IMU_PRE(vs.x_buf[vs.win_count - 2].bg, vs.x_buf[vs.win_count - 2].ba));
+      imu_pre_buf[vs.win_count - 2]->push_imu(imus);
+    }
+    pcl::PointCloud<PointType> pl_mid = *orig;
+    down_sampling_close(*orig, vs.down_size);
+    if (orig->size() < 1000)
+    {
+      *orig = pl_mid;
+      down_sampling_close(*orig, vs.down_size / 2);
+    }
+    sort(orig->begin(), orig->end(), [](PointType& x, PointType& y) { return x.curvature < y.curvature; });
+    pl_origs.push_back(orig);
+    beg_times.push_back(vs.odom_ekf.pcl_beg_time);
+    vec_imus.push_back(imus);
+    if (vs.win_count >= vs.win_size)
+    {
+      int ok = Initialization::instance(init_node).motion_init(pl_origs, vec_imus, beg_times, &init_hess, voxhess, vs.x_buf,
+                                                               vs.surf_map, vs.surf_map_slide, vs.pvec_buf, vs.win_size,
+                                                               vs.sws, vs.x_curr, imu_pre_buf, vs.extrin_para);
+      return ok == 0 ? -1 : 1;
+    }
+    return 0;
+  }
+  rclcpp::Node::SharedPtr init_node = std::make_shared<rclcpp::Node>();
+
+  void system_reset(deque<std::shared_ptr<sensor_msgs::msg::Imu>>& imus)
+  {
+    for (auto iter = vs.surf_map.begin(); iter != vs.surf_map.end(); iter++)
+    {
+      iter->second->tras_ptr(vs.octos_release);
+      iter->second->clear_slwd(vs.sws[0]);
+      delete iter->second;
+    }
+    for (OctoTree* ot : vs.octos_release) delete ot;  // (the idle path of the loop deletes these, local_mapping.cpp:552-571)
+    vs.octos_release.clear();
+    vs.surf_map.clear();
+    vs.surf_map_slide.clear();
+    vs.x_curr.setZero();
+    vs.x_curr.p = Eigen::Vector3d(0, 0, 30);
+    vs.odom_ekf.mean_acc.setZero();
+    vs.odom_ekf.init_num = 0;
+    vs.odom_ekf.IMU_init(imus);
+    vs.x_curr.g = -vs.odom_ekf.mean_acc * imupre_scale_gravity;
+    for (size_t i = 0; i < imu_pre_buf.size(); i++) delete imu_pre_buf[i];
+    vs.x_buf.clear();
+    vs.pvec_buf.clear();
+    imu_pre_buf.clear();
+    vs.pl_tree->clear();
+    for (int i = 0; i < vs.win_size; i++) mp[i] = i;
+    vs.win_base = 0;
+    vs.win_count = 0;
+  }
+
+  // one scan of the start-up phase: 0 = still collecting, 1 = initialised (the window is full and has been
+  // marginalised once: the next scan goes to step()), -1 = motion_init failed and the system was reset
+  int init_scan(pcl::PointCloud<PointType>::Ptr pcl_curr, double beg, deque<std::shared_ptr<sensor_msgs::msg::Imu>>& imus)
+  {
+    vs.odom_ekf.pcl_beg_time = beg;
+    vs.odom_ekf.pcl_end_time = beg + pcl_curr->back().curvature;  // sync.cpp:40
+    int init = initialization(imus, pcl_curr);
+    if (init == 1)
+    {
+      window_tail();
+      return 1;
+    }
+    if (init == -1) system_reset(imus);
+    return init;
   }
 
   // local_mapping.cpp:317-341, the `else if (release_flag)` branch of the idle path, with the 700 as a
@@ -456,6 +562,9 @@ void vo_log(const double R[9], double w[3])
 void* vo_odom_create(const vo_config* cfg)
 {
   if (g_inst) return nullptr;  // the reference's globals allow one instance per process
+  // the reference reports on std::cout (IMU init, motion_init); this library's copy of the stream has no business
+  // writing into the test output: a stream without a buffer ignores everything it is sent
+  std::cout.rdbuf(nullptr);
   RefOdom* o = new RefOdom(cfg->win_size);
   VINA_SLAM& vs = o->vs;
   voxel_size = cfg->voxel_size;
@@ -533,6 +642,28 @@ int vo_odom_step(void* h, float* xyz4, int n, double beg, const double* imu7, in
   int r = ((RefOdom*)h)->step(c, beg, imus, iekf_on_full != 0);
   from_cloud(c, xyz4);
   return r;
+}
+// one scan of the start-up phase (see RefOdom::init_scan); the context must have been switched to a cold start with
+// vo_odom_cold_start (the default set-up bootstraps at known states instead)
+void vo_odom_cold_start(void* h)
+{
+  RefOdom* o = (RefOdom*)h;
+  IMUEKF& e = o->vs.odom_ekf;
+  e.init_flag = false;
+  e.init_num = 0;
+  e.mean_acc.setZero();
+  e.mean_gyr.setZero();
+  o->vs.x_curr.setZero();  // (the state a freshly constructed node starts from)
+  if (!o->vs.pl_tree) o->vs.pl_tree.reset(new pcl::PointCloud<PointType>());
+  o->vs.pl_tree->clear();
+}
+int vo_odom_init_scan(void* h, const float* xyz4, int n, double beg, const double* imu7, int m)
+{
+  RefOdom* o = (RefOdom*)h;
+  pcl::PointCloud<PointType>::Ptr c(new pcl::PointCloud<PointType>(to_cloud(xyz4, n)));
+  deque<std::shared_ptr<sensor_msgs::msg::Imu>> imus;
+  for (int i = 0; i < m; i++) imus.push_back(to_imu(imu7 + 7 * (size_t)i));
+  return o->init_scan(c, beg, imus);
 }
 void vo_odom_stage_times(void* h, double t[4])
 {

@@ -254,6 +254,7 @@ public:
   // writable views
   using Base<Matrix, R, C>::block;
   using Base<Matrix, R, C>::col;
+  using Base<Matrix, R, C>::row;
   using Base<Matrix, R, C>::diagonal;
   template <int BR, int BC>
   Block<Matrix, BR, BC> block(int r0, int c0)
@@ -261,6 +262,7 @@ public:
     return Block<Matrix, BR, BC>(*this, r0, c0);
   }
   Block<Matrix, R, 1> col(int j) { return Block<Matrix, R, 1>(*this, 0, j); }
+  Block<Matrix, 1, C> row(int i) { return Block<Matrix, 1, C>(*this, i, 0); }  // writable: A.row(i) << x, y, z
   DiagRef<Matrix> diagonal() { return DiagRef<Matrix>(*this); }
   SegRef<Matrix> head(int n) { return SegRef<Matrix>(*this, 0, n); }
   SegRef<Matrix> tail(int n) { return SegRef<Matrix>(*this, R * C - n, n); }
@@ -1028,6 +1030,29 @@ public:
     Vector3d k(R(2, 1) - R(1, 2), R(0, 2) - R(2, 0), R(1, 0) - R(0, 1));
     double n = k.norm();
     ax = n > 0 ? Vector3d(k / n) : Vector3d(1, 0, 0);
+  }
+  // (angle, axis) and toRotationMatrix(): Eigen 3.4.0 Geometry/AngleAxis.h (used by Initialization::align_gravity)
+  AngleAxisd(double angle, const Vector3d& axis) : ax(axis), ang(angle) {}
+  Matrix3d toRotationMatrix() const
+  {
+    Matrix3d res;
+    const double s = std::sin(ang), c = std::cos(ang);
+    const Vector3d sin_axis(s * ax[0], s * ax[1], s * ax[2]);
+    const Vector3d cos1_axis((1.0 - c) * ax[0], (1.0 - c) * ax[1], (1.0 - c) * ax[2]);
+    double tmp;
+    tmp = cos1_axis[0] * ax[1];
+    res(0, 1) = tmp - sin_axis[2];
+    res(1, 0) = tmp + sin_axis[2];
+    tmp = cos1_axis[0] * ax[2];
+    res(0, 2) = tmp + sin_axis[1];
+    res(2, 0) = tmp - sin_axis[1];
+    tmp = cos1_axis[1] * ax[2];
+    res(1, 2) = tmp - sin_axis[0];
+    res(2, 1) = tmp + sin_axis[0];
+    res(0, 0) = cos1_axis[0] * ax[0] + c;
+    res(1, 1) = cos1_axis[1] * ax[1] + c;
+    res(2, 2) = cos1_axis[2] * ax[2] + c;
+    return res;
   }
   const Vector3d& axis() const { return ax; }
   double angle() const { return ang; }

@@ -446,7 +446,7 @@ static void tras_opt_mark(OctoTree* n, int& counter)
 }
 
 // src/mapping/octree.cpp:498-521 with the container (the BA probe): same traversal, same acceptance test
-static void tras_opt_collect(OctoTree* n, LidarFactor& vox_opt, std::vector<OctoTree*>* nodes = nullptr)
+void tras_opt_collect(OctoTree* n, LidarFactor& vox_opt, std::vector<OctoTree*>* nodes = nullptr)
 {
   if (n->octo_state == 0)
   {
@@ -1206,29 +1206,44 @@ void Odom::map_update(PVecPtr pptr, std::deque<ImuSample>* imus)
     ba_xs = x_buf;
   }
   t_margi = 0;
+  window_tail();
+}
 
+// src/pipeline/local_mapping.cpp:489-546
+void Odom::window_tail(LidarFactor* vh, std::vector<OctoTree*>* vh_nodes)
+{
+  const int mgsize = 1;
   if (win_count >= G.win_size)
   {
     bool all_imu = (int)imu_pre_buf.size() == win_count - 1;
     for (IMU_PRE* f : imu_pre_buf) all_imu = all_imu && f != nullptr;
-    if (if_BA && all_imu)
+    LidarFactor voxhess;
+    std::vector<OctoTree*> nodes;
+    if (vh == nullptr && if_BA && all_imu)
     {
-      // local_mapping.cpp:492-497: LI_BA_Optimizer on the factors tras_opt collected in multi_recut (none when
-      // multi_recut took its early-out, local_mapping.cpp:150-154)
-      LidarFactor voxhess;
+      // the factors tras_opt collected in multi_recut (none when multi_recut took its early-out,
+      // local_mapping.cpp:150-154)
       voxhess.win_size = G.win_size;
-      std::vector<OctoTree*> nodes;
       if ((int)surf_map_slide.size() >= G.thread_num)
         for (auto iter = surf_map_slide.begin(); iter != surf_map_slide.end(); iter++)
           tras_opt_collect(iter->second, voxhess, &nodes);
-      ba_last_iters = ba_damping_iter(x_buf, voxhess, imu_pre_buf, imu_coef, nullptr);
+      vh = &voxhess;
+      vh_nodes = &nodes;
+    }
+    if (if_BA && all_imu)
+    {
+      // local_mapping.cpp:492-497: LI_BA_Optimizer
+      ba_last_iters = ba_damping_iter(x_buf, *vh, imu_pre_buf, imu_coef, nullptr);
       ba_runs++;
+    }
+    if (vh != nullptr)
+    {
       // OctoTree::margi takes the factors' (possibly re-evaluated) pcr_add / eig back (octree.cpp:410-416)
-      for (size_t a = 0; a < nodes.size(); a++)
+      for (size_t a = 0; a < vh_nodes->size(); a++)
       {
-        nodes[a]->pcr_add = voxhess.pcr_adds[a];
-        nodes[a]->eig_value = voxhess.eig_values[a];
-        nodes[a]->eig_vector = voxhess.eig_vectors[a];
+        (*vh_nodes)[a]->pcr_add = vh->pcr_adds[a];
+        (*vh_nodes)[a]->eig_value = vh->eig_values[a];
+        (*vh_nodes)[a]->eig_vector = vh->eig_vectors[a];
       }
     }
     x_curr.R = x_buf[win_count - 1].R;

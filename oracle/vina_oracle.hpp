@@ -284,6 +284,7 @@ void calcBodyVar(Vec3& pb, const float range_inc, const float degree_inc, Mat3& 
 void var_init(IMUST& ext, Cloud& pl_cur, PVecPtr pptr, double dept_err, double beam_err);
 void pvec_update(PVecPtr pptr, IMUST& x_curr, std::vector<Vec3>& pwld);
 void down_sampling_voxel(Cloud& pl_feat, double voxel_size);
+void down_sampling_close(Cloud& pl_feat, double voxel_size);  // point_utils.hpp:47-113 (vina_oracle_init.cpp)
 
 // voxel key, src/mapping/voxel_map.cpp:56-65 / 246-253
 VOXEL_LOC voxel_key(const Vec3& pw, double voxel_size);
@@ -305,6 +306,13 @@ public:
   double scale_gravity = 1.0;
   std::vector<IMUST> imu_poses;
   int point_notime = 0;
+  // start-up (imu_ekf.cpp:147-201, ekf_imu.hpp:16-20); the harness bootstrap sets init_flag and skips it
+  bool init_flag = true;
+  int init_num = 0, min_init_num = 30;
+  Vec3 mean_acc = Vec3::Zero(), mean_gyr = Vec3::Zero();
+  void IMU_init(std::deque<ImuSample>& imus);
+  // 0 = still initialising, 1 = scan deskewed, -1 = "LiDAR time regress" (the reference exit(0)s)
+  int process(IMUST& x_curr, Cloud& pcl_in, std::deque<ImuSample>& imus);
   IMUEKF();
   // returns 0 on success, -1 for "LiDAR time regress" (the reference exit(0)s)
   int motion_blur(IMUST& xc, Cloud& pcl_in, std::deque<ImuSample>& imus);
@@ -366,11 +374,17 @@ struct IMU_PRE
   void push_imu(std::deque<ImuSample>& imu_buffer, const BaNoise& nz);
   void add_imu(Vec3& cur_gyr, Vec3& cur_acc, double dt, const BaNoise& nz);
   double give_evaluate(IMUST& st1, IMUST& st2, Mat<30, 30>& jtj, Mat<30, 1>& gg, bool jac_enable);
+  // imu_preintegration.cpp:165-237: with the gravity Jacobian (3 more columns)
+  double give_evaluate_g(IMUST& st1, IMUST& st2, Mat<33, 33>& jtj, Mat<33, 1>& gg, bool jac_enable);
   void update_state(const Vec15& dxi);
 };
 // LI_BA_Optimizer::damping_iter (src/mapping/optimizers.cpp:430-517); returns the number of LM iterations
 int ba_damping_iter(std::vector<IMUST>& x_stats, LidarFactor& voxhess, std::deque<IMU_PRE*>& imus_factor, double imu_coef,
                     std::vector<double>* hess_out);
+
+// LI_BA_OptimizerGravity::damping_iter (src/mapping/optimizers.cpp:746-826), vina_oracle_init.cpp
+void ba_damping_iter_gravity(std::vector<IMUST>& x_stats, LidarFactor& voxhess, std::deque<IMU_PRE*>& imus_factor,
+                             std::vector<double>& resis, int max_iter, double imu_coef);
 
 // The owner of everything VINA_SLAM keeps for the per-scan loop
 // (include/vina_slam/platform/ros2/node.hpp:30-96; src/pipeline/local_mapping.cpp:258-550)
@@ -414,6 +428,26 @@ public:
   double jour = 0;
   Vec3 last_pos = Vec3::Zero();
   bool release_flag = false;
+
+  // start-up phase (node.cpp:293-408, initialization.cpp, odometry.cpp:267-439; vina_oracle_init.cpp)
+  Cloud pl_tree, kd_cloud;
+  std::vector<std::shared_ptr<Cloud>> pl_origs;
+  std::vector<double> beg_times;
+  std::vector<std::deque<ImuSample>> vec_imus;
+  LidarFactor init_voxhess;
+  std::vector<OctoTree*> init_nodes;
+  int init_rounds = 0;
+  Vec3 init_eig = Vec3::Zero();
+  void lio_state_estimation_kdtree(PVecPtr pptr);
+  int motion_init();
+  void clear_map();
+  int initialization(std::deque<ImuSample>& imus, Cloud& pcl_curr);
+  void system_reset(std::deque<ImuSample>& imus);
+  // one scan of the start-up phase: 0 = collecting, 1 = initialised, -1 = failed (system reset)
+  int init_scan(Cloud& pcl_curr, double beg, std::deque<ImuSample>& imus);
+  // local_mapping.cpp:489-546 (BA, margi, journey, window shift); vh / nodes: the factor container margi takes its
+  // values from (motion_init's), nullptr = the one multi_recut of this scan marked
+  void window_tail(LidarFactor* vh = nullptr, std::vector<OctoTree*>* nodes = nullptr);
 
   explicit Odom(const Globals& g);
   ~Odom();

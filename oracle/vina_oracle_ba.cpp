@@ -15,8 +15,8 @@
 
 namespace vo
 {
-namespace
-{
+// (jr, jr_inv, angle_axis and ldlt_solve are shared with vina_oracle_init.cpp)
+
 // include/vina_slam/core/math.hpp:57-71
 Mat3 jr(Vec3 vec)
 {
@@ -112,7 +112,7 @@ std::vector<double> ldlt_solve(std::vector<double> L, int n, const std::vector<d
     if (perm[k] != k) std::swap(x[k], x[perm[k]]);
   return x;
 }
-}  // namespace
+
 
 // ---- imu_preintegration.cpp ---------------------------------------------------------------------------------
 IMU_PRE::IMU_PRE(const Vec3& bg1, const Vec3& ba1)

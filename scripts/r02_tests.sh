@@ -1,3 +1,2 @@
 set -x
-free -g | head -2; nproc
-timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu_b.log 2>&1; echo pytest rc=$?; tail -15 gpurun_out/r02_pytest_gpu_b.log
+timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu_l.log 2>&1; echo pytest rc=$?; tail -15 gpurun_out/r02_pytest_gpu_l.log

@@ -173,3 +173,74 @@ def test_sigma_gate_ten_million_evaluations(oracle_lib, gpu_lib):
     finally:
         od.close()
         gx.close()
+
+
+def test_raw_front_to_back_path_matches_oracle(oracle_lib, gpu_lib):
+    """The whole front of the loop, raw messages in: shuffled scans -> decoder keep rule + pcl_handler (filter, time
+    sort, 0.11 s cut; lidar_decoder.cpp:8-43) -> sync_packages (sync.cpp:18-96) -> the per-scan step, through
+    replay.replay_stream (vina_scan_prepare + vina_sync + vina_odom_step_prepared) against the ORACLE's restatements
+    of the same three stages driven by the same message streams: same packages (scan, pcl_beg / pcl_end, IMU
+    samples), prepared scans bit for bit, trajectory within 1 mm / 0.01 deg."""
+    from vina_slam_b200 import replay
+
+    cfg = synth.small_sensor("robosense128", 64, 900)  # 57 600 points per scan
+    pfn = 2  # point_filter_num: every second point, like the reference's yaml files use
+    boots, scans = replay.synthetic_frames(cfg, 9)
+    caps = dict(max_scan_points=cfg.n_points + 1024, max_nodes=300000, hash_capacity_log2=19)
+    rows, _, worst = replay.replay_stream(cfg, boots, scans, caps=caps, point_filter_num=pfn, shuffle_seed=3, prune_horizon=0)
+    assert rows.shape[0] == len(scans) - 1 and worst < 0.02  # (the last scan's package stays open)
+
+    # the oracle side: its own pcl_handler on the same shuffled raw scans, its own sync_packages on the same streams
+    od = oracle_lib.Odom(cfg)
+    for f in boots:
+        od.bootstrap(f.xyzt, oracle_lib.make_state(f.gt_R, f.gt_p, f.gt_v, t=f.end_time))
+    od.set_imu_anchor(boots[-1].end_time, boots[-1].imu[-1])
+    rng = np.random.default_rng(3)
+    raws = [f.xyzt[rng.permutation(f.xyzt.shape[0])] for f in scans]
+    blind2 = float(cfg.blind) ** 2
+    prepared = [oracle_lib.scan_prepare(r, pfn, blind2) for r in raws]
+    assert all(p is not None and p.shape[0] > 0.45 * cfg.n_points for p in prepared)
+    sync = oracle_lib.Sync(0)
+    msgs = []
+    for k, f in enumerate(scans):
+        for row in f.imu:
+            msgs.append((float(row[0]), 0, k, row))
+        msgs.append((f.end_time, 1, k, None))
+    msgs.sort(key=lambda m: (m[0], m[1]))
+    got = []
+    try:
+        for _, kind, k, row in msgs:
+            if kind == 0:
+                sync.push_imu(row)
+            else:
+                sync.push_scan(scans[k].beg_time, float(prepared[k][-1, 3]), k)
+            while True:
+                r, tag, beg, end, imu = sync.next()
+                assert r >= 0
+                if r == 0:
+                    break
+                if r == 1:
+                    rr, _ = od.step(prepared[tag], beg, imu, iekf_on_full=True, max_iter=4)
+                    assert rr == 0
+                    s = oracle_lib.state_arrays(od.get_state())
+                    got.append((tag, s["t"], s["p"].copy(), s["R"].copy()))
+    finally:
+        sync.close()
+        od.close()
+    assert [g[0] for g in got] == list(range(len(scans) - 1))
+    for (tag, t, p, R), row in zip(got, rows):
+        assert abs(row[0] - t) < 1e-9
+        assert np.linalg.norm(row[1:4] - p) < 1e-3, (tag, np.linalg.norm(row[1:4] - p))
+        q = replay.quat_xyzw(R)
+        ang = 2 * np.degrees(np.arccos(min(1.0, abs(float(np.dot(q, row[4:8]))))))
+        assert ang < 0.01, (tag, ang)
+
+    # and the prepared scans themselves, bit for bit (order of equal stamps included)
+    gx = gpu_lib.Ctx(cfg, **caps)
+    try:
+        for k in (0, 4):
+            n, t_last = gx.scan_prepare(raws[k], pfn, blind2)
+            dev = gx.scan_download(n)
+            assert n == prepared[k].shape[0] and np.array_equal(dev, prepared[k]) and t_last == prepared[k][-1, 3]
+    finally:
+        gx.close()

@@ -321,3 +321,34 @@ def test_front_end_and_pruning_golden_vectors(oracle_lib):
     o = mod.scenario(False)
     assert g["prune_rows"][:, 2].sum() > 300 and (g["prune_rows"][:, 2] > 0).sum() >= 2
     _assert_same(o, g, "restatements vs reference golden (front end, pruning)")
+
+
+def _init_scenario():
+    spec = importlib.util.spec_from_file_location("make_ref_init_golden", os.path.join(HERE, "golden", "make_ref_init_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["make_ref_init_golden"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_cold_start_restatement_reproduces_reference_golden_vectors(oracle_lib):
+    """The start-up phase: IMU init, nine scans of the kd-tree IEKF (odometry.cpp:267-439),
+    Initialization::motion_init (re-deskew, cut_voxel, recut, tras_opt, LI_BA_OptimizerGravity, align_gravity;
+    initialization.cpp:158-367), the window tail and three ordinary steps - the oracle's restatement against vectors
+    produced by the reference's own files (tests/golden/ref_init.npz): every state and covariance after every scan and
+    the final map, bit for bit."""
+    g = dict(np.load(os.path.join(HERE, "golden", "ref_init.npz")))
+    mod = _init_scenario()
+    o = mod.run(lambda cfg: oracle_lib.Odom(cfg))
+    codes = g["rows"][:, 0]
+    assert codes.max() == 1 and (codes == 0).sum() >= 11 and g["map_key"].shape[0] > 1500
+    _assert_same(o, g, "oracle cold start vs reference golden")
+
+
+def test_cold_start_side_by_side(oracle_lib):
+    if not oracle_lib.have_ref():
+        pytest.skip("oracle/_ref is not built here (needs /root/reference)")
+    mod = _init_scenario()
+    o = mod.run(lambda cfg: oracle_lib.Odom(cfg), n_steps=2)
+    r = mod.run(lambda cfg: oracle_lib.Odom(cfg, ref=True), n_steps=2)
+    _assert_same(o, r, "oracle cold start vs the reference build")
