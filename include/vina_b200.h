@@ -313,9 +313,21 @@ int vina_odom_iekf_sharded_p2p(vina_ctx* ctx, int first, int count, int max_iter
 int vina_odom_set_state(vina_ctx* ctx, const vina_state* s);
 int vina_odom_get_state(vina_ctx* ctx, vina_state* s);
 int vina_odom_set_imu_anchor(vina_ctx* ctx, double last_pcl_end_time, const vina_imu* last_imu, double scale_gravity);
-/* harness bootstrap (replaces initialization()): an already
+/* harness bootstrap (instead of the start-up phase below, when the first states are known): an already
  * deskewed scan at a known state -> downsample, var_init, map update */
 int vina_odom_bootstrap(vina_ctx* ctx, const float* xyzt, int n, const vina_state* x_known);
+/* ---- the start-up phase: VINA_SLAM::initialization (src/platform/ros2/node.cpp:293-366) as the loop calls it
+ * (src/pipeline/local_mapping.cpp:362-388) - IMU initialisation (IMUEKF::IMU_init, imu_ekf.cpp:147-172), then for
+ * win_size scans the kd-tree IEKF against a local map (lio_state_estimation_kdtree, odometry.cpp:267-439), then
+ * Initialization::motion_init (initialization.cpp:158-367: map rebuilt from the re-deskewed frames, recut, gravity
+ * BA LI_BA_OptimizerGravity, optimizers.cpp:746-826; gravity alignment), the window's first marginalisation.
+ * vina_odom_cold_start puts a context into that phase (empty map, zero state); every scan then goes to
+ * vina_odom_init_scan (raw scan: n x (x, y, z, time offset), time-sorted; its IMU batch as sync_packages hands it
+ * over) until *status == 1: 0 = still collecting, 1 = initialised - the next scan goes to vina_odom_step -,
+ * -1 = motion_init failed and the system was reset (node.cpp:368-408): keep feeding scans. x_out: x_curr. */
+int vina_odom_cold_start(vina_ctx* ctx);
+int vina_odom_init_scan(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time, const vina_imu* imus, int m,
+                        vina_state* x_out, int32_t* status);
 /* one scan from HOST buffers. iekf_on_full: IEKF on the un-downsampled scan
  * (production, local_mapping.cpp:413) or the down-sampled one (:412).
  * max_iter <= 0: the reference's 20 (plain variant); 4 = the VNC_lio budget. */

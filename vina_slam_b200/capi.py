@@ -58,6 +58,7 @@ NODE_DTYPE = np.dtype([
 
 # every symbol include/vina_b200.h declares
 EXPORTS = [
+    "vina_odom_cold_start", "vina_odom_init_scan",
     "vina_config_default", "vina_ctx_create", "vina_ctx_destroy", "vina_last_error", "vina_ctx_set_stream",
     "vina_ctx_sync", "vina_scan_upload", "vina_scan_upload_device", "vina_down_count", "vina_deskew", "vina_scan_download", "vina_downsample", "vina_down_upload",
     "vina_down_download", "vina_var_init", "vina_pvec_upload", "vina_pvec_download", "vina_iekf_begin",
@@ -516,6 +517,20 @@ class Ctx:
         a = np.ascontiguousarray(xyzt, dtype=np.float32)
         self._ck(self.lib.vina_odom_bootstrap(self.h, _fp(a), C.c_int(a.shape[0]), C.byref(state)))
         self.sync()
+
+    def cold_start(self):
+        """Start-up phase of the reference (VINA_SLAM::initialization): empty map, zero state, IMU not initialised."""
+        self._ck(self.lib.vina_odom_cold_start(self.h))
+
+    def init_scan(self, xyzt: np.ndarray, beg_time: float, imu7: np.ndarray):
+        """One scan of the start-up phase -> (status, state): 0 = collecting, 1 = initialised (go on with step),
+        -1 = motion_init failed, the system was reset."""
+        a = np.ascontiguousarray(xyzt, dtype=np.float32)
+        im = imu_array(np.asarray(imu7, dtype=np.float64))
+        out, st = VinaState(), C.c_int32(0)
+        self._ck(self.lib.vina_odom_init_scan(self.h, _fp(a), C.c_int(a.shape[0]), C.c_double(beg_time),
+                                              im.ctypes.data_as(C.c_void_p), C.c_int(im.shape[0]), C.byref(out), C.byref(st)))
+        return st.value, out
 
     def step(self, xyzt: np.ndarray, beg_time: float, imu7: np.ndarray, iekf_on_full: bool = True, max_iter: int = 4):
         a = np.ascontiguousarray(xyzt, dtype=np.float32)

@@ -4,6 +4,11 @@
 // results can be compared bit-for-bit with the strict CPU restatement.
 #include "vn_kernels.cuh"
 
+struct Cov2x
+{
+  double rot[9], tsl[9];
+};
+
 // ---------------------------------------------------------------------------
 // a2 deskew: src/estimation/imu_ekf.cpp:114-144. The reference walks the
 // time-sorted scan backwards together with the IMU pose table; for sorted
@@ -112,13 +117,13 @@ __global__ void __launch_bounds__(256) k_deskew(float4* __restrict__ pts, int n,
 
 // ---------------------------------------------------------------------------
 // a3 var_init: src/core/point_utils.cpp:3-52 (calcBodyVar + extrinsic).
-__device__ __forceinline__ void var_init_point(const float4 q, const int i, const ScanView& out, const VarInitParams& prm)
+// calcBodyVar (point_utils.cpp:3-34): pb may be mutated (z == 0 -> 1e-4), var = 3x3 column-major
+__device__ __forceinline__ void calc_body_var(double* pb, float range_var, double dir_var, double* var)
 {
-  double pb[3] = { (double)q.x, (double)q.y, (double)q.z };
   if (pb[2] == 0) pb[2] = 0.0001;
   float range = (float)sqrt(pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2]);
-  double rv = (double)prm.range_var;
-  double dv = prm.dir_var;
+  double rv = (double)range_var;
+  double dv = dir_var;
   double d[3] = { pb[0], pb[1], pb[2] };
   {
     double z = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
@@ -170,9 +175,15 @@ __device__ __forceinline__ void var_init_point(const float4 q, const int i, cons
     AD[r] = A[r] * dv + A[r + 3] * 0.0;
     AD[r + 3] = A[r] * 0.0 + A[r + 3] * dv;
   }
-  double var[9];
   for (int c = 0; c < 3; c++)
     for (int r = 0; r < 3; r++) var[r + 3 * c] = (d[r] * rv) * d[c] + (AD[r] * A[c] + AD[r + 3] * A[c + 3]);
+}
+
+__device__ __forceinline__ void var_init_point(const float4 q, const int i, const ScanView& out, const VarInitParams& prm)
+{
+  double pb[3] = { (double)q.x, (double)q.y, (double)q.z };
+  double var[9];
+  calc_body_var(pb, prm.range_var, prm.dir_var, var);
   // extrinsic: pnt = R_L pnt + t_L ; var = R_L var R_L^T
   double pn[3];
   for (int r = 0; r < 3; r++)
@@ -370,6 +381,321 @@ __global__ void k_down_init(DownSlot* tab, unsigned int nslots)
 
 // ---------------------------------------------------------------------------
 // launchers
+// ---------------------------------------------------------------------------
+// Start-up phase: the kernels behind vina_odom_init_scan.
+//
+// k_init_assoc: one iteration of VINA_SLAM::lio_state_estimation_kdtree (src/pipeline/odometry.cpp:332-392) for every
+// point of the down-sampled scan: world point; when `refind`, the NMATCH = 5 nearest points of the local map
+// (pcl::KdTreeFLANN::nearestKSearch - an exact search, here by brute force over the map tiled through shared
+// memory: the map is a 0.5 m grid of a few 10^4 points and this runs for the first win_size scans only), the
+// plane n.x + 1 = 0 through them by least squares (A.colPivHouseholderQr().solve(b), 5 x 3; normal equations here)
+// and the acceptance test |n.a_k + 1| <= 0.1; then the point-to-plane terms HTH += j j^T, HTz -= j d, summed per
+// block in a fixed order (28 partials per block, added up by k_init_sum).
+#define INIT_NMATCH 5
+#define INIT_THREADS 128
+#define INIT_TILE 1024
+#define INIT_NSUM 28  // 21 (HTH upper) + 6 (HTz) + 1 (valid)
+
+__device__ __forceinline__ bool solve3_lu(const double* A, const double* b, double* x)
+{
+  // x = A^-1 b for a 3x3 (column-major) by LU with partial pivoting (Eigen's inverse() route for the 3 x 3 normal
+  // equations is a closed form; the fit is toleranced)
+  double m[3][4];
+  for (int i = 0; i < 3; i++)
+  {
+    for (int j = 0; j < 3; j++) m[i][j] = A[i + 3 * j];
+    m[i][3] = b[i];
+  }
+  for (int k = 0; k < 3; k++)
+  {
+    int piv = k;
+    double best = fabs(m[k][k]);
+    for (int i = k + 1; i < 3; i++)
+      if (fabs(m[i][k]) > best)
+      {
+        best = fabs(m[i][k]);
+        piv = i;
+      }
+    if (best == 0.0) return false;
+    if (piv != k)
+      for (int j = 0; j < 4; j++)
+      {
+        const double t = m[k][j];
+        m[k][j] = m[piv][j];
+        m[piv][j] = t;
+      }
+    for (int i = k + 1; i < 3; i++)
+    {
+      const double f = m[i][k] / m[k][k];
+      for (int j = k; j < 4; j++) m[i][j] = m[i][j] - f * m[k][j];
+    }
+  }
+  for (int i = 2; i >= 0; i--)
+  {
+    double sacc = m[i][3];
+    for (int j = i + 1; j < 3; j++) sacc = sacc - m[i][j] * x[j];
+    x[i] = sacc / m[i][i];
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(INIT_THREADS)
+    k_init_assoc(ScanView pv, int n, PoseD x, const float4* __restrict__ tree, int n_tree, int refind,
+                 double* __restrict__ ds, double* __restrict__ dir, double* __restrict__ partial)
+{
+  __shared__ float4 tile[INIT_TILE];
+  __shared__ double red[INIT_THREADS / 32][INIT_NSUM];
+  const int i = blockIdx.x * INIT_THREADS + threadIdx.x;
+  const bool live = i < n;
+  double pnt[3] = { 0, 0, 0 }, wld[3] = { 0, 0, 0 };
+  if (live)
+  {
+    for (int k = 0; k < 3; k++) pnt[k] = pv.p[k][i];
+    rot_trans(x.R, x.p, pnt, wld);
+  }
+  double d_i = -1.0, n_i[3] = { 0, 0, 0 };
+  if (refind)
+  {
+    const float qx = (float)wld[0], qy = (float)wld[1], qz = (float)wld[2];
+    float bd[INIT_NMATCH];
+    int bi[INIT_NMATCH];
+#pragma unroll
+    for (int k = 0; k < INIT_NMATCH; k++) bd[k] = 3.0e38f, bi[k] = -1;
+    for (int base = 0; base < n_tree; base += INIT_TILE)
+    {
+      __syncthreads();
+      for (int t = threadIdx.x; t < INIT_TILE; t += INIT_THREADS)
+        if (base + t < n_tree) tile[t] = tree[base + t];
+      __syncthreads();
+      const int m = min(INIT_TILE, n_tree - base);
+      if (live)
+        for (int t = 0; t < m; t++)
+        {
+          const float4 p = tile[t];
+          const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+          const float d2 = (dx * dx + dy * dy) + dz * dz;
+          if (d2 < bd[INIT_NMATCH - 1])
+          {
+            // sorted insertion; candidates arrive in ascending index, so equal distances keep the smaller index first
+            float cd = d2;
+            int ci = base + t;
+#pragma unroll
+            for (int k = 0; k < INIT_NMATCH; k++)
+              if (cd < bd[k])
+              {
+                const float td = bd[k];
+                const int ti = bi[k];
+                bd[k] = cd;
+                bi[k] = ci;
+                cd = td;
+                ci = ti;
+              }
+          }
+        }
+    }
+    if (live && bi[INIT_NMATCH - 1] >= 0)
+    {
+      double A[INIT_NMATCH][3];
+#pragma unroll
+      for (int k = 0; k < INIT_NMATCH; k++)
+      {
+        const float4 p = tree[bi[k]];
+        A[k][0] = (double)p.x;
+        A[k][1] = (double)p.y;
+        A[k][2] = (double)p.z;
+      }
+      double AtA[9], Atb[3];
+      for (int c = 0; c < 3; c++)
+      {
+        for (int r = 0; r < 3; r++)
+        {
+          double sacc = A[0][r] * A[0][c];
+          for (int k = 1; k < INIT_NMATCH; k++) sacc = sacc + A[k][r] * A[k][c];
+          AtA[r + 3 * c] = sacc;
+        }
+        double sb = A[0][c] * -1.0;
+        for (int k = 1; k < INIT_NMATCH; k++) sb = sb + A[k][c] * -1.0;
+        Atb[c] = sb;
+      }
+      double direct[3];
+      bool ok = solve3_lu(AtA, Atb, direct);
+      if (ok)
+        for (int k = 0; k < INIT_NMATCH; k++)
+        {
+          const double v = (direct[0] * A[k][0] + direct[1] * A[k][1]) + direct[2] * A[k][2];
+          if (!(fabs(v + 1.0) <= 0.1)) ok = false;
+        }
+      if (ok)
+      {
+        const double nn = sqrt((direct[0] * direct[0] + direct[1] * direct[1]) + direct[2] * direct[2]);
+        d_i = 1.0 / nn;
+        for (int k = 0; k < 3; k++) n_i[k] = direct[k] * d_i;
+      }
+    }
+    if (live)
+    {
+      ds[i] = d_i;
+      for (int k = 0; k < 3; k++) dir[3 * (size_t)i + k] = n_i[k];
+    }
+  }
+  else if (live)
+  {
+    d_i = ds[i];
+    for (int k = 0; k < 3; k++) n_i[k] = dir[3 * (size_t)i + k];
+  }
+  // point-to-plane terms (odometry.cpp:378-391): jac = [hat(pnt) R^T n ; n], HTH += jac jac^T, HTz += jac * (-pd2)
+  double acc[INIT_NSUM];
+#pragma unroll
+  for (int k = 0; k < INIT_NSUM; k++) acc[k] = 0.0;
+  if (live && d_i >= 0)
+  {
+    const double pd2 = ((n_i[0] * wld[0] + n_i[1] * wld[1]) + n_i[2] * wld[2]) + d_i;
+    double m[3];
+    rotT_vec(x.R, n_i, m);
+    const double j[6] = { pnt[1] * m[2] - pnt[2] * m[1], pnt[2] * m[0] - pnt[0] * m[2], pnt[0] * m[1] - pnt[1] * m[0],
+                          n_i[0], n_i[1], n_i[2] };
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = a; b < 6; b++) acc[t++] = j[a] * j[b];
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc[21 + a] = j[a] * (-pd2);
+    acc[27] = 1.0;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < INIT_NSUM; k++)
+  {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < INIT_NSUM)
+  {
+    double v = 0.0;
+    for (int w = 0; w < INIT_THREADS / 32; w++) v += red[w][threadIdx.x];
+    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+  }
+}
+
+// the blocks' partials in block order -> out[28] (mapped host memory)
+__global__ void __launch_bounds__(32 * INIT_NSUM) k_init_sum(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
+{
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double v = 0.0;
+  for (int b = lane; b < nblocks; b += 32) v += partial[(size_t)k * nblocks + b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) out[k] = v;
+}
+
+// pl_tree->push_back(R pnt + p) for the whole scan (odometry.cpp:276-284, 429-436)
+__global__ void __launch_bounds__(256) k_init_tree_append(ScanView pv, int n, PoseD x, float4* __restrict__ tree_tail)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double pnt[3] = { pv.p[0][i], pv.p[1][i], pv.p[2][i] };
+  double w[3];
+  rot_trans(x.R, x.p, pnt, w);
+  tree_tail[i] = make_float4((float)w[0], (float)w[1], (float)w[2], 0.0f);
+}
+
+// Initialization::motion_blur (src/pipeline/initialization.cpp:64-156) + what motion_init does with every point
+// right after (:222-241): the frame's retained raw points (time-sorted), compensated with the pose table of a
+// BACKWARD integration from the frame's end state into the end IMU frame; then either the body covariance
+// (calcBodyVar on that point, the z == 0 mutation included) and pvec_update with the frame's state, or - before
+// the first convergence - the identity covariance and the plain world point. Output in the reference's order:
+// the scan is walked from its last point to its first (index n - 1 - i), the points at or before the earliest pose
+// are skipped, and point 0 is pushed once more for every further pose once the walk has reached begin()
+// (:150-153: the inner loop breaks there, the outer loop goes on). The poses are ordered as the reference builds
+// them: latest first.
+__global__ void __launch_bounds__(256)
+    k_init_redeskew(const float4* __restrict__ orig, int n, int n_skip, const DeskewPoses* __restrict__ Pg, PoseD x,
+                    Cov2x cv, int converged, VarInitParams prm, ScanView out, InsertScratch sc)
+{
+  __shared__ DeskewPoses P;
+  stage_poses(P, Pg);
+  __syncthreads();
+  const int i = n_skip + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = orig[i];
+  const double cvt = (double)q.w;
+  // first pose (latest first) with t < curvature
+  int lo = 0, hi = P.m;
+  while (lo < hi)
+  {
+    const int mid = (lo + hi) >> 1;
+    if (P.pose[mid].t < cvt)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  const int k0 = lo;
+  const int reps = (i == 0) ? (P.m - k0) : 1;  // point 0 again for every later pose (all of them are earlier in time)
+  for (int rep = 0; rep < reps; rep++)
+  {
+    const vina_imu_pose& h = P.pose[k0 + rep];
+    const double dt = cvt - h.t;
+    double E[9], Ri[9];
+    exp_so3_dt(h.w, dt, E);
+    for (int c = 0; c < 3; c++)
+      for (int r = 0; r < 3; r++) Ri[r + 3 * c] = h.R[r] * E[3 * c] + h.R[r + 3] * E[3 * c + 1] + h.R[r + 6] * E[3 * c + 2];
+    double T[3];
+    for (int r = 0; r < 3; r++) T[r] = ((h.p[r] + h.v[r] * dt) + ((0.5 * h.a[r]) * dt) * dt) - P.p_end[r];
+    const double Pi[3] = { (double)q.x, (double)q.y, (double)q.z };
+    double a[3], b[3], pnt[3];
+    for (int r = 0; r < 3; r++) a[r] = ((P.ext_R[r] * Pi[0] + P.ext_R[r + 3] * Pi[1]) + P.ext_R[r + 6] * Pi[2]) + P.ext_t[r];
+    for (int r = 0; r < 3; r++) b[r] = ((Ri[r] * a[0] + Ri[r + 3] * a[1]) + Ri[r + 6] * a[2]) + T[r];
+    for (int r = 0; r < 3; r++) pnt[r] = (P.R_end[3 * r] * b[0] + P.R_end[3 * r + 1] * b[1]) + P.R_end[3 * r + 2] * b[2];
+    double v6[6] = { 1.0, 0.0, 0.0, 1.0, 0.0, 1.0 };
+    double pw[3];
+    if (converged)
+    {
+      double var[9], b6[6];
+      calc_body_var(pnt, prm.range_var, prm.dir_var, var);
+      b6[0] = var[0], b6[1] = var[3], b6[2] = var[6], b6[3] = var[4], b6[4] = var[7], b6[5] = var[8];
+      world_var(x.R, pnt, b6, cv.rot, cv.tsl, v6);
+    }
+    rot_trans(x.R, x.p, pnt, pw);
+    const int j = rep == 0 ? (n - 1 - i) : (n - n_skip) + (rep - 1);
+    for (int r = 0; r < 3; r++)
+    {
+      out.p[r][j] = pnt[r];
+      sc.pw[r][j] = pw[r];
+    }
+    for (int r = 0; r < 6; r++) sc.vw[r][j] = v6[r];
+  }
+}
+
+int launch_init_assoc(cudaStream_t st, const ScanView& pv, int n, const PoseD& x, const float4* tree, int n_tree, int refind,
+                      double* ds, double* dir, double* partial, double* out28)
+{
+  if (n <= 0) return 0;
+  const int nb = (n + INIT_THREADS - 1) / INIT_THREADS;
+  k_init_assoc<<<nb, INIT_THREADS, 0, st>>>(pv, n, x, tree, n_tree, refind, ds, dir, partial);
+  k_init_sum<<<1, 32 * INIT_NSUM, 0, st>>>(partial, nb, out28);
+  return 2;
+}
+int launch_init_tree_append(cudaStream_t st, const ScanView& pv, int n, const PoseD& x, float4* tree_tail)
+{
+  if (n <= 0) return 0;
+  k_init_tree_append<<<(n + 255) / 256, 256, 0, st>>>(pv, n, x, tree_tail);
+  return 1;
+}
+int launch_init_redeskew(cudaStream_t st, const float4* orig, int n, int n_skip, const DeskewPoses* d_poses, const PoseD& x,
+                         const double* rot_var, const double* tsl_var, int converged, const VarInitParams& prm,
+                         const ScanView& out, const InsertScratch& sc)
+{
+  if (n - n_skip <= 0) return 0;
+  Cov2x cv;
+  for (int k = 0; k < 9; k++) cv.rot[k] = rot_var[k], cv.tsl[k] = tsl_var[k];
+  k_init_redeskew<<<(n - n_skip + 255) / 256, 256, 0, st>>>(orig, n, n_skip, d_poses, x, cv, converged, prm, out, sc);
+  return 1;
+}
+
 void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status)
 {
   if (n <= 0) return;

@@ -382,6 +382,11 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(S.touched);
   cudaFree(S.counters < S.counters_alt ? S.counters : S.counters_alt);
   cudaFree(S.idx);
+  for (int k = 0; k < 2; k++) cudaFree(ctx->d_tree[k]);
+  cudaFree(ctx->d_init_ds);
+  cudaFree(ctx->d_init_dir);
+  cudaFree(ctx->d_init_part);
+  if (ctx->h_init_sums) cudaFreeHost(ctx->h_init_sums);
   for (int l = 0; l < 4; l++) cudaFree(ctx->layers.list[l]);
   cudaFree(ctx->layers.split);
   cudaFree(ctx->layers.count < ctx->layers.count_alt ? ctx->layers.count : ctx->layers.count_alt);
@@ -948,6 +953,148 @@ extern "C" int vina_iekf_accumulate_debug(vina_ctx* ctx, const double R[9], cons
 }
 
 // ---------------------------------------------------------------------------
+// start-up phase (host/vina_pipeline.cpp: vina_odom_init_scan)
+int vn_init_ensure(vina_ctx* ctx)
+{
+  if (ctx->d_tree[0]) return VINA_OK;
+  const size_t cap = ctx->cap_points;
+  for (int k = 0; k < 2; k++) CU(dalloc(&ctx->d_tree[k], 2 * cap, false));
+  CU(dalloc(&ctx->d_init_ds, cap));
+  CU(dalloc(&ctx->d_init_dir, 3 * cap));
+  CU(dalloc(&ctx->d_init_part, (cap / 128 + 2) * 28));
+  CU(cudaHostAlloc((void**)&ctx->h_init_sums, 32 * sizeof(double), cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_init_sums, ctx->h_init_sums, 0));
+  return VINA_OK;
+}
+
+int vn_map_clear(vina_ctx* ctx)
+{
+  MapView& M = ctx->map;
+  CU(cudaStreamSynchronize(ctx->stream));
+  int nn = 0;
+  CU(cudaMemcpy(&nn, M.node_count, 4, cudaMemcpyDeviceToHost));
+  if (nn > M.max_nodes) nn = M.max_nodes;
+  // used records back to zero (= never-used pool memory, which the allocators rely on), table emptied, cursors reset
+  if (nn > 0)
+  {
+    CU(cudaMemsetAsync(M.hot, 0, (size_t)nn * sizeof(NodeHot), ctx->stream));
+    CU(cudaMemsetAsync(M.cold, 0, (size_t)nn * sizeof(NodeCold), ctx->stream));
+  }
+  launch_map_init(ctx->stream, M, ctx->hash_slots);
+  CU(cudaMemsetAsync(M.node_count, 0, 4, ctx->stream));
+  CU(cudaMemsetAsync(M.root_count, 0, 4, ctx->stream));
+  CU(cudaMemsetAsync(M.win_cursor, 0, VINA_MAX_WIN * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(M.fix_cursor, 0, 4, ctx->stream));
+  CU(cudaMemsetAsync(M.fixseg_cursor, 0, 4, ctx->stream));
+  CU(cudaMemsetAsync(M.free_count, 0, 4, ctx->stream));
+  CU(cudaMemsetAsync(M.free_seg_count, 0, 4, ctx->stream));
+  CU(cudaMemsetAsync(M.slide_count, 0, 2 * sizeof(int), ctx->stream));
+  M.slide_cur = 0;
+  for (int i = 0; i < VINA_MAX_WIN; i++) M.mp[i] = i;
+  ctx->ba_n = -1;
+  return VINA_OK;
+}
+
+int vn_downsample_cloud(vina_ctx* ctx, const float4* in, int n, double size, float4* out, int* n_out)
+{
+  *n_out = 0;
+  if (n <= 0) return VINA_OK;
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "cloud of %d points > max_scan_points %d", n, ctx->cap_points);
+  int k = launch_downsample(ctx->stream, in, n, size, ctx->d_dtab, ctx->dmask, ctx->d_slot_of, ctx->d_flag, ctx->d_scanbuf,
+                            ctx->d_block_sums, ctx->d_n_down, out, ctx->d_status);
+  if (k < 0) return vn_fail(ctx, VINA_E_CAPACITY, "cloud too large for the down-sampling scan kernels");
+  ctx->launches += k;
+  CU(cudaMemcpyAsync(ctx->h_n_down, ctx->d_n_down, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *n_out = *ctx->h_n_down;
+  return vn_check_status(ctx);
+}
+
+// one iteration of the kd-tree IEKF's point loop on the down-sampled pointVar set (pv[1]) against the local map
+int vn_init_assoc(vina_ctx* ctx, const double R[9], const double p[3], int refind, double sums28[28])
+{
+  PoseD x;
+  memcpy(x.R, R, 72);
+  memcpy(x.p, p, 24);
+  const int n = ctx->n_pv[1];
+  for (int k = 0; k < 28; k++) ctx->h_init_sums[k] = 0.0;
+  ctx->launches += launch_init_assoc(ctx->stream, ctx->pv[1], n, x, ctx->d_tree[ctx->tree_cur], ctx->n_tree, refind,
+                                     ctx->d_init_ds, ctx->d_init_dir, ctx->d_init_part, ctx->d_init_sums);
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(sums28, ctx->h_init_sums, 28 * sizeof(double));
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_init_assoc");
+}
+
+// pl_tree += R pnt + p for the scan's points (no down-sampling here)
+int vn_init_tree_push(vina_ctx* ctx, const double R[9], const double p[3])
+{
+  PoseD x;
+  memcpy(x.R, R, 72);
+  memcpy(x.p, p, 24);
+  const int n = ctx->n_pv[1];
+  if ((size_t)ctx->n_tree + n > 2 * (size_t)ctx->cap_points)
+    return vn_fail(ctx, VINA_E_CAPACITY, "local map of the start-up phase: %d + %d points", ctx->n_tree, n);
+  ctx->launches += launch_init_tree_append(ctx->stream, ctx->pv[1], n, x, ctx->d_tree[ctx->tree_cur] + ctx->n_tree);
+  ctx->n_tree += n;
+  return vn_check_cuda(ctx, cudaGetLastError(), "k_init_tree_append");
+}
+
+int vn_init_insert_frame(vina_ctx* ctx, const float* xyzt, int n, int n_skip, const vina_imu_pose* poses, int m,
+                         const vina_state* x, int converged, int frame)
+{
+  if (n > ctx->cap_points) return vn_fail(ctx, VINA_E_CAPACITY, "frame of %d points > max_scan_points", n);
+  if (m > VINA_MAX_POSES) return vn_fail(ctx, VINA_E_CAPACITY, "%d IMU poses > VINA_MAX_POSES", m);
+  int r = ensure_front(ctx);  // (d_raw: the upload buffer)
+  if (r) return r;
+  CU(cudaStreamSynchronize(ctx->stream));  // the staging buffer of the pose table is reused
+  DeskewPoses* hp = ctx->h_poses;
+  hp->m = m;
+  memcpy(hp->pose, poses, (size_t)m * sizeof(vina_imu_pose));
+  memcpy(hp->R_end, x->R, 72);
+  memcpy(hp->p_end, x->p, 24);
+  memcpy(hp->ext_R, ctx->cfg.ext_R, 72);
+  memcpy(hp->ext_t, ctx->cfg.ext_t, 24);
+  CU(cudaMemcpyAsync(ctx->d_poses, hp, sizeof(DeskewPoses), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_raw, xyzt, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  PoseD px;
+  memcpy(px.R, x->R, 72);
+  memcpy(px.p, x->p, 24);
+  double rv[9], tv[9];
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++)
+    {
+      rv[i + 3 * j] = x->cov[i + 15 * j];
+      tv[i + 3 * j] = x->cov[(3 + i) + 15 * (3 + j)];
+    }
+  const VarInitParams prm = var_init_params(ctx);
+  ctx->launches += launch_init_redeskew(ctx->stream, ctx->d_raw, n, n_skip, ctx->d_poses, px, rv, tv, converged, prm,
+                                        ctx->pv[1], ctx->ins);
+  // point 0 is pushed once more for every pose behind its own (see k_init_redeskew)
+  int n_dup = 0;
+  if (n_skip == 0 && n > 0)
+  {
+    int k0 = 0;
+    while (k0 < m && !(poses[k0].t < (double)xyzt[3])) k0++;
+    n_dup = m - 1 - k0 > 0 ? m - 1 - k0 : 0;
+  }
+  const int n_out = (n - n_skip) + n_dup;
+  ctx->n_pv[1] = n_out;
+  ctx->n_down = n_out;
+  ctx->n_down_pending = false;
+  if (n_out <= 0) return VINA_OK;
+  // cut_voxel (voxel_map.cpp:4-45, the serial variant motion_init uses): no "fewer roots than threads" early-out
+  MapView M = ctx->map;
+  M.thread_num = 0;
+  ctx->ins.stamp++;
+  PoseD z;
+  memset(&z, 0, sizeof(z));
+  const double z9[9] = { 0 };
+  ctx->launches += launch_map_insert_roots(ctx->stream, M, ctx->pv[1], nullptr, n_out, ctx->ins, z, z9, z9, 1);
+  ctx->launches += launch_map_insert_leaves(ctx->stream, M, ctx->pv[1], nullptr, n_out, ctx->ins, frame);
+  return vn_check_cuda(ctx, cudaGetLastError(), "start-up insert");
+}
+
+// ---------------------------------------------------------------------------
 extern "C" int vina_map_insert(vina_ctx* ctx, int win_ord, const double R[9], const double p[3],
                                const double cov_rot[9], const double cov_tsl[9])
 {
@@ -1465,6 +1612,26 @@ int vn_ba_collect_enqueue(vina_ctx* ctx)
   ctx->launches += launch_ba_collect(ctx->stream, ctx->map, ctx->layers, ctx->d_ba, ctx->d_ba_n, ctx->ba_cap);
   ctx->ba_n = -1;
   return vn_check_cuda(ctx, cudaGetLastError(), "k_ba_collect");
+}
+
+int vn_ba_normal_scatter(vina_ctx* ctx, double nnt[9])
+{
+  for (int k = 0; k < 9; k++) nnt[k] = 0.0;
+  int32_t n = 0;
+  int r = vina_ba_count(ctx, &n);
+  if (r) return r;
+  if (n <= 0) return VINA_OK;
+  // (a few thousand factors, once per motion_init convergence check: read the store back)
+  std::vector<BaFactor> h((size_t)n);
+  CU(cudaMemcpyAsync(h.data(), ctx->d_ba, (size_t)n * sizeof(BaFactor), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int a = 0; a < n; a++)
+  {
+    const double* v = h[a].eig_vector;  // column 0
+    for (int c = 0; c < 3; c++)
+      for (int rr = 0; rr < 3; rr++) nnt[rr + 3 * c] += v[rr] * v[c];
+  }
+  return VINA_OK;
 }
 
 int vn_ba_writeback_enqueue(vina_ctx* ctx)

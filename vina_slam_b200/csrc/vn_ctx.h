@@ -128,10 +128,32 @@ struct vina_ctx
   vina_timings tm;
   int launches = 0;
 
+  // start-up phase (vina_odom_init_scan; allocated on first use): the local map of the kd-tree IEKF (two buffers:
+  // appended to, then down-sampled into the other), per-point plane (distance, normal), block partials, the 28 sums
+  float4* d_tree[2] = { nullptr, nullptr };
+  int tree_cur = 0, n_tree = 0;
+  double* d_init_ds = nullptr;
+  double* d_init_dir = nullptr;
+  double* d_init_part = nullptr;
+  double* h_init_sums = nullptr;  // mapped pinned
+  double* d_init_sums = nullptr;  // device alias
+
   OdomHost* odom = nullptr;
 };
 
 int vn_fail(vina_ctx* c, int code, const char* fmt, ...);
+int vn_init_ensure(vina_ctx* c);        // buffers of the start-up phase
+int vn_map_clear(vina_ctx* c);          // the map back to its state after vina_ctx_create (motion_init rebuilds it every round)
+// down_sampling_voxel of an arbitrary device cloud (no "< 2000 points" retry); synchronises, returns the count
+int vn_downsample_cloud(vina_ctx* c, const float4* in, int n, double size, float4* out, int* n_out);
+// sum of n n^T over the normals (eigenvector of the smallest eigenvalue) of the collected BA factors, 3x3 column-major
+int vn_ba_normal_scatter(vina_ctx* c, double nnt[9]);
+int vn_init_assoc(vina_ctx* c, const double R[9], const double p[3], int refind, double sums28[28]);
+int vn_init_tree_push(vina_ctx* c, const double R[9], const double p[3]);
+// one frame of motion_init: re-deskew `n` retained raw points (host, time-sorted) with the backward pose table, world
+// points / covariances, then cut_voxel into window slot `frame`
+int vn_init_insert_frame(vina_ctx* c, const float* xyzt, int n, int n_skip, const vina_imu_pose* poses, int m,
+                         const vina_state* x, int converged, int frame);
 int vn_check_cuda(vina_ctx* c, cudaError_t e, const char* what);
 // copy the device status word back (synchronises) and translate it
 int vn_check_status(vina_ctx* c);

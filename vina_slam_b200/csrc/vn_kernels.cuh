@@ -94,6 +94,15 @@ void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots);
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
                       int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status);
 
+// start-up phase (scan_kernels.cu): kd-tree IEKF association / sums, local-map append, motion_init's re-deskew
+struct InsertScratch;
+int launch_init_assoc(cudaStream_t st, const ScanView& pv, int n, const PoseD& x, const float4* tree, int n_tree, int refind,
+                      double* ds, double* dir, double* partial, double* out28);
+int launch_init_tree_append(cudaStream_t st, const ScanView& pv, int n, const PoseD& x, float4* tree_tail);
+int launch_init_redeskew(cudaStream_t st, const float4* orig, int n, int n_skip, const DeskewPoses* d_poses, const PoseD& x,
+                         const double* rot_var, const double* tsl_var, int converged, const VarInitParams& prm,
+                         const ScanView& out, const InsertScratch& sc);
+
 // iekf_kernel.cu
 int iekf_grid_blocks(int n, int sm_count);
 // grid = (blocks, nseq); every sequence gets `blocks` persistent 1024-thread blocks

@@ -458,6 +458,14 @@ struct ImuPre
   // (imu_preintegration.cpp:102-163)
   double evaluate(const vina_state& s1, const vina_state& s2, HM<30, 30>* jtj, HM<30, 1>* gg) const
   {
+    if (!jtj || !gg) return evaluate_n(s1, s2, nullptr, nullptr, 10);
+    return evaluate_n(s1, s2, jtj->d, gg->d, 10);
+  }
+  // ncols = 10: the two frames' states; ncols = 11: plus the gravity vector of the window (IMU_PRE::give_evaluate_g,
+  // imu_preintegration.cpp:165-237: g enters the position and velocity residuals through -R1^T g T^2/2 and -R1^T g T).
+  // jtj: (3 ncols)^2 column-major, gg: 3 ncols
+  double evaluate_n(const vina_state& s1, const vina_state& s2, double* jtj, double* gg, int ncols) const
+  {
     const M3 R1 = m3(s1.R), R2 = m3(s2.R), R1t = R1.T();
     const V3 p1 = v3(s1.p), p2 = v3(s2.p), v1 = v3(s1.v), v2 = v3(s2.v), g = v3(s1.g);
     const V3 th = dR_dbg * dbg;
@@ -478,9 +486,10 @@ struct ImuPre
     for (int k = 1; k < 15; k++) cost = cost + r[k] * Wr[k];
     if (!jtj || !gg) return cost;
 
-    // the Jacobian as 5 x 10 blocks of 3 x 3 (block row = residual part, block column = state part of frame 1, 2)
-    M3 J[5][10];
-    bool nz[5][10] = { { false } };
+    // the Jacobian as 5 x 10 (11) blocks of 3 x 3 (block row = residual part, block column = state part of frame 1,
+    // 2, then gravity)
+    M3 J[5][11];
+    bool nz[5][11] = { { false } };
     auto put = [&](int i, int c, const M3& m) {
       J[i][c] = m;
       nz[i][c] = true;
@@ -504,9 +513,14 @@ struct ImuPre
     put(3, 8, I3);
     put(4, 4, -I3);
     put(4, 9, I3);
+    if (ncols == 11)
+    {
+      put(1, 10, R1t * (-0.5 * dtime * dtime));
+      put(2, 10, R1t * (-dtime));
+    }
     // WJ = W J: only the non-zero blocks of each block column contribute
-    M3 WJ[5][10];
-    for (int c = 0; c < 10; c++)
+    M3 WJ[5][11];
+    for (int c = 0; c < ncols; c++)
       for (int i = 0; i < 5; i++)
       {
         M3 acc = M3::zero();
@@ -514,21 +528,21 @@ struct ImuPre
           if (nz[k][c]) acc = acc + cov_inv.blk<3, 3>(3 * i, 3 * k) * J[k][c];
         WJ[i][c] = acc;
       }
-    *jtj = HM<30, 30>::zero();
-    *gg = HM<30, 1>::zero();
-    for (int a2 = 0; a2 < 10; a2++)
+    const int ld = 3 * ncols;
+    for (int a2 = 0; a2 < ncols; a2++)
     {
-      for (int c = 0; c < 10; c++)
+      for (int c = 0; c < ncols; c++)
       {
         M3 acc = M3::zero();
         for (int i = 0; i < 5; i++)
           if (nz[i][a2]) acc = acc + J[i][a2].T() * WJ[i][c];
-        jtj->set<3, 3>(3 * a2, 3 * c, acc);
+        for (int cc = 0; cc < 3; cc++)
+          for (int rr = 0; rr < 3; rr++) jtj[(3 * a2 + rr) + (size_t)ld * (3 * c + cc)] = acc(rr, cc);
       }
       V3 ga = V3::zero();
       for (int i = 0; i < 5; i++)
         if (nz[i][a2]) ga = ga + J[i][a2].T() * Wr.blk<3, 1>(3 * i, 0);
-      gg->set<3, 1>(3 * a2, 0, ga);
+      for (int rr = 0; rr < 3; rr++) gg[3 * a2 + rr] = ga[rr];
     }
     return cost;
   }
@@ -558,6 +572,15 @@ void ba_imu_factor_delete(ImuPre* f) { delete f; }
 int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPre*>& imus_factor, double imu_coef,
                     int* iters_out)
 {
+  return ba_damping_iter_ex(ctx, xs, imus_factor, imu_coef, iters_out, false, 10, nullptr);
+}
+
+// gravity = the start-up variant (LI_BA_OptimizerGravity::damping_iter, optimizers.cpp:746-826): the window's gravity
+// vector is a 3-dim unknown behind the states, only the POSE of the first frame is fixed (its v, bg, ba are free),
+// max_iter iterations; resis (if given) receives the cost before the first and after the last iteration.
+int ba_damping_iter_ex(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPre*>& imus_factor, double imu_coef,
+                       int* iters_out, bool gravity, int max_iter, double* resis)
+{
   // Levenberg-Marquardt with Nielsen's damping update on the window's 15-dim states, first frame fixed. What must
   // equal the reference (LI_BA_Optimizer::damping_iter, optimizers.cpp:430-517) is the SEQUENCE OF DECISIONS - which
   // steps are accepted, when the Hessian is re-evaluated, when the loop stops - because the oracle comparison counts
@@ -568,8 +591,11 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
   // and the device evaluates the LiDAR factor while the host evaluates the IMU factors.
   const int SD = 15, PD = 6;  // state / pose dimension per frame
   const int win = (int)xs.size();
-  const int m = (win - 1) * SD, nl = win * PD;
-  std::vector<double> Hf((size_t)m * m), gf(m), dvec(m), step((size_t)win * SD, 0.0);
+  const int FX = gravity ? PD : SD;             // fixed leading unknowns (frame 0: its pose, or its whole state)
+  const int NG = gravity ? 3 : 0;               // gravity unknowns behind the states
+  const int ntot = win * SD + NG;
+  const int m = ntot - FX, nl = win * PD;
+  std::vector<double> Hf((size_t)m * m), gf(m), dvec(m), step((size_t)ntot, 0.0);
   std::vector<double> hl((size_t)nl * nl), jl(nl);
   std::vector<vina_pose> poses(win);
   auto set_poses = [&](const std::vector<vina_state>& st) {
@@ -581,15 +607,20 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
   };
   // entry (r, c) of the full system lands in the free block when neither index belongs to frame 0
   auto addH = [&](int r, int c, double v) {
-    if (r >= SD && c >= SD) Hf[(r - SD) + (size_t)m * (c - SD)] += v;
+    if (r >= FX && c >= FX) Hf[(r - FX) + (size_t)m * (c - FX)] += v;
   };
   auto addg = [&](int r, double v) {
-    if (r >= SD) gf[r - SD] += v;
+    if (r >= FX) gf[r - FX] += v;
   };
+  // index of local unknown k of the IMU factor between frames i, i + 1 (30 states, then gravity) in the system
+  auto gidx = [&](int i, int k) { return k < 2 * SD ? i * SD + k : win * SD + (k - 2 * SD); };
+  const int NC = gravity ? 11 : 10, NL = 3 * NC;
+  std::vector<double> jtj((size_t)NL * NL), gg(NL);
   double lambda = 0.01, nu = 2;
   double cost_cur = 0, cost_try = 0;
   bool relinearise = true;
   std::vector<vina_state> xt = xs;
+  double g_try[3] = { xs[0].g[0], xs[0].g[1], xs[0].g[2] };
   int iters = 0;
   // VINA_TRACE: where a BA run spends its time (host IMU factors / device LiDAR factor / solve)
   static double tr_us[5] = { 0, 0, 0, 0, 0 };
@@ -598,7 +629,7 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
   };
   double t0 = 0;
-  for (int it = 0; it < 10; it++)
+  for (int it = 0; it < max_iter; it++)
   {
     iters++;
     if (relinearise)
@@ -612,14 +643,12 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
       int r = vn_ba_hess_enqueue(ctx, poses.data(), win);
       if (r) return r;
       double cost_imu = 0;
-      HM<30, 30> jtj;
-      HM<30, 1> gg;
       for (int i = 0; i < win - 1; i++)
       {
-        cost_imu += imus_factor[i]->evaluate(xs[i], xs[i + 1], &jtj, &gg);
-        for (int c = 0; c < 2 * SD; c++)
-          for (int r2 = 0; r2 < 2 * SD; r2++) addH(i * SD + r2, i * SD + c, imu_coef * jtj(r2, c));
-        for (int r2 = 0; r2 < 2 * SD; r2++) addg(i * SD + r2, imu_coef * gg[r2]);
+        cost_imu += imus_factor[i]->evaluate_n(xs[i], xs[i + 1], jtj.data(), gg.data(), NC);
+        for (int c = 0; c < NL; c++)
+          for (int r2 = 0; r2 < NL; r2++) addH(gidx(i, r2), gidx(i, c), imu_coef * jtj[r2 + (size_t)NL * c]);
+        for (int r2 = 0; r2 < NL; r2++) addg(gidx(i, r2), imu_coef * gg[r2]);
       }
       cost_imu *= (imu_coef * 0.5);
       tr_us[0] += now_us() - t0;
@@ -628,16 +657,17 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
       r = vn_ba_hess_finish(ctx, win, hl.data(), jl.data(), &cost_lidar);
       if (r) return r;
       tr_us[1] += now_us() - t0;
-      for (int a = 1; a < win; a++)  // the pose blocks of the LiDAR factor (hess_plus, optimizers.cpp:171-179)
+      for (int a = 0; a < win; a++)  // the pose blocks of the LiDAR factor (hess_plus, optimizers.cpp:171-179)
       {
         for (int k = 0; k < PD; k++) addg(a * SD + k, jl[a * PD + k]);
-        for (int b2 = 1; b2 < win; b2++)
+        for (int b2 = 0; b2 < win; b2++)
           for (int c = 0; c < PD; c++)
             for (int k = 0; k < PD; k++) addH(a * SD + k, b2 * SD + c, hl[(a * PD + k) + (size_t)nl * (b2 * PD + c)]);
       }
       cost_cur = cost_imu + cost_lidar;
       for (int k = 0; k < m; k++) dvec[k] = Hf[k + (size_t)m * k];
     }
+    if (it == 0 && resis) resis[0] = cost_cur;
     t0 = now_us();
     {
       // step = -(H + lambda D)^-1 g on the free block
@@ -648,7 +678,7 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
         nb[k] = -gf[k];
       }
       std::vector<double> sol = ldlt_solve(A, m, nb);
-      for (int k = 0; k < m; k++) step[SD + k] = sol[k];
+      for (int k = 0; k < m; k++) step[FX + k] = sol[k];
     }
     tr_us[2] += now_us() - t0;
     for (int j = 0; j < win; j++)  // xt = xs (+) step
@@ -665,10 +695,19 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
         xt[j].ba[k] = xs[j].ba[k] + d[12 + k];
       }
     }
+    if (gravity)
+    {
+      // one gravity vector for the whole window. The reference adds the increment to the CANDIDATE's gravity
+      // (x_stats_temp[0].g += dxi.tail(3), optimizers.cpp:781), which keeps the increments of rejected steps: the
+      // sequence of LM decisions has to be the reference's, so the same bookkeeping here
+      for (int k = 0; k < 3; k++) g_try[k] += step[win * SD + k];
+      for (int j = 0; j < win; j++)
+        for (int k = 0; k < 3; k++) xt[j].g[k] = g_try[k];
+    }
     for (int j = 0; j < win - 1; j++) imus_factor[j]->update_state(&step[SD * j]);
     // predicted decrease of the quadratic model: 1/2 step^T (lambda D step - g)
     double predicted = 0;
-    for (int k = 0; k < m; k++) predicted += step[SD + k] * ((lambda * dvec[k]) * step[SD + k] - gf[k]);
+    for (int k = 0; k < m; k++) predicted += step[FX + k] * ((lambda * dvec[k]) * step[FX + k] - gf[k]);
     predicted *= 0.5;
     {
       // cost at the candidate (only_residual, optimizers.cpp:340-376)
@@ -708,6 +747,7 @@ int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPr
     }
     if (std::fabs(decrease / cost_cur) < 1e-6) break;
   }
+  if (resis) resis[1] = cost_try;
   if (iters_out) *iters_out = iters;
   if (ctx->trace && (++tr_calls % 10) == 0)
     fprintf(stderr, "[vina trace] BA, us per run over %d runs: imu jac (device Hessian in flight) %.1f, wait for the device Hessian %.1f, solve %.1f, imu res %.1f, "

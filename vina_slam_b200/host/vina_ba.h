@@ -14,3 +14,7 @@ ImuPre* ba_imu_factor_new(const double* bg, const double* ba, const std::deque<v
 void ba_imu_factor_delete(ImuPre* f);
 int ba_damping_iter(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPre*>& imus_factor, double imu_coef,
                     int* iters_out);
+// the same loop with the window's gravity vector as an additional unknown (LI_BA_OptimizerGravity::damping_iter,
+// optimizers.cpp:746-826; used by the start-up phase): see vina_ba.cpp
+int ba_damping_iter_ex(vina_ctx* ctx, std::vector<vina_state>& xs, std::deque<ImuPre*>& imus_factor, double imu_coef,
+                       int* iters_out, bool gravity, int max_iter, double* resis);

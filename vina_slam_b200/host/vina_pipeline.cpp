@@ -6,9 +6,11 @@
 // and drives the CUDA kernels only through the low-level C ABI of
 // include/vina_b200.h — the same calls a reference-side adapter would make
 // (INTEGRATION.md). No point-level work happens here.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <deque>
+#include <unordered_map>
 #include <vector>
 #include <chrono>
 #include "../csrc/vn_ctx.h"
@@ -23,6 +25,7 @@ namespace
 {
 // column-major helpers -------------------------------------------------------
 inline void m3_mul(const double* A, const double* B, double* C) { mat3_mul(A, B, C); }
+inline void m3_vec(const double* A, const double* v, double* w) { rot_vec(A, v, w); }
 inline void m3_T(const double* A, double* T)
 {
   for (int i = 0; i < 3; i++)
@@ -118,6 +121,16 @@ struct OdomHost
   double jour = 0.0;
   double last_pos[3] = { 0, 0, 0 };
   bool release_flag = false;
+  // start-up phase (VINA_SLAM::initialization, node.cpp:293-366; vina_odom_cold_start / vina_odom_init_scan)
+  bool in_init = false;
+  bool imu_init_flag = true;  // IMUEKF::init_flag: a context that is bootstrapped at known states never needs IMU_init
+  int imu_init_num = 0;
+  double mean_acc[3] = { 0, 0, 0 }, mean_gyr[3] = { 0, 0, 0 };
+  std::vector<vina_state> init_xs;                 // x_buf with the full states
+  std::vector<std::vector<float>> pl_origs;        // per frame: retained raw points (x, y, z, t), time-sorted
+  std::vector<double> beg_times;
+  std::vector<std::deque<vina_imu>> vec_imus;      // per frame: its IMU batch, ends re-stamped
+  int init_rounds = 0;
   ~OdomHost()
   {
     for (ImuPre* f : imu_pre_buf) ba_imu_factor_delete(f);
@@ -246,7 +259,7 @@ static int imu_propagate(vina_ctx* ctx, OdomHost* o, const vina_imu* imus_in, in
   for (int k = 0; k < 3; k++)
     xc.p[k] = (pos_imu[k] + (note * vel_imu[k]) * dt) + (((note * 0.5) * acc_imu[k]) * dt) * dt;
   xc.t = o->pcl_end_time;
-  if (o->if_BA)
+  if (o->if_BA || o->in_init)
   {
     // imu_ekf.cpp:95-104: the batch handed to the pre-integration, first / last sample re-stamped to the scan
     // boundaries (integer nanoseconds, rclcpp::Time)
@@ -1225,4 +1238,559 @@ int vina_odom_window(vina_ctx* ctx, int* win_count, int* mp, int cap)
   for (int i = 0; i < ctx->cfg.win_size && i < cap; i++) mp[i] = ctx->map.mp[i];
   return ctx->cfg.win_size;
 }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Start-up phase: what the reference does with the first scans before the per-scan loop
+// above can run - VINA_SLAM::initialization (src/platform/ros2/node.cpp:293-366) and the loop's handling of its
+// result (src/pipeline/local_mapping.cpp:362-388, then :489-546 on success). Per scan: IMU initialisation or
+// IMU propagation + deskew (IMUEKF::process, imu_ekf.cpp:174-201), down-sampling at max(down_size, 0.5 m),
+// var_init, the kd-tree IEKF against a local map of world points (lio_state_estimation_kdtree,
+// odometry.cpp:267-439), the window bookkeeping, the frame's retained raw cloud (down_sampling_close + time sort);
+// with the window full, Initialization::motion_init (initialization.cpp:158-367): up to ten rounds of "rebuild the
+// map from re-deskewed frames, recut, gravity BA", gravity alignment after the first convergence.
+// Where it runs: the point-sized work on the device (deskew, down-sampling, var_init, nearest neighbours + plane
+// fit + normal equations of the kd-tree IEKF, the re-deskew / covariance / insert / recut of every motion_init
+// round, the LiDAR factor of the BA); on the host the sequential 15-dim algebra (IMU, the 15 x 15 IEKF update, the
+// LM loop, gravity alignment) and down_sampling_close, whose result depends on the order of a float running sum
+// (point_utils.hpp:75-86) - ten scans, once per run.
+namespace
+{
+// down_sampling_close (include/vina_slam/core/point_utils.hpp:47-113) on (x, y, z, t) rows; the voxel map iterates in
+// the order of the reference's container (same key, same hash: types.hpp:13-41)
+struct CloseKey
+{
+  int64_t x, y, z;
+  bool operator==(const CloseKey& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct CloseHash
+{
+  size_t operator()(const CloseKey& s) const
+  {
+    using std::hash;
+    const long long P = 1000033, N = 100000000000LL;
+    return (size_t)((((hash<int64_t>()(s.z) * P) % N + hash<int64_t>()(s.y)) * P) % N + hash<int64_t>()(s.x));
+  }
+};
+void down_sampling_close_host(std::vector<float>& pl, double voxel_size)
+{
+  if (voxel_size < 0.001) return;
+  const size_t n = pl.size() / 4;
+  std::unordered_map<CloseKey, std::vector<int>, CloseHash> feat_map;
+  for (size_t i = 0; i < n; i++)
+  {
+    float loc[3];
+    for (int j = 0; j < 3; j++)
+    {
+      loc[j] = pl[4 * i + j] / voxel_size;
+      if (loc[j] < 0) loc[j] -= 1.0;
+    }
+    feat_map[CloseKey{ (int64_t)loc[0], (int64_t)loc[1], (int64_t)loc[2] }].push_back((int)i);
+  }
+  std::vector<float> out;
+  out.reserve(4 * feat_map.size());
+  for (auto it = feat_map.begin(); it != feat_map.end(); ++it)
+  {
+    const std::vector<int>& idx = it->second;
+    float pb[3] = { pl[4 * (size_t)idx[0]], pl[4 * (size_t)idx[0] + 1], pl[4 * (size_t)idx[0] + 2] };
+    const int plsize = (int)idx.size();
+    for (int k = 1; k < plsize; k++)
+      for (int j = 0; j < 3; j++) pb[j] += pl[4 * (size_t)idx[k] + j];
+    for (int j = 0; j < 3; j++) pb[j] /= plsize;
+    double ndis = 100;
+    int mnum = 0;
+    for (int k = 0; k < plsize; k++)
+    {
+      const float* pp = &pl[4 * (size_t)idx[k]];
+      const double xx = pb[0] - pp[0], yy = pb[1] - pp[1], zz = pb[2] - pp[2];
+      const double dis = xx * xx + yy * yy + zz * zz;
+      if (dis < ndis)
+      {
+        mnum = k;
+        ndis = dis;
+      }
+    }
+    const float* q = &pl[4 * (size_t)idx[mnum]];
+    out.insert(out.end(), q, q + 4);
+  }
+  pl.swap(out);
+}
+void sort_by_time(std::vector<float>& pl)
+{
+  struct P4
+  {
+    float v[4];
+  };
+  P4* b = reinterpret_cast<P4*>(pl.data());
+  std::sort(b, b + pl.size() / 4, [](const P4& x, const P4& y) { return x.v[3] < y.v[3]; });
+}
+
+// IMUEKF::IMU_init (imu_ekf.cpp:147-172)
+void imu_init(OdomHost* o, const vina_imu* imus, int m)
+{
+  for (int k = 0; k < m; k++)
+  {
+    if (o->imu_init_num != 0)
+    {
+      for (int j = 0; j < 3; j++)
+      {
+        o->mean_acc[j] += (imus[k].acc[j] - o->mean_acc[j]) / (double)o->imu_init_num;
+        o->mean_gyr[j] += (imus[k].gyr[j] - o->mean_gyr[j]) / (double)o->imu_init_num;
+      }
+    }
+    else
+    {
+      for (int j = 0; j < 3; j++) o->mean_acc[j] = imus[k].acc[j], o->mean_gyr[j] = imus[k].gyr[j];
+      o->imu_init_num = 1;
+    }
+    o->imu_init_num++;
+  }
+  o->last_imu = imus[m - 1];
+}
+
+void state_set_zero(vina_state& x)  // IMUST::setZero (types.hpp:101-112)
+{
+  memset(&x, 0, sizeof(x));
+  x.R[0] = x.R[4] = x.R[8] = 1;
+  x.g[2] = -9.8;
+  for (int i = 0; i < 15; i++) x.cov[i + 15 * i] = i < 9 ? 1e-4 : 1e-5;
+}
+
+// VINA_SLAM::lio_state_estimation_kdtree (odometry.cpp:267-439): point loop on the device, update on the host
+int kdtree_iekf(vina_ctx* ctx, OdomHost* o)
+{
+  vina_state& x_curr = o->x_curr;
+  int r;
+  if (ctx->n_pv[1] <= 0) return VINA_OK;
+  if (ctx->n_tree < 100)
+  {
+    r = vn_init_tree_push(ctx, x_curr.R, x_curr.p);
+    return r;
+  }
+  const int num_max_iter = 4;
+  const vina_state x_prop = x_curr;
+  bool converged_once = false;
+  double G[225], HTH15[225], cov_inv[225], K1[225], tmp[225];
+  memset(G, 0, sizeof(G));
+  memset(HTH15, 0, sizeof(HTH15));
+  int rematch_num = 0;
+  inverse_lu<15>(x_curr.cov, cov_inv);
+  bool refind = true;
+  for (int iterCount = 0; iterCount < num_max_iter; iterCount++)
+  {
+    double sums[28];
+    r = vn_init_assoc(ctx, x_curr.R, x_curr.p, refind ? 1 : 0, sums);
+    if (r) return r;
+    double HTH[36], HTz[6];
+    {
+      int t = 0;
+      for (int a = 0; a < 6; a++)
+        for (int b = a; b < 6; b++, t++) HTH[a + 6 * b] = HTH[b + 6 * a] = sums[t];
+      for (int a = 0; a < 6; a++) HTz[a] = sums[21 + a];
+    }
+    for (int j = 0; j < 6; j++)
+      for (int i = 0; i < 6; i++) HTH15[i + 15 * j] = HTH[i + 6 * j];
+    for (int i = 0; i < 225; i++) tmp[i] = HTH15[i] + cov_inv[i] / 1000;  // (H_T_H + cov_inv / 1000).inverse()
+    inverse_lu<15>(tmp, K1);
+    double G6[90];
+    mat_mul(15, 6, 6, K1, HTH, G6);
+    memcpy(G, G6, sizeof(G6));
+    double vec[15], sol[15], a[15], b[15];
+    state_boxminus(x_prop, x_curr, vec);
+    mat_mul(15, 6, 1, K1, HTz, a);
+    mat_mul(15, 6, 1, G6, vec, b);
+    for (int i = 0; i < 15; i++) sol[i] = (a[i] + vec[i]) - b[i];
+    state_boxplus(x_curr, sol);
+    refind = false;
+    if ((norm3(sol) * 57.3 < 0.01) && (norm3(sol + 3) * 100 < 0.015))
+    {
+      refind = true;
+      converged_once = true;
+      rematch_num++;
+    }
+    if (iterCount == num_max_iter - 2 && !converged_once) refind = true;
+    if (rematch_num >= 2 || (iterCount == num_max_iter - 1))
+    {
+      double IG[225], nc[225];
+      for (int i = 0; i < 225; i++) IG[i] = -G[i];
+      for (int i = 0; i < 15; i++) IG[i + 15 * i] = 1.0 - G[i + 15 * i];
+      mat_mul(15, 15, 15, IG, x_curr.cov, nc);
+      memcpy(x_curr.cov, nc, sizeof(nc));
+      break;
+    }
+  }
+  // the scan joins the local map, which is thinned to a 0.5 m grid (odometry.cpp:429-438)
+  r = vn_init_tree_push(ctx, x_curr.R, x_curr.p);
+  if (r) return r;
+  int n_out = 0;
+  r = vn_downsample_cloud(ctx, ctx->d_tree[ctx->tree_cur], ctx->n_tree, 0.5, ctx->d_tree[1 - ctx->tree_cur], &n_out);
+  if (r) return r;
+  ctx->tree_cur = 1 - ctx->tree_cur;
+  ctx->n_tree = n_out;
+  return VINA_OK;
+}
+
+// Initialization::align_gravity (initialization.cpp:28-62)
+void align_gravity(std::vector<vina_state>& xs)
+{
+  double g0[3] = { xs[0].g[0], xs[0].g[1], xs[0].g[2] };
+  const double gn = norm3(g0);
+  double n0[3] = { g0[0] / gn, g0[1] / gn, g0[2] / gn };
+  double n1[3] = { 0, 0, 1 };
+  if (n0[2] < 0) n1[2] = -1;
+  double rv[3] = { n0[1] * n1[2] - n0[2] * n1[1], n0[2] * n1[0] - n0[0] * n1[2], n0[0] * n1[1] - n0[1] * n1[0] };
+  const double rnorm = norm3(rv);
+  for (int k = 0; k < 3; k++) rv[k] /= rnorm;
+  // AngleAxisd(asin(rnorm), axis).toRotationMatrix()
+  const double ang = std::asin(rnorm), s = std::sin(ang), c = std::cos(ang);
+  double rot[9];  // column-major
+  const double c1[3] = { (1 - c) * rv[0], (1 - c) * rv[1], (1 - c) * rv[2] }, sa[3] = { s * rv[0], s * rv[1], s * rv[2] };
+  double tmpv;
+  tmpv = c1[0] * rv[1];
+  rot[0 + 3 * 1] = tmpv - sa[2];
+  rot[1 + 3 * 0] = tmpv + sa[2];
+  tmpv = c1[0] * rv[2];
+  rot[0 + 3 * 2] = tmpv + sa[1];
+  rot[2 + 3 * 0] = tmpv - sa[1];
+  tmpv = c1[1] * rv[2];
+  rot[1 + 3 * 2] = tmpv - sa[0];
+  rot[2 + 3 * 1] = tmpv + sa[0];
+  rot[0] = c1[0] * rv[0] + c;
+  rot[4] = c1[1] * rv[1] + c;
+  rot[8] = c1[2] * rv[2] + c;
+  double g1[3];
+  m3_vec(rot, g0, g1);
+  const double p0[3] = { xs[0].p[0], xs[0].p[1], xs[0].p[2] };
+  for (size_t i = 0; i < xs.size(); i++)
+  {
+    double d[3] = { xs[i].p[0] - p0[0], xs[i].p[1] - p0[1], xs[i].p[2] - p0[2] }, rd[3], Rn[9], vn[3];
+    m3_vec(rot, d, rd);
+    for (int k = 0; k < 3; k++) xs[i].p[k] = rd[k] + p0[k];
+    m3_mul(rot, xs[i].R, Rn);
+    memcpy(xs[i].R, Rn, 72);
+    m3_vec(rot, xs[i].v, vn);
+    memcpy(xs[i].v, vn, 24);
+    memcpy(xs[i].g, g1, 24);
+  }
+}
+
+// the pose table of Initialization::motion_blur (initialization.cpp:64-111): BACKWARD integration from the frame's
+// end state xc (biases of the previous frame), latest pose first
+void backward_poses(const vina_state& xc_in, const vina_state& xl, const std::deque<vina_imu>& imus, double pcl_beg_time,
+                    double scale_gravity, std::vector<vina_imu_pose>& out)
+{
+  out.clear();
+  double R_imu[9], pos[3], vel[3];
+  memcpy(R_imu, xc_in.R, 72);
+  memcpy(pos, xc_in.p, 24);
+  memcpy(vel, xc_in.v, 24);
+  for (size_t it = imus.size() - 1; it != 0; it--)
+  {
+    const vina_imu &head = imus[it - 1], &tail = imus[it];
+    double w[3], a[3], acc[3];
+    for (int k = 0; k < 3; k++)
+    {
+      w[k] = 0.5 * (head.gyr[k] + tail.gyr[k]) - xl.bg[k];
+      a[k] = 0.5 * (head.acc[k] + tail.acc[k]) * scale_gravity - xl.ba[k];
+    }
+    const double dt = head.t - tail.t;
+    double E[9], Rn[9], Ra[3];
+    Exp_dt(w, dt, E);
+    m3_vec(R_imu, a, Ra);
+    for (int k = 0; k < 3; k++) acc[k] = Ra[k] + xc_in.g[k];
+    for (int k = 0; k < 3; k++) pos[k] = pos[k] + vel[k] * dt + 0.5 * acc[k] * dt * dt;
+    for (int k = 0; k < 3; k++) vel[k] = vel[k] + acc[k] * dt;
+    m3_mul(R_imu, E, Rn);
+    memcpy(R_imu, Rn, 72);
+    vina_imu_pose ps;
+    ps.t = head.t - pcl_beg_time;
+    memcpy(ps.R, R_imu, 72);
+    memcpy(ps.p, pos, 24);
+    memcpy(ps.v, vel, 24);
+    memcpy(ps.w, w, 24);
+    memcpy(ps.a, acc, 24);
+    out.push_back(ps);
+  }
+}
+
+// Initialization::motion_init (initialization.cpp:158-367); 1 = converged, 0 = failed (the map is empty then)
+int motion_init(vina_ctx* ctx, OdomHost* o, int* ok_out)
+{
+  *ok_out = 0;
+  const int win_size = ctx->cfg.win_size;
+  std::vector<vina_state>& xs = o->init_xs;
+  int converge_flag = 0;
+  MapView& M = ctx->map;
+  const double min_eig_orig = M.min_eigen_value;
+  double thre_orig[4];
+  for (int k = 0; k < 4; k++) thre_orig[k] = M.thre[k];
+  const int thread_num_orig = M.thread_num;
+  M.min_eigen_value = 0.02;
+  for (int k = 0; k < 4; k++) M.thre[k] = 1.0 / 4;
+  M.thread_num = 0;  // motion_init calls cut_voxel / recut / tras_opt directly: none of the fan-out drivers' early-outs
+  double converge_thre = 0.05;
+  bool is_degrade = true;
+  double eigvalue[3] = { 0, 0, 0 };
+  std::vector<vina_imu_pose> poses;
+  std::vector<vina_pose> xb(win_size);
+  int r = VINA_OK;
+  o->init_rounds = 0;
+  for (int iterCnt = 0; iterCnt < 10 && r == VINA_OK; iterCnt++)
+  {
+    o->init_rounds++;
+    if (converge_flag == 1)
+    {
+      M.min_eigen_value = min_eig_orig;
+      for (int k = 0; k < 4; k++) M.thre[k] = thre_orig[k];
+    }
+    r = vn_map_clear(ctx);
+    if (r) break;
+    for (int i = 0; i < win_size && r == VINA_OK; i++)
+    {
+      const int l = i == 0 ? i : i - 1;
+      backward_poses(xs[i], xs[l], o->vec_imus[i], o->beg_times[i], o->scale_gravity, poses);
+      const std::vector<float>& pl = o->pl_origs[i];
+      const int n = (int)(pl.size() / 4);
+      // points at or before the earliest pose are not compensated and not pushed (initialization.cpp:139)
+      const double t_first = poses.empty() ? 1e300 : poses.back().t;
+      int n_skip = 0;
+      while (n_skip < n && !((double)pl[4 * (size_t)n_skip + 3] > t_first)) n_skip++;
+      r = vn_init_insert_frame(ctx, pl.data(), n, n_skip, poses.data(), (int)poses.size(), &xs[i], converge_flag, i);
+    }
+    if (r) break;
+    for (int i = 0; i < win_size; i++)
+    {
+      memcpy(xb[i].R, xs[i].R, 72);
+      memcpy(xb[i].p, xs[i].p, 24);
+    }
+    r = vina_map_recut(ctx, win_size, xb.data());
+    if (r) break;
+    int32_t n_fac = 0;
+    r = vina_ba_collect(ctx, &n_fac);  // tras_opt of every root
+    if (r) break;
+    if (n_fac < 10) break;
+    double resis[2] = { 0, 0 };
+    int iters = 0;
+    r = ba_damping_iter_ex(ctx, xs, o->imu_pre_buf, o->imu_coef, &iters, true, 3, resis);
+    if (r) break;
+    for (ImuPre* f : o->imu_pre_buf) ba_imu_factor_delete(f);
+    o->imu_pre_buf.clear();
+    for (int i = 1; i < win_size; i++)
+      o->imu_pre_buf.push_back(ba_imu_factor_new(xs[i - 1].bg, xs[i - 1].ba, o->vec_imus[i], o->scale_gravity, ctx->cfg));
+    if (std::fabs(resis[0] - resis[1]) / resis[0] < converge_thre && iterCnt >= 2)
+    {
+      // lambda_min of the sum of n n^T over the factors' normals (initialization.cpp:277-285)
+      double nnt[9];
+      r = vn_ba_normal_scatter(ctx, nnt);
+      if (r) break;
+      double L[6] = { nnt[0], nnt[1], nnt[2], nnt[4], nnt[5], nnt[8] }, Q[9];
+      eig3_sym(L, eigvalue, Q);
+      is_degrade = eigvalue[0] < 15;
+      converge_thre = 0.01;
+      if (converge_flag == 0)
+      {
+        align_gravity(xs);
+        converge_flag = 1;
+        continue;
+      }
+      break;
+    }
+  }
+  M.min_eigen_value = min_eig_orig;
+  for (int k = 0; k < 4; k++) M.thre[k] = thre_orig[k];
+  M.thread_num = thread_num_orig;
+  if (r) return r;
+  o->x_curr = xs[win_size - 1];
+  const double gnm = norm3(o->x_curr.g);
+  if (is_degrade) converge_flag = 0;
+  if (gnm < 9.6 || gnm > 10.0) converge_flag = 0;
+  if (converge_flag == 0)
+  {
+    r = vn_map_clear(ctx);
+    if (r) return r;
+  }
+  o->pl_origs.clear();
+  o->vec_imus.clear();
+  o->beg_times.clear();
+  *ok_out = converge_flag;
+  return VINA_OK;
+}
+
+// VINA_SLAM::system_reset (node.cpp:368-408)
+int system_reset(vina_ctx* ctx, OdomHost* o, const vina_imu* imus, int m)
+{
+  int r = vn_map_clear(ctx);
+  if (r) return r;
+  state_set_zero(o->x_curr);
+  o->x_curr.p[2] = 30;
+  for (int k = 0; k < 3; k++) o->mean_acc[k] = 0;
+  o->imu_init_num = 0;
+  imu_init(o, imus, m);
+  for (int k = 0; k < 3; k++) o->x_curr.g[k] = -o->mean_acc[k] * o->scale_gravity;
+  for (ImuPre* f : o->imu_pre_buf) ba_imu_factor_delete(f);
+  o->imu_pre_buf.clear();
+  o->x_buf.clear();
+  o->xs_buf.clear();
+  o->init_xs.clear();
+  ctx->n_tree = 0;
+  o->win_base = 0;
+  o->win_count = 0;
+  return VINA_OK;
+}
+}  // namespace
+
+int vina_odom_cold_start(vina_ctx* ctx)
+{
+  if (!ctx) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  int r = vn_init_ensure(ctx);
+  if (r) return r;
+  r = vn_map_clear(ctx);
+  if (r) return r;
+  state_set_zero(o->x_curr);
+  o->in_init = true;
+  o->imu_init_flag = false;
+  o->imu_init_num = 0;
+  for (int k = 0; k < 3; k++) o->mean_acc[k] = o->mean_gyr[k] = 0;
+  for (ImuPre* f : o->imu_pre_buf) ba_imu_factor_delete(f);
+  o->imu_pre_buf.clear();
+  o->x_buf.clear();
+  o->xs_buf.clear();
+  o->init_xs.clear();
+  o->pl_origs.clear();
+  o->vec_imus.clear();
+  o->beg_times.clear();
+  o->win_base = o->win_count = 0;
+  o->scale_gravity = 1.0;
+  o->last_pcl_end_time = 0;
+  ctx->n_tree = 0;
+  ctx->tree_cur = 0;
+  return VINA_OK;
+}
+
+int vina_odom_init_scan(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time, const vina_imu* imus, int m,
+                        vina_state* x_out, int32_t* status)
+{
+  if (!ctx || !xyzt || !imus || n <= 0 || m <= 0 || !status) return VINA_E_ARG;
+  OdomHost* o = odom(ctx);
+  if (!o->in_init) return vn_fail(ctx, VINA_E_STATE, "vina_odom_init_scan without vina_odom_cold_start");
+  *status = 0;
+  const int win_size = ctx->cfg.win_size;
+  o->pcl_beg_time = pcl_beg_time;
+  o->pcl_end_time = pcl_beg_time + (double)xyzt[4 * (size_t)(n - 1) + 3];  // sync.cpp:40
+  int r;
+  // ---- IMUEKF::process (imu_ekf.cpp:174-201)
+  if (!o->imu_init_flag)
+  {
+    imu_init(o, imus, m);
+    if (norm3(o->mean_acc) < 2) o->scale_gravity = 9.8;
+    for (int k = 0; k < 3; k++) o->x_curr.g[k] = -o->mean_acc[k] * o->scale_gravity;
+    if (o->imu_init_num > 30) o->imu_init_flag = true;  // min_init_num (ekf_imu.hpp:18)
+    o->last_pcl_end_time = o->pcl_end_time;
+    if (x_out) *x_out = o->x_curr;
+    return VINA_OK;
+  }
+  r = vina_scan_upload(ctx, xyzt, n);
+  if (r) return r;
+  r = imu_propagate(ctx, o, imus, m);
+  if (r) return r;
+  r = vina_deskew(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+  if (r) return r;
+  // ---- down_sampling_voxel(max(down_size, 0.5)), var_init, the kd-tree IEKF
+  const double downkd = ctx->cfg.down_size >= 0.5 ? ctx->cfg.down_size : 0.5;
+  int n_down = 0;
+  r = vn_downsample_cloud(ctx, ctx->d_scan, ctx->n_scan, downkd, ctx->d_down, &n_down);
+  if (r) return r;
+  ctx->n_down = n_down;
+  ctx->n_down_pending = false;
+  r = vina_var_init(ctx, 1);
+  if (r) return r;
+  r = kdtree_iekf(ctx, o);
+  if (r) return r;
+  // ---- the window (node.cpp:322-331)
+  o->win_count++;
+  o->init_xs.push_back(o->x_curr);
+  if (o->win_count > 1)
+  {
+    const vina_state& prev = o->init_xs[o->win_count - 2];
+    o->imu_pre_buf.push_back(ba_imu_factor_new(prev.bg, prev.ba, o->ba_imus, o->scale_gravity, ctx->cfg));
+  }
+  // ---- the frame's retained raw cloud (node.cpp:333-345)
+  std::vector<float> orig(xyzt, xyzt + 4 * (size_t)n);
+  {
+    std::vector<float> mid = orig;
+    down_sampling_close_host(orig, ctx->cfg.down_size);
+    if (orig.size() / 4 < 1000)
+    {
+      orig = mid;
+      down_sampling_close_host(orig, ctx->cfg.down_size / 2);
+    }
+    sort_by_time(orig);
+  }
+  o->pl_origs.push_back(std::move(orig));
+  o->beg_times.push_back(o->pcl_beg_time);
+  o->vec_imus.push_back(o->ba_imus);
+  if (x_out) *x_out = o->x_curr;
+  if (o->win_count < win_size) return VINA_OK;
+  // ---- motion_init and what the loop does with its result
+  int ok = 0;
+  r = motion_init(ctx, o, &ok);
+  if (r) return r;
+  if (!ok)
+  {
+    *status = -1;
+    r = system_reset(ctx, o, imus, m);
+    if (x_out) *x_out = o->x_curr;
+    return r;
+  }
+  // success: the window tail of this scan (local_mapping.cpp:489-546) - BA on the factors motion_init left, margi,
+  // window shift - and the hand-over to the per-scan loop
+  *status = 1;
+  o->in_init = false;
+  o->x_buf.clear();
+  o->xs_buf.clear();
+  for (int i = 0; i < win_size; i++)
+  {
+    vina_pose ps;
+    memcpy(ps.R, o->init_xs[i].R, 72);
+    memcpy(ps.p, o->init_xs[i].p, 24);
+    o->x_buf.push_back(ps);
+    if (o->if_BA) o->xs_buf.push_back(o->init_xs[i]);
+  }
+  if (o->if_BA)
+  {
+    r = ba_damping_iter(ctx, o->xs_buf, o->imu_pre_buf, o->imu_coef, &o->ba_last_iters);
+    if (r) return r;
+    o->ba_runs++;
+    for (int i = 0; i < win_size; i++)
+    {
+      memcpy(o->x_buf[i].R, o->xs_buf[i].R, 72);
+      memcpy(o->x_buf[i].p, o->xs_buf[i].p, 24);
+    }
+  }
+  r = vn_ba_writeback_enqueue(ctx);  // margi takes the factors' (re-evaluated) pcr_add / eig (octree.cpp:410-416)
+  if (r) return r;
+  memcpy(o->x_curr.R, o->x_buf.back().R, 72);
+  memcpy(o->x_curr.p, o->x_buf.back().p, 24);
+  ctx->map.jour = o->jour;
+  r = vina_map_margi(ctx, o->win_count, o->x_buf.data());
+  if (r) return r;
+  journey_update(o);
+  r = vina_map_shift_window(ctx);
+  if (r) return r;
+  o->x_buf.erase(o->x_buf.begin());
+  if (o->if_BA) o->xs_buf.erase(o->xs_buf.begin());
+  ba_imu_factor_delete(o->imu_pre_buf.front());
+  o->imu_pre_buf.pop_front();
+  if (!o->if_BA)
+  {
+    // (without BA the per-scan loop keeps no pre-integration factors)
+    for (ImuPre* f : o->imu_pre_buf) ba_imu_factor_delete(f);
+    o->imu_pre_buf.clear();
+  }
+  o->win_base += 1;
+  o->win_count -= 1;
+  o->init_xs.clear();
+  if (x_out) *x_out = o->x_curr;
+  return VINA_OK;
 }
