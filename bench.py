@@ -237,7 +237,7 @@ def main_ours(args, cfg):
         gx.set_profiling(profiled)
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
-        tm_rows, traj, traj_p_pass = [], 0.0, []
+        tm_rows, traj, traj_p_pass, map_counts = [], 0.0, [], []
         barrier()
         for k, sc in enumerate(scans):
             if k == W:
@@ -254,6 +254,8 @@ def main_ours(args, cfg):
                 tm_rows.append(gx.timings())
                 traj = max(traj, float(np.linalg.norm(np.array(st.p[:]) - sc.gt_p)))
                 traj_p_pass.append(np.array(st.p[:]))
+                if profiled:
+                    map_counts.append(gx.map_last_counts())
         barrier()
         if not profiled:
             clocks = sampler.stop() if sampler else {}
@@ -288,13 +290,46 @@ def main_ours(args, cfg):
     miss = (n_mean + (iters_per_step - 1) * n_mean * (1 - match_frac)) / max(iters_per_step, 1)
     bytes_per_launch = 80.0 * n_mean + 256.0 * U + 16.0 * miss + 34 * 8
     launch_ms = iekf_kernel_ms / max(iters, 1)
-    traffic = None
-    try:  # dram__bytes_read + write per launch from the committed `ncu --set full` capture of this kernel
-        with open(os.path.join(ROOT, "profiles", "r01_iekf_ncu_full_summary.json")) as f:
-            traffic = json.load(f)["dram_traffic_bytes_per_launch"] if cfg.name == "robosense128" else None
+    # dram__bytes_read + write per launch from the committed `ncu --set full` capture of this kernel - valid only for the
+    # workload it was taken on and for as long as the kernel's source is the one that was profiled
+    traffic, traffic_source = None, None
+    try:
+        import hashlib
+
+        with open(os.path.join(ROOT, "profiles", "r02_iekf_ncu_full_summary.json")) as f:
+            cap = json.load(f)
+        with open(os.path.join(ROOT, "vina_slam_b200", "csrc", "iekf_kernel.cu"), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()[:16]
+        if cfg.name == cap.get("workload") and sha == cap.get("kernel_source_sha256_16"):
+            traffic = cap["dram_traffic_bytes_per_launch"]
+            traffic_source = "profiles/r02_iekf_ncu_full_summary.json (ncu --set full, same kernel source %s)" % sha
+        else:
+            traffic_source = "none: the committed ncu capture is of another workload or kernel source"
     except Exception:
-        pass
+        traffic_source = "none: no committed ncu capture"
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+
+    # ---- the other stages: algorithmic bytes (SURVEY.md 8d per-unit figures x the units of this workload) over the
+    # stage's device time from the instrumented pass - they are latency-bound kernels over ~10^4 tree nodes, the
+    # table says by how much
+    mc = np.array([[c[0], c[1], sum(c[2]), c[3]] for c in map_counts], dtype=np.float64).mean(axis=0) if map_counts else np.zeros(4)
+    n_ins, u_ins, u_fit, n_split = [float(v) for v in mc]
+    stage_bytes = {
+        "deskew + var_init (k_deskew_var_init)": (28.0 + 72.0 + 4.0) * n_mean,
+        "iekf loop (k_iekf x iterations)": bytes_per_launch * iters_per_step,
+        "insert (k_insert_*)": (72.0 + 72.0 + 16.0 + 80.0) * n_ins + 1040.0 * u_ins,
+        "recut (k_recut_*, k_split)": (80.0 + 96.0) * u_fit,
+        "margi (k_margi_*)": (80.0 + 800.0 + 360.0 + 96.0 + 224.0) * u_fit,
+    }
+    stage_time = {"deskew + var_init (k_deskew_var_init)": stage["deskew_ms"], "iekf loop (k_iekf x iterations)": stage["iekf_ms"],
+                  "insert (k_insert_*)": stage["insert_ms"], "recut (k_recut_*, k_split)": stage["recut_ms"],
+                  "margi (k_margi_*)": stage["margi_ms"]}
+    roofline_stages = []
+    for nm, bts in stage_bytes.items():
+        ms = stage_time[nm]
+        gbs = bts / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        roofline_stages.append({"stage": nm, "algorithmic_bytes": bts, "ms": ms, "achieved_GBs": gbs, "frac": gbs / hbm_peak})
+    whole = sum(stage_bytes.values())
     gx.close()
     del d_scans
 
@@ -441,9 +476,18 @@ def main_ours(args, cfg):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_iekf", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
+                         "traffic_source": traffic_source,
                          "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_us": 1e3 * launch_ms,
                          "launches_timed": iters, "unique_leaves": U, "match_frac": match_frac},
             "stage_ms": stage,
+            "roofline_stages": {"note": "every stage of the step: algorithmic bytes (SURVEY 8d) / device time of the "
+                                        "instrumented pass / measured HBM peak; units: points inserted %.0f, leaves "
+                                        "touched %.0f, tree nodes under the window map %.0f, leaves subdivided %.0f per "
+                                        "scan" % (n_ins, u_ins, u_fit, n_split),
+                                "stages": roofline_stages,
+                                "whole_step": {"algorithmic_bytes": whole, "ms": 1e3 * t_res / K,
+                                               "achieved_GBs": whole / (t_res / K) / 1e9,
+                                               "frac": whole / (t_res / K) / 1e9 / hbm_peak}},
             "clocks": clocks,
         }
         if per_rank:

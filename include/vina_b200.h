@@ -205,6 +205,9 @@ int vina_map_insert(vina_ctx* ctx, int win_ord, const double R[9], const double 
 int vina_map_recut(vina_ctx* ctx, int win_count, const vina_pose* x_buf);
 int vina_map_margi(vina_ctx* ctx, int win_count, const vina_pose* x_buf);
 /* rotate the ring map mp[] after a marginalisation (local_mapping.cpp:521-526) */
+/* sizes of the last map update, for the measurement (bench.py): [0] points inserted, [1] leaves touched, [2..5]
+ * nodes under surf_map_slide per layer (as multi_recut listed them), [6] leaves subdivided. Synchronises. */
+int vina_map_last_counts(vina_ctx* ctx, int32_t out[8]);
 int vina_map_shift_window(vina_ctx* ctx);
 int64_t vina_map_count(vina_ctx* ctx, int64_t* n_roots, int64_t* n_slide);
 int64_t vina_map_export(vina_ctx* ctx, vina_node_record* out, int64_t cap);

@@ -58,7 +58,7 @@ NODE_DTYPE = np.dtype([
 
 # every symbol include/vina_b200.h declares
 EXPORTS = [
-    "vina_odom_cold_start", "vina_odom_init_scan",
+    "vina_odom_cold_start", "vina_odom_init_scan", "vina_map_last_counts",
     "vina_config_default", "vina_ctx_create", "vina_ctx_destroy", "vina_last_error", "vina_ctx_set_stream",
     "vina_ctx_sync", "vina_scan_upload", "vina_scan_upload_device", "vina_down_count", "vina_deskew", "vina_scan_download", "vina_downsample", "vina_down_upload",
     "vina_down_download", "vina_var_init", "vina_pvec_upload", "vina_pvec_download", "vina_iekf_begin",
@@ -517,6 +517,12 @@ class Ctx:
         a = np.ascontiguousarray(xyzt, dtype=np.float32)
         self._ck(self.lib.vina_odom_bootstrap(self.h, _fp(a), C.c_int(a.shape[0]), C.byref(state)))
         self.sync()
+
+    def map_last_counts(self):
+        """(points inserted, leaves touched, [nodes per layer under surf_map_slide], leaves subdivided) of the last update"""
+        a = (C.c_int32 * 8)()
+        self._ck(self.lib.vina_map_last_counts(self.h, a))
+        return a[0], a[1], [a[2], a[3], a[4], a[5]], a[6]
 
     def cold_start(self):
         """Start-up phase of the reference (VINA_SLAM::initialization): empty map, zero state, IMU not initialised."""

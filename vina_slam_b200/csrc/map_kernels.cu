@@ -492,7 +492,6 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
     KT();
     const int leaf = sc.touched[j];
     NodeCold& c = M.cold[leaf];
-    prefetch_cold(&c, lane, 32);
     const int cnt = c.pend_cnt;
     KT();
     int* idx = sc.idx + c.pend_off;

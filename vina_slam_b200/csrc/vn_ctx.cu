@@ -1149,6 +1149,27 @@ int vn_map_margi_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
   return VINA_OK;
 }
 
+// sizes of the last map update (bench.py: algorithmic bytes of the map stages): [0] points inserted, [1] leaves they
+// touched, [2..5] nodes under surf_map_slide per layer as multi_recut listed them, [6] leaves subdivided
+extern "C" int vina_map_last_counts(vina_ctx* ctx, int32_t out[8])
+{
+  if (!ctx || !out) return VINA_E_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  int c[4] = { 0, 0, 0, 0 }, l[8] = { 0 }, sc[2] = { 0, 0 };
+  CU(cudaMemcpy(c, ctx->ins.counters, sizeof(c), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(l, ctx->layers.count, sizeof(l), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(sc, ctx->map.slide_count, sizeof(sc), cudaMemcpyDeviceToHost));
+  out[0] = ctx->n_pv[1];
+  out[1] = c[1];
+  out[2] = sc[ctx->map.slide_cur];
+  out[3] = l[1];
+  out[4] = l[2];
+  out[5] = l[3];
+  out[6] = l[4];
+  out[7] = 0;
+  return VINA_OK;
+}
+
 extern "C" int vina_map_shift_window(vina_ctx* ctx)
 {
   if (!ctx) return VINA_E_ARG;

@@ -3,9 +3,10 @@ recorded or synthetic sequence through `vina_odom_step` and write the trajectory
 (`FileReaderWriter::save_pose_tum`, src/platform/ros2/io.cpp:67-77, written after every scan at
 local_mapping.cpp:429-430: `t x y z qx qy qz qw`, 9 decimals).
 
-The reference's own start-up (`initialization()`, src/pipeline/initialization.cpp) is not part of this library: the
-window is bootstrapped from `win_size` scans at known poses, which a recording has to provide (`boot_R`, `boot_p`,
-`boot_v`) - the synthetic generator does.
+Two ways to start: `--cold-start` runs the reference's own start-up phase (`initialization()`, node.cpp:293-366:
+IMU initialisation, kd-tree IEKF, motion_init with the gravity BA) on the first scans - nothing but scans and IMU
+samples is needed; without it the window is bootstrapped from `win_size` scans at known poses, which a recording
+then has to provide (`boot_R`, `boot_p`, `boot_v`) - the synthetic generator does.
 
     python -m vina_slam_b200.replay --workload mid360 --scans 50 --ba --out traj.txt
     python -m vina_slam_b200.replay --npz recording.npz --config robosense128 --out traj.txt
@@ -55,6 +56,12 @@ def synthetic_frames(cfg, n_scans: int, seed=None):
     boots = [seq.next_scan(deskewed=True) for _ in range(cfg.win_size)]
     scans = [seq.next_scan() for _ in range(n_scans)]
     return boots, scans
+
+
+def _undistorted_first(cfg, n_scans: int):
+    """A synthetic sequence for a cold start: every scan raw (distorted by the motion), none at a known state."""
+    seq = synth.Sequence(cfg)
+    return [seq.next_scan() for _ in range(n_scans)]
 
 
 def npz_frames(path: str, win_size: int):
@@ -198,6 +205,45 @@ def replay(cfg, boots, scans, out=None, ba=False, max_iter=4, caps=None, prune_h
     return np.array(rows), dt, worst
 
 
+def replay_cold_start(cfg, scans, out=None, ba=False, max_iter=4, caps=None, prune_horizon=700, max_init_scans=200):
+    """No known states at all: the reference's own start-up phase (VINA_SLAM::initialization, node.cpp:293-366) through
+    vina_odom_cold_start / vina_odom_init_scan - IMU initialisation, the kd-tree IEKF over win_size scans,
+    Initialization::motion_init (gravity BA, gravity alignment) - then the per-scan loop. The trajectory lives in the
+    gravity-aligned frame of the first window frame, like the reference's. Returns (rows, seconds per scan, scans the
+    start-up consumed)."""
+    caps = caps or dict(max_scan_points=max(300000, max(f.xyzt.shape[0] for f in scans) + 1024))
+    gx = capi.Ctx(cfg, **caps)
+    if ba:
+        gx.set_ba(True)
+    gx.cold_start()
+    rows, used, started = [], 0, False
+    fh = open(out, "w") if out else None
+    t0 = time.perf_counter()
+    for f in scans:
+        if not started:
+            st, s = gx.init_scan(f.xyzt, f.beg_time, f.imu)
+            used += 1
+            started = st == 1
+            if used > max_init_scans and not started:
+                raise RuntimeError(f"the start-up phase did not converge within {max_init_scans} scans")
+            if not started:
+                continue
+            s = capi.state_arrays(s)
+        else:
+            s = capi.state_arrays(gx.step(f.xyzt, f.beg_time, f.imu, True, max_iter))
+            if prune_horizon > 0:
+                gx.idle(prune_horizon)
+        rows.append(np.concatenate([[s["t"]], s["p"], quat_xyzw(s["R"])]))
+        if fh:
+            fh.write(tum_line(s["t"], s["p"], s["R"]))
+    gx.sync()
+    dt = (time.perf_counter() - t0) / max(len(scans), 1)
+    if fh:
+        fh.close()
+    gx.close()
+    return np.array(rows), dt, used
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--workload", default="robosense128", choices=sorted(synth.SENSORS), help="synthetic sensor shape")
@@ -208,12 +254,22 @@ def main(argv=None):
     ap.add_argument("--out", default=None, help="TUM trajectory file")
     ap.add_argument("--raw", action="store_true",
                     help="feed raw message streams: shuffled scans through vina_scan_prepare, pairing by vina_sync")
+    ap.add_argument("--cold-start", action="store_true",
+                    help="no bootstrap states: start with the reference's own initialisation (IMU init, kd-tree IEKF, "
+                         "motion_init) on the sequence's scans")
     ap.add_argument("--prune-horizon", type=int, default=700,
                     help="metres of travel after which unvisited root voxels are erased (reference: 700; 0 = never)")
     a = ap.parse_args(argv)
     cfg = synth.SENSORS[a.config or a.workload]
     boots, scans = npz_frames(a.npz, cfg.win_size) if a.npz else synthetic_frames(cfg, a.scans)
     st = {}
+    if a.cold_start:
+        rows, dt, used = replay_cold_start(cfg, boots + scans if a.npz else
+                                           [f for f in _undistorted_first(cfg, a.scans)], out=a.out, ba=a.ba,
+                                           prune_horizon=a.prune_horizon)
+        print(f"{len(rows)} poses after a start-up phase of {used} scans, {1e3 * dt:.3f} ms/scan (wall clock)"
+              + (f", trajectory -> {a.out}" if a.out else ""))
+        return 0
     if a.raw:
         rows, dt, worst = replay_stream(cfg, boots, scans, out=a.out, prune_horizon=a.prune_horizon)
     else:
