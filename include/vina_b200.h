@@ -484,6 +484,14 @@ int vina_set_profiling(vina_ctx* ctx, int on);
  * stream order with the host in between (the schedule the per-stage timers of vina_set_profiling see). Both give
  * bitwise the same states and maps. */
 int vina_set_overlap(vina_ctx* ctx, int on);
+/* the IEKF iteration loop of LioStateEstimation (odometry.cpp:98-231) inside vina_odom_step as ONE persistent
+ * cooperative launch (k_iekf_loop: scan resident in shared memory over the iterations, grid barrier and the a7
+ * update between them; the front of the step then goes out as two fused launches in stream order). Default off =
+ * one k_iekf launch per iteration with the update in its last block and the down-sampling on a side stream next to
+ * them: on B200 the persistent kernel shortens the loop by ~30 us per scan but fills every SM, so the side stream no
+ * longer overlaps and the whole step is ~5 % slower. Same associations either way; the sums
+ * agree to rounding (different, but fixed, summation order). Environment: VINA_IEKF_LOOP=1. */
+int vina_set_iekf_loop(vina_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

@@ -892,6 +892,55 @@ def test_overlapped_step_is_bitwise_the_serial_step(oracle_lib, gpu_lib):
         gx.close()
 
 
+def test_iekf_loop_kernel_matches_per_iteration_launches_and_the_oracle(oracle_lib, gpu_lib):
+    """vina_set_iekf_loop: the whole iteration loop of LioStateEstimation (odometry.cpp:98-231) as one persistent
+    cooperative launch (k_iekf_loop: scan in shared memory through 1-D TMA bulk copies, grid barrier + the update
+    between iterations, every block solving redundantly) with the two fused front launches, against the default
+    schedule (one k_iekf launch per iteration) and against the oracle: same iteration count on every scan, states within
+    1e-9 of each other (the sums are added in another fixed order) and within 1 mm / 0.01 deg of the oracle, the same
+    number of map nodes - over enough scans for the window to slide and leaves to split. The overlapped and the serial
+    step of the loop schedule must again be bitwise identical."""
+    cfg = small_cfg("robosense128", 32, 600)
+    seq = synth.Sequence(cfg)
+    od = oracle_lib.Odom(cfg)
+    ctxs = [gpu_lib.Ctx(cfg, **SMALL_CAPS) for _ in range(3)]
+    ctxs[0].set_iekf_loop(True)
+    ctxs[1].set_iekf_loop(False)
+    ctxs[2].set_iekf_loop(True)
+    ctxs[2].set_overlap(False)
+    for k in range(cfg.win_size):
+        sc = seq.next_scan(deskewed=True)
+        od.bootstrap(sc.xyzt, oracle_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        for gx in ctxs:
+            gx.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+    od.set_imu_anchor(sc.end_time, sc.imu[-1])
+    for gx in ctxs:
+        gx.set_imu_anchor(sc.end_time, sc.imu[-1])
+    for k in range(16):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        so = oracle_lib.state_arrays(od.get_state())
+        sa, sb, scx = [gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)) for gx in ctxs]
+        assert ctxs[0].timings().iekf_iters == ctxs[1].timings().iekf_iters == od.last_iters(), k
+        for f in ("R", "p", "v", "bg", "ba"):
+            assert np.max(np.abs(sa[f] - sb[f])) < 1e-9, (k, f)
+            assert np.array_equal(sa[f], scx[f]), (k, f)
+        assert np.max(np.abs(sa["cov"] - sb["cov"])) < 1e-9 * max(1.0, float(np.max(np.abs(sb["cov"]))))
+        assert np.array_equal(sa["cov"], scx["cov"]), k
+        assert np.linalg.norm(sa["p"] - so["p"]) < 1e-3
+        assert synth.rot_err_deg(sa["R"], so["R"]) < 0.01
+    for gx in ctxs:
+        gx.sync()
+    na, nb, nc = [gx.map_count()[0] for gx in ctxs]
+    assert na == nb == nc > 2000
+    ma, mc = sort_nodes(ctxs[0].map_export()), sort_nodes(ctxs[2].map_export())
+    for f in ma.dtype.names:
+        assert np.array_equal(ma[f], mc[f]), f
+    for gx in ctxs:
+        gx.close()
+
+
 def test_ba_lidar_factor_matches_oracle(oracle_lib, gpu_lib):
     """SURVEY section 8f rank 3, the data-parallel part of the sliding-window BA: the device factor store
     (tras_opt) and LidarFactor::acc_evaluate2 / evaluate_only_residual (factors.cpp:22-158) against the oracle,

@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "libvina_b200.so")
 OBJ = os.path.join(HERE, "_build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = (["-DVINA_SPLIT_TRACE"] if os.environ.get("VINA_SPLIT_TRACE") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function,-Wno-unknown-pragmas",
+COMMON = (["-DVINA_SPLIT_TRACE"] if os.environ.get("VINA_SPLIT_TRACE") else []) + (["-DVINA_LOOP_TRACE"] if os.environ.get("VINA_LOOP_TRACE") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function,-Wno-unknown-pragmas",
           "-I", os.path.join(HERE, "..", "include")]
 
 UNITS = [

@@ -29,6 +29,7 @@
 // bit-exact against the CPU restatement. sigma_l and the sums use FMA freely (tolerance 1e-4 rel):
 // n^T var_world n is evaluated as (R^T n)^T var (R^T n) + (n x p)^T S_R (n x p) + n^T S_t n, which needs ~1/4
 // of the flops of forming var_world.
+#include <cstdio>
 #include "vn_kernels.cuh"
 
 #ifndef IEKF_THREADS
@@ -105,23 +106,6 @@ __device__ __forceinline__ void warp_inverse6(double (&c)[6], int lane)
   }
 }
 
-// Exp(ang), include/vina_slam/core/math.hpp:12-24
-__device__ void so3_exp(const double* a, double* E)
-{
-  for (int i = 0; i < 9; i++) E[i] = 0;
-  E[0] = E[4] = E[8] = 1;
-  const double nrm = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-  if (nrm >= 1e-9)
-  {
-    const double ax[3] = { a[0] / nrm, a[1] / nrm, a[2] / nrm };
-    double K[9], sK[9], KK[9];
-    hat3(ax, K);
-    const double s = sin(nrm), c1 = 1.0 - cos(nrm);
-    for (int i = 0; i < 9; i++) sK[i] = c1 * K[i];
-    mat3_mul(sK, K, KK);
-    for (int i = 0; i < 9; i++) E[i] = (E[i] + s * K[i]) + KK[i];
-  }
-}
 // Log(R), math.hpp:43-48
 __device__ void so3_log(const double* R, double* w)
 {
@@ -132,161 +116,223 @@ __device__ void so3_log(const double* R, double* w)
   for (int i = 0; i < 3; i++) w[i] = f * K[i];
 }
 
-// The update of one iteration (odometry.cpp:192-230, types.hpp:67-86). fin = the 34 packed sums, ws = >= 376
-// doubles of scratch, cov = the 15x15 prior covariance (replaced by the posterior when the loop ends), st = the
-// first 42 doubles of IekfDev (x_curr: R p v bg ba, then x_prop) - all in SHARED memory, staged and written
-// back by the whole block, so that this single warp never waits on a global load. Returns (to lane 0's
-// callers via ws) whether the loop is finished.
-__device__ __noinline__ void iekf_solve_warp(IekfDev* dev, const double* fin, double* ws, double* cov, double* st,
-                                             int lane)
+// The update of one iteration (odometry.cpp:192-230, types.hpp:67-86), by a whole thread block. fin = the 34
+// packed sums, ws = IEKF_SOLVE_WS doubles of scratch, cov = the 15x15 prior covariance (replaced by the posterior
+// when the loop ends), st = the first 42 doubles of IekfDev (x_curr: R p v bg ba, then x_prop), ctl = {iter, rematch,
+// done, max_iter} - all in SHARED memory, so that nothing here waits on a global load. Every thread of the block
+// calls it (it synchronises the block); needs >= 64 threads.
+//
+// A single warp walking through this took ~20 us per iteration on B200 (dependent fp64 operations cost 23-33 cycles
+// each there, a division 123, and sin / cos / acos are long chains of them) - more than the point loop it follows.
+// So the independent parts run side by side and the products are re-associated around the 6x6 core:
+//   T = (I6 + H P66)^-1                              warp 0, Gauss-Jordan        | vec = x_prop (-) x_curr   warp 1
+//   TH = T H (36 threads),  w = T HTz (6 threads)
+//   u = w - TH vec(0:6)                              6 threads
+//   solution = P(:, 0:6) u + vec  (15 threads)       = K HTz + vec - G vec(0:6) with K = P(:,0:6) T, G = K H
+//   G(:, 0:6) = P(:, 0:6) TH      (90 threads, next to the solution)
+//   x_curr (+)= solution: Exp() with sin, 1 - cos and the axis on different lanes | P - G P(0:6, :) into a spare
+//   buffer (225 threads), committed only if this iteration ends the loop
+#define IEKF_SOLVE_WS 536
+__device__ __forceinline__ void iekf_solve_cta(int* ctl, const double* fin, double* ws, double* cov, double* st, int tid,
+                                               int nthreads)
 {
-  double* HTH = ws;        // 6x6 column-major (symmetric)
-  double* HTz = ws + 36;   // 6
-  double* K6 = ws + 48;    // K1(:, 0:6), 15x6 column-major
-  double* G6 = ws + 144;   // G(:, 0:6)
-  double* vec = ws + 240;  // x_prop (-) x_curr
-  double* sol = ws + 256;
-  double* C6 = ws + 272;   // rows 0..5 of the prior covariance, 6x15 (row a, column j at a + 6 j)
-  int* flg = reinterpret_cast<int*>(ws + 368);
-  double *R = st, *p = st + 9, *v = st + 12, *bg = st + 15, *ba = st + 18;
-  const double *Rp = st + 21, *pp = st + 30, *vp = st + 33, *bgp = st + 36, *bap = st + 39;
-  const int iter = dev->iter, max_iter = dev->max_iter;
+  double* HTH = ws;         // 6x6 column-major (symmetric)
+  double* HTz = ws + 36;    // 6
+  double* T6 = ws + 48;     // (I + H P66)^-1, column-major
+  double* TH = ws + 96;     // T H, column-major
+  double* wv = ws + 132;    // T HTz
+  double* uv = ws + 138;    // w - TH vec(0:6)
+  double* vec = ws + 144;   // x_prop (-) x_curr (15)
+  double* sol = ws + 160;   // (15)
+  double* G6 = ws + 176;    // G(:, 0:6), 15x6 column-major
+  double* covn = ws + 272;  // candidate posterior (225)
+  double* M9 = ws + 500;    // R^T Rp, later Exp(solution(0:3))
+  double* tmp = ws + 512;   // hat(axis) (9)
+  int* flg = reinterpret_cast<int*>(ws + 528);
+  double *R = st, *p = st + 9;
+  const double* Rp = st + 21;
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned int F = 0xffffffffu;
 
+  // ---- phase 0: unpack the sums; M = R^T Rp
+  if (tid < 36)
   {
-    int t = 0;
-    for (int a = 0; a < 6; a++)
-      for (int b = a; b < 6; b++, t++)
-        if (lane == 0)
-        {
-          HTH[a + 6 * b] = fin[t];
-          HTH[b + 6 * a] = fin[t];
-        }
-    if (lane < 6) HTz[lane] = fin[21 + lane];
+    const int i = tid % 6, j = tid / 6;
+    const int a_ = i < j ? i : j, b_ = i < j ? j : i;
+    HTH[tid] = fin[a_ * 6 - (a_ * (a_ - 1)) / 2 + (b_ - a_)];
   }
-  __syncwarp();
-  // T = (I6 + H P66)^-1; K6 = P(:, 0:6) T
-  double c[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++)
+  else if (tid < 42)
+    HTz[tid - 36] = fin[21 + (tid - 36)];
+  else if (tid >= 64 - 9 && tid < 64)
   {
-    double x = (lane - 6 == i) ? 1.0 : 0.0;
-    if (lane < 6)
+    const int e = tid - (64 - 9), i = e % 3, j = e / 3;  // M(i, j) = sum_k R(k, i) Rp(k, j)
+    M9[e] = da(da(dm(R[3 * i], Rp[3 * j]), dm(R[3 * i + 1], Rp[3 * j + 1])), dm(R[3 * i + 2], Rp[3 * j + 2]));
+  }
+  __syncthreads();
+  // ---- phase 1: warp 0 inverts, warp 1 forms x_prop (-) x_curr (types.hpp:77-86)
+  if (warp == 0)
+  {
+    // lane j < 6 holds column j of I6 + H P66, lanes 6..11 the columns of the identity
+    double c[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
     {
-      x = (lane == i) ? 1.0 : 0.0;
+      double x = (lane - 6 == i) ? 1.0 : 0.0;
+      if (lane < 6)
+      {
+        x = (lane == i) ? 1.0 : 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; k++) x = fma(HTH[i + 6 * k], cov[k + 15 * lane], x);
+        for (int k = 0; k < 6; k++) x = fma(HTH[i + 6 * k], cov[k + 15 * lane], x);
+      }
+      c[i] = x;
     }
-    c[i] = x;
-  }
-  warp_inverse6(c, lane);
-  double* T6 = C6;  // scratch until the final covariance update
-  if (lane >= 6 && lane < 12)
+    warp_inverse6(c, lane);
+    if (lane >= 6 && lane < 12)
 #pragma unroll
-    for (int i = 0; i < 6; i++) T6[i + 6 * (lane - 6)] = c[i];
-  __syncwarp();
-  for (int e = lane; e < 90; e += 32)
-  {
-    const int i = e % 15, a = e / 15;
-    double s = 0.0;
-#pragma unroll
-    for (int b = 0; b < 6; b++) s = fma(cov[i + 15 * b], T6[b + 6 * a], s);
-    K6[e] = s;
+      for (int i = 0; i < 6; i++) T6[i + 6 * (lane - 6)] = c[i];
   }
-  // vec = x_prop (-) x_curr (types.hpp:77-86)
-  if (lane == 0)
+  else if (warp == 1)
   {
-    double Rt[9], M[9];
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) Rt[j + 3 * i] = R[i + 3 * j];
-    mat3_mul(Rt, Rp, M);
-    so3_log(M, vec);
-    for (int k = 0; k < 3; k++)
+    if (lane == 0) so3_log(M9, vec);
+    if (lane >= 3 && lane < 15) vec[lane] = st[21 + 6 + lane] - st[6 + lane];  // p, v, bg, ba: x_prop - x_curr
+  }
+  __syncthreads();
+  // ---- phase 2: TH = T H, w = T HTz
+  if (tid < 36)
+  {
+    const int a_ = tid % 6, b_ = tid / 6;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v = fma(T6[a_ + 6 * k], HTH[k + 6 * b_], v);
+    TH[tid] = v;
+  }
+  else if (tid < 42)
+  {
+    const int a_ = tid - 36;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v = fma(T6[a_ + 6 * k], HTz[k], v);
+    wv[a_] = v;
+  }
+  __syncthreads();
+  // ---- phase 3: u = w - TH vec(0:6)
+  if (tid < 6)
+  {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v = fma(TH[tid + 6 * k], vec[k], v);
+    uv[tid] = wv[tid] - v;
+  }
+  __syncthreads();
+  // ---- phase 4: solution = P(:, 0:6) u + vec;  G(:, 0:6) = P(:, 0:6) TH
+  if (tid < 15)
+  {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v = fma(cov[tid + 15 * k], uv[k], v);
+    sol[tid] = v + vec[tid];
+  }
+  else if (tid >= 32 && tid < 32 + 90)
+  {
+    const int e = tid - 32, i = e % 15, b_ = e / 15;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v = fma(cov[i + 15 * k], TH[k + 6 * b_], v);
+    G6[e] = v;
+  }
+  __syncthreads();
+  // ---- phase 5: x_curr (+)= solution (types.hpp:67-75, math.hpp:12-24) on warp 0; the candidate posterior
+  // P - G P(0:6, :) (odometry.cpp:223: only the first 6 columns of G are non-zero) on the other warps
+  if (warp == 0)
+  {
+    const double s0 = sol[0], s1 = sol[1], s2 = sol[2];
+    const double nrm = sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+    double val = 0.0;
+    if (lane == 0) val = sin(nrm);
+    if (lane == 1) val = 1.0 - cos(nrm);
+    if (lane >= 2 && lane < 5) val = sol[lane - 2] / nrm;
+    if (lane == 5) val = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
+    const double sn = __shfl_sync(F, val, 0), c1 = __shfl_sync(F, val, 1);
+    const double ax[3] = { __shfl_sync(F, val, 2), __shfl_sync(F, val, 3), __shfl_sync(F, val, 4) };
+    const double nt = __shfl_sync(F, val, 5);
+    // E = I + sin K + (1 - cos) K K, K = hat(axis); lane e < 9 owns E(i, j)
+    double Ee = 0.0;
+    double* K = tmp;  // hat(axis), column-major, in shared memory (indexed by row / column below)
+    if (lane < 9)
     {
-      vec[3 + k] = pp[k] - p[k];
-      vec[6 + k] = vp[k] - v[k];
-      vec[9 + k] = bgp[k] - bg[k];
-      vec[12 + k] = bap[k] - ba[k];
+      const double kv = lane == 1 ? ax[2] : lane == 2 ? -ax[1] : lane == 3 ? -ax[2] : lane == 5 ? ax[0] : lane == 6 ? ax[1]
+                                                                                                      : lane == 7 ? -ax[0] : 0.0;
+      K[lane] = kv;
     }
-  }
-  __syncwarp();
-  // G(:, 0:6) = K1(:, 0:6) * HTH
-  for (int e = lane; e < 90; e += 32)
-  {
-    const int i = e % 15, b = e / 15;
-    double s = 0.0;
-#pragma unroll
-    for (int a = 0; a < 6; a++) s = fma(K6[i + 15 * a], HTH[a + 6 * b], s);
-    G6[e] = s;
-  }
-  __syncwarp();
-  // solution = K1(:, 0:6) HTz + vec - G(:, 0:6) vec(0:6)
-  if (lane < 15)
-  {
-    double a = 0.0, b = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; k++)
-    {
-      a = fma(K6[lane + 15 * k], HTz[k], a);
-      b = fma(G6[lane + 15 * k], vec[k], b);
-    }
-    sol[lane] = (a + vec[lane]) - b;
-  }
-  __syncwarp();
-  if (lane == 0)
-  {
-    // x_curr (+)= solution (types.hpp:67-75)
-    double E[9], Rn[9];
-    so3_exp(sol, E);
-    mat3_mul(R, E, Rn);
-    for (int i = 0; i < 9; i++) R[i] = Rn[i];
-    for (int k = 0; k < 3; k++)
-    {
-      p[k] += sol[3 + k];
-      v[k] += sol[6 + k];
-      bg[k] += sol[9 + k];
-      ba[k] += sol[12 + k];
-    }
-    const double nr = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
-    const double nt = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
-    const bool conv = (nr * 57.3 < 0.01) && (nt * 100 < 0.015);
-    int rematch = dev->rematch;
-    if (conv || (rematch == 0 && iter == max_iter - 2)) rematch++;
-    const int fin_it = (rematch >= 2 || iter == max_iter - 1) ? 1 : 0;
-    dev->rematch = rematch;
-    dev->iter = iter + 1;
-    dev->done = fin_it;
-    flg[0] = fin_it;
-  }
-  __syncwarp();
-  if (flg[0])
-  {
-    // cov = (I - G) cov; only the first 6 columns of G are non-zero (odometry.cpp:223)
-    for (int e = lane; e < 90; e += 32) C6[e] = cov[(e % 6) + 15 * (e / 6)];
     __syncwarp();
-    for (int e = lane; e < 225; e += 32)
+    if (lane < 9)
+    {
+      const int i = lane % 3, j = lane / 3;
+      double kk = 0.0;
+      if (nrm >= 1e-9)
+      {
+        kk = da(da(dm(c1 * K[i], K[3 * j]), dm(c1 * K[i + 3], K[3 * j + 1])), dm(c1 * K[i + 6], K[3 * j + 2]));
+        Ee = ((i == j ? 1.0 : 0.0) + sn * K[lane]) + kk;
+      }
+      else
+        Ee = (i == j) ? 1.0 : 0.0;
+      M9[lane] = Ee;
+    }
+    __syncwarp();
+    double Rn = 0.0;
+    if (lane < 9)
+    {
+      const int i = lane % 3, j = lane / 3;
+      Rn = da(da(dm(R[i], M9[3 * j]), dm(R[i + 3], M9[3 * j + 1])), dm(R[i + 6], M9[3 * j + 2]));
+    }
+    __syncwarp();
+    if (lane < 9) R[lane] = Rn;
+    if (lane >= 9 && lane < 21) p[lane - 9] += sol[3 + (lane - 9)];  // p, v, bg, ba are contiguous behind R
+    if (lane == 0)
+    {
+      const int iter = ctl[0], max_iter = ctl[3];
+      const bool conv = (nrm * 57.3 < 0.01) && (nt * 100 < 0.015);
+      int rematch = ctl[1];
+      if (conv || (rematch == 0 && iter == max_iter - 2)) rematch++;
+      const int fin_it = (rematch >= 2 || iter == max_iter - 1) ? 1 : 0;
+      ctl[1] = rematch;
+      ctl[0] = iter + 1;
+      ctl[2] = fin_it;
+      flg[0] = fin_it;
+    }
+  }
+  else
+  {
+    for (int e = tid - 32; e < 225; e += nthreads - 32)
     {
       const int i = e % 15, j = e / 15;
-      double s = 0.0;
+      double v = 0.0;
 #pragma unroll
-      for (int a = 0; a < 6; a++) s = fma(G6[i + 15 * a], C6[a + 6 * j], s);
-      cov[e] = cov[e] - s;
+      for (int k = 0; k < 6; k++) v = fma(G6[i + 15 * k], cov[k + 15 * j], v);
+      covn[e] = cov[e] - v;
     }
   }
+  __syncthreads();
+  if (flg[0])
+    for (int e = tid; e < 225; e += nthreads) cov[e] = covn[e];
+  __syncthreads();
 }
 
-// a7 with a whole block: stage the iterate in shared memory (`smem` >= 660 doubles), let warp 0 solve, write back
+// a7 with a whole block: stage the iterate in shared memory (`smem` >= IEKF_SOLVE_WS + 280 doubles), solve, write back
 __device__ __forceinline__ void iekf_solve_block(IekfDev* dev, const double* fin, double* smem, int nthreads)
 {
   double* ws = smem;
-  double* s_cov = smem + 384;
-  double* s_st = smem + 384 + 232;
+  double* s_cov = smem + IEKF_SOLVE_WS;
+  double* s_st = smem + IEKF_SOLVE_WS + 232;
+  int* s_ctl = reinterpret_cast<int*>(smem + IEKF_SOLVE_WS + 232 + 42);
   for (int i = threadIdx.x; i < 225; i += nthreads) s_cov[i] = dev->cov[i];
   if (threadIdx.x < 42) s_st[threadIdx.x] = reinterpret_cast<const double*>(dev)[threadIdx.x];
+  if (threadIdx.x >= 64 && threadIdx.x < 68) s_ctl[threadIdx.x - 64] = (&dev->iter)[threadIdx.x - 64];
   __syncthreads();
-  if (threadIdx.x < 32) iekf_solve_warp(dev, fin, ws, s_cov, s_st, threadIdx.x);
-  __syncthreads();
+  iekf_solve_cta(s_ctl, fin, ws, s_cov, s_st, threadIdx.x, nthreads);
   if (threadIdx.x < 21) reinterpret_cast<double*>(dev)[threadIdx.x] = s_st[threadIdx.x];
-  if (reinterpret_cast<const int*>(ws + 368)[0])
+  if (threadIdx.x >= 64 && threadIdx.x < 67) (&dev->iter)[threadIdx.x - 64] = s_ctl[threadIdx.x - 64];
+  if (reinterpret_cast<const int*>(ws + 528)[0])
     for (int i = threadIdx.x; i < 225; i += nthreads) dev->cov[i] = s_cov[i];
 }
 
@@ -599,7 +645,7 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
   if (bt.mode & VN_IEKF_SOLVE)
   {
     iekf_solve_block(dev, fin, smem, IEKF_THREADS);
-    if ((bt.mode & VN_IEKF_HANDOVER) && reinterpret_cast<const int*>(smem + 368)[0])
+    if ((bt.mode & VN_IEKF_HANDOVER) && reinterpret_cast<const int*>(smem + 528)[0])
     {
       // the loop has just finished: hand the iterate to the host (data, system-wide fence, then the flag)
       __syncthreads();
@@ -624,6 +670,507 @@ __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const
     __syncthreads();
     if (threadIdx.x == 0) reinterpret_cast<volatile unsigned long long*>(q.result)[40] = q.seq;
   }
+}
+
+// ---------------------------------------------------------------------------
+// The whole iteration loop of LioStateEstimation (odometry.cpp:98-231) as ONE persistent launch (the default
+// per-scan path). What changes against max_iter launches of k_iekf:
+//   * the scan stays on chip: every block owns a contiguous chunk of the scan and pulls its 9 pointVar rows into
+//     shared memory once, with 1-D TMA bulk copies (cp.async.bulk -> mbarrier, one barrier per round so that round 0
+//     starts while round 1 is still in flight); iterations 1.. read the points from shared memory, and the per-point
+//     leaf cache (odometry.cpp:79, 124-127) lives there too - after iteration 0 the only global traffic is the
+//     gather of the cached leaves' records (L2);
+//   * no launch per iteration: blocks meet at a grid barrier (arrival counter in global memory, cooperative launch
+//     guarantees co-residency), then EVERY block adds the per-block partial sums in the same fixed order and
+//     applies the update (a7) to its own shared-memory copy of the iterate - bitwise the same everywhere, so all
+//     blocks take the same convergence decision and go straight on: one barrier per iteration, no broadcast;
+//   * a cached leaf's two record lines are requested together (one L2 latency instead of two), the DMMA
+//     reduction runs two independent accumulator chains, and the staging tile holds b = [j, r] and 1/(0.0005 +
+//     sigma) once (the a-operand Rinv*j is formed in the fragment load: the same single product as before).
+// Rounds beyond the resident store (scans larger than LOOP_RS * LOOP_T * gridDim.x points) stream from global
+// memory with the global leaf cache, like k_iekf.
+#define LOOP_T 832   // 26 warps: two rounds cover 240 000 points on 148 SMs
+#define LOOP_RS 2    // resident rounds
+#define LOOP_WARPS (LOOP_T / 32)
+#define LOOP_ROWS 8  // j0..j5, r, Rinv
+#define LOOP_TILE (LOOP_ROWS * IEKF_LD)
+#define LOOP_SMEM ((size_t)(LOOP_RS * 9 * LOOP_T + LOOP_WARPS * LOOP_TILE) * sizeof(double) + (size_t)LOOP_RS * LOOP_T * sizeof(int))
+#define LOOP_SPIN_LIMIT (1ll << 24)
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned int bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* b)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned int parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LOOP_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LOOP_MBAR_DONE;\n"
+      "bra LOOP_MBAR_WAIT;\n"
+      "LOOP_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+#ifdef VINA_LOOP_TRACE
+#define LT(k) \
+  if (tid == 0 && tr_n < 64) tr[tr_n++] = (((unsigned long long)(k)) << 56) | (gtimer() & 0xffffffffffffffull)
+__device__ __forceinline__ unsigned long long gtimer()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#else
+#define LT(k)
+#endif
+
+__global__ void __launch_bounds__(LOOP_T, 1) k_iekf_loop(const __grid_constant__ IekfLoop a)
+{
+#ifdef VINA_LOOP_TRACE
+  unsigned long long tr[64];
+  int tr_n = 0;
+#endif
+  const IekfSeq& q = a.q;
+  IekfDev* __restrict__ dev = q.dev;
+  extern __shared__ __align__(128) double smem[];
+  double* S = smem;                                   // [LOOP_RS][9][LOOP_T] resident pointVar rows
+  double* tiles = smem + LOOP_RS * 9 * LOOP_T;        // [LOOP_WARPS][LOOP_TILE] staging; the solve's scratch afterwards
+  int* scache = reinterpret_cast<int*>(tiles + LOOP_WARPS * LOOP_TILE);  // [LOOP_RS][LOOP_T] leaf cache
+  __shared__ double s_st[42];    // x_curr (R p v bg ba), x_prop: the block's own copy of the iterate
+  __shared__ double s_cov[232];  // prior covariance (posterior once the loop ends)
+  __shared__ double crv[9], ctv[9];
+  __shared__ double fin[VN_IEKF_NACC];
+  __shared__ int ctl[4];  // iter, rematch, done, max_iter
+  __shared__ __align__(8) unsigned long long mbar[LOOP_RS];
+  __shared__ int s_abort;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  LT(0);
+  const int nblk = gridDim.x;
+  const int n = q.n_ptr ? *q.n_ptr : q.n_host;
+  const int blk_base = blockIdx.x * a.chunk;
+  const int blk_end = min(n, blk_base + a.chunk);
+  const int blk_cnt = max(0, blk_end - blk_base);
+  const int nrounds = (blk_cnt + LOOP_T - 1) / LOOP_T;
+  const double* __restrict__ pv = q.pv_base;
+  const size_t pvs = (size_t)q.pv_stride;
+  const NodeHot* __restrict__ hot = q.hot;
+  int* __restrict__ gcache = q.cache;
+
+  if (tid == 0)
+  {
+    for (int r = 0; r < LOOP_RS; r++) mbar_init(&mbar[r], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_abort = 0;
+    // the block's chunk, 9 rows per round, straight into shared memory (in flight while the iterate is staged)
+    for (int r = 0; r < LOOP_RS; r++)
+    {
+      const int first = blk_base + r * LOOP_T;
+      int cnt = min(LOOP_T, blk_end - first);
+      if (cnt <= 0) break;
+      cnt = (cnt + 1) & ~1;  // 16-byte granules (the row pitch is even and the chunk a multiple of 32)
+      mbar_expect_tx(&mbar[r], 9u * (unsigned int)cnt * 8u);
+      for (int k = 0; k < 9; k++) bulk_g2s(S + (r * 9 + k) * LOOP_T, pv + (size_t)k * pvs + first, (unsigned int)cnt * 8u, &mbar[r]);
+    }
+  }
+  for (int i = tid; i < 225; i += LOOP_T) s_cov[i] = dev->cov[i];
+  if (tid < 42) s_st[tid] = reinterpret_cast<const double*>(dev)[tid];
+  if (tid < 9)
+  {
+    crv[tid] = dev->rot_var[tid];
+    ctv[tid] = dev->tsl_var[tid];
+  }
+  if (tid < 4) ctl[tid] = (&dev->iter)[tid];
+  for (int i = tid; i < LOOP_RS * LOOP_T; i += LOOP_T) scache[i] = -1;  // octos(psize, nullptr), odometry.cpp:79
+  __syncthreads();
+  // (the host stages an unfinished iterate before every launch: iekf_stage)
+
+  double* Sw = tiles + warp * LOOP_TILE;
+  const int g = lane >> 2, t4 = lane & 3;
+  const double* fa = Sw + (g < 6 ? g : g - 3) * IEKF_LD + t4;  // a = [Rinv j0..j5, n0 (= j3), n1 (= j4)]
+  const double* fr = Sw + 7 * IEKF_LD + t4;                    // Rinv per point
+  const double* fb = Sw + (g < 7 ? g : 0) * IEKF_LD + t4;      // b = [j0..j5, r, 0]
+  int par = 0;
+  bool first_iter = true;
+
+  for (int it_local = 0;; it_local++)
+  {
+    const double* cR = s_st;
+    const double* cp = s_st + 9;
+    LT(1);
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0, s22 = 0.0;
+    int cnt = 0;
+    for (int r = 0; r < nrounds; r++)
+    {
+      const bool res = r < LOOP_RS;
+      const int off = r * LOOP_T + tid;
+      const int idx = blk_base + off;
+      const bool live = off < blk_cnt;
+      if (res && first_iter) mbar_wait(&mbar[r], 0);
+      const double* sp = S + (r * 9) * LOOP_T + tid;
+      const double* gp = pv + (live ? idx : 0);
+      int flag = 0;
+      double st_j0 = 0, st_j1 = 0, st_j2 = 0, st_n0 = 0, st_n1 = 0, st_n2 = 0, st_r = 0, st_w = 0;
+      if (live)
+      {
+        double pnt[3];
+        if (res)
+        {
+          pnt[0] = sp[0];
+          pnt[1] = sp[LOOP_T];
+          pnt[2] = sp[2 * LOOP_T];
+        }
+        else
+        {
+          pnt[0] = __ldg(gp);
+          pnt[1] = __ldg(gp + pvs);
+          pnt[2] = __ldg(gp + 2 * pvs);
+        }
+        const int cached = res ? scache[off] : gcache[idx];
+        double wld[3];
+        rot_trans(cR, cp, pnt, wld);
+        int node = -1;
+        bool have = false;
+        double2 l0, l1, l2, l8, l9, l10, l11;
+        double qb2 = 0.0, qk = 0.0;
+        float radius = 0.0f;
+        if (cached >= 0)
+        {
+          // cached leaf (odometry.cpp:124-127): a plane leaf that passed the gate before; both lines of its record
+          // are requested at once
+          const double2* L = reinterpret_cast<const double2*>(hot + cached);
+          const double2 l3 = __ldg(L + 3), l4 = __ldg(L + 4);
+          l0 = __ldg(L + 0);
+          l1 = __ldg(L + 1);
+          l2 = __ldg(L + 2);
+          l8 = __ldg(L + 8);
+          l9 = __ldg(L + 9);
+          l10 = __ldg(L + 10);
+          l11 = __ldg(L + 11);
+          qb2 = __ldg(reinterpret_cast<const double*>(L + 12));
+          qk = __ldg(reinterpret_cast<const double*>(L + 7) + 1);
+          const double vc[3] = { l3.x, l3.y, l4.x };
+          const float2 rq = *reinterpret_cast<const float2*>(&l4.y);  // (radius, quater_length)
+          if (inside_box(wld, vc, rq.y))
+          {
+            node = cached;
+            radius = rq.x;
+            have = true;
+          }
+        }
+        if (!have)
+        {
+          long long kc[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) kc[k] = voxel_coord(wld[k], q.voxel_size);
+          unsigned long long key;
+          node = -1;
+          if (pack_key(kc[0], kc[1], kc[2], &key))
+          {
+            unsigned int hh = hash_key(key) & q.hmask;
+            for (unsigned int probe = 0; probe <= q.hmask; probe++)
+            {
+              const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2*>(q.slots + hh));
+              if (s.x == key)
+              {
+                node = (int)(unsigned int)(s.y & 0xffffffffull);
+                break;
+              }
+              if (s.x == VN_EMPTY_KEY) break;
+              hh = (hh + 1) & q.hmask;
+            }
+          }
+          int flags = 0;
+          while (node >= 0)  // descend to the leaf (octree.cpp:584-591): one line per level
+          {
+            const NodeHot* h = hot + node;
+            flags = h->flags;
+            if (!(flags & VN_FLAG_INTERIOR)) break;
+            const double vc[3] = { h->vcenter[0], h->vcenter[1], h->vcenter[2] };
+            node = h->children[child_index(wld, vc)];
+          }
+          if (node >= 0 && (flags & VN_FLAG_PLANE))
+          {
+            const double2* L = reinterpret_cast<const double2*>(hot + node);
+            l0 = __ldg(L + 0);
+            l1 = __ldg(L + 1);
+            l2 = __ldg(L + 2);
+            l8 = __ldg(L + 8);
+            l9 = __ldg(L + 9);
+            l10 = __ldg(L + 10);
+            l11 = __ldg(L + 11);
+            qb2 = __ldg(reinterpret_cast<const double*>(L + 12));
+            qk = __ldg(reinterpret_cast<const double*>(L + 7) + 1);
+            radius = hot[node].radius;
+            have = true;
+          }
+        }
+        if (have)
+        {
+          const double c[3] = { l0.x, l0.y, l1.x };
+          const double nr[3] = { l1.y, l2.x, l2.y };
+          const double d[3] = { ds(wld[0], c[0]), ds(wld[1], c[1]), ds(wld[2], c[2]) };
+          const double dn = dot3(nr, d);
+          const float dis_to_plane = (float)fabs(dn);
+          const double e[3] = { ds(c[0], wld[0]), ds(c[1], wld[1]), ds(c[2], wld[2]) };
+          const float dis_to_center = (float)dot3(e, e);
+          const float range_dis = fs(dis_to_center, fm(dis_to_plane, dis_to_plane));
+          if (range_dis <= fm(9.0f, radius))
+          {
+            // sigma_l = J plane_var J^T, J = [wld - center, -normal] = d^T A d - 2 d.(B n) + n^T C n (NodeHot, line 1)
+            const double A0 = l8.x, A1 = l8.y, A2 = l9.x, A3 = l9.y, A4 = l10.x, A5 = l10.y;
+            const double dAd = d[0] * (A0 * d[0] + 2.0 * (A1 * d[1] + A2 * d[2])) + d[1] * (A3 * d[1] + 2.0 * A4 * d[2]) +
+                               d[2] * A5 * d[2];
+            double sigma_l = dAd - 2.0 * (d[0] * l11.x + d[1] * l11.y + d[2] * qb2) + qk;
+            // + n^T var_world n
+            double var6[6];
+            if (res)
+            {
+#pragma unroll
+              for (int k = 0; k < 6; k++) var6[k] = sp[(3 + k) * LOOP_T];
+            }
+            else
+            {
+#pragma unroll
+              for (int k = 0; k < 6; k++) var6[k] = __ldg(gp + (3 + k) * pvs);
+            }
+            double m[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) m[k] = cR[3 * k] * nr[0] + cR[3 * k + 1] * nr[1] + cR[3 * k + 2] * nr[2];
+            const double q1 = m[0] * (var6[0] * m[0] + 2.0 * (var6[1] * m[1] + var6[2] * m[2])) +
+                              m[1] * (var6[3] * m[1] + 2.0 * var6[4] * m[2]) + m[2] * var6[5] * m[2];
+            const double u[3] = { nr[1] * pnt[2] - nr[2] * pnt[1], nr[2] * pnt[0] - nr[0] * pnt[2],
+                                  nr[0] * pnt[1] - nr[1] * pnt[0] };  // hat(p)^T n = n x p
+            double q2 = 0.0, q3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+              q2 += u[k] * (crv[k] * u[0] + crv[k + 3] * u[1] + crv[k + 6] * u[2]);
+              q3 += nr[k] * (ctv[k] * nr[0] + ctv[k + 3] * nr[1] + ctv[k + 6] * nr[2]);
+            }
+            sigma_l += q1 + q2 + q3;
+            // dis_to_plane < 3 sqrt(sigma_l)  <=>  dis_to_plane^2 < 9 sigma_l (the fp32 value squares exactly in fp64)
+            if ((double)dis_to_plane * (double)dis_to_plane < 9.0 * sigma_l)
+            {
+              flag = 1;
+              if (node != cached)  // oc = this (octree.cpp:571-575)
+              {
+                if (res)
+                  scache[off] = node;
+                else
+                  gcache[idx] = node;
+              }
+              st_w = 1.0 / (0.0005 + sigma_l);
+              // jac = [hat(p) R^T n ; n] = [p x m ; n]
+              st_j0 = pnt[1] * m[2] - pnt[2] * m[1];
+              st_j1 = pnt[2] * m[0] - pnt[0] * m[2];
+              st_j2 = pnt[0] * m[1] - pnt[1] * m[0];
+              st_n0 = nr[0];
+              st_n1 = nr[1];
+              st_n2 = nr[2];
+              st_r = dn;
+              s22 = fma(nr[2], nr[2], s22);
+              cnt++;
+            }
+          }
+        }
+      }
+      // the warp's 32 (a, b) pairs go through the FP64 tensor pipe; a point without a match contributes zeros
+      __syncwarp();  // the previous round's fragment loads are done
+      Sw[0 * IEKF_LD + lane] = st_j0;
+      Sw[1 * IEKF_LD + lane] = st_j1;
+      Sw[2 * IEKF_LD + lane] = st_j2;
+      Sw[3 * IEKF_LD + lane] = st_n0;
+      Sw[4 * IEKF_LD + lane] = st_n1;
+      Sw[5 * IEKF_LD + lane] = st_n2;
+      Sw[6 * IEKF_LD + lane] = st_r;
+      Sw[7 * IEKF_LD + lane] = st_w;
+      (void)flag;
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < 8; s += 2)
+      {
+        const double a0 = g < 6 ? fa[4 * s] * fr[4 * s] : fa[4 * s];
+        const double b0 = g < 7 ? fb[4 * s] : 0.0;
+        const double a1 = g < 6 ? fa[4 * s + 4] * fr[4 * s + 4] : fa[4 * s + 4];
+        const double b1 = g < 7 ? fb[4 * s + 4] : 0.0;
+        dmma_8x8x4(c0, c1, a0, b0);
+        dmma_8x8x4(d0, d1, a1, b1);
+      }
+    }
+    first_iter = false;
+    LT(2);
+    c0 += d0;
+    c1 += d1;
+
+    // ---- block reduction across the warps in fixed order
+    double s22w = s22;
+    int cntw = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      s22w += __shfl_xor_sync(0xffffffffu, s22w, o);
+      cntw += __shfl_xor_sync(0xffffffffu, cntw, o);
+    }
+    __syncwarp();
+    Sw[g * 8 + 2 * t4] = c0;
+    Sw[g * 8 + 2 * t4 + 1] = c1;
+    if (lane == 0)
+    {
+      Sw[64] = s22w;
+      Sw[65] = (double)cntw;
+    }
+    __syncthreads();
+    double* part = a.partials + (size_t)par * VN_IEKF_NACC * nblk;
+    if (tid < VN_IEKF_NACC)
+    {
+      const int src = iekf_src(tid);
+      double v = 0.0;
+#pragma unroll 2
+      for (int w = 0; w < LOOP_WARPS; w++) v += tiles[w * LOOP_TILE + src];
+      if (tid >= 21 && tid < 27) v = -v;  // HTz -= Rinv j r
+      __stcg(part + (size_t)tid * nblk + blockIdx.x, v);
+    }
+    __syncthreads();
+    // ---- grid barrier: arrive, wait for everybody's partial sums
+    LT(3);
+    if (tid == 0)
+    {
+      __threadfence();
+      atomicAdd(a.bar, 1ull);
+      const unsigned long long target = (unsigned long long)(it_local + 1) * (unsigned long long)nblk;
+      long long spins = 0;
+      while (ld_acquire_u64(a.bar) < target)
+      {
+        if (++spins > LOOP_SPIN_LIMIT)
+        {
+          atomicOr(a.status, VN_ST_SPIN);
+          s_abort = 1;
+          break;
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    LT(4);
+    // every block: the same sums in the same order (a half-warp per column: 34 columns in one pass; lanes stride
+    // over the blocks with independent loads, then a fixed shuffle tree)
+    {
+      const int hw = tid >> 4, hl = tid & 15;
+      double v0 = 0.0, v1 = 0.0;
+      if (hw < VN_IEKF_NACC)
+      {
+        const double* col = part + (size_t)hw * nblk;
+#pragma unroll 5
+        for (int b = hl; b < nblk; b += 32)
+        {
+          v0 += __ldcg(col + b);
+          if (b + 16 < nblk) v1 += __ldcg(col + b + 16);
+        }
+      }
+      double v = v0 + v1;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (hw < VN_IEKF_NACC && hl == 0) fin[hw] = v;
+    }
+    __syncthreads();
+    LT(5);
+    iekf_solve_cta(ctl, fin, tiles, s_cov, s_st, tid, LOOP_T);
+    LT(6);
+    par ^= 1;
+    if (ctl[2] || s_abort) break;
+  }
+
+  // ---- the loop has finished: block 0 stores the iterate and hands it to the host
+  if (blockIdx.x == 0)
+  {
+    double* dd = reinterpret_cast<double*>(dev);
+    if (tid < 21) dd[tid] = s_st[tid];
+    for (int i = tid; i < 225; i += LOOP_T) dev->cov[i] = s_cov[i];
+    if (tid < VN_IEKF_NACC) dev->sums[tid] = fin[tid];
+    if (tid < 3) (&dev->iter)[tid] = ctl[tid];
+    if (a.mode & VN_IEKF_HANDOVER)
+    {
+      __threadfence();
+      __syncthreads();
+      const double* sd = reinterpret_cast<const double*>(dev);
+      double* pd = reinterpret_cast<double*>(q.pub);
+      for (int i = tid; i < (int)(sizeof(IekfDev) / sizeof(double)); i += LOOP_T) pd[i] = __ldcg(sd + i);
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(q.pub_flag) = q.pub_seq;
+    }
+  }
+#ifdef VINA_LOOP_TRACE
+  LT(7);
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == nblk - 1 || blockIdx.x == nblk / 2))
+  {
+    // phase stamps in ns since the block started: 1 iteration starts, 2 rounds done, 3 partials written, 4 barrier
+    // passed, 5 sums added, 6 update done, 7 handed over
+    char buf[8];
+    (void)buf;
+    printf("[loop trace] blk %d:", (int)blockIdx.x);
+    for (int i = 1; i < tr_n; i++)
+      printf(" %d:%llu", (int)(tr[i] >> 56), (tr[i] & 0xffffffffffffffull) - (tr[0] & 0xffffffffffffffull));
+    printf("\n");
+  }
+#endif
+  // the last block out leaves the barrier words at zero for the next launch
+  if (tid == 0)
+  {
+    const unsigned long long t = atomicAdd(a.bar + 1, 1ull);
+    if (t == (unsigned long long)nblk - 1ull)
+    {
+      a.bar[0] = 0ull;
+      a.bar[1] = 0ull;
+      __threadfence();
+    }
+  }
+}
+
+int iekf_loop_chunk(int n, int blocks)
+{
+  int c = (n + blocks - 1) / blocks;
+  c = (c + 31) & ~31;
+  return c < 32 ? 32 : c;
+}
+
+int launch_iekf_loop(cudaStream_t st, const IekfLoop& a, int blocks)
+{
+  static bool attr_set_dev[64] = { false };
+  int dv = 0;
+  cudaGetDevice(&dv);
+  bool& attr_set = attr_set_dev[dv & 63];
+  if (!attr_set)
+  {
+    cudaError_t e = cudaFuncSetAttribute(k_iekf_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  void* args[] = { const_cast<IekfLoop*>(&a) };
+  return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_iekf_loop), dim3(blocks), dim3(LOOP_T), args, LOOP_SMEM, st);
 }
 
 // Hand the converged iterate to the host through mapped pinned memory: the data first, then (after a
@@ -664,7 +1211,7 @@ __global__ void __launch_bounds__(256) k_p2p_sums_solve(ShardPeers peers, IekfDe
                                                         int* __restrict__ status)
 {
   if (dev->done) return;
-  __shared__ double smem[672];
+  __shared__ double smem[IEKF_SOLVE_WS + 288];
   __shared__ double fin[VN_IEKF_NACC];
   const ShardCtrl* me = peers.ctrl[peers.rank];
   if (threadIdx.x < peers.world)

@@ -238,13 +238,9 @@ __global__ void __launch_bounds__(256)
 // and rounded to float, and voxels are emitted in order of their first point.
 // Same voxel set and counts as the reference; coordinates agree to fp32
 // rounding ("tolerance parity only").
-__global__ void __launch_bounds__(256)
-    k_down_accum(const float4* __restrict__ pts, int n, double voxel_size, DownSlot* __restrict__ tab, unsigned int mask,
-                 int* __restrict__ slot_of, int* __restrict__ status)
+__device__ __forceinline__ void down_accum_point(const float4 q, const int i, double voxel_size, DownSlot* __restrict__ tab,
+                                                 unsigned int mask, int* __restrict__ slot_of, int* __restrict__ status)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 q = pts[i];
   const float data[3] = { q.x, q.y, q.z };
   long long kc[3];
   for (int j = 0; j < 3; j++)
@@ -279,6 +275,177 @@ __global__ void __launch_bounds__(256)
   }
   atomicOr(status, VN_ST_DOWN_FULL);
   slot_of[i] = -1;
+}
+
+__global__ void __launch_bounds__(256)
+    k_down_accum(const float4* __restrict__ pts, int n, double voxel_size, DownSlot* __restrict__ tab, unsigned int mask,
+                 int* __restrict__ slot_of, int* __restrict__ status)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  down_accum_point(pts[i], i, voxel_size, tab, mask, slot_of, status);
+}
+
+// The front of the per-scan step in one pass over the raw scan: a2 + a3 of the full scan and the leaf-cache reset (as
+// k_deskew_var_init) plus the accumulation pass of f1 on the deskewed point the thread still holds - the
+// down-sampling no longer re-reads the scan, and what is left of it is one more launch (k_down_emit_all).
+__global__ void __launch_bounds__(256, 3)
+    k_deskew_var_init_down(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg, int* __restrict__ status,
+                           ScanView out, VarInitParams prm, int* __restrict__ cache, double voxel_size,
+                           DownSlot* __restrict__ tab, unsigned int mask, int* __restrict__ slot_of)
+{
+  __shared__ DeskewPoses P;
+  stage_poses(P, Pg);
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 r = deskew_point(P, pts, i, n, status);
+  pts[i] = r;
+  down_accum_point(r, i, voxel_size, tab, mask, slot_of, status);
+  var_init_point(r, i, out, prm);
+  cache[i] = -1;
+}
+
+// The rest of f1 (first-point flags, exclusive scan, emission of the voxel means in first-point order, table
+// clean-up) and the var_init of the emitted set (a3 on the map's point set, point_utils.cpp:36-52) in ONE persistent
+// launch: every block owns a contiguous chunk of the scan, counts its first points, meets the others at a grid
+// barrier (cooperative launch), adds the counts of the blocks before it and emits. The total goes to mapped host
+// memory with a sequence number, so that the host has the count without a copy or a stream synchronisation.
+#define EMIT_T 1024
+#define EMIT_KEEP 2  // rounds whose flags stay in registers (two rounds cover 148 x 2048 = 303 000 points)
+#define EMIT_SPIN_LIMIT (1ll << 24)
+__device__ __forceinline__ int block_sum_int(int v, int* wsum)
+{
+  // (all EMIT_T threads; returns the block total to everybody)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) wsum[w] = v;
+  __syncthreads();
+  int t = wsum[lane];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+__global__ void __launch_bounds__(EMIT_T, 1) k_down_emit_all(const __grid_constant__ DownEmit a)
+{
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = gridDim.x;
+  const int first = blockIdx.x * a.chunk;
+  const int end = min(a.n, first + a.chunk);
+  DownSlot* __restrict__ tab = a.tab;
+  // phase 1: first points of this chunk (the slot of a first point stays in a register for phase 2, -1 otherwise)
+  int mine = 0;
+  int keep[EMIT_KEEP];
+#pragma unroll
+  for (int k = 0; k < EMIT_KEEP; k++)
+  {
+    const int i = first + k * EMIT_T + tid;
+    int s = -1;
+    if (i < end)
+    {
+      s = a.slot_of[i];
+      if (s >= 0 && tab[s].first != i) s = -1;
+    }
+    keep[k] = s;
+    mine += s >= 0 ? 1 : 0;
+  }
+  for (int i = first + EMIT_KEEP * EMIT_T + tid; i < end; i += EMIT_T)
+  {
+    const int s = a.slot_of[i];
+    mine += (s >= 0 && tab[s].first == i) ? 1 : 0;
+  }
+  const int total = block_sum_int(mine, wsum);
+  if (tid == 0)
+  {
+    __stcg(a.counts + blockIdx.x, total);
+    __threadfence();
+    atomicAdd(a.bar, 1ull);
+    long long spins = 0;
+    while (*reinterpret_cast<volatile unsigned long long*>(a.bar) < (unsigned long long)nblk)
+      if (++spins > EMIT_SPIN_LIMIT)
+      {
+        atomicOr(a.status, VN_ST_SPIN);
+        break;
+      }
+    __threadfence();
+  }
+  __syncthreads();
+  // the counts of the blocks before this one, and of all
+  int before = 0, all = 0;
+  for (int b = tid; b < nblk; b += EMIT_T)
+  {
+    const int c = __ldcg(a.counts + b);
+    all += c;
+    if (b < (int)blockIdx.x) before += c;
+  }
+  before = block_sum_int(before, wsum);
+  all = block_sum_int(all, wsum);
+  // phase 2: emit in first-point order, var_init of the emitted point, clean the slot for the next scan
+  int run = before;
+  int rk = 0;
+  for (int r0 = first; r0 < end; r0 += EMIT_T, rk++)
+  {
+    const int i = r0 + tid;
+    int s = -1;
+    bool flag = false;
+    if (rk < EMIT_KEEP)
+    {
+#pragma unroll
+      for (int k = 0; k < EMIT_KEEP; k++)
+        if (k == rk) s = keep[k];
+      flag = s >= 0;
+    }
+    else if (i < end)
+    {
+      s = a.slot_of[i];
+      flag = s >= 0 && tab[s].first == i;
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int t = wsum[lane], incl = t;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int warp_off = __shfl_sync(0xffffffffu, incl - t, warp);
+    const int round_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (flag)
+    {
+      const int ord = run + warp_off + __popc(bal & ((1u << lane) - 1u));
+      DownSlot& sl = tab[s];
+      const double c = (double)sl.cnt;
+      const float4 m = make_float4((float)(sl.sum[0] / c), (float)(sl.sum[1] / c), (float)(sl.sum[2] / c), (float)sl.cnt);
+      a.out[ord] = m;
+      sl.key = VN_EMPTY_KEY;
+      sl.sum[0] = sl.sum[1] = sl.sum[2] = 0.0;
+      sl.cnt = 0;
+      sl.first = 0x7fffffff;
+      var_init_point(m, ord, a.pv, a.prm);
+    }
+    run += round_total;
+  }
+  if (tid == 0)
+  {
+    if (blockIdx.x == 0)
+    {
+      *a.n_out_dev = all;
+      a.pub[1] = (unsigned long long)all;
+      __threadfence_system();
+      a.pub[0] = a.seq;
+    }
+    const unsigned long long t = atomicAdd(a.bar + 1, 1ull);
+    if (t == (unsigned long long)nblk - 1ull)
+    {
+      a.bar[0] = 0ull;
+      a.bar[1] = 0ull;
+      __threadfence();
+    }
+  }
 }
 
 // flag[i] = 1 when point i is the first point of its voxel
@@ -705,6 +872,23 @@ void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPos
                             const VarInitParams& prm, int* cache)
 {
   if (n > 0) k_deskew_var_init<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status, out, prm, cache);
+}
+void launch_deskew_var_init_down(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
+                                 const VarInitParams& prm, int* cache, double voxel_size, DownSlot* tab, unsigned int mask,
+                                 int* slot_of)
+{
+  if (n > 0)
+    k_deskew_var_init_down<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status, out, prm, cache, voxel_size, tab, mask,
+                                                           slot_of);
+}
+int launch_down_emit_all(cudaStream_t st, DownEmit& a, int sm_count)
+{
+  int blocks = (a.n + EMIT_T - 1) / EMIT_T;
+  if (blocks > sm_count) blocks = sm_count;
+  if (blocks < 1) blocks = 1;
+  a.chunk = (((a.n + blocks - 1) / blocks) + 31) & ~31;
+  void* args[] = { &a };
+  return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k_down_emit_all), dim3(blocks), dim3(EMIT_T), args, 0, st);
 }
 void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n_host, ScanView out,
                      const VarInitParams& prm)

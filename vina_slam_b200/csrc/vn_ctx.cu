@@ -169,6 +169,15 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   // IEKF
   CU(dalloc(&ctx->d_partials, ((size_t)cap / 128 + 64) * VN_IEKF_NACC));
   CU(dalloc(&ctx->d_ticket, 1));
+  CU(dalloc(&ctx->d_emit_counts, ctx->sm_count));
+  CU(dalloc(&ctx->d_emit_bar, 2));
+  CU(cudaHostAlloc((void**)&ctx->h_down_pub, 64, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_down_pub, ctx->h_down_pub, 0));
+  memset(ctx->h_down_pub, 0, 64);
+  if (const char* e = getenv("VINA_FRONT_FUSED")) ctx->front_fused = atoi(e) != 0;
+  CU(dalloc(&ctx->d_loop_bar, 2));
+  CU(dalloc(&ctx->d_loop_partials, (size_t)2 * VN_IEKF_NACC * ctx->sm_count));
+  if (const char* e = getenv("VINA_IEKF_LOOP")) ctx->iekf_loop = atoi(e) != 0;
   CU(cudaHostAlloc((void**)&ctx->h_result, 64 * sizeof(double), cudaHostAllocMapped));
   CU(cudaHostGetDevicePointer((void**)&ctx->d_result, ctx->h_result, 0));
   memset(ctx->h_result, 0, 64 * sizeof(double));
@@ -286,6 +295,11 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   cudaFree(ctx->d_block_sums);
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_ticket);
+  cudaFree(ctx->d_emit_counts);
+  cudaFree(ctx->d_emit_bar);
+  if (ctx->h_down_pub) cudaFreeHost(ctx->h_down_pub);
+  cudaFree(ctx->d_loop_bar);
+  cudaFree(ctx->d_loop_partials);
   cudaFreeHost(ctx->h_result);
   cudaFree(ctx->d_iekf);
   cudaFreeHost(ctx->h_iekf);
@@ -433,6 +447,13 @@ extern "C" int vina_set_overlap(vina_ctx* ctx, int on)
 {
   if (!ctx) return VINA_E_ARG;
   ctx->overlap = on != 0;
+  return VINA_OK;
+}
+
+extern "C" int vina_set_iekf_loop(vina_ctx* ctx, int on)
+{
+  if (!ctx) return VINA_E_ARG;
+  ctx->iekf_loop = on != 0;
   return VINA_OK;
 }
 
@@ -590,6 +611,28 @@ static int run_downsample(vina_ctx* ctx, double size)
 static int resolve_n_down(vina_ctx* ctx)
 {
   if (!ctx->n_down_pending) return VINA_OK;
+  if (ctx->n_down_mapped)
+  {
+    // published by k_down_emit_all: poll the sequence number (no stream synchronisation; the IEKF loop behind it
+    // keeps running)
+    volatile unsigned long long* pub = ctx->h_down_pub;
+    for (long spins = 0; pub[0] != ctx->down_seq; spins++)
+      if ((spins & 0xfff) == 0xfff)
+      {
+        cudaError_t e = cudaStreamQuery(ctx->stream);
+        if (e == cudaSuccess)
+        {
+          if (pub[0] == ctx->down_seq) break;
+          return vn_fail(ctx, VINA_E_CUDA, "the down-sampling finished without publishing its count");
+        }
+        if (e != cudaErrorNotReady) return vn_check_cuda(ctx, e, "down-sampling");
+      }
+    __sync_synchronize();
+    ctx->n_down = (int)pub[1];
+    ctx->n_down_mapped = false;
+    ctx->n_down_pending = false;
+    return VINA_OK;
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->n_down = *ctx->h_n_down;
   ctx->n_down_pending = false;
@@ -615,8 +658,10 @@ int vn_finish_downsample(vina_ctx* ctx)
 {
   int r = resolve_n_down(ctx);
   if (r) return r;
+  ctx->down_retried = false;
   if (ctx->n_down < 2000 && ctx->cfg.down_size >= 0.001 && ctx->n_scan > 0)
   {
+    ctx->down_retried = true;
     // retry with half the voxel size (local_mapping.cpp:399-403)
     r = run_downsample(ctx, ctx->cfg.down_size / 2);
     if (r) return r;
@@ -688,6 +733,50 @@ int vn_deskew_var_init(vina_ctx* ctx, const vina_imu_pose* poses, int m, const d
   ctx->n_pv[0] = ctx->n_scan;
   ctx->cache_is_reset = true;
   ctx->launches += 1;
+  return mark_scan_read(ctx);
+}
+
+// The front of the per-scan step as two launches: k_deskew_var_init_down (vina_deskew + vina_var_init(ctx, 0) + the
+// cache reset + the accumulation pass of vina_downsample) and k_down_emit_all (the rest of vina_downsample +
+// vina_var_init(ctx, 1)). The count is published through mapped memory (resolve_n_down polls it).
+int vn_front_fused(vina_ctx* ctx, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3])
+{
+  if (m > VINA_MAX_POSES) return vn_fail(ctx, VINA_E_CAPACITY, "%d IMU poses > VINA_MAX_POSES", m);
+  if (ctx->poses_in_flight) CU(cudaEventSynchronize(ctx->ev_poses));
+  DeskewPoses* P = ctx->h_poses;
+  P->m = m;
+  memcpy(P->pose, poses, (size_t)m * sizeof(vina_imu_pose));
+  memcpy(P->R_end, R_end, 72);
+  memcpy(P->p_end, p_end, 24);
+  memcpy(P->ext_R, ctx->cfg.ext_R, 72);
+  memcpy(P->ext_t, ctx->cfg.ext_t, 24);
+  CU(cudaMemcpyAsync(ctx->d_poses, P, sizeof(DeskewPoses), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_poses, ctx->stream));
+  ctx->poses_in_flight = true;
+  const VarInitParams prm = var_init_params(ctx);
+  launch_deskew_var_init_down(ctx->stream, ctx->d_scan, ctx->n_scan, ctx->d_poses, ctx->d_status, ctx->pv[0], prm, ctx->d_cache,
+                              ctx->cfg.down_size, ctx->d_dtab, ctx->dmask, ctx->d_slot_of);
+  ctx->n_pv[0] = ctx->n_scan;
+  ctx->cache_is_reset = true;
+  DownEmit de;
+  de.n = ctx->n_scan;
+  de.chunk = 0;
+  de.tab = ctx->d_dtab;
+  de.slot_of = ctx->d_slot_of;
+  de.out = ctx->d_down;
+  de.n_out_dev = ctx->d_n_down;
+  de.pv = ctx->pv[1];
+  de.prm = prm;
+  de.counts = ctx->d_emit_counts;
+  de.bar = ctx->d_emit_bar;
+  de.pub = ctx->d_down_pub;
+  de.seq = ++ctx->down_seq;
+  de.status = ctx->d_status;
+  int e = launch_down_emit_all(ctx->stream, de, ctx->sm_count);
+  if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_down_emit_all launch");
+  ctx->launches += 2;
+  ctx->n_down_pending = true;
+  ctx->n_down_mapped = true;
   return mark_scan_read(ctx);
 }
 

@@ -26,6 +26,17 @@ struct vina_ctx
   bool n_down_pending = false;
   int* d_n_down = nullptr;
   int* h_n_down = nullptr;   // pinned
+  // fused front (vn_front_fused): the count arrives through mapped memory, [0] sequence number, [1] count
+  bool front_fused = true;
+  bool n_down_mapped = false;           // the pending count is the one k_down_emit_all publishes
+  bool batch_member = false;            // the context belongs to a vina_batch
+  bool front_was_fused = false;         // the serial step's front went out as the two fused launches
+  bool down_retried = false;            // vn_finish_downsample re-ran the down-sampling (< 2000 points rule)
+  unsigned long long* h_down_pub = nullptr;
+  unsigned long long* d_down_pub = nullptr;
+  unsigned long long down_seq = 0;
+  int* d_emit_counts = nullptr;
+  unsigned long long* d_emit_bar = nullptr;
   ScanView pv[2];            // [0] full scan, [1] down-sampled
   int n_pv[2] = { 0, 0 };
   int* d_cache = nullptr;
@@ -53,6 +64,11 @@ struct vina_ctx
   double rot_var[9], tsl_var[9];
   double* d_partials = nullptr;
   unsigned int* d_ticket = nullptr;
+  bool iekf_loop = false;                    // vina_set_iekf_loop: the iteration loop as one persistent launch (k_iekf_loop)
+  unsigned long long* d_loop_bar = nullptr;  // grid-barrier words of k_iekf_loop
+  double* d_loop_partials = nullptr;         // [2][34][sm_count]
+  bool iekf_looped = false;                  // the last enqueued loop went out as k_iekf_loop
+  int loop_launches = 0;                     // profiling: launches of k_iekf_loop timed so far
   double* h_result = nullptr;  // pinned + mapped; the kernel's last block writes it
   double* d_result = nullptr;  // device alias of h_result
   IekfDev* d_iekf = nullptr;   // device-resident iterate (state, covariance, flags)
@@ -145,6 +161,7 @@ int vn_fail(vina_ctx* c, int code, const char* fmt, ...);
 int vn_init_ensure(vina_ctx* c);        // buffers of the start-up phase
 int vn_map_clear(vina_ctx* c);          // the map back to its state after vina_ctx_create (motion_init rebuilds it every round)
 // down_sampling_voxel of an arbitrary device cloud (no "< 2000 points" retry); synchronises, returns the count
+int vn_front_fused(vina_ctx* c, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vn_downsample_cloud(vina_ctx* c, const float4* in, int n, double size, float4* out, int* n_out);
 // sum of n n^T over the normals (eigenvector of the smallest eigenvalue) of the collected BA factors, 3x3 column-major
 int vn_ba_normal_scatter(vina_ctx* c, double nnt[9]);

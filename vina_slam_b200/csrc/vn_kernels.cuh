@@ -83,6 +83,17 @@ struct IekfBatch
   IekfSeq s[VN_MAX_BATCH];
 };
 
+// the whole iteration loop as one persistent cooperative launch (k_iekf_loop)
+struct IekfLoop
+{
+  IekfSeq q;
+  unsigned long long* bar;  // [0] arrivals at the grid barrier, [1] blocks that have left; both zero between launches
+  double* partials;         // [2][VN_IEKF_NACC][gridDim.x], ping-pong over the iterations
+  int* status;
+  int chunk;                // points per block, a multiple of 32
+  int mode;                 // VN_IEKF_HANDOVER
+};
+
 // scan_kernels.cu
 void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status);
 void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n_host, ScanView out,
@@ -90,6 +101,28 @@ void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n
 // deskew + var_init of the full scan + leaf-cache reset in one pass
 void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
                             const VarInitParams& prm, int* cache);
+// the fused front of the per-scan step: deskew + var_init + cache reset + the accumulation pass of the down-sampling,
+// then ONE cooperative launch for the rest of the down-sampling and the var_init of the emitted set
+struct DownEmit
+{
+  int n;
+  int chunk;  // points per block (set by the launcher)
+  DownSlot* tab;
+  const int* slot_of;
+  float4* out;
+  int* n_out_dev;
+  ScanView pv;
+  VarInitParams prm;
+  int* counts;                       // [gridDim.x]
+  unsigned long long* bar;           // [0] arrivals, [1] exits; zero between launches
+  volatile unsigned long long* pub;  // mapped host memory: [0] sequence number (written last), [1] count
+  unsigned long long seq;
+  int* status;
+};
+void launch_deskew_var_init_down(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
+                                 const VarInitParams& prm, int* cache, double voxel_size, DownSlot* tab, unsigned int mask,
+                                 int* slot_of);
+int launch_down_emit_all(cudaStream_t st, DownEmit& a, int sm_count);
 void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots);
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
                       int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status);
@@ -107,6 +140,8 @@ int launch_init_redeskew(cudaStream_t st, const float4* orig, int n, int n_skip,
 int iekf_grid_blocks(int n, int sm_count);
 // grid = (blocks, nseq); every sequence gets `blocks` persistent 1024-thread blocks
 int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug);
+int iekf_loop_chunk(int n, int blocks);
+int launch_iekf_loop(cudaStream_t st, const IekfLoop& a, int blocks);
 void launch_fill_int(cudaStream_t st, int* p, int v, int n);
 static_assert(sizeof(IekfDev) % sizeof(double) == 0, "IekfDev is copied as doubles");
 static_assert(offsetof(IekfDev, Rp) == 21 * sizeof(double) && offsetof(IekfDev, cov) == 42 * sizeof(double),

@@ -458,6 +458,29 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
     ctx->iekf_ev.resize(2 * (size_t)num_max_iter);
     for (size_t i = old; i < ctx->iekf_ev.size(); i++) cudaEventCreate(&ctx->iekf_ev[i]);
   }
+  // the default: the whole loop as one persistent launch (needs 16-byte aligned pointVar rows for the bulk copies)
+  if (ctx->iekf_loop && (ctx->cap_points & 1) == 0 && (reinterpret_cast<uintptr_t>(bt.s[0].pv_base) & 15) == 0)
+  {
+    IekfLoop lp;
+    lp.q = bt.s[0];
+    lp.bar = ctx->d_loop_bar;
+    lp.partials = ctx->d_loop_partials;
+    lp.status = ctx->d_status;
+    lp.mode = VN_IEKF_HANDOVER;
+    const int n = ctx->n_pv[which];
+    int blocks = (n + 255) / 256;
+    if (blocks > ctx->sm_count) blocks = ctx->sm_count;
+    if (blocks < 1) blocks = 1;
+    lp.chunk = iekf_loop_chunk(n, blocks);
+    if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[0], ctx->stream);
+    int e = launch_iekf_loop(ctx->stream, lp, blocks);
+    if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf_loop launch");
+    ctx->launches += 1;
+    if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[1], ctx->stream);
+    ctx->iekf_looped = true;
+    return VINA_OK;
+  }
+  ctx->iekf_looped = false;
   for (int it = 0; it < num_max_iter; it++)
   {
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it], ctx->stream);
@@ -478,7 +501,7 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
   if (r) return r;
   r = vn_iterate_wait(ctx, ctx->stream);
   if (r) return r;
-  if (ctx->n_down_pending)
+  if (ctx->n_down_pending && !ctx->n_down_mapped)
   {
     // the count's device-to-host copy was enqueued before the loop: it has landed (stream order)
     ctx->n_down = *ctx->h_n_down;
@@ -487,8 +510,14 @@ static int lio_state_estimation(vina_ctx* ctx, OdomHost* o, int which, int max_i
   unstage_iterate(ctx->h_pub, o->x_curr, &o->last_iters, not_degenerate);
   ctx->tm.iekf_iters = o->last_iters;
   float kernel_ms = 0;
-  if (ctx->profiling) cudaEventSynchronize(ctx->iekf_ev[2 * num_max_iter - 1]);
-  if (ctx->profiling)
+  if (ctx->profiling && ctx->iekf_looped)
+  {
+    cudaEventSynchronize(ctx->iekf_ev[1]);
+    cudaEventElapsedTime(&kernel_ms, ctx->iekf_ev[0], ctx->iekf_ev[1]);  // one launch = the whole loop
+  }
+  else if (ctx->profiling)
+    cudaEventSynchronize(ctx->iekf_ev[2 * num_max_iter - 1]);
+  if (ctx->profiling && !ctx->iekf_looped)
     for (int it = 0; it < o->last_iters; it++)
     {
       float ms = 0;
@@ -623,6 +652,23 @@ static int step_front(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, double pc
   if (r) return r;
   cudaEvent_t* ev = ctx->ev;
   if (ctx->profiling) cudaEventRecord(ev[0], ctx->stream);
+  ctx->front_was_fused = false;
+  if (iekf_on_full && ctx->front_fused && ctx->iekf_loop && !ctx->batch_member && ctx->cfg.down_size >= 0.001 && ctx->n_scan > 0)
+  {
+    // the product schedule's two front launches (see odom_step_overlapped); the per-stage timers see the first as
+    // "deskew" and the second as "downsample"
+    r = vn_front_fused(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+    if (r) return r;
+    if (ctx->profiling)
+    {
+      cudaEventRecord(ev[1], ctx->stream);  // (both launches are enqueued: the split is not resolved here)
+      cudaEventRecord(ev[2], ctx->stream);
+      cudaEventRecord(ev[3], ctx->stream);
+    }
+    ctx->front_was_fused = true;
+    *which_out = 0;
+    return VINA_OK;
+  }
   r = vina_deskew(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
   if (r) return r;
   if (ctx->profiling) cudaEventRecord(ev[1], ctx->stream);
@@ -663,8 +709,13 @@ static int step_back(vina_ctx* ctx, OdomHost* o, int iekf_on_full, int ok, vina_
     // the down-sampled count arrived with the IEKF readback: no extra sync in the common case
     r = vn_finish_downsample(ctx);
     if (r) return r;
-    r = vina_var_init(ctx, 1);
-    if (r) return r;
+    if (ctx->front_was_fused && !ctx->down_retried)
+      ctx->n_pv[1] = ctx->n_down;  // k_down_emit_all has done the var_init of the emitted set
+    else
+    {
+      r = vina_var_init(ctx, 1);
+      if (r) return r;
+    }
   }
   r = map_update(ctx, o);
   if (r) return r;
@@ -694,13 +745,38 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (r) return r;
   cudaStream_t A = ctx->stream, B = ctx->side_stream;
   if (tr) th[1] = now_us(), cudaEventRecord(ctx->tr_ev[0], A);
+  const int num_max_iter = max_iter > 0 ? max_iter : 20;
+  const bool fused = ctx->front_fused && ctx->iekf_loop && ctx->cfg.down_size >= 0.001 && ctx->n_scan > 0;
+  if (fused)
+  {
+    // The persistent loop kernel fills every SM, so a side stream has nothing to run on next to it: the front is two
+    // launches in stream order instead - deskew + var_init + cache reset + the accumulation pass of the down-sampling,
+    // then the rest of the down-sampling with the var_init of the map's point set - and the loop follows. The
+    // down-sampled count reaches the host through mapped memory while the loop runs.
+    r = vn_front_fused(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+    if (r) return r;
+    r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
+    if (r) return r;
+    if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
+    r = vn_finish_downsample(ctx);
+    if (r) return r;
+    if (ctx->down_retried)
+    {
+      r = vina_var_init(ctx, 1);  // (the "< 2000 points" retry re-ran the down-sampling with the separate kernels)
+      if (r) return r;
+    }
+    else
+      ctx->n_pv[1] = ctx->n_down;
+    if (tr) th[3] = now_us();
+    if (tr) cudaEventRecord(ctx->tr_ev[2], A);
+    goto map_part;
+  }
   // deskew, var_init of the full scan and the leaf-cache reset are one kernel
   r = vn_deskew_var_init(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
   if (r) return r;
   r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
   if (r) return r;
   // the IEKF launches go out first: they are on the critical path, the side stream has slack
-  const int num_max_iter = max_iter > 0 ? max_iter : 20;
   r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
   if (r) return r;
   if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
@@ -722,6 +798,7 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (tr) cudaEventRecord(ctx->tr_ev[2], A);
   r = vn_mark_scan_read(ctx);  // (covers the side stream's readers of the scan buffer as well)
   if (r) return r;
+map_part:
   if (o->if_BA)
   {
     // the LM loop of the BA needs the host between recut and margi: take the IEKF result first, then the map
@@ -852,6 +929,9 @@ extern "C" int vina_batch_create(vina_ctx** ctxs, int n, vina_batch** out)
     if (!ctxs[i] || ctxs[i]->device != ctxs[0]->device) return VINA_E_ARG;
   vina_batch* b = new vina_batch();
   b->c.assign(ctxs, ctxs + n);
+  // (the sequences of a batch run their fronts concurrently on their own streams: they keep the plain kernels - several
+  // cooperative launches at once would only queue behind each other)
+  for (int i = 0; i < n; i++) ctxs[i]->batch_member = true;
   b->device = ctxs[0]->device;
   cudaSetDevice(b->device);
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -942,7 +1022,7 @@ extern "C" int vina_batch_step_resident(vina_batch* b, const void* const* d_xyzt
     OdomHost* o = odom(ctx);
     int r = vn_iterate_wait(ctx, b->stream);
     if (r) return r;
-    if (ctx->n_down_pending)
+    if (ctx->n_down_pending && !ctx->n_down_mapped)
     {
       ctx->n_down = *ctx->h_n_down;  // enqueued before the batched launches: has landed
       ctx->n_down_pending = false;
