@@ -941,6 +941,26 @@ def test_iekf_loop_kernel_matches_per_iteration_launches_and_the_oracle(oracle_l
         gx.close()
 
 
+def test_iekf_loop_schedule_small_scan_retry(oracle_lib, gpu_lib):
+    """The fused front of the loop schedule publishes the down-sampled count through mapped memory; a scan that
+    down-samples to < 2000 points must still take the "down_size / 2" retry of local_mapping.cpp:396-403 (separate
+    kernels, then var_init again) and land on the oracle's voxel set and trajectory."""
+    cfg = small_cfg("robosense128", 8, 150)  # 1200 points per scan: always below the 2000-point threshold
+    seq, od, gx, last = bootstrap_pair(oracle_lib, gpu_lib, cfg, gpu_own_downsample=True)
+    gx.set_iekf_loop(True)
+    for k in range(4):
+        sc = seq.next_scan()
+        r, _ = od.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4)
+        assert r == 0
+        sg = gpu_lib.state_arrays(gx.step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+        so = oracle_lib.state_arrays(od.get_state())
+        n_d = gx.n_down()
+        assert 0 < n_d < 2000 and n_d == od.last_down().shape[0]
+        assert np.linalg.norm(sg["p"] - so["p"]) < 1e-3 and synth.rot_err_deg(sg["R"], so["R"]) < 0.01
+    assert gx.map_count()[0] == od.map_count()[0]
+    gx.close()
+
+
 def test_ba_lidar_factor_matches_oracle(oracle_lib, gpu_lib):
     """SURVEY section 8f rank 3, the data-parallel part of the sliding-window BA: the device factor store
     (tras_opt) and LidarFactor::acc_evaluate2 / evaluate_only_residual (factors.cpp:22-158) against the oracle,

@@ -1286,7 +1286,10 @@ int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool
   if (debug)
     k_iekf<true><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);
   else
-    k_iekf<false><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);
+    k_iekf<false><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);  // (no programmatic launch here: the next iteration's
+                                                                // blocks would sit on the SMs through this one's tail - the
+                                                                // reduction and the update in the last block - and keep the
+                                                                // side stream's kernels out)
   return (int)cudaGetLastError();
 }
 

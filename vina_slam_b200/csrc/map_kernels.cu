@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256)
     k_insert_root(MapView M, ScanView scan, const int* __restrict__ n_ptr, int n_host, InsertScratch sc, PoseD x_host,
                   Cov2 cv_host, int pre, const IekfDev* __restrict__ live)
 {
+  vn_pdl_sync();
   // pose and posterior covariance blocks of pvec_update: from the host, or straight from the device iterate
   __shared__ PoseD x;
   __shared__ Cov2 cv;
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_insert_leaf(MapView M, const int* __restrict__ n_ptr, int n_host, InsertScratch sc)
 {
+  vn_pdl_sync();
   int n = n_ptr ? *n_ptr : n_host;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(128) k_insert_alloc(MapView M, InsertScratch sc)
 {
+  vn_pdl_sync();
   int nt = sc.counters[1];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nt; j += gridDim.x * blockDim.x)
   {
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(128) k_insert_alloc(MapView M, InsertScratch s
 __global__ void __launch_bounds__(256)
     k_insert_scatter(MapView M, const int* __restrict__ n_ptr, int n_host, InsertScratch sc)
 {
+  vn_pdl_sync();
   int n = n_ptr ? *n_ptr : n_host;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -472,6 +476,7 @@ __device__ __forceinline__ void bf_var_terms(const double* v, const double* p, d
 #define ACC_RED_ROWS 8
 __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, ScanView scan, InsertScratch sc, int win_ord)
 {
+  vn_pdl_sync();
   // shared memory per warp bounds the number of resident warps of this kernel: the Bf_var terms are staged
   // 8 rows at a time (3 KB); per row the 9 + 9 products of PointCluster::push (types.hpp:137-142) for the world
   // and the body point are formed by the row's lane, so that the sequential chains only add (4.8 KB)
@@ -771,6 +776,7 @@ __device__ __forceinline__ int warp_reserve(int* counter, int mine, int lane)
 
 __global__ void __launch_bounds__(128) k_recut_collect(MapView M, LayerLists LL)
 {
+  vn_pdl_sync();
   if (blockIdx.x == 0 && threadIdx.x < 8) LL.count_alt[threadIdx.x] = 0;
   const int nroots = M.slide_count[M.slide_cur];
   if (nroots + M.slide_others < M.thread_num) return;  // local_mapping.cpp:150-154
@@ -835,6 +841,7 @@ __global__ void __launch_bounds__(128) k_recut_collect(MapView M, LayerLists LL)
 // have to wait for it - those are handled by k_split itself. Leaves that must be subdivided go to the split list.
 __global__ void __launch_bounds__(128) k_recut_all(MapView M, LayerLists LL)
 {
+  vn_pdl_sync();
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:150-154
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
@@ -967,6 +974,7 @@ __device__ __forceinline__ void split_push(const LayerLists& LL, int node)
 
 __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
 {
+  vn_pdl_sync();
   extern __shared__ double split_smem[];
   double(*val)[19] = reinterpret_cast<double(*)[19]>(split_smem);  // per row: the 9 push() terms of the world point, then of the stored point
   double(*red)[RED_STRIDE] = reinterpret_cast<double(*)[RED_STRIDE]>(split_smem + SPLIT_BATCH * 19);
@@ -1798,6 +1806,7 @@ __device__ void margi_warp_pass(const MapView& M, const int* __restrict__ nodes,
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
 __global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
 {
+  vn_pdl_sync();
   __shared__ MargiShared sh_all[128 / MG];
   // (the slide list the compaction fills after this kernel starts empty)
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) M.slide_count[1 - M.slide_cur] = 0;
@@ -1876,6 +1885,7 @@ __device__ __forceinline__ void clear_slwd_node(const MapView& M, NodeCold& c)
 //  * iter->second->jour = jour (local_mapping.cpp:36).
 __global__ void __launch_bounds__(128) k_margi_finish(MapView M)
 {
+  vn_pdl_sync();
   const int cur = M.slide_cur;
   const int nroots = M.slide_count[cur];
   const bool early_out = nroots + M.slide_others < M.thread_num;  // multi_margi returned before its erase loop
@@ -2230,7 +2240,7 @@ int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView&
   int* t = sc.counters;
   sc.counters = sc.counters_alt;
   sc.counters_alt = t;
-  k_insert_root<<<grid_for(n_host, 256), 256, 0, st>>>(map, scan, n_dev, n_host, sc, x, cv, pre, live);
+  vn_launch(k_insert_root, dim3(grid_for(n_host, 256)), dim3(256), 0, st, map, scan, n_dev, n_host, sc, x, cv, pre, live);
   return 1;
 }
 
@@ -2238,14 +2248,14 @@ int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView
                              const InsertScratch& sc, int win_ord)
 {
   if (n_host <= 0) return 0;
-  k_insert_leaf<<<grid_for(n_host, 256), 256, 0, st>>>(map, n_dev, n_host, sc);
+  vn_launch(k_insert_leaf, dim3(grid_for(n_host, 256)), dim3(256), 0, st, map, n_dev, n_host, sc);
   int tg = grid_for(n_host, 128);
   if (tg > 1184) tg = 1184;
-  k_insert_alloc<<<tg, 128, 0, st>>>(map, sc);
-  k_insert_scatter<<<grid_for(n_host, 256), 256, 0, st>>>(map, n_dev, n_host, sc);
+  vn_launch(k_insert_alloc, dim3(tg), dim3(128), 0, st, map, sc);
+  vn_launch(k_insert_scatter, dim3(grid_for(n_host, 256)), dim3(256), 0, st, map, n_dev, n_host, sc);
   int ag = grid_for(n_host, ACC_WARPS);  // at most one warp per point's leaf
   if (ag > 148 * 16) ag = 148 * 16;
-  k_insert_accum<<<ag, 32 * ACC_WARPS, 0, st>>>(map, scan, sc, win_ord);
+  vn_launch(k_insert_accum, dim3(ag), dim3(32 * ACC_WARPS), 0, st, map, scan, sc, win_ord);
   return 4;
 }
 
@@ -2283,14 +2293,14 @@ int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int wi
   int* t = LL.count;
   LL.count = LL.count_alt;
   LL.count_alt = t;
-  k_recut_collect<<<592, 128, 0, st>>>(map, LL);
-  k_recut_all<<<dim3(296, map.max_layer + 1), 128, 0, st>>>(map, LL);
+  vn_launch(k_recut_collect, dim3(592), dim3(128), 0, st, map, LL);
+  vn_launch(k_recut_all, dim3(296, map.max_layer + 1), dim3(128), 0, st, map, LL);
   int launches = 2;
   // every subdivision of this multi_recut, all levels, through the kernel's work queue (two blocks per SM: all
   // 296 are resident; a block that finds the queue empty but work in flight polls)
   if (map.max_layer > 0)
   {
-    k_split<<<296, SPLIT_THREADS, SPLIT_SMEM, st>>>(map, LL, win_count, b, lv);
+    vn_launch(k_split, dim3(296), dim3(SPLIT_THREADS), SPLIT_SMEM, st, map, LL, win_count, b, lv);
     launches++;
   }
   return launches;
@@ -2301,8 +2311,8 @@ int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, 
 {
   const LivePose lv = { live, win_count - 1 };
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  k_margi_leaves<<<dim3(592, map.max_layer + 1), 128, 0, st>>>(map, LL, win_count, b, lv);
-  k_margi_finish<<<592, 128, 0, st>>>(map);
+  vn_launch(k_margi_leaves, dim3(592, map.max_layer + 1), dim3(128), 0, st, map, LL, win_count, b, lv);
+  vn_launch(k_margi_finish, dim3(592), dim3(128), 0, st, map);
   return 2;
 }
 

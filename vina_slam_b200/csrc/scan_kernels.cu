@@ -206,6 +206,7 @@ __device__ __forceinline__ void var_init_point(const float4 q, const int i, cons
 __global__ void __launch_bounds__(256)
     k_var_init(const float4* __restrict__ pts, const int* __restrict__ n_ptr, int n_host, ScanView out, VarInitParams prm)
 {
+  vn_pdl_sync();
   int n = n_ptr ? *n_ptr : n_host;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(256)
     k_deskew_var_init(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg, int* __restrict__ status,
                       ScanView out, VarInitParams prm, int* __restrict__ cache)
 {
+  vn_pdl_sync();
   __shared__ DeskewPoses P;
   stage_poses(P, Pg);
   __syncthreads();
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(256)
     k_down_accum(const float4* __restrict__ pts, int n, double voxel_size, DownSlot* __restrict__ tab, unsigned int mask,
                  int* __restrict__ slot_of, int* __restrict__ status)
 {
+  vn_pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   down_accum_point(pts[i], i, voxel_size, tab, mask, slot_of, status);
@@ -452,6 +455,7 @@ __global__ void __launch_bounds__(EMIT_T, 1) k_down_emit_all(const __grid_consta
 __global__ void __launch_bounds__(256)
     k_down_flag(int n, const DownSlot* __restrict__ tab, const int* __restrict__ slot_of, int* __restrict__ flag)
 {
+  vn_pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int s = slot_of[i];
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(1024) k_scan_block(const int* __restrict__ in, int* __restrict__ out, int n,
                                                      int* __restrict__ block_sums)
 {
+  vn_pdl_sync();
   __shared__ int warp_sums[32];
   int i = blockIdx.x * 1024 + threadIdx.x;
   int v = (i < n) ? in[i] : 0;
@@ -491,6 +496,7 @@ __global__ void __launch_bounds__(1024) k_scan_block(const int* __restrict__ in,
 }
 __global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ block_sums, int nb, int* __restrict__ total)
 {
+  vn_pdl_sync();
   __shared__ int warp_sums[32];
   int v = (threadIdx.x < nb) ? block_sums[threadIdx.x] : 0;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -523,6 +529,7 @@ __global__ void __launch_bounds__(256)
     k_down_emit(int n, DownSlot* __restrict__ tab, const int* __restrict__ slot_of, const int* __restrict__ flag,
                 const int* __restrict__ scan, const int* __restrict__ block_sums, float4* __restrict__ out)
 {
+  vn_pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (!flag[i]) return;
@@ -871,7 +878,7 @@ void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_pos
 void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
                             const VarInitParams& prm, int* cache)
 {
-  if (n > 0) k_deskew_var_init<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status, out, prm, cache);
+  if (n > 0) vn_launch(k_deskew_var_init, dim3((n + 255) / 256), dim3(256), 0, st, pts, n, d_poses, status, out, prm, cache);
 }
 void launch_deskew_var_init_down(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
                                  const VarInitParams& prm, int* cache, double voxel_size, DownSlot* tab, unsigned int mask,
@@ -894,7 +901,7 @@ void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n
                      const VarInitParams& prm)
 {
   if (n_host <= 0) return;
-  k_var_init<<<(n_host + 255) / 256, 256, 0, st>>>(pts, n_dev, n_host, out, prm);
+  vn_launch(k_var_init, dim3((n_host + 255) / 256), dim3(256), 0, st, pts, n_dev, n_host, out, prm);
 }
 void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots)
 {
@@ -906,10 +913,10 @@ int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_si
   if (n <= 0) return 0;
   int nb = (n + 1023) / 1024;
   if (nb > 1024) return -1;
-  k_down_accum<<<(n + 255) / 256, 256, 0, st>>>(pts, n, voxel_size, tab, mask, slot_of, status);
-  k_down_flag<<<(n + 255) / 256, 256, 0, st>>>(n, tab, slot_of, flag);
-  k_scan_block<<<nb, 1024, 0, st>>>(flag, scan, n, block_sums);
-  k_scan_sums<<<1, 1024, 0, st>>>(block_sums, nb, n_out_dev);
-  k_down_emit<<<(n + 255) / 256, 256, 0, st>>>(n, tab, slot_of, flag, scan, block_sums, out);
+  vn_launch(k_down_accum, dim3((n + 255) / 256), dim3(256), 0, st, pts, n, voxel_size, tab, mask, slot_of, status);
+  vn_launch(k_down_flag, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag);
+  vn_launch(k_scan_block, dim3(nb), dim3(1024), 0, st, flag, scan, n, block_sums);
+  vn_launch(k_scan_sums, dim3(1), dim3(1024), 0, st, block_sums, nb, n_out_dev);
+  vn_launch(k_down_emit, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag, scan, block_sums, out);
   return 5;
 }

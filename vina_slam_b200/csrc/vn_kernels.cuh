@@ -1,5 +1,6 @@
 // Launcher prototypes and small parameter blocks shared by the kernel TUs and the context.
 #pragma once
+#include <cstdlib>
 #include <cstddef>
 #include <cuda_runtime.h>
 #include "vn_math.cuh"
@@ -19,6 +20,44 @@ struct DownSlot
   int cnt;
   int first;
 };
+
+
+// Programmatic dependent launch (sm_90+): the kernels of the per-scan step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and begin with vn_pdl_sync(): "my dependents may be scheduled"
+// right away, then "wait until everything before me in the stream has completed and is visible". The next kernel's
+// launch processing and block scheduling then overlap the tail of the running one instead of following its
+// completion - the step is a chain of ~20 short dependent kernels, and the gaps between them are a tenth of it.
+// Nothing may touch global memory before vn_pdl_sync(). Launched without the attribute both instructions do nothing.
+#ifdef __CUDACC__
+__device__ __forceinline__ void vn_pdl_sync()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+inline bool vn_pdl_enabled()
+{
+  static const bool on = [] {
+    const char* e = getenv("VINA_PDL");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+template <typename... KA, typename... A>
+inline cudaError_t vn_launch(void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t st, A&&... a)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g;
+  cfg.blockDim = b;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = vn_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, static_cast<KA>(a)...);
+}
 
 #define VN_IEKF_NACC 34  // 21 (HTH upper) + 6 (HTz) + 6 (nnt upper) + 1 (count)
 #define VN_MAX_BATCH 16  // sequences per batched k_iekf launch
