@@ -26,7 +26,7 @@ UNITS = [
     (os.path.join(CSRC, "map_kernels.cu"), ["-fmad=false"]),
     (os.path.join(CSRC, "front_kernels.cu"), ["-fmad=false"]),
     (os.path.join(CSRC, "shard_kernels.cu"), ["-fmad=false"]),
-    (os.path.join(CSRC, "iekf_kernel.cu"), ["-DIEKF_THREADS=" + os.environ.get("VINA_IEKF_THREADS", "768"),
+    (os.path.join(CSRC, "iekf_kernel.cu"), ["-DIEKF_THREADS=" + os.environ.get("VINA_IEKF_THREADS", "832"),
                                             "-DIEKF_BLOCKS_PER_SM=" + os.environ.get("VINA_IEKF_BLOCKS_PER_SM", "1")]),
     (os.path.join(CSRC, "ba_kernels.cu"), []),
     (os.path.join(CSRC, "vn_ctx.cu"), []),

@@ -842,6 +842,8 @@ __global__ void __launch_bounds__(128) k_recut_collect(MapView M, LayerLists LL)
 __global__ void __launch_bounds__(128) k_recut_all(MapView M, LayerLists LL)
 {
   vn_pdl_sync();
+  // the lists as they are before any subdivision of this multi_recut (k_split appends the children it creates)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) LL.snap[threadIdx.x] = LL.count[threadIdx.x];
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:150-154
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
@@ -857,7 +859,11 @@ __global__ void __launch_bounds__(128) k_recut_all(MapView M, LayerLists LL)
       prefetch_line(b + offsetof(NodeCold, last_num));
     }
     if (h.flags & VN_FLAG_INTERIOR) continue;
-    if (recut_leaf(M, h, M.cold[n])) LL.split[atomicAdd(&LL.count[4], 1)] = n;
+    if (recut_leaf(M, h, M.cold[n]))
+    {
+      h.flags |= VN_FLAG_SPLIT_PENDING;
+      LL.split[atomicAdd(&LL.count[4], 1)] = n;
+    }
   }
 }
 
@@ -1360,7 +1366,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         c.fix_count = 0;
       }
       c.has_sw = 0;
-      h.flags |= VN_FLAG_INTERIOR;
+      h.flags = (h.flags | VN_FLAG_INTERIOR) & ~VN_FLAG_SPLIT_PENDING;  // (one store: a concurrent margi pass skips both states)
     }
     else if (t >= 32 && t < 32 + M.win_size)
     {
@@ -1534,9 +1540,12 @@ struct MargiShared
 // (BA-factor leaf or not, plane or not, update due or not); the phases are separated by FULL-warp barriers so that
 // the groups reconverge after every phase and run the common ones in lock step - without them four diverged groups
 // execute one after the other and a warp takes the sum of its leaves' times instead of the longest.
+// mode 0: every leaf of the list. mode 1 (runs next to k_split): the leaves multi_recut has not queued for
+// subdivision. mode 2 (after k_split): what mode 1 left out - the children the subdivisions created (list positions
+// >= n_old) and any queued leaf that was not subdivided after all.
 __device__ void margi_warp_pass(const MapView& M, const int* __restrict__ nodes, int nn, int j0, int win_count,
                                 const PoseBuf& xb, const LivePose& lv, int lane, MargiShared* sh4,
-                                const PointRec*& job_src, int& job_off, int& job_np)
+                                const PointRec*& job_src, int& job_off, int& job_np, int mode, int n_old)
 {
   const int g = lane & (MG - 1), grp = lane / MG;
   MargiShared& sh = sh4[grp];
@@ -1548,7 +1557,14 @@ __device__ void margi_warp_pass(const MapView& M, const int* __restrict__ nodes,
   if (j < nn)
   {
     n = nodes[j];
-    active = !(M.hot[n].flags & VN_FLAG_INTERIOR);
+    const int fl = M.hot[n].flags;
+    active = !(fl & VN_FLAG_INTERIOR);
+    if (mode == 1) active = active && !(fl & VN_FLAG_SPLIT_PENDING);
+    if (mode == 2 && j < n_old)
+    {
+      active = active && (fl & VN_FLAG_SPLIT_PENDING);
+      if (active && g == 0) M.hot[n].flags = fl & ~VN_FLAG_SPLIT_PENDING;  // (queued, but not subdivided after all)
+    }
   }
   NodeHot& h = M.hot[n];
   NodeCold& c = M.cold[n];
@@ -1804,15 +1820,21 @@ __device__ void margi_warp_pass(const MapView& M, const int* __restrict__ nodes,
 }
 
 // OctoTree::margi, leaf branch, for every leaf under surf_map_slide (blockIdx.y = layer)
-__global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv)
+__global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists LL, int win_count, PoseBuf xb, LivePose lv, int mode)
 {
   vn_pdl_sync();
   __shared__ MargiShared sh_all[128 / MG];
   // (the slide list the compaction fills after this kernel starts empty)
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) M.slide_count[1 - M.slide_cur] = 0;
+  if (mode != 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) M.slide_count[1 - M.slide_cur] = 0;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
   int nn;
   const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
+  int n_old = nn;  // layer 0 is the slide list: subdivisions add nothing to it
+  if (blockIdx.y > 0 && mode != 0)
+  {
+    n_old = LL.snap[blockIdx.y];
+    if (mode == 1) nn = n_old;  // (k_split may be appending behind it right now)
+  }
   const int lane = threadIdx.x & 31;
   MargiShared* sh4 = sh_all + (threadIdx.x >> 5) * (32 / MG);
   const int gpw = 32 / MG;  // leaves per warp and pass
@@ -1821,7 +1843,7 @@ __global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists L
   {
     const PointRec* job_src = nullptr;
     int job_off = 0, job_np = 0;
-    margi_warp_pass(M, nodes, nn, j0, win_count, xb, lv, lane, sh4, job_src, job_off, job_np);
+    margi_warp_pass(M, nodes, nn, j0, win_count, xb, lv, lane, sh4, job_src, job_off, job_np, mode, n_old);
     __syncwarp();
     // the warp's copy jobs as ONE stream of points, 32 per pass (points go to the world frame of x_buf[0]): a
     // leaf folds only a handful of points per scan, so walking the jobs one after the other would leave most
@@ -2311,9 +2333,54 @@ int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, 
 {
   const LivePose lv = { live, win_count - 1 };
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  vn_launch(k_margi_leaves, dim3(592, map.max_layer + 1), dim3(128), 0, st, map, LL, win_count, b, lv);
+  vn_launch(k_margi_leaves, dim3(592, map.max_layer + 1), dim3(128), 0, st, map, LL, win_count, b, lv, 0);
   vn_launch(k_margi_finish, dim3(592), dim3(128), 0, st, map);
   return 2;
+}
+
+// multi_recut followed by multi_margi of the same frame set (local_mapping.cpp:451, 507 with if_BA == 0), with the
+// subdivisions taken off the critical path: a scan subdivides a dozen leaves, two levels deep, and that is one block's
+// latency per level (~50 us on an otherwise idle GPU) - while the marginalisation of the ~10^4 leaves that are NOT
+// being subdivided does not depend on it. So k_split runs on `side`, k_margi_leaves(mode 1) next to it on `st`, and a
+// second, small k_margi_leaves(mode 2) picks up the children once k_split is through. Per-leaf arithmetic is
+// unchanged; only the order in which independent leaves draw from the fixed-point pool differs.
+int launch_map_recut_margi(cudaStream_t st, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join, const MapView& map,
+                           LayerLists& LL, int win_count, const PoseD* h_xbuf, const IekfDev* live)
+{
+  const LivePose lv = { live, win_count - 1 };
+  static bool attr_set[64] = { false };
+  int dv = 0;
+  cudaGetDevice(&dv);
+  if (!attr_set[dv & 63])
+  {
+    cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPLIT_SMEM);
+    attr_set[dv & 63] = true;
+  }
+  PoseBuf b = make_posebuf(h_xbuf, win_count);
+  int* t = LL.count;
+  LL.count = LL.count_alt;
+  LL.count_alt = t;
+  vn_launch(k_recut_collect, dim3(592), dim3(128), 0, st, map, LL);
+  vn_launch(k_recut_all, dim3(296, map.max_layer + 1), dim3(128), 0, st, map, LL);
+  int launches = 2;
+  if (map.max_layer > 0)
+  {
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    vn_launch(k_split, dim3(296), dim3(SPLIT_THREADS), SPLIT_SMEM, side, map, LL, win_count, b, lv);
+    cudaEventRecord(ev_join, side);
+    vn_launch(k_margi_leaves, dim3(592, map.max_layer + 1), dim3(128), 0, st, map, LL, win_count, b, lv, 1);
+    cudaStreamWaitEvent(st, ev_join, 0);
+    vn_launch(k_margi_leaves, dim3(148, map.max_layer + 1), dim3(128), 0, st, map, LL, win_count, b, lv, 2);
+    launches += 3;
+  }
+  else
+  {
+    vn_launch(k_margi_leaves, dim3(592, map.max_layer + 1), dim3(128), 0, st, map, LL, win_count, b, lv, 0);
+    launches += 1;
+  }
+  vn_launch(k_margi_finish, dim3(592), dim3(128), 0, st, map);
+  return launches + 1;
 }
 
 int launch_ba_collect(cudaStream_t st, const MapView& map, const LayerLists& LL, BaFactor* out, int* count, int cap)

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256)
 // a2 + a3 of the full scan in one pass (the production schedule: VNC_lio runs on the un-downsampled scan,
 // local_mapping.cpp:406-413): deskew, store the float point, var_init from that float value - exactly what the
 // two kernels do one after the other - and reset the IEKF's per-point leaf cache (odometry.cpp:79)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     k_deskew_var_init(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg, int* __restrict__ status,
                       ScanView out, VarInitParams prm, int* __restrict__ cache)
 {

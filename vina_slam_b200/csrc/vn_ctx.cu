@@ -265,6 +265,8 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   CU(cudaMemset(ctx->layers.split, 0xFF, (size_t)cfg.max_nodes * sizeof(int)));  // k_split's queue: -1 = slot not written yet
   CU(dalloc(&ctx->layers.count, 16));
   ctx->layers.count_alt = ctx->layers.count + 8;
+  CU(dalloc(&ctx->layers.snap, 4));
+  if (const char* e = getenv("VINA_SPLIT_OVERLAP")) ctx->split_overlap = atoi(e) != 0;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaDeviceSynchronize());  // the zero-fills of dalloc ran on the legacy stream (see ensure_debug)
   CU(cudaGetLastError());
@@ -403,6 +405,7 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
   if (ctx->h_init_sums) cudaFreeHost(ctx->h_init_sums);
   for (int l = 0; l < 4; l++) cudaFree(ctx->layers.list[l]);
   cudaFree(ctx->layers.split);
+  cudaFree(ctx->layers.snap);
   cudaFree(ctx->layers.count < ctx->layers.count_alt ? ctx->layers.count : ctx->layers.count_alt);
   for (int i = 0; i < 16; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1236,6 +1239,15 @@ int vn_map_margi_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
                                     ctx->d_iekf);
   ctx->map.slide_cur = 1 - ctx->map.slide_cur;
   return VINA_OK;
+}
+
+// multi_recut + multi_margi with the subdivisions next to the marginalisation (launch_map_recut_margi)
+int vn_map_recut_margi_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
+{
+  ctx->launches += launch_map_recut_margi(ctx->stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join, ctx->map, ctx->layers,
+                                          win_count, reinterpret_cast<const PoseD*>(x_buf), ctx->d_iekf);
+  ctx->map.slide_cur = 1 - ctx->map.slide_cur;
+  return vn_check_cuda(ctx, cudaGetLastError(), "recut + margi");
 }
 
 // sizes of the last map update (bench.py: algorithmic bytes of the map stages): [0] points inserted, [1] leaves they

@@ -29,6 +29,7 @@ struct vina_ctx
   // fused front (vn_front_fused): the count arrives through mapped memory, [0] sequence number, [1] count
   bool front_fused = true;
   bool n_down_mapped = false;           // the pending count is the one k_down_emit_all publishes
+  bool split_overlap = false;           // k_split on the side stream next to the marginalisation (launch_map_recut_margi)
   bool batch_member = false;            // the context belongs to a vina_batch
   bool front_was_fused = false;         // the serial step's front went out as the two fused launches
   bool down_retried = false;            // vn_finish_downsample re-ran the down-sampling (< 2000 points rule)
@@ -161,6 +162,7 @@ int vn_fail(vina_ctx* c, int code, const char* fmt, ...);
 int vn_init_ensure(vina_ctx* c);        // buffers of the start-up phase
 int vn_map_clear(vina_ctx* c);          // the map back to its state after vina_ctx_create (motion_init rebuilds it every round)
 // down_sampling_voxel of an arbitrary device cloud (no "< 2000 points" retry); synchronises, returns the count
+int vn_map_recut_margi_live(vina_ctx* c, int win_count, const vina_pose* x_buf);
 int vn_front_fused(vina_ctx* c, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vn_downsample_cloud(vina_ctx* c, const float4* in, int n, double size, float4* out, int* n_out);
 // sum of n n^T over the normals (eigenvector of the smallest eigenvalue) of the collected BA factors, 3x3 column-major

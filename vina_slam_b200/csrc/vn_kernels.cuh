@@ -244,6 +244,8 @@ int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanVie
 int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int win_count, const PoseD* h_xbuf,
                      const IekfDev* live = nullptr);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
+int launch_map_recut_margi(cudaStream_t st, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join, const MapView& map,
+                           LayerLists& LL, int win_count, const PoseD* h_xbuf, const IekfDev* live);
 int launch_map_margi(cudaStream_t st, const MapView& map, const LayerLists& LL, int win_count, const PoseD* h_xbuf,
                      const IekfDev* live = nullptr);
 // BA LiDAR factor (map_kernels.cu: collect; ba_kernels.cu: Hessian / residual). d_out = Hess (6 win)^2, JacT, residual
@@ -277,4 +279,5 @@ struct LayerLists
   int* split;  // leaves to subdivide: the lists of the subdivision rounds, one behind the other
   int* count;  // [0..3] nodes per layer, [4..7] leaves to subdivide per round
   int* count_alt;  // the set the next multi_recut uses (cleared by this one: no launch spent on zeroing)
+  int* snap;       // [4] nodes per layer before the subdivisions of this multi_recut (written by k_recut_all)
 };

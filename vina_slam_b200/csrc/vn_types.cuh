@@ -10,6 +10,7 @@
 
 #define VN_FLAG_PLANE 1     // Plane::is_plane
 #define VN_FLAG_INTERIOR 2  // octo_state == 1
+#define VN_FLAG_SPLIT_PENDING 8  // a leaf multi_recut has queued for subdivision (cleared when k_split turns it interior)
 #define VN_FLAG_DEAD 4      // released by the map pruning (k_prune_*): the record is zero, layer == -1, id on the free stack
 #define VN_KEY_BIAS (1 << 20)
 #define VN_KEY_MASK ((1u << 21) - 1)

@@ -829,22 +829,36 @@ map_part:
   r = vn_map_insert_live(ctx, o->win_count - 1);
   if (r) return r;
   if (tr) cudaEventRecord(ctx->tr_ev[3], A);
-  r = vn_map_recut_live(ctx, o->win_count, o->x_buf.data());
-  if (r) return r;
-  if (tr) cudaEventRecord(ctx->tr_ev[4], A);
   const bool margi = o->win_count >= ctx->cfg.win_size;
-  if (margi && ctx->ba_capture)
+  if (margi && !ctx->ba_capture && ctx->split_overlap && ctx->side_stream)
   {
-    r = vn_ba_collect_enqueue(ctx);
+    // multi_recut and multi_margi as one enqueue: the subdivisions run on the side stream next to the
+    // marginalisation of the leaves they do not touch
+    ctx->map.jour = o->jour;
+    r = vn_map_recut_margi_live(ctx, o->win_count, o->x_buf.data());
     if (r) return r;
-  }
-  if (margi)
-  {
-    ctx->map.jour = o->jour;  // (the journey only advances after multi_margi: known before the pose is)
-    r = vn_map_margi_live(ctx, o->win_count, o->x_buf.data());
-    if (r) return r;
+    if (tr) cudaEventRecord(ctx->tr_ev[4], A);
     r = vina_map_shift_window(ctx);
     if (r) return r;
+  }
+  else
+  {
+    r = vn_map_recut_live(ctx, o->win_count, o->x_buf.data());
+    if (r) return r;
+    if (tr) cudaEventRecord(ctx->tr_ev[4], A);
+    if (margi && ctx->ba_capture)
+    {
+      r = vn_ba_collect_enqueue(ctx);
+      if (r) return r;
+    }
+    if (margi)
+    {
+      ctx->map.jour = o->jour;  // (the journey only advances after multi_margi: known before the pose is)
+      r = vn_map_margi_live(ctx, o->win_count, o->x_buf.data());
+      if (r) return r;
+      r = vina_map_shift_window(ctx);
+      if (r) return r;
+    }
   }
   if (tr) th[4] = now_us(), cudaEventRecord(ctx->tr_ev[5], A);
   // the result of the loop (it landed while the map update was being enqueued)
