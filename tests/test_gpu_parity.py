@@ -1297,7 +1297,8 @@ def test_odometry_with_map_pruning_stays_on_the_oracle_trajectory(oracle_lib, gp
 
 
 def test_scan_front_end_matches_oracle(oracle_lib, gpu_lib):
-    """vina_scan_prepare (decoder keep rule + pcl_handler on the device: filter, stable radix sort by time offset,
+    """vina_scan_prepare (decoder keep rule + pcl_handler on the device: filter, stable sort by time offset - one
+    bucket pass by time and a shared-memory sort per bucket, the radix passes when a bucket overflows -
     cut at 0.11 s) against the oracle's restatement, bit for bit including the order of equal stamps: many ties,
     blind-zone points, decimation, stamps beyond the cut, negative stamps, sizes around the sort's tile, the empty
     cloud's two-point stand-in, the error the reference cannot survive, and the device-pointer entry."""
@@ -1328,6 +1329,14 @@ def test_scan_front_end_matches_oracle(oracle_lib, gpu_lib):
         g = gx.scan_download(k)
         assert k == o.shape[0] and np.array_equal(g, o), (n, pfn, k, o.shape)
         assert tl == o[-1, 3]
+    # one stamp for the whole scan (and a scan with 3 distinct stamps): the time buckets of the fast path overflow
+    # shared memory and the radix passes take over - same result
+    for stamps in (1, 3):
+        a = cloud(60000, True)
+        a[:, 3] = (rng.integers(0, stamps, a.shape[0]).astype(np.float32) * np.float32(0.03) + np.float32(0.02))
+        o = oracle_lib.scan_prepare(a, 1, 0.01)
+        k, tl = gx.scan_prepare(a, 1, 0.01)
+        assert k == o.shape[0] and np.array_equal(gx.scan_download(k), o) and tl == o[-1, 3]
     a = cloud(70000, False)
     o = oracle_lib.scan_prepare(a, 2, 0.25)
     d = torch.from_numpy(a).cuda()

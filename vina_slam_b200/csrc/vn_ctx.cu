@@ -379,6 +379,9 @@ extern "C" void vina_ctx_destroy(vina_ctx* ctx)
     cudaFree(ctx->d_fidx[k]);
   }
   cudaFree(ctx->d_fhist);
+  cudaFree(ctx->d_fbkt);
+  if (ctx->h_front_pub) cudaFreeHost(ctx->h_front_pub);
+  cudaFree(ctx->d_fpairs);
   cudaFree(ctx->d_fcnt);
   if (ctx->h_fcnt) cudaFreeHost(ctx->h_fcnt);
   cudaFree(M.free_nodes);
@@ -501,6 +504,11 @@ static int ensure_front(vina_ctx* ctx)
     CU(dalloc(&ctx->d_fidx[k], cap, false));
   }
   CU(dalloc(&ctx->d_fhist, 256 * (cap / 2048 + 1)));
+  CU(dalloc(&ctx->d_fbkt, 3 * 1024 + 8));
+  CU(cudaHostAlloc((void**)&ctx->h_front_pub, 64, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&ctx->d_front_pub, ctx->h_front_pub, 0));
+  memset(ctx->h_front_pub, 0, 64);
+  CU(dalloc(&ctx->d_fpairs, cap, false));
   CU(dalloc(&ctx->d_fcnt, 4));
   CU(cudaHostAlloc((void**)&ctx->h_fcnt, 4 * sizeof(int), cudaHostAllocDefault));
   CU(cudaDeviceSynchronize());
@@ -515,10 +523,37 @@ static int front_run(vina_ctx* ctx, const float4* d_raw, int n, int point_filter
   float tl = 0.f;
   if (n > 0)
   {
-    ctx->launches += launch_front_prepare(ctx->stream, d_raw, n, point_filter_num, blind2, ctx->d_fkey, ctx->d_fidx,
-                                          ctx->d_fhist, ctx->d_fcnt, ctx->d_scan, reinterpret_cast<float*>(ctx->d_fcnt + 2));
-    CU(cudaMemcpyAsync(ctx->h_fcnt, ctx->d_fcnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    // one bucket pass by time + a shared-memory sort per bucket; the radix passes only if a bucket overflowed
+    // (VINA_FRONT_RADIX=1 forces them)
+    static const bool force_radix = getenv("VINA_FRONT_RADIX") && atoi(getenv("VINA_FRONT_RADIX")) != 0;
+    if (!force_radix)
+    {
+      const unsigned long long seq = ++ctx->front_seq;
+      ctx->launches += launch_front_prepare_buckets(ctx->stream, d_raw, n, point_filter_num, blind2, ctx->d_fidx[0], ctx->d_fbkt,
+                                                    ctx->d_fpairs, ctx->d_scan, ctx->d_front_pub, seq);
+      // the counters arrive through mapped memory (written by the block that finishes last)
+      volatile unsigned long long* pub = ctx->h_front_pub;
+      for (long spins = 0; pub[0] != seq; spins++)
+        if ((spins & 0xfff) == 0xfff)
+        {
+          cudaError_t e = cudaStreamQuery(ctx->stream);
+          if (e == cudaSuccess)
+          {
+            if (pub[0] == seq) break;
+            return vn_fail(ctx, VINA_E_CUDA, "the scan front end finished without publishing its counters");
+          }
+          if (e != cudaErrorNotReady) return vn_check_cuda(ctx, e, "scan front end");
+        }
+      __sync_synchronize();
+      for (int k = 0; k < 4; k++) ctx->h_fcnt[k] = (int)(unsigned int)pub[1 + k];
+    }
+    if (force_radix || ctx->h_fcnt[3])
+    {
+      ctx->launches += launch_front_prepare(ctx->stream, d_raw, n, point_filter_num, blind2, ctx->d_fkey, ctx->d_fidx,
+                                            ctx->d_fhist, ctx->d_fcnt, ctx->d_scan, reinterpret_cast<float*>(ctx->d_fcnt + 2));
+      CU(cudaMemcpyAsync(ctx->h_fcnt, ctx->d_fcnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
     kept = ctx->h_fcnt[0];
     keep = ctx->h_fcnt[1];
     memcpy(&tl, &ctx->h_fcnt[2], 4);

@@ -49,6 +49,11 @@ struct vina_ctx
   unsigned int* d_fkey[2] = { nullptr, nullptr };
   int* d_fidx[2] = { nullptr, nullptr };
   int* d_fhist = nullptr;
+  unsigned long long* h_front_pub = nullptr;  // mapped: [0] sequence number, [1..4] the counters of k_front_sort
+  unsigned long long* d_front_pub = nullptr;
+  unsigned long long front_seq = 0;
+  int* d_fbkt = nullptr;                    // bucket counts + cursors of the front end's fast path (2 x 1024)
+  unsigned long long* d_fpairs = nullptr;   // (time key, arrival index) pairs grouped by bucket
   int* d_fcnt = nullptr;     // 2 counters + the last point's time offset
   int* h_fcnt = nullptr;     // pinned copy
   float front_t_last = 0.f;  // time offset of the last point of the prepared scan (pcl_end_time - pcl_beg_time)

@@ -190,6 +190,9 @@ void launch_publish_iterate(cudaStream_t st, const IekfDev* src, IekfDev* dst_ma
 
 // front_kernels.cu: decoder keep rule + pcl_handler (filter, stable radix sort by time offset, cut at 0.11 s).
 // counters: [0] kept by the decoder rule, [1] of those within 0.11 s (= points written to `out`, time-sorted)
+int launch_front_prepare_buckets(cudaStream_t st, const float4* raw, int n, int point_filter_num, double blind, int* bkt_of,
+                                 int* work, unsigned long long* pairs, float4* out, unsigned long long* pub_mapped,
+                                 unsigned long long seq);
 int launch_front_prepare(cudaStream_t st, const float4* raw, int n, int point_filter_num, double blind2,
                          unsigned int* key[2], int* idx[2], int* hist, int* counters, float4* out, float* t_last);
 
