@@ -340,6 +340,7 @@ __device__ __forceinline__ void iekf_solve_block(IekfDev* dev, const double* fin
 template <bool DEBUG>
 __global__ void __launch_bounds__(IEKF_THREADS, IEKF_BLOCKS_PER_SM) k_iekf(const __grid_constant__ IekfBatch bt)
 {
+  vn_pdl_sync();  // (does nothing unless the launch carries the programmatic attribute: launch_iekf, `pdl`)
   const IekfSeq& q = bt.s[blockIdx.y];
   IekfDev* __restrict__ dev = q.dev;
   if ((bt.mode & (VN_IEKF_SOLVE | VN_IEKF_GATED)) && dev->done) return;  // converged earlier (uniform over the grid)
@@ -1268,7 +1269,7 @@ int iekf_grid_blocks(int n, int sm_count)
   return need < cap ? need : cap;
 }
 
-int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug)
+int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug, bool pdl)
 {
   static bool attr_set_dev[64] = { false };
   int dv = 0;
@@ -1285,11 +1286,14 @@ int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool
   dim3 grid(blocks, nseq);
   if (debug)
     k_iekf<true><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);
+  else if (pdl)
+    vn_launch(k_iekf<false>, grid, dim3(IEKF_THREADS), IEKF_SMEM, st, bt);
   else
-    k_iekf<false><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);  // (no programmatic launch here: the next iteration's
-                                                                // blocks would sit on the SMs through this one's tail - the
-                                                                // reduction and the update in the last block - and keep the
-                                                                // side stream's kernels out)
+    k_iekf<false><<<grid, IEKF_THREADS, IEKF_SMEM, st>>>(bt);  // (no programmatic launch for the first iterations: the next
+                                                                // one's blocks would sit on the SMs through this one's tail -
+                                                                // the reduction and the update in the last block - and keep
+                                                                // the side stream's kernels out; from the third launch on the
+                                                                // side stream is through and most launches are no-ops)
   return (int)cudaGetLastError();
 }
 

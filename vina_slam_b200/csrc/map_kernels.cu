@@ -613,18 +613,50 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
         }
         __syncwarp();
         const int mh = min(ACC_RED_ROWS, m - ACC_RED_ROWS * part);
-        for (int r = 0; r < mh; r++)
+        if (mh == ACC_RED_ROWS)
         {
-          s0 += red[r][lane];
-          if (has2) s1 += red[r][lane + 32];
+          // (straight-line: a counted loop costs ~20 cycles of branch per row on top of the 10-cycle add)
+#pragma unroll
+          for (int r = 0; r < ACC_RED_ROWS; r++)
+          {
+            s0 += red[r][lane];
+            if (has2) s1 += red[r][lane + 32];
+          }
         }
+        else
+          for (int r = 0; r < mh; r++)
+          {
+            s0 += red[r][lane];
+            if (has2) s1 += red[r][lane + 32];
+          }
         __syncwarp();
       }
       // lanes 0..8: pcr_add (world point), lanes 9..17: pcrs_local[slot] (body point); L.ck = lane % 9
       if (lane < 18)
       {
         const int col = lane;  // 0..8 world terms, 9..17 body terms
-        for (int r = 0; r < m; r++) cl = da(cl, pt[r][col]);
+        if (m == 32)
+        {
+          // a full batch, straight-line: the 32 loads go out ahead of the chain of dependent adds
+          double v[32];
+#pragma unroll
+          for (int r = 0; r < 32; r++) v[r] = pt[r][col];
+#pragma unroll
+          for (int r = 0; r < 32; r++) cl = da(cl, v[r]);
+        }
+        else
+        {
+          int r = 0;
+          for (; r + 8 <= m; r += 8)
+          {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = pt[r + u][col];
+#pragma unroll
+            for (int u = 0; u < 8; u++) cl = da(cl, v[u]);
+          }
+          for (; r < m; r++) cl = da(cl, pt[r][col]);
+        }
       }
       cv0 += s0;
       cv1 += s1;

@@ -178,7 +178,7 @@ int launch_init_redeskew(cudaStream_t st, const float4* orig, int n, int n_skip,
 // iekf_kernel.cu
 int iekf_grid_blocks(int n, int sm_count);
 // grid = (blocks, nseq); every sequence gets `blocks` persistent 1024-thread blocks
-int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug);
+int launch_iekf(cudaStream_t st, const IekfBatch& bt, int nseq, int blocks, bool debug, bool pdl = false);
 int iekf_loop_chunk(int n, int blocks);
 int launch_iekf_loop(cudaStream_t st, const IekfLoop& a, int blocks);
 void launch_fill_int(cudaStream_t st, int* p, int v, int n);

@@ -484,7 +484,7 @@ static int iekf_enqueue_device(vina_ctx* ctx, OdomHost* o, int which, int num_ma
   for (int it = 0; it < num_max_iter; it++)
   {
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it], ctx->stream);
-    int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false);
+    int e = launch_iekf(ctx->stream, bt, 1, ctx->iekf_blocks, false, it >= 2 && !ctx->profiling);
     if (e) return vn_check_cuda(ctx, (cudaError_t)e, "k_iekf launch");
     ctx->launches += 1;
     if (ctx->profiling) cudaEventRecord(ctx->iekf_ev[2 * it + 1], ctx->stream);
