@@ -290,19 +290,27 @@ def main_ours(args, cfg):
     miss = (n_mean + (iters_per_step - 1) * n_mean * (1 - match_frac)) / max(iters_per_step, 1)
     bytes_per_launch = 80.0 * n_mean + 256.0 * U + 16.0 * miss + 34 * 8
     launch_ms = iekf_kernel_ms / max(iters, 1)
+    # VINA_IEKF_LOOP=1 (opt-in schedule): ONE persistent launch runs all iterations of a scan - the units of a launch
+    # are (point, iteration) evaluations, its algorithmic bytes the per-iteration figure x the iterations it ran
+    loop_mode = os.environ.get("VINA_IEKF_LOOP", "0") not in ("", "0")
+    roof_kernel, roof_launches = "k_iekf", iters
+    if loop_mode:
+        bytes_per_launch *= iters_per_step
+        launch_ms = iekf_kernel_ms / max(K, 1)
+        roof_kernel, roof_launches = "k_iekf_loop (all iterations of a scan in one launch)", K
     # dram__bytes_read + write per launch from the committed `ncu --set full` capture of this kernel - valid only for the
     # workload it was taken on and for as long as the kernel's source is the one that was profiled
     traffic, traffic_source = None, None
     try:
         import hashlib
 
-        with open(os.path.join(ROOT, "profiles", "r02_iekf_ncu_full_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02b_iekf_ncu_full_summary.json")) as f:
             cap = json.load(f)
         with open(os.path.join(ROOT, "vina_slam_b200", "csrc", "iekf_kernel.cu"), "rb") as f:
             sha = hashlib.sha256(f.read()).hexdigest()[:16]
         if cfg.name == cap.get("workload") and sha == cap.get("kernel_source_sha256_16"):
             traffic = cap["dram_traffic_bytes_per_launch"]
-            traffic_source = "profiles/r02_iekf_ncu_full_summary.json (ncu --set full, same kernel source %s)" % sha
+            traffic_source = "profiles/r02b_iekf_ncu_full_summary.json (ncu --set full, same kernel source %s)" % sha
         else:
             traffic_source = "none: the committed ncu capture is of another workload or kernel source"
     except Exception:
@@ -335,7 +343,11 @@ def main_ours(args, cfg):
 
     # ---- leg 2: end to end from pinned host buffers ---------------------------------------------------
     gx = new_ctx()
-    pinned = [torch.from_numpy(sc.xyzt).pin_memory() for sc in scans]
+    gx.set_upload_ordered(True)  # the step's host-to-device copy starts behind e0 (not while the L2 flush is still running)
+    # a ring of two pinned buffers, refilled by the host right before the step (outside the timed region) like a driver /
+    # decoder would: the DMA then reads lines the CPU has just written instead of host memory that was last touched
+    # seconds ago (a 3.84 MB copy: 76 us vs ~125 us on this box, scripts/h2d_probe.py)
+    ring = [torch.empty((max(sc.xyzt.shape[0] for sc in scans), 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(W + K)]
     iters_e2e = 0
@@ -343,9 +355,11 @@ def main_ours(args, cfg):
     for k, sc in enumerate(scans):
         if k == W:
             barrier()
+        buf = ring[k & 1][:sc.xyzt.shape[0]]
+        buf.numpy()[...] = sc.xyzt
         flush.fill_(k & 0xFF)
         e0[k].record(stream)
-        gx.step(pinned[k].numpy(), sc.beg_time, sc.imu, True, MAX_ITER)
+        gx.step(buf.numpy(), sc.beg_time, sc.imu, True, MAX_ITER)
         e1[k].record(stream)
         if k >= W:
             iters_e2e += gx.timings().iekf_iters
@@ -463,22 +477,31 @@ def main_ours(args, cfg):
                        "l2": "256 MiB buffer written between timed steps (L2 flush); steps timed individually "
                              "with CUDA events on the launching stream and summed; stage_ms / roofline launch times "
                              "come from a second, instrumented pass over the same scans",
+                       "schedule": {"iekf": "k_iekf_loop: one persistent cooperative launch per scan" if loop_mode else
+                                    "one k_iekf launch per iteration (832-thread blocks), update in the last block",
+                                    "programmatic_dependent_launch": os.environ.get("VINA_PDL", "1") != "0",
+                                    "side_stream": "down-sampling + var_init of the map's point set next to the IEKF launches"
+                                    if not loop_mode else "none (two fused front launches in stream order)"},
                        "iekf_iters_per_step": iters_per_step, "gt_traj_err_m": traj_err,
                        **({"ba": {"runs_in_timed_steps": ba_runs, "lm_iters_last": ba_iters,
                                   "note": "LI_BA_Optimizer every scan: IMU factors + LM on the host, LiDAR factor "
                                           "(Hessian / residual over the plane voxels of the window) on the device"}}
                           if args.ba else {})},
             "e2e": {"value": pts_all / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K,
+                    "how": "vina_odom_step from a ring of two pinned host buffers refilled before every step; the "
+                           "host-to-device copy is ordered behind the step's first CUDA event (vina_set_upload_ordered), so "
+                           "it lies inside the timed region and cannot start while the L2 flush is still running; the "
+                           "converged iterate comes back through mapped host memory",
                     # scan (16 B / point) + pose table (DeskewPoses) + the iterate (IekfDev, 2 616 B) up; the
                     # converged iterate + its sequence number + the down-sampled count back
                     "h2d_bytes_per_step": int(16 * n_mean + 17096 + 2616),
                     "d2h_bytes_per_step": 2616 + 8 + 4},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_iekf", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
                          "traffic_source": traffic_source,
                          "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_us": 1e3 * launch_ms,
-                         "launches_timed": iters, "unique_leaves": U, "match_frac": match_frac},
+                         "launches_timed": roof_launches, "unique_leaves": U, "match_frac": match_frac},
             "stage_ms": stage,
             "roofline_stages": {"note": "every stage of the step: algorithmic bytes (SURVEY 8d) / device time of the "
                                         "instrumented pass / measured HBM peak; units: points inserted %.0f, leaves "

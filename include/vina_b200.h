@@ -484,6 +484,11 @@ int vina_set_profiling(vina_ctx* ctx, int on);
  * stream order with the host in between (the schedule the per-stage timers of vina_set_profiling see). Both give
  * bitwise the same states and maps. */
 int vina_set_overlap(vina_ctx* ctx, int on);
+/* on: the host-to-device copy of vina_odom_step starts only behind the work that is already on the context's stream
+ * when the call is made (default off: the copy runs on its own stream as early as the scan buffer is free and
+ * overlaps the previous scan's map update). For timing a step end to end with events on that stream: with the
+ * option on the copy lies inside the bracketed region. */
+int vina_set_upload_ordered(vina_ctx* ctx, int on);
 /* the IEKF iteration loop of LioStateEstimation (odometry.cpp:98-231) inside vina_odom_step as ONE persistent
  * cooperative launch (k_iekf_loop: scan resident in shared memory over the iterations, grid barrier and the a7
  * update between them; the front of the step then goes out as two fused launches in stream order). Default off =

@@ -73,7 +73,7 @@ EXPORTS = [
     "vina_shard_query_accumulate", "vina_odom_iekf_host_begin", "vina_odom_iekf_host_update",
     "vina_shard_p2p_create", "vina_shard_p2p_connect", "vina_shard_p2p_pointers", "vina_shard_p2p_connect_local",
     "vina_shard_route_p2p", "vina_shard_insert_begin_p2p", "vina_odom_iekf_sharded_p2p",
-    "vina_set_overlap", "vina_set_iekf_loop", "vina_ba_set_capture", "vina_ba_collect", "vina_ba_count", "vina_ba_lidar_hessian",
+    "vina_set_overlap", "vina_set_upload_ordered", "vina_set_iekf_loop", "vina_ba_set_capture", "vina_ba_collect", "vina_ba_count", "vina_ba_lidar_hessian",
     "vina_ba_lidar_residual", "vina_odom_set_ba", "vina_odom_ba_stats",
     "vina_ba_imu_evaluate", "vina_ba_solve",
     "vina_map_set_journey", "vina_map_prune", "vina_odom_journey", "vina_odom_idle",
@@ -491,6 +491,9 @@ class Ctx:
 
     def set_overlap(self, on: bool):
         self._ck(self.lib.vina_set_overlap(self.h, C.c_int(1 if on else 0)))
+
+    def set_upload_ordered(self, on: bool):
+        self._ck(self.lib.vina_set_upload_ordered(self.h, C.c_int(1 if on else 0)))
 
     def set_iekf_loop(self, on: bool):
         self._ck(self.lib.vina_set_iekf_loop(self.h, C.c_int(1 if on else 0)))

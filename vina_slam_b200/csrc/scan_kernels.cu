@@ -216,17 +216,22 @@ __global__ void __launch_bounds__(256)
 // a2 + a3 of the full scan in one pass (the production schedule: VNC_lio runs on the un-downsampled scan,
 // local_mapping.cpp:406-413): deskew, store the float point, var_init from that float value - exactly what the
 // two kernels do one after the other - and reset the IEKF's per-point leaf cache (odometry.cpp:79)
+// [first, last) = the part of the scan this launch covers: a scan that is still arriving from the host is processed
+// chunk by chunk behind the chunks' copies (vn_deskew_var_init). The sortedness check of the contract looks at the
+// right-hand neighbour, which for the last point of a chunk may not have landed yet: a chunk checks its first point
+// against the point before it instead.
 __global__ void __launch_bounds__(256, 3)
     k_deskew_var_init(float4* __restrict__ pts, int n, const DeskewPoses* __restrict__ Pg, int* __restrict__ status,
-                      ScanView out, VarInitParams prm, int* __restrict__ cache)
+                      ScanView out, VarInitParams prm, int* __restrict__ cache, int first, int last)
 {
   vn_pdl_sync();
   __shared__ DeskewPoses P;
   stage_poses(P, Pg);
   __syncthreads();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 r = deskew_point(P, pts, i, n, status);
+  int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= last) return;
+  if (i == first && i > 0 && pts[i].w < pts[i - 1].w) atomicOr(status, VN_ST_UNSORTED);
+  const float4 r = deskew_point(P, pts, i, last, status);
   pts[i] = r;
   var_init_point(r, i, out, prm);
   cache[i] = -1;
@@ -494,7 +499,11 @@ __global__ void __launch_bounds__(1024) k_scan_block(const int* __restrict__ in,
   if (i < n) out[i] = incl - v;
   if (threadIdx.x == 1023) block_sums[blockIdx.x] = incl;
 }
-__global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ block_sums, int nb, int* __restrict__ total)
+// (the total also goes to mapped host memory, then the sequence number the host polls: the host has the down-sampled
+// count a few microseconds after this kernel, without a copy or a stream synchronisation - it can enqueue the map
+// update while the emission and the IEKF loop are still running)
+__global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ block_sums, int nb, int* __restrict__ total,
+                                                    volatile unsigned long long* __restrict__ pub, unsigned long long seq)
 {
   vn_pdl_sync();
   __shared__ int warp_sums[32];
@@ -521,7 +530,16 @@ __global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ block_sums
   __syncthreads();
   int incl = x + (w > 0 ? warp_sums[w - 1] : 0);
   if (threadIdx.x < nb) block_sums[threadIdx.x] = incl - v;
-  if (threadIdx.x == 1023) *total = incl;
+  if (threadIdx.x == 1023)
+  {
+    *total = incl;
+    if (pub)
+    {
+      pub[1] = (unsigned long long)(unsigned int)incl;
+      __threadfence_system();
+      pub[0] = seq;
+    }
+  }
 }
 
 // emit voxel means in first-point order and clean the table slot for the next scan
@@ -876,9 +894,11 @@ void launch_deskew(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_pos
   k_deskew<<<(n + 255) / 256, 256, 0, st>>>(pts, n, d_poses, status);
 }
 void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
-                            const VarInitParams& prm, int* cache)
+                            const VarInitParams& prm, int* cache, int first, int last)
 {
-  if (n > 0) vn_launch(k_deskew_var_init, dim3((n + 255) / 256), dim3(256), 0, st, pts, n, d_poses, status, out, prm, cache);
+  if (last > first)
+    vn_launch(k_deskew_var_init, dim3((last - first + 255) / 256), dim3(256), 0, st, pts, n, d_poses, status, out, prm, cache,
+              first, last);
 }
 void launch_deskew_var_init_down(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
                                  const VarInitParams& prm, int* cache, double voxel_size, DownSlot* tab, unsigned int mask,
@@ -908,7 +928,8 @@ void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots)
   k_down_init<<<(nslots + 255) / 256, 256, 0, st>>>(tab, nslots);
 }
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
-                      int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status)
+                      int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status,
+                      unsigned long long* pub, unsigned long long seq)
 {
   if (n <= 0) return 0;
   int nb = (n + 1023) / 1024;
@@ -916,7 +937,7 @@ int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_si
   vn_launch(k_down_accum, dim3((n + 255) / 256), dim3(256), 0, st, pts, n, voxel_size, tab, mask, slot_of, status);
   vn_launch(k_down_flag, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag);
   vn_launch(k_scan_block, dim3(nb), dim3(1024), 0, st, flag, scan, n, block_sums);
-  vn_launch(k_scan_sums, dim3(1), dim3(1024), 0, st, block_sums, nb, n_out_dev);
+  vn_launch(k_scan_sums, dim3(1), dim3(1024), 0, st, block_sums, nb, n_out_dev, pub, seq);
   vn_launch(k_down_emit, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag, scan, block_sums, out);
   return 5;
 }

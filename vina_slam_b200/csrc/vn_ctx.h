@@ -88,6 +88,13 @@ struct vina_ctx
   cudaEvent_t ev_scan_up = nullptr;    // the upload into d_scan has landed
   cudaEvent_t ev_scan_rd = nullptr;    // the last enqueued reader of d_scan is done
   bool scan_rd_valid = false;
+  // vina_odom_step: the scan is uploaded in chunks, and the fused deskew kernel follows chunk by chunk (the copy of a
+  // 240 000-point scan takes ~3x as long as its deskew: only the last chunk's kernel is left behind the copy)
+  cudaEvent_t ev_chunk[4] = { nullptr, nullptr, nullptr, nullptr };
+  int upload_chunks = 0;        // > 0: chunks of the scan in d_scan whose events the deskew still has to wait for
+  int chunk_end[4] = { 0, 0, 0, 0 };
+  bool upload_ordered = false;  // vina_set_upload_ordered: the upload starts behind the work already on the stream
+  cudaEvent_t ev_step_begin = nullptr;
   bool overlap = true;                 // vina_set_overlap: the per-scan step forks / hands the pose over on the device
   cudaStream_t side_stream = nullptr;  // down-sampling + var_init of the map's point set, concurrent with the IEKF
   cudaEvent_t ev_fork = nullptr;       // the deskewed scan is ready (compute stream -> side stream)
@@ -168,6 +175,8 @@ int vn_init_ensure(vina_ctx* c);        // buffers of the start-up phase
 int vn_map_clear(vina_ctx* c);          // the map back to its state after vina_ctx_create (motion_init rebuilds it every round)
 // down_sampling_voxel of an arbitrary device cloud (no "< 2000 points" retry); synchronises, returns the count
 int vn_map_recut_margi_live(vina_ctx* c, int win_count, const vina_pose* x_buf);
+int vn_scan_upload_chunked(vina_ctx* c, const float* xyzt, int n);
+int vn_settle_upload(vina_ctx* c);
 int vn_front_fused(vina_ctx* c, const vina_imu_pose* poses, int m, const double R_end[9], const double p_end[3]);
 int vn_downsample_cloud(vina_ctx* c, const float4* in, int n, double size, float4* out, int* n_out);
 // sum of n n^T over the normals (eigenvector of the smallest eigenvalue) of the collected BA factors, 3x3 column-major

@@ -139,7 +139,7 @@ void launch_var_init(cudaStream_t st, const float4* pts, const int* n_dev, int n
                      const VarInitParams& prm);
 // deskew + var_init of the full scan + leaf-cache reset in one pass
 void launch_deskew_var_init(cudaStream_t st, float4* pts, int n, const DeskewPoses* d_poses, int* status, ScanView out,
-                            const VarInitParams& prm, int* cache);
+                            const VarInitParams& prm, int* cache, int first, int last);
 // the fused front of the per-scan step: deskew + var_init + cache reset + the accumulation pass of the down-sampling,
 // then ONE cooperative launch for the rest of the down-sampling and the var_init of the emitted set
 struct DownEmit
@@ -164,7 +164,8 @@ void launch_deskew_var_init_down(cudaStream_t st, float4* pts, int n, const Desk
 int launch_down_emit_all(cudaStream_t st, DownEmit& a, int sm_count);
 void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots);
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
-                      int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status);
+                      int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status,
+                      unsigned long long* pub = nullptr, unsigned long long seq = 0);
 
 // start-up phase (scan_kernels.cu): kd-tree IEKF association / sums, local-map append, motion_init's re-deskew
 struct InsertScratch;

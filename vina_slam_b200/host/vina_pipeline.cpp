@@ -753,6 +753,8 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
     // launches in stream order instead - deskew + var_init + cache reset + the accumulation pass of the down-sampling,
     // then the rest of the down-sampling with the var_init of the map's point set - and the loop follows. The
     // down-sampled count reaches the host through mapped memory while the loop runs.
+    r = vn_settle_upload(ctx);
+    if (r) return r;
     r = vn_front_fused(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
     if (r) return r;
     r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
@@ -908,7 +910,9 @@ static int odom_step_resident(vina_ctx* ctx, OdomHost* o, double pcl_beg_time, d
     return odom_step_overlapped(ctx, o, pcl_beg_time, pcl_end_time, imus, m, max_iter, x_out);
   const int l0 = ctx->launches;
   int which = 1, ok = 0;
-  int r = step_front(ctx, o, pcl_beg_time, pcl_end_time, imus, m, iekf_on_full, &which);
+  int r = vn_settle_upload(ctx);
+  if (r) return r;
+  r = step_front(ctx, o, pcl_beg_time, pcl_end_time, imus, m, iekf_on_full, &which);
   if (r) return r;
   r = lio_state_estimation(ctx, o, which, max_iter, &ok);
   if (r) return r;
@@ -1116,7 +1120,9 @@ int vina_odom_step(vina_ctx* ctx, const float* xyzt, int n, double pcl_beg_time,
                    int iekf_on_full, int max_iter, vina_state* x_out)
 {
   if (!ctx || !xyzt || !imus || n <= 0 || m <= 0) return VINA_E_ARG;
-  int r = vina_scan_upload(ctx, xyzt, n);
+  // (in chunks, the compute stream not waiting yet: the overlapped step's fused deskew follows the chunks; every other
+  // path lets the stream wait for the whole upload first)
+  int r = vn_scan_upload_chunked(ctx, xyzt, n);
   if (r) return r;
   // pcl_end_time = pcl_beg_time + back().curvature (sync.cpp:40)
   return odom_step_resident(ctx, odom(ctx), pcl_beg_time, pcl_beg_time + (double)xyzt[4 * (size_t)(n - 1) + 3], imus, m,
