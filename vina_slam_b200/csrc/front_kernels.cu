@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) k_front_gather(const float4* __restrict__
 // stamp, say) raises counters[3] and the caller falls back to the radix passes below.
 #define FB_BUCKETS 1024
 #define FB_CAP 4096  // pairs per bucket the shared-memory sort takes
+#define FB_TILE 512  // points per block of the scatter pass
 __device__ __forceinline__ int time_bucket(float t)
 {
   const float x = t * (float)(FB_BUCKETS / 0.11);  // monotone in t (one rounding), like the conversion below
@@ -234,10 +235,10 @@ __global__ void __launch_bounds__(256) k_front_scatter(const float4* __restrict_
   bucket_offsets(counts, offs, wsum);
   if (blockIdx.x == 0)  // the sort kernel's blocks read their first output position from here
     for (int k = threadIdx.x; k < FB_BUCKETS; k += 256) offs_g[k] = offs[k];
-  const int base = blockIdx.x * SORT_TILE;
-  for (int r = 0; r < SORT_ROUNDS; r++)
+  const int base = blockIdx.x * FB_TILE;
+  for (int r = 0; r < FB_TILE / 256; r++)
   {
-    const int i = base + r * SORT_THREADS + threadIdx.x;
+    const int i = base + r * 256 + threadIdx.x;
     if (i >= n) break;
     const int b = bkt_of[i];
     if (b < 0) continue;
@@ -314,7 +315,7 @@ int launch_front_prepare_buckets(cudaStream_t st, const float4* raw, int n, int 
                                  int* work, unsigned long long* pairs, float4* out, unsigned long long* pub_mapped,
                                  unsigned long long seq)
 {
-  const int nb = (n + SORT_TILE - 1) / SORT_TILE;
+  const int nb = (n + FB_TILE - 1) / FB_TILE;
   int* counts = work;
   int* cursors = work + FB_BUCKETS;
   int* counters = work + 2 * FB_BUCKETS;
