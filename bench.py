@@ -62,8 +62,44 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self._halt = threading.Event()
+        self._nv = None
+        try:  # NVML is initialised here, before the timed region starts (nvmlInit alone takes longer than 20 steps)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            hs = [nv.nvmlDeviceGetHandleByIndex(int(i)) for i in str(self.index).split(",")]
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(hs[0], nv.NVML_CLOCK_SM))
+            self._nv = (nv, hs)
+        except Exception:
+            self._nv = None
+
+    def _run_nvml(self):
+        """In-process NVML (the same counters nvidia-smi prints, without a subprocess that takes the driver's lock for
+        tens of milliseconds in the middle of a 10 ms timed region). False if NVML is not usable here."""
+        if self._nv is None:
+            return False
+        nv, hs = self._nv
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while True:
+            try:
+                for h in hs:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for nm, b in bits.items():
+                        if r & b:
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            if self._halt.wait(0.002):
+                break
+        return True
 
     def run(self):
+        if self._run_nvml():
+            return
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -87,7 +123,8 @@ class ClockSampler(threading.Thread):
         self._halt.set()
         self.join(timeout=3)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": getattr(self, "source", None)}
 
 
 def gen_sequence(cfg, seed, n_boot, n_steps):
@@ -470,7 +507,8 @@ def main_ours(args, cfg):
                    "stage_ms": dict(zip(["odom", "insert", "recut", "margi"], r["stage_ms"]))}
         line = {
             "metric": METRIC, "value": pts_all / t_res, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * t_res / K, "ms_per_step_median": float(np.median(step_ms)),
+            "ms_per_step_max": float(np.max(step_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg), "max_iter": MAX_ITER, "iekf_on": "full scan",
                        "vnc_terms": False, "if_BA": int(args.ba), "parallelism": f"replicas x{world}",
@@ -488,6 +526,7 @@ def main_ours(args, cfg):
                                           "(Hessian / residual over the plane voxels of the window) on the device"}}
                           if args.ba else {})},
             "e2e": {"value": pts_all / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / K,
+                    "ms_per_step_median": float(np.median(e2e_ms)), "ms_per_step_max": float(np.max(e2e_ms)),
                     "how": "vina_odom_step from a ring of two pinned host buffers refilled before every step; the "
                            "host-to-device copy is ordered behind the step's first CUDA event (vina_set_upload_ordered), so "
                            "it lies inside the timed region and cannot start while the L2 flush is still running; the "

@@ -2,6 +2,7 @@
 // This translation unit is compiled with -fmad=false: every expression keeps
 // the reference's operation order with one rounding per operation, so the
 // results can be compared bit-for-bit with the strict CPU restatement.
+#include <cstring>
 #include "vn_kernels.cuh"
 
 struct Cov2x
@@ -456,25 +457,27 @@ __global__ void __launch_bounds__(EMIT_T, 1) k_down_emit_all(const __grid_consta
   }
 }
 
-// flag[i] = 1 when point i is the first point of its voxel
-__global__ void __launch_bounds__(256)
-    k_down_flag(int n, const DownSlot* __restrict__ tab, const int* __restrict__ slot_of, int* __restrict__ flag)
-{
-  vn_pdl_sync();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int s = slot_of[i];
-  flag[i] = (s >= 0 && tab[s].first == i) ? 1 : 0;
-}
-
-// three-kernel exclusive scan over int flags (n <= 1024*1024)
+// three-kernel exclusive scan over int flags (n <= 1024*1024); with `tab` the flags are formed here (k_down_flag's
+// job: flag[i] = 1 when point i is the first point of its voxel) and written to `flag_out` for the emission
 __global__ void __launch_bounds__(1024) k_scan_block(const int* __restrict__ in, int* __restrict__ out, int n,
-                                                     int* __restrict__ block_sums)
+                                                     int* __restrict__ block_sums, const DownSlot* __restrict__ tab,
+                                                     int* __restrict__ flag_out)
 {
   vn_pdl_sync();
   __shared__ int warp_sums[32];
   int i = blockIdx.x * 1024 + threadIdx.x;
-  int v = (i < n) ? in[i] : 0;
+  int v = 0;
+  if (i < n)
+  {
+    if (tab)
+    {
+      const int s = in[i];  // (`in` = slot_of)
+      v = (s >= 0 && tab[s].first == i) ? 1 : 0;
+      flag_out[i] = v;
+    }
+    else
+      v = in[i];
+  }
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int x = v;
   for (int o = 1; o < 32; o <<= 1)
@@ -545,7 +548,8 @@ __global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ block_sums
 // emit voxel means in first-point order and clean the table slot for the next scan
 __global__ void __launch_bounds__(256)
     k_down_emit(int n, DownSlot* __restrict__ tab, const int* __restrict__ slot_of, const int* __restrict__ flag,
-                const int* __restrict__ scan, const int* __restrict__ block_sums, float4* __restrict__ out)
+                const int* __restrict__ scan, const int* __restrict__ block_sums, float4* __restrict__ out, ScanView pv,
+                VarInitParams prm)
 {
   vn_pdl_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -554,7 +558,10 @@ __global__ void __launch_bounds__(256)
   int ord = scan[i] + block_sums[i >> 10];
   DownSlot& s = tab[slot_of[i]];
   double c = (double)s.cnt;
-  out[ord] = make_float4((float)(s.sum[0] / c), (float)(s.sum[1] / c), (float)(s.sum[2] / c), (float)s.cnt);
+  const float4 mean = make_float4((float)(s.sum[0] / c), (float)(s.sum[1] / c), (float)(s.sum[2] / c), (float)s.cnt);
+  out[ord] = mean;
+  // a3 on the emitted point right away (what k_var_init would do from the stored float4): one launch less per scan
+  if (pv.p[0]) var_init_point(mean, ord, pv, prm);
   s.key = VN_EMPTY_KEY;
   s.sum[0] = s.sum[1] = s.sum[2] = 0.0;
   s.cnt = 0;
@@ -929,15 +936,19 @@ void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots)
 }
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
                       int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status,
-                      unsigned long long* pub, unsigned long long seq)
+                      unsigned long long* pub, unsigned long long seq, const ScanView* pv, const VarInitParams* prm)
 {
   if (n <= 0) return 0;
   int nb = (n + 1023) / 1024;
   if (nb > 1024) return -1;
   vn_launch(k_down_accum, dim3((n + 255) / 256), dim3(256), 0, st, pts, n, voxel_size, tab, mask, slot_of, status);
-  vn_launch(k_down_flag, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag);
-  vn_launch(k_scan_block, dim3(nb), dim3(1024), 0, st, flag, scan, n, block_sums);
+  ScanView none;
+  memset(&none, 0, sizeof(none));
+  VarInitParams pz;
+  memset(&pz, 0, sizeof(pz));
+  vn_launch(k_scan_block, dim3(nb), dim3(1024), 0, st, slot_of, scan, n, block_sums, tab, flag);
   vn_launch(k_scan_sums, dim3(1), dim3(1024), 0, st, block_sums, nb, n_out_dev, pub, seq);
-  vn_launch(k_down_emit, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag, scan, block_sums, out);
-  return 5;
+  vn_launch(k_down_emit, dim3((n + 255) / 256), dim3(256), 0, st, n, tab, slot_of, flag, scan, block_sums, out, pv ? *pv : none,
+            prm ? *prm : pz);
+  return 4;
 }

@@ -684,11 +684,15 @@ extern "C" int vina_scan_download(vina_ctx* ctx, float* xyzt, int cap)
   return ctx->n_scan;
 }
 
+static VarInitParams var_init_params(const vina_ctx* ctx);
 static int run_downsample(vina_ctx* ctx, double size)
 {
+  // (the per-scan step lets the emission do the var_init of the emitted set as well: ctx->down_fuse_var_init)
+  const VarInitParams prm = var_init_params(ctx);
   int k = launch_downsample(ctx->stream, ctx->d_scan, ctx->n_scan, size, ctx->d_dtab, ctx->dmask, ctx->d_slot_of,
                             ctx->d_flag, ctx->d_scanbuf, ctx->d_block_sums, ctx->d_n_down, ctx->d_down, ctx->d_status,
-                            ctx->d_down_pub, ++ctx->down_seq);
+                            ctx->d_down_pub, ++ctx->down_seq, ctx->down_fuse_var_init ? &ctx->pv[1] : nullptr,
+                            ctx->down_fuse_var_init ? &prm : nullptr);
   if (k < 0) return vn_fail(ctx, VINA_E_CAPACITY, "scan too large for the down-sampling scan kernels");
   ctx->launches += k;
   ctx->n_down_pending = true;

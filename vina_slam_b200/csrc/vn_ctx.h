@@ -27,6 +27,7 @@ struct vina_ctx
   int* d_n_down = nullptr;
   int* h_n_down = nullptr;   // pinned
   // fused front (vn_front_fused): the count arrives through mapped memory, [0] sequence number, [1] count
+  bool down_fuse_var_init = false;      // run_downsample: k_down_emit also does var_init(1) (set around the per-scan step)
   bool front_fused = true;
   bool n_down_mapped = false;           // the pending count is the one k_down_emit_all publishes
   bool split_overlap = false;           // k_split on the side stream next to the marginalisation (launch_map_recut_margi)

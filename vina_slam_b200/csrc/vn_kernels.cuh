@@ -165,7 +165,8 @@ int launch_down_emit_all(cudaStream_t st, DownEmit& a, int sm_count);
 void launch_down_init(cudaStream_t st, DownSlot* tab, unsigned int nslots);
 int launch_downsample(cudaStream_t st, const float4* pts, int n, double voxel_size, DownSlot* tab, unsigned int mask,
                       int* slot_of, int* flag, int* scan, int* block_sums, int* n_out_dev, float4* out, int* status,
-                      unsigned long long* pub = nullptr, unsigned long long seq = 0);
+                      unsigned long long* pub = nullptr, unsigned long long seq = 0, const ScanView* pv = nullptr,
+                      const VarInitParams* prm = nullptr);
 
 // start-up phase (scan_kernels.cu): kd-tree IEKF association / sums, local-map append, motion_init's re-deskew
 struct InsertScratch;

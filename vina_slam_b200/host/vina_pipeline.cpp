@@ -169,7 +169,10 @@ static int imu_propagate(vina_ctx* ctx, OdomHost* o, const vina_imu* imus_in, in
   memcpy(vel_imu, xc.v, 24);
   memcpy(pos_imu, xc.p, 24);
   memcpy(R_imu, xc.R, 72);
-  std::vector<double> F(225), W(225), T1(225), T2(225), Ft(225);
+  // F is the identity plus five 3x3 blocks (imu_ekf.cpp:60-73): cov = F cov F^T + W is evaluated over F's non-zero
+  // entries only - the skipped terms are products with an exact 0.0, and the kept ones are added in the dense
+  // product's order (k ascending), so every non-zero result is the dense one bit for bit at a fifth of the work
+  double F[225], W[225], T1[225], T2[225];
   double dt = 0;
   for (size_t it = 0; it + 1 < imus.size(); it++)
   {
@@ -205,10 +208,10 @@ static int imu_propagate(vina_ctx* ctx, OdomHost* o, const vina_imu* imus_in, in
     hat3(acc_avr, acc_skew);
     Exp_dt(angvel_avr, dt, Exp_f);
     Exp_dt(angvel_avr, -dt, Exp_b);
-    std::fill(F.begin(), F.end(), 0.0);
-    std::fill(W.begin(), W.end(), 0.0);
+    std::fill(F, F + 225, 0.0);
+    std::fill(W, W + 225, 0.0);
     for (int i = 0; i < 15; i++) F[i + 15 * i] = 1.0;
-    auto setblk = [&](std::vector<double>& M, int r0, int c0, const double* B) {
+    auto setblk = [&](double* M, int r0, int c0, const double* B) {
       for (int j = 0; j < 3; j++)
         for (int i = 0; i < 3; i++) M[(r0 + i) + 15 * (c0 + j)] = B[i + 3 * j];
     };
@@ -236,10 +239,30 @@ static int imu_propagate(vina_ctx* ctx, OdomHost* o, const vina_imu* imus_in, in
     for (int k = 0; k < 3; k++) W[(9 + k) + 15 * (9 + k)] = cfg.rdw_gyr * dt * dt;
     for (int k = 0; k < 3; k++) W[(12 + k) + 15 * (12 + k)] = cfg.rdw_acc * dt * dt;
     // cov = F cov F^T + W
-    mat_mul(15, 15, 15, F.data(), xc.cov, T1.data());
-    for (int i = 0; i < 15; i++)
-      for (int j = 0; j < 15; j++) Ft[j + 15 * i] = F[i + 15 * j];
-    mat_mul(15, 15, 15, T1.data(), Ft.data(), T2.data());
+    {
+      int nz[15][15], nnz[15];
+      for (int i = 0; i < 15; i++)
+      {
+        nnz[i] = 0;
+        for (int k = 0; k < 15; k++)
+          if (F[i + 15 * k] != 0.0) nz[i][nnz[i]++] = k;
+      }
+      const double* P = xc.cov;
+      for (int j = 0; j < 15; j++)
+        for (int i = 0; i < 15; i++)
+        {
+          double s = F[i + 15 * nz[i][0]] * P[nz[i][0] + 15 * j];  // (every row holds its diagonal 1 or a rotation)
+          for (int a = 1; a < nnz[i]; a++) s = s + F[i + 15 * nz[i][a]] * P[nz[i][a] + 15 * j];
+          T1[i + 15 * j] = s;
+        }
+      for (int j = 0; j < 15; j++)  // (T1 F^T)(i, j) = sum_k T1(i, k) F(j, k)
+        for (int i = 0; i < 15; i++)
+        {
+          double s = T1[i + 15 * nz[j][0]] * F[j + 15 * nz[j][0]];
+          for (int a = 1; a < nnz[j]; a++) s = s + T1[i + 15 * nz[j][a]] * F[j + 15 * nz[j][a]];
+          T2[i + 15 * j] = s;
+        }
+    }
     for (int i = 0; i < 225; i++) xc.cov[i] = T2[i] + W[i];
 
     for (int k = 0; k < 3; k++) pos_imu[k] = (pos_imu[k] + vel_imu[k] * dt) + ((0.5 * acc_imu[k]) * dt) * dt;
@@ -783,15 +806,21 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
   if (r) return r;
   if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
   cudaStreamWaitEvent(B, ctx->ev_fork, 0);
+  // the map's point set on the side stream: down-sampling with the var_init of the emitted points in its last kernel.
+  // The host needs the count (and the "< 2000 points" retry, local_mapping.cpp:396-403): it arrives through mapped
+  // memory while the IEKF keeps running
   ctx->stream = B;
+  ctx->down_fuse_var_init = ctx->cfg.down_size >= 0.001;
   r = vina_downsample(ctx);
-  ctx->stream = A;
-  if (r) return r;
-  // the map's point set: the host needs the down-sampled count (and the "< 2000 points" retry,
-  // local_mapping.cpp:396-403) - a wait on the side stream only, the IEKF keeps running
-  ctx->stream = B;
-  r = vn_finish_downsample(ctx);
-  if (!r) r = vina_var_init(ctx, 1);
+  if (!r) r = vn_finish_downsample(ctx);
+  if (!r)
+  {
+    if (ctx->down_fuse_var_init)
+      ctx->n_pv[1] = ctx->n_down;
+    else
+      r = vina_var_init(ctx, 1);
+  }
+  ctx->down_fuse_var_init = false;
   ctx->stream = A;
   if (r) return r;
   if (tr) th[3] = now_us();
