@@ -74,6 +74,7 @@ struct vina_ctx
   bool iekf_loop = false;                    // vina_set_iekf_loop: the iteration loop as one persistent launch (k_iekf_loop)
   unsigned long long* d_loop_bar = nullptr;  // grid-barrier words of k_iekf_loop
   double* d_loop_partials = nullptr;         // [2][34][sm_count]
+  bool iterate_uploaded = false;             // iekf_upload_iterate ran ahead of iekf_stage (the overlapped step)
   bool iekf_looped = false;                  // the last enqueued loop went out as k_iekf_loop
   int loop_launches = 0;                     // profiling: launches of k_iekf_loop timed so far
   double* h_result = nullptr;  // pinned + mapped; the kernel's last block writes it

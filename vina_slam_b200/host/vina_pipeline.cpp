@@ -444,11 +444,22 @@ static void unstage_iterate(const IekfDev* h, vina_state& x, int* iters, int* no
 }
 
 // upload the iterate and reset the per-point leaf cache (ctx stream)
-static int iekf_stage(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
+// the iterate (x_curr after the IMU propagation, prior covariance, counters) to the device. The overlapped step does
+// this BEFORE the deskew kernel: the copy does not depend on it and no longer sits between the deskew and the first
+// IEKF launch
+static int iekf_upload_iterate(vina_ctx* ctx, OdomHost* o, int num_max_iter)
 {
   stage_iterate(o->x_curr, num_max_iter, ctx->h_iekf);
   int r = vn_check_cuda(ctx, cudaMemcpyAsync(ctx->d_iekf, ctx->h_iekf, sizeof(IekfDev), cudaMemcpyHostToDevice, ctx->stream),
                         "iterate upload");
+  if (!r) ctx->iterate_uploaded = true;
+  return r;
+}
+
+static int iekf_stage(vina_ctx* ctx, OdomHost* o, int which, int num_max_iter)
+{
+  int r = ctx->iterate_uploaded ? VINA_OK : iekf_upload_iterate(ctx, o, num_max_iter);
+  ctx->iterate_uploaded = false;
   if (r) return r;
   ctx->iekf_which = which;
   const int n = ctx->n_pv[which];
@@ -796,7 +807,9 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
     if (tr) cudaEventRecord(ctx->tr_ev[2], A);
     goto map_part;
   }
-  // deskew, var_init of the full scan and the leaf-cache reset are one kernel
+  // deskew, var_init of the full scan and the leaf-cache reset are one kernel (the iterate goes up first)
+  r = iekf_upload_iterate(ctx, o, num_max_iter);
+  if (r) return r;
   r = vn_deskew_var_init(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
   if (r) return r;
   r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
