@@ -1128,8 +1128,15 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       const int ns = nseg, tot = total;
       for (int g = t; g < tot; g += SPLIT_THREADS)
       {
-        int sgi = 0;
-        while (sgi + 1 < ns && segs[sgi + 1].start <= g) sgi++;
+        int sgi = 0, hi = ns - 1;  // last segment that starts at or before g
+        while (sgi < hi)
+        {
+          const int mid = (sgi + hi + 1) >> 1;
+          if (segs[mid].start <= g)
+            sgi = mid;
+          else
+            hi = mid - 1;
+        }
         const int cls = segs[sgi].cls;
         const PointRec* src = segs[sgi].src + (g - segs[sgi].start);
         double pw[3];
@@ -1204,9 +1211,28 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     double cv[SPLIT_PAIRS];  // pairs p = t + SPLIT_THREADS q < 360: child p / 45, entry p % 45
     for (int q = 0; q < SPLIT_PAIRS; q++) cv[q] = 0.0;
 
-    // pass 2: the row stream, 64 rows at a time
+    // pass 2: the row stream, 256 rows at a time. The row of the NEXT batch is fetched while this one is processed
+    // (a heavy leaf is twenty batches: one L2 round trip each on the block's critical path otherwise); the segment of a
+    // row by bisection (a leaf has up to ~50 segments: a linear walk per row and batch was ~1000 cycles)
     {
       const int ns = nseg, tot = total;
+      auto fetch_row = [&](int g, PointRec& out, int& out_cls) {
+        if (g >= tot) return;
+        int lo = 0, hi = ns - 1;
+        while (lo < hi)
+        {
+          const int mid = (lo + hi + 1) >> 1;
+          if (segs[mid].start <= g)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+        out_cls = segs[lo].cls;
+        out = segs[lo].src[g - segs[lo].start];
+      };
+      PointRec pr_next;
+      int cls_next = 0;
+      if (t < SPLIT_BATCH) fetch_row(t, pr_next, cls_next);
       for (int base = 0; base < tot; base += SPLIT_BATCH)
       {
         // phase 1 (rows in stream order): load, world position, child index
@@ -1216,12 +1242,11 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         if (t < SPLIT_BATCH)
         {
           const int g = base + t;
+          pr = pr_next;
+          cls = cls_next;
+          fetch_row(g + SPLIT_BATCH, pr_next, cls_next);
           if (g < tot)
           {
-            int sgi = 0;
-            while (sgi + 1 < ns && segs[sgi + 1].start <= g) sgi++;
-            cls = segs[sgi].cls;
-            pr = segs[sgi].src[g - segs[sgi].start];
             if (cls == 0)
             {
               pw[0] = pr.p[0];
