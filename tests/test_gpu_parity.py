@@ -941,6 +941,46 @@ def test_iekf_loop_kernel_matches_per_iteration_launches_and_the_oracle(oracle_l
         gx.close()
 
 
+def test_host_buffer_step_is_bitwise_the_resident_step(gpu_lib):
+    """vina_odom_step uploads the scan in two chunks on the copy stream and lets the fused deskew follow them
+    (vn_scan_upload_chunked; with vina_set_upload_ordered the copy starts behind the work already on the stream). Same
+    states and the same map, bit for bit, as vina_odom_step_resident on a scan that is already in HBM - pinned and
+    pageable host buffers, scans above and below the chunking threshold."""
+    import torch
+
+    for beams, steps in ((64, 700), (16, 400)):  # 44 800 points (two chunks) / 6 400 points (one)
+        cfg = small_cfg("robosense128", beams, steps)
+        seq = synth.Sequence(cfg)
+        caps = dict(SMALL_CAPS, max_scan_points=max(SMALL_CAPS.get("max_scan_points", 0), beams * steps + 64))
+        ctxs = [gpu_lib.Ctx(cfg, **caps) for _ in range(3)]
+        ctxs[1].set_upload_ordered(True)
+        for k in range(cfg.win_size):
+            sc = seq.next_scan(deskewed=True)
+            for gx in ctxs:
+                gx.bootstrap(sc.xyzt, gpu_lib.make_state(sc.gt_R, sc.gt_p, sc.gt_v, t=sc.end_time))
+        for gx in ctxs:
+            gx.set_imu_anchor(sc.end_time, sc.imu[-1])
+        for k in range(12):
+            sc = seq.next_scan()
+            pinned = torch.from_numpy(sc.xyzt).pin_memory()
+            dev = torch.from_numpy(sc.xyzt).cuda()
+            sa = gpu_lib.state_arrays(ctxs[0].step(sc.xyzt, sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+            sb = gpu_lib.state_arrays(ctxs[1].step(pinned.numpy(), sc.beg_time, sc.imu, iekf_on_full=True, max_iter=4))
+            end_time = sc.beg_time + float(sc.xyzt[-1, 3])
+            scx = gpu_lib.state_arrays(ctxs[2].step_resident(dev.data_ptr(), sc.xyzt.shape[0], sc.beg_time, end_time, sc.imu,
+                                                              True, 4))
+            for f in ("R", "p", "v", "bg", "ba", "cov"):
+                assert np.array_equal(sa[f], scx[f]) and np.array_equal(sb[f], scx[f]), (beams, k, f)
+            assert np.linalg.norm(sa["p"] - sc.gt_p) < 0.02
+        for gx in ctxs:
+            gx.sync()
+        ma, mb, mc = [sort_nodes(gx.map_export()) for gx in ctxs]
+        for f in ma.dtype.names:
+            assert np.array_equal(ma[f], mc[f]) and np.array_equal(mb[f], mc[f]), f
+        for gx in ctxs:
+            gx.close()
+
+
 def test_iekf_loop_schedule_small_scan_retry(oracle_lib, gpu_lib):
     """The fused front of the loop schedule publishes the down-sampled count through mapped memory; a scan that
     down-samples to < 2000 points must still take the "down_size / 2" retry of local_mapping.cpp:396-403 (separate
