@@ -2323,11 +2323,27 @@ int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView&
   return 1;
 }
 
+// early != nullptr: the node lists of the multi_recut that follows are collected on early->side right behind
+// k_insert_leaf (they only depend on the tree's structure, which is final once the leaves exist), next to the
+// accumulation of this insert; launch_map_recut(..., collected = true) then only waits for early->done
 int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                             const InsertScratch& sc, int win_ord)
+                             const InsertScratch& sc, int win_ord, const EarlyCollect* early)
 {
   if (n_host <= 0) return 0;
   vn_launch(k_insert_leaf, dim3(grid_for(n_host, 256)), dim3(256), 0, st, map, n_dev, n_host, sc);
+  int extra = 0;
+  if (early)
+  {
+    LayerLists& LL = *early->LL;
+    int* t = LL.count;  // this multi_recut's counters are the set the previous one cleared
+    LL.count = LL.count_alt;
+    LL.count_alt = t;
+    cudaEventRecord(early->fork, st);
+    cudaStreamWaitEvent(early->side, early->fork, 0);
+    vn_launch(k_recut_collect, dim3(592), dim3(128), 0, early->side, map, LL);
+    cudaEventRecord(early->done, early->side);
+    extra = 1;
+  }
   int tg = grid_for(n_host, 128);
   if (tg > 1184) tg = 1184;
   vn_launch(k_insert_alloc, dim3(tg), dim3(128), 0, st, map, sc);
@@ -2335,16 +2351,16 @@ int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView
   int ag = grid_for(n_host, ACC_WARPS);  // at most one warp per point's leaf
   if (ag > 148 * 16) ag = 148 * 16;
   vn_launch(k_insert_accum, dim3(ag), dim3(32 * ACC_WARPS), 0, st, map, scan, sc, win_ord);
-  return 4;
+  return 4 + extra;
 }
 
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                       InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
-                      const double* tsl_var, const IekfDev* live)
+                      const double* tsl_var, const IekfDev* live, const EarlyCollect* early)
 {
   if (n_host <= 0) return 0;
   int k = launch_map_insert_roots(st, map, scan, n_dev, n_host, sc, x, rot_var, tsl_var, 0, live);
-  return k + launch_map_insert_leaves(st, map, scan, n_dev, n_host, sc, win_ord);
+  return k + launch_map_insert_leaves(st, map, scan, n_dev, n_host, sc, win_ord, early);
 }
 
 static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)
@@ -2356,7 +2372,7 @@ static PoseBuf make_posebuf(const PoseD* xbuf, int win_count)
 }
 
 int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int win_count, const PoseD* h_xbuf,
-                     const IekfDev* live)
+                     const IekfDev* live, const EarlyCollect* collected)
 {
   const LivePose lv = { live, win_count - 1 };
   static bool attr_set[64] = { false };
@@ -2368,13 +2384,19 @@ int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int wi
     attr_set[dv & 63] = true;
   }
   PoseBuf b = make_posebuf(h_xbuf, win_count);
-  // this call's counters are the set the previous call cleared (both sets start out zero)
-  int* t = LL.count;
-  LL.count = LL.count_alt;
-  LL.count_alt = t;
-  vn_launch(k_recut_collect, dim3(592), dim3(128), 0, st, map, LL);
+  int launches = 1;
+  if (collected)
+    cudaStreamWaitEvent(st, collected->done, 0);  // (the lists were collected next to the insert's accumulation)
+  else
+  {
+    // this call's counters are the set the previous call cleared (both sets start out zero)
+    int* t = LL.count;
+    LL.count = LL.count_alt;
+    LL.count_alt = t;
+    vn_launch(k_recut_collect, dim3(592), dim3(128), 0, st, map, LL);
+    launches = 2;
+  }
   vn_launch(k_recut_all, dim3(296, map.max_layer + 1), dim3(128), 0, st, map, LL);
-  int launches = 2;
   // every subdivision of this multi_recut, all levels, through the kernel's work queue (two blocks per SM: all
   // 296 are resident; a block that finds the queue empty but work in flight polls)
   if (map.max_layer > 0)

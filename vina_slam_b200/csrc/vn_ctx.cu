@@ -199,6 +199,9 @@ extern "C" int vina_ctx_create(const vina_config* cfg_in, vina_ctx** out)
   ctx->trace = getenv("VINA_TRACE") != nullptr;
   if (ctx->trace)
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&ctx->tr_ev[i]));
+  CU(cudaEventCreateWithFlags(&ctx->ev_collect_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_collect_done, cudaEventDisableTiming));
+  if (const char* e = getenv("VINA_EARLY_COLLECT")) ctx->early_collect = atoi(e) != 0;
   CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU(dalloc(&ctx->d_status, 1));
@@ -1335,13 +1338,21 @@ int vn_map_insert_live(vina_ctx* ctx, int win_ord)
   const double z9[9] = { 0 };
   ctx->ins.stamp++;
   const int n = ctx->n_pv[1];
-  ctx->launches += launch_map_insert(ctx->stream, ctx->map, ctx->pv[1], nullptr, n, ctx->ins, win_ord, x, z9, z9, ctx->d_iekf);
+  // the node lists of the multi_recut that follows are collected on the side stream next to this insert's accumulation
+  // (VINA_EARLY_COLLECT=0: in stream order, as part of the recut)
+  EarlyCollect ec = { &ctx->layers, ctx->side_stream, ctx->ev_collect_fork, ctx->ev_collect_done };
+  const bool early = ctx->early_collect && !ctx->split_overlap && ctx->side_stream && n > 0;
+  ctx->launches += launch_map_insert(ctx->stream, ctx->map, ctx->pv[1], nullptr, n, ctx->ins, win_ord, x, z9, z9, ctx->d_iekf,
+                                     early ? &ec : nullptr);
+  ctx->collected_early = early;
   return VINA_OK;
 }
 int vn_map_recut_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)
 {
+  EarlyCollect ec = { &ctx->layers, ctx->side_stream, ctx->ev_collect_fork, ctx->ev_collect_done };
   ctx->launches += launch_map_recut(ctx->stream, ctx->map, ctx->layers, win_count, reinterpret_cast<const PoseD*>(x_buf),
-                                    ctx->d_iekf);
+                                    ctx->d_iekf, ctx->collected_early ? &ec : nullptr);
+  ctx->collected_early = false;
   return VINA_OK;
 }
 int vn_map_margi_live(vina_ctx* ctx, int win_count, const vina_pose* x_buf)

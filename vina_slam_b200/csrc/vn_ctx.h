@@ -99,6 +99,8 @@ struct vina_ctx
   cudaEvent_t ev_step_begin = nullptr;
   bool overlap = true;                 // vina_set_overlap: the per-scan step forks / hands the pose over on the device
   cudaStream_t side_stream = nullptr;  // down-sampling + var_init of the map's point set, concurrent with the IEKF
+  cudaEvent_t ev_collect_fork = nullptr, ev_collect_done = nullptr;  // k_recut_collect next to the insert's accumulation
+  bool early_collect = true, collected_early = false;
   cudaEvent_t ev_fork = nullptr;       // the deskewed scan is ready (compute stream -> side stream)
   cudaEvent_t ev_join = nullptr;       // the down-sampled pointVar set is ready (side stream -> compute stream)
   cudaEvent_t ev_poses = nullptr;  // the pose-table staging buffer has been consumed

@@ -213,9 +213,15 @@ struct InsertScratch
   int* idx;        // point indices grouped by leaf
   int stamp;       // scan stamp for distinct-root counting
 };
+struct EarlyCollect  // k_recut_collect of the following multi_recut on `side`, next to the insert's accumulation
+{
+  LayerLists* LL;
+  cudaStream_t side;
+  cudaEvent_t fork, done;
+};
 int launch_map_insert(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
                       InsertScratch& sc, int win_ord, const PoseD& x, const double* rot_var,
-                      const double* tsl_var, const IekfDev* live = nullptr);
+                      const double* tsl_var, const IekfDev* live = nullptr, const EarlyCollect* early = nullptr);
 // the two halves of an insert, for the sharded map: (1) key + root find/create on points whose world
 // position / covariance are already in sc.pw / sc.vw (pre != 0) or come from pvec_update; (2) the rest.
 // Between them the caller may overwrite sc.counters[0] (distinct roots) with the all-reduced count.
@@ -223,7 +229,7 @@ int launch_map_insert_roots(cudaStream_t st, const MapView& map, const ScanView&
                             InsertScratch& sc, const PoseD& x, const double* rot_var, const double* tsl_var,
                             int pre, const IekfDev* live = nullptr);
 int launch_map_insert_leaves(cudaStream_t st, const MapView& map, const ScanView& scan, const int* n_dev, int n_host,
-                             const InsertScratch& sc, int win_ord);
+                             const InsertScratch& sc, int win_ord, const EarlyCollect* early = nullptr);
 // shard_kernels.cu
 int launch_shard_route(cudaStream_t st, const ScanView& scan, int first, int count, const PoseD& x,
                        const double* rot_var, const double* tsl_var, double voxel_size, int world,
@@ -247,7 +253,7 @@ int launch_shard_unpack(cudaStream_t st, const double* rec, int n, const ScanVie
 // live != nullptr: the pose of frame win_count - 1 (and, for the insert, the posterior covariance blocks) are read
 // from the device iterate instead of the host arguments (the IEKF result need not have reached the host yet)
 int launch_map_recut(cudaStream_t st, const MapView& map, LayerLists& LL, int win_count, const PoseD* h_xbuf,
-                     const IekfDev* live = nullptr);
+                     const IekfDev* live = nullptr, const EarlyCollect* collected = nullptr);
 // margi + erase loop; the surviving roots land in slide_list[1 - map.slide_cur] (caller flips slide_cur)
 int launch_map_recut_margi(cudaStream_t st, cudaStream_t side, cudaEvent_t ev_fork, cudaEvent_t ev_join, const MapView& map,
                            LayerLists& LL, int win_count, const PoseD* h_xbuf, const IekfDev* live);
