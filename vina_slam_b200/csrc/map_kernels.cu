@@ -1049,6 +1049,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     NodeCold& c = M.cold[n];
     NodeHot& h = M.hot[n];
     const bool store = (h.layer + 1) < M.max_layer;
+    const int flags0 = h.flags;
     const double vc[3] = { h.vcenter[0], h.vcenter[1], h.vcenter[2] };
     const bool has_fix = c.pcr_fix.N != 0;
     __syncthreads();
@@ -1337,6 +1338,17 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
               vb[u] = val[r][9 + L.ck];
               rcs[u] = clsrow[r];
             }
+            if (rb + 8 <= r1 && rcs[0] == cur_cls && rcs[7] == cur_cls)
+            {
+              // eight rows of the class in progress (a child's rows come in class order): two straight-line add chains
+#pragma unroll
+              for (int u = 0; u < 8; u++)
+              {
+                clA = da(clA, va[u]);
+                clB = da(clB, vb[u]);
+              }
+              continue;
+            }
 #pragma unroll
             for (int u = 0; u < 8; u++)
             {
@@ -1349,8 +1361,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
                 {
                   NodeCold& kc = M.cold[kid[my_k]];
                   Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
-                  cluster_set(dst, L.ck, clB);
-                  if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
+                  cluster_set(dst, L.ck, clB);  // (the counts go in behind the loop: a read-modify-write here puts a
+                                                // global round trip per class on the chain)
                 }
                 cur_cls = rc;
                 clB = 0.0;
@@ -1393,19 +1405,30 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       NodeCold& kc = M.cold[kid[my_k]];
       Cluster& dst = cur_cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cur_cls - 1]];
       cluster_set(dst, L.ck, clB);
-      if (L.ck == 0) dst.N += cnt[cur_cls][my_k];
     }
     // children's pcr_add / cov_add
     if (chain && kid[my_k] >= 0)
     {
       NodeCold& kc = M.cold[kid[my_k]];
       cluster_set(kc.pcr_add, L.ck, clA);
-      if (L.ck == 0)
+    }
+    // the point counts of the clusters the chains filled: one thread per (class, child) and per child, all in flight
+    // together (PointCluster::push counts every point: N += 1 per row)
+    if (t >= 128 && t < 128 + 8 * (win_count + 1))  // (not thread 0: it has the parent's bookkeeping below)
+    {
+      const int k = (t - 128) & 7, cls = (t - 128) >> 3;
+      if (cnt[cls][k] > 0 && kid[k] >= 0)
       {
-        int tot = 0;
-        for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][my_k];
-        kc.pcr_add.N += tot;
+        NodeCold& kc = M.cold[kid[k]];
+        Cluster& dst = cls == 0 ? kc.pcr_fix : kc.pcrs_local[M.mp[cls - 1]];
+        dst.N += cnt[cls][k];
       }
+    }
+    else if (t >= 232 && t < 240 && kid[t - 232] >= 0)
+    {
+      int tot = 0;
+      for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][t - 232];
+      M.cold[kid[t - 232]].pcr_add.N += tot;
     }
 #pragma unroll
     for (int q = 0; q < SPLIT_PAIRS; q++)
@@ -1423,7 +1446,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
         c.fix_count = 0;
       }
       c.has_sw = 0;
-      h.flags = (h.flags | VN_FLAG_INTERIOR) & ~VN_FLAG_SPLIT_PENDING;  // (one store: a concurrent margi pass skips both states)
+      // (one store, from the value read when the leaf was claimed - nobody else writes this node's flags meanwhile: a
+      // concurrent margi pass skips both states, and thread 0 does not wait for a load here)
+      h.flags = (flags0 | VN_FLAG_INTERIOR) & ~VN_FLAG_SPLIT_PENDING;
     }
     else if (t >= 32 && t < 32 + M.win_size)
     {
@@ -1449,7 +1474,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     {
       KT();
 #ifdef VINA_SPLIT_TRACE
-      kt_[KT_PH - 1] = total;  // (rows of the leaf, shown as the last "stamp")
+      for (int z = kt_k; z < KT_PH - 1; z++) kt_[z] = 0;
+      kt_[KT_PH - 1] = total + 1000000ll * h.layer;  // (rows of the leaf + 10^6 x its layer, shown as the tag)
       kt_k = KT_PH;
 #endif
       KT_COMMIT(0);
@@ -1494,6 +1520,19 @@ void vn_split_trace_dump()
     fprintf(stderr, "\n  slowest unit (%lld cycles, tag %lld):", worst_t, h[w][worst][KT_PH - 1]);
     for (int i = 1; i < np && h[w][worst][i] != 0; i++) fprintf(stderr, " %lld", h[w][worst][i] - h[w][worst][i - 1]);
     fprintf(stderr, "\n");
+    if (w == 0)
+    {
+      // the last 40 units (the last scans): tag, total, phases
+      for (int s = cnt > 40 ? cnt - 40 : 0; s < cnt; s++)
+      {
+        int k = 0;
+        while (k < KT_PH - 1 && h[w][s][k] != 0) k++;
+        fprintf(stderr, "    unit %d tag %lld start %lld total %lld:", s, h[w][s][KT_PH - 1], h[w][s][0] % 100000000ll,
+                k > 1 ? h[w][s][k - 1] - h[w][s][0] : 0ll);
+        for (int i = 1; i < k; i++) fprintf(stderr, " %lld", h[w][s][i] - h[w][s][i - 1]);
+        fprintf(stderr, "\n");
+      }
+    }
   }
 }
 #endif
