@@ -785,6 +785,29 @@ __device__ bool recut_leaf(const MapView& M, NodeHot& h, NodeCold& c)
   return h.layer < M.max_layer;
 }
 
+// recut_leaf for a child k_split has just created, from what the block still holds: the child's pcr_add (shared
+// memory), its layer, "has points in the window" - no global read on the way to the eigen-solver, and the flags are a
+// plain store (a new node's flags are 0). Same arithmetic and decisions as recut_leaf.
+__device__ bool recut_child(const MapView& M, NodeHot& h, NodeCold& c, const Cluster& add, bool in_window, int layer)
+{
+  c.opt_state = -1;
+  if ((double)add.N <= M.min_point[layer]) return false;  // (flags stay 0: not a plane)
+  if (!in_window) return false;
+  double L[6], ev[3], Q[9];
+  cluster_cov(add, L);
+  eig3_sym(L, ev, Q);
+  for (int k = 0; k < 3; k++) c.eig_value[k] = ev[k];
+  for (int k = 0; k < 9; k++) c.eig_vector[k] = Q[k];
+  const bool is_plane = (ev[0] < M.min_eigen_value) && ((ev[0] / ev[2]) < M.thre[layer]);  // octree.cpp:198-201
+  if (is_plane)
+  {
+    h.flags = VN_FLAG_PLANE;
+    if (!(ev[0] / ev[1] > 0.12)) c.opt_state = 1;  // tras_opt: this leaf is a BA factor
+    return false;
+  }
+  return layer < M.max_layer;
+}
+
 // multi_recut, step 1: the nodes below the roots of surf_map_slide, listed per layer (layer 0 is the slide list
 // itself). EIGHT threads per root, one per first-level child; a thread walks that child's subtree through the
 // children mirrors of NodeHot (one 128-byte line per node, the loads of a level issued together). The trees are at
@@ -1028,6 +1051,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
   __shared__ int nseg, total, nfix, fixtot;
   __shared__ int wcnt_s[VINA_MAX_WIN], woff_s[VINA_MAX_WIN];
   __shared__ int s_item, s_index;
+  __shared__ double s_add[8][9];  // the children's pcr_add as the chains leave it (P lower triangle, v), for the judge
+  __shared__ int s_addN[8], s_made[8];
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   LaneRole L;
@@ -1048,7 +1073,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     KT_DECL;
     NodeCold& c = M.cold[n];
     NodeHot& h = M.hot[n];
-    const bool store = (h.layer + 1) < M.max_layer;
+    const int h_layer = h.layer;
+    const bool store = (h_layer + 1) < M.max_layer;
     const int flags0 = h.flags;
     const double vc[3] = { h.vcenter[0], h.vcenter[1], h.vcenter[2] };
     const bool has_fix = c.pcr_fix.N != 0;
@@ -1167,6 +1193,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       int id = -1;
       if (tot > 0)
       {
+        s_made[k] = c.children[k] < 0 ? 1 : 0;
         id = c.children[k] >= 0 ? c.children[k] : make_child(M, n, k);
         c.children[k] = id;
         if (id >= 0)
@@ -1411,6 +1438,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     {
       NodeCold& kc = M.cold[kid[my_k]];
       cluster_set(kc.pcr_add, L.ck, clA);
+      s_add[my_k][L.ck] = clA;
     }
     // the point counts of the clusters the chains filled: one thread per (class, child) and per child, all in flight
     // together (PointCluster::push counts every point: N += 1 per row)
@@ -1429,6 +1457,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
       int tot = 0;
       for (int cls = 0; cls <= win_count; cls++) tot += cnt[cls][t - 232];
       M.cold[kid[t - 232]].pcr_add.N += tot;
+      s_addN[t - 232] = tot;
     }
 #pragma unroll
     for (int q = 0; q < SPLIT_PAIRS; q++)
@@ -1462,13 +1491,26 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_split(MapView M, LayerLists L
     // complete (written by this block), nobody else knows them yet. A child that has to be subdivided itself
     // goes into the queue; every child joins its layer's node list for the multi_margi of this scan.
     __syncthreads();
+    const int child_layer = h_layer + 1;
     if (t < 8 && kid[t] >= 0)
     {
       NodeHot& kh = M.hot[kid[t]];
-      const int cl = kh.layer;
-      if (cl <= 3) LL.list[cl][atomicAdd(&LL.count[cl], 1)] = kid[t];
-      if (!(kh.flags & VN_FLAG_INTERIOR) && recut_leaf(M, kh, M.cold[kid[t]])) split_push(LL, kid[t]);
+      bool again;
+      if (s_made[t])
+      {
+        // a child this block created: everything the judge needs is still on chip
+        Cluster add;
+        for (int q = 0; q < 6; q++) add.P[q] = s_add[t][q];
+        for (int q = 0; q < 3; q++) add.v[q] = s_add[t][6 + q];
+        add.N = s_addN[t];
+        again = recut_child(M, kh, M.cold[kid[t]], add, s_addN[t] > cnt[0][t], child_layer);
+      }
+      else
+        again = !(kh.flags & VN_FLAG_INTERIOR) && recut_leaf(M, kh, M.cold[kid[t]]);
+      if (again) split_push(LL, kid[t]);
     }
+    else if (t >= 32 && t < 40 && kid[t - 32] >= 0 && child_layer <= 3)  // (next to the judge: the children join their layer's list)
+      LL.list[child_layer][atomicAdd(&LL.count[child_layer], 1)] = kid[t - 32];
     __syncthreads();
     if (t == 0)
     {
