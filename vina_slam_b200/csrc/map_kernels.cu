@@ -497,9 +497,23 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
     KT();
     const int leaf = sc.touched[j];
     NodeCold& c = M.cold[leaf];
+    // everything this leaf's pass needs from its records goes out NOW, together: these loads are independent once the
+    // leaf is known, and one L2 / DRAM round trip costs about as much as the whole accumulation of a small leaf
     const int cnt = c.pend_cnt;
+    const int poff = c.pend_off;
+    const int old_cnt = c.win_cnt[mord];
+    const int old_off = c.win_off[mord];
+    const int leaf_layer = M.hot[leaf].layer;
+    double cl = 0.0;
+    if (lane < 9)
+      cl = cluster_get(c.pcr_add, L.ck);
+    else if (lane < 18)
+      cl = cluster_get(c.pcrs_local[mord], L.ck);
+    double cv0 = c.cov_add[lane];
+    double cv1 = has2 ? c.cov_add[lane + 32] : 0.0;
+    const int n_add0 = c.pcr_add.N, n_loc0 = c.pcrs_local[mord].N;
     KT();
-    int* idx = sc.idx + c.pend_off;
+    int* idx = sc.idx + poff;
     // ascending point order
     if (cnt <= 32)
     {
@@ -542,8 +556,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
     }
     __syncwarp();
     KT();
-    const bool store = M.hot[leaf].layer < M.max_layer;
-    const int old_cnt = c.win_cnt[mord];
+    const bool store = leaf_layer < M.max_layer;
     int woff = 0;
     if (store)
     {
@@ -559,15 +572,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
         continue;
       }
       PointRec* pool = M.win_pool[mord];
-      for (int a = lane; a < old_cnt; a += 32) pool[woff + a] = pool[c.win_off[mord] + a];
+      for (int a = lane; a < old_cnt; a += 32) pool[woff + a] = pool[old_off + a];
     }
-    double cl = 0.0;
-    if (lane < 9)
-      cl = cluster_get(c.pcr_add, L.ck);
-    else if (lane < 18)
-      cl = cluster_get(c.pcrs_local[mord], L.ck);
-    double cv0 = c.cov_add[lane];
-    double cv1 = has2 ? c.cov_add[lane + 32] : 0.0;
     KT();
     for (int base = 0; base < cnt; base += 32)
     {
@@ -671,8 +677,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_insert_accum(MapView M, Scan
     if (has2) c.cov_add[lane + 32] = cv1;
     if (lane == 0)
     {
-      c.pcr_add.N += cnt;
-      c.pcrs_local[mord].N += cnt;
+      c.pcr_add.N = n_add0 + cnt;
+      c.pcrs_local[mord].N = n_loc0 + cnt;
       c.has_sw = 1;   // sw acquired (octree.cpp:154-164); recycled windows are empty
       c.isexist = 1;  // octree.cpp:165-166
       if (store)
