@@ -1971,12 +1971,15 @@ __global__ void __launch_bounds__(128, 4) k_margi_leaves(MapView M, LayerLists L
   // (the slide list the compaction fills after this kernel starts empty)
   if (mode != 2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) M.slide_count[1 - M.slide_cur] = 0;
   if (M.slide_count[M.slide_cur] + M.slide_others < M.thread_num) return;  // local_mapping.cpp:26-28
+  // (the deepest layer first: it holds most of the leaves, and the grid's rows are scheduled in order - 592 blocks are
+  // resident at a time)
+  const int layer = M.max_layer - (int)blockIdx.y;
   int nn;
-  const int* nodes = layer_nodes(M, LL, blockIdx.y, &nn);
+  const int* nodes = layer_nodes(M, LL, layer, &nn);
   int n_old = nn;  // layer 0 is the slide list: subdivisions add nothing to it
-  if (blockIdx.y > 0 && mode != 0)
+  if (layer > 0 && mode != 0)
   {
-    n_old = LL.snap[blockIdx.y];
+    n_old = LL.snap[layer];
     if (mode == 1) nn = n_old;  // (k_split may be appending behind it right now)
   }
   const int lane = threadIdx.x & 31;
