@@ -805,44 +805,46 @@ static int odom_step_overlapped(vina_ctx* ctx, OdomHost* o, double pcl_beg_time,
       ctx->n_pv[1] = ctx->n_down;
     if (tr) th[3] = now_us();
     if (tr) cudaEventRecord(ctx->tr_ev[2], A);
-    goto map_part;
   }
-  // deskew, var_init of the full scan and the leaf-cache reset are one kernel (the iterate goes up first)
-  r = iekf_upload_iterate(ctx, o, num_max_iter);
-  if (r) return r;
-  r = vn_deskew_var_init(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
-  if (r) return r;
-  r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
-  if (r) return r;
-  // the IEKF launches go out first: they are on the critical path, the side stream has slack
-  r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
-  if (r) return r;
-  if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
-  cudaStreamWaitEvent(B, ctx->ev_fork, 0);
-  // the map's point set on the side stream: down-sampling with the var_init of the emitted points in its last kernel.
-  // The host needs the count (and the "< 2000 points" retry, local_mapping.cpp:396-403): it arrives through mapped
-  // memory while the IEKF keeps running
-  ctx->stream = B;
-  ctx->down_fuse_var_init = ctx->cfg.down_size >= 0.001;
-  r = vina_downsample(ctx);
-  if (!r) r = vn_finish_downsample(ctx);
-  if (!r)
+  else
   {
-    if (ctx->down_fuse_var_init)
-      ctx->n_pv[1] = ctx->n_down;
-    else
-      r = vina_var_init(ctx, 1);
+    // the default schedule. Deskew, var_init of the full scan and the leaf-cache reset are one kernel (the iterate goes
+    // up first)
+    r = iekf_upload_iterate(ctx, o, num_max_iter);
+    if (r) return r;
+    r = vn_deskew_var_init(ctx, o->imu_poses.data(), (int)o->imu_poses.size(), o->x_curr.R, o->x_curr.p);
+    if (r) return r;
+    r = vn_check_cuda(ctx, cudaEventRecord(ctx->ev_fork, A), "fork");
+    if (r) return r;
+    // the IEKF launches go out first: they are on the critical path, the side stream has slack
+    r = iekf_enqueue_device(ctx, o, 0, num_max_iter);
+    if (r) return r;
+    if (tr) th[2] = now_us(), cudaEventRecord(ctx->tr_ev[1], A);
+    cudaStreamWaitEvent(B, ctx->ev_fork, 0);
+    // the map's point set on the side stream: down-sampling with the var_init of the emitted points in its last kernel.
+    // The host needs the count (and the "< 2000 points" retry, local_mapping.cpp:396-403): it arrives through mapped
+    // memory while the IEKF keeps running
+    ctx->stream = B;
+    ctx->down_fuse_var_init = ctx->cfg.down_size >= 0.001;
+    r = vina_downsample(ctx);
+    if (!r) r = vn_finish_downsample(ctx);
+    if (!r)
+    {
+      if (ctx->down_fuse_var_init)
+        ctx->n_pv[1] = ctx->n_down;
+      else
+        r = vina_var_init(ctx, 1);
+    }
+    ctx->down_fuse_var_init = false;
+    ctx->stream = A;
+    if (r) return r;
+    if (tr) th[3] = now_us();
+    cudaEventRecord(ctx->ev_join, B);
+    cudaStreamWaitEvent(A, ctx->ev_join, 0);
+    if (tr) cudaEventRecord(ctx->tr_ev[2], A);
+    r = vn_mark_scan_read(ctx);  // (covers the side stream's readers of the scan buffer as well)
+    if (r) return r;
   }
-  ctx->down_fuse_var_init = false;
-  ctx->stream = A;
-  if (r) return r;
-  if (tr) th[3] = now_us();
-  cudaEventRecord(ctx->ev_join, B);
-  cudaStreamWaitEvent(A, ctx->ev_join, 0);
-  if (tr) cudaEventRecord(ctx->tr_ev[2], A);
-  r = vn_mark_scan_read(ctx);  // (covers the side stream's readers of the scan buffer as well)
-  if (r) return r;
-map_part:
   if (o->if_BA)
   {
     // the LM loop of the BA needs the host between recut and margi: take the IEKF result first, then the map
